@@ -1,0 +1,404 @@
+"""Host-side mirror of the reference's public API for the sweep path.
+
+The reference's host language is Julia, which this image does not have; `julia/PTMCB200.jl` is the binding
+a maintainer adds.  This module restates the same *interface* in Python (same type names, argument
+meaning, defaults and error behaviour) so that tests read like the reference's own tests and so that
+bench.py has a reference-facing call (`ptmc_run`) to time end-to-end.  It contains host logic only
+(parameter structs, the ptmc_run! driver loop, histogram bounds, finalise_results); all per-move
+arithmetic happens in libptmc_b200.so.
+
+Reference: src/InputParams.jl, src/BoundaryConditions.jl, src/Configurations.jl, src/Ensembles.jl,
+src/EnergyEvaluation.jl (constructors only), src/MCRun.jl:282-432, src/Sampling.jl:141-223,377-399."""
+from __future__ import annotations
+
+import json
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi
+from .engine import Engine, RunnerParams, SweepConfig
+
+kB = 3.16681196e-6  # src/InputParams.jl:19
+DATA_DIR = abi.PKG_DIR / "data"
+
+
+# ------------------------------------------------------------------------------------ InputParams --
+@dataclass
+class MCParams:
+    """src/InputParams.jl:35-63"""
+    mc_cycles: int
+    n_traj: int
+    n_atoms: int
+    eq_percentage: float = 0.2
+    mc_sample: int = 1
+    n_adjust: int = 100
+    n_bin: int = 100
+    min_acc: float = 0.4
+    max_acc: float = 0.6
+
+    @property
+    def eq_cycles(self) -> int:
+        # round(Int, x): ties to even, like Python's round
+        return int(round(self.eq_percentage * self.mc_cycles))
+
+
+class TempGrid:
+    """src/InputParams.jl:77-93 (geometric default)"""
+
+    def __init__(self, ti: float, tf: float, n: int, tdistr: str = "geometric"):
+        if tdistr == "equally_spaced":
+            delta = (tf - ti) / (n - 1)
+            t = [ti + (i - 1) * delta for i in range(1, n + 1)]
+        elif tdistr == "geometric":
+            t = [ti * (tf / ti) ** ((i - 1) / (n - 1)) for i in range(1, n + 1)]
+        else:
+            raise ValueError(f"chosen temperature distribution {tdistr} does not exist")
+        self.t_grid = np.array(t, dtype=np.float64)
+        self.beta_grid = 1.0 / (kB * self.t_grid)
+
+    def __len__(self):
+        return len(self.t_grid)
+
+
+@dataclass
+class Output:
+    """src/InputParams.jl:114-134 (fields the sweep path fills)"""
+    n_bin: int
+    en_min: float = 0.0
+    en_max: float = 0.0
+    v_min: float = 0.0
+    v_max: float = 0.0
+    delta_en_hist: float = 0.0
+    delta_v_hist: float = 0.0
+    delta_r2: float = 0.0
+    max_displ: list = field(default_factory=list)
+    en_avg: np.ndarray | None = None
+    heat_cap: np.ndarray | None = None
+    en_histogram: np.ndarray | None = None   # [n_traj][n_bin+2]
+    ev_histogram: np.ndarray | None = None   # [n_traj][n_bin+2][n_bin+2]
+    count_stat_atom: np.ndarray | None = None
+    count_stat_exc: np.ndarray | None = None
+
+
+# ----------------------------------------------------------------------------- BoundaryConditions --
+@dataclass(frozen=True)
+class SphericalBC:
+    """src/BoundaryConditions.jl:44-47 (stores radius^2)"""
+    radius: float
+
+    @property
+    def radius2(self):
+        return self.radius * self.radius
+
+    kind = abi.BC_SPHERICAL
+
+    def box(self):
+        return (self.radius2, 0.0)
+
+
+@dataclass(frozen=True)
+class CubicBC:
+    """src/BoundaryConditions.jl:72-77"""
+    box_length: float
+    kind = abi.BC_CUBIC
+
+    def box(self):
+        return (self.box_length, self.box_length)
+
+
+@dataclass(frozen=True)
+class RhombicBC:
+    """src/BoundaryConditions.jl:110-115"""
+    box_length: float
+    box_height: float
+    kind = abi.BC_RHOMBIC
+
+    def box(self):
+        return (self.box_length, self.box_height)
+
+
+@dataclass(frozen=True)
+class RectangularBC:
+    """src/BoundaryConditions.jl:89-92"""
+    box_length: float
+    box_height: float
+    kind = abi.BC_RECTANGULAR
+
+    def box(self):
+        return (self.box_length, self.box_height)
+
+
+def get_volume(bc) -> float:
+    """src/Configurations.jl:246-256"""
+    if isinstance(bc, CubicBC):
+        return bc.box_length * bc.box_length * bc.box_length
+    if isinstance(bc, RhombicBC):
+        return bc.box_length * bc.box_length * bc.box_height * 3 ** 0.5 / 2
+    if isinstance(bc, RectangularBC):
+        return bc.box_length * bc.box_length * bc.box_height
+    raise TypeError("get_volume is defined for periodic boundary conditions only")
+
+
+class Config:
+    """src/Configurations.jl:42-58"""
+
+    def __init__(self, positions, boundary_condition):
+        self.positions = np.array(positions, dtype=np.float64).reshape(-1, 3)
+        self.boundary_condition = boundary_condition
+
+    def __len__(self):
+        return len(self.positions)
+
+
+# --------------------------------------------------------------------------------------- Ensembles --
+@dataclass(frozen=True)
+class NVT:
+    """src/Ensembles.jl:42-49"""
+    n_atoms: int
+    n_atom_moves: int | None = None
+    n_atom_swaps: int = 0
+    kind = abi.ENS_NVT
+
+    def atom_moves(self):
+        return self.n_atoms if self.n_atom_moves is None else self.n_atom_moves
+
+
+@dataclass(frozen=True)
+class NPT:
+    """src/Ensembles.jl:75-85 — NPT(n_atoms, pressure, separated_volume)"""
+    n_atoms: int
+    pressure: float
+    separated_volume: bool = False
+    n_atom_moves: int | None = None
+    n_volume_moves: int = 1
+    kind = abi.ENS_NPT
+
+    def atom_moves(self):
+        return self.n_atoms if self.n_atom_moves is None else self.n_atom_moves
+
+
+# -------------------------------------------------------------------------------------- potentials --
+@dataclass(frozen=True)
+class ELJPotential:
+    """src/EnergyEvaluation.jl:891-907: sum c_i r^-(5+i)"""
+    coeff: tuple
+    kind = abi.POT_ELJ
+
+
+@dataclass(frozen=True)
+class ELJPotentialEven:
+    """src/EnergyEvaluation.jl:138-154: sum c_i r^-(4+2i)"""
+    coeff: tuple
+    kind = abi.POT_ELJ_EVEN
+
+
+class EmbeddedAtomPotential:
+    """src/EnergyEvaluation.jl:1059-1073: EmbeddedAtomPotential(n, m, eps, C, a)"""
+    kind = abi.POT_EAM
+
+    def __init__(self, n, m, eps, Cc, a):
+        self.n, self.m = float(n), float(m)
+        self.ean = eps * a ** self.n / 2
+        self.eCam = eps * Cc * a ** (self.m / 2)
+
+
+class RuNNerPotential:
+    """src/EnergyEvaluation.jl:1182-1218 with RadialType2 / AngularType3 tables
+    (MachineLearningPotential/SymmFunc.jl:24-44,86-112) and NeuralNetworkPotential (ForwardPass.jl:23-45)."""
+    kind = abi.POT_RUNNER
+
+    def __init__(self, num_nodes, activation, params, radial, angular, boundary: float = 0.0):
+        # radial rows: (type, eta, r_cut, G_max, G_min); angular rows: (eta, lambda, zeta, r_cut, type, G_max, G_min)
+        radial = np.asarray(radial, dtype=np.float64).reshape(-1, 5)
+        angular = np.asarray(angular, dtype=np.float64).reshape(-1, 7)
+        self.r_cut = float(radial[0, 2])
+        self.boundary2 = float(boundary) * float(boundary)
+        self.params = RunnerParams(
+            rad_eta=radial[:, 1].copy(), rad_type=radial[:, 0].astype(np.int32),
+            rad_gmax_gmin=radial[:, 3:5].copy(),
+            ang_eta=angular[:, 0].copy(), ang_lambda=angular[:, 1].copy(), ang_zeta=angular[:, 2].copy(),
+            ang_type=angular[:, 4].astype(np.int32), ang_gmax_gmin=angular[:, 5:7].copy(),
+            r_cut=self.r_cut, boundary2=self.boundary2,
+            num_nodes=np.asarray(num_nodes, dtype=np.int32), activation=np.asarray(activation, dtype=np.int32),
+            params=np.asarray(params, dtype=np.float64))
+
+
+# ------------------------------------------------------------------------------- config building --
+def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, ensemble, *, n_ladders=1,
+                 seed=1234, device=0, rng_mode=abi.RNG_XOSHIRO, lanes_per_replica=0) -> SweepConfig:
+    cfgs = start_config if isinstance(start_config, (list, tuple)) else (start_config,)
+    bc = cfgs[0].boundary_condition
+    if isinstance(ensemble, NPT):
+        if isinstance(bc, SphericalBC):
+            raise ValueError("SphericalBC cannot be used in an NPT ensemble.")  # src/Ensembles.jl:189
+        if ensemble.separated_volume:
+            raise NotImplementedError("separated_volume moves are outside the B200 hot path (SURVEY §8f)")
+    kw = dict(n_ladders=n_ladders, n_traj=mc_params.n_traj, n_atoms=mc_params.n_atoms, betas=temp.beta_grid,
+              pot_kind=potential.kind, bc_kind=bc.kind, ensemble=ensemble.kind,
+              n_atom_moves=ensemble.atom_moves(), n_adjust=mc_params.n_adjust, mc_sample=mc_params.mc_sample,
+              n_bin=mc_params.n_bin, min_acc=mc_params.min_acc, max_acc=mc_params.max_acc, seed=seed,
+              device=device, rng_mode=rng_mode, lanes_per_replica=lanes_per_replica)
+    if isinstance(ensemble, NPT):
+        kw.update(n_volume_moves=ensemble.n_volume_moves, pressure=ensemble.pressure)
+    if potential.kind in (abi.POT_ELJ, abi.POT_ELJ_EVEN):
+        kw["coeff"] = tuple(potential.coeff)
+    elif potential.kind == abi.POT_EAM:
+        kw["eam"] = (potential.n, potential.m, potential.ean, potential.eCam)
+    else:
+        kw["runner"] = potential.params
+    return SweepConfig(**kw)
+
+
+def initial_arrays(mc_params: MCParams, start_config, n_ladders: int):
+    """initialisation (src/Initialization.jl:79-101): slot i starts from start_config[mod1(i, len)]."""
+    cfgs = start_config if isinstance(start_config, (list, tuple)) else (start_config,)
+    T, N = mc_params.n_traj, mc_params.n_atoms
+    pos = np.zeros((n_ladders, T, N, 3))
+    box = np.zeros((n_ladders, T, 2))
+    for i in range(T):
+        c = cfgs[i % len(cfgs)]
+        if len(c) != N:
+            raise ValueError("number of atoms and positions not the same - check starting config")
+        pos[:, i] = c.positions
+        box[:, i] = c.boundary_condition.box()
+    return pos, box
+
+
+def check_e_bounds(energy, ebounds):
+    """src/MCRun.jl:258-265 (note the elseif)"""
+    if energy < ebounds[0]:
+        ebounds[0] = energy
+    elif energy > ebounds[1]:
+        ebounds[1] = energy
+    return ebounds
+
+
+def histogram_bounds(mc_params: MCParams, en_tot_ladder: np.ndarray, bc):
+    """Second half of equilibration_cycle! (src/MCRun.jl:293-310) + initialise_histograms!
+    (src/Sampling.jl:141-223) for ONE ladder: returns (en_min, en_max, v_min, v_max)."""
+    ebounds = [100.0, -100.0]
+    for _ in range(mc_params.eq_cycles // 2 + 1, mc_params.eq_cycles + 1):
+        for e in en_tot_ladder:
+            ebounds = check_e_bounds(float(e), ebounds)
+    v_min = v_max = 0.0
+    if not isinstance(bc, SphericalBC):
+        v0 = get_volume(bc)
+        v_min, v_max = v0 * 0.8, v0 * 2.0
+    return ebounds[0], ebounds[1], v_min, v_max
+
+
+def finalise_results(mc_params: MCParams, betas, ham, counters, results: Output) -> Output:
+    """src/Sampling.jl:377-399 for one ladder (ham [n_traj][2], counters [n_traj][NCOUNT])."""
+    n_sample = mc_params.mc_cycles / mc_params.mc_sample
+    en_avg = ham[:, 0] / n_sample
+    en2_avg = ham[:, 1] / n_sample
+    results.en_avg = en_avg
+    results.heat_cap = (en2_avg - en_avg ** 2) * np.asarray(betas) ** 2
+    results.count_stat_atom = counters[:, abi.C_ATOM_TOT] / (mc_params.n_atoms * mc_params.mc_cycles)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        results.count_stat_exc = counters[:, abi.C_EXC_ACC] / counters[:, abi.C_EXC_ATT]
+    return results
+
+
+def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensemble, *, n_ladders: int = 1,
+             seed: int = 1234, device: int = 0, engine_cls=Engine, engine_kwargs=None, chunk: int = 100000,
+             shared_bounds: bool = False, lanes_per_replica: int = 0):
+    """ptmc_run! (src/MCRun.jl:363-432) for `n_ladders` independent ladders batched on one device.
+
+    Returns (states, results): `states` is the dict of `Engine.download_states()` (per ladder, per slot),
+    `results` a list of one `Output` per ladder.  With shared_bounds=True all ladders bin into the same
+    [en_min, en_max] (the min/max over every ladder) so that their histograms can be summed."""
+    cfg = sweep_config(mc_params, temp, start_config, potential, ensemble, n_ladders=n_ladders, seed=seed,
+                       device=device, lanes_per_replica=lanes_per_replica)
+    eng = engine_cls(cfg, **(engine_kwargs or {}))
+    cfgs = start_config if isinstance(start_config, (list, tuple)) else (start_config,)
+    bc0 = cfgs[0].boundary_condition
+    try:
+        pos, box = initial_arrays(mc_params, start_config, n_ladders)
+        eng.upload_states(pos, box)
+        eng.seed(seed)
+        # equilibration (src/MCRun.jl:282-313): MC for eq_cycles ÷ 2 cycles only, cycle index from 1
+        n_eq = mc_params.eq_cycles // 2
+        if n_eq > 0:
+            eng.run_cycles(1, n_eq, False)
+        en = eng.download_states(("en_tot",))["en_tot"]
+        bounds = np.array([histogram_bounds(mc_params, en[l], bc0) for l in range(n_ladders)])
+        if shared_bounds:
+            bounds[:, 0] = bounds[:, 0].min()
+            bounds[:, 1] = bounds[:, 1].max()
+        eng.reset_counters()
+        eng.set_hist_bounds(bounds[:, 0].copy(), bounds[:, 1].copy(), bounds[:, 2].copy(), bounds[:, 3].copy())
+        # main loop (src/MCRun.jl:397-421), chunked; nothing is read back between chunks
+        i = 1
+        while i <= mc_params.mc_cycles:
+            k = min(chunk, mc_params.mc_cycles - i + 1)
+            eng.run_cycles(i, k, True)
+            i += k
+        eng.sync()
+        states = eng.download_states()
+        hist = eng.download_hist()
+        results = []
+        for l in range(n_ladders):
+            r = Output(mc_params.n_bin, en_min=bounds[l, 0], en_max=bounds[l, 1], v_min=bounds[l, 2], v_max=bounds[l, 3])
+            r.delta_en_hist = (r.en_max - r.en_min) / (r.n_bin - 1)
+            if ensemble.kind == abi.ENS_NPT:
+                r.delta_v_hist = (r.v_max - r.v_min) / r.n_bin
+                r.ev_histogram = hist[l]
+            else:
+                r.en_histogram = hist[l]
+            r.max_displ = states["max_displ"][l]
+            finalise_results(mc_params, temp.beta_grid, states["ham"][l], states["counters"][l], r)
+            results.append(r)
+        return states, results
+    finally:
+        eng.close()
+
+
+# ------------------------------------------------------------------------- reference input decks --
+def _geom(name):
+    return np.array([[float(x) for x in row] for row in json.loads((DATA_DIR / f"{name}.json").read_text())])
+
+
+ELJ_NE_COEFF = (-10.5097942564988, 989.725135614556, -101383.865938807, 3918846.12841668,
+                -56234083.4334278, 288738837.441765)  # scripts/ne13.jl:39-47, ne55.jl:39-46, pbc216.jl:45-52
+
+
+def deck_ne13(n_traj=32, cycles=1000):
+    """examples/ne13.jl:24-70 (BASELINE C1: 32 temperatures)"""
+    a2b = 1.8897259886
+    pos = _geom("ne13") * a2b
+    start = Config(pos, SphericalBC(radius=5.32 * a2b))
+    return MCParams(cycles, n_traj, 13), TempGrid(4.0, 16.0, n_traj), start, ELJPotentialEven(ELJ_NE_COEFF), NVT(13)
+
+
+def deck_ne55(n_traj=24, cycles=1000):
+    """scripts/ne55.jl:12-133 (BASELINE C2; positions used as given)"""
+    a2b = 1.8897259886
+    start = Config(_geom("ne55"), SphericalBC(radius=14 * a2b))
+    return MCParams(cycles, n_traj, 55), TempGrid(6.0, 19.0, n_traj), start, ELJPotentialEven(ELJ_NE_COEFF), NVT(55)
+
+
+def cu55_geometry():
+    nmtobohr = 18.8973
+    return (0.36258 * nmtobohr) * _geom("ico55")  # scripts/cu55.jl:222-224
+
+
+def deck_cu55_eam(n_traj=28, cycles=1000):
+    """scripts/cu55.jl:14-53,222-234 (BASELINE C3)"""
+    evtohartree, nmtobohr, a2b = 0.0367493, 18.8973, 1.8897259886
+    pot = EmbeddedAtomPotential(8.482, 4.692, evtohartree * 0.0370, 27.561, 0.25 * nmtobohr)
+    start = Config(cu55_geometry(), SphericalBC(radius=14 * a2b))
+    return MCParams(cycles, n_traj, 55), TempGrid(400.0, 1200.0, n_traj), start, pot, NVT(55)
+
+
+def deck_pbc216(n_traj=16, cycles=100):
+    """scripts/pbc216.jl:14-70,517-529 (BASELINE C4; the LookupTable lines 62-63 are dropped)"""
+    a2b = 1.8897261259077824
+    fcc = _geom("ne216_fcc") * a2b * 0.85
+    hcp = _geom("ne216_hcp") * a2b * 0.85
+    bc = RhombicBC(18.79489824 * a2b * 0.85, 15.34597014 * a2b * 0.85)
+    ens = NPT(216, 50000000000 * 2.2937122783969076e-13 / (a2b * a2b * a2b), False)
+    return (MCParams(cycles, n_traj, 216), TempGrid(1600.0, 2100.0, n_traj), [Config(fcc, bc), Config(hcp, bc)],
+            ELJPotentialEven(ELJ_NE_COEFF), ens)

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Extract the *input data* (start geometries, NNP weights/scaling) that the reference's run scripts
+embed, into plain data files under paralleltemperingmontecarlo.jl_b200/data/.
+
+Only numbers are extracted (cluster coordinates, network weights); no reference code is copied.
+Run in the build container (needs /root/reference); outputs are committed.
+
+Sources (all under /root/reference):
+  examples/ne13.jl:40-54      Ne13 icosahedron (Angstrom)
+  scripts/ne55.jl:65-121      Ne55 (used as given)
+  scripts/cu55.jl:164-220     ico_55 unit icosahedron
+  scripts/pbc216.jl:79-515    fcc / hcp 216-atom lattices (Angstrom)
+  scripts/data/weights.029.data, scripts/data/scaling.data  (RuNNer Cu network)
+"""
+import json, re, shutil, sys
+from pathlib import Path
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent.parent / "paralleltemperingmontecarlo.jl_b200" / "data"
+
+ROW = re.compile(r"\[\s*([-+0-9.eE]+)\s*,\s*([-+0-9.eE]+)\s*,\s*([-+0-9.eE]+)\s*\]")
+
+
+def grab(path, name):
+    lines = (REF / path).read_text().splitlines()
+    start = next(i for i, l in enumerate(lines) if re.match(rf"\s*{name}\s*=\s*\[", l))
+    rows = []
+    for l in lines[start:]:
+        m = ROW.search(l)
+        if m:
+            rows.append([m.group(1), m.group(2), m.group(3)])
+        if l.strip().startswith("]") and rows:
+            break
+    return rows
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    geo = {
+        "ne13": grab("examples/ne13.jl", "pos_ne13"),
+        "ne55": grab("scripts/ne55.jl", "pos_ne55"),
+        "ico55": grab("scripts/cu55.jl", "ico_55"),
+        "ne216_fcc": grab("scripts/pbc216.jl", "pos_ne216_fcc"),
+        "ne216_hcp": grab("scripts/pbc216.jl", "pos_ne216_hcp"),
+    }
+    want = {"ne13": 13, "ne55": 55, "ico55": 55, "ne216_fcc": 216, "ne216_hcp": 216}
+    for k, rows in geo.items():
+        assert len(rows) == want[k], (k, len(rows))
+        # keep the decimal literals as strings -> float() parses them exactly as Julia does
+        (OUT / f"{k}.json").write_text(json.dumps(rows))
+    for f in ("weights.029.data", "scaling.data"):
+        shutil.copy(REF / "scripts" / "data" / f, OUT / f)
+    print("wrote", sorted(p.name for p in OUT.iterdir()))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
