@@ -32,6 +32,13 @@
 extern "C" {
 #endif
 
+/* Every entry point is exported explicitly; the library is built with -fvisibility=hidden. */
+#if defined(__GNUC__)
+#define PTMC_API __attribute__((visibility("default")))
+#else
+#define PTMC_API
+#endif
+
 #define PTMC_ABI_VERSION 1
 #define PTMC_MAX_COEFF 16
 #define PTMC_NCOUNT 10
@@ -119,15 +126,15 @@ typedef struct ptmc_config {
 typedef struct ptmc_handle ptmc_handle;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
-int ptmc_abi_version(void);
+PTMC_API int ptmc_abi_version(void);
 /* Text of the last error on this host thread (handle may be NULL for create-time errors). */
-const char* ptmc_last_error(const ptmc_handle* h);
+PTMC_API const char* ptmc_last_error(const ptmc_handle* h);
 /* Replaces `initialisation` (src/Initialization.jl:79-101) for the device side: allocates all
  * per-replica state for n_ladders x n_traj replicas. */
-int ptmc_create(const ptmc_config* cfg, ptmc_handle** out);
-void ptmc_destroy(ptmc_handle* h);
+PTMC_API int ptmc_create(const ptmc_config* cfg, ptmc_handle** out);
+PTMC_API void ptmc_destroy(ptmc_handle* h);
 /* Launch all work of this handle on an existing cudaStream_t (e.g. torch's current stream). */
-int ptmc_set_stream(ptmc_handle* h, void* cuda_stream);
+PTMC_API int ptmc_set_stream(ptmc_handle* h, void* cuda_stream);
 
 /* ---- state in ------------------------------------------------------------------------------------ */
 /* MCState constructor (src/MCStates.jl:137-162): uploads positions/box, recomputes on the device every
@@ -136,24 +143,24 @@ int ptmc_set_stream(ptmc_handle* h, void* cuda_stream);
  * :1735-1747, get_r_cut src/Ensembles.jl:118-125), sets max_boxlength = 1.8*box_length
  * (src/MCStates.jl:63-87).  max_displ may be NULL (=> 0.1 everywhere, src/MCStates.jl:104). Counters and
  * ham are zeroed. */
-int ptmc_upload_states(ptmc_handle* h, const double* pos, const double* box, const double* max_displ);
+PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, const double* box, const double* max_displ);
 /* Optional restart data (src/ReadSave.jl:436 rebuild_states): any pointer may be NULL. */
-int ptmc_upload_counters(ptmc_handle* h, const int64_t* counters, const double* ham);
+PTMC_API int ptmc_upload_counters(ptmc_handle* h, const int64_t* counters, const double* ham);
 /* reset_counters (src/MCRun.jl:270-276) on every replica. */
-int ptmc_reset_counters(ptmc_handle* h);
+PTMC_API int ptmc_reset_counters(ptmc_handle* h);
 
 /* ---- random streams ------------------------------------------------------------------------------ */
 /* Julia-compatible seeding: slot stream of (ladder l, slot i) = Random.seed!(seed + l*n_traj + i),
  * ladder ("driver task") stream of ladder l = Random.seed!(seed + n_ladders*n_traj + l). */
-int ptmc_seed(ptmc_handle* h, uint64_t seed);
+PTMC_API int ptmc_seed(ptmc_handle* h, uint64_t seed);
 /* Raw Xoshiro256++ states: slot_states [n_ladders][n_traj][4], ladder_states [n_ladders][4]. */
-int ptmc_set_rng_states(ptmc_handle* h, const uint64_t* slot_states, const uint64_t* ladder_states);
-int ptmc_get_rng_states(ptmc_handle* h, uint64_t* slot_states, uint64_t* ladder_states);
+PTMC_API int ptmc_set_rng_states(ptmc_handle* h, const uint64_t* slot_states, const uint64_t* ladder_states);
+PTMC_API int ptmc_get_rng_states(ptmc_handle* h, uint64_t* slot_states, uint64_t* ladder_states);
 /* Replay mode: pre-drawn raw UInt64 draws. slot_draws [n_ladders][n_traj][slot_len] is consumed by
  * mc_move! of that slot (rand(1:N), 3 uniforms (+3 per redraw), acceptance uniform: src/MCRun.jl:145,
  * src/MCMoves.jl:34-38,170, src/MCRun.jl:123); ladder_draws [n_ladders][ladder_len] by the exchange
  * gate / pair / uniform (src/MCRun.jl:203, src/Exchange.jl:135,145).  Cursors restart at 0. */
-int ptmc_set_replay(ptmc_handle* h, const uint64_t* slot_draws, int64_t slot_len,
+PTMC_API int ptmc_set_replay(ptmc_handle* h, const uint64_t* slot_draws, int64_t slot_len,
                     const uint64_t* ladder_draws, int64_t ladder_len);
 
 /* ---- histograms ---------------------------------------------------------------------------------- */
@@ -161,7 +168,7 @@ int ptmc_set_replay(ptmc_handle* h, const uint64_t* slot_draws, int64_t slot_len
  * zeroes the histograms.  With per_ladder = 0 the four pointers address one value used by every ladder,
  * otherwise arrays of n_ladders.  delta_en_hist = (en_max-en_min)/(n_bin-1), delta_v_hist =
  * (v_max-v_min)/n_bin are derived exactly as the reference does. */
-int ptmc_set_hist_bounds(ptmc_handle* h, const double* en_min, const double* en_max,
+PTMC_API int ptmc_set_hist_bounds(ptmc_handle* h, const double* en_min, const double* en_max,
                          const double* v_min, const double* v_max, int per_ladder);
 
 /* ---- the hot path -------------------------------------------------------------------------------- */
@@ -170,42 +177,46 @@ int ptmc_set_hist_bounds(ptmc_handle* h, const double* en_min, const double* en_
  * idx % mc_sample == 0).  sample = 0 gives the 7-argument (equilibration) method, sample = 1 the
  * 10-argument method with sampling_step! (src/Sampling.jl:330-371).  Asynchronous on the handle's
  * stream; errors raised inside the kernel surface at the next ptmc_sync / download. */
-int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64_t n_cycles, int sample);
+PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64_t n_cycles, int sample);
 /* Wait for the stream and report in-kernel errors (PTMC_ERR_SPHERE, PTMC_ERR_REPLAY). */
-int ptmc_sync(ptmc_handle* h);
+PTMC_API int ptmc_sync(ptmc_handle* h);
 
 /* ---- parity trace (test / replay mode) ----------------------------------------------------------- */
 /* Record per-move (index, new_en - en_tot, accepted) and per-cycle exchange (gate, n_exc, accepted) for
  * the next run_cycles calls; capacity in cycles.  capacity 0 disables tracing. */
-int ptmc_trace_enable(ptmc_handle* h, int64_t capacity_cycles);
+PTMC_API int ptmc_trace_enable(ptmc_handle* h, int64_t capacity_cycles);
 /* move_index [n_ladders][cycles][n_traj][n_steps] (1-based, > n_atoms = volume move),
  * delta_en same shape, accepted same shape (0/1); exchange [n_ladders][cycles][3] = {gate, n_exc, acc}.
  * Any pointer may be NULL.  *n_cycles_out = cycles recorded. */
-int ptmc_trace_download(ptmc_handle* h, int32_t* move_index, double* delta_en, uint8_t* accepted,
+PTMC_API int ptmc_trace_download(ptmc_handle* h, int32_t* move_index, double* delta_en, uint8_t* accepted,
                         int32_t* exchange, int64_t* n_cycles_out);
 
 /* ---- state out ----------------------------------------------------------------------------------- */
 /* Everything the reference's driver touches between cycles (checkpoint src/ReadSave.jl:178-218,
  * finalise_results src/Sampling.jl:377-399).  Any pointer may be NULL. Results are per *slot*. */
-int ptmc_download_states(ptmc_handle* h, double* pos, double* box, double* en_tot, double* max_displ,
+PTMC_API int ptmc_download_states(ptmc_handle* h, double* pos, double* box, double* en_tot, double* max_displ,
                          int64_t* counters, double* ham);
 /* en_hist [n_ladders][n_traj][n_bin+2] (NVT) / ev_hist [n_ladders][n_traj][n_bin+2][n_bin+2] (NPT,
  * E index slowest), as Float64 counts like Output.en_histogram (src/InputParams.jl:126-127).
  * With reduce_ladders != 0 the ladder axis is summed on the device first and the arrays lose it. */
-int ptmc_download_hist(ptmc_handle* h, double* en_hist, double* ev_hist, int reduce_ladders);
+PTMC_API int ptmc_download_hist(ptmc_handle* h, double* en_hist, double* ev_hist, int reduce_ladders);
 /* Device pointer + element count of the ladder-reduced histogram (uint64 counts) so that the host
  * plumbing (torch.distributed / NCCL all-reduce) can sum it across GPUs in place. */
-int ptmc_reduced_hist_dev(ptmc_handle* h, void** dev_ptr, int64_t* n_elems);
+PTMC_API int ptmc_reduced_hist_dev(ptmc_handle* h, void** dev_ptr, int64_t* n_elems);
 
 /* ---- introspection ------------------------------------------------------------------------------- */
 /* Number of kernel launches issued so far by this handle, and the lanes-per-replica actually used. */
-int64_t ptmc_launch_count(const ptmc_handle* h);
-int ptmc_lanes_per_replica(const ptmc_handle* h);
+PTMC_API int64_t ptmc_launch_count(const ptmc_handle* h);
+PTMC_API int ptmc_lanes_per_replica(const ptmc_handle* h);
+/* Measured FP64 FMA-pipe peak of `device` in TFLOP/s (independent DFMA chains on every SM, best of
+ * `iters` timed launches).  The sweep is bound by this pipe, not by HBM or the tensor cores, so bench.py
+ * uses it as the roofline denominator (MEASURED_PEAKS.json holds no FP64 figure). */
+PTMC_API int ptmc_fp64_peak(int device, int iters, double* tflops);
 
 /* ---- RuNNer forward pass: drop-in for librunnerjulia.so ------------------------------------------ */
 /* Exact ABI of the Fortran symbol the reference ccall()s (ForwardPass.jl:60-83): every argument by
  * reference, caller owns eatom.  Re-entrant. The Float64 return value is the last atom's energy. */
-double forward(const double* input, const int32_t* n_in, const int32_t* n_layers, const int32_t* nodes,
+PTMC_API double forward(const double* input, const int32_t* n_in, const int32_t* n_layers, const int32_t* nodes,
                const int32_t* batch, const int32_t* n_params, const double* params, const int32_t* act,
                double* eatom);
 

@@ -86,6 +86,7 @@ SYMBOLS = {
     "ptmc_reduced_hist_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
     "ptmc_launch_count": (C.c_int64, [_vp]),
     "ptmc_lanes_per_replica": (C.c_int, [_vp]),
+    "ptmc_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp]),
     "forward": (C.c_double, [_dp, _ip, _ip, _ip, _ip, _ip, _dp, _ip, _dp]),
 }
 

@@ -1,0 +1,512 @@
+// ptmc_api.cu — the C ABI of include/ptmc_b200.h: handle lifetime, state in/out, launches.
+// Host side only; all arithmetic of the sweep happens in sweep_kernel.cuh.  No CPU fallback anywhere:
+// every entry point either runs on the CUDA device of the handle or fails with PTMC_ERR_CUDA.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sweep_kernel.cuh"
+
+namespace ptmc {
+sweep_fn sweep_table_g4(int pot, int geom, int dbg);
+sweep_fn sweep_table_g8(int pot, int geom, int dbg);
+sweep_fn sweep_table_g16(int pot, int geom, int dbg);
+sweep_fn sweep_table_g32(int pot, int geom, int dbg);
+int sweep_max_threads(int G);
+void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
+void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
+double measure_fp64_peak(cudaStream_t st, int iters);
+struct RunnerState;
+}  // namespace ptmc
+
+using namespace ptmc;
+
+static thread_local std::string g_create_error;
+
+struct ptmc_handle {
+    ptmc_config cfg;
+    std::vector<double> betas;
+    DevParams P;
+    int device = 0;
+    int G = 0;
+    int threads = 0;
+    size_t smem = 0;
+    int geom = 0;
+    cudaStream_t stream = nullptr;   // nullptr = legacy default stream
+    i64 n_rep = 0, n_steps = 0;
+    size_t hist_per_ladder = 0;      // counters per ladder
+    // device buffers (owned)
+    std::vector<void*> owned;
+    u64* d_reduced = nullptr;
+    int* d_error = nullptr;
+    void* d_slot_draws = nullptr; void* d_ladder_draws = nullptr;
+    void* d_trace[4] = {nullptr, nullptr, nullptr, nullptr};
+    i64 trace_cap = 0, trace_n = 0;
+    bool uploaded = false, hist_ready = false, seeded = false;
+    i64 launches = 0;
+    std::string err;
+};
+
+// ------------------------------------------------------------------------------------------ helpers --
+static int fail(ptmc_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) return fail(h, PTMC_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+static int dev_alloc(ptmc_handle* h, T** p, size_t n) {
+    void* q = nullptr;
+    CU(h, cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    CU(h, cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+    h->owned.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+// SHA-256 of a short message: Julia's Random.seed!(n) hashes the seed's little-endian UInt32 words and
+// reads the digest back as four little-endian UInt64.
+static void sha256_block(const uint8_t* msg, size_t len, uint8_t out[32]) {
+    static const uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+        0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+        0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+        0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+        0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+        0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    auto rr = [](uint32_t x, int n) { return (x >> n) | (x << (32 - n)); };
+    uint8_t blk[64] = {0};
+    memcpy(blk, msg, len);
+    blk[len] = 0x80;
+    uint64_t bits = (uint64_t)len * 8;
+    for (int i = 0; i < 8; ++i) blk[63 - i] = (uint8_t)(bits >> (8 * i));
+    uint32_t w[64];
+    for (int i = 0; i < 16; ++i) w[i] = (uint32_t)blk[4 * i] << 24 | (uint32_t)blk[4 * i + 1] << 16 | (uint32_t)blk[4 * i + 2] << 8 | blk[4 * i + 3];
+    for (int i = 16; i < 64; ++i) {
+        uint32_t s0 = rr(w[i - 15], 7) ^ rr(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = rr(w[i - 2], 17) ^ rr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t H[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t v[8];
+    memcpy(v, H, sizeof v);
+    for (int i = 0; i < 64; ++i) {
+        uint32_t t1 = v[7] + (rr(v[4], 6) ^ rr(v[4], 11) ^ rr(v[4], 25)) + ((v[4] & v[5]) ^ (~v[4] & v[6])) + K[i] + w[i];
+        uint32_t t2 = (rr(v[0], 2) ^ rr(v[0], 13) ^ rr(v[0], 22)) + ((v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]));
+        v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = v[3] + t1; v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = t1 + t2;
+    }
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x = H[i] + v[i];
+        out[4 * i] = x >> 24; out[4 * i + 1] = x >> 16; out[4 * i + 2] = x >> 8; out[4 * i + 3] = x;
+    }
+}
+static void julia_seed(uint64_t seed, uint64_t s[4]) {
+    uint8_t msg[8], dig[32];
+    for (int i = 0; i < 8; ++i) msg[i] = (uint8_t)(seed >> (8 * i));
+    sha256_block(msg, (seed >> 32) ? 8 : 4, dig);
+    for (int k = 0; k < 4; ++k) {
+        uint64_t v = 0;
+        for (int i = 7; i >= 0; --i) v = (v << 8) | dig[8 * k + i];
+        s[k] = v;
+    }
+}
+
+static sweep_fn pick_kernel(const ptmc_handle* h, int dbg) {
+    switch (h->G) {
+        case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg);
+        case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg);
+        case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg);
+        default: return sweep_table_g32(h->cfg.pot_kind, h->geom, dbg);
+    }
+}
+
+// lanes per replica: enough lanes to keep the per-move serial chain short, few enough that the redundant
+// per-group scalar work (RNG, Metropolis) stays small and many replicas are resident.
+static int auto_lanes(int n_atoms, int n_traj) {
+    int g = n_atoms <= 20 ? 4 : (n_atoms <= 72 ? 8 : (n_atoms <= 144 ? 16 : 32));
+    while (g > 4 && ((n_traj * g + 31) / 32) * 32 > sweep_max_threads(g)) g /= 2;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------ lifetime --
+extern "C" PTMC_API int ptmc_abi_version(void) { return PTMC_ABI_VERSION; }
+
+extern "C" PTMC_API const char* ptmc_last_error(const ptmc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" PTMC_API void ptmc_destroy(ptmc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->d_slot_draws) cudaFree(h->d_slot_draws);
+    if (h->d_ladder_draws) cudaFree(h->d_ladder_draws);
+    for (void* p : h->d_trace) if (p) cudaFree(p);
+    delete h;
+}
+
+extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
+    if (!c || !out) return fail(nullptr, PTMC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (c->abi_version != PTMC_ABI_VERSION) return fail(nullptr, PTMC_ERR_ARG, "abi_version %d != %d", c->abi_version, PTMC_ABI_VERSION);
+    if (c->n_ladders < 1 || c->n_traj < 2 || c->n_atoms < 2) return fail(nullptr, PTMC_ERR_ARG, "need n_ladders >= 1, n_traj >= 2, n_atoms >= 2");
+    if (!c->betas) return fail(nullptr, PTMC_ERR_ARG, "betas is null");
+    if (c->n_atom_moves < 1 || c->n_atom_moves > c->n_atoms) return fail(nullptr, PTMC_ERR_ARG, "n_atom_moves must be in 1..n_atoms");
+    if (c->n_adjust < 1 || c->mc_sample < 1 || c->n_bin < 2) return fail(nullptr, PTMC_ERR_ARG, "n_adjust, mc_sample >= 1 and n_bin >= 2 required");
+    const bool npt = c->ensemble == PTMC_ENS_NPT;
+    const bool sphere = c->bc_kind == PTMC_BC_SPHERICAL;
+    if (c->ensemble != PTMC_ENS_NVT && !npt) return fail(nullptr, PTMC_ERR_ARG, "unknown ensemble %d", c->ensemble);
+    if (c->bc_kind < PTMC_BC_SPHERICAL || c->bc_kind > PTMC_BC_RECTANGULAR) return fail(nullptr, PTMC_ERR_ARG, "unknown boundary condition %d", c->bc_kind);
+    if (npt && sphere) return fail(nullptr, PTMC_ERR_ARG, "SphericalBC cannot be used in an NPT ensemble");   // src/Ensembles.jl:189
+    if (npt && c->n_volume_moves < 1) return fail(nullptr, PTMC_ERR_ARG, "NPT needs n_volume_moves >= 1");
+    switch (c->pot_kind) {
+        case PTMC_POT_ELJ: case PTMC_POT_ELJ_EVEN:
+            if (c->n_coeff < 1 || c->n_coeff > PTMC_MAX_COEFF) return fail(nullptr, PTMC_ERR_ARG, "n_coeff must be in 1..%d", PTMC_MAX_COEFF);
+            if (npt && c->pot_kind != PTMC_POT_ELJ_EVEN) return fail(nullptr, PTMC_ERR_ARG, "NPT long-range correction exists for ELJPotentialEven only (src/EnergyEvaluation.jl:968)");
+            break;
+        case PTMC_POT_EAM:
+            if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
+            break;
+        case PTMC_POT_RUNNER:
+            return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential sweep is not part of this build yet (forward() is)");
+        default: return fail(nullptr, PTMC_ERR_ARG, "unknown potential %d", c->pot_kind);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, PTMC_ERR_CUDA, "no CUDA device: libptmc_b200 has no CPU fallback");
+    if (c->device < 0 || c->device >= ndev) return fail(nullptr, PTMC_ERR_ARG, "device %d out of range (%d visible)", c->device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) return fail(nullptr, PTMC_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, PTMC_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", c->device, prop.major, prop.minor);
+
+    ptmc_handle* h = new ptmc_handle();
+    h->cfg = *c;
+    h->betas.assign(c->betas, c->betas + c->n_traj);
+    h->cfg.betas = h->betas.data();
+    h->cfg.runner = nullptr;
+    h->device = c->device;
+    h->geom = sphere ? GEOM_SPHERE : GEOM_PBC;
+    h->n_rep = c->n_ladders * c->n_traj;
+    h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0);
+    int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj);
+    if (G != 4 && G != 8 && G != 16 && G != 32) { delete h; return fail(nullptr, PTMC_ERR_ARG, "lanes_per_replica must be 0, 4, 8, 16 or 32"); }
+    h->G = G;
+    h->threads = ((c->n_traj * G + 31) / 32) * 32;
+    if (h->threads > sweep_max_threads(G)) { int mt = sweep_max_threads(G); delete h; return fail(nullptr, PTMC_ERR_ARG, "n_traj * lanes_per_replica = %d exceeds %d threads per ladder", c->n_traj * G, mt); }
+
+    auto bail = [&](int rc) { g_create_error = h->err; ptmc_destroy(h); return rc; };
+    if (cudaSetDevice(h->device) != cudaSuccess) return bail(fail(h, PTMC_ERR_CUDA, "cudaSetDevice failed"));
+
+    DevParams& P = h->P;
+    memset(&P, 0, sizeof P);
+    P.n_traj = c->n_traj; P.n_atoms = c->n_atoms; P.n_pad = ((c->n_atoms + G - 1) / G) * G;
+    P.n_atom_moves = c->n_atom_moves; P.n_volume_moves = npt ? c->n_volume_moves : 0; P.n_steps = (int)h->n_steps;
+    P.ensemble = c->ensemble; P.bc_kind = c->bc_kind; P.pot_kind = c->pot_kind; P.n_coeff = c->n_coeff;
+    P.n_adjust = c->n_adjust; P.mc_sample = c->mc_sample; P.n_bin = c->n_bin;
+    P.replay = c->rng_mode == PTMC_RNG_REPLAY;
+    P.min_acc = c->min_acc; P.max_acc = c->max_acc; P.pressure = c->pressure;
+    for (int i = 0; i < PTMC_MAX_COEFF; ++i) P.coeff[i] = i < c->n_coeff ? c->coeff[i] : 0.0;
+    P.eam_hn = c->eam_n / 2; P.eam_hm = c->eam_m / 2; P.eam_ean = c->eam_ean; P.eam_ecam = c->eam_ecam;
+
+    const SmemLayout lay = smem_layout(c->n_traj, P.n_pad, c->pot_kind);
+    h->smem = lay.bytes;
+    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
+
+    const size_t R = (size_t)h->n_rep, N = (size_t)c->n_atoms, L = (size_t)c->n_ladders;
+    const size_t nb2 = (size_t)c->n_bin + 2;
+    h->hist_per_ladder = (size_t)c->n_traj * (npt ? nb2 * nb2 : nb2);
+    double* d_betas = nullptr;
+    double *en_min, *en_max, *v_min, *v_max;
+    int rc = 0;
+    if ((rc = dev_alloc(h, &P.pos, R * N * 3)) || (rc = dev_alloc(h, &P.box, R * 2)) || (rc = dev_alloc(h, &P.en_tot, R)) ||
+        (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
+        (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
+        (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||
+        (rc = dev_alloc(h, &P.slot_cursor, R)) || (rc = dev_alloc(h, &P.ladder_cursor, L)) ||
+        (rc = dev_alloc(h, &en_min, L)) || (rc = dev_alloc(h, &en_max, L)) || (rc = dev_alloc(h, &v_min, L)) || (rc = dev_alloc(h, &v_max, L)) ||
+        (rc = dev_alloc(h, &P.hist, L * h->hist_per_ladder)) || (rc = dev_alloc(h, &h->d_reduced, h->hist_per_ladder)) ||
+        (rc = dev_alloc(h, &h->d_error, 1)))
+        return bail(rc);
+    P.betas = d_betas; P.en_min = en_min; P.en_max = en_max; P.v_min = v_min; P.v_max = v_max;
+    P.error = h->d_error;
+    if (cudaMemcpy(d_betas, h->betas.data(), sizeof(double) * c->n_traj, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(h, PTMC_ERR_CUDA, "copying betas failed"));
+    // opt in to large dynamic shared memory for both builds of the kernel
+    for (int dbg = 0; dbg < 2; ++dbg) {
+        sweep_fn f = pick_kernel(h, dbg);
+        if (!f) return bail(fail(h, PTMC_ERR_ARG, "no kernel for potential %d / boundary %d", c->pot_kind, c->bc_kind));
+        if (cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess)
+            return bail(fail(h, PTMC_ERR_CUDA, "cudaFuncSetAttribute(%zu B smem) failed: %s", h->smem, cudaGetErrorString(cudaGetLastError())));
+    }
+    *out = h;
+    if (c->rng_mode == PTMC_RNG_XOSHIRO) { int r2 = ptmc_seed(h, c->seed); if (r2) { *out = nullptr; return bail(r2); } }
+    return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_set_stream(ptmc_handle* h, void* cuda_stream) {
+    if (!h) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return PTMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ state in --
+extern "C" PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, const double* box, const double* max_displ) {
+    if (!h || !pos || !box) return h ? fail(h, PTMC_ERR_ARG, "pos and box are required") : PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const size_t R = (size_t)h->n_rep, N = (size_t)h->cfg.n_atoms;
+    const DevParams& P = h->P;
+    CU(h, cudaMemcpyAsync(P.pos, pos, sizeof(double) * R * N * 3, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(P.box, box, sizeof(double) * R * 2, cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> md(R * 4), mb(R);
+    for (size_t r = 0; r < R; ++r) {
+        for (int k = 0; k < 4; ++k) md[4 * r + k] = max_displ ? max_displ[4 * r + k] : 0.1;             // src/MCStates.jl:104
+        mb[r] = h->cfg.bc_kind == PTMC_BC_SPHERICAL ? 30.0 : box[2 * r] * 1.8;                          // src/MCStates.jl:63-75
+    }
+    CU(h, cudaMemcpyAsync(P.max_displ, md.data(), sizeof(double) * R * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(P.max_boxlength, mb.data(), sizeof(double) * R, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(P.counters, 0, sizeof(i64) * R * PTMC_NCOUNT, h->stream));
+    CU(h, cudaMemsetAsync(P.ham, 0, sizeof(double) * R * 2, h->stream));
+    CU(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
+    launch_init(P, h->n_rep, h->stream);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));   // md/mb are stack-owned
+    h->uploaded = true;
+    return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_upload_counters(ptmc_handle* h, const int64_t* counters, const double* ham) {
+    if (!h) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const size_t R = (size_t)h->n_rep;
+    if (counters) CU(h, cudaMemcpyAsync(h->P.counters, counters, sizeof(i64) * R * PTMC_NCOUNT, cudaMemcpyHostToDevice, h->stream));
+    if (ham) CU(h, cudaMemcpyAsync(h->P.ham, ham, sizeof(double) * R * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_reset_counters(ptmc_handle* h) {
+    if (!h) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemsetAsync(h->P.counters, 0, sizeof(i64) * (size_t)h->n_rep * PTMC_NCOUNT, h->stream));
+    return PTMC_OK;
+}
+
+// ------------------------------------------------------------------------------------ random streams --
+extern "C" PTMC_API int ptmc_set_rng_states(ptmc_handle* h, const uint64_t* slot_states, const uint64_t* ladder_states) {
+    if (!h || !slot_states || !ladder_states) return h ? fail(h, PTMC_ERR_ARG, "null rng states") : PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpyAsync(h->P.slot_rng, slot_states, sizeof(u64) * (size_t)h->n_rep * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->P.ladder_rng, ladder_states, sizeof(u64) * (size_t)h->cfg.n_ladders * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->seeded = true;
+    return PTMC_OK;
+}
+extern "C" PTMC_API int ptmc_get_rng_states(ptmc_handle* h, uint64_t* slot_states, uint64_t* ladder_states) {
+    if (!h) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (slot_states) CU(h, cudaMemcpyAsync(slot_states, h->P.slot_rng, sizeof(u64) * (size_t)h->n_rep * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (ladder_states) CU(h, cudaMemcpyAsync(ladder_states, h->P.ladder_rng, sizeof(u64) * (size_t)h->cfg.n_ladders * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PTMC_OK;
+}
+extern "C" PTMC_API int ptmc_seed(ptmc_handle* h, uint64_t seed) {
+    if (!h) return PTMC_ERR_ARG;
+    const size_t R = (size_t)h->n_rep, L = (size_t)h->cfg.n_ladders;
+    std::vector<uint64_t> s(R * 4), l(L * 4);
+    for (size_t r = 0; r < R; ++r) julia_seed(seed + r, &s[4 * r]);
+    for (size_t k = 0; k < L; ++k) julia_seed(seed + R + k, &l[4 * k]);
+    return ptmc_set_rng_states(h, s.data(), l.data());
+}
+extern "C" PTMC_API int ptmc_set_replay(ptmc_handle* h, const uint64_t* slot_draws, int64_t slot_len, const uint64_t* ladder_draws, int64_t ladder_len) {
+    if (!h || !slot_draws || !ladder_draws || slot_len < 0 || ladder_len < 0) return h ? fail(h, PTMC_ERR_ARG, "bad replay streams") : PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->d_slot_draws) { cudaFree(h->d_slot_draws); h->d_slot_draws = nullptr; }
+    if (h->d_ladder_draws) { cudaFree(h->d_ladder_draws); h->d_ladder_draws = nullptr; }
+    const size_t ns = (size_t)h->n_rep * slot_len, nl = (size_t)h->cfg.n_ladders * ladder_len;
+    CU(h, cudaMalloc(&h->d_slot_draws, std::max<size_t>(ns, 1) * sizeof(u64)));
+    CU(h, cudaMalloc(&h->d_ladder_draws, std::max<size_t>(nl, 1) * sizeof(u64)));
+    CU(h, cudaMemcpy(h->d_slot_draws, slot_draws, ns * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->d_ladder_draws, ladder_draws, nl * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(h, cudaMemset(h->P.slot_cursor, 0, sizeof(i64) * (size_t)h->n_rep));
+    CU(h, cudaMemset(h->P.ladder_cursor, 0, sizeof(i64) * (size_t)h->cfg.n_ladders));
+    h->P.slot_draws = static_cast<const u64*>(h->d_slot_draws); h->P.slot_len = slot_len;
+    h->P.ladder_draws = static_cast<const u64*>(h->d_ladder_draws); h->P.ladder_len = ladder_len;
+    h->P.replay = 1;
+    h->seeded = true;
+    return PTMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------- histograms --
+extern "C" PTMC_API int ptmc_set_hist_bounds(ptmc_handle* h, const double* en_min, const double* en_max, const double* v_min, const double* v_max, int per_ladder) {
+    if (!h || !en_min || !en_max) return h ? fail(h, PTMC_ERR_ARG, "en_min/en_max required") : PTMC_ERR_ARG;
+    const bool npt = h->cfg.ensemble == PTMC_ENS_NPT;
+    if (npt && (!v_min || !v_max)) return fail(h, PTMC_ERR_ARG, "NPT needs v_min/v_max");
+    CU(h, cudaSetDevice(h->device));
+    const size_t L = (size_t)h->cfg.n_ladders;
+    std::vector<double> a(L), b(L), c(L, 0.0), d(L, 0.0);
+    for (size_t l = 0; l < L; ++l) {
+        size_t k = per_ladder ? l : 0;
+        a[l] = en_min[k]; b[l] = en_max[k];
+        if (v_min) c[l] = v_min[k];
+        if (v_max) d[l] = v_max[k];
+    }
+    CU(h, cudaMemcpyAsync(const_cast<double*>(h->P.en_min), a.data(), sizeof(double) * L, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(const_cast<double*>(h->P.en_max), b.data(), sizeof(double) * L, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(const_cast<double*>(h->P.v_min), c.data(), sizeof(double) * L, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(const_cast<double*>(h->P.v_max), d.data(), sizeof(double) * L, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->P.hist, 0, sizeof(u64) * L * h->hist_per_ladder, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->hist_ready = true;
+    return PTMC_OK;
+}
+
+// -------------------------------------------------------------------------------------- the hot path --
+extern "C" PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64_t n_cycles, int sample) {
+    if (!h) return PTMC_ERR_ARG;
+    if (!h->uploaded) return fail(h, PTMC_ERR_STATE, "ptmc_run_cycles before ptmc_upload_states");
+    if (!h->seeded) return fail(h, PTMC_ERR_STATE, "no random stream: call ptmc_seed / ptmc_set_rng_states / ptmc_set_replay");
+    if (sample && !h->hist_ready) return fail(h, PTMC_ERR_STATE, "sampling before ptmc_set_hist_bounds");
+    if (n_cycles < 0 || first_idx < 0) return fail(h, PTMC_ERR_ARG, "negative cycle count / index");
+    const bool tracing = h->trace_cap > 0;
+    if (tracing && h->trace_n + n_cycles > h->trace_cap) return fail(h, PTMC_ERR_ARG, "trace capacity %lld exceeded", (long long)h->trace_cap);
+    CU(h, cudaSetDevice(h->device));
+    const int dbg = (tracing || h->P.replay) ? 1 : 0;
+    sweep_fn f = pick_kernel(h, dbg);
+    // per-launch acceptance counters are 32-bit: keep moves per launch below 2^31
+    const i64 max_chunk = std::max<i64>(1, (i64)0x7fffffff / std::max<i64>(1, h->n_steps));
+    i64 done = 0;
+    while (done < n_cycles) {
+        const i64 k = std::min(max_chunk, n_cycles - done);
+        DevParams P = h->P;
+        P.trace_cap = h->trace_cap; P.trace_base = h->trace_n;
+        P.tr_index = static_cast<int32_t*>(h->d_trace[0]); P.tr_de = static_cast<double*>(h->d_trace[1]);
+        P.tr_acc = static_cast<uint8_t*>(h->d_trace[2]); P.tr_exc = static_cast<int32_t*>(h->d_trace[3]);
+        f<<<(unsigned)h->cfg.n_ladders, h->threads, h->smem, h->stream>>>(P, first_idx + done, k, sample);
+        CU(h, cudaGetLastError());
+        h->launches += 1;
+        if (tracing) h->trace_n += k;
+        done += k;
+    }
+    return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_sync(ptmc_handle* h) {
+    if (!h) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    int e = 0;
+    CU(h, cudaMemcpy(&e, h->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e == PTMC_ERR_SPHERE) return fail(h, e, "Error: too many moves out of binding sphere");   // src/MCMoves.jl:132
+    if (e == PTMC_ERR_REPLAY) return fail(h, e, "replay stream exhausted");
+    if (e) return fail(h, e, "device error %d", e);
+    return PTMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------- trace --
+extern "C" PTMC_API int ptmc_trace_enable(ptmc_handle* h, int64_t capacity_cycles) {
+    if (!h || capacity_cycles < 0) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (void*& p : h->d_trace) { if (p) cudaFree(p); p = nullptr; }
+    h->trace_cap = capacity_cycles; h->trace_n = 0;
+    if (capacity_cycles > 0) {
+        const size_t m = (size_t)h->cfg.n_ladders * capacity_cycles * h->cfg.n_traj * h->n_steps;
+        CU(h, cudaMalloc(&h->d_trace[0], m * sizeof(int32_t)));
+        CU(h, cudaMalloc(&h->d_trace[1], m * sizeof(double)));
+        CU(h, cudaMalloc(&h->d_trace[2], m));
+        CU(h, cudaMalloc(&h->d_trace[3], (size_t)h->cfg.n_ladders * capacity_cycles * 3 * sizeof(int32_t)));
+        CU(h, cudaMemset(h->d_trace[0], 0, m * sizeof(int32_t)));
+        CU(h, cudaMemset(h->d_trace[1], 0, m * sizeof(double)));
+        CU(h, cudaMemset(h->d_trace[2], 0, m));
+        CU(h, cudaMemset(h->d_trace[3], 0, (size_t)h->cfg.n_ladders * capacity_cycles * 3 * sizeof(int32_t)));
+    }
+    return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_trace_download(ptmc_handle* h, int32_t* move_index, double* delta_en, uint8_t* accepted, int32_t* exchange, int64_t* n_cycles_out) {
+    if (!h) return PTMC_ERR_ARG;
+    TRY(ptmc_sync(h));
+    const size_t L = (size_t)h->cfg.n_ladders, per = (size_t)h->cfg.n_traj * h->n_steps;
+    const size_t cap = (size_t)h->trace_cap, k = (size_t)h->trace_n;
+    if (k > 0) {
+        // compact [L][cap][...] -> [L][k][...]
+        if (move_index) CU(h, cudaMemcpy2D(move_index, k * per * 4, h->d_trace[0], cap * per * 4, k * per * 4, L, cudaMemcpyDeviceToHost));
+        if (delta_en) CU(h, cudaMemcpy2D(delta_en, k * per * 8, h->d_trace[1], cap * per * 8, k * per * 8, L, cudaMemcpyDeviceToHost));
+        if (accepted) CU(h, cudaMemcpy2D(accepted, k * per, h->d_trace[2], cap * per, k * per, L, cudaMemcpyDeviceToHost));
+        if (exchange) CU(h, cudaMemcpy2D(exchange, k * 12, h->d_trace[3], cap * 12, k * 12, L, cudaMemcpyDeviceToHost));
+    }
+    if (n_cycles_out) *n_cycles_out = (int64_t)k;
+    return PTMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------- state out --
+extern "C" PTMC_API int ptmc_download_states(ptmc_handle* h, double* pos, double* box, double* en_tot, double* max_displ, int64_t* counters, double* ham) {
+    if (!h) return PTMC_ERR_ARG;
+    TRY(ptmc_sync(h));
+    const size_t R = (size_t)h->n_rep, N = (size_t)h->cfg.n_atoms;
+    const DevParams& P = h->P;
+    if (pos) CU(h, cudaMemcpy(pos, P.pos, sizeof(double) * R * N * 3, cudaMemcpyDeviceToHost));
+    if (box) CU(h, cudaMemcpy(box, P.box, sizeof(double) * R * 2, cudaMemcpyDeviceToHost));
+    if (en_tot) CU(h, cudaMemcpy(en_tot, P.en_tot, sizeof(double) * R, cudaMemcpyDeviceToHost));
+    if (max_displ) CU(h, cudaMemcpy(max_displ, P.max_displ, sizeof(double) * R * 4, cudaMemcpyDeviceToHost));
+    if (counters) CU(h, cudaMemcpy(counters, P.counters, sizeof(i64) * R * PTMC_NCOUNT, cudaMemcpyDeviceToHost));
+    if (ham) CU(h, cudaMemcpy(ham, P.ham, sizeof(double) * R * 2, cudaMemcpyDeviceToHost));
+    return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_reduced_hist_dev(ptmc_handle* h, void** dev_ptr, int64_t* n_elems) {
+    if (!h) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    launch_reduce_hist(h->P.hist, h->d_reduced, h->cfg.n_ladders, (i64)h->hist_per_ladder, h->stream);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (dev_ptr) *dev_ptr = h->d_reduced;
+    if (n_elems) *n_elems = (int64_t)h->hist_per_ladder;
+    return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_download_hist(ptmc_handle* h, double* en_hist, double* ev_hist, int reduce_ladders) {
+    if (!h) return PTMC_ERR_ARG;
+    TRY(ptmc_sync(h));
+    double* dst = h->cfg.ensemble == PTMC_ENS_NPT ? ev_hist : en_hist;
+    if (!dst) return PTMC_OK;
+    const u64* src = h->P.hist;
+    size_t n = (size_t)h->cfg.n_ladders * h->hist_per_ladder;
+    if (reduce_ladders) {
+        void* p; int64_t m;
+        TRY(ptmc_reduced_hist_dev(h, &p, &m));
+        src = static_cast<const u64*>(p); n = (size_t)m;
+    }
+    std::vector<u64> tmp(n);
+    CU(h, cudaMemcpy(tmp.data(), src, n * sizeof(u64), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) dst[i] = (double)tmp[i];   // Output.en_histogram holds Float64 counts
+    return PTMC_OK;
+}
+
+// ------------------------------------------------------------------------------------- introspection --
+extern "C" PTMC_API int64_t ptmc_launch_count(const ptmc_handle* h) { return h ? h->launches : 0; }
+extern "C" PTMC_API int ptmc_lanes_per_replica(const ptmc_handle* h) { return h ? h->G : 0; }
+
+extern "C" PTMC_API int ptmc_fp64_peak(int device, int iters, double* tflops) {
+    if (!tflops) return PTMC_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(nullptr, PTMC_ERR_CUDA, "no such CUDA device");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, PTMC_ERR_CUDA, "cudaSetDevice failed");
+    double v = measure_fp64_peak(nullptr, iters > 0 ? iters : 5);
+    if (v <= 0) return fail(nullptr, PTMC_ERR_CUDA, "fp64 peak measurement failed");
+    *tflops = v;
+    return PTMC_OK;
+}

@@ -1,0 +1,250 @@
+// ptmc_device.cuh — device-side building blocks of the B200 (sm_100a) sweep kernels.
+//
+// Data layout.  One CTA = one parallel-tempering ladder; one group of G lanes
+// (G = 4/8/16/32, a power of two inside one warp) = one replica slot.  Configuration-side state
+// (positions, box, en_tot, r_cut, EAM components) lives in shared memory, indexed through a slot->config
+// permutation so that a replica exchange (src/Exchange.jl:115-124) is a swap of two ints.
+// Slot-side state (beta, max_displ, counters, ham, RNG) lives in registers, replicated in every lane of
+// the group, so every lane takes identical decisions from identical bits.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/ptmc_b200.h"
+
+namespace ptmc {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+// Everything the kernels need, passed by value as the kernel parameter (constant bank).
+struct DevParams {
+    // sizes
+    int n_traj, n_atoms, n_pad;          // n_pad = n_atoms rounded up to a multiple of 32
+    int n_atom_moves, n_volume_moves, n_steps;
+    int ensemble, bc_kind, pot_kind, n_coeff;
+    int n_adjust, mc_sample, n_bin;
+    int replay;                          // 1: consume pre-drawn draws
+    double min_acc, max_acc, pressure;
+    double coeff[PTMC_MAX_COEFF];
+    double eam_hn, eam_hm;               // n/2, m/2  (r^-n = exp(-(n/2) log r2))
+    double eam_ean, eam_ecam;
+    // config-side state at rest, slot ordered: [L][T]...
+    double* pos;        // [L][T][N][3]
+    double* box;        // [L][T][2]
+    double* en_tot;     // [L][T]
+    double* comp;       // [L][T][N][2]  EAM (phi, rho)
+    // slot-side state
+    double* max_displ;  // [L][T][4]
+    double* max_boxlength; // [L][T]
+    i64* counters;      // [L][T][PTMC_NCOUNT]
+    double* ham;        // [L][T][2]
+    const double* betas;// [T]
+    u64* slot_rng;      // [L][T][4]
+    u64* ladder_rng;    // [L][4]
+    // replay
+    const u64* slot_draws; i64 slot_len; i64* slot_cursor;       // [L][T][slot_len], [L][T]
+    const u64* ladder_draws; i64 ladder_len; i64* ladder_cursor; // [L][ladder_len], [L]
+    // histograms
+    const double* en_min; const double* en_max; const double* v_min; const double* v_max; // [L]
+    u64* hist;          // NVT [L][T][nb+2]; NPT [L][T][nb+2][nb+2]
+    // trace (parity mode)
+    int32_t* tr_index; double* tr_de; uint8_t* tr_acc; int32_t* tr_exc;
+    i64 trace_cap, trace_base;
+    int* error;         // device error word (most negative ptmc_status wins)
+};
+
+// --------------------------------------------------------------------------------- exact arithmetic --
+// Decisions and positions must follow the reference bit for bit, so everything that feeds a stored
+// position, a comparison or a histogram index is written with non-contracting intrinsics (Julia never
+// fuses a*b+c).  Energies may use FMA (parity bar: 1e-10 relative).
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---------------------------------------------------------------------------------------------- RNG --
+// Julia's default generator: Xoshiro256++; rand() = (u >> 11) * 2^-53; rand(1:n) = Lemire.
+struct Xo { u64 s0, s1, s2, s3; };
+__device__ __forceinline__ u64 rotl64(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
+__device__ __forceinline__ u64 xo_next(Xo& r) {
+    u64 res = rotl64(r.s0 + r.s3, 23) + r.s0;
+    u64 t = r.s1 << 17;
+    r.s2 ^= r.s0; r.s3 ^= r.s1; r.s1 ^= r.s2; r.s0 ^= r.s3; r.s2 ^= t; r.s3 = rotl64(r.s3, 45);
+    return res;
+}
+
+template <bool DBG>
+struct Stream {
+    Xo r;
+    const u64* draws; i64 pos, len; int exhausted;   // replay (DBG kernels only)
+    __device__ __forceinline__ u64 next() {
+        if (DBG) {
+            if (draws) {
+                if (pos >= len) { exhausted = 1; return 0; }
+                return draws[pos++];
+            }
+        }
+        return xo_next(r);
+    }
+    __device__ __forceinline__ double rand() { return (double)(next() >> 11) * 0x1.0p-53; }
+    // rand(1:n)
+    __device__ __forceinline__ int range(u64 n) {
+        u64 x = next();
+        u64 hi = __umul64hi(x, n), lo = x * n;
+        if (lo < n) {
+            u64 t = (0 - n) % n;
+            while (lo < t) {
+                if (DBG) { if (exhausted) break; }
+                x = next(); hi = __umul64hi(x, n); lo = x * n;
+            }
+        }
+        return (int)hi + 1;
+    }
+};
+
+// ----------------------------------------------------------------------------------- group reduction --
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned mask) {
+#pragma unroll
+    for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(mask, v, m);
+    return v;   // xor butterfly: every lane ends with the same bits (a+b == b+a)
+}
+
+// --------------------------------------------------------------------------------------- reciprocals --
+// 1/x for normal positive x: MUFU.RCP64H seed (~2^-20) + two Newton steps (error ~1 ulp), no special cases.
+__device__ __forceinline__ double rcp_pos(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed + two Newton steps.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
+// -------------------------------------------------------------------------------------- pair energy --
+// dimer_energy(::ELJPotentialEven) src/EnergyEvaluation.jl:934-942: sum_i c_i r^-(4+2i) = x^3 * Horner(x),
+// x = 1/r2.  Same polynomial, one reciprocal instead of 1+K divisions (differs at the 1e-16 level).
+__device__ __forceinline__ double elj_even(const DevParams& P, double r2) {
+    double x = rcp_pos(r2);
+    double x3 = x * x * x;
+    double p;
+    if (P.n_coeff == 6) {
+        p = P.coeff[5];
+        p = fma(p, x, P.coeff[4]); p = fma(p, x, P.coeff[3]); p = fma(p, x, P.coeff[2]);
+        p = fma(p, x, P.coeff[1]); p = fma(p, x, P.coeff[0]);
+    } else {
+        p = P.coeff[P.n_coeff - 1];
+        for (int k = P.n_coeff - 2; k >= 0; --k) p = fma(p, x, P.coeff[k]);
+    }
+    return p * x3;
+}
+// dimer_energy(::ELJPotential) src/EnergyEvaluation.jl:923-932: sum_i c_i r^-(5+i) = y^6 * Horner(y), y = 1/r.
+__device__ __forceinline__ double elj_odd(const DevParams& P, double r2) {
+    double y = rsqrt_pos(r2);
+    double y2 = y * y;
+    double y6 = y2 * y2 * y2;
+    double p = P.coeff[P.n_coeff - 1];
+    for (int k = P.n_coeff - 2; k >= 0; --k) p = fma(p, y, P.coeff[k]);
+    return p * y6;
+}
+template <int POT>
+__device__ __forceinline__ double pair_energy(const DevParams& P, double r2) {
+    return POT == PTMC_POT_ELJ ? elj_odd(P, r2) : elj_even(P, r2);
+}
+// invrexp src/EnergyEvaluation.jl:1088-1095: (r^-n, r^-m) = (exp(-(n/2) log r2), exp(-(m/2) log r2)); r2 > 0.
+__device__ __forceinline__ void eam_invrexp(const DevParams& P, double r2, double& phi, double& rho) {
+    double l = log(r2);
+    phi = exp(-P.eam_hn * l);
+    rho = exp(-P.eam_hm * l);
+}
+
+// lrc(::ELJPotentialEven) src/EnergyEvaluation.jl:968-982 (r_cut is the squared cut-off)
+__device__ __forceinline__ double lrc_even(const DevParams& P, double r_cut) {
+    if (r_cut <= 50.0) return 0.0;
+    double rs = sqrt(r_cut);
+    double rc3 = r_cut * rs;
+    double e = 0.0;
+    for (int i = 1; i <= P.n_coeff; ++i) { e += P.coeff[i - 1] / rc3 / (double)(2 * i + 1); rc3 *= r_cut; }
+    double nn = (double)((i64)P.n_atoms * P.n_atoms);
+    return e * 3.14159265358979323846 * nn / 4.0 / (rs * rs * rs);
+}
+
+// ----------------------------------------------------------------------------------------- geometry --
+// Periodic box of one configuration with the constants the minimum-image formulas need.
+struct Box {
+    double L, h;        // box_length, box_height (cubic: h = L)
+    double iL, ih;      // reciprocals
+    double hy, ihy;     // rhombic: sqrt(3)/2 * L and its reciprocal
+    double is3;         // 1/sqrt(3)
+};
+__device__ __forceinline__ Box make_box(int bc_kind, double L, double h) {
+    Box b;
+    b.L = L; b.h = (bc_kind == PTMC_BC_CUBIC) ? L : h;
+    b.iL = 1.0 / b.L; b.ih = 1.0 / b.h;
+    const double s3 = sqrt(3.0);
+    b.hy = s3 / 2 * L; b.ihy = 1.0 / b.hy; b.is3 = 1.0 / s3;
+    return b;
+}
+// distance2 with minimum image, src/Configurations.jl:104-109 (cubic), :110-120 (rhombic), :121-126 (rect).
+// Divisions are replaced by multiplications with reciprocals: the rounded quotient feeding rint() differs
+// only when a pair sits exactly on the half-box plane, where both images are equidistant.
+template <bool RHOMBIC>
+__device__ __forceinline__ double dist2_pbc(const Box& b, double ax, double ay, double az, double bx, double by, double bz) {
+    double dx, dy, dz;
+    if (RHOMBIC) {
+        double By = fma(b.hy, rint((ay - by) * b.ihy), by);
+        double Bx = bx - by * b.is3 + b.L * rint(((ax - bx) - b.is3 * (ay - by)) * b.iL) + b.is3 * By;
+        double Bz = fma(b.h, rint((az - bz) * b.ih), bz);
+        dx = ax - Bx; dy = ay - By; dz = az - Bz;
+    } else {
+        dx = ax - fma(b.L, rint((ax - bx) * b.iL), bx);
+        dy = ay - fma(b.L, rint((ay - by) * b.iL), by);
+        dz = az - fma(b.h, rint((az - bz) * b.ih), bz);
+    }
+    return fma(dz, dz, fma(dy, dy, dx * dx));
+}
+// get_volume src/Configurations.jl:246-256
+__device__ __forceinline__ double get_volume(int bc_kind, double L, double h) {
+    if (bc_kind == PTMC_BC_CUBIC) return xmul(xmul(L, L), L);
+    if (bc_kind == PTMC_BC_RHOMBIC) return xdiv(xmul(xmul(xmul(L, L), h), sqrt(3.0)), 2.0);
+    return xmul(xmul(L, L), h);
+}
+// get_r_cut src/Ensembles.jl:118-125,153-155 (squared)
+__device__ __forceinline__ double get_r_cut(int bc_kind, double L, double h) {
+    if (bc_kind == PTMC_BC_CUBIC) return xdiv(xmul(L, L), 4.0);
+    if (bc_kind == PTMC_BC_RHOMBIC) { double a = xdiv(xmul(xmul(L, L), 3.0), 16.0), b = xdiv(xmul(h, h), 4.0); return a < b ? a : b; }
+    double a = xdiv(xmul(L, L), 4.0), b = xdiv(xmul(h, h), 4.0);
+    return a < b ? a : b;
+}
+
+// --------------------------------------------------------------------------------------- Metropolis --
+// acc_test! src/MCRun.jl:122-132 with metropolis_condition src/Exchange.jl:53-57: accept iff
+// min(1, exp(x)) >= u, u in [0,1).  exp(x) is classified with an FP32 interval first; the FP64 exp is
+// evaluated only when u falls inside the interval (probability ~1e-5), so the decision is exactly the FP64 one.
+__device__ __forceinline__ bool metropolis_accept(double x, double u) {
+    if (!(x < 0.0)) return !(x != x);          // exp(x) >= 1 > u ; NaN -> reject (NaN >= u is false)
+    if (x > -30.0) {
+        float pf = __expf((float)x);
+        float uf = (float)u;
+        if (uf < pf * 0.9999f) return true;
+        if (uf > pf * 1.0001f) return false;
+    } else if (u > 1e-12) {
+        return false;                           // exp(-30) < 1e-13
+    }
+    return exp(x) >= u;
+}
+
+}  // namespace ptmc

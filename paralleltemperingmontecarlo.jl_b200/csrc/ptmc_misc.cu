@@ -1,0 +1,70 @@
+// ptmc_misc.cu — small kernels around the sweep: state initialisation, ladder-axis histogram reduction,
+// and the FP64 pipe peak measurement that bench.py uses as its roofline denominator.
+#include "sweep_kernel.cuh"
+
+namespace ptmc {
+
+int sweep_max_threads(int G) { return sweep_max_threads_c(G); }
+
+void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st) {
+    const int threads = 128;                         // 4 replicas (warps) per CTA
+    const unsigned blocks = (unsigned)((n_rep * 32 + threads - 1) / threads);
+    if (P.pot_kind == PTMC_POT_EAM) init_kernel<PTMC_POT_EAM><<<blocks, threads, 0, st>>>(P, n_rep);
+    else if (P.pot_kind == PTMC_POT_ELJ) init_kernel<PTMC_POT_ELJ><<<blocks, threads, 0, st>>>(P, n_rep);
+    else init_kernel<PTMC_POT_ELJ_EVEN><<<blocks, threads, 0, st>>>(P, n_rep);
+}
+
+// out[k] = sum over ladders of hist[l][k]; exact (u64 counts).
+__global__ void reduce_hist_kernel(const u64* __restrict__ hist, u64* __restrict__ out, i64 n_ladders, i64 per) {
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= per) return;
+    u64 s = 0;
+    for (i64 l = 0; l < n_ladders; ++l) s += hist[l * per + k];
+    out[k] = s;
+}
+void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st) {
+    const int threads = 256;
+    reduce_hist_kernel<<<(unsigned)((per + threads - 1) / threads), threads, 0, st>>>(hist, out, n_ladders, per);
+}
+
+// FP64 pipe peak: 8 independent DFMA chains per thread, all SMs, 2 flops per DFMA.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int n_iter, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < n_iter; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s;   // keep the chains alive
+}
+double measure_fp64_peak(cudaStream_t st, int iters) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+    const int threads = 256, blocks = sms * 8, n_iter = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dfma_peak_kernel<<<blocks, threads, 0, st>>>(d, 64, 0.999999, 1e-9);   // warm-up
+    double best = 0;
+    for (int it = 0; it < iters; ++it) {
+        cudaEventRecord(e0, st);
+        dfma_peak_kernel<<<blocks, threads, 0, st>>>(d, n_iter, 0.999999, 1e-9);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 2.0 * 64.0 * n_iter * (double)threads * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+}
+
+}  // namespace ptmc

@@ -1,0 +1,511 @@
+// sweep_kernel.cuh — the parallel-tempering sweep: n_cycles x mc_cycle! (src/MCRun.jl:192-253) for one
+// ladder per CTA.  Instantiated per (lanes-per-replica G, potential, geometry, debug) in sweep_inst_*.cu.
+//
+//   mc_step!  (src/MCRun.jl:169-182)  -> every group runs n_steps x mc_move! on its slot, no CTA sync
+//   exchange  (src/MCRun.jl:203-205, src/Exchange.jl:132-186) -> thread 0 between two __syncthreads()
+//   update_max_stepsize! (src/Exchange.jl:198-263), sampling_step! (src/Sampling.jl:330-371) -> per group
+#pragma once
+#include "ptmc_device.cuh"
+
+namespace ptmc {
+
+// Launch bounds per lanes-per-replica value: n_traj * G (rounded up to a warp) threads per ladder.
+// G <= 16: 384 threads, two CTAs per SM (80 registers); G = 32: 512 threads (128 registers).
+#ifndef PTMC_MAX_THREADS_SMALL
+#define PTMC_MAX_THREADS_SMALL 384
+#endif
+#ifndef PTMC_MIN_BLOCKS_SMALL
+#define PTMC_MIN_BLOCKS_SMALL 2
+#endif
+__host__ __device__ constexpr int sweep_max_threads_c(int G) { return G == 32 ? 512 : PTMC_MAX_THREADS_SMALL; }
+__host__ __device__ constexpr int sweep_min_blocks_c(int G) { return G == 32 ? 1 : PTMC_MIN_BLOCKS_SMALL; }
+enum Geom { GEOM_SPHERE = 0, GEOM_PBC = 1 };   // SphericalBC+NVT | periodic BC, NVT or NPT (runtime)
+
+// shared-memory layout of one CTA (doubles unless noted)
+struct SmemLayout {
+    int cfg_stride;     // doubles per configuration buffer
+    int off_scal;       // per config: en_tot, L, h, r_cut  (4 doubles)
+    int off_perm;       // int cfg_of_slot[T]
+    int off_exc;        // i64 exc counters [T][2]
+    int off_ham;        // ham [T][2] (slot side)
+    int off_lrng;       // ladder stream: 4 x u64 state + cursor
+    size_t bytes;
+};
+__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind) {
+    SmemLayout s;
+    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? 4 : 0);   // x,y,z (+ phi,rho,new_phi,new_rho)
+    s.cfg_stride = arrays * n_pad;
+    s.off_scal = n_traj * s.cfg_stride;
+    int off = s.off_scal + 4 * n_traj;
+    s.off_exc = off; off += 2 * n_traj;
+    s.off_ham = off; off += 2 * n_traj;
+    s.off_lrng = off; off += 6;
+    s.off_perm = off; off += (n_traj + 1) / 2 + 1;
+    s.bytes = (size_t)off * sizeof(double);
+    return s;
+}
+
+template <int G, int POT, int GEOM, bool DBG>
+__global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
+sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
+    extern __shared__ double sm[];
+    constexpr bool EAM = (POT == PTMC_POT_EAM);
+    constexpr bool PBC = (GEOM == GEOM_PBC);
+    const int T = P.n_traj, N = P.n_atoms, NP = P.n_pad;
+    const int lad = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int slot = tid / G, g = tid & (G - 1);
+    const bool active = slot < T;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
+    const SmemLayout lay = smem_layout(T, NP, POT);
+    double* scal = sm + lay.off_scal;
+    i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
+    double* hams = sm + lay.off_ham;
+    u64* lrng = reinterpret_cast<u64*>(sm + lay.off_lrng);
+    int* perm = reinterpret_cast<int*>(sm + lay.off_perm);
+    const bool npt = PBC && P.ensemble == PTMC_ENS_NPT;
+    const bool rhombic = PBC && P.bc_kind == PTMC_BC_RHOMBIC;
+    const i64 rep = (i64)lad * T + slot;      // replica (slot) index in the global arrays
+
+    // ---- load: slot s starts with configuration buffer s ----------------------------------------------
+    if (active) {
+        double* X = sm + (size_t)slot * lay.cfg_stride;
+        double* Y = X + NP; double* Z = Y + NP;
+        const double* gp = P.pos + rep * 3 * N;
+        for (int j = g; j < NP; j += G) {
+            bool v = j < N;
+            X[j] = v ? gp[3 * j] : 0.0; Y[j] = v ? gp[3 * j + 1] : 0.0; Z[j] = v ? gp[3 * j + 2] : 0.0;
+            if (EAM) {
+                Z[NP + j] = v ? P.comp[(rep * N + j) * 2] : 1.0;          // phi
+                Z[2 * NP + j] = v ? P.comp[(rep * N + j) * 2 + 1] : 1.0;  // rho
+                Z[3 * NP + j] = 1.0; Z[4 * NP + j] = 1.0;
+            }
+        }
+        if (g == 0) {
+            double L = P.box[rep * 2], h = P.box[rep * 2 + 1];
+            scal[4 * slot] = P.en_tot[rep];
+            scal[4 * slot + 1] = L; scal[4 * slot + 2] = h;
+            scal[4 * slot + 3] = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
+            perm[slot] = slot;
+            exc_cnt[2 * slot] = 0; exc_cnt[2 * slot + 1] = 0;
+            hams[2 * slot] = P.ham[rep * 2]; hams[2 * slot + 1] = P.ham[rep * 2 + 1];
+        }
+    }
+    // slot-side registers (identical in every lane of the group)
+    Stream<DBG> S;
+    double beta = 0, dmax = 0, vmax = 0, max_boxl = 0;
+    int n_acc_atom = 0, n_adj_atom = 0, n_acc_vol = 0, n_adj_vol = 0;   // this launch / since last adjustment
+    if (active) {
+        beta = P.betas[slot];
+        dmax = P.max_displ[rep * 4];
+        n_adj_atom = (int)P.counters[rep * PTMC_NCOUNT + PTMC_C_ATOM_ADJ];
+        if (PBC) {
+            vmax = P.max_displ[rep * 4 + 1];
+            max_boxl = P.max_boxlength[rep];
+            n_adj_vol = (int)P.counters[rep * PTMC_NCOUNT + PTMC_C_VOL_ADJ];
+        }
+        S.r.s0 = P.slot_rng[rep * 4]; S.r.s1 = P.slot_rng[rep * 4 + 1];
+        S.r.s2 = P.slot_rng[rep * 4 + 2]; S.r.s3 = P.slot_rng[rep * 4 + 3];
+        S.draws = nullptr; S.pos = 0; S.len = 0; S.exhausted = 0;
+        if (DBG) {
+            if (P.replay) { S.draws = P.slot_draws + rep * P.slot_len; S.len = P.slot_len; S.pos = P.slot_cursor[rep]; }
+        }
+    }
+    // ladder ("driver task") stream lives in shared memory; only thread 0 touches it
+    if (tid == 0) {
+        lrng[0] = P.ladder_rng[lad * 4]; lrng[1] = P.ladder_rng[lad * 4 + 1];
+        lrng[2] = P.ladder_rng[lad * 4 + 2]; lrng[3] = P.ladder_rng[lad * 4 + 3];
+        lrng[4] = (DBG && P.replay) ? (u64)P.ladder_cursor[lad] : 0;
+    }
+    // cycle phases instead of 64-bit modulo in the loop
+    int adj_phase = (int)(first_idx % P.n_adjust);
+    int smp_phase = (int)(first_idx % P.mc_sample);
+    __syncthreads();
+
+    const bool tracing = DBG && P.trace_cap > 0;
+    int err = 0;
+
+    for (i64 cyc = 0; cyc < n_cycles; ++cyc) {
+        if (active) {
+            // ================================================================== mc_step! for this slot ==
+            const int c = perm[slot];
+            double* X = sm + (size_t)c * lay.cfg_stride;
+            double* Y = X + NP; double* Z = Y + NP;
+            double en = scal[4 * c];
+            double boxL = scal[4 * c + 1], boxH = 0.0, rcut = 0.0;
+            Box bx;
+            if (PBC) { boxH = scal[4 * c + 2]; rcut = scal[4 * c + 3]; bx = make_box(P.bc_kind, boxL, boxH); }
+            const double R2 = boxL;   // spherical: box[0] = radius^2
+
+            for (int step = 0; step < P.n_steps; ++step) {
+                const int index = S.range((u64)P.n_steps);          // rand(1:N) src/MCRun.jl:145
+                double de = 0.0;
+                bool acc = false;
+                if (!PBC || index <= P.n_atom_moves) {
+                    // ------------------------------------------------ atom_displacement src/MCMoves.jl:33-145
+                    const int i = index - 1;
+                    double xi = X[i], yi = Y[i], zi = Z[i];
+                    double tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
+                    double ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
+                    double tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+                    if (!PBC) {
+                        int count = 0;
+                        while (xadd(xadd(xmul(tx, tx), xmul(ty, ty)), xmul(tz, tz)) > R2) {   // check_boundary
+                            ++count;
+                            if (count == 50) {
+                                // recentre! src/Configurations.jl:79-85: sequential means, then shift
+                                __syncwarp(gmask);
+                                double cx = 0, cy = 0, cz = 0;
+                                for (int j = 0; j < N; ++j) cx = xadd(cx, X[j]);
+                                for (int j = 0; j < N; ++j) cy = xadd(cy, Y[j]);
+                                for (int j = 0; j < N; ++j) cz = xadd(cz, Z[j]);
+                                cx = xdiv(cx, (double)N); cy = xdiv(cy, (double)N); cz = xdiv(cz, (double)N);
+                                __syncwarp(gmask);
+                                for (int j = g; j < N; j += G) { X[j] = xsub(X[j], cx); Y[j] = xsub(Y[j], cy); Z[j] = xsub(Z[j], cz); }
+                                __syncwarp(gmask);
+                                xi = X[i]; yi = Y[i]; zi = Z[i];
+                            } else {
+                                tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
+                                ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
+                                tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+                                if (count == 100) { err = PTMC_ERR_SPHERE; break; }
+                            }
+                            if (DBG) { if (S.exhausted) break; }
+                        }
+                    } else if (P.bc_kind == PTMC_BC_CUBIC) {           // src/MCMoves.jl:50-64
+                        tx = xsub(tx, xmul(boxL, rint(xdiv(tx, boxL))));
+                        ty = xsub(ty, xmul(boxL, rint(xdiv(ty, boxL))));
+                        tz = xsub(tz, xmul(boxL, rint(xdiv(tz, boxL))));
+                    } else if (P.bc_kind == PTMC_BC_RECTANGULAR) {     // :85-98
+                        tx = xsub(tx, xmul(boxL, rint(xdiv(tx, boxL))));
+                        ty = xsub(ty, xmul(boxL, rint(xdiv(ty, boxL))));
+                        tz = xsub(tz, xmul(boxH, rint(xdiv(tz, boxH))));
+                    } else {                                            // Rhombic :66-83
+                        const double s3 = sqrt(3.0);
+                        double ry = rint(xdiv(xsub(ty, xdiv(xmul(boxL, s3), 4.0)), xdiv(xmul(boxL, s3), 2.0)));
+                        double sx = xadd(xmul(boxL, rint(xdiv(xsub(xsub(tx, xdiv(ty, s3)), xdiv(boxL, 2.0)), boxL))),
+                                         xmul(xdiv(boxL, 2.0), ry));
+                        double sy = xmul(xdiv(xmul(boxL, s3), 2.0), ry);
+                        double sz = xmul(boxH, rint(xdiv(xsub(tz, xdiv(boxH, 2.0)), boxH)));
+                        tx = xsub(tx, sx); ty = xsub(ty, sy); tz = xsub(tz, sz);
+                    }
+                    // -------------------------------- energy_update! src/EnergyEvaluation.jl:1474-1506,1567-1591
+                    double new_en;
+                    if (!EAM) {
+                        // dimer_energy_update! :804-821: sum_j e(new_ij) - e(old_ij); the old row is recomputed
+                        // from the positions instead of being read from a stored dist2_mat.
+                        double accd = 0.0;
+#pragma unroll 2
+                        for (int j = g; j < NP; j += G) {
+                            const double xj = X[j], yj = Y[j], zj = Z[j];
+                            double d2n, d2o;
+                            if (PBC) {
+                                if (rhombic) { d2n = dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj); }
+                                else { d2n = dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj); }
+                            } else {
+                                double ax = tx - xj, ay = ty - yj, az = tz - zj;
+                                d2n = fma(az, az, fma(ay, ay, ax * ax));
+                                double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
+                                d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
+                            }
+                            const bool valid = (j != i) && (j < N);
+                            d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;   // identical inputs -> exact 0
+                            double en_j = pair_energy<POT>(P, d2n), eo_j = pair_energy<POT>(P, d2o);
+                            if (PBC) {
+                                if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }
+                            }
+                            accd += en_j - eo_j;
+                        }
+                        const double delta_en = group_sum<G>(accd, gmask);
+                        new_en = xadd(delta_en, en);
+                    } else {
+                        // calc_components :1111-1127 + calc_energies_from_components :1156-1162
+                        double* PHI = Z + NP; double* RHO = PHI + NP; double* NPHI = RHO + NP; double* NRHO = NPHI + NP;
+                        double sphi = 0.0, srho = 0.0, se = 0.0;
+                        for (int j = g; j < NP; j += G) {
+                            const double xj = X[j], yj = Y[j], zj = Z[j];
+                            double ax = tx - xj, ay = ty - yj, az = tz - zj;
+                            double d2n = fma(az, az, fma(ay, ay, ax * ax));
+                            double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
+                            double d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
+                            const bool valid = (j != i) && (j < N);
+                            d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
+                            double pn, rn, po, ro;
+                            eam_invrexp(P, d2n, pn, rn);
+                            eam_invrexp(P, d2o, po, ro);
+                            double tp = pn - po, tr = rn - ro;          // exactly 0 when !valid
+                            double nphi = PHI[j] + tp, nrho = RHO[j] + tr;
+                            NPHI[j] = nphi; NRHO[j] = nrho;
+                            sphi += tp; srho += tr;
+                            se += valid ? fma(-P.eam_ecam, sqrt(nrho), P.eam_ean * nphi) : 0.0;
+                        }
+                        sphi = group_sum<G>(sphi, gmask); srho = group_sum<G>(srho, gmask); se = group_sum<G>(se, gmask);
+                        const double nphi_i = PHI[i] + sphi, nrho_i = RHO[i] + srho;
+                        __syncwarp(gmask);
+                        if (g == 0) { NPHI[i] = nphi_i; NRHO[i] = nrho_i; }
+                        new_en = se + fma(-P.eam_ecam, sqrt(nrho_i), P.eam_ean * nphi_i);
+                    }
+                    // ------------------------------------------------------------ acc_test! src/MCRun.jl:122-132
+                    de = xsub(new_en, en);
+                    const double u = S.rand();
+                    acc = metropolis_accept(-xmul(de, beta), u);
+                    if (acc) {
+                        // swap_atom_config! src/swap_config.jl:40-51 (+ swap_vars! :208-211 for EAM)
+                        if (g == 0) { X[i] = tx; Y[i] = ty; Z[i] = tz; }
+                        en = new_en;
+                        n_acc_atom += 1; n_adj_atom += 1;
+                        if (EAM) {
+                            double* PHI = Z + NP; double* RHO = PHI + NP; double* NPHI = RHO + NP; double* NRHO = NPHI + NP;
+                            __syncwarp(gmask);
+                            for (int j = g; j < N; j += G) { PHI[j] = NPHI[j]; RHO[j] = NRHO[j]; }
+                        }
+                    }
+                    __syncwarp(gmask);
+                } else {
+                    // ------------------------------- volume_change_uniform src/MCMoves.jl:277-287, :169-177
+                    double scale = pow(exp(xmul(xsub(S.rand(), 0.5), vmax)), 1.0 / 3.0);
+                    if (boxL >= max_boxl && scale > 1.0) scale = 1.0;
+                    const double tL = xmul(scale, boxL), tH = xmul(scale, boxH);
+                    const double new_rcut = get_r_cut(P.bc_kind, tL, tH);
+                    const double sc2 = xmul(scale, scale);
+                    // dimer_energy_config on new_dist2_mat = dist2_mat * scale^2 (src/MCRun.jl:76-85,
+                    // src/EnergyEvaluation.jl:397-474); rows are dealt to the lanes of the group.
+                    double acce = 0.0;
+                    for (int a = 0; a < N - 1; ++a) {
+                        const double xa = X[a], ya = Y[a], za = Z[a];
+                        for (int j = a + 1 + g; j < N; j += G) {
+                            double d2 = rhombic ? dist2_pbc<true>(bx, xa, ya, za, X[j], Y[j], Z[j])
+                                                : dist2_pbc<false>(bx, xa, ya, za, X[j], Y[j], Z[j]);
+                            d2 = d2 * sc2;
+                            if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT>(P, d2);
+                        }
+                    }
+                    double e_new = group_sum<G>(acce, gmask);
+                    const double l = lrc_even(P, new_rcut);
+                    if (P.bc_kind == PTMC_BC_CUBIC) e_new = e_new + l;
+                    else if (P.bc_kind == PTMC_BC_RHOMBIC) e_new = e_new + l * 3 / 4 * tL / tH;
+                    else e_new = (tL < tH) ? e_new + l * tL / tH : e_new + l * (tH * tH) / (tL * tL);
+                    // metropolis_condition NPT src/Exchange.jl:58-71
+                    de = xsub(e_new, en);
+                    const double vc = get_volume(P.bc_kind, tL, tH), vu = get_volume(P.bc_kind, boxL, boxH);
+                    const double delta_h = xadd(de, xmul(P.pressure, xsub(vc, vu)));
+                    double p = exp(xadd(xmul(-delta_h, beta), xmul((double)P.n_atoms, log(xdiv(vc, vu)))));
+                    p = p > 1.0 ? 1.0 : p;
+                    const double u = S.rand();
+                    acc = p >= u;
+                    if (acc) {
+                        // swap_config_v! src/swap_config.jl:113-140
+                        __syncwarp(gmask);
+                        for (int j = g; j < N; j += G) { X[j] = xmul(scale, X[j]); Y[j] = xmul(scale, Y[j]); Z[j] = xmul(scale, Z[j]); }
+                        boxL = tL; boxH = tH; rcut = new_rcut; en = e_new;
+                        bx = make_box(P.bc_kind, boxL, boxH);
+                        n_acc_vol += 1; n_adj_vol += 1;
+                    }
+                    __syncwarp(gmask);
+                }
+                if (DBG) {
+                    if (tracing && g == 0) {
+                        size_t o = ((((size_t)lad * P.trace_cap + P.trace_base + cyc) * T + slot) * P.n_steps) + step;
+                        P.tr_index[o] = index; P.tr_de[o] = de; P.tr_acc[o] = acc ? 1 : 0;
+                    }
+                    if (S.exhausted) err = PTMC_ERR_REPLAY;
+                }
+            }
+            if (g == 0) {
+                scal[4 * c] = en;
+                if (PBC) { scal[4 * c + 1] = boxL; scal[4 * c + 2] = boxH; scal[4 * c + 3] = rcut; }
+            }
+        }
+        __syncthreads();
+        // ========================================= exchange: src/MCRun.jl:203-205, src/Exchange.jl:132-186 ==
+        if (tid == 0) {
+            Stream<DBG> LS;
+            LS.r.s0 = lrng[0]; LS.r.s1 = lrng[1]; LS.r.s2 = lrng[2]; LS.r.s3 = lrng[3];
+            LS.draws = nullptr; LS.pos = 0; LS.len = 0; LS.exhausted = 0;
+            if (DBG) {
+                if (P.replay) { LS.draws = P.ladder_draws + lad * P.ladder_len; LS.len = P.ladder_len; LS.pos = (i64)lrng[4]; }
+            }
+            int ex_gate = 0, ex_n = 0, ex_acc = 0;
+            if (LS.rand() < 0.1) {
+                ex_gate = 1;
+                const int n_exc = LS.range((u64)(T - 1));
+                ex_n = n_exc;
+                const int a = n_exc - 1, b = n_exc;
+                exc_cnt[2 * a] += 1; exc_cnt[2 * b] += 1;
+                const int ca = perm[a], cb = perm[b];
+                double ea = scal[4 * ca], eb = scal[4 * cb];
+                if (npt) {
+                    ea = xadd(ea, xmul(P.pressure, get_volume(P.bc_kind, scal[4 * ca + 1], scal[4 * ca + 2])));
+                    eb = xadd(eb, xmul(P.pressure, get_volume(P.bc_kind, scal[4 * cb + 1], scal[4 * cb + 2])));
+                }
+                // exc_acceptance :103-108: min(1, exp(dbeta * dE)) > rand()   (strict)
+                double pe = exp(xmul(xsub(P.betas[a], P.betas[b]), xsub(ea, eb)));
+                pe = (pe != pe) ? pe : (pe < 1.0 ? pe : 1.0);
+                if (pe > LS.rand()) {
+                    ex_acc = 1;
+                    exc_cnt[2 * a + 1] += 1; exc_cnt[2 * b + 1] += 1;
+                    perm[a] = cb; perm[b] = ca;       // exc_trajectories! :115-124
+                }
+            }
+            lrng[0] = LS.r.s0; lrng[1] = LS.r.s1; lrng[2] = LS.r.s2; lrng[3] = LS.r.s3;
+            if (DBG) {
+                lrng[4] = (u64)LS.pos;
+                if (tracing) {
+                    int32_t* e = P.tr_exc + ((size_t)lad * P.trace_cap + P.trace_base + cyc) * 3;
+                    e[0] = ex_gate; e[1] = ex_n; e[2] = ex_acc;
+                }
+                if (LS.exhausted) err = PTMC_ERR_REPLAY;
+            }
+        }
+        __syncthreads();
+        if (active) {
+            // ------------------------------------------- update_max_stepsize! src/Exchange.jl:198-263
+            if (adj_phase == 0) {
+                double rate = xdiv((double)n_adj_atom, (double)((i64)P.n_adjust * P.n_atom_moves));
+                if (rate < P.min_acc) dmax = xmul(dmax, 0.9);
+                else if (rate > P.max_acc) dmax = xmul(dmax, 1.1);
+                n_adj_atom = 0;
+                if (PBC) {
+                    if (npt) {
+                        rate = xdiv((double)n_adj_vol, (double)((i64)P.n_adjust * P.n_volume_moves));
+                        if (rate < P.min_acc) vmax = xmul(vmax, 0.9);
+                        else if (rate > P.max_acc) vmax = xmul(vmax, 1.1);
+                        n_adj_vol = 0;
+                    }
+                }
+            }
+            // ---------------------------------------------------- sampling_step! src/Sampling.jl:330-371
+            if (sample && smp_phase == 0 && g == 0) {
+                const int c = perm[slot];
+                const double e = scal[4 * c];
+                const int nb = P.n_bin;
+                const double en_min = P.en_min[lad];
+                const double delta_en = xdiv(xsub(P.en_max[lad], en_min), (double)(nb - 1));   // :150
+                if (npt) {
+                    const double L = scal[4 * c + 1], h = scal[4 * c + 2];
+                    const double hv = xadd(e, xmul(P.pressure, get_volume(P.bc_kind, L, h)));   // :35-46
+                    hams[2 * slot] = xadd(hams[2 * slot], hv);
+                    hams[2 * slot + 1] = xadd(hams[2 * slot + 1], xmul(hv, hv));
+                    const double v_min = P.v_min[lad];
+                    const double delta_v = xdiv(xsub(P.v_max[lad], v_min), (double)nb);
+                    double vol_h;   // find_hist_index :72-84, :98-113, :115-130 (rhombic quirk: 3*sqrt(h)/2)
+                    if (P.bc_kind == PTMC_BC_CUBIC) vol_h = xmul(xmul(L, L), L);
+                    else if (P.bc_kind == PTMC_BC_RECTANGULAR) vol_h = xmul(xmul(L, L), h);
+                    else vol_h = xdiv(xmul(xmul(L, L), xmul(3.0, sqrt(h))), 2.0);
+                    double fe = floor(xdiv(xsub(e, en_min), delta_en)) + 1.0;
+                    double fv = floor(xdiv(xsub(vol_h, v_min), delta_v)) + 1.0;
+                    int he = fe < 1.0 ? 1 : (fe > (double)nb ? nb + 2 : (int)fe + 1);
+                    int hv_ = fv < 1.0 ? 1 : (fv > (double)nb ? nb + 2 : (int)fv + 1);
+                    if (fe != fe) he = nb + 2;   // NaN: Julia's floor(Int, NaN) throws; park it in the overflow bin
+                    if (fv != fv) hv_ = nb + 2;
+                    P.hist[((size_t)rep * (nb + 2) + (he - 1)) * (nb + 2) + (hv_ - 1)] += 1;
+                } else {
+                    hams[2 * slot] = xadd(hams[2 * slot], e);                                  // :29-34
+                    hams[2 * slot + 1] = xadd(hams[2 * slot + 1], xmul(e, e));
+                    const double hi = xadd(xdiv(xsub(e, en_min), delta_en), 1.0);             // :63-66
+                    int h = hi < 1.0 ? 1 : (hi > (double)nb ? nb + 2 : (int)floor(hi) + 1);     // :53-62
+                    if (hi != hi) h = nb + 2;
+                    P.hist[(size_t)rep * (nb + 2) + (h - 1)] += 1;
+                }
+            }
+        }
+        if (++adj_phase == P.n_adjust) adj_phase = 0;
+        if (++smp_phase == P.mc_sample) smp_phase = 0;
+    }
+
+    // ---- store: configurations go back in slot order ----------------------------------------------------
+    __syncthreads();
+    if (active) {
+        const int c = perm[slot];
+        const double* X = sm + (size_t)c * lay.cfg_stride;
+        const double* Y = X + NP; const double* Z = Y + NP;
+        double* gp = P.pos + rep * 3 * N;
+        for (int j = g; j < N; j += G) {
+            gp[3 * j] = X[j]; gp[3 * j + 1] = Y[j]; gp[3 * j + 2] = Z[j];
+            if (EAM) { P.comp[(rep * N + j) * 2] = Z[NP + j]; P.comp[(rep * N + j) * 2 + 1] = Z[2 * NP + j]; }
+        }
+        if (g == 0) {
+            P.en_tot[rep] = scal[4 * c];
+            P.max_displ[rep * 4] = dmax;
+            P.ham[rep * 2] = hams[2 * slot]; P.ham[rep * 2 + 1] = hams[2 * slot + 1];
+            i64* cn = P.counters + rep * PTMC_NCOUNT;
+            cn[PTMC_C_ATOM_TOT] += n_acc_atom; cn[PTMC_C_ATOM_ADJ] = n_adj_atom;
+            if (PBC) {
+                P.box[rep * 2] = scal[4 * c + 1]; P.box[rep * 2 + 1] = scal[4 * c + 2];
+                P.max_displ[rep * 4 + 1] = vmax;
+                cn[PTMC_C_VOL_TOT] += n_acc_vol; cn[PTMC_C_VOL_ADJ] = n_adj_vol;
+            }
+            cn[PTMC_C_EXC_ATT] += exc_cnt[2 * slot]; cn[PTMC_C_EXC_ACC] += exc_cnt[2 * slot + 1];
+            P.slot_rng[rep * 4] = S.r.s0; P.slot_rng[rep * 4 + 1] = S.r.s1;
+            P.slot_rng[rep * 4 + 2] = S.r.s2; P.slot_rng[rep * 4 + 3] = S.r.s3;
+            if (DBG) { if (P.replay) P.slot_cursor[rep] = S.pos; }
+        }
+    }
+    if (tid == 0) {
+        P.ladder_rng[lad * 4] = lrng[0]; P.ladder_rng[lad * 4 + 1] = lrng[1];
+        P.ladder_rng[lad * 4 + 2] = lrng[2]; P.ladder_rng[lad * 4 + 3] = lrng[3];
+        if (DBG) { if (P.replay) P.ladder_cursor[lad] = (i64)lrng[4]; }
+    }
+    if (err) atomicMin(P.error, err);
+}
+
+// ------------------------------------------------------------------------------------------- init --
+// MCState constructor (src/MCStates.jl:137-162): initial en_tot (dimer_energy_config
+// src/EnergyEvaluation.jl:378-474, or EAM set_variables :1800-1811 + :1722-1734) for every replica.
+// One warp per replica.
+template <int POT>
+__global__ void init_kernel(const DevParams P, const i64 n_rep) {
+    const i64 rep = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    const int g = threadIdx.x & 31;
+    if (rep >= n_rep) return;
+    const int N = P.n_atoms;
+    const double* gp = P.pos + rep * 3 * N;
+    const double L = P.box[rep * 2], h = P.box[rep * 2 + 1];
+    const bool pbc = P.bc_kind != PTMC_BC_SPHERICAL;
+    const bool npt = P.ensemble == PTMC_ENS_NPT;
+    const bool rhombic = P.bc_kind == PTMC_BC_RHOMBIC;
+    Box bx = make_box(P.bc_kind, pbc ? L : 1.0, pbc ? h : 1.0);
+    const double rcut = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
+    if (POT == PTMC_POT_EAM) {
+        double se = 0.0;
+        for (int a = g; a < N; a += 32) {
+            double sp = 0.0, sr = 0.0;
+            for (int j = 0; j < N; ++j) {
+                if (j == a) continue;
+                double dx = gp[3 * a] - gp[3 * j], dy = gp[3 * a + 1] - gp[3 * j + 1], dz = gp[3 * a + 2] - gp[3 * j + 2];
+                double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                double p, r; eam_invrexp(P, d2, p, r);
+                sp += p; sr += r;
+            }
+            P.comp[(rep * N + a) * 2] = sp; P.comp[(rep * N + a) * 2 + 1] = sr;
+            se += fma(-P.eam_ecam, sqrt(sr), P.eam_ean * sp);
+        }
+        se = group_sum<32>(se, 0xffffffffu);
+        if (g == 0) P.en_tot[rep] = se;
+    } else {
+        double acc = 0.0;
+        for (int a = 0; a < N - 1; ++a) {
+            const double xa = gp[3 * a], ya = gp[3 * a + 1], za = gp[3 * a + 2];
+            for (int j = a + 1 + g; j < N; j += 32) {
+                double d2;
+                if (pbc) d2 = rhombic ? dist2_pbc<true>(bx, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2])
+                                      : dist2_pbc<false>(bx, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2]);
+                else { double dx = xa - gp[3 * j], dy = ya - gp[3 * j + 1], dz = za - gp[3 * j + 2]; d2 = fma(dz, dz, fma(dy, dy, dx * dx)); }
+                if (!npt || d2 <= rcut) acc += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT>(P, d2);
+            }
+        }
+        double e = group_sum<32>(acc, 0xffffffffu);
+        if (npt) {
+            const double l = lrc_even(P, rcut);
+            if (P.bc_kind == PTMC_BC_CUBIC) e = e + l;
+            else if (P.bc_kind == PTMC_BC_RHOMBIC) e = e + l * 3 / 4 * L / h;
+            else e = (L < h) ? e + l * L / h : e + l * (h * h) / (L * L);
+        }
+        if (g == 0) P.en_tot[rep] = e;
+    }
+}
+
+// Host-visible launchers (one per instantiation file).
+typedef void (*sweep_fn)(const DevParams, const i64, const i64, const int);
+
+}  // namespace ptmc

@@ -1,0 +1,66 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol the header declares,
+the ctypes mirror matches the header, and no compute entry point works without a GPU (no CPU fallback)."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+import ptmc_b200 as P
+from ptmc_b200 import abi
+from ptmc_b200.host import initial_arrays, sweep_config
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build_cuda()
+    return abi.load_library()
+
+
+def test_header_symbols_exported(lib):
+    header = (abi.PKG_DIR.parent / "include" / "ptmc_b200.h").read_text()
+    declared = set(re.findall(r"^PTMC_API [\w\s\*]+?\b(ptmc_\w+|forward)\(", header, flags=re.M))
+    assert declared == set(abi.SYMBOLS), declared ^ set(abi.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ptmc_abi_version() == abi.PTMC_ABI_VERSION
+
+
+def test_config_struct_matches_header():
+    # sizes the C compiler sees (computed by compiling a probe would need gcc + the header: do exactly that)
+    import subprocess, tempfile, pathlib
+    src = '#include "ptmc_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu\\n", sizeof(ptmc_config), sizeof(ptmc_runner_desc));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        p = pathlib.Path(d)
+        (p / "probe.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(abi.PKG_DIR.parent / "include"), str(p / "probe.c"), "-o", str(p / "probe")], check=True)
+        out = subprocess.run([str(p / "probe")], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == C.sizeof(abi.Config)
+    assert int(out[1]) == C.sizeof(abi.RunnerDesc)
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device failure path cannot be exercised")
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=4, cycles=5)
+    with pytest.raises(P.PtmcError) as e:
+        P.Engine(sweep_config(mcp, temp, start, pot, ens))
+    assert e.value.code == abi.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_argument_validation_precedes_device(lib):
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=4, cycles=5)
+    cfg = sweep_config(mcp, temp, start, pot, ens)
+    c = cfg.to_c()
+    c.abi_version = 99
+    h = C.c_void_p()
+    assert lib.ptmc_create(C.byref(c), C.byref(h)) == abi.ERR_ARG
+    assert b"abi_version" in lib.ptmc_last_error(None)
+    c = cfg.to_c()
+    c.ensemble = abi.ENS_NPT
+    c.n_volume_moves = 1
+    assert lib.ptmc_create(C.byref(c), C.byref(h)) == abi.ERR_ARG
+    assert b"SphericalBC cannot be used in an NPT ensemble" in lib.ptmc_last_error(None)

@@ -1,0 +1,203 @@
+"""Parity tests proper: the CUDA sweep (through the C ABI) against the CPU oracle on identical replayed
+streams.  Needs a B200: run with `-m gpu`."""
+import numpy as np
+import pytest
+
+import ptmc_b200 as P
+from ptmc_b200 import abi
+from ptmc_b200.engine import Engine, PtmcError
+from ptmc_b200.host import initial_arrays, sweep_config
+
+from parity import compare_traces, run_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("lanes", [0, 4, 8, 16, 32])
+def test_ne13_elj_nvt_replay(lanes):
+    # BASELINE C1 at the script's own 25 temperatures (examples/ne13.jl:82): 2 ladders, 60 cycles incl. one
+    # step-size adjustment (n_adjust=25) and two launches (chunks) so cursors/RNG/counters persist correctly.
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=25, cycles=60)
+    n_t = 25 if lanes < 32 else 16   # 25 x 32 lanes exceeds one CTA
+    if n_t != 25:
+        mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=n_t, cycles=60)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=50, eq_cycles=10, seed=1234,
+                        lanes=lanes, chunks=2, n_adjust=25)
+    worst = compare_traces(gpu, cpu)
+    assert gpu["trace"]["accepted"].mean() > 0.2
+    assert gpu["trace"]["exchange"][:, :, 0].sum() > 0          # some exchanges were attempted
+    if lanes:
+        assert gpu["lanes"] == lanes
+    print("ne13 lanes", lanes, "max |dE err|", worst)
+
+
+def test_ne55_elj_nvt_replay():
+    # BASELINE C2 geometry and ladder (scripts/ne55.jl), 3 ladders
+    mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=24, cycles=20)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=3, n_cycles=20, seed=99, n_adjust=10)
+    compare_traces(gpu, cpu)
+    assert gpu["lanes"] == 8
+
+
+def test_elj_odd_potential_replay():
+    # ELJPotential (odd powers, src/EnergyEvaluation.jl:923-932) on the Ne13 geometry
+    mcp, temp, start, _, ens = P.host.deck_ne13(n_traj=8, cycles=20)
+    pot = P.ELJPotential((-10.5097942564988, 0.0, 989.725135614556, 0.0, -101383.865938807))
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=20, seed=5)
+    compare_traces(gpu, cpu)
+
+
+def test_sphere_redraw_and_recentre():
+    # tight binding sphere + big steps: exercises the redraw loop and the recentre! at count == 50
+    # (src/MCMoves.jl:115-145, quirk 8)
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=6, cycles=30)
+    pos = start.positions
+    rmax = np.sqrt((pos ** 2).sum(axis=1).max())
+    tight = P.Config(pos, P.SphericalBC(radius=rmax * 1.02))
+    md = np.full((1, 6, 4), 0.1)
+    md[:, :, 0] = 6.0
+    gpu, cpu = run_pair(mcp, temp, tight, pot, ens, n_ladders=1, n_cycles=30, seed=11, max_displ=md)
+    compare_traces(gpu, cpu)
+
+
+def test_cu55_eam_replay():
+    # BASELINE C3 (scripts/cu55.jl): full new energy from the updated (phi, rho) components
+    mcp, temp, start, pot, ens = P.host.deck_cu55_eam(n_traj=28, cycles=10)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=10, seed=3, n_adjust=5)
+    compare_traces(gpu, cpu)
+
+
+def _small_pbc(bc_cls):
+    # 32-atom fcc block (2x2x2 cells x 4) of the neon lattice, cubic / rectangular / rhombic cell
+    a = 8.4
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
+    pos = np.array([(b + [i, j, k]) * a for i in range(2) for j in range(2) for k in range(2) for b in base])
+    L = 2 * a
+    if bc_cls is P.CubicBC:
+        bc = P.CubicBC(L)
+    elif bc_cls is P.RectangularBC:
+        bc = P.RectangularBC(L, L * 1.25)
+        pos = pos * [1, 1, 1.25]
+    else:
+        bc = P.RhombicBC(L, L)
+        pos = pos @ np.array([[1, 0, 0], [0.5, 3 ** 0.5 / 2, 0], [0, 0, 1]])
+    return P.Config(pos - pos.mean(axis=0) * 0, bc)
+
+
+@pytest.mark.parametrize("bc_cls", [P.CubicBC, P.RectangularBC, P.RhombicBC])
+def test_small_npt_replay(bc_cls):
+    start = _small_pbc(bc_cls)
+    mcp = P.MCParams(30, 6, 32, n_adjust=10)
+    temp = P.TempGrid(20.0, 40.0, 6)
+    pot = P.ELJPotentialEven(P.host.ELJ_NE_COEFF)
+    ens = P.NPT(32, 101325 * 3.398928944382626e-14, False)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=30, seed=21)
+    compare_traces(gpu, cpu, positions_exact=False)
+    assert gpu["trace"]["move_index"].max() == 33          # volume moves happened
+
+
+def test_pbc216_npt_replay():
+    # BASELINE C4 (scripts/pbc216.jl): 216 atoms, rhombic cell, 16 temperatures, fcc/hcp alternating
+    mcp, temp, start, pot, ens = P.host.deck_pbc216(n_traj=16, cycles=3)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=3, seed=8)
+    compare_traces(gpu, cpu, positions_exact=False)
+
+
+def test_periodic_nvt_replay():
+    start = _small_pbc(P.CubicBC)
+    mcp = P.MCParams(20, 4, 32)
+    gpu, cpu = run_pair(mcp, P.TempGrid(20.0, 40.0, 4), start, P.ELJPotentialEven(P.host.ELJ_NE_COEFF), P.NVT(32),
+                        n_ladders=1, n_cycles=20, seed=2)
+    compare_traces(gpu, cpu)
+
+
+def test_xoshiro_mode_matches_oracle_seeding():
+    # production RNG mode: device-side Xoshiro256++ seeded like Random.seed!(seed + k) -> same trajectory as
+    # the oracle stepping the same generator
+    from oracle import oracle
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=8, cycles=30)
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=4, seed=4321)
+    pos, box = initial_arrays(mcp, start, 4)
+    res = []
+    for cls in (Engine, oracle.OracleEngine):
+        eng = cls(cfg)
+        eng.upload_states(pos, box)
+        eng.seed(4321)
+        eng.set_hist_bounds(-0.01, 0.0)
+        eng.run_cycles(1, 30, True)
+        eng.sync()
+        res.append((eng.download_states(), eng.download_hist(), eng.get_rng_states()))
+        eng.close()
+    (sg, hg, rg), (sc, hc, rc) = res
+    assert np.array_equal(sg["pos"], sc["pos"]) and np.array_equal(sg["counters"], sc["counters"])
+    assert np.array_equal(hg, hc)
+    assert np.array_equal(rg[0], rc[0]) and np.array_equal(rg[1], rc[1])
+
+
+def test_energy_bookkeeping_at_full_size():
+    # size-independent property at BASELINE C2's full batch (4096 ladders x 24 temperatures): after a sweep
+    # the running en_tot of every replica equals the energy recomputed from its positions (the init kernel).
+    mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=24, cycles=5)
+    L = 4096
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=1)
+    pos, box = initial_arrays(mcp, start, L)
+    eng = Engine(cfg)
+    eng.upload_states(pos, box)
+    eng.run_cycles(1, 5, False)
+    eng.sync()
+    st = eng.download_states()
+    acc = st["counters"][:, :, abi.C_ATOM_TOT].sum() / (L * 24 * 55 * 5)
+    assert 0.2 < acc < 1.0
+    eng2 = Engine(cfg)
+    eng2.upload_states(st["pos"], st["box"])
+    e2 = eng2.download_states(("en_tot",))["en_tot"]
+    np.testing.assert_allclose(st["en_tot"], e2, rtol=1e-11)
+    r2 = (st["pos"] ** 2).sum(axis=-1)
+    assert (r2 <= box[..., :1] + 1e-9).all()                  # nobody left the binding sphere
+    assert not np.array_equal(st["pos"][0], st["pos"][1])      # ladders are independent streams
+    eng.close(); eng2.close()
+
+
+def test_error_behaviour():
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=4, cycles=5)
+    cfg = sweep_config(mcp, temp, start, pot, ens)
+    eng = Engine(cfg)
+    with pytest.raises(PtmcError) as e:
+        eng.run_cycles(1, 1, False)                           # before upload
+    assert e.value.code == abi.ERR_STATE
+    pos, box = initial_arrays(mcp, start, 1)
+    eng.upload_states(pos, box)
+    with pytest.raises(PtmcError) as e:
+        eng.run_cycles(1, 1, True)                            # sampling before set_hist_bounds
+    assert e.value.code == abi.ERR_STATE
+    eng.close()
+    with pytest.raises(PtmcError):                            # SphericalBC + NPT (src/Ensembles.jl:189)
+        Engine(sweep_config(mcp, temp, start, pot, P.NVT(13), lanes_per_replica=3))
+    # replay stream too short -> PTMC_ERR_REPLAY at sync
+    cfg = sweep_config(mcp, temp, start, pot, ens, rng_mode=abi.RNG_REPLAY)
+    eng = Engine(cfg)
+    eng.upload_states(pos, box)
+    eng.set_replay(np.zeros((1, 4, 8), dtype=np.uint64) + np.uint64(1 << 62), np.zeros((1, 8), dtype=np.uint64))
+    eng.run_cycles(1, 2, False)
+    with pytest.raises(PtmcError) as e:
+        eng.sync()
+    assert e.value.code == abi.ERR_REPLAY
+    eng.close()
+
+
+def test_forward_all_ones_kat():
+    # test/test_runner_forward.jl:44-75: all-ones parameters and inputs, nodes [88,20,20,1], acts [1,2,2,1],
+    # batch 2 -> 21 per atom
+    import ctypes as C
+    lib = abi.load_library()
+    nodes = np.array([88, 20, 20, 1], dtype=np.int32)
+    act = np.array([1, 2, 2, 1], dtype=np.int32)
+    npar = 88 * 20 + 20 + 20 * 20 + 20 + 20 + 1
+    params = np.ones(npar)
+    x = np.ones((2, 88))
+    e = np.zeros(2)
+    i32 = lambda v: C.byref(C.c_int32(v))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    lib.forward(dp(x), i32(88), i32(4), ip(nodes), i32(2), i32(npar), dp(params), ip(act), dp(e))
+    assert np.allclose(e, 21.0, rtol=1e-14)
