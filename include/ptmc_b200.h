@@ -60,9 +60,17 @@ typedef enum ptmc_bc_kind { PTMC_BC_SPHERICAL = 0, PTMC_BC_CUBIC = 1, PTMC_BC_RH
 /* src/Ensembles.jl:42 (NVT), :75 (NPT with separated_volume=false) */
 typedef enum ptmc_ens_kind { PTMC_ENS_NVT = 0, PTMC_ENS_NPT = 1 } ptmc_ens_kind;
 typedef enum ptmc_rng_mode {
-    PTMC_RNG_XOSHIRO = 0, /* Julia's default RNG: Xoshiro256++, rand()=(u>>11)*2^-53, rand(1:n)=Lemire  */
-    PTMC_RNG_REPLAY = 1   /* consume pre-drawn raw UInt64 draws from ptmc_set_replay (same derivations) */
+    PTMC_RNG_XOSHIRO = 0, /* Julia's default RNG as ONE sequential stream per slot: Xoshiro256++,
+                             rand()=(u>>11)*2^-53, rand(1:n)=Lemire.  Compatibility mode (slower kernel).  */
+    PTMC_RNG_REPLAY = 1,  /* consume pre-drawn raw UInt64 draws from ptmc_set_replay (same derivations)   */
+    PTMC_RNG_BATCH8 = 2   /* production mode: every slot owns PTMC_RNG_LANES Xoshiro256++ substreams that
+                             step together once per move ("batch"); position k of the batch comes from
+                             substream k: 0 index (1 + mulhi(u, n_steps)), 1-3 displacement x,y,z (1: volume
+                             move), 4 acceptance, 5-7 first out-of-sphere redraw; every further redraw steps a
+                             new batch and uses positions 0-2 (the acceptance uniform is position 4 of the
+                             latest batch).  Same generator and same uniform construction as mode 0.          */
 } ptmc_rng_mode;
+#define PTMC_RNG_LANES 8
 
 /* MCState counters (src/MCStates.jl:48-52), flattened in this order. */
 typedef enum ptmc_counter {
@@ -150,10 +158,14 @@ PTMC_API int ptmc_upload_counters(ptmc_handle* h, const int64_t* counters, const
 PTMC_API int ptmc_reset_counters(ptmc_handle* h);
 
 /* ---- random streams ------------------------------------------------------------------------------ */
-/* Julia-compatible seeding: slot stream of (ladder l, slot i) = Random.seed!(seed + l*n_traj + i),
- * ladder ("driver task") stream of ladder l = Random.seed!(seed + n_ladders*n_traj + l). */
+/* Julia-compatible seeding (Random.seed!(n): SHA-256 of the seed words).  With W = ptmc_rng_words()/4
+ * substreams per slot (1, or PTMC_RNG_LANES in BATCH8 mode): substream k of (ladder l, slot i) =
+ * Random.seed!(seed + (l*n_traj + i)*W + k), ladder ("driver task") stream of ladder l =
+ * Random.seed!(seed + n_ladders*n_traj*W + l). */
 PTMC_API int ptmc_seed(ptmc_handle* h, uint64_t seed);
-/* Raw Xoshiro256++ states: slot_states [n_ladders][n_traj][4], ladder_states [n_ladders][4]. */
+/* Number of UInt64 words of generator state per slot: 4 (XOSHIRO, REPLAY) or 4*PTMC_RNG_LANES (BATCH8). */
+PTMC_API int ptmc_rng_words(const ptmc_handle* h);
+/* Raw Xoshiro256++ states: slot_states [n_ladders][n_traj][ptmc_rng_words()], ladder_states [n_ladders][4]. */
 PTMC_API int ptmc_set_rng_states(ptmc_handle* h, const uint64_t* slot_states, const uint64_t* ladder_states);
 PTMC_API int ptmc_get_rng_states(ptmc_handle* h, uint64_t* slot_states, uint64_t* ladder_states);
 /* Replay mode: pre-drawn raw UInt64 draws. slot_draws [n_ladders][n_traj][slot_len] is consumed by

@@ -97,6 +97,10 @@ typedef struct orc_rng {
     const uint64_t* replay; /* non-NULL: consume pre-drawn raw draws instead of stepping s */
     int64_t pos, len;
     int exhausted;
+    /* PTMC_RNG_BATCH8 (include/ptmc_b200.h): PTMC_RNG_LANES substreams stepping together once per batch */
+    int batch_mode;
+    uint64_t sub[PTMC_RNG_LANES][4];
+    uint64_t buf[PTMC_RNG_LANES];
 } orc_rng;
 
 static uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
@@ -133,6 +137,12 @@ static int64_t rng_range(orc_rng* r, uint64_t n) {
     }
     return (int64_t)(m >> 64) + 1;
 }
+
+/* BATCH8 mode: step every substream once; position k of the batch is substream k's output */
+static void rng_batch_begin(orc_rng* r) {
+    for (int k = 0; k < PTMC_RNG_LANES; ++k) r->buf[k] = orc_xoshiro_next(r->sub[k]);
+}
+static double rng_batch_rand(const orc_rng* r, int k) { return (double)(r->buf[k] >> 11) * 0x1.0p-53; }
 
 /* exported thin wrappers for the KAT tests */
 double orc_rand_from_state(uint64_t s[4]) { return (double)(orc_xoshiro_next(s) >> 11) * 0x1.0p-53; }
@@ -361,10 +371,10 @@ static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
 
 /* ------------------------------------------------------------------------------------- moves -- */
 /* atom_displacement(pos, max_displacement, bc) src/MCMoves.jl:33-98 */
-static void displace(const ptmc_config* c, const double* pos, double dmax, const double* box, orc_rng* r, double* t) {
-    double dx = (rng_rand(r) - 0.5) * dmax;
-    double dy = (rng_rand(r) - 0.5) * dmax;
-    double dz = (rng_rand(r) - 0.5) * dmax;
+static void displace_u(const ptmc_config* c, const double* pos, double dmax, const double* box, const double* u, double* t) {
+    double dx = (u[0] - 0.5) * dmax;
+    double dy = (u[1] - 0.5) * dmax;
+    double dz = (u[2] - 0.5) * dmax;
     t[0] = pos[0] + dx; t[1] = pos[1] + dy; t[2] = pos[2] + dz;
     double L = box[0], h = box[1];
     switch (c->bc_kind) {
@@ -386,6 +396,19 @@ static void displace(const ptmc_config* c, const double* pos, double dmax, const
             t[0] -= sx; t[1] -= sy; t[2] -= sz;
         }
     }
+}
+
+/* sequential-stream form: draw order x, y, z (src/MCMoves.jl:35-37) */
+static void displace(const ptmc_config* c, const double* pos, double dmax, const double* box, orc_rng* r, double* t) {
+    double u[3];
+    u[0] = rng_rand(r); u[1] = rng_rand(r); u[2] = rng_rand(r);
+    displace_u(c, pos, dmax, box, u, t);
+}
+/* BATCH8 form: uniforms from positions k0..k0+2 of the current batch */
+static void displace_b(const ptmc_config* c, const double* pos, double dmax, const double* box, const orc_rng* r, int k0, double* t) {
+    double u[3];
+    u[0] = rng_batch_rand(r, k0); u[1] = rng_batch_rand(r, k0 + 1); u[2] = rng_batch_rand(r, k0 + 2);
+    displace_u(c, pos, dmax, box, u, t);
 }
 
 /* recentre! src/Configurations.jl:79-85 (mean = sum/n, sequential) */
@@ -410,7 +433,14 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
     orc_cfgside* s = st->c;
     const int n = c->n_atoms;
     const int npt = c->ensemble == PTMC_ENS_NPT;
-    int index = (int)rng_range(&st->rng, (uint64_t)n_steps_of(c)); /* :145 */
+    const int bm = st->rng.batch_mode;
+    int index;
+    if (bm) {   /* BATCH8 draw schedule, see ptmc_rng_mode in include/ptmc_b200.h */
+        rng_batch_begin(&st->rng);
+        index = (int)(((__uint128_t)st->rng.buf[0] * (uint64_t)n_steps_of(c)) >> 64) + 1;
+    } else {
+        index = (int)rng_range(&st->rng, (uint64_t)n_steps_of(c)); /* :145 */
+    }
     double trial[3];
     int accepted = 0;
     if (index <= c->n_atom_moves) {
@@ -418,19 +448,27 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
         /* generate_move! -> atom_displacement(mc_state) src/MCMoves.jl:100-113 / :115-145 */
         if (c->bc_kind == PTMC_BC_SPHERICAL) {
             double count = 0.0;
-            displace(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, trial);
+            int redraws = 0;
+            if (bm) displace_b(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, 1, trial);
+            else displace(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, trial);
             while (trial[0] * trial[0] + trial[1] * trial[1] + trial[2] * trial[2] > s->box[0]) { /* check_boundary */
                 count += 1;
                 if (count == 50) {
                     recentre(s->pos, n);
                 } else {
-                    displace(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, trial);
+                    if (bm) {
+                        if (++redraws == 1) displace_b(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, 5, trial);
+                        else { rng_batch_begin(&st->rng); displace_b(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, 0, trial); }
+                    } else {
+                        displace(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, trial);
+                    }
                     if (count == 100) return PTMC_ERR_SPHERE;
                 }
                 if (st->rng.exhausted) return PTMC_ERR_REPLAY;
             }
         } else {
-            displace(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, trial);
+            if (bm) displace_b(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, 1, trial);
+            else displace(c, s->pos + 3 * i, st->max_displ[0], s->box, &st->rng, trial);
         }
         for (int j = 0; j < n; ++j) st->new_d2[j] = orc_distance2(c->bc_kind, trial, s->pos + 3 * j, s->box[0], s->box[1]);
         st->new_d2[i] = 0.0;
@@ -456,7 +494,7 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
         /* acc_test! src/MCRun.jl:122-132 */
         double de = st->new_en - s->en_tot;
         double p = metropolis(de, st->beta);
-        double u = rng_rand(&st->rng);
+        double u = bm ? rng_batch_rand(&st->rng, 4) : rng_rand(&st->rng);
         if (tr_i) { *tr_i = index; *tr_de = de; }
         if (p >= u) {
             /* swap_atom_config! src/swap_config.jl:40-51 */
@@ -469,7 +507,8 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
         }
     } else {
         /* volume_change_uniform src/MCMoves.jl:277-287, volume_change_xyz :169-177 */
-        double scale = pow(exp((rng_rand(&st->rng) - 0.5) * st->max_displ[1]), 1.0 / 3.0);
+        double uv = bm ? rng_batch_rand(&st->rng, 1) : rng_rand(&st->rng);
+        double scale = pow(exp((uv - 0.5) * st->max_displ[1]), 1.0 / 3.0);
         if (s->box[0] >= st->max_boxlength && scale > 1.0) scale = 1.0;
         for (int k = 0; k < 3 * n; ++k) s->trial_pos[k] = scale * s->pos[k];
         s->trial_box[0] = scale * s->box[0];
@@ -486,7 +525,7 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
         double delta_h = de + c->pressure * (vc - vu);
         double p = exp(-delta_h * st->beta + c->n_atoms * log(vc / vu));
         p = p > 1 ? 1.0 : p;
-        double u = rng_rand(&st->rng);
+        double u = bm ? rng_batch_rand(&st->rng, 4) : rng_rand(&st->rng);
         if (tr_i) { *tr_i = index; *tr_de = de; }
         if (p >= u) {
             /* swap_config_v! src/swap_config.jl:113-140 (xy_or_z == 0) */
@@ -631,6 +670,7 @@ static int mc_cycle(orc_handle* H, int64_t lad, int64_t idx, int sample, int64_t
 /* =========================================================================== exported handle API == */
 static void* xcalloc(size_t n, size_t sz) { void* p = calloc(n ? n : 1, sz); if (!p) { perror("oracle calloc"); abort(); } return p; }
 
+int orc_seed(orc_handle* H, uint64_t seed);
 orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER) return NULL; /* handled by runner_oracle.c */
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
@@ -663,6 +703,7 @@ orc_handle* orc_create(const ptmc_config* cfg) {
     if (npt) H->ev_hist = (double*)xcalloc((size_t)H->n_rep * nb2 * nb2, sizeof(double));
     else H->en_hist = (double*)xcalloc((size_t)H->n_rep * nb2, sizeof(double));
     H->n_threads = 1;
+    if (cfg->rng_mode != PTMC_RNG_REPLAY) orc_seed(H, cfg->seed);   /* like ptmc_create */
     return H;
 }
 
@@ -714,21 +755,42 @@ int orc_reset_counters(orc_handle* H) {
     return 0;
 }
 
-int orc_seed(orc_handle* H, uint64_t seed) {
-    const int nt = H->cfg.n_traj;
-    for (int64_t r = 0; r < H->n_rep; ++r) { memset(&H->st[r].rng, 0, sizeof(orc_rng)); orc_julia_seed(seed + (uint64_t)r, H->st[r].rng.s); }
-    for (int64_t l = 0; l < H->cfg.n_ladders; ++l) { memset(&H->lrng[l], 0, sizeof(orc_rng)); orc_julia_seed(seed + (uint64_t)(H->cfg.n_ladders * nt) + (uint64_t)l, H->lrng[l].s); }
-    return 0;
-}
+/* words of generator state per slot (ptmc_rng_words) */
+int orc_rng_words(const orc_handle* H) { return H->cfg.rng_mode == PTMC_RNG_BATCH8 ? 4 * PTMC_RNG_LANES : 4; }
+
 int orc_set_rng_states(orc_handle* H, const uint64_t* slot_states, const uint64_t* ladder_states) {
-    for (int64_t r = 0; r < H->n_rep; ++r) { memset(&H->st[r].rng, 0, sizeof(orc_rng)); memcpy(H->st[r].rng.s, slot_states + 4 * r, 32); }
+    const int batch = H->cfg.rng_mode == PTMC_RNG_BATCH8;
+    const int w = orc_rng_words(H);
+    for (int64_t r = 0; r < H->n_rep; ++r) {
+        orc_rng* g = &H->st[r].rng;
+        memset(g, 0, sizeof *g);
+        g->batch_mode = batch;
+        if (batch) memcpy(g->sub, slot_states + (size_t)w * r, sizeof g->sub);
+        else memcpy(g->s, slot_states + 4 * r, 32);
+    }
     for (int64_t l = 0; l < H->cfg.n_ladders; ++l) { memset(&H->lrng[l], 0, sizeof(orc_rng)); memcpy(H->lrng[l].s, ladder_states + 4 * l, 32); }
     return 0;
 }
 int orc_get_rng_states(orc_handle* H, uint64_t* slot_states, uint64_t* ladder_states) {
-    for (int64_t r = 0; r < H->n_rep; ++r) memcpy(slot_states + 4 * r, H->st[r].rng.s, 32);
+    const int batch = H->cfg.rng_mode == PTMC_RNG_BATCH8;
+    const int w = orc_rng_words(H);
+    for (int64_t r = 0; r < H->n_rep; ++r) {
+        if (batch) memcpy(slot_states + (size_t)w * r, H->st[r].rng.sub, sizeof H->st[r].rng.sub);
+        else memcpy(slot_states + 4 * r, H->st[r].rng.s, 32);
+    }
     for (int64_t l = 0; l < H->cfg.n_ladders; ++l) memcpy(ladder_states + 4 * l, H->lrng[l].s, 32);
     return 0;
+}
+/* seeding rule of ptmc_seed (include/ptmc_b200.h) */
+int orc_seed(orc_handle* H, uint64_t seed) {
+    const int w = orc_rng_words(H) / 4;
+    uint64_t* s = (uint64_t*)xcalloc((size_t)H->n_rep * 4 * w, 8);
+    uint64_t* l = (uint64_t*)xcalloc((size_t)H->cfg.n_ladders * 4, 8);
+    for (int64_t r = 0; r < H->n_rep * w; ++r) orc_julia_seed(seed + (uint64_t)r, s + 4 * r);
+    for (int64_t k = 0; k < H->cfg.n_ladders; ++k) orc_julia_seed(seed + (uint64_t)(H->n_rep * w) + (uint64_t)k, l + 4 * k);
+    int rc = orc_set_rng_states(H, s, l);
+    free(s); free(l);
+    return rc;
 }
 /* the caller keeps the draw buffers alive */
 int orc_set_replay(orc_handle* H, const uint64_t* slot_draws, int64_t slot_len, const uint64_t* ladder_draws, int64_t ladder_len) {

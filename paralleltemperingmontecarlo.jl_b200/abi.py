@@ -17,7 +17,8 @@ PTMC_NCOUNT = 10
 POT_ELJ, POT_ELJ_EVEN, POT_EAM, POT_RUNNER = 0, 1, 2, 3
 BC_SPHERICAL, BC_CUBIC, BC_RHOMBIC, BC_RECTANGULAR = 0, 1, 2, 3
 ENS_NVT, ENS_NPT = 0, 1
-RNG_XOSHIRO, RNG_REPLAY = 0, 1
+RNG_XOSHIRO, RNG_REPLAY, RNG_BATCH8 = 0, 1, 2
+RNG_LANES = 8
 
 (C_ATOM_TOT, C_ATOM_ADJ, C_VOL_TOT, C_VOL_ADJ, C_VOLXY_TOT, C_VOLXY_ADJ, C_VOLZ_TOT, C_VOLZ_ADJ,
  C_EXC_ATT, C_EXC_ACC) = range(10)
@@ -73,6 +74,7 @@ SYMBOLS = {
     "ptmc_upload_counters": (C.c_int, [_vp, _i64p, _dp]),
     "ptmc_reset_counters": (C.c_int, [_vp]),
     "ptmc_seed": (C.c_int, [_vp, C.c_uint64]),
+    "ptmc_rng_words": (C.c_int, [_vp]),
     "ptmc_set_rng_states": (C.c_int, [_vp, _u64p, _u64p]),
     "ptmc_get_rng_states": (C.c_int, [_vp, _u64p, _u64p]),
     "ptmc_set_replay": (C.c_int, [_vp, _u64p, C.c_int64, _u64p, C.c_int64]),
@@ -102,11 +104,18 @@ def bind(lib, symbols=SYMBOLS, prefix_from="ptmc_", prefix_to="ptmc_"):
 
 
 def load_library(path: pathlib.Path | None = None):
-    """Load libptmc_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if missing."""
+    """Load libptmc_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if missing.
+    PTMC_B200_LIB selects another build of the same library (kernel tuning experiments)."""
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = pathlib.Path(path) if path else LIB_PATH
+    import os
+    if path is None and os.environ.get("PTMC_B200_LIB"):
+        p = pathlib.Path(os.environ["PTMC_B200_LIB"])
+        if not p.is_absolute():
+            p = LIB_PATH.parent / p
+    else:
+        p = pathlib.Path(path) if path else LIB_PATH
     if not p.exists():
         raise RuntimeError(
             f"{p} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'). "

@@ -11,10 +11,10 @@
 #include "sweep_kernel.cuh"
 
 namespace ptmc {
-sweep_fn sweep_table_g4(int pot, int geom, int dbg);
-sweep_fn sweep_table_g8(int pot, int geom, int dbg);
-sweep_fn sweep_table_g16(int pot, int geom, int dbg);
-sweep_fn sweep_table_g32(int pot, int geom, int dbg);
+sweep_fn sweep_table_g4(int pot, int geom, int dbg, int niter, int n_coeff);
+sweep_fn sweep_table_g8(int pot, int geom, int dbg, int niter, int n_coeff);
+sweep_fn sweep_table_g16(int pot, int geom, int dbg, int niter, int n_coeff);
+sweep_fn sweep_table_g32(int pot, int geom, int dbg, int niter, int n_coeff);
 int sweep_max_threads(int G);
 void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
@@ -122,13 +122,16 @@ static void julia_seed(uint64_t seed, uint64_t s[4]) {
 }
 
 static sweep_fn pick_kernel(const ptmc_handle* h, int dbg) {
+    const int niter = h->P.n_pad / h->G, nc = h->cfg.n_coeff;
     switch (h->G) {
-        case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg);
-        case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg);
-        case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg);
-        default: return sweep_table_g32(h->cfg.pot_kind, h->geom, dbg);
+        case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg, niter, nc);
+        case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg, niter, nc);
+        case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg, niter, nc);
+        default: return sweep_table_g32(h->cfg.pot_kind, h->geom, dbg, niter, nc);
     }
 }
+// words of generator state per slot
+static int rng_words(const ptmc_handle* h) { return h->cfg.rng_mode == PTMC_RNG_BATCH8 ? 4 * PTMC_RNG_LANES : 4; }
 
 // lanes per replica: enough lanes to keep the per-move serial chain short, few enough that the redundant
 // per-group scalar work (RNG, Metropolis) stays small and many replicas are resident.
@@ -162,6 +165,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     if (!c->betas) return fail(nullptr, PTMC_ERR_ARG, "betas is null");
     if (c->n_atom_moves < 1 || c->n_atom_moves > c->n_atoms) return fail(nullptr, PTMC_ERR_ARG, "n_atom_moves must be in 1..n_atoms");
     if (c->n_adjust < 1 || c->mc_sample < 1 || c->n_bin < 2) return fail(nullptr, PTMC_ERR_ARG, "n_adjust, mc_sample >= 1 and n_bin >= 2 required");
+    if (c->rng_mode < PTMC_RNG_XOSHIRO || c->rng_mode > PTMC_RNG_BATCH8) return fail(nullptr, PTMC_ERR_ARG, "unknown rng_mode %d", c->rng_mode);
     const bool npt = c->ensemble == PTMC_ENS_NPT;
     const bool sphere = c->bc_kind == PTMC_BC_SPHERICAL;
     if (c->ensemble != PTMC_ENS_NVT && !npt) return fail(nullptr, PTMC_ERR_ARG, "unknown ensemble %d", c->ensemble);
@@ -229,7 +233,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     if ((rc = dev_alloc(h, &P.pos, R * N * 3)) || (rc = dev_alloc(h, &P.box, R * 2)) || (rc = dev_alloc(h, &P.en_tot, R)) ||
         (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
         (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
-        (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||
+        (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4 * PTMC_RNG_LANES)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||
         (rc = dev_alloc(h, &P.slot_cursor, R)) || (rc = dev_alloc(h, &P.ladder_cursor, L)) ||
         (rc = dev_alloc(h, &en_min, L)) || (rc = dev_alloc(h, &en_max, L)) || (rc = dev_alloc(h, &v_min, L)) || (rc = dev_alloc(h, &v_max, L)) ||
         (rc = dev_alloc(h, &P.hist, L * h->hist_per_ladder)) || (rc = dev_alloc(h, &h->d_reduced, h->hist_per_ladder)) ||
@@ -247,7 +251,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             return bail(fail(h, PTMC_ERR_CUDA, "cudaFuncSetAttribute(%zu B smem) failed: %s", h->smem, cudaGetErrorString(cudaGetLastError())));
     }
     *out = h;
-    if (c->rng_mode == PTMC_RNG_XOSHIRO) { int r2 = ptmc_seed(h, c->seed); if (r2) { *out = nullptr; return bail(r2); } }
+    if (c->rng_mode != PTMC_RNG_REPLAY) { int r2 = ptmc_seed(h, c->seed); if (r2) { *out = nullptr; return bail(r2); } }
     return PTMC_OK;
 }
 
@@ -306,7 +310,7 @@ extern "C" PTMC_API int ptmc_reset_counters(ptmc_handle* h) {
 extern "C" PTMC_API int ptmc_set_rng_states(ptmc_handle* h, const uint64_t* slot_states, const uint64_t* ladder_states) {
     if (!h || !slot_states || !ladder_states) return h ? fail(h, PTMC_ERR_ARG, "null rng states") : PTMC_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaMemcpyAsync(h->P.slot_rng, slot_states, sizeof(u64) * (size_t)h->n_rep * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->P.slot_rng, slot_states, sizeof(u64) * (size_t)h->n_rep * rng_words(h), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->P.ladder_rng, ladder_states, sizeof(u64) * (size_t)h->cfg.n_ladders * 4, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->seeded = true;
@@ -315,21 +319,23 @@ extern "C" PTMC_API int ptmc_set_rng_states(ptmc_handle* h, const uint64_t* slot
 extern "C" PTMC_API int ptmc_get_rng_states(ptmc_handle* h, uint64_t* slot_states, uint64_t* ladder_states) {
     if (!h) return PTMC_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
-    if (slot_states) CU(h, cudaMemcpyAsync(slot_states, h->P.slot_rng, sizeof(u64) * (size_t)h->n_rep * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (slot_states) CU(h, cudaMemcpyAsync(slot_states, h->P.slot_rng, sizeof(u64) * (size_t)h->n_rep * rng_words(h), cudaMemcpyDeviceToHost, h->stream));
     if (ladder_states) CU(h, cudaMemcpyAsync(ladder_states, h->P.ladder_rng, sizeof(u64) * (size_t)h->cfg.n_ladders * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return PTMC_OK;
 }
 extern "C" PTMC_API int ptmc_seed(ptmc_handle* h, uint64_t seed) {
     if (!h) return PTMC_ERR_ARG;
-    const size_t R = (size_t)h->n_rep, L = (size_t)h->cfg.n_ladders;
+    const size_t R = (size_t)h->n_rep * (rng_words(h) / 4), L = (size_t)h->cfg.n_ladders;   // R substreams in all
     std::vector<uint64_t> s(R * 4), l(L * 4);
     for (size_t r = 0; r < R; ++r) julia_seed(seed + r, &s[4 * r]);
     for (size_t k = 0; k < L; ++k) julia_seed(seed + R + k, &l[4 * k]);
     return ptmc_set_rng_states(h, s.data(), l.data());
 }
+extern "C" PTMC_API int ptmc_rng_words(const ptmc_handle* h) { return h ? rng_words(h) : 0; }
 extern "C" PTMC_API int ptmc_set_replay(ptmc_handle* h, const uint64_t* slot_draws, int64_t slot_len, const uint64_t* ladder_draws, int64_t ladder_len) {
     if (!h || !slot_draws || !ladder_draws || slot_len < 0 || ladder_len < 0) return h ? fail(h, PTMC_ERR_ARG, "bad replay streams") : PTMC_ERR_ARG;
+    if (h->cfg.rng_mode != PTMC_RNG_REPLAY) return fail(h, PTMC_ERR_STATE, "ptmc_set_replay needs a handle created with rng_mode = PTMC_RNG_REPLAY");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->d_slot_draws) { cudaFree(h->d_slot_draws); h->d_slot_draws = nullptr; }
@@ -382,7 +388,8 @@ extern "C" PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64
     const bool tracing = h->trace_cap > 0;
     if (tracing && h->trace_n + n_cycles > h->trace_cap) return fail(h, PTMC_ERR_ARG, "trace capacity %lld exceeded", (long long)h->trace_cap);
     CU(h, cudaSetDevice(h->device));
-    const int dbg = (tracing || h->P.replay) ? 1 : 0;
+    if (tracing && h->cfg.rng_mode == PTMC_RNG_BATCH8) return fail(h, PTMC_ERR_STATE, "tracing needs rng_mode XOSHIRO or REPLAY (sequential-stream kernels)");
+    const int dbg = h->cfg.rng_mode != PTMC_RNG_BATCH8 ? 1 : 0;
     sweep_fn f = pick_kernel(h, dbg);
     // per-launch acceptance counters are 32-bit: keep moves per launch below 2^31
     const i64 max_chunk = std::max<i64>(1, (i64)0x7fffffff / std::max<i64>(1, h->n_steps));

@@ -103,6 +103,36 @@ struct Stream {
     }
 };
 
+// PTMC_RNG_BATCH8 (include/ptmc_b200.h): the slot owns 8 substreams; lane g of the group steps substream
+// (g & 7) (G = 4: substreams g and g + 4) once per batch and the lanes read position k with a shuffle, so a
+// draw costs two SHFL instead of a redundant ~25-instruction generator step in every lane.
+template <int G>
+struct BatchRng {
+    Xo a, b;          // b: second substream of the lane, G == 4 only
+    u64 bufa, bufb;
+    __device__ __forceinline__ void load(const u64* st, int g) {
+        const u64* p = st + 4 * (g & 7);
+        a.s0 = p[0]; a.s1 = p[1]; a.s2 = p[2]; a.s3 = p[3];
+        if (G == 4) { p = st + 4 * (g + 4); b.s0 = p[0]; b.s1 = p[1]; b.s2 = p[2]; b.s3 = p[3]; }
+        bufa = 0; bufb = 0;
+    }
+    __device__ __forceinline__ void store(u64* st, int g) const {
+        if (g < 8) { u64* p = st + 4 * g; p[0] = a.s0; p[1] = a.s1; p[2] = a.s2; p[3] = a.s3; }
+        if (G == 4) { u64* p = st + 4 * (g + 4); p[0] = b.s0; p[1] = b.s1; p[2] = b.s2; p[3] = b.s3; }
+    }
+    __device__ __forceinline__ void begin() {
+        bufa = xo_next(a);
+        if (G == 4) bufb = xo_next(b);
+    }
+    template <int K>
+    __device__ __forceinline__ u64 raw(unsigned mask) const {
+        if (G == 4) return __shfl_sync(mask, K < 4 ? bufa : bufb, K & 3, 4);
+        return __shfl_sync(mask, bufa, K, G);
+    }
+    template <int K>
+    __device__ __forceinline__ double rand(unsigned mask) const { return (double)(raw<K>(mask) >> 11) * 0x1.0p-53; }
+};
+
 // ----------------------------------------------------------------------------------- group reduction --
 template <int G>
 __device__ __forceinline__ double group_sum(double v, unsigned mask) {
@@ -137,11 +167,12 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 // -------------------------------------------------------------------------------------- pair energy --
 // dimer_energy(::ELJPotentialEven) src/EnergyEvaluation.jl:934-942: sum_i c_i r^-(4+2i) = x^3 * Horner(x),
 // x = 1/r2.  Same polynomial, one reciprocal instead of 1+K divisions (differs at the 1e-16 level).
+template <int NC>
 __device__ __forceinline__ double elj_even(const DevParams& P, double r2) {
     double x = rcp_pos(r2);
     double x3 = x * x * x;
     double p;
-    if (P.n_coeff == 6) {
+    if (NC == 6) {
         p = P.coeff[5];
         p = fma(p, x, P.coeff[4]); p = fma(p, x, P.coeff[3]); p = fma(p, x, P.coeff[2]);
         p = fma(p, x, P.coeff[1]); p = fma(p, x, P.coeff[0]);
@@ -160,9 +191,10 @@ __device__ __forceinline__ double elj_odd(const DevParams& P, double r2) {
     for (int k = P.n_coeff - 2; k >= 0; --k) p = fma(p, y, P.coeff[k]);
     return p * y6;
 }
-template <int POT>
+// NC = 6: the six-coefficient form of every BASELINE script, fully unrolled; NC = 0: runtime n_coeff
+template <int POT, int NC = 0>
 __device__ __forceinline__ double pair_energy(const DevParams& P, double r2) {
-    return POT == PTMC_POT_ELJ ? elj_odd(P, r2) : elj_even(P, r2);
+    return POT == PTMC_POT_ELJ ? elj_odd(P, r2) : elj_even<NC>(P, r2);
 }
 // invrexp src/EnergyEvaluation.jl:1088-1095: (r^-n, r^-m) = (exp(-(n/2) log r2), exp(-(m/2) log r2)); r2 > 0.
 __device__ __forceinline__ void eam_invrexp(const DevParams& P, double r2, double& phi, double& rho) {

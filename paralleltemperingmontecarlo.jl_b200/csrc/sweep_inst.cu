@@ -10,12 +10,12 @@
 
 namespace ptmc {
 
-// pot: ptmc_pot_kind (ELJ, ELJ_EVEN, EAM); geom: Geom; dbg: replay/trace build
-sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg) {
+// Generic kernels (runtime pair-loop trip count and coefficient count), one per potential / geometry / debug.
+static sweep_fn generic_kernel(int pot, int geom, int dbg) {
     constexpr int G = PTMC_G;
-#define PTMC_PICK(POT, GEOM)                                                             \
-    if (pot == POT && geom == GEOM)                                                      \
-        return dbg ? (sweep_fn)sweep_kernel<G, POT, GEOM, true> : (sweep_fn)sweep_kernel<G, POT, GEOM, false>;
+#define PTMC_PICK(POT, GEOM)                                                                   \
+    if (pot == POT && geom == GEOM)                                                            \
+        return dbg ? (sweep_fn)sweep_kernel<G, POT, GEOM, true, 0, 0> : (sweep_fn)sweep_kernel<G, POT, GEOM, false, 0, 0>;
     PTMC_PICK(PTMC_POT_ELJ_EVEN, GEOM_SPHERE)
     PTMC_PICK(PTMC_POT_ELJ_EVEN, GEOM_PBC)
     PTMC_PICK(PTMC_POT_ELJ, GEOM_SPHERE)
@@ -23,6 +23,28 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg) {
     PTMC_PICK(PTMC_POT_EAM, GEOM_SPHERE)
 #undef PTMC_PICK
     return nullptr;
+}
+
+// Specialised production kernels of the headline family (ELJPotentialEven with 6 coefficients, SphericalBC,
+// BATCH8 streams): pair loop fully unrolled for ceil(n_atoms / G) = 1..8.
+static sweep_fn special_kernel(int niter) {
+    constexpr int G = PTMC_G;
+    switch (niter) {
+#define PTMC_SP(K) case K: return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_SPHERE, false, K, 6>;
+        PTMC_SP(1) PTMC_SP(2) PTMC_SP(3) PTMC_SP(4) PTMC_SP(5) PTMC_SP(6) PTMC_SP(7) PTMC_SP(8)
+#undef PTMC_SP
+        default: return nullptr;
+    }
+}
+
+// pot: ptmc_pot_kind (ELJ, ELJ_EVEN, EAM); geom: Geom; dbg: sequential-stream / replay / trace build;
+// niter = n_pad / G; n_coeff: number of ELJ coefficients
+sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff) {
+    if (!dbg && pot == PTMC_POT_ELJ_EVEN && geom == GEOM_SPHERE && n_coeff == 6) {
+        sweep_fn f = special_kernel(niter);
+        if (f) return f;
+    }
+    return generic_kernel(pot, geom, dbg);
 }
 
 }  // namespace ptmc

@@ -45,13 +45,18 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     return s;
 }
 
-template <int G, int POT, int GEOM, bool DBG>
+// DBG   : sequential slot stream (Julia-compatible XOSHIRO mode, or REPLAY) + optional trace.  !DBG: BATCH8.
+// NITER : compile-time ceil(n_atoms / G) of the pair loop (n_pad = NITER * G), 0 = runtime trip count.
+// NC    : compile-time number of ELJ coefficients (6), 0 = runtime.
+template <int G, int POT, int GEOM, bool DBG, int NITER, int NC>
 __global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
 sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
     extern __shared__ double sm[];
     constexpr bool EAM = (POT == PTMC_POT_EAM);
     constexpr bool PBC = (GEOM == GEOM_PBC);
-    const int T = P.n_traj, N = P.n_atoms, NP = P.n_pad;
+    constexpr bool BATCH = !DBG;
+    const int T = P.n_traj, N = P.n_atoms;
+    const int NP = NITER ? NITER * G : P.n_pad;
     const int lad = blockIdx.x;
     const int tid = threadIdx.x;
     const int slot = tid / G, g = tid & (G - 1);
@@ -92,7 +97,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
         }
     }
     // slot-side registers (identical in every lane of the group)
-    Stream<DBG> S;
+    Stream<DBG> S;      // sequential stream (DBG kernels)
+    BatchRng<G> B;      // BATCH8 substreams (production kernels)
     double beta = 0, dmax = 0, vmax = 0, max_boxl = 0;
     int n_acc_atom = 0, n_adj_atom = 0, n_acc_vol = 0, n_adj_vol = 0;   // this launch / since last adjustment
     if (active) {
@@ -104,10 +110,12 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
             max_boxl = P.max_boxlength[rep];
             n_adj_vol = (int)P.counters[rep * PTMC_NCOUNT + PTMC_C_VOL_ADJ];
         }
-        S.r.s0 = P.slot_rng[rep * 4]; S.r.s1 = P.slot_rng[rep * 4 + 1];
-        S.r.s2 = P.slot_rng[rep * 4 + 2]; S.r.s3 = P.slot_rng[rep * 4 + 3];
         S.draws = nullptr; S.pos = 0; S.len = 0; S.exhausted = 0;
-        if (DBG) {
+        if (BATCH) {
+            B.load(P.slot_rng + rep * (4 * PTMC_RNG_LANES), g);
+        } else {
+            S.r.s0 = P.slot_rng[rep * 4]; S.r.s1 = P.slot_rng[rep * 4 + 1];
+            S.r.s2 = P.slot_rng[rep * 4 + 2]; S.r.s3 = P.slot_rng[rep * 4 + 3];
             if (P.replay) { S.draws = P.slot_draws + rep * P.slot_len; S.len = P.slot_len; S.pos = P.slot_cursor[rep]; }
         }
     }
@@ -138,18 +146,27 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
             const double R2 = boxL;   // spherical: box[0] = radius^2
 
             for (int step = 0; step < P.n_steps; ++step) {
-                const int index = S.range((u64)P.n_steps);          // rand(1:N) src/MCRun.jl:145
+                int index;                                          // rand(1:N) src/MCRun.jl:145
+                if (BATCH) { B.begin(); index = (int)__umul64hi(B.template raw<0>(gmask), (u64)P.n_steps) + 1; }
+                else index = S.range((u64)P.n_steps);
                 double de = 0.0;
                 bool acc = false;
                 if (!PBC || index <= P.n_atom_moves) {
                     // ------------------------------------------------ atom_displacement src/MCMoves.jl:33-145
                     const int i = index - 1;
                     double xi = X[i], yi = Y[i], zi = Z[i];
-                    double tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
-                    double ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
-                    double tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+                    double tx, ty, tz;
+                    if (BATCH) {
+                        tx = xadd(xi, xmul(xsub(B.template rand<1>(gmask), 0.5), dmax));
+                        ty = xadd(yi, xmul(xsub(B.template rand<2>(gmask), 0.5), dmax));
+                        tz = xadd(zi, xmul(xsub(B.template rand<3>(gmask), 0.5), dmax));
+                    } else {
+                        tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
+                        ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
+                        tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+                    }
                     if (!PBC) {
-                        int count = 0;
+                        int count = 0, redraws = 0;
                         while (xadd(xadd(xmul(tx, tx), xmul(ty, ty)), xmul(tz, tz)) > R2) {   // check_boundary
                             ++count;
                             if (count == 50) {
@@ -165,9 +182,22 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                                 __syncwarp(gmask);
                                 xi = X[i]; yi = Y[i]; zi = Z[i];
                             } else {
-                                tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
-                                ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
-                                tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+                                if (BATCH) {
+                                    if (++redraws == 1) {
+                                        tx = xadd(xi, xmul(xsub(B.template rand<5>(gmask), 0.5), dmax));
+                                        ty = xadd(yi, xmul(xsub(B.template rand<6>(gmask), 0.5), dmax));
+                                        tz = xadd(zi, xmul(xsub(B.template rand<7>(gmask), 0.5), dmax));
+                                    } else {
+                                        B.begin();
+                                        tx = xadd(xi, xmul(xsub(B.template rand<0>(gmask), 0.5), dmax));
+                                        ty = xadd(yi, xmul(xsub(B.template rand<1>(gmask), 0.5), dmax));
+                                        tz = xadd(zi, xmul(xsub(B.template rand<2>(gmask), 0.5), dmax));
+                                    }
+                                } else {
+                                    tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
+                                    ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
+                                    tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+                                }
                                 if (count == 100) { err = PTMC_ERR_SPHERE; break; }
                             }
                             if (DBG) { if (S.exhausted) break; }
@@ -195,9 +225,10 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                         // dimer_energy_update! :804-821: sum_j e(new_ij) - e(old_ij); the old row is recomputed
                         // from the positions instead of being read from a stored dist2_mat.
                         double accd = 0.0;
-#pragma unroll 2
-                        for (int j = g; j < NP; j += G) {
-                            const double xj = X[j], yj = Y[j], zj = Z[j];
+                        const double* Xg = X + g;
+                        auto pair_term = [&](int k) {
+                            const int j = g + k * G;
+                            const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
                             double d2n, d2o;
                             if (PBC) {
                                 if (rhombic) { d2n = dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj); }
@@ -208,13 +239,21 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                                 double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
                                 d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
                             }
-                            const bool valid = (j != i) && (j < N);
-                            d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;   // identical inputs -> exact 0
-                            double en_j = pair_energy<POT>(P, d2n), eo_j = pair_energy<POT>(P, d2o);
+                            double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
                             if (PBC) {
                                 if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }
                             }
-                            accd += en_j - eo_j;
+                            // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
+                            const bool valid = (j != i) && (j < N);
+                            accd += valid ? (en_j - eo_j) : 0.0;
+                        };
+                        if (NITER) {
+#pragma unroll
+                            for (int k = 0; k < NITER; ++k) pair_term(k);
+                        } else {
+                            const int nk = NP / G;
+#pragma unroll 2
+                            for (int k = 0; k < nk; ++k) pair_term(k);
                         }
                         const double delta_en = group_sum<G>(accd, gmask);
                         new_en = xadd(delta_en, en);
@@ -247,7 +286,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     }
                     // ------------------------------------------------------------ acc_test! src/MCRun.jl:122-132
                     de = xsub(new_en, en);
-                    const double u = S.rand();
+                    const double u = BATCH ? B.template rand<4>(gmask) : S.rand();
                     acc = metropolis_accept(-xmul(de, beta), u);
                     if (acc) {
                         // swap_atom_config! src/swap_config.jl:40-51 (+ swap_vars! :208-211 for EAM)
@@ -263,7 +302,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     __syncwarp(gmask);
                 } else {
                     // ------------------------------- volume_change_uniform src/MCMoves.jl:277-287, :169-177
-                    double scale = pow(exp(xmul(xsub(S.rand(), 0.5), vmax)), 1.0 / 3.0);
+                    const double uv = BATCH ? B.template rand<1>(gmask) : S.rand();
+                    double scale = pow(exp(xmul(xsub(uv, 0.5), vmax)), 1.0 / 3.0);
                     if (boxL >= max_boxl && scale > 1.0) scale = 1.0;
                     const double tL = xmul(scale, boxL), tH = xmul(scale, boxH);
                     const double new_rcut = get_r_cut(P.bc_kind, tL, tH);
@@ -277,7 +317,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                             double d2 = rhombic ? dist2_pbc<true>(bx, xa, ya, za, X[j], Y[j], Z[j])
                                                 : dist2_pbc<false>(bx, xa, ya, za, X[j], Y[j], Z[j]);
                             d2 = d2 * sc2;
-                            if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT>(P, d2);
+                            if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
                         }
                     }
                     double e_new = group_sum<G>(acce, gmask);
@@ -291,7 +331,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     const double delta_h = xadd(de, xmul(P.pressure, xsub(vc, vu)));
                     double p = exp(xadd(xmul(-delta_h, beta), xmul((double)P.n_atoms, log(xdiv(vc, vu)))));
                     p = p > 1.0 ? 1.0 : p;
-                    const double u = S.rand();
+                    const double u = BATCH ? B.template rand<4>(gmask) : S.rand();
                     acc = p >= u;
                     if (acc) {
                         // swap_config_v! src/swap_config.jl:113-140
@@ -436,10 +476,13 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                 cn[PTMC_C_VOL_TOT] += n_acc_vol; cn[PTMC_C_VOL_ADJ] = n_adj_vol;
             }
             cn[PTMC_C_EXC_ATT] += exc_cnt[2 * slot]; cn[PTMC_C_EXC_ACC] += exc_cnt[2 * slot + 1];
-            P.slot_rng[rep * 4] = S.r.s0; P.slot_rng[rep * 4 + 1] = S.r.s1;
-            P.slot_rng[rep * 4 + 2] = S.r.s2; P.slot_rng[rep * 4 + 3] = S.r.s3;
-            if (DBG) { if (P.replay) P.slot_cursor[rep] = S.pos; }
+            if (!BATCH) {
+                P.slot_rng[rep * 4] = S.r.s0; P.slot_rng[rep * 4 + 1] = S.r.s1;
+                P.slot_rng[rep * 4 + 2] = S.r.s2; P.slot_rng[rep * 4 + 3] = S.r.s3;
+                if (P.replay) P.slot_cursor[rep] = S.pos;
+            }
         }
+        if (BATCH) B.store(P.slot_rng + rep * (4 * PTMC_RNG_LANES), g);
     }
     if (tid == 0) {
         P.ladder_rng[lad * 4] = lrng[0]; P.ladder_rng[lad * 4 + 1] = lrng[1];

@@ -58,7 +58,7 @@ class SweepConfig:
     n_bin: int = 100
     min_acc: float = 0.4
     max_acc: float = 0.6
-    rng_mode: int = abi.RNG_XOSHIRO
+    rng_mode: int = abi.RNG_BATCH8
     seed: int = 1234
     device: int = 0
     lanes_per_replica: int = 0
@@ -204,15 +204,18 @@ class Engine:
     def seed(self, seed: int):
         self._check(self._fn("seed")(self._h, C.c_uint64(seed)))
 
+    def rng_words(self) -> int:
+        return int(self._fn("rng_words")(self._h))
+
     def set_rng_states(self, slot_states, ladder_states):
         L, T = self.shape
-        s = np.ascontiguousarray(slot_states, dtype=np.uint64).reshape(L, T, 4)
+        s = np.ascontiguousarray(slot_states, dtype=np.uint64).reshape(L, T, self.rng_words())
         l = np.ascontiguousarray(ladder_states, dtype=np.uint64).reshape(L, 4)
         self._check(self._fn("set_rng_states")(self._h, _p(s, C.c_uint64), _p(l, C.c_uint64)))
 
     def get_rng_states(self):
         L, T = self.shape
-        s = np.zeros((L, T, 4), dtype=np.uint64)
+        s = np.zeros((L, T, self.rng_words()), dtype=np.uint64)
         l = np.zeros((L, 4), dtype=np.uint64)
         self._check(self._fn("get_rng_states")(self._h, _p(s, C.c_uint64), _p(l, C.c_uint64)))
         return s, l

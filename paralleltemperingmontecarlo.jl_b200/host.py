@@ -227,7 +227,7 @@ class RuNNerPotential:
 
 # ------------------------------------------------------------------------------- config building --
 def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, ensemble, *, n_ladders=1,
-                 seed=1234, device=0, rng_mode=abi.RNG_XOSHIRO, lanes_per_replica=0) -> SweepConfig:
+                 seed=1234, device=0, rng_mode=abi.RNG_BATCH8, lanes_per_replica=0) -> SweepConfig:
     cfgs = start_config if isinstance(start_config, (list, tuple)) else (start_config,)
     bc = cfgs[0].boundary_condition
     if isinstance(ensemble, NPT):

@@ -18,7 +18,7 @@ def test_ne13_elj_nvt_replay(lanes):
     # BASELINE C1 at the script's own 25 temperatures (examples/ne13.jl:82): 2 ladders, 60 cycles incl. one
     # step-size adjustment (n_adjust=25) and two launches (chunks) so cursors/RNG/counters persist correctly.
     mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=25, cycles=60)
-    n_t = 25 if lanes < 32 else 16   # 25 x 32 lanes exceeds one CTA
+    n_t = {16: 24, 32: 16}.get(lanes, 25)   # 25 x 16 (x 32) lanes exceed the 384 (512) threads of one CTA
     if n_t != 25:
         mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=n_t, cycles=60)
     gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=50, eq_cycles=10, seed=1234,
@@ -47,17 +47,23 @@ def test_elj_odd_potential_replay():
     compare_traces(gpu, cpu)
 
 
-def test_sphere_redraw_and_recentre():
-    # tight binding sphere + big steps: exercises the redraw loop and the recentre! at count == 50
-    # (src/MCMoves.jl:115-145, quirk 8)
-    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=6, cycles=30)
+@pytest.mark.parametrize("fac,dmax,seed,cycles", [(1.05, 24.0, 11, 3), (1.3, 1.5, 5, 10)])
+def test_sphere_redraw_and_recentre(fac, dmax, seed, cycles):
+    # tight binding sphere + big steps (src/MCMoves.jl:115-145, quirk 8).  Case 1: ~94 % of the trials leave
+    # the sphere, so 5 of the 6 replicas reach count == 50 and recentre! (checked on the CPU oracle: their
+    # centre of mass drops from 4e-11 to 1e-16) without reaching the error at 100; case 2: frequent redraws
+    # with ~9 % of the moves accepted.
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=6, cycles=cycles)
     pos = start.positions
     rmax = np.sqrt((pos ** 2).sum(axis=1).max())
-    tight = P.Config(pos, P.SphericalBC(radius=rmax * 1.02))
+    tight = P.Config(pos, P.SphericalBC(radius=rmax * fac))
     md = np.full((1, 6, 4), 0.1)
-    md[:, :, 0] = 6.0
-    gpu, cpu = run_pair(mcp, temp, tight, pot, ens, n_ladders=1, n_cycles=30, seed=11, max_displ=md)
+    md[:, :, 0] = dmax
+    gpu, cpu = run_pair(mcp, temp, tight, pot, ens, n_ladders=1, n_cycles=cycles, seed=seed, max_displ=md, slack=400)
     compare_traces(gpu, cpu)
+    com = np.abs(gpu["states"]["pos"].mean(axis=2)).max(axis=-1)
+    if dmax > 20:
+        assert (com < 1e-14).sum() >= 4          # recentred replicas
 
 
 def test_cu55_eam_replay():
@@ -111,27 +117,71 @@ def test_periodic_nvt_replay():
     compare_traces(gpu, cpu)
 
 
-def test_xoshiro_mode_matches_oracle_seeding():
-    # production RNG mode: device-side Xoshiro256++ seeded like Random.seed!(seed + k) -> same trajectory as
-    # the oracle stepping the same generator
+def _free_run_pair(deck, n_ladders, seed, rng_mode, cycles, lanes=0, bounds=(-0.01, 0.0)):
+    """Device-generated random streams (no replay file): both engines seeded by the same rule."""
     from oracle import oracle
-    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=8, cycles=30)
-    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=4, seed=4321)
-    pos, box = initial_arrays(mcp, start, 4)
+    mcp, temp, start, pot, ens = deck
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=n_ladders, seed=seed, rng_mode=rng_mode, lanes_per_replica=lanes)
+    pos, box = initial_arrays(mcp, start, n_ladders)
     res = []
     for cls in (Engine, oracle.OracleEngine):
         eng = cls(cfg)
         eng.upload_states(pos, box)
-        eng.seed(4321)
-        eng.set_hist_bounds(-0.01, 0.0)
-        eng.run_cycles(1, 30, True)
+        eng.seed(seed)
+        eng.run_cycles(1, cycles // 2, False)
+        eng.reset_counters()
+        eng.set_hist_bounds(*bounds)
+        eng.run_cycles(1, cycles, True)
         eng.sync()
         res.append((eng.download_states(), eng.download_hist(), eng.get_rng_states()))
         eng.close()
+    return res
+
+
+def _assert_same_trajectory(res, e_rtol=1e-11):
     (sg, hg, rg), (sc, hc, rc) = res
-    assert np.array_equal(sg["pos"], sc["pos"]) and np.array_equal(sg["counters"], sc["counters"])
-    assert np.array_equal(hg, hc)
-    assert np.array_equal(rg[0], rc[0]) and np.array_equal(rg[1], rc[1])
+    assert np.array_equal(sg["counters"], sc["counters"]), "counters differ"
+    assert np.array_equal(sg["pos"], sc["pos"]), "positions differ"
+    assert np.array_equal(sg["max_displ"], sc["max_displ"])
+    assert np.array_equal(hg, hc), "histograms differ"
+    assert np.array_equal(rg[0], rc[0]) and np.array_equal(rg[1], rc[1]), "generator states differ"
+    np.testing.assert_allclose(sg["en_tot"], sc["en_tot"], rtol=e_rtol)
+    np.testing.assert_allclose(sg["ham"], sc["ham"], rtol=e_rtol)
+
+
+def test_xoshiro_mode_matches_oracle_seeding():
+    # compatibility RNG mode: ONE Julia-compatible Xoshiro256++ stream per slot, seeded like
+    # Random.seed!(seed + k) -> same trajectory as the oracle stepping the same generator
+    res = _free_run_pair(P.host.deck_ne13(n_traj=8, cycles=30), 4, 4321, abi.RNG_XOSHIRO, 30)
+    _assert_same_trajectory(res)
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+def test_batch8_production_mode_ne13(lanes):
+    # production RNG mode (8 substreams per slot, one batch per move) through the specialised kernels:
+    # the whole trajectory (positions, counters, step sizes, histograms, generator states) is bit-identical
+    # to the oracle following the same draw schedule
+    res = _free_run_pair(P.host.deck_ne13(n_traj=12, cycles=60), 3, 77, abi.RNG_BATCH8, 60, lanes=lanes)
+    _assert_same_trajectory(res)
+    assert res[0][0]["counters"][:, :, abi.C_EXC_ATT].sum() > 0
+
+
+@pytest.mark.parametrize("lanes", [0, 4, 16])
+def test_batch8_production_mode_ne55(lanes):
+    # BASELINE C2 geometry, production kernels (lanes 0 -> 8 lanes, 7 unrolled pair iterations)
+    res = _free_run_pair(P.host.deck_ne55(n_traj=24, cycles=30), 2, 5, abi.RNG_BATCH8, 30, lanes=lanes, bounds=(-0.1, 0.0))
+    _assert_same_trajectory(res)
+
+
+def test_batch8_production_mode_eam_and_redraws():
+    res = _free_run_pair(P.host.deck_cu55_eam(n_traj=28, cycles=10), 1, 9, abi.RNG_BATCH8, 10, bounds=(-10.0, 0.0))
+    _assert_same_trajectory(res, e_rtol=1e-10)
+    # tight sphere: first redraw from positions 5-7, later ones from fresh batches
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=6, cycles=20)
+    rmax = np.sqrt((start.positions ** 2).sum(axis=1).max())
+    tight = P.Config(start.positions, P.SphericalBC(radius=rmax * 1.05))
+    res = _free_run_pair((mcp, temp, tight, pot, ens), 2, 3, abi.RNG_BATCH8, 20)
+    _assert_same_trajectory(res)
 
 
 def test_energy_bookkeeping_at_full_size():
@@ -174,6 +224,13 @@ def test_error_behaviour():
     with pytest.raises(PtmcError):                            # SphericalBC + NPT (src/Ensembles.jl:189)
         Engine(sweep_config(mcp, temp, start, pot, P.NVT(13), lanes_per_replica=3))
     # replay stream too short -> PTMC_ERR_REPLAY at sync
+    with pytest.raises(PtmcError) as e:                       # tracing needs a sequential-stream kernel
+        eng = Engine(cfg)
+        eng.upload_states(pos, box)
+        eng.trace_enable(4)
+        eng.run_cycles(1, 1, False)
+    assert e.value.code == abi.ERR_STATE
+    eng.close()
     cfg = sweep_config(mcp, temp, start, pot, ens, rng_mode=abi.RNG_REPLAY)
     eng = Engine(cfg)
     eng.upload_states(pos, box)

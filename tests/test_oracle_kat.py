@@ -75,7 +75,7 @@ def _three_atom(bc, ens, pot, oracle, n_traj=2):
     conf = P.Config([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [0.0, 1.0, 0.0]], bc)
     mcp = P.MCParams(10, n_traj, 3)
     temp = P.TempGrid(10, 15, n_traj)
-    cfg = sweep_config(mcp, temp, conf, pot, ens)
+    cfg = sweep_config(mcp, temp, conf, pot, ens, rng_mode=abi.RNG_XOSHIRO)
     eng = oracle.OracleEngine(cfg)
     pos, box = initial_arrays(mcp, conf, 1)
     eng.upload_states(pos, box)
