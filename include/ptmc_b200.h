@@ -225,6 +225,11 @@ PTMC_API int ptmc_lanes_per_replica(const ptmc_handle* h);
  * uses it as the roofline denominator (MEASURED_PEAKS.json holds no FP64 figure). */
 PTMC_API int ptmc_fp64_peak(int device, int iters, double* tflops);
 
+/* Accuracy probe (tests): the pair arithmetic of the sweep kernel for n pairs of squared distances, exactly as
+ * it is accumulated per move: e_new[k] = e(d2_new[k]), e_old[k] = e(d2_old[k]) for the handle's potential
+ * (ELJ / ELJEven: dimer_energy src/EnergyEvaluation.jl:923-942; EAM: the r^-n term of invrexp :1088-1095). */
+PTMC_API int ptmc_debug_pair_energy(ptmc_handle* h, int n, const double* d2_new, const double* d2_old, double* e_new, double* e_old);
+
 /* ---- RuNNer forward pass: drop-in for librunnerjulia.so ------------------------------------------ */
 /* Exact ABI of the Fortran symbol the reference ccall()s (ForwardPass.jl:60-83): every argument by
  * reference, caller owns eatom.  Re-entrant. The Float64 return value is the last atom's energy. */

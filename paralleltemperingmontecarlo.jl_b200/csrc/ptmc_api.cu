@@ -19,6 +19,7 @@ int sweep_max_threads(int G);
 void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
 double measure_fp64_peak(cudaStream_t st, int iters);
+int run_pair_probe(const DevParams& P, int n, const double* h_d2n, const double* h_d2o, double* h_en, double* h_eo);
 struct RunnerState;
 }  // namespace ptmc
 
@@ -516,4 +517,12 @@ extern "C" PTMC_API int ptmc_fp64_peak(int device, int iters, double* tflops) {
     if (v <= 0) return fail(nullptr, PTMC_ERR_CUDA, "fp64 peak measurement failed");
     *tflops = v;
     return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_debug_pair_energy(ptmc_handle* h, int n, const double* d2_new, const double* d2_old, double* e_new, double* e_old) {
+    if (!h || n < 1 || !d2_new || !d2_old || !e_new || !e_old) return PTMC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    int rc = run_pair_probe(h->P, n, d2_new, d2_old, e_new, e_old);
+    h->launches += 1;
+    return rc ? fail(h, rc, "pair probe failed: %s", cudaGetErrorString(cudaGetLastError())) : PTMC_OK;
 }

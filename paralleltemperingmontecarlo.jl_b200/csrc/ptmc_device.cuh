@@ -152,6 +152,15 @@ __device__ __forceinline__ double rcp_pos(double x) {
     y = fma(y, e, y);
     return y;
 }
+// 1/x for normal positive x with ONE third-order (Halley) step: y1 = y0 (1 + e + e^2), e = 1 - x y0.
+// The MUFU.RCP64H seed carries >= 20 bits, so e^3 < 2^-60: 3 DFMA instead of 4 (checked by ptmc_debug_pair_energy).
+__device__ __forceinline__ double rcp_pos3(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
+}
 // 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed + two Newton steps.
 __device__ __forceinline__ double rsqrt_pos(double x) {
     double y;
@@ -191,6 +200,34 @@ __device__ __forceinline__ double elj_odd(const DevParams& P, double r2) {
     for (int k = P.n_coeff - 2; k >= 0; --k) p = fma(p, y, P.coeff[k]);
     return p * y6;
 }
+// Horner part of ELJPotentialEven for x = 1/r2: returns P(x) with e = x^3 P(x)
+template <int NC>
+__device__ __forceinline__ double elj_even_poly(const DevParams& P, double x) {
+    double p;
+    if (NC == 6) {
+        p = P.coeff[5];
+        p = fma(p, x, P.coeff[4]); p = fma(p, x, P.coeff[3]); p = fma(p, x, P.coeff[2]);
+        p = fma(p, x, P.coeff[1]); p = fma(p, x, P.coeff[0]);
+    } else {
+        p = P.coeff[P.n_coeff - 1];
+        for (int k = P.n_coeff - 2; k >= 0; --k) p = fma(p, x, P.coeff[k]);
+    }
+    return p;
+}
+// Delta-energy kernel of one pair for ELJPotentialEven (src/EnergyEvaluation.jl:804-812 with :934-942):
+// acc_new += e(d2n), acc_old += e(d2o), sharing ONE reciprocal: y = 1/(d2n d2o), 1/d2n = y d2o, 1/d2o = y d2n.
+// 34 FP64 instructions per pair including the two squared distances.
+// Lanes without a pair pass d2n = d2o = PAIR_OFF: x^3 underflows to exactly 0 and nothing is accumulated.
+#define PTMC_PAIR_OFF 1e150
+template <int NC>
+__device__ __forceinline__ void elj_even_pair_acc(const DevParams& P, double d2n, double d2o, double& acc_new, double& acc_old) {
+    const double y = rcp_pos3(d2n * d2o);
+    const double xn = y * d2o, xo = y * d2n;
+    const double pn = elj_even_poly<NC>(P, xn), po = elj_even_poly<NC>(P, xo);
+    acc_new = fma(pn, xn * xn * xn, acc_new);
+    acc_old = fma(po, xo * xo * xo, acc_old);
+}
+
 // NC = 6: the six-coefficient form of every BASELINE script, fully unrolled; NC = 0: runtime n_coeff
 template <int POT, int NC = 0>
 __device__ __forceinline__ double pair_energy(const DevParams& P, double r2) {

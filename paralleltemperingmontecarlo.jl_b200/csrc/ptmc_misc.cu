@@ -27,6 +27,38 @@ void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaS
     reduce_hist_kernel<<<(unsigned)((per + threads - 1) / threads), threads, 0, st>>>(hist, out, n_ladders, per);
 }
 
+// Accuracy probe of the production pair arithmetic: e_new[k], e_old[k] exactly as the sweep kernel accumulates
+// them for the pair (d2_new[k], d2_old[k]).
+__global__ void pair_probe_kernel(const DevParams P, int n, const double* d2n, const double* d2o, double* en, double* eo) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double a = 0.0, b = 0.0;
+    if (P.pot_kind == PTMC_POT_ELJ_EVEN) {
+        if (P.n_coeff == 6) elj_even_pair_acc<6>(P, d2n[k], d2o[k], a, b);
+        else elj_even_pair_acc<0>(P, d2n[k], d2o[k], a, b);
+    } else if (P.pot_kind == PTMC_POT_ELJ) {
+        a = elj_odd(P, d2n[k]); b = elj_odd(P, d2o[k]);
+    } else {
+        double p, r;
+        eam_invrexp(P, d2n[k], p, r); a = p; eam_invrexp(P, d2o[k], p, r); b = p;   // phi terms
+    }
+    en[k] = a; eo[k] = b;
+}
+int run_pair_probe(const DevParams& P, int n, const double* h_d2n, const double* h_d2o, double* h_en, double* h_eo) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * 4 * (size_t)n) != cudaSuccess) return PTMC_ERR_CUDA;
+    cudaMemcpy(d, h_d2n, sizeof(double) * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + n, h_d2o, sizeof(double) * n, cudaMemcpyHostToDevice);
+    pair_probe_kernel<<<(n + 127) / 128, 128>>>(P, n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) {
+        cudaMemcpy(h_en, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h_eo, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    return e == cudaSuccess ? PTMC_OK : PTMC_ERR_CUDA;
+}
+
 // FP64 pipe peak: 8 independent DFMA chains per thread, all SMs, 2 flops per DFMA.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int n_iter, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -224,28 +224,38 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     if (!EAM) {
                         // dimer_energy_update! :804-821: sum_j e(new_ij) - e(old_ij); the old row is recomputed
                         // from the positions instead of being read from a stored dist2_mat.
-                        double accd = 0.0;
+                        // (the reference also forms sum(new row) - sum(old row), :808-810)
+                        double accn = 0.0, acco = 0.0;
                         const double* Xg = X + g;
                         auto pair_term = [&](int k) {
                             const int j = g + k * G;
                             const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
-                            double d2n, d2o;
-                            if (PBC) {
-                                if (rhombic) { d2n = dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj); }
-                                else { d2n = dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj); }
-                            } else {
+                            const bool valid = (j != i) && (j < N);   // not the moved atom, not padding
+                            if (!PBC && POT == PTMC_POT_ELJ_EVEN) {
                                 double ax = tx - xj, ay = ty - yj, az = tz - zj;
-                                d2n = fma(az, az, fma(ay, ay, ax * ax));
+                                double d2n = fma(az, az, fma(ay, ay, ax * ax));
                                 double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
-                                d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
+                                double d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
+                                d2n = valid ? d2n : PTMC_PAIR_OFF; d2o = valid ? d2o : PTMC_PAIR_OFF;
+                                elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);
+                            } else {
+                                double d2n, d2o;
+                                if (PBC) {
+                                    if (rhombic) { d2n = dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj); }
+                                    else { d2n = dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj); }
+                                } else {
+                                    double ax = tx - xj, ay = ty - yj, az = tz - zj;
+                                    d2n = fma(az, az, fma(ay, ay, ax * ax));
+                                    double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
+                                    d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
+                                }
+                                double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
+                                if (PBC) {
+                                    if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }
+                                }
+                                // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
+                                accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                             }
-                            double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
-                            if (PBC) {
-                                if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }
-                            }
-                            // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
-                            const bool valid = (j != i) && (j < N);
-                            accd += valid ? (en_j - eo_j) : 0.0;
                         };
                         if (NITER) {
 #pragma unroll
@@ -255,6 +265,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
 #pragma unroll 2
                             for (int k = 0; k < nk; ++k) pair_term(k);
                         }
+                        const double accd = accn - acco;
                         const double delta_en = group_sum<G>(accd, gmask);
                         new_en = xadd(delta_en, en);
                     } else {

@@ -302,6 +302,12 @@ class Engine:
     def lanes_per_replica(self) -> int:
         return int(self._fn("lanes_per_replica")(self._h))
 
+    def debug_pair_energy(self, d2_new, d2_old):
+        a, b = _f64(d2_new), _f64(d2_old)
+        en, eo = np.zeros_like(a), np.zeros_like(b)
+        self._check(self._fn("debug_pair_energy")(self._h, a.size, _p(a), _p(b), _p(en), _p(eo)))
+        return en, eo
+
     def reduced_hist_dev(self):
         ptr = C.c_void_p()
         n = C.c_int64()

@@ -208,6 +208,27 @@ def test_energy_bookkeeping_at_full_size():
     eng.close(); eng2.close()
 
 
+def test_pair_arithmetic_accuracy(oracle):
+    # the production pair kernel (one shared reciprocal, Halley step, Horner + FMA) against the reference's
+    # own formulation (1 + K divisions, src/EnergyEvaluation.jl:934-942) over the whole physical range
+    mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=4, cycles=1)
+    eng = Engine(sweep_config(mcp, temp, start, pot, ens))
+    rng = np.random.default_rng(0)
+    r = np.concatenate([rng.uniform(3.0, 60.0, 200000), rng.uniform(4.5, 8.0, 200000)])
+    d2n, d2o = r ** 2, rng.permutation(r) ** 2
+    en, eo = eng.debug_pair_energy(d2n, d2o)
+    ref_n = np.array([oracle.dimer_energy_eljeven(pot.coeff, float(x)) for x in d2n[:20000]])
+    ref_o = np.array([oracle.dimer_energy_eljeven(pot.coeff, float(x)) for x in d2o[:20000]])
+    # the polynomial has a root near r = 5.2 bohr: compare against the scale of its largest term
+    scale = lambda d2: np.abs(np.array(pot.coeff)[None, :] * d2[:, None] ** -(np.arange(6)[None, :] + 3.0)).max(axis=1)
+    assert (np.abs(en[:20000] - ref_n) <= 16 * np.finfo(float).eps * scale(d2n[:20000])).all()
+    assert (np.abs(eo[:20000] - ref_o) <= 16 * np.finfo(float).eps * scale(d2o[:20000])).all()
+    # switched-off lanes contribute exactly nothing
+    z = eng.debug_pair_energy(np.full(4, 1e150), np.full(4, 1e150))
+    assert (z[0] == 0).all() and (z[1] == 0).all()
+    eng.close()
+
+
 def test_error_behaviour():
     mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=4, cycles=5)
     cfg = sweep_config(mcp, temp, start, pot, ens)
