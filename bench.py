@@ -249,7 +249,10 @@ def run_b200(args):
     kernel_ms_avg = sum(kms) / len(kms)
 
     # ------------------------------------------------------------------- end-to-end timing (e2e)
-    out = {k: None for k in ("pos", "box", "en_tot", "max_displ", "counters", "ham")}
+    # results land in pinned host buffers owned by the caller (what a Julia Array passed to ccall would be after
+    # cudaHostRegister): positions, box, energies, step sizes, counters, ham
+    pinned = {k: torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory().numpy()
+              for k, (shp, dt) in eng.state_shapes().items()}
     h2d = pin_pos.numel() * 8 + pin_box.numel() * 8
     d2h = 0
     e2e_steps = max(3, min(args.steps, 5))
@@ -258,7 +261,7 @@ def run_b200(args):
         eng.upload_states(pin_pos.numpy(), pin_box.numpy())
         eng.set_hist_bounds(float(en.min()) - 1e-3, float(en.max()) + 2e-3)
         eng.run_cycles(i, cycles, True)
-        st = eng.download_states()
+        st = eng.download_states(out=pinned)
         hs = eng.download_hist(reduce_ladders=True)
         return sum(v.nbytes for v in st.values()) + hs.nbytes
 

@@ -221,7 +221,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     for (int i = 0; i < PTMC_MAX_COEFF; ++i) P.coeff[i] = i < c->n_coeff ? c->coeff[i] : 0.0;
     P.eam_hn = c->eam_n / 2; P.eam_hm = c->eam_m / 2; P.eam_ean = c->eam_ean; P.eam_ecam = c->eam_ecam;
 
-    const SmemLayout lay = smem_layout(c->n_traj, P.n_pad, c->pot_kind);
+    const SmemLayout lay = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32);
     h->smem = lay.bytes;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
 

@@ -28,10 +28,10 @@ struct SmemLayout {
     int off_perm;       // int cfg_of_slot[T]
     int off_exc;        // i64 exc counters [T][2]
     int off_ham;        // ham [T][2] (slot side)
-    int off_lrng;       // ladder stream: 4 x u64 state + cursor
+    int off_lrng;       // ladder stream, one private copy per warp: 4 x u64 state + cursor + pad
     size_t bytes;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind) {
+__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps) {
     SmemLayout s;
     int arrays = 3 + (pot_kind == PTMC_POT_EAM ? 4 : 0);   // x,y,z (+ phi,rho,new_phi,new_rho)
     s.cfg_stride = arrays * n_pad;
@@ -39,7 +39,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     int off = s.off_scal + 4 * n_traj;
     s.off_exc = off; off += 2 * n_traj;
     s.off_ham = off; off += 2 * n_traj;
-    s.off_lrng = off; off += 6;
+    s.off_lrng = off; off += 6 * n_warps;
     s.off_perm = off; off += (n_traj + 1) / 2 + 1;
     s.bytes = (size_t)off * sizeof(double);
     return s;
@@ -62,7 +62,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     const int slot = tid / G, g = tid & (G - 1);
     const bool active = slot < T;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
-    const SmemLayout lay = smem_layout(T, NP, POT);
+    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5));
     double* scal = sm + lay.off_scal;
     i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
     double* hams = sm + lay.off_ham;
@@ -119,11 +119,13 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
             if (P.replay) { S.draws = P.slot_draws + rep * P.slot_len; S.len = P.slot_len; S.pos = P.slot_cursor[rep]; }
         }
     }
-    // ladder ("driver task") stream lives in shared memory; only thread 0 touches it
-    if (tid == 0) {
-        lrng[0] = P.ladder_rng[lad * 4]; lrng[1] = P.ladder_rng[lad * 4 + 1];
-        lrng[2] = P.ladder_rng[lad * 4 + 2]; lrng[3] = P.ladder_rng[lad * 4 + 3];
-        lrng[4] = (DBG && P.replay) ? (u64)P.ladder_cursor[lad] : 0;
+    // ladder ("driver task") stream: every warp keeps a private copy in shared memory, stepped by its lane 0
+    // in lock-step with the other warps, so cycles without an exchange attempt (90 %) need no CTA barrier
+    u64* wl = lrng + 6 * (tid >> 5);
+    if ((tid & 31) == 0) {
+        wl[0] = P.ladder_rng[lad * 4]; wl[1] = P.ladder_rng[lad * 4 + 1];
+        wl[2] = P.ladder_rng[lad * 4 + 2]; wl[3] = P.ladder_rng[lad * 4 + 3];
+        wl[4] = (DBG && P.replay) ? (u64)P.ladder_cursor[lad] : 0;
     }
     // cycle phases instead of 64-bit modulo in the loop
     int adj_phase = (int)(first_idx % P.n_adjust);
@@ -367,21 +369,34 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                 if (PBC) { scal[4 * c + 1] = boxL; scal[4 * c + 2] = boxH; scal[4 * c + 3] = rcut; }
             }
         }
-        __syncthreads();
         // ========================================= exchange: src/MCRun.jl:203-205, src/Exchange.jl:132-186 ==
-        if (tid == 0) {
+        __syncwarp();
+        int ex_gate = 0, ex_n = 0;
+        double ex_u = 0.0;
+        if ((tid & 31) == 0) {
             Stream<DBG> LS;
-            LS.r.s0 = lrng[0]; LS.r.s1 = lrng[1]; LS.r.s2 = lrng[2]; LS.r.s3 = lrng[3];
+            LS.r.s0 = wl[0]; LS.r.s1 = wl[1]; LS.r.s2 = wl[2]; LS.r.s3 = wl[3];
             LS.draws = nullptr; LS.pos = 0; LS.len = 0; LS.exhausted = 0;
             if (DBG) {
-                if (P.replay) { LS.draws = P.ladder_draws + lad * P.ladder_len; LS.len = P.ladder_len; LS.pos = (i64)lrng[4]; }
+                if (P.replay) { LS.draws = P.ladder_draws + lad * P.ladder_len; LS.len = P.ladder_len; LS.pos = (i64)wl[4]; }
             }
-            int ex_gate = 0, ex_n = 0, ex_acc = 0;
-            if (LS.rand() < 0.1) {
+            if (LS.rand() < 0.1) {                                  // :203
                 ex_gate = 1;
-                const int n_exc = LS.range((u64)(T - 1));
-                ex_n = n_exc;
-                const int a = n_exc - 1, b = n_exc;
+                ex_n = LS.range((u64)(T - 1));                      // Exchange.jl:135
+                ex_u = LS.rand();                                   // :145 (drawn whenever an exchange is attempted)
+            }
+            wl[0] = LS.r.s0; wl[1] = LS.r.s1; wl[2] = LS.r.s2; wl[3] = LS.r.s3;
+            if (DBG) {
+                wl[4] = (u64)LS.pos;
+                if (LS.exhausted) err = PTMC_ERR_REPLAY;
+            }
+        }
+        ex_gate = __shfl_sync(0xffffffffu, ex_gate, 0);
+        if (ex_gate) {
+            __syncthreads();                                        // every slot has finished this cycle's moves
+            if (tid == 0) {
+                int ex_acc = 0;
+                const int a = ex_n - 1, b = ex_n;
                 exc_cnt[2 * a] += 1; exc_cnt[2 * b] += 1;
                 const int ca = perm[a], cb = perm[b];
                 double ea = scal[4 * ca], eb = scal[4 * cb];
@@ -392,23 +407,22 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                 // exc_acceptance :103-108: min(1, exp(dbeta * dE)) > rand()   (strict)
                 double pe = exp(xmul(xsub(P.betas[a], P.betas[b]), xsub(ea, eb)));
                 pe = (pe != pe) ? pe : (pe < 1.0 ? pe : 1.0);
-                if (pe > LS.rand()) {
+                if (pe > ex_u) {
                     ex_acc = 1;
                     exc_cnt[2 * a + 1] += 1; exc_cnt[2 * b + 1] += 1;
                     perm[a] = cb; perm[b] = ca;       // exc_trajectories! :115-124
                 }
-            }
-            lrng[0] = LS.r.s0; lrng[1] = LS.r.s1; lrng[2] = LS.r.s2; lrng[3] = LS.r.s3;
-            if (DBG) {
-                lrng[4] = (u64)LS.pos;
-                if (tracing) {
-                    int32_t* e = P.tr_exc + ((size_t)lad * P.trace_cap + P.trace_base + cyc) * 3;
-                    e[0] = ex_gate; e[1] = ex_n; e[2] = ex_acc;
+                if (DBG) {
+                    if (tracing) {
+                        int32_t* e = P.tr_exc + ((size_t)lad * P.trace_cap + P.trace_base + cyc) * 3;
+                        e[0] = 1; e[1] = ex_n; e[2] = ex_acc;
+                    }
                 }
-                if (LS.exhausted) err = PTMC_ERR_REPLAY;
             }
+            __syncthreads();
+        } else {
+            __syncwarp(gmask);                                      // scal[] of this slot is visible to its group
         }
-        __syncthreads();
         if (active) {
             // ------------------------------------------- update_max_stepsize! src/Exchange.jl:198-263
             if (adj_phase == 0) {
@@ -496,9 +510,9 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
         if (BATCH) B.store(P.slot_rng + rep * (4 * PTMC_RNG_LANES), g);
     }
     if (tid == 0) {
-        P.ladder_rng[lad * 4] = lrng[0]; P.ladder_rng[lad * 4 + 1] = lrng[1];
-        P.ladder_rng[lad * 4 + 2] = lrng[2]; P.ladder_rng[lad * 4 + 3] = lrng[3];
-        if (DBG) { if (P.replay) P.ladder_cursor[lad] = (i64)lrng[4]; }
+        P.ladder_rng[lad * 4] = wl[0]; P.ladder_rng[lad * 4 + 1] = wl[1];
+        P.ladder_rng[lad * 4 + 2] = wl[2]; P.ladder_rng[lad * 4 + 3] = wl[3];
+        if (DBG) { if (P.replay) P.ladder_cursor[lad] = (i64)wl[4]; }
     }
     if (err) atomicMin(P.error, err);
 }

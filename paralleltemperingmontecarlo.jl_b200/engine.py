@@ -266,15 +266,22 @@ class Engine:
                 "exchange": cut(exc, (3,)), "n_cycles": k}
 
     # -- state out -----------------------------------------------------------------------------------
-    def download_states(self, what=("pos", "box", "en_tot", "max_displ", "counters", "ham")):
+    def state_shapes(self):
         L, T = self.shape
-        out = {}
-        if "pos" in what: out["pos"] = np.zeros((L, T, self.cfg.n_atoms, 3))
-        if "box" in what: out["box"] = np.zeros((L, T, 2))
-        if "en_tot" in what: out["en_tot"] = np.zeros((L, T))
-        if "max_displ" in what: out["max_displ"] = np.zeros((L, T, 4))
-        if "counters" in what: out["counters"] = np.zeros((L, T, abi.PTMC_NCOUNT), dtype=np.int64)
-        if "ham" in what: out["ham"] = np.zeros((L, T, 2))
+        return {"pos": ((L, T, self.cfg.n_atoms, 3), np.float64), "box": ((L, T, 2), np.float64),
+                "en_tot": ((L, T), np.float64), "max_displ": ((L, T, 4), np.float64),
+                "counters": ((L, T, abi.PTMC_NCOUNT), np.int64), "ham": ((L, T, 2), np.float64)}
+
+    def download_states(self, what=("pos", "box", "en_tot", "max_displ", "counters", "ham"), out=None):
+        """Per-slot state.  `out` may hold caller-owned (e.g. pinned) arrays of the right shape to fill."""
+        shapes = self.state_shapes()
+        out = {} if out is None else {k: v for k, v in out.items() if k in what}
+        for k in what:
+            shp, dt = shapes[k]
+            if k not in out:
+                out[k] = np.zeros(shp, dtype=dt)
+            elif out[k].shape != shp or out[k].dtype != dt or not out[k].flags.c_contiguous:
+                raise ValueError(f"out[{k!r}] must be a C-contiguous {dt.__name__}{shp} array")
         self._check(self._fn("download_states")(
             self._h, _p(out.get("pos")), _p(out.get("box")), _p(out.get("en_tot")), _p(out.get("max_displ")),
             _p(out.get("counters"), C.c_int64), _p(out.get("ham"))))
