@@ -221,7 +221,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     for (int i = 0; i < PTMC_MAX_COEFF; ++i) P.coeff[i] = i < c->n_coeff ? c->coeff[i] : 0.0;
     P.eam_hn = c->eam_n / 2; P.eam_hm = c->eam_m / 2; P.eam_ean = c->eam_ean; P.eam_ecam = c->eam_ecam;
 
-    const SmemLayout lay = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32);
+    const SmemLayout lay = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere);
     h->smem = lay.bytes;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
 
@@ -232,7 +232,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     double *en_min, *en_max, *v_min, *v_max;
     int rc = 0;
     if ((rc = dev_alloc(h, &P.pos, R * N * 3)) || (rc = dev_alloc(h, &P.box, R * 2)) || (rc = dev_alloc(h, &P.en_tot, R)) ||
-        (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
+        (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) ||
+        (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) || (rc = dev_alloc(h, &P.perm_g, R)) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
         (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
         (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4 * PTMC_RNG_LANES)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||
         (rc = dev_alloc(h, &P.slot_cursor, R)) || (rc = dev_alloc(h, &P.ladder_cursor, L)) ||
@@ -282,6 +283,11 @@ extern "C" PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, co
     CU(h, cudaMemsetAsync(P.counters, 0, sizeof(i64) * R * PTMC_NCOUNT, h->stream));
     CU(h, cudaMemsetAsync(P.ham, 0, sizeof(double) * R * 2, h->stream));
     CU(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
+    {   // slot -> configuration map starts as the identity
+        std::vector<int> perm(R);
+        for (size_t r = 0; r < R; ++r) perm[r] = (int)(r % (size_t)h->cfg.n_traj);
+        CU(h, cudaMemcpy(P.perm_g, perm.data(), sizeof(int) * R, cudaMemcpyHostToDevice));
+    }
     launch_init(P, h->n_rep, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());

@@ -34,6 +34,10 @@ struct DevParams {
     double* box;        // [L][T][2]
     double* en_tot;     // [L][T]
     double* comp;       // [L][T][N][2]  EAM (phi, rho)
+    // periodic boundaries: the reference's dist2_mat, kept in HBM per CONFIGURATION (not per slot) so that an
+    // exchange never moves it; perm_g is the slot -> configuration map, persisted between launches
+    double* d2mat;      // [L][T][N][N]
+    int* perm_g;        // [L][T]
     // slot-side state
     double* max_displ;  // [L][T][4]
     double* max_boxlength; // [L][T]
@@ -284,6 +288,29 @@ __device__ __forceinline__ double dist2_pbc(const Box& b, double ax, double ay, 
         dz = az - fma(b.h, rint((az - bz) * b.ih), bz);
     }
     return fma(dz, dz, fma(dy, dy, dx * dx));
+}
+// distance2 exactly as the reference writes it (src/Configurations.jl:101-126: true divisions, no FMA, image of
+// b built first).  Used where bits matter: the initial dist2_mat of a perfect lattice holds pairs that sit
+// EXACTLY on the cut-off (r_cut^2 = L^2/4, 3L^2/16, h^2/4), and d2 <= r_cut must fall the way the reference's does.
+__device__ __forceinline__ double dist2_exact(int bc_kind, double ax, double ay, double az, double bx, double by, double bz, double L, double h) {
+    double Bx, By, Bz;
+    if (bc_kind == PTMC_BC_RHOMBIC) {
+        const double s3 = sqrt(3.0);
+        const double hy = xmul(xdiv(s3, 2.0), L);
+        const double is3 = xdiv(1.0, s3);
+        By = xadd(by, xmul(hy, rint(xdiv(xsub(ay, by), hy))));
+        Bx = xadd(xadd(xsub(bx, xdiv(by, s3)), xmul(L, rint(xdiv(xsub(xsub(ax, bx), xmul(is3, xsub(ay, by))), L)))), xmul(is3, By));
+        Bz = xadd(bz, xmul(h, rint(xdiv(xsub(az, bz), h))));
+    } else if (bc_kind == PTMC_BC_SPHERICAL) {
+        Bx = bx; By = by; Bz = bz;
+    } else {
+        const double hz = bc_kind == PTMC_BC_CUBIC ? L : h;
+        Bx = xadd(bx, xmul(L, rint(xdiv(xsub(ax, bx), L))));
+        By = xadd(by, xmul(L, rint(xdiv(xsub(ay, by), L))));
+        Bz = xadd(bz, xmul(hz, rint(xdiv(xsub(az, bz), hz))));
+    }
+    const double dx = xsub(ax, Bx), dy = xsub(ay, By), dz = xsub(az, Bz);
+    return xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
 }
 // get_volume src/Configurations.jl:246-256
 __device__ __forceinline__ double get_volume(int bc_kind, double L, double h) {

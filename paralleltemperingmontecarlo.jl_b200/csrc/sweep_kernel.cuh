@@ -31,9 +31,9 @@ struct SmemLayout {
     int off_lrng;       // ladder stream, one private copy per warp: 4 x u64 state + cursor + pad
     size_t bytes;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps) {
+__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc) {
     SmemLayout s;
-    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? 4 : 0);   // x,y,z (+ phi,rho,new_phi,new_rho)
+    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? 4 : 0) + (pbc ? 1 : 0);   // x,y,z (+ phi,rho,new_phi,new_rho | + new_dist2_vec)
     s.cfg_stride = arrays * n_pad;
     s.off_scal = n_traj * s.cfg_stride;
     int off = s.off_scal + 4 * n_traj;
@@ -62,7 +62,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     const int slot = tid / G, g = tid & (G - 1);
     const bool active = slot < T;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
-    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5));
+    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC);
     double* scal = sm + lay.off_scal;
     i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
     double* hams = sm + lay.off_ham;
@@ -74,7 +74,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
 
     // ---- load: slot s starts with configuration buffer s ----------------------------------------------
     if (active) {
-        double* X = sm + (size_t)slot * lay.cfg_stride;
+        const int c0 = PBC ? P.perm_g[rep] : slot;   // periodic: the dist2_mat in HBM is indexed by configuration
+        double* X = sm + (size_t)c0 * lay.cfg_stride;
         double* Y = X + NP; double* Z = Y + NP;
         const double* gp = P.pos + rep * 3 * N;
         for (int j = g; j < NP; j += G) {
@@ -88,10 +89,10 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
         }
         if (g == 0) {
             double L = P.box[rep * 2], h = P.box[rep * 2 + 1];
-            scal[4 * slot] = P.en_tot[rep];
-            scal[4 * slot + 1] = L; scal[4 * slot + 2] = h;
-            scal[4 * slot + 3] = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
-            perm[slot] = slot;
+            scal[4 * c0] = P.en_tot[rep];
+            scal[4 * c0 + 1] = L; scal[4 * c0 + 2] = h;
+            scal[4 * c0 + 3] = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
+            perm[slot] = c0;
             exc_cnt[2 * slot] = 0; exc_cnt[2 * slot + 1] = 0;
             hams[2 * slot] = P.ham[rep * 2]; hams[2 * slot + 1] = P.ham[rep * 2 + 1];
         }
@@ -224,48 +225,53 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     // -------------------------------- energy_update! src/EnergyEvaluation.jl:1474-1506,1567-1591
                     double new_en;
                     if (!EAM) {
-                        // dimer_energy_update! :804-821: sum_j e(new_ij) - e(old_ij); the old row is recomputed
-                        // from the positions instead of being read from a stored dist2_mat.
-                        // (the reference also forms sum(new row) - sum(old row), :808-810)
+                        // dimer_energy_update! :804-821: sum_j e(new_ij) - sum_j e(old_ij) (the reference forms the same
+                        // two row sums, :808-810).
                         double accn = 0.0, acco = 0.0;
-                        const double* Xg = X + g;
-                        auto pair_term = [&](int k) {
-                            const int j = g + k * G;
-                            const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
-                            const bool valid = (j != i) && (j < N);   // not the moved atom, not padding
-                            if (!PBC && POT == PTMC_POT_ELJ_EVEN) {
+                        if (PBC) {
+                            // periodic: the old row is dist2_mat[index, :] read from HBM (frozen values, exactly the
+                            // reference's semantics for d2 <= r_cut), the new row goes to new_dist2_vec in shared memory
+                            const double* Drow = P.d2mat + (((size_t)lad * T + c) * N + i) * N;
+                            double* NEW = Z + NP;
+                            for (int j = g; j < N; j += G) {
+                                const double xj = X[j], yj = Y[j], zj = Z[j];
+                                double d2n = rhombic ? dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj) : dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj);
+                                double d2o = __ldcg(Drow + j);
+                                const bool valid = (j != i);
+                                NEW[j] = valid ? d2n : 0.0;                       // new_dist2_vec[index] = 0, MCMoves.jl:111
+                                d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
+                                double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
+                                if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }   // :323-336
+                                accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
+                            }
+                        } else {
+                            // free space: the old row is recomputed from the positions (no dist2_mat is stored)
+                            const double* Xg = X + g;
+                            auto pair_term = [&](int k) {
+                                const int j = g + k * G;
+                                const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
+                                const bool valid = (j != i) && (j < N);   // not the moved atom, not padding
                                 double ax = tx - xj, ay = ty - yj, az = tz - zj;
                                 double d2n = fma(az, az, fma(ay, ay, ax * ax));
                                 double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
                                 double d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
-                                d2n = valid ? d2n : PTMC_PAIR_OFF; d2o = valid ? d2o : PTMC_PAIR_OFF;
-                                elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);
-                            } else {
-                                double d2n, d2o;
-                                if (PBC) {
-                                    if (rhombic) { d2n = dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj); }
-                                    else { d2n = dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj); d2o = dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj); }
+                                if (POT == PTMC_POT_ELJ_EVEN) {
+                                    d2n = valid ? d2n : PTMC_PAIR_OFF; d2o = valid ? d2o : PTMC_PAIR_OFF;
+                                    elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);
                                 } else {
-                                    double ax = tx - xj, ay = ty - yj, az = tz - zj;
-                                    d2n = fma(az, az, fma(ay, ay, ax * ax));
-                                    double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
-                                    d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
+                                    // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
+                                    const double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
+                                    accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                 }
-                                double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
-                                if (PBC) {
-                                    if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }
-                                }
-                                // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
-                                accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
-                            }
-                        };
-                        if (NITER) {
+                            };
+                            if (NITER) {
 #pragma unroll
-                            for (int k = 0; k < NITER; ++k) pair_term(k);
-                        } else {
-                            const int nk = NP / G;
+                                for (int k = 0; k < NITER; ++k) pair_term(k);
+                            } else {
+                                const int nk = NP / G;
 #pragma unroll 2
-                            for (int k = 0; k < nk; ++k) pair_term(k);
+                                for (int k = 0; k < nk; ++k) pair_term(k);
+                            }
                         }
                         const double accd = accn - acco;
                         const double delta_en = group_sum<G>(accd, gmask);
@@ -306,6 +312,16 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                         if (g == 0) { X[i] = tx; Y[i] = ty; Z[i] = tz; }
                         en = new_en;
                         n_acc_atom += 1; n_adj_atom += 1;
+                        if (PBC) {
+                            // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
+                            double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
+                            const double* NEW = Z + NP;
+                            for (int j = g; j < N; j += G) {
+                                const double v = NEW[j];
+                                __stcg(D + (size_t)i * N + j, v);
+                                __stcg(D + (size_t)j * N + i, v);
+                            }
+                        }
                         if (EAM) {
                             double* PHI = Z + NP; double* RHO = PHI + NP; double* NPHI = RHO + NP; double* NRHO = NPHI + NP;
                             __syncwarp(gmask);
@@ -324,12 +340,11 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     // dimer_energy_config on new_dist2_mat = dist2_mat * scale^2 (src/MCRun.jl:76-85,
                     // src/EnergyEvaluation.jl:397-474); rows are dealt to the lanes of the group.
                     double acce = 0.0;
+                    double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
                     for (int a = 0; a < N - 1; ++a) {
-                        const double xa = X[a], ya = Y[a], za = Z[a];
+                        const double* Da = D + (size_t)a * N;
                         for (int j = a + 1 + g; j < N; j += G) {
-                            double d2 = rhombic ? dist2_pbc<true>(bx, xa, ya, za, X[j], Y[j], Z[j])
-                                                : dist2_pbc<false>(bx, xa, ya, za, X[j], Y[j], Z[j]);
-                            d2 = d2 * sc2;
+                            const double d2 = xmul(__ldcg(Da + j), sc2);      // new_dist2_mat[a, j]
                             if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
                         }
                     }
@@ -350,6 +365,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                         // swap_config_v! src/swap_config.jl:113-140
                         __syncwarp(gmask);
                         for (int j = g; j < N; j += G) { X[j] = xmul(scale, X[j]); Y[j] = xmul(scale, Y[j]); Z[j] = xmul(scale, Z[j]); }
+                        for (int k = g; k < N * N; k += G) __stcg(D + k, xmul(__ldcg(D + k), sc2));   // dist2_mat .= new_dist2_mat
                         boxL = tL; boxH = tH; rcut = new_rcut; en = e_new;
                         bx = make_box(P.bc_kind, boxL, boxH);
                         n_acc_vol += 1; n_adj_vol += 1;
@@ -496,6 +512,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
             i64* cn = P.counters + rep * PTMC_NCOUNT;
             cn[PTMC_C_ATOM_TOT] += n_acc_atom; cn[PTMC_C_ATOM_ADJ] = n_adj_atom;
             if (PBC) {
+                P.perm_g[rep] = c;
                 P.box[rep * 2] = scal[4 * c + 1]; P.box[rep * 2 + 1] = scal[4 * c + 2];
                 P.max_displ[rep * 4 + 1] = vmax;
                 cn[PTMC_C_VOL_TOT] += n_acc_vol; cn[PTMC_C_VOL_ADJ] = n_adj_vol;
@@ -531,8 +548,6 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
     const double L = P.box[rep * 2], h = P.box[rep * 2 + 1];
     const bool pbc = P.bc_kind != PTMC_BC_SPHERICAL;
     const bool npt = P.ensemble == PTMC_ENS_NPT;
-    const bool rhombic = P.bc_kind == PTMC_BC_RHOMBIC;
-    Box bx = make_box(P.bc_kind, pbc ? L : 1.0, pbc ? h : 1.0);
     const double rcut = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
     if (POT == PTMC_POT_EAM) {
         double se = 0.0;
@@ -552,16 +567,23 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
         if (g == 0) P.en_tot[rep] = se;
     } else {
         double acc = 0.0;
+        double* D = pbc ? P.d2mat + (size_t)rep * N * N : nullptr;   // perm is the identity right after an upload
         for (int a = 0; a < N - 1; ++a) {
             const double xa = gp[3 * a], ya = gp[3 * a + 1], za = gp[3 * a + 2];
             for (int j = a + 1 + g; j < N; j += 32) {
                 double d2;
-                if (pbc) d2 = rhombic ? dist2_pbc<true>(bx, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2])
-                                      : dist2_pbc<false>(bx, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2]);
-                else { double dx = xa - gp[3 * j], dy = ya - gp[3 * j + 1], dz = za - gp[3 * j + 2]; d2 = fma(dz, dz, fma(dy, dy, dx * dx)); }
+                if (pbc) {
+                    // get_distance2_mat! src/Configurations.jl:146-162: dest[i,j] = dest[j,i] = distance2(c[i], c[j], bc)
+                    d2 = dist2_exact(P.bc_kind, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], L, h);
+                    D[(size_t)a * N + j] = d2; D[(size_t)j * N + a] = d2;
+                } else {
+                    double dx = xa - gp[3 * j], dy = ya - gp[3 * j + 1], dz = za - gp[3 * j + 2];
+                    d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                }
                 if (!npt || d2 <= rcut) acc += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT>(P, d2);
             }
         }
+        if (pbc) for (int a = g; a < N; a += 32) D[(size_t)a * N + a] = 0.0;
         double e = group_sum<32>(acc, 0xffffffffu);
         if (npt) {
             const double l = lrc_even(P, rcut);
