@@ -59,7 +59,7 @@ def workload_config(ladders, cycles):
     return {"workload": "Ne55 ELJ NVT (scripts/ne55.jl), 24-temperature ladder, %d independent PT ladders per GPU" % ladders,
             "n_atoms": N_ATOMS, "n_traj": N_TRAJ, "ladders_per_gpu": ladders, "cycles_per_step": cycles,
             "moves_per_step_per_gpu": ladders * N_TRAJ * N_ATOMS * cycles,
-            "rng": "Xoshiro256++ per slot (Julia default), seeded Random.seed!(seed + k)",
+            "rng": "PTMC_RNG_BATCH8: 8 Xoshiro256++ substreams per slot (Julia's generator), seeded Random.seed!(seed + k)",
             "l2": "flushed between timed steps (256 MiB write); resident state 130 MB > 126 MB L2"}
 
 
@@ -178,8 +178,10 @@ def run_b200(args):
 
     L, cycles = args.ladders, args.cycles
     mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=N_TRAJ, cycles=cycles)
-    # ladder l of rank r is global ladder r*L + l: distinct seeds across the whole job
-    seed = 1234 + rank * L * (N_TRAJ + 1)
+    # ladder l of rank r is global ladder r*L + l of a job of world*L ladders: streams are indexed globally
+    # (ptmc_b200.multi), so per-ladder results do not depend on the number of GPUs
+    from ptmc_b200 import multi
+    seed = 1234
     cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=seed, device=local, lanes_per_replica=args.lanes)
     eng = Engine(cfg)
     stream = torch.cuda.Stream(device=dev)
@@ -188,7 +190,10 @@ def run_b200(args):
     pin_pos = torch.from_numpy(pos).pin_memory()
     pin_box = torch.from_numpy(box).pin_memory()
     eng.upload_states(pin_pos.numpy(), pin_box.numpy())
-    eng.seed(seed)
+    if world > 1:
+        multi.seed_global(eng, seed, rank * L, world * L)
+    else:
+        eng.seed(seed)
     # equilibrate a little so that step sizes have adapted and the histogram window is meaningful
     eng.run_cycles(1, 200, False)
     en = eng.download_states(("en_tot",))["en_tot"]
