@@ -1,0 +1,183 @@
+# PTMCB200.jl — the binding a maintainer of ParallelTemperingMonteCarlo.jl adds to run the sweep hot path on a B200
+# through libptmc_b200.so (C ABI: include/ptmc_b200.h).  Thin by design: it converts the package's own types into the
+# POD config + flat arrays of the ABI, calls `ccall`, and fills the package's own `MCState`s / `Output` back.
+#
+# NOT executed in the build image (no Julia there); the same call sequence is exercised from Python by
+# paralleltemperingmontecarlo.jl_b200/engine.py + host.py (ptmc_run), which the tests and bench.py drive.
+#
+#   using ParallelTemperingMonteCarlo, PTMCB200
+#   backend = B200Backend(lib = "/path/to/libptmc_b200.so", device = 0, n_ladders = 1)
+#   states, results = ptmc_run!(backend, mc_params, temp, start_config, potential, ensemble)
+module PTMCB200
+
+using ParallelTemperingMonteCarlo
+using ParallelTemperingMonteCarlo: MCParams, TempGrid, Config, MCState, Output, NVT, NPT,
+    SphericalBC, CubicBC, RhombicBC, RectangularBC, ELJPotential, ELJPotentialEven, EmbeddedAtomPotential,
+    initialisation, finalise_results, initialise_histograms!, check_e_bounds, get_volume
+
+export B200Backend, ptmc_run!
+
+const PTMC_ABI_VERSION = Int32(1)
+const PTMC_MAX_COEFF = 16
+const PTMC_NCOUNT = 10
+
+Base.@kwdef struct B200Backend
+    lib::String
+    device::Int = 0
+    n_ladders::Int = 1          # independent ladders (seeds) batched on the device; results of ladder 1 are returned
+    seed::UInt64 = 1234
+    rng_mode::Int32 = 2         # PTMC_RNG_BATCH8
+    lanes_per_replica::Int32 = 0
+    chunk::Int = 100_000        # cycles per ccall (the driver touches states only at save / saveconfigs cadence)
+end
+
+# mirror of `ptmc_config` (include/ptmc_b200.h); field order and types must match the header
+struct PtmcConfig
+    abi_version::Int32
+    device::Int32
+    n_ladders::Int64
+    n_traj::Int32
+    n_atoms::Int32
+    ensemble::Int32
+    n_atom_moves::Int32
+    n_volume_moves::Int32
+    bc_kind::Int32
+    pressure::Float64
+    pot_kind::Int32
+    n_coeff::Int32
+    coeff::NTuple{PTMC_MAX_COEFF,Float64}
+    eam_n::Float64
+    eam_m::Float64
+    eam_ean::Float64
+    eam_ecam::Float64
+    runner::Ptr{Cvoid}
+    betas::Ptr{Float64}
+    n_adjust::Int32
+    mc_sample::Int32
+    n_bin::Int32
+    rng_mode::Int32
+    min_acc::Float64
+    max_acc::Float64
+    seed::UInt64
+    lanes_per_replica::Int32
+    reserved::Int32
+end
+
+bc_kind(::SphericalBC) = Int32(0); bc_kind(::CubicBC) = Int32(1); bc_kind(::RhombicBC) = Int32(2); bc_kind(::RectangularBC) = Int32(3)
+box_of(bc::SphericalBC) = (bc.radius2, 0.0)
+box_of(bc::CubicBC) = (bc.box_length, bc.box_length)
+box_of(bc::Union{RhombicBC,RectangularBC}) = (bc.box_length, bc.box_height)
+
+pot_fields(p::ELJPotential{N}) where {N} = (Int32(0), Int32(N), Tuple(p.coeff), (0.0, 0.0, 0.0, 0.0))
+pot_fields(p::ELJPotentialEven{N}) where {N} = (Int32(1), Int32(N), Tuple(p.coeff), (0.0, 0.0, 0.0, 0.0))
+pot_fields(p::EmbeddedAtomPotential) = (Int32(2), Int32(0), (), (p.n, p.m, p.ean, p.eCam))
+
+pad16(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, PTMC_MAX_COEFF)
+
+function check(lib, h, rc)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:ptmc_last_error, lib), Cstring, (Ptr{Cvoid},), h))
+    error("libptmc_b200: $msg (code $rc)")     # same text as the reference for PTMC_ERR_SPHERE
+end
+
+"""
+    ptmc_run!(backend::B200Backend, mc_params, temp, start_config, potential, ensemble; save=false, saveconfigs=false, ...)
+
+Drop-in for `ptmc_run!` (src/MCRun.jl:363-432): same arguments after `backend`, same return value
+`(mc_states, results)`.  The sweep (`mc_cycle!`, src/MCRun.jl:192-253) runs on the device in chunks; states come
+back to the host only where the reference's driver touches them (histogram bounds after equilibration, checkpoints,
+end of run).
+"""
+function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCParams, temp::TempGrid, start_config,
+                                               potential, ensemble; save=false, saveconfigs=false, kwargs...)
+    lib = b.lib
+    # the package's own initialisation builds MCStates (host copies), MoveStrategy and the empty Output
+    mc_states, move_strategy, results, n_steps, _ = initialisation(mc_params, temp, start_config, potential, ensemble)
+    T, N, L = mc_params.n_traj, mc_params.n_atoms, b.n_ladders
+    bc = mc_states[1].config.boundary_condition
+    pk, nc, coeff, eam = pot_fields(potential)
+    npt = ensemble isa NPT
+    betas = collect(Float64, temp.beta_grid)
+    cfg = Ref(PtmcConfig(PTMC_ABI_VERSION, b.device, L, T, N, npt ? 1 : 0, ensemble.n_atom_moves,
+        npt ? ensemble.n_volume_moves : 0, bc_kind(bc), npt ? ensemble.pressure : 0.0, pk, nc, pad16(coeff),
+        eam..., C_NULL, pointer(betas), mc_params.n_adjust, mc_params.mc_sample, mc_params.n_bin, b.rng_mode,
+        mc_params.min_acc, mc_params.max_acc, b.seed, b.lanes_per_replica, 0))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve betas begin
+        rc = ccall((:ptmc_create, lib), Cint, (Ref{PtmcConfig}, Ref{Ptr{Cvoid}}), cfg, h)
+    end
+    rc == 0 || error("libptmc_b200: " * unsafe_string(ccall((:ptmc_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+    try
+        # state in: positions [L][T][N][3] (row-major = Julia (3, N, T, L)), box [L][T][2]
+        pos = Array{Float64}(undef, 3, N, T, L); box = Array{Float64}(undef, 2, T, L)
+        for l in 1:L, t in 1:T
+            for (j, p) in enumerate(mc_states[t].config.positions); pos[:, j, t, l] .= p; end
+            box[:, t, l] .= box_of(mc_states[t].config.boundary_condition)
+        end
+        check(lib, h[], ccall((:ptmc_upload_states, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), h[], pos, box, C_NULL))
+        # equilibration_cycle! (src/MCRun.jl:282-313): MC for eq_cycles ÷ 2 cycles, then the energy bounds
+        n_eq = mc_params.eq_cycles ÷ 2
+        n_eq > 0 && check(lib, h[], ccall((:ptmc_run_cycles, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Cint), h[], 1, n_eq, 0))
+        en = Array{Float64}(undef, T, L)
+        check(lib, h[], ccall((:ptmc_download_states, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
+                              h[], C_NULL, C_NULL, en, C_NULL, C_NULL, C_NULL))
+        ebounds = [100.0, -100.0]
+        for _ in (n_eq + 1):mc_params.eq_cycles, t in 1:T
+            ebounds = check_e_bounds(en[t, 1], ebounds)
+        end
+        initialise_histograms!(mc_params, results, ebounds, bc)          # fills en_min/en_max/v_min/v_max/deltas
+        check(lib, h[], ccall((:ptmc_reset_counters, lib), Cint, (Ptr{Cvoid},), h[]))
+        check(lib, h[], ccall((:ptmc_set_hist_bounds, lib), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}, Ref{Float64}, Ref{Float64}, Cint),
+                              h[], results.en_min, results.en_max, results.v_min, results.v_max, 0))
+        # main loop (src/MCRun.jl:397-421) in chunks that end where the reference's driver would look at the states
+        stops = filter(x -> x !== false, (save, saveconfigs))
+        i = 1
+        while i <= mc_params.mc_cycles
+            k = min(b.chunk, mc_params.mc_cycles - i + 1)
+            for s in stops; k = min(k, s - rem(i - 1, s)); end
+            check(lib, h[], ccall((:ptmc_run_cycles, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Cint), h[], i, k, 1))
+            i += k
+            if any(s -> rem(i - 1, s) == 0, stops)
+                download!(lib, h[], mc_states, results, N, T, L, npt)
+                save !== false && rem(i - 1, save) == 0 && ParallelTemperingMonteCarlo.checkpoint(i - 1, mc_states, results, ensemble, false)
+                saveconfigs !== false && rem(i - 1, saveconfigs) == 0 && ParallelTemperingMonteCarlo.save_configs(mc_states, string("configuration", i - 1))
+            end
+        end
+        download!(lib, h[], mc_states, results, N, T, L, npt)
+    finally
+        ccall((:ptmc_destroy, lib), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    results = finalise_results(mc_states, mc_params, results)
+    return mc_states, results
+end
+
+# state out: refill the host MCStates of ladder 1 and the histograms of `results`
+function download!(lib, h, mc_states, results, N, T, L, npt)
+    pos = Array{Float64}(undef, 3, N, T, L); box = Array{Float64}(undef, 2, T, L); en = Array{Float64}(undef, T, L)
+    md = Array{Float64}(undef, 4, T, L); cnt = Array{Int64}(undef, PTMC_NCOUNT, T, L); ham = Array{Float64}(undef, 2, T, L)
+    check(lib, h, ccall((:ptmc_download_states, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
+                        h, pos, box, en, md, cnt, ham))
+    for t in 1:T
+        s = mc_states[t]
+        for j in 1:N; s.config.positions[j] = typeof(s.config.positions[j])(pos[1, j, t, 1], pos[2, j, t, 1], pos[3, j, t, 1]); end
+        s.en_tot = en[t, 1]; s.max_displ .= md[:, t, 1]; s.ham .= ham[:, t, 1]
+        s.count_atom .= cnt[1:2, t, 1]; s.count_vol .= cnt[3:4, t, 1]; s.count_exc .= cnt[9:10, t, 1]
+        ParallelTemperingMonteCarlo.get_distance2_mat!(s.dist2_mat, s.config)     # derived state, recomputed on the host
+    end
+    nb2 = results.n_bin + 2
+    if npt
+        ev = Array{Float64}(undef, nb2, nb2, T, L)       # row-major [L][T][E][V] -> Julia (V, E, T, L)
+        check(lib, h, ccall((:ptmc_download_hist, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint), h, C_NULL, ev, 0))
+        for t in 1:T; results.ev_histogram[t] .= permutedims(ev[:, :, t, 1]); end
+    else
+        eh = Array{Float64}(undef, nb2, T, L)
+        check(lib, h, ccall((:ptmc_download_hist, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint), h, eh, C_NULL, 0))
+        for t in 1:T; results.en_histogram[t] .= eh[:, t, 1]; end
+    end
+    return nothing
+end
+
+# RuNNer forward pass: point the package's `lib_path()` at the directory holding a copy/symlink of libptmc_b200.so named
+# librunnerjulia.so; the `forward` symbol has the Fortran library's exact ABI (MachineLearningPotential/ForwardPass.jl:60-83).
+
+end # module
