@@ -58,6 +58,11 @@ def load():
         "orc_download_hist": (C.c_int, [_vp, _dp, _dp, C.c_int]),
         "orc_get_dist2_mat": (C.c_int, [_vp, C.c_int64, _dp]),
         "orc_probe_atom_move": (C.c_int, [_vp, C.c_int64, C.c_int, _dp, _dp]),
+        "orc_get_runner_state": (C.c_int, [_vp, C.c_int64, _dp, _dp]),
+        "orc_cutoff": (C.c_double, [C.c_double, C.c_double]),
+        "orc_runner_forward_raw": (None, [_dp, C.c_int, _ip, _ip, _dp, C.c_int, _dp]),
+        "orc_runner2_energy": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
+                                            C.c_int, _ip, _ip, _dp, _dp, _dp]),
         "orc_julia_seed": (None, [C.c_uint64, _u64p]),
         "orc_xoshiro_next": (C.c_uint64, [_u64p]),
         "orc_rand_from_state": (C.c_double, [_u64p]),
@@ -144,6 +149,40 @@ def tempgrid(ti, tf, n):
     return t, b
 
 
+def cutoff(r, r_cut):
+    return load().orc_cutoff(r, r_cut)
+
+
+def runner_forward(inp, nodes, act, params):
+    """forward: inp [batch][n_in] -> eatom [batch]"""
+    x, px = _arr(inp)
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    ac = np.ascontiguousarray(act, dtype=np.int32)
+    pr, pp = _arr(params)
+    e = np.zeros(x.shape[0])
+    load().orc_runner_forward_raw(px, len(nd), nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp, x.shape[0], e.ctypes.data_as(_dp))
+    return e
+
+
+def runner2_energy(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, nodes, act, params1, params2):
+    """2-species initial energy (KAT checker, test/test_potentials.jl:67-87) -> (E, f_matrix[1,2])"""
+    p, pp = _arr(pos)
+    re_, pre = _arr(rad_eta)
+    ae, pae = _arr(ang_eta)
+    al, pal = _arr(ang_lambda)
+    az, paz = _arr(ang_zeta)
+    ga, pga = _arr(gmaxmin_a)
+    gb, pgb = _arr(gmaxmin_b)
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    ac = np.ascontiguousarray(act, dtype=np.int32)
+    p1, pp1 = _arr(params1)
+    p2, pp2 = _arr(params2)
+    f12 = C.c_double()
+    e = load().orc_runner2_energy(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
+                                  nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, C.cast(C.byref(f12), _dp))
+    return e, f12.value
+
+
 class OracleEngine(Engine):
     """Engine-compatible driver of the CPU oracle."""
 
@@ -174,6 +213,16 @@ class OracleEngine(Engine):
         out = np.zeros((n, n))
         self.lib.orc_get_dist2_mat(self._h, ladder * self.cfg.n_traj + slot, out.ctypes.data_as(_dp))
         return out
+
+    def runner_state(self, ladder: int, slot: int):
+        """(g_matrix [atom][n_sym], en_atom [atom]) of one replica (RuNNer)"""
+        n = self.cfg.n_atoms
+        ns = len(self.cfg.runner.rad_eta) + len(self.cfg.runner.ang_eta)
+        g, e = np.zeros((n, ns)), np.zeros(n)
+        rc = self.lib.orc_get_runner_state(self._h, ladder * self.cfg.n_traj + slot, g.ctypes.data_as(_dp), e.ctypes.data_as(_dp))
+        if rc:
+            raise PtmcError(rc, "not a RuNNer handle")
+        return g, e
 
     def probe_atom_move(self, ladder: int, slot: int, index1: int):
         trial = np.zeros(3)

@@ -27,6 +27,20 @@
 #include <omp.h>
 #endif
 
+/* RuNNer potential: oracle/runner_oracle.c */
+typedef struct orc_runner orc_runner;
+orc_runner* orc_runner_new(const ptmc_runner_desc* d);
+void orc_runner_free(orc_runner* r);
+int orc_runner_nsym(const orc_runner* r);
+double orc_runner_boundary2(const orc_runner* r);
+double orc_runner_rcut(const orc_runner* r);
+double orc_cutoff(double r_ij, double r_cut);
+void orc_runner_fmatrix(const orc_runner* r, const double* d2, int n, double* f);
+void orc_runner_init_g(const orc_runner* r, const double* pos, const double* d2, const double* f, int n, double* g);
+void orc_runner_forward(const orc_runner* r, const double* g, int n, double* eatom);
+void orc_runner_delta(const orc_runner* r, const double* pos, const double* newpos, const double* d2, const double* new_d2,
+                      const double* f, const double* new_f, int i, int n, double* g);
+
 /* ======================================================================================= SHA-256 == */
 /* Needed only for Random.seed!(n): Julia hashes the seed's little-endian UInt32 words. */
 static const uint32_t K256[64] = {
@@ -263,6 +277,8 @@ typedef struct orc_cfgside { /* everything exc_trajectories! swaps (src/Exchange
     double new_r_cut;
     double* comp;     /* EAM component_vector [N][2] */
     double* new_comp; /* EAM new_component_vector */
+    /* NNPVariables src/EnergyEvaluation.jl:1229-1236 */
+    double *fmat, *new_f, *g, *new_g, *en_atom, *new_en_atom;
 } orc_cfgside;
 
 typedef struct orc_state { /* MCState src/MCStates.jl:33-53; slot-side fields stay put at exchange */
@@ -294,6 +310,7 @@ typedef struct orc_handle {
     int32_t* tr_index; double* tr_de; uint8_t* tr_acc; int32_t* tr_exc;
     int error;
     int n_threads;
+    orc_runner* runner;
 } orc_handle;
 
 static int n_steps_of(const ptmc_config* c) { return c->n_atom_moves + (c->ensemble == PTMC_ENS_NPT ? c->n_volume_moves : 0); }
@@ -346,6 +363,19 @@ static void d2_matrix(const ptmc_config* c, const double* pos, const double* box
 }
 
 /* MCState(temp,beta,config,ensemble,pot) src/MCStates.jl:137-162 */
+static void init_cfgside_runner(const orc_runner* R, orc_cfgside* s, int n) {
+    /* set_variables(::RuNNerPotential) src/EnergyEvaluation.jl:1812-1822 + initialise_energy :1735-1747 */
+    orc_runner_fmatrix(R, s->d2, n, s->fmat);
+    orc_runner_init_g(R, s->pos, s->d2, s->fmat, n, s->g);
+    memcpy(s->new_g, s->g, sizeof(double) * (size_t)n * orc_runner_nsym(R));
+    orc_runner_forward(R, s->g, n, s->en_atom);
+    double e = 0.0;
+    for (int i = 0; i < n; ++i) e += s->en_atom[i];
+    s->en_tot = e;
+    memset(s->new_en_atom, 0, sizeof(double) * n);
+    memset(s->new_f, 0, sizeof(double) * n);
+}
+
 static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
     int n = c->n_atoms;
     d2_matrix(c, s->pos, s->box, s->d2, n);
@@ -364,6 +394,8 @@ static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
             s->new_comp[2 * i] = 0; s->new_comp[2 * i + 1] = 0;
         }
         s->en_tot = eam_energy(c, s->comp, n); /* initialise_energy :1722-1734 */
+    } else if (c->pot_kind == PTMC_POT_RUNNER) {
+        /* done by the caller (needs the handle's orc_runner) */
     } else {
         s->en_tot = dimer_energy_config(c, s->d2, n, npt, s->r_cut, s->box); /* :1662-1693 */
     }
@@ -473,7 +505,24 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
         for (int j = 0; j < n; ++j) st->new_d2[j] = orc_distance2(c->bc_kind, trial, s->pos + 3 * j, s->box[0], s->box[1]);
         st->new_d2[i] = 0.0;
         /* get_energy! src/MCRun.jl:47-87 -> energy_update! */
-        if (c->pot_kind == PTMC_POT_EAM) {
+        if (c->pot_kind == PTMC_POT_RUNNER) {
+            /* energy_update!(::RuNNerPotential) src/EnergyEvaluation.jl:1593-1621 */
+            const orc_runner* R = H->runner;
+            int too_close = 0;
+            for (int j = 0; j < n; ++j) if (j != i && st->new_d2[j] < orc_runner_boundary2(R)) too_close = 1;
+            if (too_close) {
+                st->new_en = 100.0;
+            } else {
+                /* get_new_state_vars! :1238-1264, calc_new_runner_energy! :1269-1275 */
+                for (int j = 0; j < n; ++j) s->new_f[j] = orc_cutoff(sqrt(st->new_d2[j]), orc_runner_rcut(R));
+                memcpy(s->new_g, s->g, sizeof(double) * (size_t)n * orc_runner_nsym(R));
+                orc_runner_delta(R, s->pos, trial, s->d2, st->new_d2, s->fmat, s->new_f, i, n, s->new_g);
+                orc_runner_forward(R, s->new_g, n, s->new_en_atom);
+                double e = 0.0;
+                for (int j = 0; j < n; ++j) e += s->new_en_atom[j];
+                st->new_en = e;
+            }
+        } else if (c->pot_kind == PTMC_POT_EAM) {
             /* src/EnergyEvaluation.jl:1567-1591 + calc_components :1111-1127 */
             memcpy(s->new_comp, s->comp, sizeof(double) * 2 * n);
             for (int j = 0; j < n; ++j) {
@@ -504,6 +553,11 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             double tmp = s->en_tot; s->en_tot = st->new_en; st->new_en = tmp;
             st->count[PTMC_C_ATOM_TOT] += 1; st->count[PTMC_C_ATOM_ADJ] += 1;
             if (c->pot_kind == PTMC_POT_EAM) { double* t = s->comp; s->comp = s->new_comp; s->new_comp = t; } /* swap_vars! :208-211 */
+            if (c->pot_kind == PTMC_POT_RUNNER) {   /* swap_vars!(::NNPVariables) src/swap_config.jl:213-221 */
+                double* t = s->en_atom; s->en_atom = s->new_en_atom; s->new_en_atom = t;
+                t = s->g; s->g = s->new_g; s->new_g = t;
+                for (int j = 0; j < n; ++j) { s->fmat[(size_t)i * n + j] = s->new_f[j]; s->fmat[(size_t)j * n + i] = s->new_f[j]; }
+            }
         }
     } else {
         /* volume_change_uniform src/MCMoves.jl:277-287, volume_change_xyz :169-177 */
@@ -672,9 +726,11 @@ static void* xcalloc(size_t n, size_t sz) { void* p = calloc(n ? n : 1, sz); if 
 
 int orc_seed(orc_handle* H, uint64_t seed);
 orc_handle* orc_create(const ptmc_config* cfg) {
-    if (cfg->pot_kind == PTMC_POT_RUNNER) return NULL; /* handled by runner_oracle.c */
+    if (cfg->pot_kind == PTMC_POT_RUNNER && (!cfg->runner || cfg->bc_kind != PTMC_BC_SPHERICAL)) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
     H->cfg = *cfg;
+    if (cfg->pot_kind == PTMC_POT_RUNNER) H->runner = orc_runner_new(cfg->runner);
+    H->cfg.runner = NULL;
     const int n = cfg->n_atoms, nt = cfg->n_traj;
     H->betas = (double*)xcalloc(nt, sizeof(double));
     memcpy(H->betas, cfg->betas, sizeof(double) * nt);
@@ -690,6 +746,12 @@ orc_handle* orc_create(const ptmc_config* cfg) {
         s->d2 = (double*)xcalloc((size_t)n * n, sizeof(double));
         if (npt) { s->trial_pos = (double*)xcalloc(3 * n, sizeof(double)); s->new_d2mat = (double*)xcalloc((size_t)n * n, sizeof(double)); }
         if (cfg->pot_kind == PTMC_POT_EAM) { s->comp = (double*)xcalloc(2 * n, sizeof(double)); s->new_comp = (double*)xcalloc(2 * n, sizeof(double)); }
+        if (cfg->pot_kind == PTMC_POT_RUNNER) {
+            const size_t ns = (size_t)orc_runner_nsym(H->runner);
+            s->fmat = (double*)xcalloc((size_t)n * n, 8); s->new_f = (double*)xcalloc(n, 8);
+            s->g = (double*)xcalloc(n * ns, 8); s->new_g = (double*)xcalloc(n * ns, 8);
+            s->en_atom = (double*)xcalloc(n, 8); s->new_en_atom = (double*)xcalloc(n, 8);
+        }
         orc_state* st = &H->st[r];
         st->c = s;
         st->beta = H->betas[r % nt];
@@ -712,11 +774,13 @@ void orc_destroy(orc_handle* H) {
     for (int64_t r = 0; r < H->n_rep; ++r) {
         orc_cfgside* s = &H->cs[r];
         free(s->pos); free(s->d2); free(s->trial_pos); free(s->new_d2mat); free(s->comp); free(s->new_comp);
+        free(s->fmat); free(s->new_f); free(s->g); free(s->new_g); free(s->en_atom); free(s->new_en_atom);
         free(H->st[r].new_d2);
     }
     free(H->st); free(H->cs); free(H->lrng); free(H->betas);
     free(H->en_min); free(H->en_max); free(H->v_min); free(H->v_max); free(H->en_hist); free(H->ev_hist);
     free(H->tr_index); free(H->tr_de); free(H->tr_acc); free(H->tr_exc);
+    orc_runner_free(H->runner);
     free(H);
 }
 
@@ -739,7 +803,10 @@ int orc_upload_states(orc_handle* H, const double* pos, const double* box, const
         st->new_en = 0.0;
     }
 #pragma omp parallel for schedule(dynamic) num_threads(H->n_threads)
-    for (int64_t r = 0; r < H->n_rep; ++r) init_cfgside(c, &H->cs[r]);
+    for (int64_t r = 0; r < H->n_rep; ++r) {
+        init_cfgside(c, &H->cs[r]);
+        if (c->pot_kind == PTMC_POT_RUNNER) init_cfgside_runner(H->runner, &H->cs[r], n);
+    }
     return 0;
 }
 
@@ -925,5 +992,14 @@ int orc_probe_atom_move(orc_handle* H, int64_t replica, int index1, double* tria
     double new_en = delta + s->en_tot;
     memcpy(trial_out, trial, sizeof trial);
     *delta_en = new_en - s->en_tot;
+    return 0;
+}
+
+/* RuNNer: g_matrix [atom][n_sym] and per-atom energies of one replica (tests) */
+int orc_get_runner_state(orc_handle* H, int64_t replica, double* g, double* en_atom) {
+    if (!H->runner) return PTMC_ERR_ARG;
+    const size_t ns = (size_t)orc_runner_nsym(H->runner), n = (size_t)H->cfg.n_atoms;
+    if (g) memcpy(g, H->st[replica].c->g, sizeof(double) * n * ns);
+    if (en_atom) memcpy(en_atom, H->st[replica].c->en_atom, sizeof(double) * n);
     return 0;
 }

@@ -402,3 +402,43 @@ def deck_pbc216(n_traj=16, cycles=100):
     ens = NPT(216, 50000000000 * 2.2937122783969076e-13 / (a2b * a2b * a2b), False)
     return (MCParams(cycles, n_traj, 216), TempGrid(1600.0, 2100.0, n_traj), [Config(fcc, bc), Config(hcp, bc)],
             ELJPotentialEven(ELJ_NE_COEFF), ens)
+
+
+# scripts/cu55.jl:55-100: radial (type, eta) rows and angular (eta, lambda, zeta) rows of the Cu network
+CU_RADIAL = ((11, 0.001), (10, 0.001), (11, 0.020), (10, 0.020), (11, 0.035), (10, 0.035), (11, 0.100), (10, 0.100),
+             (11, 0.400), (10, 0.400))
+CU_ANGULAR = ((0.0001, 1, 1), (0.0001, -1, 2), (0.003, -1, 1), (0.003, -1, 2), (0.008, -1, 1), (0.008, -1, 2), (0.008, 1, 2),
+              (0.015, 1, 1), (0.015, -1, 2), (0.015, -1, 4), (0.015, -1, 16), (0.025, -1, 1), (0.025, 1, 1), (0.025, 1, 2),
+              (0.025, -1, 4), (0.025, -1, 16), (0.025, 1, 16), (0.045, 1, 1), (0.045, -1, 2), (0.045, -1, 4), (0.045, 1, 4),
+              (0.045, 1, 16), (0.08, 1, 1), (0.08, -1, 2), (0.08, -1, 4), (0.08, 1, 4))
+CU_ANGULAR_TYPES = (111, 110, 100)
+RUNNER_R_CUT = 11.338
+
+
+def load_scaling(path=None):
+    """scaling.data rows (element, index, G_min, G_max, G_avg) -> [n][2] {G_max, G_min} as scripts/cu55.jl:104-112"""
+    rows = np.loadtxt(path or DATA_DIR / "scaling.data", usecols=(0, 1, 2, 3, 4), max_rows=176)   # a 2-number footer follows
+    return np.stack([rows[:, 3], rows[:, 2]], axis=1)
+
+
+def cu_runner_potential(boundary: float = 0.0, weights=None, scaling=None):
+    """scripts/cu55.jl:55-153: 10 radial + 78 angular symmetry functions, network 88-20-20-1 (weights.029.data).
+    The script passes boundary = 28 Angstrom, which rejects every move; the default here is the
+    3-argument constructor's 0.0 (scripts/cu38.jl:151)."""
+    g = load_scaling(scaling)[:88]
+    radial = [(t, eta, RUNNER_R_CUT, g[k, 0], g[k, 1]) for k, (t, eta) in enumerate(CU_RADIAL)]
+    angular = []
+    n_index = 10
+    for eta, lam, zeta in CU_ANGULAR:
+        for t in CU_ANGULAR_TYPES:
+            angular.append((eta, lam, zeta, RUNNER_R_CUT, t, g[n_index, 0], g[n_index, 1]))
+            n_index += 1
+    w = np.loadtxt(weights or DATA_DIR / "weights.029.data").ravel()
+    return RuNNerPotential([88, 20, 20, 1], [1, 2, 2, 1], w, radial, angular, boundary)
+
+
+def deck_cu55_runner(n_traj=28, cycles=100, boundary: float = 0.0):
+    """scripts/cu55.jl with `runnerpotential` (BASELINE C5)"""
+    a2b = 1.8897259886
+    start = Config(cu55_geometry(), SphericalBC(radius=14 * a2b))
+    return (MCParams(cycles, n_traj, 55), TempGrid(400.0, 1200.0, n_traj), start, cu_runner_potential(boundary), NVT(55))
