@@ -230,6 +230,10 @@ PTMC_API int ptmc_fp64_peak(int device, int iters, double* tflops);
  * (ELJ / ELJEven: dimer_energy src/EnergyEvaluation.jl:923-942; EAM: the r^-n term of invrexp :1088-1095). */
 PTMC_API int ptmc_debug_pair_energy(ptmc_handle* h, int n, const double* d2_new, const double* d2_old, double* e_new, double* e_old);
 
+/* RuNNer (tests): the g_matrix [n_atoms][n_rad + n_ang] (= Julia's column-major (n_sym x N) NNPVariables.g_matrix) and
+ * the per-atom energies en_atom_vec of the configuration currently held by (ladder, slot). */
+PTMC_API int ptmc_debug_runner_state(ptmc_handle* h, int64_t ladder, int32_t slot, double* g_matrix, double* en_atom);
+
 /* ---- RuNNer forward pass: drop-in for librunnerjulia.so ------------------------------------------ */
 /* Exact ABI of the Fortran symbol the reference ccall()s (ForwardPass.jl:60-83): every argument by
  * reference, caller owns eatom.  Re-entrant. The Float64 return value is the last atom's energy. */

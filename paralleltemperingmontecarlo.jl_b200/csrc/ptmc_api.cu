@@ -8,6 +8,9 @@
 #include <string>
 #include <vector>
 
+#include <cmath>
+
+#include "runner_dev.cuh"
 #include "sweep_kernel.cuh"
 
 namespace ptmc {
@@ -20,7 +23,12 @@ void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
 double measure_fp64_peak(cudaStream_t st, int iters);
 int run_pair_probe(const DevParams& P, int n, const double* h_d2n, const double* h_d2o, double* h_en, double* h_eo);
-struct RunnerState;
+size_t runner_smem_bytes(int N, const RunnerDev& R);
+cudaError_t runner_prepare(int N, const RunnerDev& R);
+void runner_launch_init(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaStream_t st);
+int runner_launch_cycle(const DevParams& P, const RunnerDev& R, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st);
+void runner_launch_gather(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaStream_t st);
+void runner_launch_export(const DevParams& P, const RunnerDev& R, i64 rep, double* g_out, double* e_out, cudaStream_t st);
 }  // namespace ptmc
 
 using namespace ptmc;
@@ -31,6 +39,8 @@ struct ptmc_handle {
     ptmc_config cfg;
     std::vector<double> betas;
     DevParams P;
+    RunnerDev R;
+    bool runner = false;
     int device = 0;
     int G = 0;
     int threads = 0;
@@ -134,6 +144,75 @@ static sweep_fn pick_kernel(const ptmc_handle* h, int dbg) {
 // words of generator state per slot
 static int rng_words(const ptmc_handle* h) { return h->cfg.rng_mode == PTMC_RNG_BATCH8 ? 4 * PTMC_RNG_LANES : 4; }
 
+// RuNNerPotential -> RunnerDev: keep the evaluated symmetry functions only (type 11 / 111), find the distinct eta and
+// (lambda, zeta) values of the angular ones, sort those by (lambda, zeta) so that the kernel computes each angular
+// factor once, and restrict the first network layer to the evaluated rows.
+static int build_runner(ptmc_handle* h, const ptmc_runner_desc* d, std::vector<double>& net_host) {
+    RunnerDev& R = h->R;
+    memset(&R, 0, sizeof R);
+    if (!d->rad_eta || !d->rad_type || !d->rad_gmax_gmin || !d->ang_eta || !d->ang_lambda || !d->ang_zeta || !d->ang_type ||
+        !d->ang_gmax_gmin || !d->num_nodes || !d->activation || !d->params)
+        return fail(h, PTMC_ERR_ARG, "ptmc_runner_desc has null tables");
+    R.n_rad = d->n_rad; R.n_ang = d->n_ang; R.n_sym = d->n_rad + d->n_ang;
+    R.r_cut = d->r_cut; R.boundary2 = d->boundary2;
+    for (int k = 0; k < d->n_rad; ++k) {
+        if (d->rad_type[k] != 11) continue;
+        if (R.n_act_rad == RN_MAX_RAD) return fail(h, PTMC_ERR_ARG, "more than %d evaluated radial symmetry functions", RN_MAX_RAD);
+        const int q = R.n_act_rad++;
+        const double gmax = d->rad_gmax_gmin[2 * k], gmin = d->rad_gmax_gmin[2 * k + 1];
+        R.rad_eta[q] = d->rad_eta[k];
+        R.rad_norm[q] = 1 / (gmax - gmin);                    // SymmFunc.jl:40-44
+        R.rad_off[q] = -gmin * R.rad_norm[q];
+        R.act_row[q] = k;
+    }
+    struct Ang { int e, z, row, init; double tpz, off; };
+    std::vector<Ang> ang;
+    for (int a = 0; a < d->n_ang; ++a) {
+        if (d->ang_type[a] != 111) continue;
+        int e = -1, z = -1;
+        for (int k = 0; k < R.n_eta; ++k) if (R.eta[k] == d->ang_eta[a]) e = k;
+        if (e < 0) {
+            if (R.n_eta == RN_MAX_ETA) return fail(h, PTMC_ERR_ARG, "more than %d distinct eta among the angular symmetry functions", RN_MAX_ETA);
+            e = R.n_eta++; R.eta[e] = d->ang_eta[a];
+        }
+        for (int k = 0; k < R.n_lz; ++k) if (R.lz_lambda[k] == d->ang_lambda[a] && R.lz_zeta[k] == d->ang_zeta[a]) z = k;
+        if (z < 0) {
+            if (R.n_lz == RN_MAX_LZ) return fail(h, PTMC_ERR_ARG, "more than %d distinct (lambda, zeta) among the angular symmetry functions", RN_MAX_LZ);
+            z = R.n_lz++; R.lz_lambda[z] = d->ang_lambda[a]; R.lz_zeta[z] = d->ang_zeta[a];
+            const double ze = d->ang_zeta[a];
+            int zi = (ze >= 1 && ze <= 1024 && ze == std::floor(ze)) ? (int)ze : 0;
+            if (zi && (zi & (zi - 1))) zi = 0;                // repeated squaring handles powers of two; others use pow()
+            R.lz_zint[z] = zi;
+        }
+        const double gmax = d->ang_gmax_gmin[2 * a], gmin = d->ang_gmax_gmin[2 * a + 1];
+        const double g_norm = 1 / (gmax - gmin);              // SymmFunc.jl:107-112
+        Ang x; x.e = e; x.z = z; x.row = d->n_rad + a; x.off = -gmin * g_norm; x.tpz = std::pow(2.0, 1 - d->ang_zeta[a]) * g_norm;
+        x.init = (d->n_rad + a + 1) <= d->n_ang ? 1 : 0;      // total_symm_calc loops (Nrad+1):Nang, SymmFunc.jl:504
+        ang.push_back(x);
+    }
+    if ((int)ang.size() > RN_MAX_ANG) return fail(h, PTMC_ERR_ARG, "more than %d evaluated angular symmetry functions", RN_MAX_ANG);
+    std::stable_sort(ang.begin(), ang.end(), [](const Ang& a, const Ang& b) { return a.z < b.z; });
+    R.n_act_ang = (int)ang.size();
+    R.n_act = R.n_act_rad + R.n_act_ang;
+    for (int q = 0; q < R.n_act_ang; ++q) {
+        R.ang_eta_idx[q] = ang[q].e; R.ang_lz_idx[q] = ang[q].z; R.ang_tpz[q] = ang[q].tpz; R.ang_off[q] = ang[q].off;
+        R.ang_init[q] = ang[q].init; R.act_row[R.n_act_rad + q] = ang[q].row;
+    }
+    if (R.n_act < 1) return fail(h, PTMC_ERR_ARG, "no symmetry function of type 11 / 111");
+    if (d->n_layers != 4 || d->num_nodes[0] != R.n_sym || d->num_nodes[3] != 1 || d->num_nodes[1] < 1 || d->num_nodes[2] < 1 ||
+        d->num_nodes[1] > RN_MAX_HID || d->num_nodes[2] > RN_MAX_HID)
+        return fail(h, PTMC_ERR_ARG, "the sweep kernel supports networks n_sym-h1-h2-1 with h <= %d (forward() handles any topology)", RN_MAX_HID);
+    R.h1 = d->num_nodes[1]; R.h2 = d->num_nodes[2];
+    R.act1 = d->activation[1]; R.act2 = d->activation[2]; R.act3 = d->activation[3];
+    const size_t need = (size_t)R.h1 * R.n_sym + R.h1 + (size_t)R.h2 * R.h1 + R.h2 + R.h2 + 1;
+    if ((size_t)d->n_params < need) return fail(h, PTMC_ERR_ARG, "n_params %d < %zu", d->n_params, need);
+    const double* W1 = d->params; const double* b1 = W1 + (size_t)R.h1 * R.n_sym;
+    net_host.clear();
+    for (int q = 0; q < R.n_act; ++q) for (int o = 0; o < R.h1; ++o) net_host.push_back(W1[o + (size_t)R.act_row[q] * R.h1]);
+    net_host.insert(net_host.end(), b1, b1 + (need - (size_t)R.h1 * R.n_sym));     // b1, W2, b2, W3, b3 unchanged
+    return 0;
+}
+
 // lanes per replica: enough lanes to keep the per-move serial chain short, few enough that the redundant
 // per-group scalar work (RNG, Metropolis) stays small and many replicas are resident.
 static int auto_lanes(int n_atoms, int n_traj) {
@@ -182,7 +261,10 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
             break;
         case PTMC_POT_RUNNER:
-            return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential sweep is not part of this build yet (forward() is)");
+            if (!c->runner) return fail(nullptr, PTMC_ERR_ARG, "pot_kind RUNNER needs ptmc_config.runner");
+            if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
+            if (c->n_atoms > RN_THREADS / RN_SUB) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential sweep handles up to %d atoms", RN_THREADS / RN_SUB);
+            break;
         default: return fail(nullptr, PTMC_ERR_ARG, "unknown potential %d", c->pot_kind);
     }
     int ndev = 0;
@@ -197,15 +279,17 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->betas.assign(c->betas, c->betas + c->n_traj);
     h->cfg.betas = h->betas.data();
     h->cfg.runner = nullptr;
+    h->runner = c->pot_kind == PTMC_POT_RUNNER;
     h->device = c->device;
     h->geom = sphere ? GEOM_SPHERE : GEOM_PBC;
     h->n_rep = c->n_ladders * c->n_traj;
     h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0);
     int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj);
+    if (h->runner) G = 32;          // the RuNNer kernels use one 256-thread CTA per replica; G is not used
     if (G != 4 && G != 8 && G != 16 && G != 32) { delete h; return fail(nullptr, PTMC_ERR_ARG, "lanes_per_replica must be 0, 4, 8, 16 or 32"); }
     h->G = G;
     h->threads = ((c->n_traj * G + 31) / 32) * 32;
-    if (h->threads > sweep_max_threads(G)) { int mt = sweep_max_threads(G); delete h; return fail(nullptr, PTMC_ERR_ARG, "n_traj * lanes_per_replica = %d exceeds %d threads per ladder", c->n_traj * G, mt); }
+    if (!h->runner && h->threads > sweep_max_threads(G)) { int mt = sweep_max_threads(G); delete h; return fail(nullptr, PTMC_ERR_ARG, "n_traj * lanes_per_replica = %d exceeds %d threads per ladder", c->n_traj * G, mt); }
 
     auto bail = [&](int rc) { g_create_error = h->err; ptmc_destroy(h); return rc; };
     if (cudaSetDevice(h->device) != cudaSuccess) return bail(fail(h, PTMC_ERR_CUDA, "cudaSetDevice failed"));
@@ -221,8 +305,10 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     for (int i = 0; i < PTMC_MAX_COEFF; ++i) P.coeff[i] = i < c->n_coeff ? c->coeff[i] : 0.0;
     P.eam_hn = c->eam_n / 2; P.eam_hm = c->eam_m / 2; P.eam_ean = c->eam_ean; P.eam_ecam = c->eam_ecam;
 
+    std::vector<double> net_host;
+    if (h->runner) { int rr = build_runner(h, c->runner, net_host); if (rr) return bail(rr); }
     const SmemLayout lay = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere);
-    h->smem = lay.bytes;
+    h->smem = h->runner ? runner_smem_bytes(c->n_atoms, h->R) : lay.bytes;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
 
     const size_t R = (size_t)h->n_rep, N = (size_t)c->n_atoms, L = (size_t)c->n_ladders;
@@ -241,12 +327,27 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         (rc = dev_alloc(h, &P.hist, L * h->hist_per_ladder)) || (rc = dev_alloc(h, &h->d_reduced, h->hist_per_ladder)) ||
         (rc = dev_alloc(h, &h->d_error, 1)))
         return bail(rc);
+    if (h->runner) {
+        RunnerDev& Rr = h->R;
+        double* d_net = nullptr;
+        if ((rc = dev_alloc(h, &Rr.pos_c, R * N * 3)) || (rc = dev_alloc(h, &Rr.en_c, R)) || (rc = dev_alloc(h, &Rr.en_atom_c, R * N)) ||
+            (rc = dev_alloc(h, &Rr.g_c, R * N * Rr.n_act)) || (rc = dev_alloc(h, &Rr.d2_c, R * N * N)) || (rc = dev_alloc(h, &Rr.invd_c, R * N * N)) ||
+            (rc = dev_alloc(h, &Rr.f_c, R * N * N)) || (rc = dev_alloc(h, &Rr.ef_c, R * N * N * Rr.n_eta)) || (rc = dev_alloc(h, &d_net, net_host.size())))
+            return bail(rc);
+        if (cudaMemcpy(d_net, net_host.data(), sizeof(double) * net_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(h, PTMC_ERR_CUDA, "copying the network failed"));
+        Rr.net = d_net;
+    }
     P.betas = d_betas; P.en_min = en_min; P.en_max = en_max; P.v_min = v_min; P.v_max = v_max;
     P.error = h->d_error;
     if (cudaMemcpy(d_betas, h->betas.data(), sizeof(double) * c->n_traj, cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(fail(h, PTMC_ERR_CUDA, "copying betas failed"));
+    if (h->runner) {
+        if (runner_prepare(c->n_atoms, h->R) != cudaSuccess)
+            return bail(fail(h, PTMC_ERR_CUDA, "RuNNer kernels need %zu B of shared memory: %s", h->smem, cudaGetErrorString(cudaGetLastError())));
+    }
     // opt in to large dynamic shared memory for both builds of the kernel
-    for (int dbg = 0; dbg < 2; ++dbg) {
+    for (int dbg = 0; dbg < 2 && !h->runner; ++dbg) {
         sweep_fn f = pick_kernel(h, dbg);
         if (!f) return bail(fail(h, PTMC_ERR_ARG, "no kernel for potential %d / boundary %d", c->pot_kind, c->bc_kind));
         if (cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess)
@@ -288,7 +389,8 @@ extern "C" PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, co
         for (size_t r = 0; r < R; ++r) perm[r] = (int)(r % (size_t)h->cfg.n_traj);
         CU(h, cudaMemcpy(P.perm_g, perm.data(), sizeof(int) * R, cudaMemcpyHostToDevice));
     }
-    launch_init(P, h->n_rep, h->stream);
+    if (h->runner) runner_launch_init(P, h->R, h->n_rep, h->stream);
+    else launch_init(P, h->n_rep, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));   // md/mb are stack-owned
@@ -397,6 +499,20 @@ extern "C" PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64
     CU(h, cudaSetDevice(h->device));
     if (tracing && h->cfg.rng_mode == PTMC_RNG_BATCH8) return fail(h, PTMC_ERR_STATE, "tracing needs rng_mode XOSHIRO or REPLAY (sequential-stream kernels)");
     const int dbg = h->cfg.rng_mode != PTMC_RNG_BATCH8 ? 1 : 0;
+    if (h->runner) {
+        // one launch pair per cycle: the exchange between replicas happens at the kernel boundary
+        DevParams P = h->P;
+        P.trace_cap = h->trace_cap; P.trace_base = h->trace_n;
+        P.tr_index = static_cast<int32_t*>(h->d_trace[0]); P.tr_de = static_cast<double*>(h->d_trace[1]);
+        P.tr_acc = static_cast<uint8_t*>(h->d_trace[2]); P.tr_exc = static_cast<int32_t*>(h->d_trace[3]);
+        for (i64 k = 0; k < n_cycles; ++k)
+            h->launches += runner_launch_cycle(P, h->R, h->cfg.n_ladders, first_idx + k, k, sample, dbg != 0, h->stream);
+        runner_launch_gather(P, h->R, h->n_rep, h->stream);
+        h->launches += 1;
+        CU(h, cudaGetLastError());
+        if (tracing) h->trace_n += n_cycles;
+        return PTMC_OK;
+    }
     sweep_fn f = pick_kernel(h, dbg);
     // per-launch acceptance counters are 32-bit: keep moves per launch below 2^31
     const i64 max_chunk = std::max<i64>(1, (i64)0x7fffffff / std::max<i64>(1, h->n_steps));
@@ -531,4 +647,21 @@ extern "C" PTMC_API int ptmc_debug_pair_energy(ptmc_handle* h, int n, const doub
     int rc = run_pair_probe(h->P, n, d2_new, d2_old, e_new, e_old);
     h->launches += 1;
     return rc ? fail(h, rc, "pair probe failed: %s", cudaGetErrorString(cudaGetLastError())) : PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_debug_runner_state(ptmc_handle* h, int64_t ladder, int32_t slot, double* g_matrix, double* en_atom) {
+    if (!h || !h->runner || !g_matrix || !en_atom || ladder < 0 || ladder >= h->cfg.n_ladders || slot < 0 || slot >= h->cfg.n_traj)
+        return h ? fail(h, PTMC_ERR_ARG, "ptmc_debug_runner_state: not a RuNNer handle or bad index") : PTMC_ERR_ARG;
+    TRY(ptmc_sync(h));
+    const size_t N = (size_t)h->cfg.n_atoms, ng = N * h->R.n_sym;
+    double* d = nullptr;
+    CU(h, cudaMalloc(&d, sizeof(double) * (ng + N)));
+    runner_launch_export(h->P, h->R, ladder * h->cfg.n_traj + slot, d, d + ng, h->stream);
+    h->launches += 1;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(g_matrix, d, sizeof(double) * ng, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(en_atom, d + ng, sizeof(double) * N, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, PTMC_ERR_CUDA, "ptmc_debug_runner_state: %s", cudaGetErrorString(e));
+    return PTMC_OK;
 }

@@ -1,0 +1,45 @@
+// runner_dev.cuh — device-side description of a single-species RuNNer potential (RuNNerPotential,
+// src/EnergyEvaluation.jl:1182-1218) and of the per-configuration state its sweep keeps in HBM.
+#pragma once
+#include "ptmc_device.cuh"
+
+namespace ptmc {
+
+constexpr int RN_MAX_RAD = 8;      // evaluated radial functions (type 11)
+constexpr int RN_MAX_ANG = 32;     // evaluated angular functions (type 111)
+constexpr int RN_MAX_ETA = 8;      // distinct eta among the evaluated angular functions
+constexpr int RN_MAX_LZ = 8;       // distinct (lambda, zeta) among them
+constexpr int RN_MAX_HID = 32;     // nodes per hidden layer
+constexpr int RN_THREADS = 256;    // one CTA = one replica
+constexpr int RN_SUB = 4;          // threads sharing one atom j in the angular update
+
+// Only symmetry functions of type 11 / 111 are ever evaluated (DeltaMatrix.jl:803,840, SymmFunc.jl:261,281); the rows
+// of all others stay exactly 0 for ever and contribute exactly 0 to the first network layer, so the device keeps a
+// compact g matrix [atom][n_act] of the evaluated rows (radial first) and the first-layer weights of those rows.
+struct RunnerDev {
+    int n_sym, n_rad, n_ang;
+    int n_act_rad, n_act_ang, n_act;
+    int n_eta, n_lz;
+    int act_row[RN_MAX_RAD + RN_MAX_ANG];       // row of compact function a in the reference's g_matrix
+    double rad_eta[RN_MAX_RAD], rad_norm[RN_MAX_RAD], rad_off[RN_MAX_RAD];
+    int ang_eta_idx[RN_MAX_ANG], ang_lz_idx[RN_MAX_ANG];
+    double ang_tpz[RN_MAX_ANG], ang_off[RN_MAX_ANG];
+    int ang_init[RN_MAX_ANG];                   // 0: row is NOT filled at initialisation (SymmFunc.jl:504 loops (Nrad+1):Nang)
+    double eta[RN_MAX_ETA];
+    double lz_lambda[RN_MAX_LZ], lz_zeta[RN_MAX_LZ];
+    int lz_zint[RN_MAX_LZ];                     // zeta as a small integer power (1, 2, 4, ...) or 0 -> pow()
+    double r_cut, boundary2;
+    int h1, h2, act1, act2, act3;               // network n_act(88) - h1 - h2 - 1, activation codes 1 linear / 2 tanh
+    const double* net;                          // W1a [h1 x n_act] col-major, b1, W2 [h2 x h1] col-major, b2, W3 [h2], b3
+    // per-configuration state, indexed [ladder][config]; perm_g (DevParams) maps slot -> config
+    double* pos_c;      // [N][3]
+    double* en_c;       // en_tot
+    double* en_atom_c;  // [N]
+    double* g_c;        // [N][n_act]
+    double* d2_c;       // [N][N]  dist2_mat
+    double* invd_c;     // [N][N]  1/sqrt(dist2_mat)   (diagonal 0)
+    double* f_c;        // [N][N]  f_matrix (cut-off function, diagonal 1)
+    double* ef_c;       // [n_eta][N][N]  exp(-eta d2) * f  (diagonal 0)
+};
+
+}  // namespace ptmc

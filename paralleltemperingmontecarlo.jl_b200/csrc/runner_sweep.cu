@@ -1,0 +1,544 @@
+// runner_sweep.cu — the sweep for the single-species RuNNer neural-network potential (BASELINE C5):
+// energy_update!(::RuNNerPotential) src/EnergyEvaluation.jl:1593-1621 = boundary guard + symmetry-function delta
+// update (MachineLearningPotential/DeltaMatrix.jl:636-975) + network forward pass (ForwardPass.jl:50-96), fused with
+// the move generation, the Metropolis test and the commit in ONE kernel; nothing leaves the SM between them.
+//
+// Work decomposition: one CTA (256 threads) = one replica for the n_steps moves of a cycle; a second,
+// tiny kernel per cycle does the exchange / step-size / sampling of a ladder.  Per move the delta update touches
+// every triple (i, j, k): thread (j, s) owns the centre-j terms for k = s, s+4, ... and, for k > j, the centre-i
+// terms, so every accumulator has exactly one writer and the result is reproducible bit for bit.
+// The reference evaluates exp() and three pow() per triple PER symmetry function; here the radial part of the
+// exponential is factorised per pair and cached (ef = exp(-eta d2) f, [n_eta][N][N] in HBM/L2), the angular part
+// is shared by all functions with the same (lambda, zeta) and computed with repeated squaring.
+#include "runner_dev.cuh"
+
+namespace ptmc {
+
+// ------------------------------------------------------------------------------------------ helpers --
+__device__ __forceinline__ double rn_cutoff(double r, double rc) {       // Cutoff.jl:79-86
+    return r < rc ? 0.5 * (cos(3.14159265358979323846 * (r / rc)) + 1.0) : 0.0;
+}
+// (1 + lambda c)^zeta: repeated squaring for zeta = 2^m (1, 2, 4, 8, 16, ...), pow() otherwise  (SymmFunc.jl:192)
+__device__ __forceinline__ double rn_theta(double c, double lambda, double zeta, int zint) {
+    double b = fma(lambda, c, 1.0);
+    if (zint > 0) {
+        for (int m = zint; m > 1; m >>= 1) b *= b;
+        return b;
+    }
+    return pow(b, zeta);
+}
+__device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? tanh(z) : z; }
+
+struct RnSmem {          // offsets in doubles into the dynamic shared memory of the move kernel
+    int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, total;
+};
+__host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
+    RnSmem s; int o = 0;
+    s.pos = o; o += 3 * N;
+    s.g0 = o; o += N * R.n_act; s.g1 = o; o += N * R.n_act;
+    s.ea0 = o; o += N; s.ea1 = o; o += N;
+    s.rn = o; o += (3 + R.n_eta) * N;            // new row: d2, 1/d, f, ef[n_eta]
+    s.ro = o; o += (3 + R.n_eta) * N;            // old row
+    s.red = o; o += (RN_THREADS / 32) * (RN_MAX_ANG + RN_MAX_RAD);
+    s.net = o; o += R.h1 * R.n_act + R.h1 + R.h2 * R.h1 + R.h2 + R.h2 + 1;
+    s.h1 = o; o += N * R.h1; s.h2 = o; o += N * R.h2;
+    s.misc = o; o += 16;
+    s.total = o;
+    return s;
+}
+
+// Network forward pass for all atoms on the compact g matrix in shared memory (SURVEY A.2 semantics).
+// Returns, in every thread, the sum of the per-atom energies (calc_new_runner_energy! :1269-1275).
+__device__ double rn_forward(const RunnerDev& R, int N, const double* g, const double* net, double* h1, double* h2, double* eatom,
+                             double* red) {
+    const int tid = threadIdx.x;
+    const double* W1 = net; const double* b1 = W1 + R.h1 * R.n_act;
+    const double* W2 = b1 + R.h1; const double* b2 = W2 + R.h2 * R.h1;
+    const double* W3 = b2 + R.h2; const double* b3 = W3 + R.h2;
+    for (int t = tid; t < N * R.h1; t += RN_THREADS) {
+        const int a = t / R.h1, o = t - a * R.h1;
+        double z = b1[o];
+        const double* x = g + a * R.n_act;
+        for (int r = 0; r < R.n_act; ++r) z = fma(W1[o + r * R.h1], x[r], z);
+        h1[t] = rn_act(z, R.act1);
+    }
+    __syncthreads();
+    for (int t = tid; t < N * R.h2; t += RN_THREADS) {
+        const int a = t / R.h2, o = t - a * R.h2;
+        double z = b2[o];
+        const double* x = h1 + a * R.h1;
+        for (int r = 0; r < R.h1; ++r) z = fma(W2[o + r * R.h2], x[r], z);
+        h2[t] = rn_act(z, R.act2);
+    }
+    __syncthreads();
+    double e = 0.0;
+    for (int a = tid; a < N; a += RN_THREADS) {
+        double z = b3[0];
+        const double* x = h2 + a * R.h2;
+        for (int r = 0; r < R.h2; ++r) z = fma(W3[r], x[r], z);
+        z = rn_act(z, R.act3);
+        eatom[a] = z;
+        e += z;
+    }
+    e = group_sum<32>(e, 0xffffffffu);
+    if ((tid & 31) == 0) red[tid >> 5] = e;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < RN_THREADS / 32; ++w) tot += red[w];
+    __syncthreads();
+    return tot;
+}
+
+// -------------------------------------------------------------------------------------------- init --
+// set_variables(::RuNNerPotential) src/EnergyEvaluation.jl:1812-1822 + initialise_energy :1735-1747 for one replica
+// per CTA: dist2 / 1/d / f / ef matrices, the g matrix from scratch (total_symm_calc SymmFunc.jl:494-510, including
+// its (Nrad+1):Nang loop bound) and the first energies.
+__global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams P, const RunnerDev R) {
+    extern __shared__ double sm[];
+    const int N = P.n_atoms, tid = threadIdx.x;
+    const i64 rep = blockIdx.x;
+    const RnSmem L = rn_smem(N, R);
+    double* pos = sm + L.pos; double* g = sm + L.g0; double* net = sm + L.net;
+    double* D2 = R.d2_c + rep * N * N; double* INV = R.invd_c + rep * N * N; double* F = R.f_c + rep * N * N;
+    double* EF = R.ef_c + rep * (size_t)R.n_eta * N * N;
+    for (int k = tid; k < 3 * N; k += RN_THREADS) { pos[k] = P.pos[rep * 3 * N + k]; R.pos_c[rep * 3 * N + k] = pos[k]; }
+    for (int k = tid; k < L.h1 - L.net; k += RN_THREADS) net[k] = R.net[k];
+    __syncthreads();
+    for (int p = tid; p < N * N; p += RN_THREADS) {
+        const int a = p / N, b = p - a * N;
+        const double x = xsub(pos[3 * a], pos[3 * b]), y = xsub(pos[3 * a + 1], pos[3 * b + 1]), z = xsub(pos[3 * a + 2], pos[3 * b + 2]);
+        const double d2 = xadd(xadd(xmul(x, x), xmul(y, y)), xmul(z, z));     // distance2 src/Configurations.jl:101
+        const double r = sqrt(d2);
+        const double f = a == b ? 1.0 : rn_cutoff(r, R.r_cut);
+        D2[p] = a == b ? 0.0 : d2; INV[p] = a == b ? 0.0 : 1.0 / r; F[p] = f;
+        for (int e = 0; e < R.n_eta; ++e) EF[(size_t)e * N * N + p] = a == b ? 0.0 : exp(-R.eta[e] * d2) * f;
+    }
+    __syncthreads();
+    // one thread per atom a: every contribution with centre a, pairs (b < c) in the reference's order of arrival
+    for (int a = tid; a < N; a += RN_THREADS) {
+        double* ga = g + a * R.n_act;
+        for (int r = 0; r < R.n_act_rad; ++r) {
+            double s = 0.0;
+            for (int b = 0; b < N; ++b) {
+                const double f = F[a * N + b];
+                if (b != a && f != 0.0 && f != 1.0) s += f * exp(-R.rad_eta[r] * D2[a * N + b]) * R.rad_norm[r];   // calc_one_symm_val :231
+            }
+            ga[r] = s + R.rad_off[r];
+        }
+        for (int q = 0; q < R.n_act_ang; ++q) ga[R.n_act_rad + q] = 0.0;
+        for (int b = 0; b < N; ++b) {
+            if (b == a) continue;
+            for (int c = b + 1; c < N; ++c) {
+                if (c == a) continue;
+                const double r2ab = D2[a * N + b], r2ac = D2[a * N + c], r2bc = D2[b * N + c];
+                const double ca = (r2ab + r2ac - r2bc) * 0.5 * INV[a * N + b] * INV[a * N + c];
+                for (int q = 0; q < R.n_act_ang; ++q) {
+                    if (!R.ang_init[q]) continue;
+                    const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
+                    const double ep = EF[(size_t)e * N * N + a * N + b] * EF[(size_t)e * N * N + a * N + c] * EF[(size_t)e * N * N + b * N + c];
+                    ga[R.n_act_rad + q] += ep * rn_theta(ca, R.lz_lambda[z], R.lz_zeta[z], R.lz_zint[z]) * R.ang_tpz[q];
+                }
+            }
+        }
+        for (int q = 0; q < R.n_act_ang; ++q) if (R.ang_init[q]) ga[R.n_act_rad + q] += R.ang_off[q];
+    }
+    __syncthreads();
+    double* ea = sm + L.ea0;
+    const double e = rn_forward(R, N, g, net, sm + L.h1, sm + L.h2, ea, sm + L.red);
+    for (int k = tid; k < N * R.n_act; k += RN_THREADS) R.g_c[rep * N * R.n_act + k] = g[k];
+    for (int k = tid; k < N; k += RN_THREADS) R.en_atom_c[rep * N + k] = ea[k];
+    if (tid == 0) { R.en_c[rep] = e; P.en_tot[rep] = e; }
+}
+
+// ------------------------------------------------------------------------------------------- moves --
+// mc_step! for one replica slot: n_steps x mc_move! (src/MCRun.jl:142-182).  NA = number of evaluated angular
+// symmetry functions rounded up (accumulators live in registers and need compile-time indices).
+template <int NA, bool DBG>
+__global__ void __launch_bounds__(RN_THREADS, 1)
+runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launch) {
+    extern __shared__ double sm[];
+    constexpr bool BATCH = !DBG;
+    const int N = P.n_atoms, T = P.n_traj, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const i64 rep = blockIdx.x;                       // replica slot [ladder][slot]
+    const int lad = (int)(rep / T), slot = (int)(rep - (i64)lad * T);
+    const i64 cfg = (i64)lad * T + P.perm_g[rep];    // configuration this slot holds
+    const RnSmem L = rn_smem(N, R);
+    double* pos = sm + L.pos;
+    double* gbuf[2] = {sm + L.g0, sm + L.g1};
+    double* eabuf[2] = {sm + L.ea0, sm + L.ea1};
+    double* rn_d2 = sm + L.rn; double* rn_inv = rn_d2 + N; double* rn_f = rn_inv + N; double* rn_ef = rn_f + N;
+    double* ro_d2 = sm + L.ro; double* ro_inv = ro_d2 + N; double* ro_f = ro_inv + N; double* ro_ef = ro_f + N;
+    double* red = sm + L.red; double* net = sm + L.net;
+    double* misc = sm + L.misc;        // 0 index, 1-3 trial, 4 u_acc, 5 accept, 6 error
+    double* D2 = R.d2_c + cfg * N * N; double* INV = R.invd_c + cfg * N * N; double* F = R.f_c + cfg * N * N;
+    double* EF = R.ef_c + cfg * (size_t)R.n_eta * N * N;
+    const int nn = N * N;
+    int cur = 0;
+
+    for (int k = tid; k < 3 * N; k += RN_THREADS) pos[k] = R.pos_c[cfg * 3 * N + k];
+    for (int k = tid; k < N * R.n_act; k += RN_THREADS) gbuf[0][k] = R.g_c[cfg * N * R.n_act + k];
+    for (int k = tid; k < N; k += RN_THREADS) eabuf[0][k] = R.en_atom_c[cfg * N + k];
+    for (int k = tid; k < L.h1 - L.net; k += RN_THREADS) net[k] = R.net[k];
+    double en = R.en_c[cfg];
+    const double beta = P.betas[slot];
+    double dmax = P.max_displ[rep * 4];
+    const double R2 = P.box[rep * 2];
+    int n_acc = 0;
+    // random streams: warp 0 only
+    Stream<DBG> S; BatchRng<8> B;
+    S.draws = nullptr; S.pos = 0; S.len = 0; S.exhausted = 0;
+    if (warp == 0) {
+        if (BATCH) B.load(P.slot_rng + rep * (4 * PTMC_RNG_LANES), lane & 7);
+        else {
+            S.r.s0 = P.slot_rng[rep * 4]; S.r.s1 = P.slot_rng[rep * 4 + 1]; S.r.s2 = P.slot_rng[rep * 4 + 2]; S.r.s3 = P.slot_rng[rep * 4 + 3];
+            if (P.replay) { S.draws = P.slot_draws + rep * P.slot_len; S.len = P.slot_len; S.pos = P.slot_cursor[rep]; }
+        }
+    }
+    const bool tracing = DBG && P.trace_cap > 0;
+    int err = 0;
+    __syncthreads();
+
+    for (int step = 0; step < P.n_steps; ++step) {
+        double* g = gbuf[cur]; double* ng = gbuf[cur ^ 1];
+        // ============================================================ phase 0: draws + trial position (warp 0) ==
+        if (warp == 0) {
+            const unsigned full = 0xffffffffu;
+            int index;
+            if (BATCH) { B.begin(); index = (int)__umul64hi(B.template raw<0>(full), (u64)P.n_steps) + 1; }
+            else index = S.range((u64)P.n_steps);
+            const int i = index - 1;
+            double xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+            double tx, ty, tz;
+            if (BATCH) {
+                tx = xadd(xi, xmul(xsub(B.template rand<1>(full), 0.5), dmax));
+                ty = xadd(yi, xmul(xsub(B.template rand<2>(full), 0.5), dmax));
+                tz = xadd(zi, xmul(xsub(B.template rand<3>(full), 0.5), dmax));
+            } else {
+                tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax)); ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax)); tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+            }
+            int count = 0, redraws = 0;
+            while (xadd(xadd(xmul(tx, tx), xmul(ty, ty)), xmul(tz, tz)) > R2) {      // src/MCMoves.jl:115-145
+                ++count;
+                if (count == 50) {
+                    __syncwarp();
+                    double cx = 0, cy = 0, cz = 0;
+                    for (int j = 0; j < N; ++j) cx = xadd(cx, pos[3 * j]);
+                    for (int j = 0; j < N; ++j) cy = xadd(cy, pos[3 * j + 1]);
+                    for (int j = 0; j < N; ++j) cz = xadd(cz, pos[3 * j + 2]);
+                    cx = xdiv(cx, (double)N); cy = xdiv(cy, (double)N); cz = xdiv(cz, (double)N);
+                    __syncwarp();
+                    for (int j = lane; j < N; j += 32) { pos[3 * j] = xsub(pos[3 * j], cx); pos[3 * j + 1] = xsub(pos[3 * j + 1], cy); pos[3 * j + 2] = xsub(pos[3 * j + 2], cz); }
+                    __syncwarp();
+                    xi = pos[3 * i]; yi = pos[3 * i + 1]; zi = pos[3 * i + 2];
+                } else {
+                    if (BATCH) {
+                        if (++redraws == 1) {
+                            tx = xadd(xi, xmul(xsub(B.template rand<5>(full), 0.5), dmax));
+                            ty = xadd(yi, xmul(xsub(B.template rand<6>(full), 0.5), dmax));
+                            tz = xadd(zi, xmul(xsub(B.template rand<7>(full), 0.5), dmax));
+                        } else {
+                            B.begin();
+                            tx = xadd(xi, xmul(xsub(B.template rand<0>(full), 0.5), dmax));
+                            ty = xadd(yi, xmul(xsub(B.template rand<1>(full), 0.5), dmax));
+                            tz = xadd(zi, xmul(xsub(B.template rand<2>(full), 0.5), dmax));
+                        }
+                    } else {
+                        tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax)); ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax)); tz = xadd(zi, xmul(xsub(S.rand(), 0.5), dmax));
+                    }
+                    if (count == 100) { err = PTMC_ERR_SPHERE; break; }
+                }
+                if (DBG) { if (S.exhausted) break; }
+            }
+            const double u = BATCH ? B.template rand<4>(full) : S.rand();
+            if (lane == 0) { misc[0] = (double)i; misc[1] = tx; misc[2] = ty; misc[3] = tz; misc[4] = u; }
+            if (DBG) { if (S.exhausted) err = PTMC_ERR_REPLAY; }
+        }
+        __syncthreads();
+        const int i = (int)misc[0];
+        const double tx = misc[1], ty = misc[2], tz = misc[3];
+        // =============================================== phase 1: new / old row of atom i, radial functions ==
+        int guard = 0;
+        double prad[RN_MAX_RAD];
+#pragma unroll
+        for (int r = 0; r < RN_MAX_RAD; ++r) prad[r] = 0.0;
+        if (tid < N) {
+            const int j = tid;
+            const double x = xsub(tx, pos[3 * j]), y = xsub(ty, pos[3 * j + 1]), z = xsub(tz, pos[3 * j + 2]);
+            double d2n = xadd(xadd(xmul(x, x), xmul(y, y)), xmul(z, z));
+            const bool self = j == i;
+            if (self) d2n = 0.0;                                              // new_dist2_vec[index] = 0
+            guard = (!self && d2n < R.boundary2) ? 1 : 0;                     // EnergyEvaluation.jl:1602-1606
+            const double rr = sqrt(d2n);
+            const double fn = self ? 1.0 : rn_cutoff(rr, R.r_cut);            // cutoff_function.(sqrt.(new_dist2_vec))
+            const double d2o = __ldcg(D2 + i * N + j), fo = __ldcg(F + i * N + j);
+            rn_d2[j] = d2n; rn_inv[j] = self ? 0.0 : 1.0 / rr; rn_f[j] = fn;
+            ro_d2[j] = d2o; ro_inv[j] = __ldcg(INV + i * N + j); ro_f[j] = fo;
+            for (int e = 0; e < R.n_eta; ++e) {
+                rn_ef[e * N + j] = self ? 0.0 : exp(-R.eta[e] * d2n) * fn;
+                ro_ef[e * N + j] = __ldcg(EF + (size_t)e * nn + i * N + j);
+            }
+            if (!self) {
+                // radial_symmetry_calculation! DeltaMatrix.jl:794-822 / adjust_radial_symm_val! :648-657
+#pragma unroll
+                for (int r = 0; r < RN_MAX_RAD; ++r) {
+                    if (r < R.n_act_rad) {
+                        const double tn = exp(-R.rad_eta[r] * d2n) * (fn * R.rad_norm[r]);
+                        const double to = exp(-R.rad_eta[r] * d2o) * (-fo * R.rad_norm[r]);
+                        ng[j * R.n_act + r] = (g[j * R.n_act + r] + tn) + to;
+                        prad[r] = tn + to;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RN_MAX_RAD; ++r) {
+            if (r < R.n_act_rad) {
+                const double v = group_sum<32>(prad[r], 0xffffffffu);
+                if (lane == 0) red[warp * (RN_MAX_ANG + RN_MAX_RAD) + r] = v;
+            }
+        }
+        const int any_guard = __syncthreads_or(guard);
+        double new_en;
+        if (any_guard) {
+            new_en = 100.0;
+        } else {
+            if (tid < R.n_act_rad) {
+                double v = 0.0;
+                for (int w = 0; w < RN_THREADS / 32; ++w) v += red[w * (RN_MAX_ANG + RN_MAX_RAD) + tid];
+                ng[i * R.n_act + tid] = g[i * R.n_act + tid] + v;
+            }
+            // ======================================== phase 2: angular functions, triples (i, j, k) ==========
+            // angular_symmetry_calculation! DeltaMatrix.jl:827-872 / calc_new_symmetry_value! :702-747
+            double aj[NA], ai[NA];
+#pragma unroll
+            for (int q = 0; q < NA; ++q) { aj[q] = 0.0; ai[q] = 0.0; }
+            const int j = tid / RN_SUB, s = tid % RN_SUB;
+            if (j < N && j != i) {
+                const double an = rn_d2[j], ao = ro_d2[j], ijn = rn_inv[j], ijo = ro_inv[j];
+                for (int k = s; k < N; k += RN_SUB) {
+                    if (k == i || k == j) continue;
+                    const double c = __ldcg(D2 + j * N + k), ijk = __ldcg(INV + j * N + k);
+                    const double bn = rn_d2[k], bo = ro_d2[k], ikn = rn_inv[k], iko = ro_inv[k];
+                    // cos(theta) at centre j and centre i, new and old geometry (law of cosines on the cached d2, 1/d)
+                    const double cjn = (an + c - bn) * 0.5 * ijn * ijk, cjo = (ao + c - bo) * 0.5 * ijo * ijk;
+                    const double cin = (an + bn - c) * 0.5 * ijn * ikn, cio = (ao + bo - c) * 0.5 * ijo * iko;
+                    const bool with_i = k > j;                                // each (j, k) pair feeds centre i once
+                    int zprev = -1;
+                    double tjn = 0, tjo = 0, tin = 0, tio = 0;
+#pragma unroll
+                    for (int q = 0; q < NA; ++q) {
+                        if (q < R.n_act_ang) {
+                            const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
+                            if (z != zprev) {                                 // functions are sorted by (lambda, zeta)
+                                zprev = z;
+                                const double la = R.lz_lambda[z], ze = R.lz_zeta[z]; const int zi = R.lz_zint[z];
+                                tjn = rn_theta(cjn, la, ze, zi); tjo = rn_theta(cjo, la, ze, zi);
+                                if (with_i) { tin = rn_theta(cin, la, ze, zi); tio = rn_theta(cio, la, ze, zi); }
+                            }
+                            const double ejk = __ldcg(EF + (size_t)e * nn + j * N + k);
+                            const double epn = rn_ef[e * N + j] * rn_ef[e * N + k] * ejk;    // exponential_part, new
+                            const double epo = ro_ef[e * N + j] * ro_ef[e * N + k] * ejk;    // exponential_part, old
+                            aj[q] += epn * tjn - epo * tjo;
+                            if (with_i) ai[q] += epn * tin - epo * tio;
+                        }
+                    }
+                }
+            }
+            // centre j: sum over the RN_SUB lanes of the atom, one writer
+#pragma unroll
+            for (int q = 0; q < NA; ++q) {
+                if (q < R.n_act_ang) {
+                    double v = aj[q];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if (s == 0 && j < N && j != i) ng[j * R.n_act + R.n_act_rad + q] = g[j * R.n_act + R.n_act_rad + q] + v * R.ang_tpz[q];
+                    const double w = group_sum<32>(ai[q], 0xffffffffu);
+                    if (lane == 0) red[warp * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + q] = w;
+                }
+            }
+            __syncthreads();
+            if (tid < R.n_act_ang) {
+                double v = 0.0;
+                for (int w = 0; w < RN_THREADS / 32; ++w) v += red[w * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + tid];
+                ng[i * R.n_act + R.n_act_rad + tid] = g[i * R.n_act + R.n_act_rad + tid] + v * R.ang_tpz[tid];
+            }
+            __syncthreads();
+            // ======================================== phase 3: network forward pass on new_g_matrix ==========
+            new_en = rn_forward(R, N, ng, net, sm + L.h1, sm + L.h2, eabuf[cur ^ 1], red);
+        }
+        // ============================================================ phase 4: acc_test! src/MCRun.jl:122-132 ==
+        const double de = xsub(new_en, en);
+        const bool acc = metropolis_accept(-xmul(de, beta), misc[4]);
+        if (DBG) {
+            if (tracing && tid == 0) {
+                size_t o = ((((size_t)lad * P.trace_cap + P.trace_base + cyc_in_launch) * T + slot) * P.n_steps) + step;
+                P.tr_index[o] = i + 1; P.tr_de[o] = de; P.tr_acc[o] = acc ? 1 : 0;
+            }
+        }
+        __syncthreads();       // everybody has read misc[] and the row arrays are final
+        if (acc) {
+            // swap_atom_config! src/swap_config.jl:40-51 + swap_vars!(::NNPVariables) :213-221
+            if (tid == 0) { pos[3 * i] = tx; pos[3 * i + 1] = ty; pos[3 * i + 2] = tz; }
+            if (tid < N) {
+                const int j = tid;
+                const double d = rn_d2[j], iv = rn_inv[j], f = rn_f[j];
+                __stcg(D2 + i * N + j, d); __stcg(D2 + j * N + i, d);
+                __stcg(INV + i * N + j, iv); __stcg(INV + j * N + i, iv);
+                __stcg(F + i * N + j, f); __stcg(F + j * N + i, f);
+                for (int e = 0; e < R.n_eta; ++e) {
+                    const double v = rn_ef[e * N + j];
+                    __stcg(EF + (size_t)e * nn + i * N + j, v); __stcg(EF + (size_t)e * nn + j * N + i, v);
+                }
+            }
+            en = new_en; n_acc += 1;
+            if (!any_guard) cur ^= 1;     // g_matrix <-> new_g_matrix, en_atom_vec <-> new_en_atom
+            // (a guarded move that is accepted would swap in stale matrices in the reference; with new_en = 100
+            //  that needs u == 0 exactly and is not reproduced)
+        }
+        __syncthreads();
+    }
+
+    // ---- store ------------------------------------------------------------------------------------------
+    for (int k = tid; k < 3 * N; k += RN_THREADS) R.pos_c[cfg * 3 * N + k] = pos[k];
+    for (int k = tid; k < N * R.n_act; k += RN_THREADS) R.g_c[cfg * N * R.n_act + k] = gbuf[cur][k];
+    for (int k = tid; k < N; k += RN_THREADS) R.en_atom_c[cfg * N + k] = eabuf[cur][k];
+    if (tid == 0) {
+        R.en_c[cfg] = en;
+        P.counters[rep * PTMC_NCOUNT + PTMC_C_ATOM_TOT] += n_acc;
+        P.counters[rep * PTMC_NCOUNT + PTMC_C_ATOM_ADJ] += n_acc;
+        if (!BATCH) {
+            P.slot_rng[rep * 4] = S.r.s0; P.slot_rng[rep * 4 + 1] = S.r.s1; P.slot_rng[rep * 4 + 2] = S.r.s2; P.slot_rng[rep * 4 + 3] = S.r.s3;
+            if (P.replay) P.slot_cursor[rep] = S.pos;
+        }
+    }
+    if (BATCH && warp == 0 && lane < 8) B.store(P.slot_rng + rep * (4 * PTMC_RNG_LANES), lane);
+    if (err) atomicMin(P.error, err);
+}
+
+// ------------------------------------------------------------------------------------ end of cycle --
+// Second half of mc_cycle! (src/MCRun.jl:203-212, 248-250) for one ladder per warp: exchange attempt
+// (src/Exchange.jl:132-155), update_max_stepsize! (:250-263), sampling_step! (src/Sampling.jl:330-349).
+template <bool DBG>
+__global__ void runner_cycle_end_kernel(const DevParams P, const RunnerDev R, const i64 idx, const i64 cyc_in_launch, const int sample) {
+    const int lad = blockIdx.x, T = P.n_traj, lane = threadIdx.x;
+    int* perm = P.perm_g + (i64)lad * T;
+    if (lane == 0) {
+        Stream<DBG> LS;
+        LS.r.s0 = P.ladder_rng[lad * 4]; LS.r.s1 = P.ladder_rng[lad * 4 + 1]; LS.r.s2 = P.ladder_rng[lad * 4 + 2]; LS.r.s3 = P.ladder_rng[lad * 4 + 3];
+        LS.draws = nullptr; LS.pos = 0; LS.len = 0; LS.exhausted = 0;
+        if (DBG) { if (P.replay) { LS.draws = P.ladder_draws + lad * P.ladder_len; LS.len = P.ladder_len; LS.pos = P.ladder_cursor[lad]; } }
+        if (LS.rand() < 0.1) {
+            const int n_exc = LS.range((u64)(T - 1));
+            const double u = LS.rand();
+            const int a = n_exc - 1, b = n_exc;
+            i64* ca = P.counters + ((i64)lad * T + a) * PTMC_NCOUNT; i64* cb = P.counters + ((i64)lad * T + b) * PTMC_NCOUNT;
+            ca[PTMC_C_EXC_ATT] += 1; cb[PTMC_C_EXC_ATT] += 1;
+            const double ea = R.en_c[(i64)lad * T + perm[a]], eb = R.en_c[(i64)lad * T + perm[b]];
+            double pe = exp(xmul(xsub(P.betas[a], P.betas[b]), xsub(ea, eb)));
+            pe = (pe != pe) ? pe : (pe < 1.0 ? pe : 1.0);
+            int ex_acc = 0;
+            if (pe > u) {
+                ex_acc = 1;
+                ca[PTMC_C_EXC_ACC] += 1; cb[PTMC_C_EXC_ACC] += 1;
+                const int t = perm[a]; perm[a] = perm[b]; perm[b] = t;
+            }
+            if (DBG) {
+                if (P.trace_cap > 0) {
+                    int32_t* e = P.tr_exc + ((size_t)lad * P.trace_cap + P.trace_base + cyc_in_launch) * 3;
+                    e[0] = 1; e[1] = n_exc; e[2] = ex_acc;
+                }
+            }
+        }
+        P.ladder_rng[lad * 4] = LS.r.s0; P.ladder_rng[lad * 4 + 1] = LS.r.s1; P.ladder_rng[lad * 4 + 2] = LS.r.s2; P.ladder_rng[lad * 4 + 3] = LS.r.s3;
+        if (DBG) {
+            if (P.replay) P.ladder_cursor[lad] = LS.pos;
+            if (LS.exhausted) atomicMin(P.error, (int)PTMC_ERR_REPLAY);
+        }
+    }
+    __syncwarp();
+    for (int slot = lane; slot < T; slot += 32) {
+        const i64 rep = (i64)lad * T + slot;
+        i64* cn = P.counters + rep * PTMC_NCOUNT;
+        if (idx % P.n_adjust == 0) {
+            const double rate = xdiv((double)cn[PTMC_C_ATOM_ADJ], (double)((i64)P.n_adjust * P.n_atom_moves));
+            double dmax = P.max_displ[rep * 4];
+            if (rate < P.min_acc) dmax = xmul(dmax, 0.9);
+            else if (rate > P.max_acc) dmax = xmul(dmax, 1.1);
+            P.max_displ[rep * 4] = dmax;
+            cn[PTMC_C_ATOM_ADJ] = 0;
+        }
+        if (sample && idx % P.mc_sample == 0) {
+            const double e = R.en_c[(i64)lad * T + perm[slot]];
+            const int nb = P.n_bin;
+            const double en_min = P.en_min[lad];
+            const double delta_en = xdiv(xsub(P.en_max[lad], en_min), (double)(nb - 1));
+            P.ham[rep * 2] = xadd(P.ham[rep * 2], e);
+            P.ham[rep * 2 + 1] = xadd(P.ham[rep * 2 + 1], xmul(e, e));
+            const double hi = xadd(xdiv(xsub(e, en_min), delta_en), 1.0);
+            int h = hi < 1.0 ? 1 : (hi > (double)nb ? nb + 2 : (int)floor(hi) + 1);
+            if (hi != hi) h = nb + 2;
+            P.hist[(size_t)rep * (nb + 2) + (h - 1)] += 1;
+        }
+    }
+}
+
+// slot-ordered copies of the configuration-side state for ptmc_download_states
+__global__ void runner_gather_kernel(const DevParams P, const RunnerDev R) {
+    const i64 rep = blockIdx.x;
+    const int T = P.n_traj, N = P.n_atoms;
+    const i64 cfg = (rep / T) * T + P.perm_g[rep];
+    for (int k = threadIdx.x; k < 3 * N; k += blockDim.x) P.pos[rep * 3 * N + k] = R.pos_c[cfg * 3 * N + k];
+    if (threadIdx.x == 0) P.en_tot[rep] = R.en_c[cfg];
+}
+// compact g matrix / per-atom energies of the configuration in one slot (tests): g_out [N][n_sym], e_out [N]
+__global__ void runner_export_kernel(const DevParams P, const RunnerDev R, i64 rep, double* g_out, double* e_out) {
+    const int T = P.n_traj, N = P.n_atoms;
+    const i64 cfg = (rep / T) * T + P.perm_g[rep];
+    for (int k = threadIdx.x; k < N * R.n_sym; k += blockDim.x) g_out[k] = 0.0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N * R.n_act; k += blockDim.x) {
+        const int a = k / R.n_act, q = k - a * R.n_act;
+        g_out[a * R.n_sym + R.act_row[q]] = R.g_c[cfg * N * R.n_act + k];
+    }
+    for (int k = threadIdx.x; k < N; k += blockDim.x) e_out[k] = R.en_atom_c[cfg * N + k];
+}
+
+// -------------------------------------------------------------------------------------- host side --
+size_t runner_smem_bytes(int N, const RunnerDev& R) { return (size_t)rn_smem(N, R).total * sizeof(double); }
+
+typedef void (*rn_moves_fn)(const DevParams, const RunnerDev, const i64);
+static rn_moves_fn pick_moves(int n_ang, bool dbg) {
+#define RN_PICK(K) if (n_ang <= K) return dbg ? (rn_moves_fn)runner_moves_kernel<K, true> : (rn_moves_fn)runner_moves_kernel<K, false>;
+    RN_PICK(8) RN_PICK(16) RN_PICK(26) RN_PICK(32)
+#undef RN_PICK
+    return nullptr;
+}
+
+cudaError_t runner_prepare(int N, const RunnerDev& R) {
+    const int bytes = (int)runner_smem_bytes(N, R);
+    for (int dbg = 0; dbg < 2; ++dbg) {
+        rn_moves_fn f = pick_moves(R.n_act_ang, dbg);
+        if (!f) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaFuncSetAttribute((const void*)runner_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+void runner_launch_init(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaStream_t st) {
+    runner_init_kernel<<<(unsigned)n_rep, RN_THREADS, runner_smem_bytes(P.n_atoms, R), st>>>(P, R);
+}
+// one cycle = moves for every slot + end-of-cycle step for every ladder; returns the number of launches
+int runner_launch_cycle(const DevParams& P, const RunnerDev& R, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st) {
+    rn_moves_fn f = pick_moves(R.n_act_ang, dbg);
+    f<<<(unsigned)(n_ladders * P.n_traj), RN_THREADS, runner_smem_bytes(P.n_atoms, R), st>>>(P, R, cyc_in_launch);
+    if (dbg) runner_cycle_end_kernel<true><<<(unsigned)n_ladders, 32, 0, st>>>(P, R, idx, cyc_in_launch, sample);
+    else runner_cycle_end_kernel<false><<<(unsigned)n_ladders, 32, 0, st>>>(P, R, idx, cyc_in_launch, sample);
+    return 2;
+}
+void runner_launch_gather(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaStream_t st) {
+    runner_gather_kernel<<<(unsigned)n_rep, 64, 0, st>>>(P, R);
+}
+void runner_launch_export(const DevParams& P, const RunnerDev& R, i64 rep, double* g_out, double* e_out, cudaStream_t st) {
+    runner_export_kernel<<<1, 256, 0, st>>>(P, R, rep, g_out, e_out);
+}
+
+}  // namespace ptmc

@@ -315,6 +315,14 @@ class Engine:
         self._check(self._fn("debug_pair_energy")(self._h, a.size, _p(a), _p(b), _p(en), _p(eo)))
         return en, eo
 
+    def runner_state(self, ladder: int, slot: int):
+        """(g_matrix [atom][n_sym], en_atom [atom]) of the configuration held by one slot (RuNNer)"""
+        n = self.cfg.n_atoms
+        ns = len(self.cfg.runner.rad_eta) + len(self.cfg.runner.ang_eta)
+        g, e = np.zeros((n, ns)), np.zeros(n)
+        self._check(self._fn("debug_runner_state")(self._h, ladder, slot, _p(g), _p(e)))
+        return g, e
+
     def reduced_hist_dev(self):
         ptr = C.c_void_p()
         n = C.c_int64()

@@ -208,6 +208,65 @@ def test_energy_bookkeeping_at_full_size():
     eng.close(); eng2.close()
 
 
+def test_cu55_runner_replay(oracle):
+    # BASELINE C5 (scripts/cu55.jl, runnerpotential with boundary 0): symmetry-function delta update + network forward
+    # pass + Metropolis fused in one kernel, against the oracle's restatement of DeltaMatrix.jl / ForwardPass.jl
+    mcp, temp, start, pot, ens = P.host.deck_cu55_runner(n_traj=4, cycles=3)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=3, seed=17, n_adjust=2,
+                        max_displ=np.full((2, 4, 4), 0.35))
+    worst = compare_traces(gpu, cpu)
+    assert 0.1 < gpu["trace"]["accepted"].mean() < 0.9
+    print("runner max |dE err|", worst, "E", cpu["states"]["en_tot"][0, 0])
+
+
+def test_cu55_runner_state_matrices(oracle):
+    # initial g_matrix (incl. the (Nrad+1):Nang initialisation quirk), per-atom energies, and the same after moves
+    from oracle import oracle as orc
+    mcp, temp, start, pot, ens = P.host.deck_cu55_runner(n_traj=3, cycles=2)
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=1, seed=4, rng_mode=abi.RNG_XOSHIRO)
+    pos, box = initial_arrays(mcp, start, 1)
+    md = np.full((1, 3, 4), 0.3)
+    engs = [Engine(cfg), orc.OracleEngine(cfg)]
+    for e in engs:
+        e.upload_states(pos, box, md)
+    g0, e0 = engs[0].runner_state(0, 1)
+    g1, e1 = engs[1].runner_state(0, 1)
+    assert np.array_equal(g0 == 0, g1 == 0)                   # never-evaluated rows and rows 79..88 are exactly 0
+    np.testing.assert_allclose(g0, g1, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(e0, e1, rtol=1e-12)
+    for e in engs:
+        e.seed(4)
+        e.run_cycles(1, 2, False)
+        e.sync()
+    sg, sc = engs[0].download_states(), engs[1].download_states()
+    assert np.array_equal(sg["counters"], sc["counters"]) and np.array_equal(sg["pos"], sc["pos"])
+    assert sg["counters"][0, :, abi.C_ATOM_TOT].sum() > 30
+    for slot in range(3):
+        g0, e0 = engs[0].runner_state(0, slot)
+        g1, e1 = engs[1].runner_state(0, slot)
+        np.testing.assert_allclose(g0, g1, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(e0, e1, rtol=1e-11)
+        assert (np.abs(g0[:, [79, 82, 85]]) > 0).any()        # filled by the delta path only
+    for e in engs:
+        e.close()
+
+
+def test_cu55_runner_production_mode_and_guard(oracle):
+    res = _free_run_pair(P.host.deck_cu55_runner(n_traj=3, cycles=2), 2, 31, abi.RNG_BATCH8, 2, bounds=(-13.0, -11.0))
+    _assert_same_trajectory(res, e_rtol=1e-11)
+    # scripts/cu55.jl:153 passes boundary = 28 Angstrom: every trial has a neighbour inside it -> new_energy = 100.0
+    mcp, temp, start, pot, ens = P.host.deck_cu55_runner(n_traj=3, cycles=1, boundary=28 * 1.8897259886)
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=1, seed=2)
+    pos, box = initial_arrays(mcp, start, 1)
+    eng = Engine(cfg)
+    eng.upload_states(pos, box)
+    e0 = eng.download_states(("en_tot",))["en_tot"].copy()
+    eng.run_cycles(1, 1, False)
+    st = eng.download_states()
+    assert st["counters"][0, :, abi.C_ATOM_TOT].sum() == 0 and np.array_equal(st["pos"], pos) and np.array_equal(st["en_tot"], e0)
+    eng.close()
+
+
 def test_pair_arithmetic_accuracy(oracle):
     # the production pair kernel (one shared reciprocal, Halley step, Horner + FMA) against the reference's
     # own formulation (1 + K divisions, src/EnergyEvaluation.jl:934-942) over the whole physical range
