@@ -331,8 +331,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         RunnerDev& Rr = h->R;
         double* d_net = nullptr;
         if ((rc = dev_alloc(h, &Rr.pos_c, R * N * 3)) || (rc = dev_alloc(h, &Rr.en_c, R)) || (rc = dev_alloc(h, &Rr.en_atom_c, R * N)) ||
-            (rc = dev_alloc(h, &Rr.g_c, R * N * Rr.n_act)) || (rc = dev_alloc(h, &Rr.d2_c, R * N * N)) || (rc = dev_alloc(h, &Rr.invd_c, R * N * N)) ||
-            (rc = dev_alloc(h, &Rr.f_c, R * N * N)) || (rc = dev_alloc(h, &Rr.ef_c, R * N * N * Rr.n_eta)) || (rc = dev_alloc(h, &d_net, net_host.size())))
+            (rc = dev_alloc(h, &Rr.g_c, R * N * Rr.n_act)) || (rc = dev_alloc(h, &Rr.pair_c, R * (N * (N - 1) / 2) * (3 + Rr.n_eta))) ||
+            (rc = dev_alloc(h, &d_net, net_host.size())))
             return bail(rc);
         if (cudaMemcpy(d_net, net_host.data(), sizeof(double) * net_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(h, PTMC_ERR_CUDA, "copying the network failed"));

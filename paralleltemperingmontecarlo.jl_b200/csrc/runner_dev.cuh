@@ -36,10 +36,15 @@ struct RunnerDev {
     double* en_c;       // en_tot
     double* en_atom_c;  // [N]
     double* g_c;        // [N][n_act]
-    double* d2_c;       // [N][N]  dist2_mat
-    double* invd_c;     // [N][N]  1/sqrt(dist2_mat)   (diagonal 0)
-    double* f_c;        // [N][N]  f_matrix (cut-off function, diagonal 1)
-    double* ef_c;       // [n_eta][N][N]  exp(-eta d2) * f  (diagonal 0)
+    // pair tables, one entry per unordered pair (upper triangle, NT = N (N-1) / 2 entries, index rn_tri):
+    // [pair_c] = d2 | 1/d | f | ef[0] .. ef[n_eta-1], each NT long; staged into shared memory for a whole cycle
+    double* pair_c;     // [3 + n_eta][NT]: dist2_mat, 1/sqrt(dist2_mat), f_matrix, exp(-eta d2) * f
 };
+
+// index of the unordered pair (a, b), a != b, in the upper-triangle tables
+__host__ __device__ __forceinline__ int rn_tri(int a, int b, int N) {
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    return lo * N - (lo * (lo + 1)) / 2 + (hi - lo - 1);
+}
 
 }  // namespace ptmc

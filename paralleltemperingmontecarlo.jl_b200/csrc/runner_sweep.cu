@@ -30,7 +30,7 @@ __device__ __forceinline__ double rn_theta(double c, double lambda, double zeta,
 __device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? tanh(z) : z; }
 
 struct RnSmem {          // offsets in doubles into the dynamic shared memory of the move kernel
-    int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, total;
+    int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, pair, total;
 };
 __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
     RnSmem s; int o = 0;
@@ -43,6 +43,7 @@ __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
     s.net = o; o += R.h1 * R.n_act + R.h1 + R.h2 * R.h1 + R.h2 + R.h2 + 1;
     s.h1 = o; o += N * R.h1; s.h2 = o; o += N * R.h2;
     s.misc = o; o += 16;
+    s.pair = o; o += (3 + R.n_eta) * (N * (N - 1) / 2);      // d2 | 1/d | f | ef[n_eta], upper triangle
     s.total = o;
     return s;
 }
@@ -99,29 +100,33 @@ __global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams
     const i64 rep = blockIdx.x;
     const RnSmem L = rn_smem(N, R);
     double* pos = sm + L.pos; double* g = sm + L.g0; double* net = sm + L.net;
-    double* D2 = R.d2_c + rep * N * N; double* INV = R.invd_c + rep * N * N; double* F = R.f_c + rep * N * N;
-    double* EF = R.ef_c + rep * (size_t)R.n_eta * N * N;
+    const int NT = N * (N - 1) / 2;
+    double* D2 = sm + L.pair; double* INV = D2 + NT; double* F = INV + NT; double* EF = F + NT;
     for (int k = tid; k < 3 * N; k += RN_THREADS) { pos[k] = P.pos[rep * 3 * N + k]; R.pos_c[rep * 3 * N + k] = pos[k]; }
     for (int k = tid; k < L.h1 - L.net; k += RN_THREADS) net[k] = R.net[k];
     __syncthreads();
     for (int p = tid; p < N * N; p += RN_THREADS) {
         const int a = p / N, b = p - a * N;
+        if (a >= b) continue;
         const double x = xsub(pos[3 * a], pos[3 * b]), y = xsub(pos[3 * a + 1], pos[3 * b + 1]), z = xsub(pos[3 * a + 2], pos[3 * b + 2]);
         const double d2 = xadd(xadd(xmul(x, x), xmul(y, y)), xmul(z, z));     // distance2 src/Configurations.jl:101
         const double r = sqrt(d2);
-        const double f = a == b ? 1.0 : rn_cutoff(r, R.r_cut);
-        D2[p] = a == b ? 0.0 : d2; INV[p] = a == b ? 0.0 : 1.0 / r; F[p] = f;
-        for (int e = 0; e < R.n_eta; ++e) EF[(size_t)e * N * N + p] = a == b ? 0.0 : exp(-R.eta[e] * d2) * f;
+        const double f = rn_cutoff(r, R.r_cut);
+        const int t = rn_tri(a, b, N);
+        D2[t] = d2; INV[t] = 1.0 / r; F[t] = f;
+        for (int e = 0; e < R.n_eta; ++e) EF[e * NT + t] = exp(-R.eta[e] * d2) * f;
     }
     __syncthreads();
-    // one thread per atom a: every contribution with centre a, pairs (b < c) in the reference's order of arrival
+    // one thread per atom a: every contribution with centre a
     for (int a = tid; a < N; a += RN_THREADS) {
         double* ga = g + a * R.n_act;
         for (int r = 0; r < R.n_act_rad; ++r) {
             double s = 0.0;
             for (int b = 0; b < N; ++b) {
-                const double f = F[a * N + b];
-                if (b != a && f != 0.0 && f != 1.0) s += f * exp(-R.rad_eta[r] * D2[a * N + b]) * R.rad_norm[r];   // calc_one_symm_val :231
+                if (b == a) continue;
+                const int t = rn_tri(a, b, N);
+                const double f = F[t];
+                if (f != 0.0 && f != 1.0) s += f * exp(-R.rad_eta[r] * D2[t]) * R.rad_norm[r];   // calc_one_symm_val :231
             }
             ga[r] = s + R.rad_off[r];
         }
@@ -130,18 +135,19 @@ __global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams
             if (b == a) continue;
             for (int c = b + 1; c < N; ++c) {
                 if (c == a) continue;
-                const double r2ab = D2[a * N + b], r2ac = D2[a * N + c], r2bc = D2[b * N + c];
-                const double ca = (r2ab + r2ac - r2bc) * 0.5 * INV[a * N + b] * INV[a * N + c];
+                const int tab = rn_tri(a, b, N), tac = rn_tri(a, c, N), tbc = rn_tri(b, c, N);
+                const double ca = (D2[tab] + D2[tac] - D2[tbc]) * 0.5 * INV[tab] * INV[tac];
                 for (int q = 0; q < R.n_act_ang; ++q) {
                     if (!R.ang_init[q]) continue;
                     const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
-                    const double ep = EF[(size_t)e * N * N + a * N + b] * EF[(size_t)e * N * N + a * N + c] * EF[(size_t)e * N * N + b * N + c];
+                    const double ep = EF[e * NT + tab] * EF[e * NT + tac] * EF[e * NT + tbc];
                     ga[R.n_act_rad + q] += ep * rn_theta(ca, R.lz_lambda[z], R.lz_zeta[z], R.lz_zint[z]) * R.ang_tpz[q];
                 }
             }
         }
         for (int q = 0; q < R.n_act_ang; ++q) if (R.ang_init[q]) ga[R.n_act_rad + q] += R.ang_off[q];
     }
+    for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) R.pair_c[rep * (size_t)(3 + R.n_eta) * NT + k] = D2[k];
     __syncthreads();
     double* ea = sm + L.ea0;
     const double e = rn_forward(R, N, g, net, sm + L.h1, sm + L.h2, ea, sm + L.red);
@@ -170,10 +176,11 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
     double* ro_d2 = sm + L.ro; double* ro_inv = ro_d2 + N; double* ro_f = ro_inv + N; double* ro_ef = ro_f + N;
     double* red = sm + L.red; double* net = sm + L.net;
     double* misc = sm + L.misc;        // 0 index, 1-3 trial, 4 u_acc, 5 accept, 6 error
-    double* D2 = R.d2_c + cfg * N * N; double* INV = R.invd_c + cfg * N * N; double* F = R.f_c + cfg * N * N;
-    double* EF = R.ef_c + cfg * (size_t)R.n_eta * N * N;
-    const int nn = N * N;
+    const int NT = N * (N - 1) / 2;
+    double* D2 = sm + L.pair; double* INV = D2 + NT; double* F = INV + NT; double* EF = F + NT;   // pair tables, shared memory
+    double* pair_g = R.pair_c + cfg * (size_t)(3 + R.n_eta) * NT;
     int cur = 0;
+    for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) D2[k] = pair_g[k];
 
     for (int k = tid; k < 3 * N; k += RN_THREADS) pos[k] = R.pos_c[cfg * 3 * N + k];
     for (int k = tid; k < N * R.n_act; k += RN_THREADS) gbuf[0][k] = R.g_c[cfg * N * R.n_act + k];
@@ -270,12 +277,13 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
             guard = (!self && d2n < R.boundary2) ? 1 : 0;                     // EnergyEvaluation.jl:1602-1606
             const double rr = sqrt(d2n);
             const double fn = self ? 1.0 : rn_cutoff(rr, R.r_cut);            // cutoff_function.(sqrt.(new_dist2_vec))
-            const double d2o = __ldcg(D2 + i * N + j), fo = __ldcg(F + i * N + j);
+            const int tij = self ? 0 : rn_tri(i, j, N);
+            const double d2o = self ? 0.0 : D2[tij], fo = self ? 1.0 : F[tij];
             rn_d2[j] = d2n; rn_inv[j] = self ? 0.0 : 1.0 / rr; rn_f[j] = fn;
-            ro_d2[j] = d2o; ro_inv[j] = __ldcg(INV + i * N + j); ro_f[j] = fo;
+            ro_d2[j] = d2o; ro_inv[j] = self ? 0.0 : INV[tij]; ro_f[j] = fo;
             for (int e = 0; e < R.n_eta; ++e) {
                 rn_ef[e * N + j] = self ? 0.0 : exp(-R.eta[e] * d2n) * fn;
-                ro_ef[e * N + j] = __ldcg(EF + (size_t)e * nn + i * N + j);
+                ro_ef[e * N + j] = self ? 0.0 : EF[e * NT + tij];
             }
             if (!self) {
                 // radial_symmetry_calculation! DeltaMatrix.jl:794-822 / adjust_radial_symm_val! :648-657
@@ -317,7 +325,8 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                 const double an = rn_d2[j], ao = ro_d2[j], ijn = rn_inv[j], ijo = ro_inv[j];
                 for (int k = s; k < N; k += RN_SUB) {
                     if (k == i || k == j) continue;
-                    const double c = __ldcg(D2 + j * N + k), ijk = __ldcg(INV + j * N + k);
+                    const int tjk = rn_tri(j, k, N);
+                    const double c = D2[tjk], ijk = INV[tjk];
                     const double bn = rn_d2[k], bo = ro_d2[k], ikn = rn_inv[k], iko = ro_inv[k];
                     // cos(theta) at centre j and centre i, new and old geometry (law of cosines on the cached d2, 1/d)
                     const double cjn = (an + c - bn) * 0.5 * ijn * ijk, cjo = (ao + c - bo) * 0.5 * ijo * ijk;
@@ -335,7 +344,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                                 tjn = rn_theta(cjn, la, ze, zi); tjo = rn_theta(cjo, la, ze, zi);
                                 if (with_i) { tin = rn_theta(cin, la, ze, zi); tio = rn_theta(cio, la, ze, zi); }
                             }
-                            const double ejk = __ldcg(EF + (size_t)e * nn + j * N + k);
+                            const double ejk = EF[e * NT + tjk];
                             const double epn = rn_ef[e * N + j] * rn_ef[e * N + k] * ejk;    // exponential_part, new
                             const double epo = ro_ef[e * N + j] * ro_ef[e * N + k] * ejk;    // exponential_part, old
                             aj[q] += epn * tjn - epo * tjo;
@@ -378,16 +387,10 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
         if (acc) {
             // swap_atom_config! src/swap_config.jl:40-51 + swap_vars!(::NNPVariables) :213-221
             if (tid == 0) { pos[3 * i] = tx; pos[3 * i + 1] = ty; pos[3 * i + 2] = tz; }
-            if (tid < N) {
-                const int j = tid;
-                const double d = rn_d2[j], iv = rn_inv[j], f = rn_f[j];
-                __stcg(D2 + i * N + j, d); __stcg(D2 + j * N + i, d);
-                __stcg(INV + i * N + j, iv); __stcg(INV + j * N + i, iv);
-                __stcg(F + i * N + j, f); __stcg(F + j * N + i, f);
-                for (int e = 0; e < R.n_eta; ++e) {
-                    const double v = rn_ef[e * N + j];
-                    __stcg(EF + (size_t)e * nn + i * N + j, v); __stcg(EF + (size_t)e * nn + j * N + i, v);
-                }
+            if (tid < N && tid != i) {
+                const int j = tid, tij = rn_tri(i, j, N);
+                D2[tij] = rn_d2[j]; INV[tij] = rn_inv[j]; F[tij] = rn_f[j];     // row and column i of dist2_mat / f_matrix
+                for (int e = 0; e < R.n_eta; ++e) EF[e * NT + tij] = rn_ef[e * N + j];
             }
             en = new_en; n_acc += 1;
             if (!any_guard) cur ^= 1;     // g_matrix <-> new_g_matrix, en_atom_vec <-> new_en_atom
@@ -401,6 +404,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
     for (int k = tid; k < 3 * N; k += RN_THREADS) R.pos_c[cfg * 3 * N + k] = pos[k];
     for (int k = tid; k < N * R.n_act; k += RN_THREADS) R.g_c[cfg * N * R.n_act + k] = gbuf[cur][k];
     for (int k = tid; k < N; k += RN_THREADS) R.en_atom_c[cfg * N + k] = eabuf[cur][k];
+    if (n_acc) for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) pair_g[k] = D2[k];
     if (tid == 0) {
         R.en_c[cfg] = en;
         P.counters[rep * PTMC_NCOUNT + PTMC_C_ATOM_TOT] += n_acc;

@@ -1,0 +1,80 @@
+#!/usr/bin/env python3
+"""Throughput of every BASELINE config (C1..C5) on one GPU, device-resident, CUDA-event timed.
+Not the driver's bench (that is bench.py, C2 only); this feeds profiles/ and DESIGN.md.
+
+    python tools/bench_configs.py [--only c1,c3] > gpurun_out/configs.json"""
+import argparse
+import json
+import pathlib
+import sys
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+import ptmc_b200 as P  # noqa: E402
+from ptmc_b200.engine import Engine  # noqa: E402
+from ptmc_b200.host import initial_arrays, sweep_config  # noqa: E402
+
+CASES = {
+    # name: (deck factory, ladders, warm-up cycles, timed cycles per step, steps, histogram window)
+    "c1_ne13_elj_nvt_32T": (lambda: P.host.deck_ne13(n_traj=32, cycles=100), 8192, 200, 100, 5, (-0.01, 0.0, None, None)),
+    "c2_ne55_elj_nvt_24T": (lambda: P.host.deck_ne55(n_traj=24, cycles=100), 4096, 200, 50, 5, (-0.1, 0.0, None, None)),
+    "c3_cu55_eam_nvt_28T": (lambda: P.host.deck_cu55_eam(n_traj=28, cycles=100), 2048, 100, 20, 5, (-8.0, -5.0, None, None)),
+    "c4_pbc216_elj_npt_16T": (lambda: P.host.deck_pbc216(n_traj=16, cycles=100), 512, 20, 10, 3, None),
+    "c5_cu55_runner_nvt_28T": (lambda: P.host.deck_cu55_runner(n_traj=28, cycles=100), 32, 4, 4, 3, (-13.0, -11.0, None, None)),
+}
+
+
+def run(name):
+    deck, L, warm, cyc, steps, bounds = CASES[name]
+    mcp, temp, start, pot, ens = deck()
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=99)
+    eng = Engine(cfg)
+    pos, box = initial_arrays(mcp, start, L)
+    eng.upload_states(pos, box)
+    if bounds is None:
+        v0 = P.get_volume(start[0].boundary_condition)
+        bounds = (0.0, 1.0, 0.8 * v0, 2.0 * v0)
+    eng.set_hist_bounds(*bounds)
+    eng.run_cycles(1, warm, False)
+    eng.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    idx = 1
+    e0.record(stream)
+    for _ in range(steps):
+        eng.run_cycles(idx, cyc, True)
+        idx += cyc
+    e1.record(stream)
+    eng.sync()
+    ms = e0.elapsed_time(e1)
+    moves = L * mcp.n_traj * cfg.n_steps * cyc * steps
+    st = eng.download_states(("counters", "max_displ"))
+    acc = st["counters"][:, :, 0].sum() / (L * mcp.n_traj * mcp.n_atoms * cyc * steps)
+    out = {"config": name, "n_ladders": L, "n_traj": mcp.n_traj, "n_atoms": mcp.n_atoms, "moves": moves, "ms": ms,
+           "moves_per_s": moves / (ms * 1e-3), "atom_acceptance": float(acc), "lanes_per_replica": eng.lanes_per_replica(),
+           "launches": eng.launch_count()}
+    eng.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    names = [n for n in CASES if not a.only or any(n.startswith(p) for p in a.only.split(","))]
+    for n in names:
+        t0 = time.time()
+        r = run(n)
+        r["wall_s"] = time.time() - t0
+        print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()
