@@ -183,6 +183,10 @@ static int build_runner(ptmc_handle* h, const ptmc_runner_desc* d, std::vector<d
             int zi = (ze >= 1 && ze <= 1024 && ze == std::floor(ze)) ? (int)ze : 0;
             if (zi && (zi & (zi - 1))) zi = 0;                // repeated squaring handles powers of two; others use pow()
             R.lz_zint[z] = zi;
+            int nsq = 15;
+            if (zi) { nsq = 0; while ((1 << nsq) < zi) ++nsq; }
+            if (nsq > 5) nsq = 15;
+            R.lz_nsq[z] = nsq;
         }
         const double gmax = d->ang_gmax_gmin[2 * a], gmin = d->ang_gmax_gmin[2 * a + 1];
         const double g_norm = 1 / (gmax - gmin);              // SymmFunc.jl:107-112
@@ -194,9 +198,14 @@ static int build_runner(ptmc_handle* h, const ptmc_runner_desc* d, std::vector<d
     std::stable_sort(ang.begin(), ang.end(), [](const Ang& a, const Ang& b) { return a.z < b.z; });
     R.n_act_ang = (int)ang.size();
     R.n_act = R.n_act_rad + R.n_act_ang;
+    for (int k = 0; k < RN_MAX_ETA * RN_MAX_LZ; ++k) R.qmap[k] = -1;
     for (int q = 0; q < R.n_act_ang; ++q) {
         R.ang_eta_idx[q] = ang[q].e; R.ang_lz_idx[q] = ang[q].z; R.ang_tpz[q] = ang[q].tpz; R.ang_off[q] = ang[q].off;
         R.ang_init[q] = ang[q].init; R.act_row[R.n_act_rad + q] = ang[q].row;
+        const int bit = ang[q].e * RN_MAX_LZ + ang[q].z;
+        if (R.present >> bit & 1ull) return fail(h, PTMC_ERR_ARG, "two evaluated angular symmetry functions share (eta, lambda, zeta)");
+        R.present |= 1ull << bit;
+        R.qmap[bit] = (signed char)q;
     }
     if (R.n_act < 1) return fail(h, PTMC_ERR_ARG, "no symmetry function of type 11 / 111");
     if (d->n_layers != 4 || d->num_nodes[0] != R.n_sym || d->num_nodes[3] != 1 || d->num_nodes[1] < 1 || d->num_nodes[2] < 1 ||

@@ -25,9 +25,12 @@ struct RunnerDev {
     int ang_eta_idx[RN_MAX_ANG], ang_lz_idx[RN_MAX_ANG];
     double ang_tpz[RN_MAX_ANG], ang_off[RN_MAX_ANG];
     int ang_init[RN_MAX_ANG];                   // 0: row is NOT filled at initialisation (SymmFunc.jl:504 loops (Nrad+1):Nang)
+    unsigned long long present;                 // bit (e * RN_MAX_LZ + z): an evaluated function has eta e and (lambda, zeta) z
+    signed char qmap[RN_MAX_ETA * RN_MAX_LZ];   // (e, z) -> compact angular function index, -1 if none
     double eta[RN_MAX_ETA];
     double lz_lambda[RN_MAX_LZ], lz_zeta[RN_MAX_LZ];
     int lz_zint[RN_MAX_LZ];                     // zeta as a small integer power (1, 2, 4, ...) or 0 -> pow()
+    int lz_nsq[RN_MAX_LZ];                      // zeta = 2^nsq: number of squarings; 15 -> pow()
     double r_cut, boundary2;
     int h1, h2, act1, act2, act3;               // network n_act(88) - h1 - h2 - 1, activation codes 1 linear / 2 tanh
     const double* net;                          // W1a [h1 x n_act] col-major, b1, W2 [h2 x h1] col-major, b2, W3 [h2], b3
@@ -40,6 +43,20 @@ struct RunnerDev {
     // [pair_c] = d2 | 1/d | f | ef[0] .. ef[n_eta-1], each NT long; staged into shared memory for a whole cycle
     double* pair_c;     // [3 + n_eta][NT]: dist2_mat, 1/sqrt(dist2_mat), f_matrix, exp(-eta d2) * f
 };
+
+// The angular symmetry-function set of every RuNNer script of the reference (scripts/cu55.jl:70-97, cu38.jl, brass55.jl,
+// test/potentialfile.jl: the 26-row table "V"), as structure only: which (eta index, (lambda, zeta) index) pairs exist
+// and how many squarings each (lambda, zeta) needs, with indices in order of first appearance.  The kernels are
+// specialised on this structure (all register indices and loop bounds become compile-time); the VALUES of eta, lambda,
+// zeta, the scaling and the network stay runtime data.  Any other set runs through the generic instantiation.
+constexpr unsigned long long RN_PRESENT_V =
+    (1ull << (0 * 8 + 0)) | (1ull << (0 * 8 + 1)) | (1ull << (1 * 8 + 2)) | (1ull << (1 * 8 + 1)) | (1ull << (2 * 8 + 2)) | (1ull << (2 * 8 + 1)) |
+    (1ull << (2 * 8 + 3)) | (1ull << (3 * 8 + 0)) | (1ull << (3 * 8 + 1)) | (1ull << (3 * 8 + 4)) | (1ull << (3 * 8 + 5)) | (1ull << (4 * 8 + 2)) |
+    (1ull << (4 * 8 + 0)) | (1ull << (4 * 8 + 3)) | (1ull << (4 * 8 + 4)) | (1ull << (4 * 8 + 5)) | (1ull << (4 * 8 + 6)) | (1ull << (5 * 8 + 0)) |
+    (1ull << (5 * 8 + 1)) | (1ull << (5 * 8 + 4)) | (1ull << (5 * 8 + 7)) | (1ull << (5 * 8 + 6)) | (1ull << (6 * 8 + 0)) | (1ull << (6 * 8 + 1)) |
+    (1ull << (6 * 8 + 4)) | (1ull << (6 * 8 + 7));
+// squarings per (lambda, zeta) slot, 4 bits each, slot 0 in the low nibble: zeta = 1, 2, 1, 2, 4, 16, 16, 4
+constexpr unsigned RN_NSQ_V = 0u | (1u << 4) | (0u << 8) | (1u << 12) | (2u << 16) | (4u << 20) | (4u << 24) | (2u << 28);
 
 // index of the unordered pair (a, b), a != b, in the upper-triangle tables
 __host__ __device__ __forceinline__ int rn_tri(int a, int b, int N) {

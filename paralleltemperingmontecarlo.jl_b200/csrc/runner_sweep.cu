@@ -27,10 +27,19 @@ __device__ __forceinline__ double rn_theta(double c, double lambda, double zeta,
     }
     return pow(b, zeta);
 }
+// the same with the number of squarings nsq (zeta = 2^nsq, at most 2^5); nsq == 15 -> pow().  In the specialised
+// kernels nsq is a compile-time constant after unrolling and the predicates fold away.
+__device__ __forceinline__ double rn_theta_n(double c, double lambda, double zeta, int nsq) {
+    double b = fma(lambda, c, 1.0);
+    if (nsq == 15) return pow(b, zeta);
+#pragma unroll
+    for (int m = 0; m < 5; ++m) if (m < nsq) b *= b;
+    return b;
+}
 __device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? tanh(z) : z; }
 
 struct RnSmem {          // offsets in doubles into the dynamic shared memory of the move kernel
-    int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, pair, total;
+    int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, pair, ptab, total;
 };
 __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
     RnSmem s; int o = 0;
@@ -44,6 +53,7 @@ __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
     s.h1 = o; o += N * R.h1; s.h2 = o; o += N * R.h2;
     s.misc = o; o += 16;
     s.pair = o; o += (3 + R.n_eta) * (N * (N - 1) / 2);      // d2 | 1/d | f | ef[n_eta], upper triangle
+    s.ptab = o; o += (N * (N - 1) / 2 + 1) / 2;              // int (j << 16 | k) per pair
     s.total = o;
     return s;
 }
@@ -158,12 +168,14 @@ __global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams
 
 // ------------------------------------------------------------------------------------------- moves --
 // mc_step! for one replica slot: n_steps x mc_move! (src/MCRun.jl:142-182).  NA = number of evaluated angular
-// symmetry functions rounded up (accumulators live in registers and need compile-time indices).
-template <int NA, bool DBG>
+// symmetry functions (unused; the accumulators are dense over (eta, lambda-zeta)).
+template <bool DBG, unsigned long long PRESENT, unsigned NSQ>
 __global__ void __launch_bounds__(RN_THREADS, 1)
 runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launch) {
     extern __shared__ double sm[];
     constexpr bool BATCH = !DBG;
+    constexpr bool SPEC = PRESENT != 0;               // structure of the angular function set known at compile time
+    const unsigned long long present = SPEC ? PRESENT : R.present;
     const int N = P.n_atoms, T = P.n_traj, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 rep = blockIdx.x;                       // replica slot [ladder][slot]
     const int lad = (int)(rep / T), slot = (int)(rep - (i64)lad * T);
@@ -181,6 +193,11 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
     double* pair_g = R.pair_c + cfg * (size_t)(3 + R.n_eta) * NT;
     int cur = 0;
     for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) D2[k] = pair_g[k];
+    int* ptab = reinterpret_cast<int*>(sm + L.ptab);
+    for (int p = tid; p < N * N; p += RN_THREADS) {
+        const int a = p / N, b = p - a * N;
+        if (a < b) ptab[rn_tri(a, b, N)] = a << 16 | b;
+    }
 
     for (int k = tid; k < 3 * N; k += RN_THREADS) pos[k] = R.pos_c[cfg * 3 * N + k];
     for (int k = tid; k < N * R.n_act; k += RN_THREADS) gbuf[0][k] = R.g_c[cfg * N * R.n_act + k];
@@ -317,53 +334,93 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
             }
             // ======================================== phase 2: angular functions, triples (i, j, k) ==========
             // angular_symmetry_calculation! DeltaMatrix.jl:827-872 / calc_new_symmetry_value! :702-747
-            double aj[NA], ai[NA];
+            // Accumulators are dense over (eta, (lambda, zeta)) so that every register index is a compile-time constant;
+            // combinations without a symmetry function are skipped through the uniform bit mask R.present.
+            double acc[RN_MAX_ETA][RN_MAX_LZ];
 #pragma unroll
-            for (int q = 0; q < NA; ++q) { aj[q] = 0.0; ai[q] = 0.0; }
+            for (int e = 0; e < RN_MAX_ETA; ++e)
+#pragma unroll
+                for (int z = 0; z < RN_MAX_LZ; ++z) acc[e][z] = 0.0;
+            // ---- pass A: centre j, thread (j, s) takes k = s, s + RN_SUB, ...
             const int j = tid / RN_SUB, s = tid % RN_SUB;
-            if (j < N && j != i) {
+            const bool jok = j < N && j != i;
+            if (jok) {
                 const double an = rn_d2[j], ao = ro_d2[j], ijn = rn_inv[j], ijo = ro_inv[j];
                 for (int k = s; k < N; k += RN_SUB) {
                     if (k == i || k == j) continue;
                     const int tjk = rn_tri(j, k, N);
                     const double c = D2[tjk], ijk = INV[tjk];
-                    const double bn = rn_d2[k], bo = ro_d2[k], ikn = rn_inv[k], iko = ro_inv[k];
-                    // cos(theta) at centre j and centre i, new and old geometry (law of cosines on the cached d2, 1/d)
-                    const double cjn = (an + c - bn) * 0.5 * ijn * ijk, cjo = (ao + c - bo) * 0.5 * ijo * ijk;
-                    const double cin = (an + bn - c) * 0.5 * ijn * ikn, cio = (ao + bo - c) * 0.5 * ijo * iko;
-                    const bool with_i = k > j;                                // each (j, k) pair feeds centre i once
-                    int zprev = -1;
-                    double tjn = 0, tjo = 0, tin = 0, tio = 0;
+                    // cos(theta) at centre j, new and old geometry (law of cosines on the cached d2, 1/d)
+                    const double cn = (an + c - rn_d2[k]) * 0.5 * ijn * ijk, co = (ao + c - ro_d2[k]) * 0.5 * ijo * ijk;
+                    double epn[RN_MAX_ETA], epo[RN_MAX_ETA];
 #pragma unroll
-                    for (int q = 0; q < NA; ++q) {
-                        if (q < R.n_act_ang) {
-                            const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
-                            if (z != zprev) {                                 // functions are sorted by (lambda, zeta)
-                                zprev = z;
-                                const double la = R.lz_lambda[z], ze = R.lz_zeta[z]; const int zi = R.lz_zint[z];
-                                tjn = rn_theta(cjn, la, ze, zi); tjo = rn_theta(cjo, la, ze, zi);
-                                if (with_i) { tin = rn_theta(cin, la, ze, zi); tio = rn_theta(cio, la, ze, zi); }
-                            }
+                    for (int e = 0; e < RN_MAX_ETA; ++e) {
+                        epn[e] = 0.0; epo[e] = 0.0;
+                        if (SPEC ? ((PRESENT >> (e * RN_MAX_LZ)) & 0xffull) != 0 : e < R.n_eta) {
                             const double ejk = EF[e * NT + tjk];
-                            const double epn = rn_ef[e * N + j] * rn_ef[e * N + k] * ejk;    // exponential_part, new
-                            const double epo = ro_ef[e * N + j] * ro_ef[e * N + k] * ejk;    // exponential_part, old
-                            aj[q] += epn * tjn - epo * tjo;
-                            if (with_i) ai[q] += epn * tin - epo * tio;
+                            epn[e] = rn_ef[e * N + j] * rn_ef[e * N + k] * ejk;      // exponential_part, new geometry
+                            epo[e] = ro_ef[e * N + j] * ro_ef[e * N + k] * ejk;      // exponential_part, old geometry
+                        }
+                    }
+#pragma unroll
+                    for (int z = 0; z < RN_MAX_LZ; ++z) {
+                        if (SPEC || z < R.n_lz) {
+                            const double tn = rn_theta_n(cn, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
+                            const double to = rn_theta_n(co, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
+#pragma unroll
+                            for (int e = 0; e < RN_MAX_ETA; ++e)
+                                if (present >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * tn - epo[e] * to;
                         }
                     }
                 }
             }
-            // centre j: sum over the RN_SUB lanes of the atom, one writer
 #pragma unroll
-            for (int q = 0; q < NA; ++q) {
-                if (q < R.n_act_ang) {
-                    double v = aj[q];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    if (s == 0 && j < N && j != i) ng[j * R.n_act + R.n_act_rad + q] = g[j * R.n_act + R.n_act_rad + q] + v * R.ang_tpz[q];
-                    const double w = group_sum<32>(ai[q], 0xffffffffu);
-                    if (lane == 0) red[warp * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + q] = w;
+            for (int e = 0; e < RN_MAX_ETA; ++e)
+#pragma unroll
+                for (int z = 0; z < RN_MAX_LZ; ++z)
+                    if (present >> (e * RN_MAX_LZ + z) & 1ull) {
+                        double v = acc[e][z];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        const int q = R.qmap[e * RN_MAX_LZ + z];
+                        if (s == 0 && jok) ng[j * R.n_act + R.n_act_rad + q] = g[j * R.n_act + R.n_act_rad + q] + v * R.ang_tpz[q];
+                        acc[e][z] = 0.0;
+                    }
+            // ---- pass B: centre i, the pairs (j < k) dealt round-robin to all threads
+            for (int p = tid; p < NT; p += RN_THREADS) {
+                const int jk = ptab[p], pj = jk >> 16, pk = jk & 0xffff;
+                if (pj == i || pk == i) continue;
+                const double c = D2[p];
+                const double an = rn_d2[pj], ao = ro_d2[pj], bn = rn_d2[pk], bo = ro_d2[pk];
+                const double cn = (an + bn - c) * 0.5 * rn_inv[pj] * rn_inv[pk], co = (ao + bo - c) * 0.5 * ro_inv[pj] * ro_inv[pk];
+                double epn[RN_MAX_ETA], epo[RN_MAX_ETA];
+#pragma unroll
+                for (int e = 0; e < RN_MAX_ETA; ++e) {
+                    epn[e] = 0.0; epo[e] = 0.0;
+                    if (SPEC ? ((PRESENT >> (e * RN_MAX_LZ)) & 0xffull) != 0 : e < R.n_eta) {
+                        const double ejk = EF[e * NT + p];
+                        epn[e] = rn_ef[e * N + pj] * rn_ef[e * N + pk] * ejk;
+                        epo[e] = ro_ef[e * N + pj] * ro_ef[e * N + pk] * ejk;
+                    }
+                }
+#pragma unroll
+                for (int z = 0; z < RN_MAX_LZ; ++z) {
+                    if (SPEC || z < R.n_lz) {
+                        const double tn = rn_theta_n(cn, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
+                        const double to = rn_theta_n(co, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
+#pragma unroll
+                        for (int e = 0; e < RN_MAX_ETA; ++e)
+                            if (present >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * tn - epo[e] * to;
+                    }
                 }
             }
+#pragma unroll
+            for (int e = 0; e < RN_MAX_ETA; ++e)
+#pragma unroll
+                for (int z = 0; z < RN_MAX_LZ; ++z)
+                    if (present >> (e * RN_MAX_LZ + z) & 1ull) {
+                        const double w = group_sum<32>(acc[e][z], 0xffffffffu);
+                        if (lane == 0) red[warp * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + R.qmap[e * RN_MAX_LZ + z]] = w;
+                    }
             __syncthreads();
             if (tid < R.n_act_ang) {
                 double v = 0.0;
@@ -510,17 +567,22 @@ __global__ void runner_export_kernel(const DevParams P, const RunnerDev R, i64 r
 size_t runner_smem_bytes(int N, const RunnerDev& R) { return (size_t)rn_smem(N, R).total * sizeof(double); }
 
 typedef void (*rn_moves_fn)(const DevParams, const RunnerDev, const i64);
-static rn_moves_fn pick_moves(int n_ang, bool dbg) {
-#define RN_PICK(K) if (n_ang <= K) return dbg ? (rn_moves_fn)runner_moves_kernel<K, true> : (rn_moves_fn)runner_moves_kernel<K, false>;
-    RN_PICK(8) RN_PICK(16) RN_PICK(26) RN_PICK(32)
-#undef RN_PICK
-    return nullptr;
+// specialised on the reference's standard angular set when the potential has exactly that structure
+static bool is_standard_set(const RunnerDev& R) {
+    if (R.present != RN_PRESENT_V || R.n_eta != 7 || R.n_lz != 8) return false;
+    for (int z = 0; z < 8; ++z) if (R.lz_nsq[z] != (int)((RN_NSQ_V >> (4 * z)) & 15u)) return false;
+    return true;
+}
+static rn_moves_fn pick_moves(const RunnerDev& R, bool dbg) {
+    if (is_standard_set(R))
+        return dbg ? (rn_moves_fn)runner_moves_kernel<true, RN_PRESENT_V, RN_NSQ_V> : (rn_moves_fn)runner_moves_kernel<false, RN_PRESENT_V, RN_NSQ_V>;
+    return dbg ? (rn_moves_fn)runner_moves_kernel<true, 0ull, 0u> : (rn_moves_fn)runner_moves_kernel<false, 0ull, 0u>;
 }
 
 cudaError_t runner_prepare(int N, const RunnerDev& R) {
     const int bytes = (int)runner_smem_bytes(N, R);
     for (int dbg = 0; dbg < 2; ++dbg) {
-        rn_moves_fn f = pick_moves(R.n_act_ang, dbg);
+        rn_moves_fn f = pick_moves(R, dbg != 0);
         if (!f) return cudaErrorInvalidValue;
         cudaError_t e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
@@ -532,7 +594,7 @@ void runner_launch_init(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaS
 }
 // one cycle = moves for every slot + end-of-cycle step for every ladder; returns the number of launches
 int runner_launch_cycle(const DevParams& P, const RunnerDev& R, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st) {
-    rn_moves_fn f = pick_moves(R.n_act_ang, dbg);
+    rn_moves_fn f = pick_moves(R, dbg);
     f<<<(unsigned)(n_ladders * P.n_traj), RN_THREADS, runner_smem_bytes(P.n_atoms, R), st>>>(P, R, cyc_in_launch);
     if (dbg) runner_cycle_end_kernel<true><<<(unsigned)n_ladders, 32, 0, st>>>(P, R, idx, cyc_in_launch, sample);
     else runner_cycle_end_kernel<false><<<(unsigned)n_ladders, 32, 0, st>>>(P, R, idx, cyc_in_launch, sample);
