@@ -66,20 +66,38 @@ __device__ double rn_forward(const RunnerDev& R, int N, const double* g, const d
     const double* W1 = net; const double* b1 = W1 + R.h1 * R.n_act;
     const double* W2 = b1 + R.h1; const double* b2 = W2 + R.h2 * R.h1;
     const double* W3 = b2 + R.h2; const double* b3 = W3 + R.h2;
-    for (int t = tid; t < N * R.h1; t += RN_THREADS) {
-        const int a = t / R.h1, o = t - a * R.h1;
-        double z = b1[o];
+    // each thread: one atom x four output nodes (one load of the input per four FMAs)
+    const int ng1 = (R.h1 + 3) / 4, ng2 = (R.h2 + 3) / 4;
+    for (int t = tid; t < N * ng1; t += RN_THREADS) {
+        const int a = t / ng1, o0 = (t - a * ng1) * 4;
+        double z[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) z[m] = o0 + m < R.h1 ? b1[o0 + m] : 0.0;
         const double* x = g + a * R.n_act;
-        for (int r = 0; r < R.n_act; ++r) z = fma(W1[o + r * R.h1], x[r], z);
-        h1[t] = rn_act(z, R.act1);
+        for (int r = 0; r < R.n_act; ++r) {
+            const double xr = x[r];
+            const double* w = W1 + o0 + r * R.h1;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) if (o0 + m < R.h1) z[m] = fma(w[m], xr, z[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) if (o0 + m < R.h1) h1[a * R.h1 + o0 + m] = rn_act(z[m], R.act1);
     }
     __syncthreads();
-    for (int t = tid; t < N * R.h2; t += RN_THREADS) {
-        const int a = t / R.h2, o = t - a * R.h2;
-        double z = b2[o];
+    for (int t = tid; t < N * ng2; t += RN_THREADS) {
+        const int a = t / ng2, o0 = (t - a * ng2) * 4;
+        double z[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) z[m] = o0 + m < R.h2 ? b2[o0 + m] : 0.0;
         const double* x = h1 + a * R.h1;
-        for (int r = 0; r < R.h1; ++r) z = fma(W2[o + r * R.h2], x[r], z);
-        h2[t] = rn_act(z, R.act2);
+        for (int r = 0; r < R.h1; ++r) {
+            const double xr = x[r];
+            const double* w = W2 + o0 + r * R.h2;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) if (o0 + m < R.h2) z[m] = fma(w[m], xr, z[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) if (o0 + m < R.h2) h2[a * R.h2 + o0 + m] = rn_act(z[m], R.act2);
     }
     __syncthreads();
     double e = 0.0;
@@ -380,7 +398,8 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                 for (int z = 0; z < RN_MAX_LZ; ++z)
                     if (present >> (e * RN_MAX_LZ + z) & 1ull) {
                         double v = acc[e][z];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+#pragma unroll
+                        for (int m = 1; m < RN_SUB; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
                         const int q = R.qmap[e * RN_MAX_LZ + z];
                         if (s == 0 && jok) ng[j * R.n_act + R.n_act_rad + q] = g[j * R.n_act + R.n_act_rad + q] + v * R.ang_tpz[q];
                         acc[e][z] = 0.0;

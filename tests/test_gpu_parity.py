@@ -251,6 +251,25 @@ def test_cu55_runner_state_matrices(oracle):
         e.close()
 
 
+def test_runner_generic_symmetry_function_set(oracle):
+    # a symmetry-function set that is NOT the reference's standard table: fewer angular functions, zeta = 3 (pow()
+    # instead of repeated squaring), an extra radial function, hidden layers 7 and 5, linear second activation ->
+    # the generic (runtime-structure) instantiation of the kernel
+    rng = np.random.default_rng(3)
+    radial = [(11, 0.01, 9.0, 14.0, 0.2), (10, 0.01, 9.0, 1.0, 0.0), (11, 0.2, 9.0, 5.0, 0.1), (11, 0.05, 9.0, 8.0, 0.0)]
+    angular = [(0.002, 1, 1, 9.0, 111, 3.0, 0.0), (0.002, -1, 3, 9.0, 111, 2.0, 0.1), (0.002, -1, 3, 9.0, 110, 1.0, 0.0),
+               (0.03, -1, 3, 9.0, 111, 1.5, 0.0), (0.03, 1, 8, 9.0, 111, 0.9, 0.05), (0.01, 1, 1, 9.0, 111, 2.5, 0.3)]
+    nodes = [10, 7, 5, 1]
+    w = rng.normal(scale=0.3, size=10 * 7 + 7 + 7 * 5 + 5 + 5 + 1)
+    pot = P.RuNNerPotential(nodes, [1, 2, 1, 1], w, radial, angular, boundary=1.0)
+    mcp, temp, start, _, ens = P.host.deck_ne13(n_traj=4, cycles=6)
+    temp = P.TempGrid(300.0, 900.0, 4)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=6, seed=23, n_adjust=3, max_displ=np.full((2, 4, 4), 0.8),
+                        bounds=(-50.0, 50.0, None, None))
+    compare_traces(gpu, cpu)
+    assert 0.05 < gpu["trace"]["accepted"].mean() < 0.98
+
+
 def test_cu55_runner_production_mode_and_guard(oracle):
     res = _free_run_pair(P.host.deck_cu55_runner(n_traj=3, cycles=2), 2, 31, abi.RNG_BATCH8, 2, bounds=(-13.0, -11.0))
     _assert_same_trajectory(res, e_rtol=1e-11)
