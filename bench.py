@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ladders", type=int, default=4096, help="independent PT ladders per GPU")
-    ap.add_argument("--cycles", type=int, default=50, help="mc_cycle! calls per step")
+    ap.add_argument("--cycles", type=int, default=200, help="mc_cycle! calls per step")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per replica (0 = auto)")
     ap.add_argument("--cpu-ladders", type=int, default=0, help="ladders in the CPU sample (0 = 8 per core)")
     ap.add_argument("--cpu-cycles", type=int, default=200)
