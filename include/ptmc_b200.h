@@ -225,6 +225,10 @@ PTMC_API int ptmc_lanes_per_replica(const ptmc_handle* h);
  * uses it as the roofline denominator (MEASURED_PEAKS.json holds no FP64 figure). */
 PTMC_API int ptmc_fp64_peak(int device, int iters, double* tflops);
 
+/* Issue-port probe (DESIGN.md cost model): SM cycles per warp-DFMA per SM sub-partition when 0, 8, 16 and 32 independent
+ * integer instructions are interleaved with every 8 DFMAs... i.e. 0, 1, 2, 4 per DFMA; sm_mhz = clock to convert time. */
+PTMC_API int ptmc_issue_probe(int device, double sm_mhz, double* cycles_per_dfma4);
+
 /* Accuracy probe (tests): the pair arithmetic of the sweep kernel for n pairs of squared distances, exactly as
  * it is accumulated per move: e_new[k] = e(d2_new[k]), e_old[k] = e(d2_old[k]) for the handle's potential
  * (ELJ / ELJEven: dimer_energy src/EnergyEvaluation.jl:923-942; EAM: the r^-n term of invrexp :1088-1095). */

@@ -89,6 +89,7 @@ SYMBOLS = {
     "ptmc_launch_count": (C.c_int64, [_vp]),
     "ptmc_lanes_per_replica": (C.c_int, [_vp]),
     "ptmc_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp]),
+    "ptmc_issue_probe": (C.c_int, [C.c_int, C.c_double, _dp]),
     "ptmc_debug_pair_energy": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp]),
     "ptmc_debug_runner_state": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp, _dp]),
     "forward": (C.c_double, [_dp, _ip, _ip, _ip, _ip, _ip, _dp, _ip, _dp]),

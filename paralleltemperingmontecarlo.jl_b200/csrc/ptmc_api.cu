@@ -22,6 +22,7 @@ int sweep_max_threads(int G);
 void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
 double measure_fp64_peak(cudaStream_t st, int iters);
+int run_issue_probe(double sm_mhz, double out_cycles[4]);
 int run_pair_probe(const DevParams& P, int n, const double* h_d2n, const double* h_d2o, double* h_en, double* h_eo);
 size_t runner_smem_bytes(int N, const RunnerDev& R);
 cudaError_t runner_prepare(int N, const RunnerDev& R);
@@ -673,4 +674,12 @@ extern "C" PTMC_API int ptmc_debug_runner_state(ptmc_handle* h, int64_t ladder, 
     cudaFree(d);
     if (e != cudaSuccess) return fail(h, PTMC_ERR_CUDA, "ptmc_debug_runner_state: %s", cudaGetErrorString(e));
     return PTMC_OK;
+}
+
+extern "C" PTMC_API int ptmc_issue_probe(int device, double sm_mhz, double* cycles_per_dfma4) {
+    if (!cycles_per_dfma4) return PTMC_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(nullptr, PTMC_ERR_CUDA, "no such CUDA device");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, PTMC_ERR_CUDA, "cudaSetDevice failed");
+    return run_issue_probe(sm_mhz, cycles_per_dfma4);
 }

@@ -72,6 +72,58 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int n_iter,
     double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (s == 12345.678) out[0] = s;   // keep the chains alive
 }
+// Issue-slot probe: K independent integer (LOP3/IADD) instructions interleaved with every DFMA.  If a warp DFMA only
+// occupied the FP64 pipe for 2 cycles, up to one other instruction per DFMA would be free; the measured time per DFMA
+// as a function of K tells how FP64 and non-FP64 instructions share the issue port (cost model).
+template <int K>
+__global__ void __launch_bounds__(256) issue_probe_kernel(double* out, int n_iter, double a, double b, unsigned seed) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    unsigned u0 = seed + threadIdx.x, u1 = u0 * 3u, u2 = u0 * 5u, u3 = u0 * 7u;
+    for (int i = 0; i < n_iter; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#define PTMC_PROBE_INT(n) if (K > n) { u0 = (u0 ^ u1) + 0x9e3779b9u; u1 = (u1 ^ u2) + u0; u2 = (u2 ^ u3) + u1; u3 = (u3 ^ u0) + u2; }
+            x0 = fma(x0, a, b); PTMC_PROBE_INT(0) x1 = fma(x1, a, b); PTMC_PROBE_INT(1) x2 = fma(x2, a, b); PTMC_PROBE_INT(2)
+            x3 = fma(x3, a, b); PTMC_PROBE_INT(3) x4 = fma(x4, a, b); PTMC_PROBE_INT(0) x5 = fma(x5, a, b); PTMC_PROBE_INT(1)
+            x6 = fma(x6, a, b); PTMC_PROBE_INT(2) x7 = fma(x7, a, b); PTMC_PROBE_INT(3)
+#undef PTMC_PROBE_INT
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678 || (u0 ^ u1 ^ u2 ^ u3) == 0x12345u) out[0] = s;
+}
+// returns SM cycles per warp-DFMA per SM sub-partition for K in {0, 1, 2, 4} (8 int instructions per PROBE_INT block)
+int run_issue_probe(double sm_mhz, double out_cycles[4]) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return PTMC_ERR_CUDA;
+    const int threads = 256, blocks = sms * 8, n_iter = 2048;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int v = 0; v < 4; ++v) {
+        float best = 1e30f;
+        for (int it = 0; it < 4; ++it) {
+            cudaEventRecord(e0);
+            if (v == 0) issue_probe_kernel<0><<<blocks, threads>>>(d, n_iter, 0.999999, 1e-9, 1u);
+            if (v == 1) issue_probe_kernel<1><<<blocks, threads>>>(d, n_iter, 0.999999, 1e-9, 1u);
+            if (v == 2) issue_probe_kernel<2><<<blocks, threads>>>(d, n_iter, 0.999999, 1e-9, 1u);
+            if (v == 3) issue_probe_kernel<4><<<blocks, threads>>>(d, n_iter, 0.999999, 1e-9, 1u);
+            cudaEventRecord(e1);
+            if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return PTMC_ERR_CUDA; }
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            if (ms < best) best = ms;
+        }
+        // warp-DFMAs per SMSP: blocks*threads/32 warps over sms*4 SMSPs, 64 DFMA per iteration
+        const double warp_dfma_per_smsp = (double)blocks * threads / 32.0 / (sms * 4.0) * 64.0 * n_iter;
+        out_cycles[v] = best * 1e-3 * sm_mhz * 1e6 / warp_dfma_per_smsp;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return PTMC_OK;
+}
+
 double measure_fp64_peak(cudaStream_t st, int iters) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;

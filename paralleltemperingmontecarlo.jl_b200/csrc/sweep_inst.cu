@@ -26,12 +26,15 @@ static sweep_fn generic_kernel(int pot, int geom, int dbg) {
 }
 
 // Specialised production kernels of the headline family (ELJPotentialEven with 6 coefficients, SphericalBC,
-// BATCH8 streams): pair loop fully unrolled for ceil(n_atoms / G) = 1..8.
+// BATCH8 streams): pair loop fully unrolled for ceil(n_atoms / G) = 1..8 (1..16 for G = 4).
 static sweep_fn special_kernel(int niter) {
     constexpr int G = PTMC_G;
     switch (niter) {
 #define PTMC_SP(K) case K: return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_SPHERE, false, K, 6>;
         PTMC_SP(1) PTMC_SP(2) PTMC_SP(3) PTMC_SP(4) PTMC_SP(5) PTMC_SP(6) PTMC_SP(7) PTMC_SP(8)
+#if PTMC_G == 4
+        PTMC_SP(9) PTMC_SP(10) PTMC_SP(11) PTMC_SP(12) PTMC_SP(13) PTMC_SP(14) PTMC_SP(15) PTMC_SP(16)
+#endif
 #undef PTMC_SP
         default: return nullptr;
     }
