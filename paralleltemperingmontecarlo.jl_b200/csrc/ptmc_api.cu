@@ -307,6 +307,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     DevParams& P = h->P;
     memset(&P, 0, sizeof P);
     P.n_traj = c->n_traj; P.n_atoms = c->n_atoms; P.n_pad = ((c->n_atoms + G - 1) / G) * G;
+    P.moved_words = (c->n_atoms + 31) / 32;
     P.n_atom_moves = c->n_atom_moves; P.n_volume_moves = npt ? c->n_volume_moves : 0; P.n_steps = (int)h->n_steps;
     P.ensemble = c->ensemble; P.bc_kind = c->bc_kind; P.pot_kind = c->pot_kind; P.n_coeff = c->n_coeff;
     P.n_adjust = c->n_adjust; P.mc_sample = c->mc_sample; P.n_bin = c->n_bin;
@@ -329,7 +330,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     int rc = 0;
     if ((rc = dev_alloc(h, &P.pos, R * N * 3)) || (rc = dev_alloc(h, &P.box, R * 2)) || (rc = dev_alloc(h, &P.en_tot, R)) ||
         (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) ||
-        (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) || (rc = dev_alloc(h, &P.perm_g, R)) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
+        (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) || (rc = dev_alloc(h, &P.perm_g, R)) ||
+        (rc = dev_alloc(h, &P.moved_g, R * ((N + 31) / 32 + 1))) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
         (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
         (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4 * PTMC_RNG_LANES)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||
         (rc = dev_alloc(h, &P.slot_cursor, R)) || (rc = dev_alloc(h, &P.ladder_cursor, L)) ||
@@ -398,6 +400,7 @@ extern "C" PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, co
         std::vector<int> perm(R);
         for (size_t r = 0; r < R; ++r) perm[r] = (int)(r % (size_t)h->cfg.n_traj);
         CU(h, cudaMemcpy(P.perm_g, perm.data(), sizeof(int) * R, cudaMemcpyHostToDevice));
+        CU(h, cudaMemset(P.moved_g, 0, sizeof(int) * R * (P.moved_words + 1)));
     }
     if (h->runner) runner_launch_init(P, h->R, h->n_rep, h->stream);
     else launch_init(P, h->n_rep, h->stream);

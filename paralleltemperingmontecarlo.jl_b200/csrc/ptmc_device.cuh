@@ -38,6 +38,11 @@ struct DevParams {
     // exchange never moves it; perm_g is the slot -> configuration map, persisted between launches
     double* d2mat;      // [L][T][N][N]
     int* perm_g;        // [L][T]
+    // per configuration: bit mask of the atoms moved (accepted) since the upload + their count.  Frozen dist2_mat
+    // entries can only differ in a DECISION from recomputed distances for pairs of never-moved lattice atoms (exact
+    // cut-off ties); once every atom of a configuration has moved, its matrix is no longer read or maintained.
+    int* moved_g;       // [L][T][moved_words + 1]  (last int: count)
+    int moved_words;    // ceil(n_atoms / 32)
     // slot-side state
     double* max_displ;  // [L][T][4]
     double* max_boxlength; // [L][T]

@@ -29,6 +29,7 @@ struct SmemLayout {
     int off_exc;        // i64 exc counters [T][2]
     int off_ham;        // ham [T][2] (slot side)
     int off_lrng;       // ladder stream, one private copy per warp: 4 x u64 state + cursor + pad
+    int off_moved;      // periodic: int moved[T][words + 1]
     size_t bytes;
 };
 __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc) {
@@ -41,6 +42,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     s.off_ham = off; off += 2 * n_traj;
     s.off_lrng = off; off += 6 * n_warps;
     s.off_perm = off; off += (n_traj + 1) / 2 + 1;
+    s.off_moved = off; off += pbc ? (n_traj * ((n_pad + 31) / 32 + 1) + 1) / 2 + 1 : 0;
     s.bytes = (size_t)off * sizeof(double);
     return s;
 }
@@ -68,6 +70,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     double* hams = sm + lay.off_ham;
     u64* lrng = reinterpret_cast<u64*>(sm + lay.off_lrng);
     int* perm = reinterpret_cast<int*>(sm + lay.off_perm);
+    int* moved = reinterpret_cast<int*>(sm + lay.off_moved);
+    const int MW = P.moved_words + 1;            // ints per configuration in moved[]
     const bool npt = PBC && P.ensemble == PTMC_ENS_NPT;
     const bool rhombic = PBC && P.bc_kind == PTMC_BC_RHOMBIC;
     const i64 rep = (i64)lad * T + slot;      // replica (slot) index in the global arrays
@@ -93,6 +97,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
             scal[4 * c0 + 1] = L; scal[4 * c0 + 2] = h;
             scal[4 * c0 + 3] = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
             perm[slot] = c0;
+            if (PBC) for (int w = 0; w < MW; ++w) moved[c0 * MW + w] = P.moved_g[((i64)lad * T + c0) * MW + w];
             exc_cnt[2 * slot] = 0; exc_cnt[2 * slot + 1] = 0;
             hams[2 * slot] = P.ham[rep * 2]; hams[2 * slot + 1] = P.ham[rep * 2 + 1];
         }
@@ -229,14 +234,19 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                         // two row sums, :808-810).
                         double accn = 0.0, acco = 0.0;
                         if (PBC) {
-                            // periodic: the old row is dist2_mat[index, :] read from HBM (frozen values, exactly the
-                            // reference's semantics for d2 <= r_cut), the new row goes to new_dist2_vec in shared memory
+                            // periodic: while some atom of the configuration has never moved, the old row is
+                            // dist2_mat[index, :] read from HBM (frozen values: exactly the reference's d2 <= r_cut decisions for
+                            // lattice pairs that sit ON the cut-off) and the new row goes to new_dist2_vec; afterwards
+                            // ("thawed") no exact tie can exist and the old row is recomputed from the positions.
+                            const bool thawed = moved[c * MW + MW - 1] >= N;
                             const double* Drow = P.d2mat + (((size_t)lad * T + c) * N + i) * N;
                             double* NEW = Z + NP;
                             for (int j = g; j < N; j += G) {
                                 const double xj = X[j], yj = Y[j], zj = Z[j];
                                 double d2n = rhombic ? dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj) : dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj);
-                                double d2o = __ldcg(Drow + j);
+                                double d2o;
+                                if (thawed) d2o = rhombic ? dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj) : dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj);
+                                else d2o = __ldcg(Drow + j);
                                 const bool valid = (j != i);
                                 NEW[j] = valid ? d2n : 0.0;                       // new_dist2_vec[index] = 0, MCMoves.jl:111
                                 d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
@@ -313,13 +323,20 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                         en = new_en;
                         n_acc_atom += 1; n_adj_atom += 1;
                         if (PBC) {
-                            // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
-                            double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
-                            const double* NEW = Z + NP;
-                            for (int j = g; j < N; j += G) {
-                                const double v = NEW[j];
-                                __stcg(D + (size_t)i * N + j, v);
-                                __stcg(D + (size_t)j * N + i, v);
+                            if (moved[c * MW + MW - 1] < N) {
+                                // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
+                                double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
+                                const double* NEW = Z + NP;
+                                for (int j = g; j < N; j += G) {
+                                    const double v = NEW[j];
+                                    __stcg(D + (size_t)i * N + j, v);
+                                    __stcg(D + (size_t)j * N + i, v);
+                                }
+                                __syncwarp(gmask);
+                                if (g == 0) {
+                                    const int w = i >> 5, bit = 1 << (i & 31);
+                                    if (!(moved[c * MW + w] & bit)) { moved[c * MW + w] |= bit; moved[c * MW + MW - 1] += 1; }
+                                }
                             }
                         }
                         if (EAM) {
@@ -341,10 +358,15 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     // src/EnergyEvaluation.jl:397-474); rows are dealt to the lanes of the group.
                     double acce = 0.0;
                     double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
+                    const bool thawed = moved[c * MW + MW - 1] >= N;
                     for (int a = 0; a < N - 1; ++a) {
                         const double* Da = D + (size_t)a * N;
+                        const double xa = X[a], ya = Y[a], za = Z[a];
                         for (int j = a + 1 + g; j < N; j += G) {
-                            const double d2 = xmul(__ldcg(Da + j), sc2);      // new_dist2_mat[a, j]
+                            double d2o;
+                            if (thawed) d2o = rhombic ? dist2_pbc<true>(bx, xa, ya, za, X[j], Y[j], Z[j]) : dist2_pbc<false>(bx, xa, ya, za, X[j], Y[j], Z[j]);
+                            else d2o = __ldcg(Da + j);
+                            const double d2 = xmul(d2o, sc2);                 // new_dist2_mat[a, j]
                             if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
                         }
                     }
@@ -365,7 +387,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                         // swap_config_v! src/swap_config.jl:113-140
                         __syncwarp(gmask);
                         for (int j = g; j < N; j += G) { X[j] = xmul(scale, X[j]); Y[j] = xmul(scale, Y[j]); Z[j] = xmul(scale, Z[j]); }
-                        for (int k = g; k < N * N; k += G) __stcg(D + k, xmul(__ldcg(D + k), sc2));   // dist2_mat .= new_dist2_mat
+                        if (!thawed) for (int k = g; k < N * N; k += G) __stcg(D + k, xmul(__ldcg(D + k), sc2));   // dist2_mat .= new_dist2_mat
                         boxL = tL; boxH = tH; rcut = new_rcut; en = e_new;
                         bx = make_box(P.bc_kind, boxL, boxH);
                         n_acc_vol += 1; n_adj_vol += 1;
@@ -513,6 +535,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
             cn[PTMC_C_ATOM_TOT] += n_acc_atom; cn[PTMC_C_ATOM_ADJ] = n_adj_atom;
             if (PBC) {
                 P.perm_g[rep] = c;
+                for (int w = 0; w < MW; ++w) P.moved_g[((i64)lad * T + c) * MW + w] = moved[c * MW + w];
                 P.box[rep * 2] = scal[4 * c + 1]; P.box[rep * 2 + 1] = scal[4 * c + 2];
                 P.max_displ[rep * 4 + 1] = vmax;
                 cn[PTMC_C_VOL_TOT] += n_acc_vol; cn[PTMC_C_VOL_ADJ] = n_adj_vol;

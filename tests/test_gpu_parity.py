@@ -109,6 +109,20 @@ def test_pbc216_npt_replay():
     compare_traces(gpu, cpu, positions_exact=False)
 
 
+def test_pbc216_npt_replay_through_thaw():
+    # long enough for every atom of every configuration to have moved: the kernel stops reading the frozen dist2_mat and
+    # recomputes old rows from the positions ("thawed"); decisions and energies must stay on the oracle's trajectory
+    mcp, temp, start, pot, ens = P.host.deck_pbc216(n_traj=4, cycles=40)
+    md = np.full((1, 4, 4), 0.1)
+    md[:, :, 0] = 0.5
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=40, seed=12, max_displ=md, n_adjust=20)
+    compare_traces(gpu, cpu, positions_exact=False)
+    acc = gpu["trace"]["accepted"]
+    idx = gpu["trace"]["move_index"]
+    moved_atoms = [len(np.unique(idx[0, :, s][(acc[0, :, s] == 1) & (idx[0, :, s] <= 216)])) for s in range(4)]
+    assert min(moved_atoms) > 200, moved_atoms          # (exchanges permute configurations; every slot saw nearly all atoms move)
+
+
 def test_periodic_nvt_replay():
     start = _small_pbc(P.CubicBC)
     mcp = P.MCParams(20, 4, 32)
