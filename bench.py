@@ -189,12 +189,23 @@ def run_b200(args):
     pos, box = initial_arrays(mcp, start, L)
     pin_pos = torch.from_numpy(pos).pin_memory()
     pin_box = torch.from_numpy(box).pin_memory()
-    eng.upload_states(pin_pos.numpy(), pin_box.numpy())
+    # step sizes: a pilot of 64 ladders runs 3000 cycles (30 adaptations, src/Exchange.jl:250-263) so that the timed
+    # region works at the adapted 40-60 % acceptance instead of the constructor's max_displ = 0.1 (~87 %)
+    pcfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=64, seed=seed + 7, device=local, lanes_per_replica=args.lanes)
+    pilot = Engine(pcfg)
+    ppos, pbox = initial_arrays(mcp, start, 64)
+    pilot.upload_states(ppos, pbox)
+    pilot.run_cycles(1, 3000, False)
+    md_slot = np.median(pilot.download_states(("max_displ",))["max_displ"], axis=0)      # [n_traj][4]
+    pilot.close()
+    max_displ = np.ascontiguousarray(np.broadcast_to(md_slot, (L, N_TRAJ, 4)))
+    pin_md = torch.from_numpy(max_displ).pin_memory()
+    eng.upload_states(pin_pos.numpy(), pin_box.numpy(), pin_md.numpy())
     if world > 1:
         multi.seed_global(eng, seed, rank * L, world * L)
     else:
         eng.seed(seed)
-    # equilibrate a little so that step sizes have adapted and the histogram window is meaningful
+    # equilibrate so that the histogram window is meaningful
     eng.run_cycles(1, 200, False)
     en = eng.download_states(("en_tot",))["en_tot"]
     eng.reset_counters()
@@ -242,6 +253,7 @@ def run_b200(args):
         barrier()
     launches = eng.launch_count() - launches0
     eng.sync()
+    acc_timed = float(eng.download_states(("counters",))["counters"][:, :, abi.C_ATOM_TOT].sum()) / (L * N_TRAJ * N_ATOMS * cycles * (args.steps + args.warmup))
     ms = e0.elapsed_time(e1)
     kms = [a.elapsed_time(b) for a, b in kernel_ms]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -258,12 +270,12 @@ def run_b200(args):
     # cudaHostRegister): positions, box, energies, step sizes, counters, ham
     pinned = {k: torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory().numpy()
               for k, (shp, dt) in eng.state_shapes().items()}
-    h2d = pin_pos.numel() * 8 + pin_box.numel() * 8
+    h2d = pin_pos.numel() * 8 + pin_box.numel() * 8 + pin_md.numel() * 8
     d2h = 0
     e2e_steps = max(3, min(args.steps, 5))
 
     def e2e_step(i):
-        eng.upload_states(pin_pos.numpy(), pin_box.numpy())
+        eng.upload_states(pin_pos.numpy(), pin_box.numpy(), pin_md.numpy())
         eng.set_hist_bounds(float(en.min()) - 1e-3, float(en.max()) + 2e-3)
         eng.run_cycles(i, cycles, True)
         st = eng.download_states(out=pinned)
@@ -307,7 +319,8 @@ def run_b200(args):
     if rank == 0:
         conf = workload_config(L, cycles)
         conf.update({"lanes_per_replica": lanes, "hist_samples_total": hist_total, "hist_samples_expected": expect,
-                     "sweep_kernel_ms_avg": kernel_ms_avg, "e2e_steps": e2e_steps,
+                     "sweep_kernel_ms_avg": kernel_ms_avg, "e2e_steps": e2e_steps, "atom_move_acceptance": acc_timed,
+                     "max_displ_range": [float(md_slot[:, 0].min()), float(md_slot[:, 0].max())],
                      "algorithmic_hbm_bytes_per_move": 0, "state_bytes_per_launch_per_gpu": int(pos.nbytes * 2)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -315,7 +328,10 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": (achieved / peak) if peak else None, "traffic": None,
+                             "frac": (achieved / peak) if peak else None,
+                             # dram__bytes_read + dram__bytes_write of one sweep launch from the ncu --set full capture
+                             # profiles/r01_sweep_ne55_g8.md (state load / store; independent of the cycle count)
+                             "traffic": 305509120,
                              "note": "FP64 FMA pipe bound (not hbm/tensor): W = %d algorithmic flops per move; peak = DFMA-chain "
                                      "peak measured live (MEASURED_PEAKS.json has no FP64 figure); HBM traffic is ~0 B/move" % W_FLOPS_PER_MOVE},
                 "cpu_baseline": cpu}

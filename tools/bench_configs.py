@@ -42,6 +42,7 @@ def run(name):
         bounds = (0.0, 1.0, 0.8 * v0, 2.0 * v0)
     eng.set_hist_bounds(*bounds)
     eng.run_cycles(1, warm, False)
+    eng.reset_counters()
     eng.sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.Stream()
@@ -64,14 +65,48 @@ def run(name):
     return out
 
 
+CPU_SAMPLE = {   # ladders, cycles for the CPU-oracle sample of each config (a few seconds on 16 cores)
+    "c1_ne13_elj_nvt_32T": (64, 400), "c2_ne55_elj_nvt_24T": (64, 100), "c3_cu55_eam_nvt_28T": (32, 40),
+    "c4_pbc216_elj_npt_16T": (16, 20), "c5_cu55_runner_nvt_28T": (1, 1),
+}
+
+
+def run_cpu(name):
+    """The oracle (C restatement of the reference's CPU path) with OpenMP on all host cores, bounded sample."""
+    import os
+    from oracle import oracle
+    deck, _, _, _, _, bounds = CASES[name]
+    L, cyc = CPU_SAMPLE[name]
+    mcp, temp, start, pot, ens = deck()
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=99)
+    cores = os.cpu_count() or 1
+    eng = oracle.OracleEngine(cfg, threads=cores)
+    pos, box = initial_arrays(mcp, start, L)
+    eng.upload_states(pos, box)
+    if bounds is None:
+        v0 = P.get_volume(start[0].boundary_condition)
+        bounds = (0.0, 1.0, 0.8 * v0, 2.0 * v0)
+    eng.set_hist_bounds(*bounds)
+    t0 = time.perf_counter()
+    eng.run_cycles(1, cyc, True)
+    dt = time.perf_counter() - t0
+    eng.close()
+    moves = L * mcp.n_traj * cfg.n_steps * cyc
+    return {"cpu_moves_per_s": moves / dt, "cpu_cores": cores, "cpu_sample_moves": moves, "cpu_s": dt}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a bounded sample")
     a = ap.parse_args()
     names = [n for n in CASES if not a.only or any(n.startswith(p) for p in a.only.split(","))]
     for n in names:
         t0 = time.time()
         r = run(n)
+        if a.cpu:
+            r.update(run_cpu(n))
+            r["gpu_over_cpu"] = r["moves_per_s"] / r["cpu_moves_per_s"]
         r["wall_s"] = time.time() - t0
         print(json.dumps(r), flush=True)
 
