@@ -228,6 +228,10 @@ __device__ __forceinline__ double elj_even_poly(const DevParams& P, double x) {
 // 34 FP64 instructions per pair including the two squared distances.
 // Lanes without a pair pass d2n = d2o = PAIR_OFF: x^3 underflows to exactly 0 and nothing is accumulated.
 #define PTMC_PAIR_OFF 1e150
+// Coordinate of a "parked" atom: the moved atom itself and the padding atoms of the free-space ELJEven kernels sit at
+// (FAR, FAR, FAR) while a row is evaluated, so their pair terms vanish exactly (d2 = 3e150 -> x^3 underflows to 0)
+// without any per-pair select.
+#define PTMC_FAR 1e75
 template <int NC>
 __device__ __forceinline__ void elj_even_pair_acc(const DevParams& P, double d2n, double d2o, double& acc_new, double& acc_old) {
     const double y = rcp_pos3(d2n * d2o);

@@ -57,6 +57,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     constexpr bool EAM = (POT == PTMC_POT_EAM);
     constexpr bool PBC = (GEOM == GEOM_PBC);
     constexpr bool BATCH = !DBG;
+    constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN;   // mask by parking atoms far away instead of per-pair selects
     const int T = P.n_traj, N = P.n_atoms;
     const int NP = NITER ? NITER * G : P.n_pad;
     const int lad = blockIdx.x;
@@ -84,7 +85,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
         const double* gp = P.pos + rep * 3 * N;
         for (int j = g; j < NP; j += G) {
             bool v = j < N;
-            X[j] = v ? gp[3 * j] : 0.0; Y[j] = v ? gp[3 * j + 1] : 0.0; Z[j] = v ? gp[3 * j + 2] : 0.0;
+            const double pad = PARK ? PTMC_FAR : 0.0;
+            X[j] = v ? gp[3 * j] : pad; Y[j] = v ? gp[3 * j + 1] : pad; Z[j] = v ? gp[3 * j + 2] : pad;
             if (EAM) {
                 Z[NP + j] = v ? P.comp[(rep * N + j) * 2] : 1.0;          // phi
                 Z[2 * NP + j] = v ? P.comp[(rep * N + j) * 2 + 1] : 1.0;  // rho
@@ -229,6 +231,12 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     }
                     // -------------------------------- energy_update! src/EnergyEvaluation.jl:1474-1506,1567-1591
                     double new_en;
+                    if (PARK) {
+                        // park the moved atom: its own pair term (d2_old = 0) must not enter the row sums
+                        __syncwarp(gmask);
+                        if (g == 0) { X[i] = PTMC_FAR; Y[i] = PTMC_FAR; Z[i] = PTMC_FAR; }
+                        __syncwarp(gmask);
+                    }
                     if (!EAM) {
                         // dimer_energy_update! :804-821: sum_j e(new_ij) - sum_j e(old_ij) (the reference forms the same
                         // two row sums, :808-810).
@@ -266,8 +274,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                                 double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
                                 double d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
                                 if (POT == PTMC_POT_ELJ_EVEN) {
-                                    d2n = valid ? d2n : PTMC_PAIR_OFF; d2o = valid ? d2o : PTMC_PAIR_OFF;
-                                    elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);
+                                    elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);     // parked atoms contribute exactly 0
                                 } else {
                                     // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
                                     const double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
@@ -317,6 +324,9 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     de = xsub(new_en, en);
                     const double u = BATCH ? B.template rand<4>(gmask) : S.rand();
                     acc = metropolis_accept(-xmul(de, beta), u);
+                    if (PARK) {
+                        if (!acc && g == 0) { X[i] = xi; Y[i] = yi; Z[i] = zi; }        // un-park
+                    }
                     if (acc) {
                         // swap_atom_config! src/swap_config.jl:40-51 (+ swap_vars! :208-211 for EAM)
                         if (g == 0) { X[i] = tx; Y[i] = ty; Z[i] = tz; }
