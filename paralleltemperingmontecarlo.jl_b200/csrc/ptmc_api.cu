@@ -291,7 +291,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->cfg.runner = nullptr;
     h->runner = c->pot_kind == PTMC_POT_RUNNER;
     h->device = c->device;
-    h->geom = sphere ? GEOM_SPHERE : GEOM_PBC;
+    h->geom = sphere ? GEOM_SPHERE : (c->bc_kind == PTMC_BC_RHOMBIC ? GEOM_RHOMB : GEOM_PBC);
     h->n_rep = c->n_ladders * c->n_traj;
     h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0);
     int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj);

@@ -18,8 +18,10 @@ static sweep_fn generic_kernel(int pot, int geom, int dbg) {
         return dbg ? (sweep_fn)sweep_kernel<G, POT, GEOM, true, 0, 0> : (sweep_fn)sweep_kernel<G, POT, GEOM, false, 0, 0>;
     PTMC_PICK(PTMC_POT_ELJ_EVEN, GEOM_SPHERE)
     PTMC_PICK(PTMC_POT_ELJ_EVEN, GEOM_PBC)
+    PTMC_PICK(PTMC_POT_ELJ_EVEN, GEOM_RHOMB)
     PTMC_PICK(PTMC_POT_ELJ, GEOM_SPHERE)
     PTMC_PICK(PTMC_POT_ELJ, GEOM_PBC)
+    PTMC_PICK(PTMC_POT_ELJ, GEOM_RHOMB)
     PTMC_PICK(PTMC_POT_EAM, GEOM_SPHERE)
 #undef PTMC_PICK
     return nullptr;
@@ -43,9 +45,15 @@ static sweep_fn special_kernel(int niter) {
 // pot: ptmc_pot_kind (ELJ, ELJ_EVEN, EAM); geom: Geom; dbg: sequential-stream / replay / trace build;
 // niter = n_pad / G; n_coeff: number of ELJ coefficients
 sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff) {
+    constexpr int G = PTMC_G;
     if (!dbg && pot == PTMC_POT_ELJ_EVEN && geom == GEOM_SPHERE && n_coeff == 6) {
         sweep_fn f = special_kernel(niter);
         if (f) return f;
+    }
+    // periodic ELJEven with the six-coefficient form: Horner chain unrolled, coefficients in uniform registers
+    if (!dbg && pot == PTMC_POT_ELJ_EVEN && n_coeff == 6) {
+        if (geom == GEOM_PBC) return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_PBC, false, 0, 6>;
+        if (geom == GEOM_RHOMB) return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_RHOMB, false, 0, 6>;
     }
     return generic_kernel(pot, geom, dbg);
 }

@@ -19,7 +19,7 @@ namespace ptmc {
 #endif
 __host__ __device__ constexpr int sweep_max_threads_c(int G) { return G == 32 ? 512 : PTMC_MAX_THREADS_SMALL; }
 __host__ __device__ constexpr int sweep_min_blocks_c(int G) { return G == 32 ? 1 : PTMC_MIN_BLOCKS_SMALL; }
-enum Geom { GEOM_SPHERE = 0, GEOM_PBC = 1 };   // SphericalBC+NVT | periodic BC, NVT or NPT (runtime)
+enum Geom { GEOM_SPHERE = 0, GEOM_PBC = 1, GEOM_RHOMB = 2 };   // SphericalBC+NVT | cubic / rectangular box | rhombic box (NVT or NPT at run time)
 
 // shared-memory layout of one CTA (doubles unless noted)
 struct SmemLayout {
@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
 sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
     extern __shared__ double sm[];
     constexpr bool EAM = (POT == PTMC_POT_EAM);
-    constexpr bool PBC = (GEOM == GEOM_PBC);
+    constexpr bool PBC = (GEOM != GEOM_SPHERE);
+    constexpr bool rhombic = (GEOM == GEOM_RHOMB);
     constexpr bool BATCH = !DBG;
     constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN;   // mask by parking atoms far away instead of per-pair selects
     const int T = P.n_traj, N = P.n_atoms;
@@ -74,7 +75,6 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     int* moved = reinterpret_cast<int*>(sm + lay.off_moved);
     const int MW = P.moved_words + 1;            // ints per configuration in moved[]
     const bool npt = PBC && P.ensemble == PTMC_ENS_NPT;
-    const bool rhombic = PBC && P.bc_kind == PTMC_BC_RHOMBIC;
     const i64 rep = (i64)lad * T + slot;      // replica (slot) index in the global arrays
 
     // ---- load: slot s starts with configuration buffer s ----------------------------------------------
@@ -257,10 +257,17 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                                 else d2o = __ldcg(Drow + j);
                                 const bool valid = (j != i);
                                 NEW[j] = valid ? d2n : 0.0;                       // new_dist2_vec[index] = 0, MCMoves.jl:111
-                                d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
-                                double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
-                                if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }   // :323-336
-                                accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
+                                if (POT == PTMC_POT_ELJ_EVEN) {
+                                    // one shared reciprocal for the pair; beyond the cut-off (:323-336) or self -> contributes exactly 0
+                                    const double a = (valid && (!npt || d2n <= rcut)) ? d2n : PTMC_PAIR_OFF;
+                                    const double b = (valid && (!npt || d2o <= rcut)) ? d2o : PTMC_PAIR_OFF;
+                                    elj_even_pair_acc<NC>(P, a, b, accn, acco);
+                                } else {
+                                    d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
+                                    double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
+                                    if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }   // :323-336
+                                    accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
+                                }
                             }
                         } else {
                             // free space: the old row is recomputed from the positions (no dist2_mat is stored)
