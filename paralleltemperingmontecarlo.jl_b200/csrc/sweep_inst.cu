@@ -50,7 +50,19 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, 
         sweep_fn f = special_kernel(niter);
         if (f) return f;
     }
-    // periodic ELJEven with the six-coefficient form: Horner chain unrolled, coefficients in uniform registers
+    // periodic ELJEven with the six-coefficient form: Horner chain unrolled, coefficients in uniform registers; for the wide
+    // lane groups that periodic systems use, the thawed pair loop is unrolled as well
+#if PTMC_G >= 16
+    if (!dbg && pot == PTMC_POT_ELJ_EVEN && n_coeff == 6 && (geom == GEOM_PBC || geom == GEOM_RHOMB)) {
+        switch (niter) {
+#define PTMC_SPB(K) case K: return geom == GEOM_PBC ? (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_PBC, false, K, 6> \
+                                                    : (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_RHOMB, false, K, 6>;
+            PTMC_SPB(1) PTMC_SPB(2) PTMC_SPB(3) PTMC_SPB(4) PTMC_SPB(5) PTMC_SPB(6) PTMC_SPB(7) PTMC_SPB(8)
+#undef PTMC_SPB
+            default: break;
+        }
+    }
+#endif
     if (!dbg && pot == PTMC_POT_ELJ_EVEN && n_coeff == 6) {
         if (geom == GEOM_PBC) return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_PBC, false, 0, 6>;
         if (geom == GEOM_RHOMB) return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_RHOMB, false, 0, 6>;

@@ -249,12 +249,38 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                             const bool thawed = moved[c * MW + MW - 1] >= N;
                             const double* Drow = P.d2mat + (((size_t)lad * T + c) * N + i) * N;
                             double* NEW = Z + NP;
+                            if (thawed) {
+                                // thawed: both rows from the positions in shared memory, pair loop unrolled like the free-space one
+                                const double* Xg = X + g;
+                                auto pbc_term = [&](int k) {
+                                    const int j = g + k * G;
+                                    const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
+                                    const double d2n = rhombic ? dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj) : dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj);
+                                    const double d2o = rhombic ? dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj) : dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj);
+                                    const bool valid = (j != i) && (j < N);
+                                    if (POT == PTMC_POT_ELJ_EVEN) {
+                                        const double a = (valid && (!npt || d2n <= rcut)) ? d2n : PTMC_PAIR_OFF;
+                                        const double b = (valid && (!npt || d2o <= rcut)) ? d2o : PTMC_PAIR_OFF;
+                                        elj_even_pair_acc<NC>(P, a, b, accn, acco);
+                                    } else {
+                                        const double dn = valid ? d2n : 1.0, dold = valid ? d2o : 1.0;
+                                        double en_j = pair_energy<POT, NC>(P, dn), eo_j = pair_energy<POT, NC>(P, dold);
+                                        if (npt) { en_j = (dn <= rcut) ? en_j : 0.0; eo_j = (dold <= rcut) ? eo_j : 0.0; }
+                                        accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
+                                    }
+                                };
+                                if (NITER) {
+#pragma unroll
+                                    for (int k = 0; k < NITER; ++k) pbc_term(k);
+                                } else {
+                                    const int nk = NP / G;
+                                    for (int k = 0; k < nk; ++k) pbc_term(k);
+                                }
+                            } else
                             for (int j = g; j < N; j += G) {
                                 const double xj = X[j], yj = Y[j], zj = Z[j];
                                 double d2n = rhombic ? dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj) : dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj);
-                                double d2o;
-                                if (thawed) d2o = rhombic ? dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj) : dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj);
-                                else d2o = __ldcg(Drow + j);
+                                double d2o = __ldcg(Drow + j);
                                 const bool valid = (j != i);
                                 NEW[j] = valid ? d2n : 0.0;                       // new_dist2_vec[index] = 0, MCMoves.jl:111
                                 if (POT == PTMC_POT_ELJ_EVEN) {
