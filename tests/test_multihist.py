@@ -23,6 +23,17 @@ def test_reference_known_answer():
         assert cv[int(idx) - 1] == pytest.approx(want, rel=1e-9)      # Julia sums sequentially; we sum with numpy
 
 
+def test_reference_known_answer_npt():
+    from ptmc_b200.multihist import multihistogram_NPT
+    k = json.loads((GOLD / "multihist_npt_kat.json").read_text())
+    temp = P.TempGrid(*k["temp"][:2], k["temp"][2])
+    t, cp = multihistogram_NPT(temp.t_grid, temp.beta_grid, k["ev_histogram"], k["en_min"], k["en_max"], k["v_min"], k["v_max"],
+                               k["n_bin"], k["pressure"], k["conv_threshold"])
+    assert len(cp) == 30
+    for idx, want in k["cp_expected_1based"].items():
+        assert cp[int(idx) - 1] == pytest.approx(want, rel=1e-9)
+
+
 BOUNDS = (-0.00565, -0.0024)     # fixed energy window (the reference's own Ne13 run: -0.005638 .. -0.002419, multihist_test.jl:7)
 
 
