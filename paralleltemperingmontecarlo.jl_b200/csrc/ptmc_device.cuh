@@ -20,7 +20,7 @@ typedef long long i64;
 // Everything the kernels need, passed by value as the kernel parameter (constant bank).
 struct DevParams {
     // sizes
-    int n_traj, n_atoms, n_pad;          // n_pad = n_atoms rounded up to a multiple of 32
+    int n_traj, n_atoms, n_pad;          // n_pad = n_atoms rounded up to a multiple of the lanes per replica
     int n_atom_moves, n_volume_moves, n_steps;
     int ensemble, bc_kind, pot_kind, n_coeff;
     int n_adjust, mc_sample, n_bin;

@@ -1,5 +1,5 @@
 // sweep_kernel.cuh — the parallel-tempering sweep: n_cycles x mc_cycle! (src/MCRun.jl:192-253) for one
-// ladder per CTA.  Instantiated per (lanes-per-replica G, potential, geometry, debug) in sweep_inst_*.cu.
+// ladder per CTA.  Instantiated per (lanes-per-replica G, potential, geometry, debug, unrolling) in sweep_inst.cu.
 //
 //   mc_step!  (src/MCRun.jl:169-182)  -> every group runs n_steps x mc_move! on its slot, no CTA sync
 //   exchange  (src/MCRun.jl:203-205, src/Exchange.jl:132-186) -> thread 0 between two __syncthreads()

@@ -360,6 +360,30 @@ def test_energy_bookkeeping_other_potentials(case):
     eng.close(); eng2.close()
 
 
+def test_ptmc_run_host_api(oracle):
+    # the reference-facing call: ptmc_run! (src/MCRun.jl:363-432) with the reference's argument list; the same call through
+    # the oracle engine gives the same Output (histogram window from the half-length equilibration, quirk 1; finalise_results)
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=8, cycles=300)
+    out = []
+    for cls in (Engine, oracle.OracleEngine):
+        states, results = P.ptmc_run(mcp, temp, start, pot, ens, n_ladders=3, seed=5, engine_cls=cls)
+        out.append((states, results))
+    (sg, rg), (sc, rc) = out
+    assert len(rg) == 3
+    for a, b in zip(rg, rc):
+        # the window comes from each engine's own running energies, which agree to the last bits only
+        assert a.en_min == pytest.approx(b.en_min, rel=1e-12) and a.en_max == pytest.approx(b.en_max, rel=1e-12)
+        assert a.delta_en_hist == (a.en_max - a.en_min) / (a.n_bin - 1)
+        assert a.en_histogram.sum() == 8 * 300 and np.abs(a.en_histogram - b.en_histogram).sum() <= 4   # bin-edge ties
+        np.testing.assert_allclose(a.en_avg, b.en_avg, rtol=1e-12)
+        np.testing.assert_allclose(a.heat_cap, b.heat_cap, rtol=1e-8)
+        assert np.array_equal(a.count_stat_atom, b.count_stat_atom)
+        assert np.array_equal(np.nan_to_num(a.count_stat_exc), np.nan_to_num(b.count_stat_exc))
+    assert np.array_equal(sg["pos"], sc["pos"])
+    with pytest.raises(ValueError):                           # SphericalBC + NPT, src/Ensembles.jl:189
+        P.ptmc_run(mcp, temp, start, pot, P.NPT(13, 1e-9, False))
+
+
 def test_error_behaviour():
     mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=4, cycles=5)
     cfg = sweep_config(mcp, temp, start, pot, ens)
