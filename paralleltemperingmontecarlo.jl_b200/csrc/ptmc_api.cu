@@ -350,6 +350,29 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             return bail(fail(h, PTMC_ERR_CUDA, "copying the network failed"));
         Rr.net = d_net;
     }
+    if (c->pot_kind == PTMC_POT_EAM && P.eam_hn > 0 && P.eam_hm > 0 && P.eam_hn <= 12 && P.eam_hm <= 12) {
+        // (r2)^-p table of eam_invrexp (ptmc_device.cuh); p <= 12 keeps the degree-6 series below 1e-16
+        std::vector<double> tab(PTMC_EAM_TAB_DOUBLES, 0.0);
+        const long double pn = (long double)P.eam_hn, pm = (long double)P.eam_hm;
+        for (int k = 0; k < PTMC_EAM_K; ++k) {
+            const double rk = 1.0 / (1.0 + (k + 0.5) / PTMC_EAM_K);
+            tab[4 * k] = rk; tab[4 * k + 1] = (double)powl((long double)rk, pn); tab[4 * k + 2] = (double)powl((long double)rk, pm);
+        }
+        for (int e = -PTMC_EAM_E; e < PTMC_EAM_E; ++e) {
+            tab[4 * PTMC_EAM_K + 2 * (e + PTMC_EAM_E)] = (double)powl(2.0L, -pn * e);
+            tab[4 * PTMC_EAM_K + 2 * (e + PTMC_EAM_E) + 1] = (double)powl(2.0L, -pm * e);
+        }
+        long double cn = 1, cm = 1;
+        for (int j = 1; j <= PTMC_EAM_DEG; ++j) {
+            cn = cn * (-pn - (j - 1)) / j; cm = cm * (-pm - (j - 1)) / j;      // binom(-p, j)
+            P.eam_cn[j - 1] = (double)cn; P.eam_cm[j - 1] = (double)cm;
+        }
+        double* d_tab = nullptr;
+        if ((rc = dev_alloc(h, &d_tab, tab.size()))) return bail(rc);
+        if (cudaMemcpy(d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(h, PTMC_ERR_CUDA, "copying the EAM power table failed"));
+        P.eam_tab = d_tab;
+    }
     P.betas = d_betas; P.en_min = en_min; P.en_max = en_max; P.v_min = v_min; P.v_max = v_max;
     P.error = h->d_error;
     if (cudaMemcpy(d_betas, h->betas.data(), sizeof(double) * c->n_traj, cudaMemcpyHostToDevice) != cudaSuccess)

@@ -17,6 +17,11 @@ namespace ptmc {
 typedef unsigned long long u64;
 typedef long long i64;
 
+#define PTMC_EAM_DEG 6          // degree of the binomial series of (1 + t)^-p, |t| <= 2^-9
+#define PTMC_EAM_K 256          // mantissa intervals
+#define PTMC_EAM_E 64           // binary exponents -64..63 of r2 are tabulated
+#define PTMC_EAM_TAB_DOUBLES (PTMC_EAM_K * 4 + 2 * PTMC_EAM_E * 2)
+
 // Everything the kernels need, passed by value as the kernel parameter (constant bank).
 struct DevParams {
     // sizes
@@ -27,8 +32,12 @@ struct DevParams {
     int replay;                          // 1: consume pre-drawn draws
     double min_acc, max_acc, pressure;
     double coeff[PTMC_MAX_COEFF];
-    double eam_hn, eam_hm;               // n/2, m/2  (r^-n = exp(-(n/2) log r2))
+    double eam_hn, eam_hm;               // n/2, m/2  (r^-n = (r2)^-(n/2))
     double eam_ean, eam_ecam;
+    // table-driven (r2)^-p, p = n/2 and m/2 (eam_invrexp): binomial coefficients binom(-p, 1..6) and the table
+    // [256][4] = {1/m_k, (1/m_k)^(n/2), (1/m_k)^(m/2), 0} followed by [128][2] = {2^(-n/2 e), 2^(-m/2 e)}, e = -64..63
+    double eam_cn[PTMC_EAM_DEG], eam_cm[PTMC_EAM_DEG];
+    const double* eam_tab;               // nullptr: exponents too large for the series, use log/exp
     // config-side state at rest, slot ordered: [L][T]...
     double* pos;        // [L][T][N][3]
     double* box;        // [L][T][2]
@@ -246,11 +255,32 @@ template <int POT, int NC = 0>
 __device__ __forceinline__ double pair_energy(const DevParams& P, double r2) {
     return POT == PTMC_POT_ELJ ? elj_odd(P, r2) : elj_even<NC>(P, r2);
 }
-// invrexp src/EnergyEvaluation.jl:1088-1095: (r^-n, r^-m) = (exp(-(n/2) log r2), exp(-(m/2) log r2)); r2 > 0.
-__device__ __forceinline__ void eam_invrexp(const DevParams& P, double r2, double& phi, double& rho) {
+// invrexp src/EnergyEvaluation.jl:1088-1095: (r^-n, r^-m) = ((r2)^-(n/2), (r2)^-(m/2)); r2 > 0.
+// Reference form of this library: exp(-(n/2) log r2), ~16 ulp, ~80 FP64 instructions.
+__device__ __forceinline__ void eam_invrexp_slow(const DevParams& P, double r2, double& phi, double& rho) {
     double l = log(r2);
     phi = exp(-P.eam_hn * l);
     rho = exp(-P.eam_hm * l);
+}
+// Table-driven form: r2 = 2^e m, m in [1, 2); k = top 8 mantissa bits, t = m / m_k - 1 (one FMA with the tabulated
+// reciprocal, |t| <= 2^-9); (r2)^-p = 2^(-p e) (1/m_k)^p (1 + t)^-p with the binomial series to degree 6
+// (truncation < 2e-17): 17 FP64 instructions for both powers, <= 2 ulp.  `tab` may live in shared or global memory.
+__device__ __forceinline__ void eam_invrexp(const DevParams& P, const double* tab, double r2, double& phi, double& rho) {
+    const int hi = __double2hiint(r2), lo = __double2loint(r2);
+    const int e = (hi >> 20) - 1023;
+    if (tab == nullptr || (unsigned)(e + PTMC_EAM_E) >= 2u * PTMC_EAM_E) { eam_invrexp_slow(P, r2, phi, rho); return; }
+    const int k = (hi >> 12) & (PTMC_EAM_K - 1);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 a = *reinterpret_cast<const double2*>(tab + 4 * k);        // 1/m_k, (1/m_k)^(n/2)
+    const double tm = tab[4 * k + 2];                                         // (1/m_k)^(m/2)
+    const double2 ee = *reinterpret_cast<const double2*>(tab + 4 * PTMC_EAM_K + 2 * (e + PTMC_EAM_E));
+    const double t = fma(m, a.x, -1.0);
+    double pn = P.eam_cn[5], pm = P.eam_cm[5];
+#pragma unroll
+    for (int j = 4; j >= 0; --j) { pn = fma(pn, t, P.eam_cn[j]); pm = fma(pm, t, P.eam_cm[j]); }
+    pn = fma(pn, t, 1.0); pm = fma(pm, t, 1.0);
+    phi = pn * (a.y * ee.x);
+    rho = pm * (tm * ee.y);
 }
 
 // lrc(::ELJPotentialEven) src/EnergyEvaluation.jl:968-982 (r_cut is the squared cut-off)

@@ -30,6 +30,7 @@ struct SmemLayout {
     int off_ham;        // ham [T][2] (slot side)
     int off_lrng;       // ladder stream, one private copy per warp: 4 x u64 state + cursor + pad
     int off_moved;      // periodic: int moved[T][words + 1]
+    int off_tab;        // EAM: the (r2)^-p table (PTMC_EAM_TAB_DOUBLES, 16-byte aligned)
     size_t bytes;
 };
 __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc) {
@@ -43,6 +44,8 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     s.off_lrng = off; off += 6 * n_warps;
     s.off_perm = off; off += (n_traj + 1) / 2 + 1;
     s.off_moved = off; off += pbc ? (n_traj * ((n_pad + 31) / 32 + 1) + 1) / 2 + 1 : 0;
+    off += off & 1;
+    s.off_tab = off; off += pot_kind == PTMC_POT_EAM ? PTMC_EAM_TAB_DOUBLES : 0;
     s.bytes = (size_t)off * sizeof(double);
     return s;
 }
@@ -76,6 +79,14 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     const int MW = P.moved_words + 1;            // ints per configuration in moved[]
     const bool npt = PBC && P.ensemble == PTMC_ENS_NPT;
     const i64 rep = (i64)lad * T + slot;      // replica (slot) index in the global arrays
+    const double* eam_tab = nullptr;
+    if (EAM) {
+        if (P.eam_tab) {
+            double* tb = sm + lay.off_tab;
+            for (int k = tid; k < PTMC_EAM_TAB_DOUBLES; k += blockDim.x) tb[k] = P.eam_tab[k];
+            eam_tab = tb;
+        }
+    }
 
     // ---- load: slot s starts with configuration buffer s ----------------------------------------------
     if (active) {
@@ -339,8 +350,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                             const bool valid = (j != i) && (j < N);
                             d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
                             double pn, rn, po, ro;
-                            eam_invrexp(P, d2n, pn, rn);
-                            eam_invrexp(P, d2o, po, ro);
+                            eam_invrexp(P, eam_tab, d2n, pn, rn);
+                            eam_invrexp(P, eam_tab, d2o, po, ro);
                             double tp = pn - po, tr = rn - ro;          // exactly 0 when !valid
                             double nphi = PHI[j] + tp, nrho = RHO[j] + tr;
                             NPHI[j] = nphi; NRHO[j] = nrho;
@@ -623,7 +634,7 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                 if (j == a) continue;
                 double dx = gp[3 * a] - gp[3 * j], dy = gp[3 * a + 1] - gp[3 * j + 1], dz = gp[3 * a + 2] - gp[3 * j + 2];
                 double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                double p, r; eam_invrexp(P, d2, p, r);
+                double p, r; eam_invrexp(P, P.eam_tab, d2, p, r);
                 sp += p; sr += r;
             }
             P.comp[(rep * N + a) * 2] = sp; P.comp[(rep * N + a) * 2 + 1] = sr;

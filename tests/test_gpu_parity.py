@@ -321,6 +321,23 @@ def test_pair_arithmetic_accuracy(oracle):
     eng.close()
 
 
+def test_eam_power_accuracy():
+    # invrexp (src/EnergyEvaluation.jl:1088-1095): the table-driven (r2)^-(n/2) of the sweep kernel against extended
+    # precision over the physical range and at the edges of the tabulated exponent range (log/exp path outside it)
+    mcp, temp, start, pot, ens = P.host.deck_cu55_eam(n_traj=4, cycles=1)
+    eng = Engine(sweep_config(mcp, temp, start, pot, ens))
+    rng = np.random.default_rng(1)
+    d2 = np.concatenate([rng.uniform(1.0, 4000.0, 400000), 2.0 ** rng.uniform(-70, 70, 20000),
+                         np.array([1.0, 2.0, 4.0, 1.0 + 2.0 ** -52, 2.0 - 2.0 ** -52, 2.0 ** -64, 2.0 ** 63.5])])
+    phi, _ = eng.debug_pair_energy(d2, d2[::-1].copy())
+    ref = d2.astype(np.longdouble) ** np.longdouble(-pot.n / 2)
+    rel = np.abs((phi.astype(np.longdouble) - ref) / ref).astype(float)
+    inside = (d2 >= 2.0 ** -64) & (d2 < 2.0 ** 64)
+    assert rel[inside].max() <= 4 * np.finfo(float).eps, rel[inside].max()
+    assert rel[~inside].max() <= 1e-12, rel[~inside].max()      # exp(-p log r2): the rounding of p * log r2 ~ 200
+    eng.close()
+
+
 @pytest.mark.parametrize("case", ["eam", "pbc216", "runner"])
 def test_energy_bookkeeping_other_potentials(case):
     # size-independent property for the other potentials: the running en_tot (updated move by move, through exchanges,
