@@ -45,7 +45,8 @@ struct ptmc_handle {
     int device = 0;
     int G = 0;
     int threads = 0;
-    size_t smem = 0;
+    size_t smem = 0;                 // dynamic shared memory per CTA: smem_k[dbg] for the sweep kernels
+    size_t smem_k[2] = {0, 0};
     int geom = 0;
     cudaStream_t stream = nullptr;   // nullptr = legacy default stream
     i64 n_rep = 0, n_steps = 0;
@@ -269,6 +270,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             break;
         case PTMC_POT_EAM:
             if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
+            if (!(c->eam_n > 0 && c->eam_n <= 24 && c->eam_m > 0 && c->eam_m <= 24)) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential exponents n, m must be in (0, 24] (series of eam_invrexp)");
             break;
         case PTMC_POT_RUNNER:
             if (!c->runner) return fail(nullptr, PTMC_ERR_ARG, "pot_kind RUNNER needs ptmc_config.runner");
@@ -318,8 +320,9 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
 
     std::vector<double> net_host;
     if (h->runner) { int rr = build_runner(h, c->runner, net_host); if (rr) return bail(rr); }
-    const SmemLayout lay = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere);
-    h->smem = h->runner ? runner_smem_bytes(c->n_atoms, h->R) : lay.bytes;
+    for (int dbg = 0; dbg < 2; ++dbg)
+        h->smem_k[dbg] = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere, !eam_unrolled(P.n_pad / G, dbg != 0)).bytes;
+    h->smem = h->runner ? runner_smem_bytes(c->n_atoms, h->R) : std::max(h->smem_k[0], h->smem_k[1]);
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
 
     const size_t R = (size_t)h->n_rep, N = (size_t)c->n_atoms, L = (size_t)c->n_ladders;
@@ -350,17 +353,18 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             return bail(fail(h, PTMC_ERR_CUDA, "copying the network failed"));
         Rr.net = d_net;
     }
-    if (c->pot_kind == PTMC_POT_EAM && P.eam_hn > 0 && P.eam_hm > 0 && P.eam_hn <= 12 && P.eam_hm <= 12) {
-        // (r2)^-p table of eam_invrexp (ptmc_device.cuh); p <= 12 keeps the degree-6 series below 1e-16
-        std::vector<double> tab(PTMC_EAM_TAB_DOUBLES, 0.0);
+    if (c->pot_kind == PTMC_POT_EAM) {
+        // (r2)^-p tables of eam_invrexp (ptmc_device.cuh)
+        std::vector<double> tab(PTMC_EAM_KTAB_DOUBLES + PTMC_EAM_ETAB_DOUBLES, 0.0);
         const long double pn = (long double)P.eam_hn, pm = (long double)P.eam_hm;
         for (int k = 0; k < PTMC_EAM_K; ++k) {
             const double rk = 1.0 / (1.0 + (k + 0.5) / PTMC_EAM_K);
-            tab[4 * k] = rk; tab[4 * k + 1] = (double)powl((long double)rk, pn); tab[4 * k + 2] = (double)powl((long double)rk, pm);
+            double* e = tab.data() + (size_t)PTMC_EAM_KSTRIDE * k;
+            e[0] = rk; e[1] = (double)powl((long double)rk, pn); e[2] = (double)powl((long double)rk, pm);
         }
-        for (int e = -PTMC_EAM_E; e < PTMC_EAM_E; ++e) {
-            tab[4 * PTMC_EAM_K + 2 * (e + PTMC_EAM_E)] = (double)powl(2.0L, -pn * e);
-            tab[4 * PTMC_EAM_K + 2 * (e + PTMC_EAM_E) + 1] = (double)powl(2.0L, -pm * e);
+        for (int eb = 0; eb < 2048; ++eb) {
+            tab[PTMC_EAM_KTAB_DOUBLES + 2 * eb] = (double)powl(2.0L, -pn * (eb - 1023));
+            tab[PTMC_EAM_KTAB_DOUBLES + 2 * eb + 1] = (double)powl(2.0L, -pm * (eb - 1023));
         }
         long double cn = 1, cm = 1;
         for (int j = 1; j <= PTMC_EAM_DEG; ++j) {
@@ -370,8 +374,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         double* d_tab = nullptr;
         if ((rc = dev_alloc(h, &d_tab, tab.size()))) return bail(rc);
         if (cudaMemcpy(d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess)
-            return bail(fail(h, PTMC_ERR_CUDA, "copying the EAM power table failed"));
-        P.eam_tab = d_tab;
+            return bail(fail(h, PTMC_ERR_CUDA, "copying the EAM power tables failed"));
+        P.eam_ktab = d_tab; P.eam_etab = d_tab + PTMC_EAM_KTAB_DOUBLES;
     }
     P.betas = d_betas; P.en_min = en_min; P.en_max = en_max; P.v_min = v_min; P.v_max = v_max;
     P.error = h->d_error;
@@ -385,8 +389,10 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     for (int dbg = 0; dbg < 2 && !h->runner; ++dbg) {
         sweep_fn f = pick_kernel(h, dbg);
         if (!f) return bail(fail(h, PTMC_ERR_ARG, "no kernel for potential %d / boundary %d", c->pot_kind, c->bc_kind));
-        if (cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess)
+        if (cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_k[dbg]) != cudaSuccess)
             return bail(fail(h, PTMC_ERR_CUDA, "cudaFuncSetAttribute(%zu B smem) failed: %s", h->smem, cudaGetErrorString(cudaGetLastError())));
+        // residency is bounded by shared memory: ask for the largest carve-out instead of the driver's per-kernel guess
+        cudaFuncSetAttribute((const void*)f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     *out = h;
     if (c->rng_mode != PTMC_RNG_REPLAY) { int r2 = ptmc_seed(h, c->seed); if (r2) { *out = nullptr; return bail(r2); } }
@@ -559,7 +565,7 @@ extern "C" PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64
         P.trace_cap = h->trace_cap; P.trace_base = h->trace_n;
         P.tr_index = static_cast<int32_t*>(h->d_trace[0]); P.tr_de = static_cast<double*>(h->d_trace[1]);
         P.tr_acc = static_cast<uint8_t*>(h->d_trace[2]); P.tr_exc = static_cast<int32_t*>(h->d_trace[3]);
-        f<<<(unsigned)h->cfg.n_ladders, h->threads, h->smem, h->stream>>>(P, first_idx + done, k, sample);
+        f<<<(unsigned)h->cfg.n_ladders, h->threads, h->smem_k[dbg ? 1 : 0], h->stream>>>(P, first_idx + done, k, sample);
         CU(h, cudaGetLastError());
         h->launches += 1;
         if (tracing) h->trace_n += k;

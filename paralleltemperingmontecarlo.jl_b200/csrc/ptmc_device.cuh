@@ -19,8 +19,14 @@ typedef long long i64;
 
 #define PTMC_EAM_DEG 6          // degree of the binomial series of (1 + t)^-p, |t| <= 2^-9
 #define PTMC_EAM_K 256          // mantissa intervals
-#define PTMC_EAM_E 64           // binary exponents -64..63 of r2 are tabulated
-#define PTMC_EAM_TAB_DOUBLES (PTMC_EAM_K * 4 + 2 * PTMC_EAM_E * 2)
+#ifndef PTMC_EAM_KSTRIDE
+#define PTMC_EAM_KSTRIDE 6       // doubles per mantissa entry {1/m_k, (1/m_k)^(n/2), (1/m_k)^(m/2), pad}: 48 B spreads LDS.128 over all banks
+#endif
+#ifndef PTMC_EAM_ESTRIN
+#define PTMC_EAM_ESTRIN 1
+#endif
+#define PTMC_EAM_KTAB_DOUBLES (PTMC_EAM_K * PTMC_EAM_KSTRIDE)
+#define PTMC_EAM_ETAB_DOUBLES (2048 * 2)  // every biased binary exponent of r2
 
 // Everything the kernels need, passed by value as the kernel parameter (constant bank).
 struct DevParams {
@@ -34,10 +40,10 @@ struct DevParams {
     double coeff[PTMC_MAX_COEFF];
     double eam_hn, eam_hm;               // n/2, m/2  (r^-n = (r2)^-(n/2))
     double eam_ean, eam_ecam;
-    // table-driven (r2)^-p, p = n/2 and m/2 (eam_invrexp): binomial coefficients binom(-p, 1..6) and the table
-    // [256][4] = {1/m_k, (1/m_k)^(n/2), (1/m_k)^(m/2), 0} followed by [128][2] = {2^(-n/2 e), 2^(-m/2 e)}, e = -64..63
+    // table-driven (r2)^-p, p = n/2 and m/2 (eam_invrexp): binomial coefficients binom(-p, 1..6) and the tables
     double eam_cn[PTMC_EAM_DEG], eam_cm[PTMC_EAM_DEG];
-    const double* eam_tab;               // nullptr: exponents too large for the series, use log/exp
+    const double* eam_ktab;              // [256][PTMC_EAM_KSTRIDE]
+    const double* eam_etab;              // [2048][2]
     // config-side state at rest, slot ordered: [L][T]...
     double* pos;        // [L][T][N][3]
     double* box;        // [L][T][2]
@@ -256,31 +262,47 @@ __device__ __forceinline__ double pair_energy(const DevParams& P, double r2) {
     return POT == PTMC_POT_ELJ ? elj_odd(P, r2) : elj_even<NC>(P, r2);
 }
 // invrexp src/EnergyEvaluation.jl:1088-1095: (r^-n, r^-m) = ((r2)^-(n/2), (r2)^-(m/2)); r2 > 0.
-// Reference form of this library: exp(-(n/2) log r2), ~16 ulp, ~80 FP64 instructions.
-__device__ __forceinline__ void eam_invrexp_slow(const DevParams& P, double r2, double& phi, double& rho) {
-    double l = log(r2);
-    phi = exp(-P.eam_hn * l);
-    rho = exp(-P.eam_hm * l);
-}
-// Table-driven form: r2 = 2^e m, m in [1, 2); k = top 8 mantissa bits, t = m / m_k - 1 (one FMA with the tabulated
-// reciprocal, |t| <= 2^-9); (r2)^-p = 2^(-p e) (1/m_k)^p (1 + t)^-p with the binomial series to degree 6
-// (truncation < 2e-17): 17 FP64 instructions for both powers, <= 2 ulp.  `tab` may live in shared or global memory.
-__device__ __forceinline__ void eam_invrexp(const DevParams& P, const double* tab, double r2, double& phi, double& rho) {
+// Table-driven and branch-free: r2 = 2^e m, m in [1, 2); k = top 8 mantissa bits, t = m / m_k - 1 (one FMA with the
+// tabulated reciprocal, |t| <= 2^-9); (r2)^-p = 2^(-p e) (1/m_k)^p (1 + t)^-p with the binomial series to degree 6
+// (truncation < 2e-17 for p <= 12): 17 FP64 instructions for both powers, <= 2 ulp (exp(-p log r2): ~80 instructions,
+// ~16 ulp).  ktab: [256][PTMC_EAM_KSTRIDE] = {1/m_k, (1/m_k)^(n/2), (1/m_k)^(m/2), pad} (shared memory in the sweep kernel);
+// etab: [2048][2] = {2^(-n/2 e), 2^(-m/2 e)}, e = -1023..1024 (global memory: a handful of entries is ever touched).
+// r2 = 0 / denormal / inf / NaN are not special-cased (the reference returns (0, 0) for r2 == 0, which needs two atoms
+// on the same point).
+__device__ __forceinline__ void eam_invrexp(const DevParams& P, const double* ktab, const double* etab, double r2, double& phi, double& rho) {
     const int hi = __double2hiint(r2), lo = __double2loint(r2);
-    const int e = (hi >> 20) - 1023;
-    if (tab == nullptr || (unsigned)(e + PTMC_EAM_E) >= 2u * PTMC_EAM_E) { eam_invrexp_slow(P, r2, phi, rho); return; }
+    const int eb = (hi >> 20) & 0x7ff;                                         // biased exponent = e + 1023
     const int k = (hi >> 12) & (PTMC_EAM_K - 1);
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double2 a = *reinterpret_cast<const double2*>(tab + 4 * k);        // 1/m_k, (1/m_k)^(n/2)
-    const double tm = tab[4 * k + 2];                                         // (1/m_k)^(m/2)
-    const double2 ee = *reinterpret_cast<const double2*>(tab + 4 * PTMC_EAM_K + 2 * (e + PTMC_EAM_E));
+    const double2 a = *reinterpret_cast<const double2*>(ktab + PTMC_EAM_KSTRIDE * k);   // 1/m_k, (1/m_k)^(n/2)
+    const double tm = ktab[PTMC_EAM_KSTRIDE * k + 2];                                    // (1/m_k)^(m/2)
+    const double2 ee = __ldg(reinterpret_cast<const double2*>(etab) + eb);
     const double t = fma(m, a.x, -1.0);
+#if PTMC_EAM_ESTRIN
+    // Estrin: 1 + c1 t + t2 ((c2 + c3 t) + t2 ((c4 + c5 t) + t2 c6)): depth 4 instead of 7 (the kernel is latency bound)
+    const double t2 = t * t;
+    double pn = fma(P.eam_cn[5], t2, fma(P.eam_cn[4], t, P.eam_cn[3])), pm = fma(P.eam_cm[5], t2, fma(P.eam_cm[4], t, P.eam_cm[3]));
+    pn = fma(pn, t2, fma(P.eam_cn[2], t, P.eam_cn[1])); pm = fma(pm, t2, fma(P.eam_cm[2], t, P.eam_cm[1]));
+    pn = fma(pn, t2, fma(P.eam_cn[0], t, 1.0)); pm = fma(pm, t2, fma(P.eam_cm[0], t, 1.0));
+#else
     double pn = P.eam_cn[5], pm = P.eam_cm[5];
 #pragma unroll
     for (int j = 4; j >= 0; --j) { pn = fma(pn, t, P.eam_cn[j]); pm = fma(pm, t, P.eam_cm[j]); }
     pn = fma(pn, t, 1.0); pm = fma(pm, t, 1.0);
+#endif
     phi = pn * (a.y * ee.x);
     rho = pm * (tm * ee.y);
+}
+// sqrt(x) for normal positive x, branch-free: MUFU.RSQ64H seed, coupled Newton iteration on (sqrt, 1/(2 sqrt)); <= 1 ulp
+__device__ __forceinline__ double sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    return fma(fma(-g, g, x), h, g);
 }
 
 // lrc(::ELJPotentialEven) src/EnergyEvaluation.jl:968-982 (r_cut is the squared cut-off)

@@ -22,7 +22,7 @@ static sweep_fn generic_kernel(int pot, int geom, int dbg) {
     PTMC_PICK(PTMC_POT_ELJ, GEOM_SPHERE)
     PTMC_PICK(PTMC_POT_ELJ, GEOM_PBC)
     PTMC_PICK(PTMC_POT_ELJ, GEOM_RHOMB)
-    PTMC_PICK(PTMC_POT_EAM, GEOM_SPHERE)
+    if (pot == PTMC_POT_EAM && geom == GEOM_SPHERE) return dbg ? (sweep_fn)sweep_kernel_eam<G, true, 0> : (sweep_fn)sweep_kernel_eam<G, false, 0>;
 #undef PTMC_PICK
     return nullptr;
 }
@@ -49,6 +49,15 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, 
     if (!dbg && pot == PTMC_POT_ELJ_EVEN && geom == GEOM_SPHERE && n_coeff == 6) {
         sweep_fn f = special_kernel(niter);
         if (f) return f;
+    }
+    // EmbeddedAtomPotential: pair loop unrolled, trial components in registers
+    if (pot == PTMC_POT_EAM && geom == GEOM_SPHERE && eam_unrolled(niter, dbg != 0)) {
+        switch (niter) {
+#define PTMC_SPE(K) case K: return (sweep_fn)sweep_kernel_eam<G, false, K>;
+            PTMC_SPE(1) PTMC_SPE(2) PTMC_SPE(3) PTMC_SPE(4) PTMC_SPE(5) PTMC_SPE(6) PTMC_SPE(7) PTMC_SPE(8)
+#undef PTMC_SPE
+            default: break;
+        }
     }
     // periodic ELJEven with the six-coefficient form: Horner chain unrolled, coefficients in uniform registers; for the wide
     // lane groups that periodic systems use, the thawed pair loop is unrolled as well

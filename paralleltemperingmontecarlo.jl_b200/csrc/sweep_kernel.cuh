@@ -30,12 +30,18 @@ struct SmemLayout {
     int off_ham;        // ham [T][2] (slot side)
     int off_lrng;       // ladder stream, one private copy per warp: 4 x u64 state + cursor + pad
     int off_moved;      // periodic: int moved[T][words + 1]
-    int off_tab;        // EAM: the (r2)^-p table (PTMC_EAM_TAB_DOUBLES, 16-byte aligned)
+    int off_tab;        // EAM: the mantissa table of eam_invrexp (PTMC_EAM_KTAB_DOUBLES, 16-byte aligned)
     size_t bytes;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc) {
+// EAM kernels with an unrolled pair loop keep the trial components in registers (eam_scratch = false).
+#define PTMC_EAM_MAX_NITER 8
+#ifndef PTMC_EAM_UNROLL
+#define PTMC_EAM_UNROLL 1
+#endif
+__host__ __device__ constexpr bool eam_unrolled(int niter, bool dbg) { return PTMC_EAM_UNROLL && !dbg && niter >= 1 && niter <= PTMC_EAM_MAX_NITER; }
+__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch) {
     SmemLayout s;
-    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? 4 : 0) + (pbc ? 1 : 0);   // x,y,z (+ phi,rho,new_phi,new_rho | + new_dist2_vec)
+    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + (pbc ? 1 : 0);   // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec)
     s.cfg_stride = arrays * n_pad;
     s.off_scal = n_traj * s.cfg_stride;
     int off = s.off_scal + 4 * n_traj;
@@ -45,7 +51,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     s.off_perm = off; off += (n_traj + 1) / 2 + 1;
     s.off_moved = off; off += pbc ? (n_traj * ((n_pad + 31) / 32 + 1) + 1) / 2 + 1 : 0;
     off += off & 1;
-    s.off_tab = off; off += pot_kind == PTMC_POT_EAM ? PTMC_EAM_TAB_DOUBLES : 0;
+    s.off_tab = off; off += pot_kind == PTMC_POT_EAM ? PTMC_EAM_KTAB_DOUBLES : 0;
     s.bytes = (size_t)off * sizeof(double);
     return s;
 }
@@ -54,8 +60,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
 // NITER : compile-time ceil(n_atoms / G) of the pair loop (n_pad = NITER * G), 0 = runtime trip count.
 // NC    : compile-time number of ELJ coefficients (6), 0 = runtime.
 template <int G, int POT, int GEOM, bool DBG, int NITER, int NC>
-__global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
-sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
+__device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_idx, const i64 n_cycles, const int sample) {
     extern __shared__ double sm[];
     constexpr bool EAM = (POT == PTMC_POT_EAM);
     constexpr bool PBC = (GEOM != GEOM_SPHERE);
@@ -69,7 +74,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     const int slot = tid / G, g = tid & (G - 1);
     const bool active = slot < T;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
-    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC);
+    constexpr bool EAM_REG = EAM && NITER > 0 && PTMC_EAM_UNROLL;     // trial (phi, rho) components in registers instead of shared memory
+    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG);
     double* scal = sm + lay.off_scal;
     i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
     double* hams = sm + lay.off_ham;
@@ -79,14 +85,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     const int MW = P.moved_words + 1;            // ints per configuration in moved[]
     const bool npt = PBC && P.ensemble == PTMC_ENS_NPT;
     const i64 rep = (i64)lad * T + slot;      // replica (slot) index in the global arrays
-    const double* eam_tab = nullptr;
-    if (EAM) {
-        if (P.eam_tab) {
-            double* tb = sm + lay.off_tab;
-            for (int k = tid; k < PTMC_EAM_TAB_DOUBLES; k += blockDim.x) tb[k] = P.eam_tab[k];
-            eam_tab = tb;
-        }
-    }
+    const double* eam_tab = sm + lay.off_tab;
+    if (EAM) for (int k = tid; k < PTMC_EAM_KTAB_DOUBLES; k += blockDim.x) sm[lay.off_tab + k] = P.eam_ktab[k];
 
     // ---- load: slot s starts with configuration buffer s ----------------------------------------------
     if (active) {
@@ -101,7 +101,7 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
             if (EAM) {
                 Z[NP + j] = v ? P.comp[(rep * N + j) * 2] : 1.0;          // phi
                 Z[2 * NP + j] = v ? P.comp[(rep * N + j) * 2 + 1] : 1.0;  // rho
-                Z[3 * NP + j] = 1.0; Z[4 * NP + j] = 1.0;
+                if (!EAM_REG) { Z[3 * NP + j] = 1.0; Z[4 * NP + j] = 1.0; }
             }
         }
         if (g == 0) {
@@ -242,6 +242,8 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                     }
                     // -------------------------------- energy_update! src/EnergyEvaluation.jl:1474-1506,1567-1591
                     double new_en;
+                    constexpr int EAM_NK = EAM_REG ? NITER : 1;
+                    double nph[EAM_NK], nrh[EAM_NK], nphi_i = 0.0, nrho_i = 0.0;   // EAM: trial components of this lane's atoms / of atom i
                     if (PARK) {
                         // park the moved atom: its own pair term (d2_old = 0) must not enter the row sums
                         __syncwarp(gmask);
@@ -339,9 +341,9 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                         new_en = xadd(delta_en, en);
                     } else {
                         // calc_components :1111-1127 + calc_energies_from_components :1156-1162
-                        double* PHI = Z + NP; double* RHO = PHI + NP; double* NPHI = RHO + NP; double* NRHO = NPHI + NP;
+                        double* PHI = Z + NP; double* RHO = PHI + NP;
                         double sphi = 0.0, srho = 0.0, se = 0.0;
-                        for (int j = g; j < NP; j += G) {
+                        auto eam_term = [&](int j, double& nphi, double& nrho) {
                             const double xj = X[j], yj = Y[j], zj = Z[j];
                             double ax = tx - xj, ay = ty - yj, az = tz - zj;
                             double d2n = fma(az, az, fma(ay, ay, ax * ax));
@@ -350,19 +352,27 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                             const bool valid = (j != i) && (j < N);
                             d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
                             double pn, rn, po, ro;
-                            eam_invrexp(P, eam_tab, d2n, pn, rn);
-                            eam_invrexp(P, eam_tab, d2o, po, ro);
+                            eam_invrexp(P, eam_tab, P.eam_etab, d2n, pn, rn);
+                            eam_invrexp(P, eam_tab, P.eam_etab, d2o, po, ro);
                             double tp = pn - po, tr = rn - ro;          // exactly 0 when !valid
-                            double nphi = PHI[j] + tp, nrho = RHO[j] + tr;
-                            NPHI[j] = nphi; NRHO[j] = nrho;
+                            nphi = PHI[j] + tp; nrho = RHO[j] + tr;
                             sphi += tp; srho += tr;
-                            se += valid ? fma(-P.eam_ecam, sqrt(nrho), P.eam_ean * nphi) : 0.0;
+                            se += valid ? fma(-P.eam_ecam, sqrt_pos(nrho), P.eam_ean * nphi) : 0.0;
+                        };
+                        if (EAM_REG) {
+#pragma unroll
+                            for (int k = 0; k < EAM_NK; ++k) eam_term(g + k * G, nph[k], nrh[k]);
+                        } else {
+                            double* NPHI = RHO + NP; double* NRHO = NPHI + NP;
+                            for (int j = g; j < NP; j += G) {
+                                double nphi, nrho;
+                                eam_term(j, nphi, nrho);
+                                NPHI[j] = nphi; NRHO[j] = nrho;
+                            }
                         }
                         sphi = group_sum<G>(sphi, gmask); srho = group_sum<G>(srho, gmask); se = group_sum<G>(se, gmask);
-                        const double nphi_i = PHI[i] + sphi, nrho_i = RHO[i] + srho;
-                        __syncwarp(gmask);
-                        if (g == 0) { NPHI[i] = nphi_i; NRHO[i] = nrho_i; }
-                        new_en = se + fma(-P.eam_ecam, sqrt(nrho_i), P.eam_ean * nphi_i);
+                        nphi_i = PHI[i] + sphi; nrho_i = RHO[i] + srho;
+                        new_en = se + fma(-P.eam_ecam, sqrt_pos(nrho_i), P.eam_ean * nphi_i);
                     }
                     // ------------------------------------------------------------ acc_test! src/MCRun.jl:122-132
                     de = xsub(new_en, en);
@@ -394,9 +404,18 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
                             }
                         }
                         if (EAM) {
-                            double* PHI = Z + NP; double* RHO = PHI + NP; double* NPHI = RHO + NP; double* NRHO = NPHI + NP;
+                            double* PHI = Z + NP; double* RHO = PHI + NP;
                             __syncwarp(gmask);
-                            for (int j = g; j < N; j += G) { PHI[j] = NPHI[j]; RHO[j] = NRHO[j]; }
+                            if (EAM_REG) {
+#pragma unroll
+                                for (int k = 0; k < EAM_NK; ++k) {
+                                    const int j = g + k * G;
+                                    PHI[j] = (j == i) ? nphi_i : nph[k]; RHO[j] = (j == i) ? nrho_i : nrh[k];
+                                }
+                            } else {
+                                const double* NPHI = RHO + NP; const double* NRHO = NPHI + NP;
+                                for (int j = g; j < N; j += G) { PHI[j] = (j == i) ? nphi_i : NPHI[j]; RHO[j] = (j == i) ? nrho_i : NRHO[j]; }
+                            }
                         }
                     }
                     __syncwarp(gmask);
@@ -611,6 +630,22 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
     if (err) atomicMin(P.error, err);
 }
 
+template <int G, int POT, int GEOM, bool DBG, int NITER, int NC>
+__global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
+sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
+    sweep_body<G, POT, GEOM, DBG, NITER, NC>(P, first_idx, n_cycles, sample);
+}
+// EmbeddedAtomPotential: the unrolled loop wants ~170 registers; capped so that two 224-thread ladders (scripts/cu55.jl:
+// 28 temperatures x 8 lanes) stay resident per SM (a 96-register cap for three ladders spills and measured slower)
+#ifndef PTMC_EAM_MAXREG
+#define PTMC_EAM_MAXREG 128
+#endif
+template <int G, bool DBG, int NITER>
+__global__ void __maxnreg__(PTMC_EAM_MAXREG)
+sweep_kernel_eam(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
+    sweep_body<G, PTMC_POT_EAM, GEOM_SPHERE, DBG, NITER, 0>(P, first_idx, n_cycles, sample);
+}
+
 // ------------------------------------------------------------------------------------------- init --
 // MCState constructor (src/MCStates.jl:137-162): initial en_tot (dimer_energy_config
 // src/EnergyEvaluation.jl:378-474, or EAM set_variables :1800-1811 + :1722-1734) for every replica.
@@ -634,7 +669,7 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                 if (j == a) continue;
                 double dx = gp[3 * a] - gp[3 * j], dy = gp[3 * a + 1] - gp[3 * j + 1], dz = gp[3 * a + 2] - gp[3 * j + 2];
                 double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                double p, r; eam_invrexp(P, P.eam_tab, d2, p, r);
+                double p, r; eam_invrexp(P, P.eam_ktab, P.eam_etab, d2, p, r);
                 sp += p; sr += r;
             }
             P.comp[(rep * N + a) * 2] = sp; P.comp[(rep * N + a) * 2 + 1] = sr;
