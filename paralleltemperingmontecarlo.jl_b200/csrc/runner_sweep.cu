@@ -36,7 +36,37 @@ __device__ __forceinline__ double rn_theta_n(double c, double lambda, double zet
     for (int m = 0; m < 5; ++m) if (m < nsq) b *= b;
     return b;
 }
-__device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? tanh(z) : z; }
+// exp(x) for x in [-700, 0], branch-free: x = k ln2 + r, |r| <= ln2 / 2, Taylor series to degree 13 (remainder 4e-18),
+// exponent patched into the high word
+__device__ __forceinline__ double rn_exp_neg(double x) {
+    x = fmax(x, -700.0);
+    const double kf = rint(x * 1.4426950408889634);
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 1.60590438368216145994e-10;                  // 1/13!
+    p = fma(p, r, 2.08767569878680989792e-09);
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)kf << 20), __double2loint(p));
+}
+// tanh(z) = sign(z) (1 - t) / (1 + t), t = exp(-2 |z|): branch-free, absolute error ~1e-16 (the library routine
+// diverges between its two argument ranges inside a warp: 9 % of the kernel's instructions before)
+__device__ __forceinline__ double rn_tanh(double z) {
+    const double t = rn_exp_neg(-2.0 * fabs(z));
+    const double r = (1.0 - t) * rcp_pos(1.0 + t);
+    return copysign(r, z);
+}
+__device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? rn_tanh(z) : z; }
 
 struct RnSmem {          // offsets in doubles into the dynamic shared memory of the move kernel
     int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, pair, ptab, total;
@@ -60,55 +90,58 @@ __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
 
 // Network forward pass for all atoms on the compact g matrix in shared memory (SURVEY A.2 semantics).
 // Returns, in every thread, the sum of the per-atom energies (calc_new_runner_energy! :1269-1275).
+// Thread (a, q) = (tid / RN_SUB, tid % RN_SUB) computes a contiguous block of output nodes of atom a in every layer; the
+// RN_SUB lanes of an atom sit in one warp, so the layers are separated by __syncwarp() only and the last layer is a shuffle
+// reduction over the lanes' own hidden values.
+constexpr int RN_MAX_OPT = (RN_MAX_HID + RN_SUB - 1) / RN_SUB;      // output nodes per thread and layer
 __device__ double rn_forward(const RunnerDev& R, int N, const double* g, const double* net, double* h1, double* h2, double* eatom,
                              double* red) {
     const int tid = threadIdx.x;
     const double* W1 = net; const double* b1 = W1 + R.h1 * R.n_act;
     const double* W2 = b1 + R.h1; const double* b2 = W2 + R.h2 * R.h1;
     const double* W3 = b2 + R.h2; const double* b3 = W3 + R.h2;
-    // each thread: one atom x four output nodes (one load of the input per four FMAs)
-    const int ng1 = (R.h1 + 3) / 4, ng2 = (R.h2 + 3) / 4;
-    for (int t = tid; t < N * ng1; t += RN_THREADS) {
-        const int a = t / ng1, o0 = (t - a * ng1) * 4;
-        double z[4];
+    const int a = tid / RN_SUB, q = tid % RN_SUB;
+    const bool on = a < N;
+    const int aa = on ? a : 0;
+    const int n1 = (R.h1 + RN_SUB - 1) / RN_SUB, n2 = (R.h2 + RN_SUB - 1) / RN_SUB;
+    const int o1 = q * n1, o2 = q * n2;
+    double z[RN_MAX_OPT];
+    {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) z[m] = o0 + m < R.h1 ? b1[o0 + m] : 0.0;
-        const double* x = g + a * R.n_act;
+        for (int m = 0; m < RN_MAX_OPT; ++m) z[m] = (m < n1 && o1 + m < R.h1) ? b1[o1 + m] : 0.0;
+        const double* x = g + aa * R.n_act;
         for (int r = 0; r < R.n_act; ++r) {
             const double xr = x[r];
-            const double* w = W1 + o0 + r * R.h1;
+            const double* w = W1 + o1 + r * R.h1;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) if (o0 + m < R.h1) z[m] = fma(w[m], xr, z[m]);
+            for (int m = 0; m < RN_MAX_OPT; ++m) if (m < n1 && o1 + m < R.h1) z[m] = fma(w[m], xr, z[m]);
         }
 #pragma unroll
-        for (int m = 0; m < 4; ++m) if (o0 + m < R.h1) h1[a * R.h1 + o0 + m] = rn_act(z[m], R.act1);
+        for (int m = 0; m < RN_MAX_OPT; ++m) if (on && m < n1 && o1 + m < R.h1) h1[aa * R.h1 + o1 + m] = rn_act(z[m], R.act1);
     }
-    __syncthreads();
-    for (int t = tid; t < N * ng2; t += RN_THREADS) {
-        const int a = t / ng2, o0 = (t - a * ng2) * 4;
-        double z[4];
+    __syncwarp();
+    {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) z[m] = o0 + m < R.h2 ? b2[o0 + m] : 0.0;
-        const double* x = h1 + a * R.h1;
+        for (int m = 0; m < RN_MAX_OPT; ++m) z[m] = (m < n2 && o2 + m < R.h2) ? b2[o2 + m] : 0.0;
+        const double* x = h1 + aa * R.h1;
         for (int r = 0; r < R.h1; ++r) {
             const double xr = x[r];
-            const double* w = W2 + o0 + r * R.h2;
+            const double* w = W2 + o2 + r * R.h2;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) if (o0 + m < R.h2) z[m] = fma(w[m], xr, z[m]);
+            for (int m = 0; m < RN_MAX_OPT; ++m) if (m < n2 && o2 + m < R.h2) z[m] = fma(w[m], xr, z[m]);
         }
+    }
+    double part = 0.0;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) if (o0 + m < R.h2) h2[a * R.h2 + o0 + m] = rn_act(z[m], R.act2);
-    }
-    __syncthreads();
+    for (int m = 0; m < RN_MAX_OPT; ++m) if (m < n2 && o2 + m < R.h2) part = fma(W3[o2 + m], rn_act(z[m], R.act2), part);
+#pragma unroll
+    for (int m = 1; m < RN_SUB; m <<= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
     double e = 0.0;
-    for (int a = tid; a < N; a += RN_THREADS) {
-        double z = b3[0];
-        const double* x = h2 + a * R.h2;
-        for (int r = 0; r < R.h2; ++r) z = fma(W3[r], x[r], z);
-        z = rn_act(z, R.act3);
-        eatom[a] = z;
-        e += z;
+    if (on && q == 0) {
+        e = rn_act(part + b3[0], R.act3);
+        eatom[a] = e;
     }
+    (void)h2;
     e = group_sum<32>(e, 0xffffffffu);
     if ((tid & 31) == 0) red[tid >> 5] = e;
     __syncthreads();
@@ -303,8 +336,10 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
         double prad[RN_MAX_RAD];
 #pragma unroll
         for (int r = 0; r < RN_MAX_RAD; ++r) prad[r] = 0.0;
-        if (tid < N) {
-            const int j = tid;
+        // thread (j, s) = (tid / RN_SUB, tid % RN_SUB): the RN_SUB lanes of atom j share its exponentials (angular eta e
+        // on lane e % RN_SUB, radial function r on lane (RN_SUB - 1 - r) % RN_SUB); the scalars are computed by every lane
+        if (tid < N * RN_SUB) {
+            const int j = tid / RN_SUB, ls = tid % RN_SUB;
             const double x = xsub(tx, pos[3 * j]), y = xsub(ty, pos[3 * j + 1]), z = xsub(tz, pos[3 * j + 2]);
             double d2n = xadd(xadd(xmul(x, x), xmul(y, y)), xmul(z, z));
             const bool self = j == i;
@@ -314,9 +349,11 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
             const double fn = self ? 1.0 : rn_cutoff(rr, R.r_cut);            // cutoff_function.(sqrt.(new_dist2_vec))
             const int tij = self ? 0 : rn_tri(i, j, N);
             const double d2o = self ? 0.0 : D2[tij], fo = self ? 1.0 : F[tij];
-            rn_d2[j] = d2n; rn_inv[j] = self ? 0.0 : 1.0 / rr; rn_f[j] = fn;
-            ro_d2[j] = d2o; ro_inv[j] = self ? 0.0 : INV[tij]; ro_f[j] = fo;
-            for (int e = 0; e < R.n_eta; ++e) {
+            if (ls == 0) {
+                rn_d2[j] = d2n; rn_inv[j] = self ? 0.0 : 1.0 / rr; rn_f[j] = fn;
+                ro_d2[j] = d2o; ro_inv[j] = self ? 0.0 : INV[tij]; ro_f[j] = fo;
+            }
+            for (int e = ls; e < R.n_eta; e += RN_SUB) {
                 rn_ef[e * N + j] = self ? 0.0 : exp(-R.eta[e] * d2n) * fn;
                 ro_ef[e * N + j] = self ? 0.0 : EF[e * NT + tij];
             }
@@ -324,7 +361,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                 // radial_symmetry_calculation! DeltaMatrix.jl:794-822 / adjust_radial_symm_val! :648-657
 #pragma unroll
                 for (int r = 0; r < RN_MAX_RAD; ++r) {
-                    if (r < R.n_act_rad) {
+                    if (r < R.n_act_rad && (RN_SUB - 1 - r % RN_SUB) == ls) {
                         const double tn = exp(-R.rad_eta[r] * d2n) * (fn * R.rad_norm[r]);
                         const double to = exp(-R.rad_eta[r] * d2o) * (-fo * R.rad_norm[r]);
                         ng[j * R.n_act + r] = (g[j * R.n_act + r] + tn) + to;
