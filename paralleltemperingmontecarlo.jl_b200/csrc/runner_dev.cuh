@@ -58,6 +58,13 @@ constexpr unsigned long long RN_PRESENT_V =
 // squarings per (lambda, zeta) slot, 4 bits each, slot 0 in the low nibble: zeta = 1, 2, 1, 2, 4, 16, 16, 4
 constexpr unsigned RN_NSQ_V = 0u | (1u << 4) | (0u << 8) | (1u << 12) | (2u << 16) | (4u << 20) | (4u << 24) | (2u << 28);
 
+// Evaluation order of the (lambda, zeta) slots of that set: two chains (lambda = +1: slots 0, 3, 7, 6 with zeta 1, 2, 4, 16;
+// lambda = -1: slots 2, 1, 4, 5), each slot obtained from its predecessor by squaring - (1 + lambda cos)^zeta costs 2 FMA +
+// 8 MUL for all eight slots instead of 8 + 14.  Position q: slot (4 bits), root flag, squarings from the predecessor (4 bits).
+constexpr unsigned RN_ZSEQ_V = 0u | (3u << 4) | (7u << 8) | (6u << 12) | (2u << 16) | (1u << 20) | (4u << 24) | (5u << 28);
+constexpr unsigned RN_ZROOT_V = (1u << 0) | (1u << 4);
+constexpr unsigned RN_ZSQ_V = 0u | (1u << 4) | (1u << 8) | (2u << 12) | (0u << 16) | (1u << 20) | (1u << 24) | (2u << 28);
+
 // index of the unordered pair (a, b), a != b, in the upper-triangle tables
 __host__ __device__ __forceinline__ int rn_tri(int a, int b, int N) {
     const int lo = a < b ? a : b, hi = a < b ? b : a;

@@ -68,6 +68,37 @@ __device__ __forceinline__ double rn_tanh(double z) {
 }
 __device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? rn_tanh(z) : z; }
 
+// acc[e][z] += ep_new[e] (1 + lambda_z cos_new)^zeta_z - ep_old[e] (1 + lambda_z cos_old)^zeta_z for every evaluated (e, z).
+// SPEC (the reference's standard set): the slots are walked along the two squaring chains of RN_ZSEQ_V.
+template <bool SPEC, unsigned long long PRESENT, unsigned NSQ>
+__device__ __forceinline__ void rn_angular_acc(const RunnerDev& R, unsigned long long present, double cn, double co,
+                                               const double (&epn)[RN_MAX_ETA], const double (&epo)[RN_MAX_ETA], double (&acc)[RN_MAX_ETA][RN_MAX_LZ]) {
+    if (SPEC) {
+        double bn = 0.0, bo = 0.0;
+#pragma unroll
+        for (int q = 0; q < RN_MAX_LZ; ++q) {
+            const int z = (int)((RN_ZSEQ_V >> (4 * q)) & 15u), sq = (int)((RN_ZSQ_V >> (4 * q)) & 15u);
+            if ((RN_ZROOT_V >> q) & 1u) { bn = fma(R.lz_lambda[z], cn, 1.0); bo = fma(R.lz_lambda[z], co, 1.0); }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) if (m < sq) { bn *= bn; bo *= bo; }
+#pragma unroll
+            for (int e = 0; e < RN_MAX_ETA; ++e)
+                if (PRESENT >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * bn - epo[e] * bo;
+        }
+    } else {
+#pragma unroll
+        for (int z = 0; z < RN_MAX_LZ; ++z) {
+            if (z < R.n_lz) {
+                const double tn = rn_theta_n(cn, R.lz_lambda[z], R.lz_zeta[z], R.lz_nsq[z]);
+                const double to = rn_theta_n(co, R.lz_lambda[z], R.lz_zeta[z], R.lz_nsq[z]);
+#pragma unroll
+                for (int e = 0; e < RN_MAX_ETA; ++e)
+                    if (present >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * tn - epo[e] * to;
+            }
+        }
+    }
+}
+
 struct RnSmem {          // offsets in doubles into the dynamic shared memory of the move kernel
     int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, pair, ptab, total;
 };
@@ -417,16 +448,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                             epo[e] = ro_ef[e * N + j] * ro_ef[e * N + k] * ejk;      // exponential_part, old geometry
                         }
                     }
-#pragma unroll
-                    for (int z = 0; z < RN_MAX_LZ; ++z) {
-                        if (SPEC || z < R.n_lz) {
-                            const double tn = rn_theta_n(cn, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
-                            const double to = rn_theta_n(co, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
-#pragma unroll
-                            for (int e = 0; e < RN_MAX_ETA; ++e)
-                                if (present >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * tn - epo[e] * to;
-                        }
-                    }
+                    rn_angular_acc<SPEC, PRESENT, NSQ>(R, present, cn, co, epn, epo, acc);
                 }
             }
 #pragma unroll
@@ -458,16 +480,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                         epo[e] = ro_ef[e * N + pj] * ro_ef[e * N + pk] * ejk;
                     }
                 }
-#pragma unroll
-                for (int z = 0; z < RN_MAX_LZ; ++z) {
-                    if (SPEC || z < R.n_lz) {
-                        const double tn = rn_theta_n(cn, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
-                        const double to = rn_theta_n(co, R.lz_lambda[z], R.lz_zeta[z], SPEC ? (int)((NSQ >> (4 * z)) & 15u) : R.lz_nsq[z]);
-#pragma unroll
-                        for (int e = 0; e < RN_MAX_ETA; ++e)
-                            if (present >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * tn - epo[e] * to;
-                    }
-                }
+                rn_angular_acc<SPEC, PRESENT, NSQ>(R, present, cn, co, epn, epo, acc);
             }
 #pragma unroll
             for (int e = 0; e < RN_MAX_ETA; ++e)
@@ -627,6 +640,13 @@ typedef void (*rn_moves_fn)(const DevParams, const RunnerDev, const i64);
 static bool is_standard_set(const RunnerDev& R) {
     if (R.present != RN_PRESENT_V || R.n_eta != 7 || R.n_lz != 8) return false;
     for (int z = 0; z < 8; ++z) if (R.lz_nsq[z] != (int)((RN_NSQ_V >> (4 * z)) & 15u)) return false;
+    // the squaring chains of RN_ZSEQ_V: every slot has the lambda of its chain's root
+    int root = 0;
+    for (int q = 0; q < 8; ++q) {
+        const int z = (int)((RN_ZSEQ_V >> (4 * q)) & 15u);
+        if ((RN_ZROOT_V >> q) & 1u) root = z;
+        else if (R.lz_lambda[z] != R.lz_lambda[root]) return false;
+    }
     return true;
 }
 static rn_moves_fn pick_moves(const RunnerDev& R, bool dbg) {
