@@ -216,6 +216,17 @@ PTMC_API int ptmc_download_hist(ptmc_handle* h, double* en_hist, double* ev_hist
  * plumbing (torch.distributed / NCCL all-reduce) can sum it across GPUs in place. */
 PTMC_API int ptmc_reduced_hist_dev(ptmc_handle* h, void** dev_ptr, int64_t* n_elems);
 
+/* ---- radial distribution function ------------------------------------------------------------------
+ * update_rdf! (src/Sampling.jl:282-316), called by sampling_step! when rdfsave is set and rem(idx, 1000) == 0
+ * (:343-347, :363-367): for every slot and every unordered pair, idx = floor(d2 / delta_r2); idx != 0 && idx <=
+ * 5 n_bin  =>  rdf[slot][idx] += 1.  delta_r2 is results.delta_r2 of initialise_histograms! (:151,185,213,240).
+ * The host loop ends a ptmc_run_cycles call on those cycles and calls ptmc_rdf_sample (distances are recomputed from
+ * the positions with the reference's distance2 arithmetic; the reference reads its stored dist2_mat). */
+PTMC_API int ptmc_rdf_enable(ptmc_handle* h, double delta_r2);
+PTMC_API int ptmc_rdf_sample(ptmc_handle* h);
+/* rdf [n_ladders][n_traj][5 n_bin] as Float64 counts like Output.rdf (src/InputParams.jl:128) */
+PTMC_API int ptmc_download_rdf(ptmc_handle* h, double* rdf);
+
 /* ---- introspection ------------------------------------------------------------------------------- */
 /* Number of kernel launches issued so far by this handle, and the lanes-per-replica actually used. */
 PTMC_API int64_t ptmc_launch_count(const ptmc_handle* h);

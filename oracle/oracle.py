@@ -214,6 +214,25 @@ class OracleEngine(Engine):
         self.lib.orc_get_dist2_mat(self._h, ladder * self.cfg.n_traj + slot, out.ctypes.data_as(_dp))
         return out
 
+    # update_rdf! (src/Sampling.jl:301-316) straight from the oracle's dist2_mat, as the reference does
+    def rdf_enable(self, delta_r2: float):
+        L, T = self.shape
+        self._delta_r2 = float(delta_r2)
+        self._rdf = np.zeros((L, T, 5 * self.cfg.n_bin))
+
+    def rdf_sample(self):
+        L, T = self.shape
+        nrb = 5 * self.cfg.n_bin
+        for l in range(L):
+            for t in range(T):
+                d2 = self.dist2_mat(l, t)
+                idx = np.floor(d2[np.tril_indices(self.cfg.n_atoms)] / self._delta_r2).astype(np.int64)   # for i, for k in 1:i
+                idx = idx[(idx != 0) & (idx <= nrb)]
+                np.add.at(self._rdf[l, t], idx - 1, 1.0)
+
+    def download_rdf(self):
+        return self._rdf.copy()
+
     def runner_state(self, ladder: int, slot: int):
         """(g_matrix [atom][n_sym], en_atom [atom]) of one replica (RuNNer)"""
         n = self.cfg.n_atoms

@@ -86,6 +86,9 @@ SYMBOLS = {
     "ptmc_download_states": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _i64p, _dp]),
     "ptmc_download_hist": (C.c_int, [_vp, _dp, _dp, C.c_int]),
     "ptmc_reduced_hist_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
+    "ptmc_rdf_enable": (C.c_int, [_vp, C.c_double]),
+    "ptmc_rdf_sample": (C.c_int, [_vp]),
+    "ptmc_download_rdf": (C.c_int, [_vp, _dp]),
     "ptmc_launch_count": (C.c_int64, [_vp]),
     "ptmc_lanes_per_replica": (C.c_int, [_vp]),
     "ptmc_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp]),

@@ -21,6 +21,7 @@ sweep_fn sweep_table_g32(int pot, int geom, int dbg, int niter, int n_coeff);
 int sweep_max_threads(int G);
 void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
+void launch_rdf(const DevParams& P, u64* rdf, double delta_r2, int n_rdf_bins, i64 n_rep, cudaStream_t st);
 double measure_fp64_peak(cudaStream_t st, int iters);
 int run_issue_probe(double sm_mhz, double out_cycles[4]);
 int run_pair_probe(const DevParams& P, int n, const double* h_d2n, const double* h_d2o, double* h_en, double* h_eo);
@@ -54,6 +55,7 @@ struct ptmc_handle {
     // device buffers (owned)
     std::vector<void*> owned;
     u64* d_reduced = nullptr;
+    u64* d_rdf = nullptr; double delta_r2 = 0.0;    // radial distribution histogram [L][T][5 n_bin]
     int* d_error = nullptr;
     void* d_slot_draws = nullptr; void* d_ladder_draws = nullptr;
     void* d_trace[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -665,6 +667,38 @@ extern "C" PTMC_API int ptmc_download_hist(ptmc_handle* h, double* en_hist, doub
     std::vector<u64> tmp(n);
     CU(h, cudaMemcpy(tmp.data(), src, n * sizeof(u64), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) dst[i] = (double)tmp[i];   // Output.en_histogram holds Float64 counts
+    return PTMC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- rdf --
+extern "C" PTMC_API int ptmc_rdf_enable(ptmc_handle* h, double delta_r2) {
+    if (!h) return PTMC_ERR_ARG;
+    if (!(delta_r2 > 0)) return fail(h, PTMC_ERR_ARG, "delta_r2 must be positive");
+    CU(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_rep * 5 * (size_t)h->cfg.n_bin;
+    if (!h->d_rdf) TRY(dev_alloc(h, &h->d_rdf, n));
+    else CU(h, cudaMemsetAsync(h->d_rdf, 0, n * sizeof(u64), h->stream));
+    h->delta_r2 = delta_r2;
+    return PTMC_OK;
+}
+extern "C" PTMC_API int ptmc_rdf_sample(ptmc_handle* h) {
+    if (!h) return PTMC_ERR_ARG;
+    if (!h->d_rdf) return fail(h, PTMC_ERR_STATE, "ptmc_rdf_enable first");
+    if (!h->uploaded) return fail(h, PTMC_ERR_STATE, "no states uploaded");
+    CU(h, cudaSetDevice(h->device));
+    launch_rdf(h->P, h->d_rdf, h->delta_r2, 5 * h->cfg.n_bin, h->n_rep, h->stream);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+    return PTMC_OK;
+}
+extern "C" PTMC_API int ptmc_download_rdf(ptmc_handle* h, double* rdf) {
+    if (!h || !rdf) return PTMC_ERR_ARG;
+    if (!h->d_rdf) return fail(h, PTMC_ERR_STATE, "ptmc_rdf_enable first");
+    TRY(ptmc_sync(h));
+    const size_t n = (size_t)h->n_rep * 5 * (size_t)h->cfg.n_bin;
+    std::vector<u64> tmp(n);
+    CU(h, cudaMemcpy(tmp.data(), h->d_rdf, n * sizeof(u64), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) rdf[i] = (double)tmp[i];
     return PTMC_OK;
 }
 

@@ -27,6 +27,30 @@ void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaS
     reduce_hist_kernel<<<(unsigned)((per + threads - 1) / threads), threads, 0, st>>>(hist, out, n_ladders, per);
 }
 
+// update_rdf! (src/Sampling.jl:301-316): one CTA per replica slot, private bins in shared memory.  Distances with the
+// reference's distance2 arithmetic from the slot-ordered positions (P.pos is current after every ptmc_run_cycles).
+__global__ void rdf_kernel(const DevParams P, u64* rdf, const double delta_r2, const int nrb) {
+    extern __shared__ unsigned int rdf_bins[];
+    const i64 rep = blockIdx.x;
+    const int N = P.n_atoms;
+    for (int k = threadIdx.x; k < nrb; k += blockDim.x) rdf_bins[k] = 0u;
+    __syncthreads();
+    const double* gp = P.pos + rep * 3 * N;
+    const double L = P.box[rep * 2], h = P.box[rep * 2 + 1];
+    for (int p = threadIdx.x; p < N * N; p += blockDim.x) {
+        const int a = p / N, b = p - a * N;
+        if (a >= b) continue;
+        const double d2 = dist2_exact(P.bc_kind, gp[3 * a], gp[3 * a + 1], gp[3 * a + 2], gp[3 * b], gp[3 * b + 1], gp[3 * b + 2], L, h);
+        const double q = floor(xdiv(d2, delta_r2));                  // rdf_index :282
+        if (q >= 1.0 && q <= (double)nrb) atomicAdd(&rdf_bins[(int)q - 1], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nrb; k += blockDim.x) if (rdf_bins[k]) rdf[rep * nrb + k] += rdf_bins[k];
+}
+void launch_rdf(const DevParams& P, u64* rdf, double delta_r2, int n_rdf_bins, i64 n_rep, cudaStream_t st) {
+    rdf_kernel<<<(unsigned)n_rep, 256, (size_t)n_rdf_bins * sizeof(unsigned int), st>>>(P, rdf, delta_r2, n_rdf_bins);
+}
+
 // Accuracy probe of the production pair arithmetic: e_new[k], e_old[k] exactly as the sweep kernel accumulates
 // them for the pair (d2_new[k], d2_old[k]).
 __global__ void pair_probe_kernel(const DevParams P, int n, const double* d2n, const double* d2o, double* en, double* eo) {

@@ -299,6 +299,19 @@ class Engine:
         self._check(self._fn("download_hist")(self._h, _p(en), None, int(reduce_ladders)))
         return en
 
+    # -- radial distribution function (src/Sampling.jl:282-316) ---------------------------------------
+    def rdf_enable(self, delta_r2: float):
+        self._check(self._fn("rdf_enable")(self._h, float(delta_r2)))
+
+    def rdf_sample(self):
+        self._check(self._fn("rdf_sample")(self._h))
+
+    def download_rdf(self):
+        L, T = self.shape
+        out = np.zeros((L, T, 5 * self.cfg.n_bin))
+        self._check(self._fn("download_rdf")(self._h, _p(out)))
+        return out
+
     # -- device-side extras (CUDA library only) -------------------------------------------------------
     def set_stream(self, cuda_stream: int):
         self._check(self._fn("set_stream")(self._h, C.c_void_p(cuda_stream)))

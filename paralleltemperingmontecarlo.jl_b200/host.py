@@ -78,6 +78,7 @@ class Output:
     heat_cap: np.ndarray | None = None
     en_histogram: np.ndarray | None = None   # [n_traj][n_bin+2]
     ev_histogram: np.ndarray | None = None   # [n_traj][n_bin+2][n_bin+2]
+    rdf: np.ndarray | None = None            # [n_traj][5 n_bin]
     count_stat_atom: np.ndarray | None = None
     count_stat_exc: np.ndarray | None = None
 
@@ -302,55 +303,145 @@ def finalise_results(mc_params: MCParams, betas, ham, counters, results: Output)
     return results
 
 
+def rdf_delta_r2(bc, n_bin: int) -> float:
+    """delta_r2 of initialise_histograms! (src/Sampling.jl:151,185,213-214,240-241): rdf bins of the squared distance."""
+    if isinstance(bc, SphericalBC):
+        return 4 * bc.radius2 / n_bin / 5
+    if isinstance(bc, CubicBC):
+        return 3 / 4 * bc.box_length ** 2 / n_bin / 5
+    if isinstance(bc, RhombicBC):
+        return (3 / 8 * bc.box_length ** 2 + 1 / 4 * bc.box_height ** 2) / n_bin / 5
+    return (1 / 2 * bc.box_length ** 2 + 1 / 4 * bc.box_height ** 2) / n_bin / 5
+
+
+def _ladder_dir(save_dir, ladder: int, n_ladders: int):
+    import pathlib
+    return pathlib.Path(save_dir) if n_ladders == 1 else pathlib.Path(save_dir) / f"ladder{ladder}"
+
+
 def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensemble, *, n_ladders: int = 1,
              seed: int = 1234, device: int = 0, engine_cls=Engine, engine_kwargs=None, chunk: int = 100000,
-             shared_bounds: bool = False, lanes_per_replica: int = 0):
-    """ptmc_run! (src/MCRun.jl:363-432) for `n_ladders` independent ladders batched on one device.
+             shared_bounds: bool = False, lanes_per_replica: int = 0, rdfsave: bool = False, save=False,
+             save_dir="./checkpoint", restart: bool = False):
+    """ptmc_run! (src/MCRun.jl:363-432, restart method :434-488) for `n_ladders` independent ladders batched on one device.
 
     Returns (states, results): `states` is the dict of `Engine.download_states()` (per ladder, per slot),
     `results` a list of one `Output` per ladder.  With shared_bounds=True all ladders bin into the same
-    [en_min, en_max] (the min/max over every ladder) so that their histograms can be summed."""
+    [en_min, en_max] (the min/max over every ladder) so that their histograms can be summed.
+
+    rdfsave: radial distribution histograms every 1000 cycles (src/Sampling.jl:282-316), `results[l].rdf`.
+    save: False or a cycle count: every `save` cycles (and at the end) the reference's checkpoint files are written to
+    `save_dir` (one sub-directory `ladder<l>` per ladder when n_ladders > 1), readsave.py / src/ReadSave.jl.
+    restart: continue from the checkpoint in `save_dir` (configurations, step sizes, total counters, histograms, cycle
+    index); equilibration is skipped (src/MCRun.jl:337-339)."""
+    from . import readsave
     cfg = sweep_config(mc_params, temp, start_config, potential, ensemble, n_ladders=n_ladders, seed=seed,
                        device=device, lanes_per_replica=lanes_per_replica)
     eng = engine_cls(cfg, **(engine_kwargs or {}))
     cfgs = start_config if isinstance(start_config, (list, tuple)) else (start_config,)
     bc0 = cfgs[0].boundary_condition
+    npt = ensemble.kind == abi.ENS_NPT
+    nb2 = mc_params.n_bin + 2
     try:
-        pos, box = initial_arrays(mc_params, start_config, n_ladders)
-        eng.upload_states(pos, box)
-        eng.seed(seed)
-        # equilibration (src/MCRun.jl:282-313): MC for eq_cycles ÷ 2 cycles only, cycle index from 1
-        n_eq = mc_params.eq_cycles // 2
-        if n_eq > 0:
-            eng.run_cycles(1, n_eq, False)
-        en = eng.download_states(("en_tot",))["en_tot"]
-        bounds = np.array([histogram_bounds(mc_params, en[l], bc0) for l in range(n_ladders)])
-        if shared_bounds:
-            bounds[:, 0] = bounds[:, 0].min()
-            bounds[:, 1] = bounds[:, 1].max()
-        eng.reset_counters()
+        start_counter = 1
+        old_hist = old_rdf = None
+        if restart:
+            # rebuild_states (src/ReadSave.jl:437-483): every ladder resumes from its own directory
+            T, N = mc_params.n_traj, mc_params.n_atoms
+            pos = np.empty((n_ladders, T, N, 3)); box = np.empty((n_ladders, T, 2)); md = np.full((n_ladders, T, 4), 0.1)
+            counters = np.zeros((n_ladders, T, abi.PTMC_NCOUNT), dtype=np.int64)
+            bounds = np.zeros((n_ladders, 4)); deltas = np.zeros((n_ladders, 3))
+            old_hist = np.zeros((n_ladders, T, nb2, nb2) if npt else (n_ladders, T, nb2))
+            old_rdf = np.zeros((n_ladders, T, 5 * mc_params.n_bin))
+            for l in range(n_ladders):
+                cf, m, ca, cv, res, rdf, index = readsave.rebuild_states(T, _ladder_dir(save_dir, l, n_ladders), npt)
+                for t in range(T):
+                    pos[l, t] = cf[t].positions; box[l, t] = cf[t].boundary_condition.box(); md[l, t, :3] = m[t]
+                counters[l, :, abi.C_ATOM_TOT] = ca; counters[l, :, abi.C_VOL_TOT] = cv
+                bounds[l] = (res.en_min, res.en_max, res.v_min, res.v_max)
+                deltas[l] = (res.delta_en_hist, res.delta_v_hist, res.delta_r2)
+                old_hist[l] = res.ev_histogram if npt else res.en_histogram
+                if rdf is not None:
+                    old_rdf[l] = rdf
+                start_counter = index + 1
+            eng.upload_states(pos, box, md)
+            eng.upload_counters(counters, None)
+            eng.seed(seed + start_counter)          # the reference restarts with whatever its task-local generator holds
+        else:
+            pos, box = initial_arrays(mc_params, start_config, n_ladders)
+            eng.upload_states(pos, box)
+            eng.seed(seed)
+            # equilibration (src/MCRun.jl:282-313): MC for eq_cycles ÷ 2 cycles only, cycle index from 1
+            n_eq = mc_params.eq_cycles // 2
+            if n_eq > 0:
+                eng.run_cycles(1, n_eq, False)
+            en = eng.download_states(("en_tot",))["en_tot"]
+            bounds = np.array([histogram_bounds(mc_params, en[l], bc0) for l in range(n_ladders)])
+            if shared_bounds:
+                bounds[:, 0] = bounds[:, 0].min()
+                bounds[:, 1] = bounds[:, 1].max()
+            eng.reset_counters()
         eng.set_hist_bounds(bounds[:, 0].copy(), bounds[:, 1].copy(), bounds[:, 2].copy(), bounds[:, 3].copy())
-        # main loop (src/MCRun.jl:397-421), chunked; nothing is read back between chunks
-        i = 1
+        delta_r2 = rdf_delta_r2(bc0, mc_params.n_bin)
+        if rdfsave:
+            eng.rdf_enable(delta_r2)
+
+        def make_results(states, hist, rdf):
+            out = []
+            for l in range(n_ladders):
+                r = Output(mc_params.n_bin, en_min=bounds[l, 0], en_max=bounds[l, 1], v_min=bounds[l, 2], v_max=bounds[l, 3])
+                r.delta_en_hist = (r.en_max - r.en_min) / (r.n_bin - 1)
+                r.delta_r2 = delta_r2
+                hl = hist[l] + (old_hist[l] if old_hist is not None else 0)
+                if npt:
+                    r.delta_v_hist = (r.v_max - r.v_min) / r.n_bin
+                    r.ev_histogram = hl
+                else:
+                    r.en_histogram = hl
+                if rdf is not None:
+                    r.rdf = rdf[l] + (old_rdf[l] if old_rdf is not None else 0)
+                r.max_displ = states["max_displ"][l]
+                out.append(r)
+            return out
+
+        def write_checkpoint(i):
+            states = eng.download_states()
+            res = make_results(states, eng.download_hist(), eng.download_rdf() if rdfsave else None)
+            for l in range(n_ladders):
+                readsave.checkpoint(i, states, res[l], ensemble, bc0.kind, ladder=l, rdf=res[l].rdf if rdfsave else None,
+                                    directory=_ladder_dir(save_dir, l, n_ladders))
+
+        if save and not restart:
+            res0 = make_results({"max_displ": np.zeros((n_ladders, mc_params.n_traj, 4))},
+                                np.zeros((n_ladders,) + ((mc_params.n_traj, nb2, nb2) if npt else (mc_params.n_traj, nb2))), None)
+            for l in range(n_ladders):
+                d = _ladder_dir(save_dir, l, n_ladders)
+                readsave.save_init(potential, ensemble, mc_params, temp, d)       # src/MCRun.jl:378-380
+                readsave.save_histparams(res0[l], d)                              # :390-392
+        # main loop (src/MCRun.jl:397-421), chunked; launches end where the reference touches the states: checkpoints
+        # (rem(i, save) == 0) and rdf samples (rem(i, 1000) == 0 on sampled cycles, src/Sampling.jl:343-347)
+        i = start_counter
+        last_saved = None
         while i <= mc_params.mc_cycles:
-            k = min(chunk, mc_params.mc_cycles - i + 1)
-            eng.run_cycles(i, k, True)
-            i += k
+            stop = min(i + chunk - 1, mc_params.mc_cycles)
+            if save:
+                stop = min(stop, (i + save - 1) // save * save)
+            if rdfsave:
+                stop = min(stop, (i + 999) // 1000 * 1000)
+            eng.run_cycles(i, stop - i + 1, True)
+            if rdfsave and stop % 1000 == 0 and stop % mc_params.mc_sample == 0:
+                eng.rdf_sample()
+            if save and stop % save == 0:
+                write_checkpoint(stop)
+                last_saved = stop
+            i = stop + 1
+        if save and last_saved != mc_params.mc_cycles:
+            write_checkpoint(mc_params.mc_cycles)                                 # :424-427
         eng.sync()
         states = eng.download_states()
-        hist = eng.download_hist()
-        results = []
+        results = make_results(states, eng.download_hist(), eng.download_rdf() if rdfsave else None)
         for l in range(n_ladders):
-            r = Output(mc_params.n_bin, en_min=bounds[l, 0], en_max=bounds[l, 1], v_min=bounds[l, 2], v_max=bounds[l, 3])
-            r.delta_en_hist = (r.en_max - r.en_min) / (r.n_bin - 1)
-            if ensemble.kind == abi.ENS_NPT:
-                r.delta_v_hist = (r.v_max - r.v_min) / r.n_bin
-                r.ev_histogram = hist[l]
-            else:
-                r.en_histogram = hist[l]
-            r.max_displ = states["max_displ"][l]
-            finalise_results(mc_params, temp.beta_grid, states["ham"][l], states["counters"][l], r)
-            results.append(r)
+            finalise_results(mc_params, temp.beta_grid, states["ham"][l], states["counters"][l], results[l])
         return states, results
     finally:
         eng.close()

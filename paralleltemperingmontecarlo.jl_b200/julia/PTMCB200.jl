@@ -89,7 +89,7 @@ back to the host only where the reference's driver touches them (histogram bound
 end of run).
 """
 function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCParams, temp::TempGrid, start_config,
-                                               potential, ensemble; save=false, saveconfigs=false, kwargs...)
+                                               potential, ensemble; rdfsave=false, save=false, saveconfigs=false, kwargs...)
     lib = b.lib
     # the package's own initialisation builds MCStates (host copies), MoveStrategy and the empty Output
     mc_states, move_strategy, results, n_steps, _ = initialisation(mc_params, temp, start_config, potential, ensemble)
@@ -130,20 +130,26 @@ function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCPara
         check(lib, h[], ccall((:ptmc_set_hist_bounds, lib), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}, Ref{Float64}, Ref{Float64}, Cint),
                               h[], results.en_min, results.en_max, results.v_min, results.v_max, 0))
         # main loop (src/MCRun.jl:397-421) in chunks that end where the reference's driver would look at the states
-        stops = filter(x -> x !== false, (save, saveconfigs))
+        stops = filter(x -> x !== false, (save, saveconfigs, rdfsave ? 1000 : false))
+        rdfsave && check(lib, h[], ccall((:ptmc_rdf_enable, lib), Cint, (Ptr{Cvoid}, Float64), h[], results.delta_r2))
         i = 1
         while i <= mc_params.mc_cycles
             k = min(b.chunk, mc_params.mc_cycles - i + 1)
             for s in stops; k = min(k, s - rem(i - 1, s)); end
             check(lib, h[], ccall((:ptmc_run_cycles, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Cint), h[], i, k, 1))
             i += k
-            if any(s -> rem(i - 1, s) == 0, stops)
+            # update_rdf! (src/Sampling.jl:343-347): sampled cycles with rem(idx, 1000) == 0
+            rdfsave && rem(i - 1, 1000) == 0 && rem(i - 1, mc_params.mc_sample) == 0 &&
+                check(lib, h[], ccall((:ptmc_rdf_sample, lib), Cint, (Ptr{Cvoid},), h[]))
+            if any(s -> s !== 1000 && rem(i - 1, s) == 0, filter(x -> x !== false, (save, saveconfigs)))
                 download!(lib, h[], mc_states, results, N, T, L, npt)
-                save !== false && rem(i - 1, save) == 0 && ParallelTemperingMonteCarlo.checkpoint(i - 1, mc_states, results, ensemble, false)
+                rdfsave && download_rdf!(lib, h[], results, T, L)
+                save !== false && rem(i - 1, save) == 0 && ParallelTemperingMonteCarlo.checkpoint(i - 1, mc_states, results, ensemble, rdfsave)
                 saveconfigs !== false && rem(i - 1, saveconfigs) == 0 && ParallelTemperingMonteCarlo.save_configs(mc_states, string("configuration", i - 1))
             end
         end
         download!(lib, h[], mc_states, results, N, T, L, npt)
+        rdfsave && download_rdf!(lib, h[], results, T, L)
     finally
         ccall((:ptmc_destroy, lib), Cvoid, (Ptr{Cvoid},), h[])
     end
@@ -174,6 +180,13 @@ function download!(lib, h, mc_states, results, N, T, L, npt)
         check(lib, h, ccall((:ptmc_download_hist, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint), h, eh, C_NULL, 0))
         for t in 1:T; results.en_histogram[t] .= eh[:, t, 1]; end
     end
+    return nothing
+end
+
+function download_rdf!(lib, h, results, T, L)
+    rdf = Array{Float64}(undef, 5 * results.n_bin, T, L)
+    check(lib, h, ccall((:ptmc_download_rdf, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, rdf))
+    for t in 1:T; results.rdf[t] .= rdf[:, t, 1]; end
     return nothing
 end
 

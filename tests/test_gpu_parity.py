@@ -300,6 +300,74 @@ def test_cu55_runner_production_mode_and_guard(oracle):
     eng.close()
 
 
+@pytest.mark.parametrize("case", ["ne13", "eam", "cubic_nvt", "rhombic_npt", "runner"])
+def test_rdf_matches_oracle(case, oracle):
+    # update_rdf! (src/Sampling.jl:301-316): the device bins distances recomputed from the positions, the oracle bins its
+    # stored dist2_mat like the reference; same trajectory (production streams) -> identical histograms.  NPT: the reference's
+    # matrix is rescaled by scale^2 at volume moves instead of being recomputed (1-ulp differences): a count may move to the
+    # neighbouring bin when a distance sits within 1e-16 of a bin edge.
+    from oracle import oracle as orc
+    if case == "ne13":
+        deck, bounds = P.host.deck_ne13(n_traj=6, cycles=30), (-0.01, 0.0)
+    elif case == "eam":
+        deck, bounds = P.host.deck_cu55_eam(n_traj=4, cycles=10), (-10.0, 0.0)
+    elif case == "cubic_nvt":
+        deck, bounds = (P.MCParams(20, 4, 32), P.TempGrid(20.0, 40.0, 4), _small_pbc(P.CubicBC), P.ELJPotentialEven(P.host.ELJ_NE_COEFF), P.NVT(32)), (-0.1, 0.0)
+    elif case == "rhombic_npt":
+        deck, bounds = (P.MCParams(20, 4, 32), P.TempGrid(20.0, 40.0, 4), _small_pbc(P.RhombicBC), P.ELJPotentialEven(P.host.ELJ_NE_COEFF), P.NPT(32, 101325 * 3.398928944382626e-14)), None
+    else:
+        deck, bounds = P.host.deck_cu55_runner(n_traj=3, cycles=2), (-13.0, -11.0)
+    mcp, temp, start, pot, ens = deck
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=2, seed=11, rng_mode=abi.RNG_BATCH8)
+    pos, box = initial_arrays(mcp, start, 2)
+    bc = (start[0] if isinstance(start, (list, tuple)) else start).boundary_condition
+    if bounds is None:
+        v0 = P.get_volume(bc)
+        bounds = (-1.0, 1.0, 0.8 * v0, 2.0 * v0)
+    delta = P.host.rdf_delta_r2(bc, mcp.n_bin)
+    out = []
+    for cls in (Engine, orc.OracleEngine):
+        eng = cls(cfg)
+        eng.upload_states(pos, box)
+        eng.seed(11)
+        eng.set_hist_bounds(*bounds)
+        eng.rdf_enable(delta)
+        for k in range(3):
+            eng.run_cycles(1 + k * mcp.mc_cycles, mcp.mc_cycles, True)
+            eng.rdf_sample()
+        out.append((eng.download_rdf(), eng.download_states()))
+        eng.close()
+    (rg, sg), (rc, sc) = out
+    if case == "rhombic_npt":
+        np.testing.assert_allclose(sg["pos"], sc["pos"], rtol=1e-11, atol=1e-11)   # exp / pow of two libms in the volume scale
+    else:
+        assert np.array_equal(sg["pos"], sc["pos"])
+    n_pairs = mcp.n_atoms * (mcp.n_atoms - 1) // 2
+    assert rg.shape == (2, mcp.n_traj, 5 * mcp.n_bin) and 0 < rg.sum() <= 3 * 2 * mcp.n_traj * n_pairs
+    if case == "rhombic_npt":
+        assert np.abs(rg - rc).sum() <= 8 and abs(rg.sum() - rc.sum()) <= 4
+    else:
+        assert np.array_equal(rg, rc)
+
+
+def test_ptmc_run_checkpoint_files_gpu(tmp_path):
+    # ptmc_run with save / rdfsave on the device, restart from the written directory (src/MCRun.jl:363-488, src/ReadSave.jl)
+    from ptmc_b200 import readsave
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=8, cycles=2000)
+    mcp.eq_percentage = 0.05
+    st, res = P.host.ptmc_run(mcp, temp, start, pot, ens, n_ladders=3, seed=5, rdfsave=True, save=1000, save_dir=tmp_path)
+    for l in range(3):
+        cfgs, md, ca, cv, back, rdf, index = readsave.rebuild_states(8, tmp_path / f"ladder{l}")
+        assert index == 2000 and np.array_equal(back.en_histogram, res[l].en_histogram) and np.array_equal(rdf, res[l].rdf)
+        assert np.array_equal(np.stack([c.positions for c in cfgs]), st["pos"][l]) and np.array_equal(ca, st["counters"][l, :, abi.C_ATOM_TOT])
+        assert rdf.sum() > 0 and back.en_histogram.sum() == 8 * 2000
+    mcp2, temp2, ens2, pot2 = readsave.read_init(tmp_path / "ladder0")
+    mcp2.mc_cycles = 2500
+    st2, res2 = P.host.ptmc_run(mcp2, temp2, start, pot2, ens2, n_ladders=3, seed=5, save=1000, save_dir=tmp_path, restart=True)
+    assert all(r.en_histogram.sum() == 8 * 2500 for r in res2)
+    assert readsave.rebuild_states(8, tmp_path / "ladder2")[-1] == 2500
+
+
 def test_pair_arithmetic_accuracy(oracle):
     # the production pair kernel (one shared reciprocal, Halley step, Horner + FMA) against the reference's
     # own formulation (1 + K divisions, src/EnergyEvaluation.jl:934-942) over the whole physical range
