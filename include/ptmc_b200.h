@@ -39,7 +39,7 @@ extern "C" {
 #define PTMC_API
 #endif
 
-#define PTMC_ABI_VERSION 1
+#define PTMC_ABI_VERSION 2
 #define PTMC_MAX_COEFF 16
 #define PTMC_NCOUNT 10
 
@@ -54,7 +54,8 @@ typedef enum ptmc_status {
 
 /* src/EnergyEvaluation.jl:891 (ELJPotential), :138 (ELJPotentialEven), :1059 (EmbeddedAtomPotential),
  * :1182 (RuNNerPotential) */
-typedef enum ptmc_pot_kind { PTMC_POT_ELJ = 0, PTMC_POT_ELJ_EVEN = 1, PTMC_POT_EAM = 2, PTMC_POT_RUNNER = 3 } ptmc_pot_kind;
+/* :909-921 (ELJPotentialB: extended Lennard-Jones in a magnetic field, pair energy depends on the angle to the z axis) */
+typedef enum ptmc_pot_kind { PTMC_POT_ELJ = 0, PTMC_POT_ELJ_EVEN = 1, PTMC_POT_EAM = 2, PTMC_POT_RUNNER = 3, PTMC_POT_ELJ_B = 4 } ptmc_pot_kind;
 /* src/BoundaryConditions.jl:44,72,89,110 */
 typedef enum ptmc_bc_kind { PTMC_BC_SPHERICAL = 0, PTMC_BC_CUBIC = 1, PTMC_BC_RHOMBIC = 2, PTMC_BC_RECTANGULAR = 3 } ptmc_bc_kind;
 /* src/Ensembles.jl:42 (NVT), :75 (NPT with separated_volume=false) */
@@ -129,6 +130,9 @@ typedef struct ptmc_config {
     uint64_t seed;            /* base seed: slot stream s gets Random.seed!(seed + s), see ptmc_seed  */
     int32_t lanes_per_replica;/* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one replica       */
     int32_t reserved;
+    /* ABI 2: PTMC_POT_ELJ_B only - coeff_a, coeff_b [n_coeff] (coeff_c travels in coeff[])                */
+    const double* eljb_a;
+    const double* eljb_b;
 } ptmc_config;
 
 typedef struct ptmc_handle ptmc_handle;

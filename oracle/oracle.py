@@ -72,6 +72,9 @@ def load():
         "orc_lrc_eljeven": (C.c_double, [_dp, C.c_int, C.c_int, C.c_double]),
         "orc_eam_ctor": (None, [C.c_double] * 5 + [_dp, _dp]),
         "orc_distance2": (C.c_double, [C.c_int, _dp, _dp, C.c_double, C.c_double]),
+        "orc_get_tan": (C.c_double, [C.c_int, _dp, _dp, C.c_double, C.c_double]),
+        "orc_dimer_energy_eljb": (C.c_double, [_dp, _dp, _dp, C.c_int, C.c_double, C.c_double]),
+        "orc_lrc_eljb": (C.c_double, [C.c_int, C.c_double]),
         "orc_get_volume": (C.c_double, [C.c_int, C.c_double, C.c_double]),
         "orc_get_r_cut": (C.c_double, [C.c_int, C.c_double, C.c_double]),
         "orc_tempgrid": (None, [C.c_double, C.c_double, C.c_int, _dp, _dp]),
@@ -132,6 +135,20 @@ def distance2(bc_kind, a, b, L=0.0, h=0.0):
     aa, pa = _arr(a)
     bb, pb = _arr(b)
     return load().orc_distance2(bc_kind, pa, pb, L, h)
+
+
+def get_tan(bc_kind, a, b, L=0.0, h=0.0):
+    (_, pa), (_, pb) = _arr(a), _arr(b)
+    return load().orc_get_tan(bc_kind, pa, pb, L, h)
+
+
+def dimer_energy_eljb(ca, cb, cc, r2, tan):
+    (a, pa), (b, pb), (c, pc) = _arr(ca), _arr(cb), _arr(cc)
+    return load().orc_dimer_energy_eljb(pa, pb, pc, len(c), float(r2), float(tan))
+
+
+def lrc_eljb(n_atoms, r_cut):
+    return load().orc_lrc_eljb(int(n_atoms), float(r_cut))
 
 
 def get_volume(bc_kind, L, h=0.0):

@@ -238,6 +238,52 @@ double orc_distance2(int bc_kind, const double* a, const double* b, double L, do
     }
 }
 /* get_volume src/Configurations.jl:246-256 */
+/* get_tan src/Configurations.jl:177-219: |tan| of the angle between a -> (nearest image of) b and the z axis */
+double orc_get_tan(int bc_kind, const double* a, const double* b, double L, double h) {
+    double bx = b[0], by = b[1], bz = b[2];
+    if (bc_kind == PTMC_BC_CUBIC) {
+        bx = b[0] + L * rint((a[0] - b[0]) / L); by = b[1] + L * rint((a[1] - b[1]) / L); bz = b[2] + L * rint((a[2] - b[2]) / L);
+    } else if (bc_kind == PTMC_BC_RHOMBIC) {
+        by = b[1] + (pow(3, 0.5) / 2 * L) * rint((a[1] - b[1]) / (pow(3, 0.5) / 2 * L));
+        bx = b[0] - b[1] / pow(3, 0.5) + L * rint(((a[0] - b[0]) - 1 / pow(3, 0.5) * (a[1] - b[1])) / L) + 1 / pow(3, 0.5) * by;
+        bz = b[2] + h * rint((a[2] - b[2]) / h);
+    } else if (bc_kind == PTMC_BC_RECTANGULAR) {
+        bx = b[0] + L * rint((a[0] - b[0]) / L); by = b[1] + L * rint((a[1] - b[1]) / L); bz = b[2] + h * rint((a[2] - b[2]) / h);
+    }
+    double dx = a[0] - bx, dy = a[1] - by;
+    double t = pow(dx * dx + dy * dy, 0.5) / (a[2] - bz);
+    return fabs(t);
+}
+/* dimer_energy(::ELJPotentialB) src/EnergyEvaluation.jl:943-958 */
+double orc_dimer_energy_eljb(const double* ca, const double* cb, const double* cc, int n, double r2, double z_angle) {
+    double sum1;
+    if (r2 >= 5.30) {
+        double r6inv = 1 / (r2 * r2 * r2);
+        double t2 = 2 / (z_angle * z_angle + 1) - 1;     /* cos(2 theta) */
+        double t4 = 2 * (t2 * t2) - 1;
+        sum1 = cc[0] * r6inv * (1 + ca[0] * t2 + cb[0] * t4);
+        r6inv /= r2;
+        for (int i = 1; i < n; ++i) {
+            sum1 += cc[i] * r6inv * (1 + ca[i] * t2 + cb[i] * t4);
+            r6inv /= pow(r2, 0.5);
+        }
+    } else {
+        sum1 = 0.1;
+    }
+    return sum1;
+}
+/* lrc(::ELJPotentialB) src/EnergyEvaluation.jl:983-998 */
+double orc_lrc_eljb(int n_atoms, double r_cut) {
+    static const double coeff[4] = {-0.1279111890228638, -1.328138539967966, 12.260941135261255, 41.12212408251662};
+    if (r_cut <= 16) return 0.0;
+    double r_cut_sqrt = pow(r_cut, 0.5);
+    double rc3 = r_cut * r_cut_sqrt;
+    double e_lrc = 0.0;
+    for (int i = 1; i <= 4; ++i) { e_lrc += coeff[i - 1] / rc3 / (2 * i + 1); rc3 *= r_cut; }
+    e_lrc *= M_PI * ((double)n_atoms * n_atoms) / 4 / (r_cut_sqrt * r_cut_sqrt * r_cut_sqrt);
+    return e_lrc;
+}
+
 double orc_get_volume(int bc_kind, double L, double h) {
     switch (bc_kind) {
         case PTMC_BC_CUBIC: return L * L * L;
@@ -275,6 +321,7 @@ typedef struct orc_cfgside { /* everything exc_trajectories! swaps (src/Exchange
     double trial_box[2];
     double* new_d2mat;/* NPTVariables.new_dist2_mat */
     double new_r_cut;
+    double* tan;      /* ELJPotentialBVariables.tan_mat [N][N] (src/EnergyEvaluation.jl:187-192) */
     double* comp;     /* EAM component_vector [N][2] */
     double* new_comp; /* EAM new_component_vector */
     /* NNPVariables src/EnergyEvaluation.jl:1229-1236 */
@@ -288,6 +335,7 @@ typedef struct orc_state { /* MCState src/MCStates.jl:33-53; slot-side fields st
     double ham[2];
     int64_t count[PTMC_NCOUNT];
     double* new_d2;   /* new_dist2_vec */
+    double* new_tan;  /* ELJPotentialBVariables.new_tan_vec */
     double new_en;
     orc_rng rng;
     orc_cfgside* c;
@@ -311,6 +359,7 @@ typedef struct orc_handle {
     int error;
     int n_threads;
     orc_runner* runner;
+    double *eljb_a, *eljb_b;   /* copies of cfg.eljb_a / eljb_b */
 } orc_handle;
 
 static int n_steps_of(const ptmc_config* c) { return c->n_atom_moves + (c->ensemble == PTMC_ENS_NPT ? c->n_volume_moves : 0); }
@@ -362,6 +411,14 @@ static void d2_matrix(const ptmc_config* c, const double* pos, const double* box
     for (int i = 0; i < n; ++i) d2[(size_t)i * n + i] = 0;
 }
 
+/* dimer_energy_atom with tangents src/EnergyEvaluation.jl:337-346 */
+static double eljb_energy_atom(const ptmc_config* c, int i, const double* d2vec, const double* tanvec, int n) {
+    double sum1 = 0.0;
+    for (int j = 0; j < i; ++j) sum1 += orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, d2vec[j], tanvec[j]);
+    for (int j = i + 1; j < n; ++j) sum1 += orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, d2vec[j], tanvec[j]);
+    return sum1;
+}
+
 /* MCState(temp,beta,config,ensemble,pot) src/MCStates.jl:137-162 */
 static void init_cfgside_runner(const orc_runner* R, orc_cfgside* s, int n) {
     /* set_variables(::RuNNerPotential) src/EnergyEvaluation.jl:1812-1822 + initialise_energy :1735-1747 */
@@ -396,6 +453,17 @@ static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
         s->en_tot = eam_energy(c, s->comp, n); /* initialise_energy :1722-1734 */
     } else if (c->pot_kind == PTMC_POT_RUNNER) {
         /* done by the caller (needs the handle's orc_runner) */
+    } else if (c->pot_kind == PTMC_POT_ELJ_B) {
+        /* set_variables(::ELJPotentialB): get_tantheta_mat! src/Configurations.jl:229-244; dimer_energy_config :476-492 */
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j)
+                s->tan[(size_t)i * n + j] = s->tan[(size_t)j * n + i] = orc_get_tan(c->bc_kind, s->pos + 3 * i, s->pos + 3 * j, s->box[0], s->box[1]);
+        for (int i = 0; i < n; ++i) s->tan[(size_t)i * n + i] = 0;
+        double energy_tot = 0.0;
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j)
+                energy_tot += orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, s->d2[(size_t)i * n + j], s->tan[(size_t)i * n + j]);
+        s->en_tot = energy_tot;
     } else {
         s->en_tot = dimer_energy_config(c, s->d2, n, npt, s->r_cut, s->box); /* :1662-1693 */
     }
@@ -534,6 +602,13 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
                 s->new_comp[2 * i] += t0; s->new_comp[2 * i + 1] += t1;
             }
             st->new_en = eam_energy(c, s->new_comp, n);
+        } else if (c->pot_kind == PTMC_POT_ELJ_B) {
+            /* energy_update!(::AbstractDimerPotentialB) src/EnergyEvaluation.jl:1508-1533, dimer_energy_update! :822-836 */
+            for (int j = 0; j < n; ++j) st->new_tan[j] = orc_get_tan(c->bc_kind, trial, s->pos + 3 * j, s->box[0], s->box[1]);
+            st->new_tan[i] = 0;
+            double delta_en = eljb_energy_atom(c, i, st->new_d2, st->new_tan, n) -
+                              eljb_energy_atom(c, i, s->d2 + (size_t)i * n, s->tan + (size_t)i * n, n);
+            st->new_en = delta_en + s->en_tot;
         } else {
             /* dimer_energy_update! src/EnergyEvaluation.jl:804-821 */
             double delta_en = dimer_energy_atom(c, i, st->new_d2, n, npt, s->r_cut) -
@@ -553,6 +628,8 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             double tmp = s->en_tot; s->en_tot = st->new_en; st->new_en = tmp;
             st->count[PTMC_C_ATOM_TOT] += 1; st->count[PTMC_C_ATOM_ADJ] += 1;
             if (c->pot_kind == PTMC_POT_EAM) { double* t = s->comp; s->comp = s->new_comp; s->new_comp = t; } /* swap_vars! :208-211 */
+            if (c->pot_kind == PTMC_POT_ELJ_B)   /* swap_vars!(::ELJPotentialBVariables) src/swap_config.jl:197-201 */
+                for (int j = 0; j < n; ++j) { s->tan[(size_t)i * n + j] = st->new_tan[j]; s->tan[(size_t)j * n + i] = st->new_tan[j]; }
             if (c->pot_kind == PTMC_POT_RUNNER) {   /* swap_vars!(::NNPVariables) src/swap_config.jl:213-221 */
                 double* t = s->en_atom; s->en_atom = s->new_en_atom; s->new_en_atom = t;
                 t = s->g; s->g = s->new_g; s->new_g = t;
@@ -727,8 +804,15 @@ static void* xcalloc(size_t n, size_t sz) { void* p = calloc(n ? n : 1, sz); if 
 int orc_seed(orc_handle* H, uint64_t seed);
 orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER && (!cfg->runner || cfg->bc_kind != PTMC_BC_SPHERICAL)) return NULL;
+    /* ELJPotentialB: the free-space NVT path (scripts/ne13_B.jl); the periodic methods are outside the hot path */
+    if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->ensemble != PTMC_ENS_NVT)) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
     H->cfg = *cfg;
+    if (cfg->pot_kind == PTMC_POT_ELJ_B) {
+        H->eljb_a = (double*)xcalloc(cfg->n_coeff, sizeof(double)); H->eljb_b = (double*)xcalloc(cfg->n_coeff, sizeof(double));
+        memcpy(H->eljb_a, cfg->eljb_a, sizeof(double) * cfg->n_coeff); memcpy(H->eljb_b, cfg->eljb_b, sizeof(double) * cfg->n_coeff);
+        H->cfg.eljb_a = H->eljb_a; H->cfg.eljb_b = H->eljb_b;
+    } else { H->cfg.eljb_a = NULL; H->cfg.eljb_b = NULL; }
     if (cfg->pot_kind == PTMC_POT_RUNNER) H->runner = orc_runner_new(cfg->runner);
     H->cfg.runner = NULL;
     const int n = cfg->n_atoms, nt = cfg->n_traj;
@@ -746,6 +830,7 @@ orc_handle* orc_create(const ptmc_config* cfg) {
         s->d2 = (double*)xcalloc((size_t)n * n, sizeof(double));
         if (npt) { s->trial_pos = (double*)xcalloc(3 * n, sizeof(double)); s->new_d2mat = (double*)xcalloc((size_t)n * n, sizeof(double)); }
         if (cfg->pot_kind == PTMC_POT_EAM) { s->comp = (double*)xcalloc(2 * n, sizeof(double)); s->new_comp = (double*)xcalloc(2 * n, sizeof(double)); }
+        if (cfg->pot_kind == PTMC_POT_ELJ_B) s->tan = (double*)xcalloc((size_t)n * n, sizeof(double));
         if (cfg->pot_kind == PTMC_POT_RUNNER) {
             const size_t ns = (size_t)orc_runner_nsym(H->runner);
             s->fmat = (double*)xcalloc((size_t)n * n, 8); s->new_f = (double*)xcalloc(n, 8);
@@ -756,6 +841,7 @@ orc_handle* orc_create(const ptmc_config* cfg) {
         st->c = s;
         st->beta = H->betas[r % nt];
         st->new_d2 = (double*)xcalloc(n, sizeof(double));
+        st->new_tan = (double*)xcalloc(n, sizeof(double));
     }
     H->en_min = (double*)xcalloc(cfg->n_ladders, sizeof(double));
     H->en_max = (double*)xcalloc(cfg->n_ladders, sizeof(double));
@@ -775,12 +861,13 @@ void orc_destroy(orc_handle* H) {
         orc_cfgside* s = &H->cs[r];
         free(s->pos); free(s->d2); free(s->trial_pos); free(s->new_d2mat); free(s->comp); free(s->new_comp);
         free(s->fmat); free(s->new_f); free(s->g); free(s->new_g); free(s->en_atom); free(s->new_en_atom);
-        free(H->st[r].new_d2);
+        free(s->tan); free(H->st[r].new_d2); free(H->st[r].new_tan);
     }
     free(H->st); free(H->cs); free(H->lrng); free(H->betas);
     free(H->en_min); free(H->en_max); free(H->v_min); free(H->v_max); free(H->en_hist); free(H->ev_hist);
     free(H->tr_index); free(H->tr_de); free(H->tr_acc); free(H->tr_exc);
     orc_runner_free(H->runner);
+    free(H->eljb_a); free(H->eljb_b);
     free(H);
 }
 

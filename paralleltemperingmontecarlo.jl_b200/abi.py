@@ -10,11 +10,11 @@ import pathlib
 PKG_DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libptmc_b200.so"
 
-PTMC_ABI_VERSION = 1
+PTMC_ABI_VERSION = 2
 PTMC_MAX_COEFF = 16
 PTMC_NCOUNT = 10
 
-POT_ELJ, POT_ELJ_EVEN, POT_EAM, POT_RUNNER = 0, 1, 2, 3
+POT_ELJ, POT_ELJ_EVEN, POT_EAM, POT_RUNNER, POT_ELJ_B = 0, 1, 2, 3, 4
 BC_SPHERICAL, BC_CUBIC, BC_RHOMBIC, BC_RECTANGULAR = 0, 1, 2, 3
 ENS_NVT, ENS_NPT = 0, 1
 RNG_XOSHIRO, RNG_REPLAY, RNG_BATCH8 = 0, 1, 2
@@ -56,6 +56,7 @@ class Config(C.Structure):
         ("min_acc", C.c_double), ("max_acc", C.c_double),
         ("seed", C.c_uint64),
         ("lanes_per_replica", C.c_int32), ("reserved", C.c_int32),
+        ("eljb_a", _dp), ("eljb_b", _dp),
     ]
 
 

@@ -270,6 +270,11 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             if (c->n_coeff < 1 || c->n_coeff > PTMC_MAX_COEFF) return fail(nullptr, PTMC_ERR_ARG, "n_coeff must be in 1..%d", PTMC_MAX_COEFF);
             if (npt && c->pot_kind != PTMC_POT_ELJ_EVEN) return fail(nullptr, PTMC_ERR_ARG, "NPT long-range correction exists for ELJPotentialEven only (src/EnergyEvaluation.jl:968)");
             break;
+        case PTMC_POT_ELJ_B:
+            if (c->n_coeff < 1 || c->n_coeff > PTMC_MAX_COEFF) return fail(nullptr, PTMC_ERR_ARG, "n_coeff must be in 1..%d", PTMC_MAX_COEFF);
+            if (!c->eljb_a || !c->eljb_b) return fail(nullptr, PTMC_ERR_ARG, "pot_kind ELJ_B needs ptmc_config.eljb_a / eljb_b");
+            if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "ELJPotentialB is built for SphericalBC/NVT (scripts/ne13_B.jl); its periodic methods are outside the hot path");
+            break;
         case PTMC_POT_EAM:
             if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
             if (!(c->eam_n > 0 && c->eam_n <= 24 && c->eam_m > 0 && c->eam_m <= 24)) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential exponents n, m must be in (0, 24] (series of eam_invrexp)");
@@ -293,6 +298,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->betas.assign(c->betas, c->betas + c->n_traj);
     h->cfg.betas = h->betas.data();
     h->cfg.runner = nullptr;
+    h->cfg.eljb_a = nullptr; h->cfg.eljb_b = nullptr;      // copied into DevParams below
     h->runner = c->pot_kind == PTMC_POT_RUNNER;
     h->device = c->device;
     h->geom = sphere ? GEOM_SPHERE : (c->bc_kind == PTMC_BC_RHOMBIC ? GEOM_RHOMB : GEOM_PBC);
@@ -318,6 +324,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     P.replay = c->rng_mode == PTMC_RNG_REPLAY;
     P.min_acc = c->min_acc; P.max_acc = c->max_acc; P.pressure = c->pressure;
     for (int i = 0; i < PTMC_MAX_COEFF; ++i) P.coeff[i] = i < c->n_coeff ? c->coeff[i] : 0.0;
+    if (c->pot_kind == PTMC_POT_ELJ_B)
+        for (int i = 0; i < c->n_coeff; ++i) { P.eljb_ca[i] = c->coeff[i] * c->eljb_a[i]; P.eljb_cb[i] = c->coeff[i] * c->eljb_b[i]; }
     P.eam_hn = c->eam_n / 2; P.eam_hm = c->eam_m / 2; P.eam_ean = c->eam_ean; P.eam_ecam = c->eam_ecam;
 
     std::vector<double> net_host;

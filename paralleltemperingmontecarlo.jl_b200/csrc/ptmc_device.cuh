@@ -38,6 +38,7 @@ struct DevParams {
     int replay;                          // 1: consume pre-drawn draws
     double min_acc, max_acc, pressure;
     double coeff[PTMC_MAX_COEFF];
+    double eljb_ca[PTMC_MAX_COEFF], eljb_cb[PTMC_MAX_COEFF];   // ELJPotentialB: c_i a_i, c_i b_i (c_i in coeff[])
     double eam_hn, eam_hm;               // n/2, m/2  (r^-n = (r2)^-(n/2))
     double eam_ean, eam_ecam;
     // table-driven (r2)^-p, p = n/2 and m/2 (eam_invrexp): binomial coefficients binom(-p, 1..6) and the tables
@@ -254,6 +255,22 @@ __device__ __forceinline__ void elj_even_pair_acc(const DevParams& P, double d2n
     const double pn = elj_even_poly<NC>(P, xn), po = elj_even_poly<NC>(P, xo);
     acc_new = fma(pn, xn * xn * xn, acc_new);
     acc_old = fma(po, xo * xo * xo, acc_old);
+}
+
+// dimer_energy(::ELJPotentialB) src/EnergyEvaluation.jl:943-958: sum_i c_i r^-k_i (1 + a_i t2 + b_i t4), k = 6, 8, 9, 10, ...;
+// t2 = cos 2theta = 2 / (tan^2 + 1) - 1 = 2 dz^2 / r^2 - 1 (no tangent matrix is stored: the angle comes from the positions
+// like the distance), t4 = 2 t2^2 - 1; below r2 = 5.30 the reference returns 0.1.
+__device__ __forceinline__ double eljb_energy(const DevParams& P, double r2, double dz2) {
+    const double y = rsqrt_pos(r2);
+    const double x = y * y;
+    const double t2 = fma(2.0 * dz2, x, -1.0);
+    const double t4 = fma(2.0 * t2, t2, -1.0);
+    const int n = P.n_coeff;
+    double p = 0.0;
+    for (int k = n - 1; k >= 1; --k) p = fma(p, y, fma(P.eljb_cb[k], t4, fma(P.eljb_ca[k], t2, P.coeff[k])));
+    const double w1 = fma(P.eljb_cb[0], t4, fma(P.eljb_ca[0], t2, P.coeff[0]));
+    const double s = (x * x * x) * fma(x, p, w1);
+    return r2 >= 5.30 ? s : 0.1;
 }
 
 // NC = 6: the six-coefficient form of every BASELINE script, fully unrolled; NC = 0: runtime n_coeff

@@ -47,6 +47,7 @@ class SweepConfig:
     pot_kind: int = abi.POT_ELJ_EVEN
     coeff: tuple = ()
     eam: tuple = (0.0, 0.0, 0.0, 0.0)  # n, m, ean, eCam
+    eljb_ab: tuple | None = None       # ELJPotentialB: (coeff_a, coeff_b); coeff_c in `coeff`
     runner: RunnerParams | None = None
     bc_kind: int = abi.BC_SPHERICAL
     ensemble: int = abi.ENS_NVT
@@ -96,6 +97,13 @@ class SweepConfig:
             raise ValueError("betas must have n_traj entries")
         self._keep = [betas]
         c.betas = betas.ctypes.data_as(C.POINTER(C.c_double))
+        if self.eljb_ab is not None:
+            ea, eb = (np.ascontiguousarray(v, dtype=np.float64) for v in self.eljb_ab)
+            if ea.shape != (len(self.coeff),) or eb.shape != (len(self.coeff),):
+                raise ValueError("ELJPotentialB needs coeff_a, coeff_b, coeff_c of equal length")
+            self._keep += [ea, eb]
+            c.eljb_a = ea.ctypes.data_as(C.POINTER(C.c_double))
+            c.eljb_b = eb.ctypes.data_as(C.POINTER(C.c_double))
         if self.runner is not None:
             r = self.runner
             d = abi.RunnerDesc()

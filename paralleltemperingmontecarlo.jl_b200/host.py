@@ -195,6 +195,16 @@ class ELJPotentialEven:
     kind = abi.POT_ELJ_EVEN
 
 
+@dataclass(frozen=True)
+class ELJPotentialB:
+    """src/EnergyEvaluation.jl:909-921, dimer_energy :943-958: extended Lennard-Jones in a magnetic field,
+    sum_i c_i r^-k_i (1 + a_i cos 2theta + b_i cos 4theta), theta = angle of the pair to the z axis."""
+    coeff_a: tuple
+    coeff_b: tuple
+    coeff_c: tuple
+    kind = abi.POT_ELJ_B
+
+
 class EmbeddedAtomPotential:
     """src/EnergyEvaluation.jl:1059-1073: EmbeddedAtomPotential(n, m, eps, C, a)"""
     kind = abi.POT_EAM
@@ -245,6 +255,9 @@ def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, e
         kw.update(n_volume_moves=ensemble.n_volume_moves, pressure=ensemble.pressure)
     if potential.kind in (abi.POT_ELJ, abi.POT_ELJ_EVEN):
         kw["coeff"] = tuple(potential.coeff)
+    elif potential.kind == abi.POT_ELJ_B:
+        kw["coeff"] = tuple(potential.coeff_c)
+        kw["eljb_ab"] = (tuple(potential.coeff_a), tuple(potential.coeff_b))
     elif potential.kind == abi.POT_EAM:
         kw["eam"] = (potential.n, potential.m, potential.ean, potential.eCam)
     else:
@@ -462,6 +475,20 @@ def deck_ne13(n_traj=32, cycles=1000):
     pos = _geom("ne13") * a2b
     start = Config(pos, SphericalBC(radius=5.32 * a2b))
     return MCParams(cycles, n_traj, 13), TempGrid(4.0, 16.0, n_traj), start, ELJPotentialEven(ELJ_NE_COEFF), NVT(13)
+
+
+# scripts/ne13_B.jl:40-44 (also ne38_B.jl, ne51_B.jl, ne55.jl): neon in a magnetic field
+ELJB_NE_A = (0.0005742, -0.4032, -0.2101, -0.0595, 0.0606, 0.1608)
+ELJB_NE_B = (-0.01336, -0.02005, -0.1051, -0.1268, -0.1405, -0.1751)
+ELJB_NE_C = (-0.1132, -1.5012, 35.6955, -268.7494, 729.7605, -583.4203)
+
+
+def deck_ne13_B(n_traj=16, cycles=1000):
+    """scripts/ne13_B.jl: Ne13 with ELJPotentialB, NVT, 16 temperatures 9-16 K; the script works in Angstrom
+    (positions :46-60 unconverted :64-66, SphericalBC(radius=5.32) :72)."""
+    mcp, _, _, _, ens = deck_ne13(n_traj, cycles)
+    start = Config(_geom("ne13"), SphericalBC(radius=5.32))
+    return mcp, TempGrid(9.0, 16.0, n_traj), start, ELJPotentialB(ELJB_NE_A, ELJB_NE_B, ELJB_NE_C), ens
 
 
 def deck_ne55(n_traj=24, cycles=1000):

@@ -519,3 +519,24 @@ def test_forward_all_ones_kat():
     ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
     lib.forward(dp(x), i32(88), i32(4), ip(nodes), i32(2), i32(npar), dp(params), ip(act), dp(e))
     assert np.allclose(e, 21.0, rtol=1e-14)
+
+
+def test_eljb_magnetic_field_potential(oracle):
+    # ELJPotentialB (src/EnergyEvaluation.jl:943-958), SphericalBC / NVT as scripts/ne13_B.jl: the device takes cos 2theta from
+    # the positions (2 dz^2 / r^2 - 1) where the reference keeps a tangent matrix; replayed streams -> same decisions, delta
+    # energies to 1e-10; production streams -> identical trajectory
+    mcp, temp, start, pot, ens = P.host.deck_ne13_B(n_traj=8, cycles=40)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=40, seed=17)
+    compare_traces(gpu, cpu)
+    assert 0.05 < gpu["trace"]["accepted"].mean() < 0.999
+    res = _free_run_pair(P.host.deck_ne13_B(n_traj=16, cycles=60), 3, 23, abi.RNG_BATCH8, 60, bounds=(-0.02, 0.0))
+    _assert_same_trajectory(res, e_rtol=1e-10)
+    # energy bookkeeping: running en_tot == energy recomputed from the final positions by a fresh handle
+    (sg, _, _), _ = res
+    cfg = sweep_config(*P.host.deck_ne13_B(n_traj=16, cycles=60), n_ladders=3, seed=1)
+    eng = Engine(cfg)
+    eng.upload_states(sg["pos"], sg["box"])
+    np.testing.assert_allclose(eng.download_states(("en_tot",))["en_tot"], sg["en_tot"], rtol=1e-11)
+    eng.close()
+    with pytest.raises(PtmcError):          # periodic / NPT ELJB is outside the hot path: refused, not approximated
+        Engine(sweep_config(P.MCParams(10, 4, 32), P.TempGrid(20.0, 40.0, 4), _small_pbc(P.CubicBC), pot, P.NVT(32)))

@@ -125,3 +125,25 @@ def test_lrc_matches_closed_form(oracle):
         rc3 *= rc2
     ref *= math.pi * 216 ** 2 / 4 / rc ** 3
     assert got == pytest.approx(ref, rel=1e-14)
+
+
+def test_eljb_rhombic_three_atom_energy(oracle):
+    # test/separated_v_test.jl:90-113: ELJPotentialB, RhombicBC(10, 10), NPT -> tan_mat[1,2], tan_mat[1,3] and
+    # state.en_tot == -0.00016263185592172208 (pair energies within r_cut = min(3/16 L^2, h^2/4) + lrc * 3/4 * L/h,
+    # src/EnergyEvaluation.jl:519-543)
+    from ptmc_b200 import abi
+    from ptmc_b200.host import ELJB_NE_A, ELJB_NE_B, ELJB_NE_C
+    v = [np.array([1.0, 2.0, 3.0]), np.array([2.0, 4.0, 6.0]), np.array([0.0, 1.0, 0.0])]
+    L = h = 10.0
+    t12 = oracle.get_tan(abi.BC_RHOMBIC, v[0], v[1], L, h)
+    t13 = oracle.get_tan(abi.BC_RHOMBIC, v[0], v[2], L, h)
+    assert t12 == pytest.approx(0.7453559924999299, rel=1e-15) and t13 == pytest.approx(0.47140452079103173, rel=1e-15)
+    r_cut = oracle.get_r_cut(abi.BC_RHOMBIC, L, h)
+    e = 0.0
+    for i in range(3):
+        for j in range(i + 1, 3):
+            d2 = oracle.distance2(abi.BC_RHOMBIC, v[i], v[j], L, h)
+            if d2 <= r_cut:
+                e += oracle.dimer_energy_eljb(ELJB_NE_A, ELJB_NE_B, ELJB_NE_C, d2, oracle.get_tan(abi.BC_RHOMBIC, v[i], v[j], L, h))
+    e = e + oracle.lrc_eljb(3, r_cut) * 3 / 4 * L / h
+    assert e == -0.00016263185592172208
