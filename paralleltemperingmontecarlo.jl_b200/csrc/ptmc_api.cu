@@ -282,7 +282,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         case PTMC_POT_RUNNER:
             if (!c->runner) return fail(nullptr, PTMC_ERR_ARG, "pot_kind RUNNER needs ptmc_config.runner");
             if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
-            if (c->n_atoms > RN_THREADS / RN_SUB) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential sweep handles up to %d atoms", RN_THREADS / RN_SUB);
+            if (c->n_atoms > RN_MAX_ATOMS) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential sweep handles up to %d atoms", RN_MAX_ATOMS);
             break;
         default: return fail(nullptr, PTMC_ERR_ARG, "unknown potential %d", c->pot_kind);
     }

@@ -10,8 +10,12 @@ constexpr int RN_MAX_ANG = 32;     // evaluated angular functions (type 111)
 constexpr int RN_MAX_ETA = 8;      // distinct eta among the evaluated angular functions
 constexpr int RN_MAX_LZ = 8;       // distinct (lambda, zeta) among them
 constexpr int RN_MAX_HID = 32;     // nodes per hidden layer
-constexpr int RN_THREADS = 256;    // one CTA = one replica (512 threads / 128 registers measured 4 % slower)
+#ifndef PTMC_RN_THREADS
+#define PTMC_RN_THREADS 384
+#endif
+constexpr int RN_THREADS = PTMC_RN_THREADS;   // one CTA = one replica: 7 warps on the centre-j terms, 5 on the centre-i terms (N = 55)
 constexpr int RN_SUB = 4;          // threads sharing one atom j in the angular update
+constexpr int RN_MAX_ATOMS = (RN_THREADS / 32 - 2) * 32 / RN_SUB;   // at least two warps stay with the centre-i terms
 
 // Only symmetry functions of type 11 / 111 are ever evaluated (DeltaMatrix.jl:803,840, SymmFunc.jl:261,281); the rows
 // of all others stay exactly 0 for ever and contribute exactly 0 to the first network layer, so the device keeps a

@@ -427,6 +427,10 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
             for (int e = 0; e < RN_MAX_ETA; ++e)
 #pragma unroll
                 for (int z = 0; z < RN_MAX_LZ; ++z) acc[e][z] = 0.0;
+            // The two passes are independent and run side by side: the first nwa warps take the centre-j terms (pass A), the
+            // remaining warps the centre-i terms (pass B); N = 55: 7 warps x 13 k-iterations next to 5 warps x 10 pair iterations.
+            const int nwa = (N * RN_SUB + 31) >> 5;
+            if (warp < nwa) {
             // ---- pass A: centre j, thread (j, s) takes k = s, s + RN_SUB, ...
             const int j = tid / RN_SUB, s = tid % RN_SUB;
             const bool jok = j < N && j != i;
@@ -461,10 +465,10 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                         for (int m = 1; m < RN_SUB; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
                         const int q = R.qmap[e * RN_MAX_LZ + z];
                         if (s == 0 && jok) ng[j * R.n_act + R.n_act_rad + q] = g[j * R.n_act + R.n_act_rad + q] + v * R.ang_tpz[q];
-                        acc[e][z] = 0.0;
                     }
-            // ---- pass B: centre i, the pairs (j < k) dealt round-robin to all threads
-            for (int p = tid; p < NT; p += RN_THREADS) {
+            } else {
+            // ---- pass B: centre i, the pairs (j < k) dealt round-robin to the threads of the remaining warps
+            for (int p = tid - 32 * nwa; p < NT; p += RN_THREADS - 32 * nwa) {
                 const int jk = ptab[p], pj = jk >> 16, pk = jk & 0xffff;
                 if (pj == i || pk == i) continue;
                 const double c = D2[p];
@@ -490,10 +494,11 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                         const double w = group_sum<32>(acc[e][z], 0xffffffffu);
                         if (lane == 0) red[warp * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + R.qmap[e * RN_MAX_LZ + z]] = w;
                     }
+            }
             __syncthreads();
             if (tid < R.n_act_ang) {
                 double v = 0.0;
-                for (int w = 0; w < RN_THREADS / 32; ++w) v += red[w * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + tid];
+                for (int w = nwa; w < RN_THREADS / 32; ++w) v += red[w * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + tid];
                 ng[i * R.n_act + R.n_act_rad + tid] = g[i * R.n_act + R.n_act_rad + tid] + v * R.ang_tpz[tid];
             }
             __syncthreads();
