@@ -119,52 +119,56 @@ __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
     return s;
 }
 
+// D (8 x 8, FP64) += A (8 x 4, row) * B (4 x 8, col) on the tensor cores (DMMA; tcgen05 has no f64 kind).  Lane l holds
+// A[l / 4][l % 4], B[l % 4][l / 4] and D[l / 4][2 (l % 4) + {0, 1}].
+__device__ __forceinline__ void rn_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// One dense layer for all atoms: out[a][o] = act(b[o] + sum_r W[o][r] in[a][r]) as (n_out x n_in) * (n_in x N) tiles of
+// 8 output nodes x 8 atoms, one tile per warp and round, k in steps of 4.  W is column-major [r * n_out + o].
+__device__ __forceinline__ void rn_layer_dmma(const double* W, const double* b, int n_out, int n_in, int act, const double* in, int in_stride,
+                                              double* out, int N) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const int mt = (n_out + 7) >> 3, nt = (N + 7) >> 3, kt = (n_in + 3) >> 2;
+    for (int t = warp; t < mt * nt; t += RN_THREADS / 32) {
+        const int m = t % mt, n = t / mt;
+        const int o = 8 * m + gid, ab = 8 * n + gid;
+        const bool ok_o = o < n_out, ok_a = ab < N;
+        double d0 = ok_o ? b[o] : 0.0, d1 = d0;
+        const double* wp = W + (ok_o ? o : 0);
+        const double* ip = in + (ok_a ? ab : 0) * in_stride;
+        for (int k = 0; k < kt; ++k) {
+            const int r = 4 * k + tig;
+            const bool ok_r = r < n_in;
+            const double av = (ok_o && ok_r) ? wp[r * n_out] : 0.0;
+            const double bv = (ok_a && ok_r) ? ip[r] : 0.0;
+            rn_dmma(d0, d1, av, bv);
+        }
+        const int a0 = 8 * n + 2 * tig;
+        if (ok_o) {
+            if (a0 < N) out[a0 * n_out + o] = rn_act(d0, act);
+            if (a0 + 1 < N) out[(a0 + 1) * n_out + o] = rn_act(d1, act);
+        }
+    }
+}
 // Network forward pass for all atoms on the compact g matrix in shared memory (SURVEY A.2 semantics).
 // Returns, in every thread, the sum of the per-atom energies (calc_new_runner_energy! :1269-1275).
-// Thread (a, q) = (tid / RN_SUB, tid % RN_SUB) computes a contiguous block of output nodes of atom a in every layer; the
-// RN_SUB lanes of an atom sit in one warp, so the layers are separated by __syncwarp() only and the last layer is a shuffle
-// reduction over the lanes' own hidden values.
-constexpr int RN_MAX_OPT = (RN_MAX_HID + RN_SUB - 1) / RN_SUB;      // output nodes per thread and layer
+// The two hidden layers are FP64 tensor-core GEMMs (rn_layer_dmma); the output node is a dot product split over the RN_SUB
+// lanes of an atom.
 __device__ double rn_forward(const RunnerDev& R, int N, const double* g, const double* net, double* h1, double* h2, double* eatom,
                              double* red) {
     const int tid = threadIdx.x;
     const double* W1 = net; const double* b1 = W1 + R.h1 * R.n_act;
     const double* W2 = b1 + R.h1; const double* b2 = W2 + R.h2 * R.h1;
     const double* W3 = b2 + R.h2; const double* b3 = W3 + R.h2;
+    rn_layer_dmma(W1, b1, R.h1, R.n_act, R.act1, g, R.n_act, h1, N);
+    __syncthreads();
+    rn_layer_dmma(W2, b2, R.h2, R.h1, R.act2, h1, R.h1, h2, N);
+    __syncthreads();
     const int a = tid / RN_SUB, q = tid % RN_SUB;
     const bool on = a < N;
-    const int aa = on ? a : 0;
-    const int n1 = (R.h1 + RN_SUB - 1) / RN_SUB, n2 = (R.h2 + RN_SUB - 1) / RN_SUB;
-    const int o1 = q * n1, o2 = q * n2;
-    double z[RN_MAX_OPT];
-    {
-#pragma unroll
-        for (int m = 0; m < RN_MAX_OPT; ++m) z[m] = (m < n1 && o1 + m < R.h1) ? b1[o1 + m] : 0.0;
-        const double* x = g + aa * R.n_act;
-        for (int r = 0; r < R.n_act; ++r) {
-            const double xr = x[r];
-            const double* w = W1 + o1 + r * R.h1;
-#pragma unroll
-            for (int m = 0; m < RN_MAX_OPT; ++m) if (m < n1 && o1 + m < R.h1) z[m] = fma(w[m], xr, z[m]);
-        }
-#pragma unroll
-        for (int m = 0; m < RN_MAX_OPT; ++m) if (on && m < n1 && o1 + m < R.h1) h1[aa * R.h1 + o1 + m] = rn_act(z[m], R.act1);
-    }
-    __syncwarp();
-    {
-#pragma unroll
-        for (int m = 0; m < RN_MAX_OPT; ++m) z[m] = (m < n2 && o2 + m < R.h2) ? b2[o2 + m] : 0.0;
-        const double* x = h1 + aa * R.h1;
-        for (int r = 0; r < R.h1; ++r) {
-            const double xr = x[r];
-            const double* w = W2 + o2 + r * R.h2;
-#pragma unroll
-            for (int m = 0; m < RN_MAX_OPT; ++m) if (m < n2 && o2 + m < R.h2) z[m] = fma(w[m], xr, z[m]);
-        }
-    }
     double part = 0.0;
-#pragma unroll
-    for (int m = 0; m < RN_MAX_OPT; ++m) if (m < n2 && o2 + m < R.h2) part = fma(W3[o2 + m], rn_act(z[m], R.act2), part);
+    if (on) for (int o = q; o < R.h2; o += RN_SUB) part = fma(W3[o], h2[a * R.h2 + o], part);
 #pragma unroll
     for (int m = 1; m < RN_SUB; m <<= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
     double e = 0.0;
@@ -172,7 +176,6 @@ __device__ double rn_forward(const RunnerDev& R, int N, const double* g, const d
         e = rn_act(part + b3[0], R.act3);
         eatom[a] = e;
     }
-    (void)h2;
     e = group_sum<32>(e, 0xffffffffu);
     if ((tid & 31) == 0) red[tid >> 5] = e;
     __syncthreads();
