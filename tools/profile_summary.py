@@ -27,7 +27,9 @@ KEYS = [
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe (MUFU, conversions)"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe"),
     ("sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active", "ADU pipe"),
-    ("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "tensor pipe"),
+    ("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "tcgen05 tensor pipe"),
+    ("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "FP64 tensor sub-pipe (DMMA)"),
+    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe cycles active (all sub-pipes)"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput"),
     ("dram__bytes_read.sum", "DRAM bytes read"),
     ("dram__bytes_write.sum", "DRAM bytes written"),
