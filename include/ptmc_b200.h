@@ -194,6 +194,17 @@ PTMC_API int ptmc_set_hist_bounds(ptmc_handle* h, const double* en_min, const do
  * 10-argument method with sampling_step! (src/Sampling.jl:330-371).  Asynchronous on the handle's
  * stream; errors raised inside the kernel surface at the next ptmc_sync / download. */
 PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64_t n_cycles, int sample);
+/* The same with mc_cycle! split at the exchange, for a ladder whose temperatures are spread over several handles / GPUs
+ * (SURVEY §8e): phase 1 = mc_step! only (src/MCRun.jl:197-202), phase 2 = update_max_stepsize! + sampling_step! only
+ * (:206-212, :248-250), phase 0 = ptmc_run_cycles.  Between phase 1 and phase 2 of a cycle the host performs
+ * parallel_tempering_exchange! (src/Exchange.jl:132-155) on the energies of all handles and moves configurations with
+ * ptmc_export_config / ptmc_import_config; the handle's own exchange step and ladder stream are not touched. */
+PTMC_API int ptmc_run_phase(ptmc_handle* h, int64_t first_idx, int64_t n_cycles, int sample, int phase);
+/* What exc_trajectories! (src/Exchange.jl:115-124) swaps, for one slot of a SphericalBC handle: buf holds
+ * ptmc_config_doubles(h) doubles = positions [N][3], box[2], en_tot, EAM components [N][2]. */
+PTMC_API int64_t ptmc_config_doubles(const ptmc_handle* h);
+PTMC_API int ptmc_export_config(ptmc_handle* h, int64_t ladder, int32_t slot, double* buf);
+PTMC_API int ptmc_import_config(ptmc_handle* h, int64_t ladder, int32_t slot, const double* buf);
 /* Wait for the stream and report in-kernel errors (PTMC_ERR_SPHERE, PTMC_ERR_REPLAY). */
 PTMC_API int ptmc_sync(ptmc_handle* h);
 

@@ -52,6 +52,10 @@ def load():
         "orc_set_replay": (C.c_int, [_vp, _u64p, C.c_int64, _u64p, C.c_int64]),
         "orc_set_hist_bounds": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_int]),
         "orc_run_cycles": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int]),
+        "orc_run_phase": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+        "orc_config_doubles": (C.c_int64, [_vp]),
+        "orc_export_config": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp]),
+        "orc_import_config": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp]),
         "orc_trace_enable": (C.c_int, [_vp, C.c_int64]),
         "orc_trace_download": (C.c_int, [_vp, _ip, _dp, _u8p, _ip, _i64p]),
         "orc_download_states": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _i64p, _dp]),

@@ -743,13 +743,14 @@ static double exc_acceptance(double b1, double b2, double e1, double e2) {
 }
 
 /* mc_cycle! src/MCRun.jl:192-253 for one ladder.  par != 0: thread over replicas like :176. */
-static int mc_cycle(orc_handle* H, int64_t lad, int64_t idx, int sample, int64_t tr_cycle, int par) {
+/* phase (ptmc_run_phase): 0 whole cycle, 1 mc_step! only, 2 step-size adaptation + sampling only */
+static int mc_cycle(orc_handle* H, int64_t lad, int64_t idx, int sample, int64_t tr_cycle, int par, int phase) {
     const ptmc_config* c = &H->cfg;
     const int nt = c->n_traj, ns = n_steps_of(c);
     int err = 0;
     /* mc_step! :169-182 */
 #pragma omp parallel for schedule(static) if (par) reduction(min : err)
-    for (int t = 0; t < nt; ++t) {
+    for (int t = 0; t < (phase == 2 ? 0 : nt); ++t) {
         orc_state* st = &H->st[lad * nt + t];
         for (int k = 0; k < ns; ++k) {
             int32_t* ti = NULL; double* td = NULL; uint8_t* ta = NULL;
@@ -766,7 +767,7 @@ static int mc_cycle(orc_handle* H, int64_t lad, int64_t idx, int sample, int64_t
     /* :203-205 exchange, driver-task RNG */
     orc_rng* lr = &H->lrng[lad];
     int32_t ex_gate = 0, ex_n = 0, ex_acc = 0;
-    if (rng_rand(lr) < 0.1) {
+    if (phase == 0 && rng_rand(lr) < 0.1) {
         ex_gate = 1;
         /* parallel_tempering_exchange! src/Exchange.jl:132-186 */
         int n_exc = (int)rng_range(lr, (uint64_t)(nt - 1));
@@ -790,6 +791,7 @@ static int mc_cycle(orc_handle* H, int64_t lad, int64_t idx, int sample, int64_t
         int32_t* e = H->tr_exc + ((size_t)lad * H->trace_cap + tr_cycle) * 3;
         e[0] = ex_gate; e[1] = ex_n; e[2] = ex_acc;
     }
+    if (phase == 1) return 0;
     /* :206-212 */
     if (idx % c->n_adjust == 0)
         for (int t = 0; t < nt; ++t) update_max_stepsize(c, &H->st[lad * nt + t]);
@@ -999,8 +1001,11 @@ int orc_trace_download(orc_handle* H, int32_t* move_index, double* delta_en, uin
     return 0;
 }
 
-int orc_run_cycles(orc_handle* H, int64_t first_idx, int64_t n_cycles, int sample) {
+int orc_run_phase(orc_handle* H, int64_t first_idx, int64_t n_cycles, int sample, int phase);
+int orc_run_cycles(orc_handle* H, int64_t first_idx, int64_t n_cycles, int sample) { return orc_run_phase(H, first_idx, n_cycles, sample, 0); }
+int orc_run_phase(orc_handle* H, int64_t first_idx, int64_t n_cycles, int sample, int phase) {
     if (sample && !H->hist_ready) return PTMC_ERR_STATE;
+    if (phase < 0 || phase > 2 || (phase && H->trace_cap > 0)) return PTMC_ERR_ARG;
     const int64_t nl = H->cfg.n_ladders;
     int err = 0;
     int64_t tr0 = H->trace_n;
@@ -1011,7 +1016,7 @@ int orc_run_cycles(orc_handle* H, int64_t first_idx, int64_t n_cycles, int sampl
 #pragma omp parallel for schedule(dynamic) num_threads(H->n_threads) reduction(min : err)
         for (int64_t l = 0; l < nl; ++l) {
             for (int64_t k = 0; k < n_cycles; ++k) {
-                int e = mc_cycle(H, l, first_idx + k, sample, tracing ? tr0 + k : -1, 0);
+                int e = mc_cycle(H, l, first_idx + k, sample, tracing ? tr0 + k : -1, 0, phase);
                 if (e < err) err = e;
                 if (e) break;
             }
@@ -1022,7 +1027,7 @@ int orc_run_cycles(orc_handle* H, int64_t first_idx, int64_t n_cycles, int sampl
 #endif
         for (int64_t k = 0; k < n_cycles && !err; ++k)
             for (int64_t l = 0; l < nl && !err; ++l)
-                err = mc_cycle(H, l, first_idx + k, sample, tracing ? tr0 + k : -1, H->n_threads > 1);
+                err = mc_cycle(H, l, first_idx + k, sample, tracing ? tr0 + k : -1, H->n_threads > 1, phase);
     }
     if (tracing) H->trace_n += n_cycles;
     H->error = err;
@@ -1040,6 +1045,39 @@ int orc_download_states(orc_handle* H, double* pos, double* box, double* en_tot,
         if (counters) memcpy(counters + r * PTMC_NCOUNT, st->count, sizeof(int64_t) * PTMC_NCOUNT);
         if (ham) { ham[2 * r] = st->ham[0]; ham[2 * r + 1] = st->ham[1]; }
     }
+    return 0;
+}
+/* ptmc_config_doubles / ptmc_export_config / ptmc_import_config: what exc_trajectories! moves (SphericalBC handles) */
+int64_t orc_config_doubles(const orc_handle* H) {
+    const int64_t n = H->cfg.n_atoms;
+    return 3 * n + 3 + (H->cfg.pot_kind == PTMC_POT_EAM ? 2 * n : 0);
+}
+int orc_export_config(orc_handle* H, int64_t ladder, int32_t slot, double* buf) {
+    if (H->cfg.bc_kind != PTMC_BC_SPHERICAL || H->cfg.pot_kind == PTMC_POT_RUNNER) return PTMC_ERR_ARG;
+    const int n = H->cfg.n_atoms;
+    const orc_cfgside* s = H->st[ladder * H->cfg.n_traj + slot].c;
+    memcpy(buf, s->pos, sizeof(double) * 3 * n);
+    buf[3 * n] = s->box[0]; buf[3 * n + 1] = s->box[1]; buf[3 * n + 2] = s->en_tot;
+    if (H->cfg.pot_kind == PTMC_POT_EAM) memcpy(buf + 3 * n + 3, s->comp, sizeof(double) * 2 * n);
+    return 0;
+}
+int orc_import_config(orc_handle* H, int64_t ladder, int32_t slot, const double* buf) {
+    if (H->cfg.bc_kind != PTMC_BC_SPHERICAL || H->cfg.pot_kind == PTMC_POT_RUNNER) return PTMC_ERR_ARG;
+    const ptmc_config* c = &H->cfg;
+    const int n = c->n_atoms;
+    orc_cfgside* s = H->st[ladder * c->n_traj + slot].c;
+    memcpy(s->pos, buf, sizeof(double) * 3 * n);
+    s->box[0] = buf[3 * n]; s->box[1] = buf[3 * n + 1];
+    /* derived matrices are functions of the positions alone in free space (distance2 and get_tan are symmetric bit for bit) */
+    d2_matrix(c, s->pos, s->box, s->d2, n);
+    if (c->pot_kind == PTMC_POT_ELJ_B) {
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j)
+                s->tan[(size_t)i * n + j] = s->tan[(size_t)j * n + i] = orc_get_tan(c->bc_kind, s->pos + 3 * i, s->pos + 3 * j, s->box[0], s->box[1]);
+        for (int i = 0; i < n; ++i) s->tan[(size_t)i * n + i] = 0;
+    }
+    s->en_tot = buf[3 * n + 2];
+    if (c->pot_kind == PTMC_POT_EAM) memcpy(s->comp, buf + 3 * n + 3, sizeof(double) * 2 * n);
     return 0;
 }
 int orc_download_hist(orc_handle* H, double* en_hist, double* ev_hist, int reduce_ladders) {

@@ -81,6 +81,10 @@ SYMBOLS = {
     "ptmc_set_replay": (C.c_int, [_vp, _u64p, C.c_int64, _u64p, C.c_int64]),
     "ptmc_set_hist_bounds": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_int]),
     "ptmc_run_cycles": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int]),
+    "ptmc_run_phase": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "ptmc_config_doubles": (C.c_int64, [_vp]),
+    "ptmc_export_config": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp]),
+    "ptmc_import_config": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp]),
     "ptmc_sync": (C.c_int, [_vp]),
     "ptmc_trace_enable": (C.c_int, [_vp, C.c_int64]),
     "ptmc_trace_download": (C.c_int, [_vp, _ip, _dp, _u8p, _ip, _i64p]),

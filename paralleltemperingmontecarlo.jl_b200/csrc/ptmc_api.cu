@@ -541,7 +541,14 @@ extern "C" PTMC_API int ptmc_set_hist_bounds(ptmc_handle* h, const double* en_mi
 
 // -------------------------------------------------------------------------------------- the hot path --
 extern "C" PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64_t n_cycles, int sample) {
+    return ptmc_run_phase(h, first_idx, n_cycles, sample, 0);
+}
+
+extern "C" PTMC_API int ptmc_run_phase(ptmc_handle* h, int64_t first_idx, int64_t n_cycles, int sample, int phase) {
     if (!h) return PTMC_ERR_ARG;
+    if (phase < 0 || phase > 2) return fail(h, PTMC_ERR_ARG, "phase must be 0 (whole cycle), 1 (moves) or 2 (adaptation + sampling)");
+    if (phase && h->runner) return fail(h, PTMC_ERR_ARG, "split cycles are not built for the RuNNer kernels");
+    if (phase && h->trace_cap > 0) return fail(h, PTMC_ERR_STATE, "tracing records whole cycles only");
     if (!h->uploaded) return fail(h, PTMC_ERR_STATE, "ptmc_run_cycles before ptmc_upload_states");
     if (!h->seeded) return fail(h, PTMC_ERR_STATE, "no random stream: call ptmc_seed / ptmc_set_rng_states / ptmc_set_replay");
     if (sample && !h->hist_ready) return fail(h, PTMC_ERR_STATE, "sampling before ptmc_set_hist_bounds");
@@ -572,6 +579,7 @@ extern "C" PTMC_API int ptmc_run_cycles(ptmc_handle* h, int64_t first_idx, int64
     while (done < n_cycles) {
         const i64 k = std::min(max_chunk, n_cycles - done);
         DevParams P = h->P;
+        P.phase = phase;
         P.trace_cap = h->trace_cap; P.trace_base = h->trace_n;
         P.tr_index = static_cast<int32_t*>(h->d_trace[0]); P.tr_de = static_cast<double*>(h->d_trace[1]);
         P.tr_acc = static_cast<uint8_t*>(h->d_trace[2]); P.tr_exc = static_cast<int32_t*>(h->d_trace[3]);
@@ -676,6 +684,35 @@ extern "C" PTMC_API int ptmc_download_hist(ptmc_handle* h, double* en_hist, doub
     CU(h, cudaMemcpy(tmp.data(), src, n * sizeof(u64), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) dst[i] = (double)tmp[i];   // Output.en_histogram holds Float64 counts
     return PTMC_OK;
+}
+
+// ------------------------------------------------------------------------ configurations in and out --
+// everything exc_trajectories! (src/Exchange.jl:115-124) moves between two slots, for SphericalBC handles:
+// positions [N][3], box[2], en_tot, and the EAM components [N][2]
+extern "C" PTMC_API int64_t ptmc_config_doubles(const ptmc_handle* h) {
+    if (!h) return 0;
+    const int64_t N = h->cfg.n_atoms;
+    return 3 * N + 3 + (h->cfg.pot_kind == PTMC_POT_EAM ? 2 * N : 0);
+}
+static int config_io(ptmc_handle* h, int64_t ladder, int32_t slot, double* buf, bool out) {
+    if (!h || !buf) return PTMC_ERR_ARG;
+    if (!h->uploaded) return fail(h, PTMC_ERR_STATE, "no states uploaded");
+    if (h->runner || h->cfg.bc_kind != PTMC_BC_SPHERICAL) return fail(h, PTMC_ERR_ARG, "configuration export / import is built for the SphericalBC sweep kernels");
+    if (ladder < 0 || ladder >= h->cfg.n_ladders || slot < 0 || slot >= h->cfg.n_traj) return fail(h, PTMC_ERR_ARG, "ladder / slot out of range");
+    TRY(ptmc_sync(h));
+    const size_t N = (size_t)h->cfg.n_atoms, rep = (size_t)ladder * h->cfg.n_traj + slot;
+    const DevParams& P = h->P;
+    const cudaMemcpyKind kind = out ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+    auto cp = [&](double* dev, double* host, size_t n) { return out ? cudaMemcpy(host, dev, n * sizeof(double), kind) : cudaMemcpy(dev, host, n * sizeof(double), kind); };
+    CU(h, cp(P.pos + rep * 3 * N, buf, 3 * N));
+    CU(h, cp(P.box + rep * 2, buf + 3 * N, 2));
+    CU(h, cp(P.en_tot + rep, buf + 3 * N + 2, 1));
+    if (h->cfg.pot_kind == PTMC_POT_EAM) CU(h, cp(P.comp + rep * 2 * N, buf + 3 * N + 3, 2 * N));
+    return PTMC_OK;
+}
+extern "C" PTMC_API int ptmc_export_config(ptmc_handle* h, int64_t ladder, int32_t slot, double* buf) { return config_io(h, ladder, slot, buf, true); }
+extern "C" PTMC_API int ptmc_import_config(ptmc_handle* h, int64_t ladder, int32_t slot, const double* buf) {
+    return config_io(h, ladder, slot, const_cast<double*>(buf), false);
 }
 
 // ----------------------------------------------------------------------------------------------- rdf --

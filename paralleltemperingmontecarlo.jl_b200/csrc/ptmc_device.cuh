@@ -36,6 +36,7 @@ struct DevParams {
     int ensemble, bc_kind, pot_kind, n_coeff;
     int n_adjust, mc_sample, n_bin;
     int replay;                          // 1: consume pre-drawn draws
+    int phase;                           // ptmc_run_phase: 0 whole mc_cycle!, 1 mc_step! only, 2 step-size adaptation + sampling only
     double min_acc, max_acc, pressure;
     double coeff[PTMC_MAX_COEFF];
     double eljb_ca[PTMC_MAX_COEFF], eljb_cb[PTMC_MAX_COEFF];   // ELJPotentialB: c_i a_i, c_i b_i (c_i in coeff[])

@@ -154,8 +154,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     const bool tracing = DBG && P.trace_cap > 0;
     int err = 0;
 
+    // P.phase splits mc_cycle! at the exchange (a ladder that spans GPUs exchanges on the host, ptmc_run_phase)
+    const int phase = P.phase;
     for (i64 cyc = 0; cyc < n_cycles; ++cyc) {
-        if (active) {
+        if (active && phase != 2) {
             // ================================================================== mc_step! for this slot ==
             const int c = perm[slot];
             double* X = sm + (size_t)c * lay.cfg_stride;
@@ -485,7 +487,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
         __syncwarp();
         int ex_gate = 0, ex_n = 0;
         double ex_u = 0.0;
-        if ((tid & 31) == 0) {
+        if (phase == 0 && (tid & 31) == 0) {
             Stream<DBG> LS;
             LS.r.s0 = wl[0]; LS.r.s1 = wl[1]; LS.r.s2 = wl[2]; LS.r.s3 = wl[3];
             LS.draws = nullptr; LS.pos = 0; LS.len = 0; LS.exhausted = 0;
@@ -535,7 +537,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
         } else {
             __syncwarp(gmask);                                      // scal[] of this slot is visible to its group
         }
-        if (active) {
+        if (active && phase != 1) {
             // ------------------------------------------- update_max_stepsize! src/Exchange.jl:198-263
             if (adj_phase == 0) {
                 double rate = xdiv((double)n_adj_atom, (double)((i64)P.n_adjust * P.n_atom_moves));

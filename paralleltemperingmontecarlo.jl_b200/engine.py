@@ -248,6 +248,19 @@ class Engine:
     def run_cycles(self, first_idx: int, n_cycles: int, sample: bool):
         self._check(self._fn("run_cycles")(self._h, first_idx, n_cycles, int(bool(sample))))
 
+    def run_phase(self, first_idx: int, n_cycles: int, sample: bool, phase: int):
+        """mc_cycle! split at the exchange: phase 1 = mc_step! only, 2 = step-size adaptation + sampling only (multi.run_split_ladder)"""
+        self._check(self._fn("run_phase")(self._h, int(first_idx), int(n_cycles), int(bool(sample)), int(phase)))
+
+    def export_config(self, ladder: int, slot: int) -> np.ndarray:
+        buf = np.zeros(int(self._fn("config_doubles")(self._h)))
+        self._check(self._fn("export_config")(self._h, int(ladder), int(slot), _p(buf)))
+        return buf
+
+    def import_config(self, ladder: int, slot: int, buf):
+        buf = _f64(buf, (int(self._fn("config_doubles")(self._h)),))
+        self._check(self._fn("import_config")(self._h, int(ladder), int(slot), _p(buf)))
+
     def sync(self):
         self._check(self._fn("sync")(self._h))
 

@@ -540,3 +540,33 @@ def test_eljb_magnetic_field_potential(oracle):
     eng.close()
     with pytest.raises(PtmcError):          # periodic / NPT ELJB is outside the hot path: refused, not approximated
         Engine(sweep_config(P.MCParams(10, 4, 32), P.TempGrid(20.0, 40.0, 4), _small_pbc(P.CubicBC), pot, P.NVT(32)))
+
+
+@pytest.mark.parametrize("case", ["ne13", "eam", "eljb"])
+def test_split_cycle_phases_equal_whole_cycles(case):
+    # ptmc_run_phase + ptmc_export_config / ptmc_import_config (a ladder that spans GPUs): mc_step! and the tail of
+    # mc_cycle! as separate launches with the exchange done by the host driver give the trajectory of whole cycles on one handle
+    from ptmc_b200 import multi
+    deck = {"ne13": P.host.deck_ne13(n_traj=6, cycles=40), "eam": P.host.deck_cu55_eam(n_traj=4, cycles=12),
+            "eljb": P.host.deck_ne13_B(n_traj=6, cycles=40)}[case]
+    bounds = {"ne13": (-0.0075, -0.0045), "eam": (-10.0, 0.0), "eljb": (-0.02, 0.0)}[case]
+    mcp, temp, start, pot, ens = deck
+    mcp.n_adjust = 10
+    L, seed = 3, 99
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=seed)
+    eng = Engine(cfg)
+    pos, box = initial_arrays(mcp, start, L)
+    eng.upload_states(pos, box)
+    multi.seed_global(eng, seed, 0, L)
+    eng.run_cycles(1, 6, False)
+    eng.reset_counters()
+    eng.set_hist_bounds(*bounds)
+    eng.run_cycles(1, mcp.mc_cycles, True)
+    ref, ref_hist = eng.download_states(), eng.download_hist()
+    eng.close()
+    st, hist, (t0, cnt) = multi.run_split_ladder(mcp, temp, start, pot, ens, n_ladders=L, seed=seed, bounds=bounds, eq_cycles=6)
+    assert (t0, cnt) == (0, mcp.n_traj)
+    assert ref["counters"][:, :, abi.C_EXC_ATT].sum() > 0
+    for k in ("pos", "counters", "max_displ", "en_tot", "ham"):
+        assert np.array_equal(st[k], ref[k]), k
+    assert np.array_equal(hist, ref_hist)
