@@ -58,7 +58,7 @@ typedef enum ptmc_status {
 typedef enum ptmc_pot_kind { PTMC_POT_ELJ = 0, PTMC_POT_ELJ_EVEN = 1, PTMC_POT_EAM = 2, PTMC_POT_RUNNER = 3, PTMC_POT_ELJ_B = 4 } ptmc_pot_kind;
 /* src/BoundaryConditions.jl:44,72,89,110 */
 typedef enum ptmc_bc_kind { PTMC_BC_SPHERICAL = 0, PTMC_BC_CUBIC = 1, PTMC_BC_RHOMBIC = 2, PTMC_BC_RECTANGULAR = 3 } ptmc_bc_kind;
-/* src/Ensembles.jl:42 (NVT), :75 (NPT with separated_volume=false) */
+/* src/Ensembles.jl:42 (NVT), :75 (NPT; separated_volume in ptmc_config) */
 typedef enum ptmc_ens_kind { PTMC_ENS_NVT = 0, PTMC_ENS_NPT = 1 } ptmc_ens_kind;
 typedef enum ptmc_rng_mode {
     PTMC_RNG_XOSHIRO = 0, /* Julia's default RNG as ONE sequential stream per slot: Xoshiro256++,
@@ -77,7 +77,7 @@ typedef enum ptmc_rng_mode {
 typedef enum ptmc_counter {
     PTMC_C_ATOM_TOT = 0, PTMC_C_ATOM_ADJ = 1,   /* count_atom[1], [2] */
     PTMC_C_VOL_TOT = 2, PTMC_C_VOL_ADJ = 3,     /* count_vol[1], [2]  */
-    PTMC_C_VOLXY_TOT = 4, PTMC_C_VOLXY_ADJ = 5, /* count_vol_xy (separated moves: never touched here) */
+    PTMC_C_VOLXY_TOT = 4, PTMC_C_VOLXY_ADJ = 5, /* count_vol_xy (separated volume moves)                 */
     PTMC_C_VOLZ_TOT = 6, PTMC_C_VOLZ_ADJ = 7,   /* count_vol_z                                         */
     PTMC_C_EXC_ATT = 8, PTMC_C_EXC_ACC = 9      /* count_exc[1] (attempts), [2] (accepted)             */
 } ptmc_counter;
@@ -129,7 +129,7 @@ typedef struct ptmc_config {
     double min_acc, max_acc;  /* MCParams.min_acc / max_acc                                          */
     uint64_t seed;            /* base seed: slot stream s gets Random.seed!(seed + s), see ptmc_seed  */
     int32_t lanes_per_replica;/* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one replica       */
-    int32_t reserved;
+    int32_t separated_volume; /* NPT.separated_volume (src/Ensembles.jl:81): volume_change_separated, RhombicBC / RectangularBC */
     /* ABI 2: PTMC_POT_ELJ_B only - coeff_a, coeff_b [n_coeff] (coeff_c travels in coeff[])                */
     const double* eljb_a;
     const double* eljb_b;

@@ -332,6 +332,7 @@ typedef struct orc_state { /* MCState src/MCStates.jl:33-53; slot-side fields st
     double beta;
     double max_displ[4];
     double max_boxlength;
+    double max_boxheight, lh_ratio;   /* src/MCStates.jl:106-107 */
     double ham[2];
     int64_t count[PTMC_NCOUNT];
     double* new_d2;   /* new_dist2_vec */
@@ -637,6 +638,46 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             }
         }
     } else {
+        int xy_or_z = 0;
+        if (c->separated_volume) {
+            /* volume_change_separated src/MCMoves.jl:300-343: z with 1/6, xy with 2/6, all directions with 3/6; the new
+             * distance matrix is recomputed from the trial configuration (get_distance2_mat!) */
+            int ra = bm ? (int)(((__uint128_t)st->rng.buf[2] * 6u) >> 64) + 1 : (int)rng_range(&st->rng, 6);
+            double uv = bm ? rng_batch_rand(&st->rng, 1) : rng_rand(&st->rng);
+            double sxy = 1.0, sz = 1.0;
+            const double lh = s->box[0] / s->box[1];
+            if (ra == 1) {            /* volume_change_z :256-271 */
+                xy_or_z = 2;
+                double scale = exp((uv - 0.5) * st->max_displ[3]);
+                if (lh <= st->lh_ratio * 1.1 && scale > 1.0) scale = 1 / scale;
+                else if (lh >= st->lh_ratio * 0.909 && scale < 1.0) scale = 1 / scale;
+                if (s->box[1] >= st->max_boxheight && scale > 1.0) scale = 1 / scale;
+                sz = scale;
+            } else if (ra <= 3) {     /* volume_change_xy :232-247 */
+                xy_or_z = 1;
+                double scale = pow(exp((uv - 0.5) * st->max_displ[2]), 1.0 / 2.0);
+                if (lh >= st->lh_ratio * 1.1 && scale > 1.0) scale = 1 / scale;
+                else if (lh <= st->lh_ratio * 0.909 && scale < 1.0) scale = 1 / scale;
+                if (s->box[0] >= st->max_boxlength && scale > 1.0) scale = 1 / scale;
+                sxy = scale;
+            } else {                  /* volume_change_xyz :169-177 */
+                double scale = pow(exp((uv - 0.5) * st->max_displ[1]), 1.0 / 3.0);
+                if (s->box[0] >= st->max_boxlength && scale > 1.0) scale = 1.0;
+                sxy = scale; sz = scale;
+            }
+            if (xy_or_z == 0) {
+                for (int k = 0; k < 3 * n; ++k) s->trial_pos[k] = sxy * s->pos[k];
+                s->trial_box[0] = sxy * s->box[0]; s->trial_box[1] = sxy * s->box[1];
+            } else if (xy_or_z == 1) {   /* scale_xy :189-201: p * scale */
+                for (int k = 0; k < n; ++k) { s->trial_pos[3 * k] = s->pos[3 * k] * sxy; s->trial_pos[3 * k + 1] = s->pos[3 * k + 1] * sxy; s->trial_pos[3 * k + 2] = s->pos[3 * k + 2]; }
+                s->trial_box[0] = s->box[0] * sxy; s->trial_box[1] = s->box[1];
+            } else {                     /* scale_z :211-222 */
+                for (int k = 0; k < n; ++k) { s->trial_pos[3 * k] = s->pos[3 * k]; s->trial_pos[3 * k + 1] = s->pos[3 * k + 1]; s->trial_pos[3 * k + 2] = s->pos[3 * k + 2] * sz; }
+                s->trial_box[0] = s->box[0]; s->trial_box[1] = s->box[1] * sz;
+            }
+            s->new_r_cut = orc_get_r_cut(c->bc_kind, s->trial_box[0], s->trial_box[1]);
+            d2_matrix(c, s->trial_pos, s->trial_box, s->new_d2mat, n);
+        } else {
         /* volume_change_uniform src/MCMoves.jl:277-287, volume_change_xyz :169-177 */
         double uv = bm ? rng_batch_rand(&st->rng, 1) : rng_rand(&st->rng);
         double scale = pow(exp((uv - 0.5) * st->max_displ[1]), 1.0 / 3.0);
@@ -647,6 +688,7 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
         s->new_r_cut = orc_get_r_cut(c->bc_kind, s->trial_box[0], s->trial_box[1]);
         double sc2 = scale * scale;
         for (size_t k = 0; k < (size_t)n * n; ++k) s->new_d2mat[k] = s->d2[k] * sc2;
+        }
         /* get_energy! NPT else-branch src/MCRun.jl:76-85 */
         st->new_en = dimer_energy_config(c, s->new_d2mat, n, 1, s->new_r_cut, s->trial_box);
         /* metropolis_condition NPT src/Exchange.jl:58-71,77-85 */
@@ -665,7 +707,9 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             s->box[0] = s->trial_box[0]; s->box[1] = s->trial_box[1];
             memcpy(s->d2, s->new_d2mat, sizeof(double) * (size_t)n * n);
             s->en_tot = st->new_en;
-            st->count[PTMC_C_VOL_TOT] += 1; st->count[PTMC_C_VOL_ADJ] += 1;
+            if (xy_or_z == 0) { st->count[PTMC_C_VOL_TOT] += 1; st->count[PTMC_C_VOL_ADJ] += 1; }
+            else if (xy_or_z == 1) { st->count[PTMC_C_VOLXY_TOT] += 1; st->count[PTMC_C_VOLXY_ADJ] += 1; }
+            else { st->count[PTMC_C_VOLZ_TOT] += 1; st->count[PTMC_C_VOLZ_ADJ] += 1; }
             s->r_cut = s->new_r_cut;
         }
     }
@@ -680,11 +724,26 @@ static void update_max_stepsize(const ptmc_config* c, orc_state* st) {
     if (acc_rate < c->min_acc) st->max_displ[0] *= 0.9;
     else if (acc_rate > c->max_acc) st->max_displ[0] *= 1.1;
     st->count[PTMC_C_ATOM_ADJ] = 0;
-    if (c->ensemble == PTMC_ENS_NPT) {
+    if (c->ensemble == PTMC_ENS_NPT && !c->separated_volume) {
         acc_rate = (double)st->count[PTMC_C_VOL_ADJ] / (double)((int64_t)c->n_adjust * c->n_volume_moves);
         if (acc_rate < c->min_acc) st->max_displ[1] *= 0.9;
         else if (acc_rate > c->max_acc) st->max_displ[1] *= 1.1;
         st->count[PTMC_C_VOL_ADJ] = 0;
+    } else if (c->ensemble == PTMC_ENS_NPT) {
+        /* src/Exchange.jl:221-245: n_update * n_volume_moves * 1 / 2, ... * 1 / 3, ... / 6 (integer product, then Float64 division) */
+        const double nv = (double)((int64_t)c->n_adjust * c->n_volume_moves);
+        acc_rate = (double)st->count[PTMC_C_VOL_ADJ] / (nv / 2);
+        if (acc_rate < c->min_acc) st->max_displ[1] *= 0.9;
+        else if (acc_rate > c->max_acc) st->max_displ[1] *= 1.1;
+        st->count[PTMC_C_VOL_ADJ] = 0;
+        acc_rate = (double)st->count[PTMC_C_VOLXY_ADJ] / (nv / 3);
+        if (acc_rate < c->min_acc) st->max_displ[2] *= 0.9;
+        else if (acc_rate > c->max_acc) st->max_displ[2] *= 1.1;
+        st->count[PTMC_C_VOLXY_ADJ] = 0;
+        acc_rate = (double)st->count[PTMC_C_VOLZ_ADJ] / (nv / 6);
+        if (acc_rate < c->min_acc) st->max_displ[3] *= 0.9;
+        else if (acc_rate > c->max_acc) st->max_displ[3] *= 1.1;
+        st->count[PTMC_C_VOLZ_ADJ] = 0;
     }
 }
 
@@ -808,6 +867,7 @@ orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER && (!cfg->runner || cfg->bc_kind != PTMC_BC_SPHERICAL)) return NULL;
     /* ELJPotentialB: the free-space NVT path (scripts/ne13_B.jl); the periodic methods are outside the hot path */
     if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->ensemble != PTMC_ENS_NVT)) return NULL;
+    if (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume && cfg->bc_kind != PTMC_BC_RHOMBIC && cfg->bc_kind != PTMC_BC_RECTANGULAR) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
     H->cfg = *cfg;
     if (cfg->pot_kind == PTMC_POT_ELJ_B) {
@@ -887,6 +947,8 @@ int orc_upload_states(orc_handle* H, const double* pos, const double* box, const
         s->box[0] = box[2 * r]; s->box[1] = box[2 * r + 1];
         for (int k = 0; k < 4; ++k) st->max_displ[k] = max_displ ? max_displ[4 * r + k] : 0.1;
         st->max_boxlength = c->bc_kind == PTMC_BC_SPHERICAL ? 30.0 : s->box[0] * 1.8; /* src/MCStates.jl:63-75 */
+        st->max_boxheight = c->bc_kind == PTMC_BC_SPHERICAL ? 30.0 : (c->bc_kind == PTMC_BC_CUBIC ? s->box[0] * 1.8 : s->box[1] * 1.8); /* :76-87 */
+        st->lh_ratio = st->max_boxlength / st->max_boxheight;
         st->ham[0] = st->ham[1] = 0.0;
         memset(st->count, 0, sizeof st->count);
         st->new_en = 0.0;

@@ -55,7 +55,7 @@ class Config(C.Structure):
         ("n_adjust", C.c_int32), ("mc_sample", C.c_int32), ("n_bin", C.c_int32), ("rng_mode", C.c_int32),
         ("min_acc", C.c_double), ("max_acc", C.c_double),
         ("seed", C.c_uint64),
-        ("lanes_per_replica", C.c_int32), ("reserved", C.c_int32),
+        ("lanes_per_replica", C.c_int32), ("separated_volume", C.c_int32),
         ("eljb_a", _dp), ("eljb_b", _dp),
     ]
 

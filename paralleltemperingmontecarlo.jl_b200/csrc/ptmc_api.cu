@@ -265,6 +265,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     if (c->bc_kind < PTMC_BC_SPHERICAL || c->bc_kind > PTMC_BC_RECTANGULAR) return fail(nullptr, PTMC_ERR_ARG, "unknown boundary condition %d", c->bc_kind);
     if (npt && sphere) return fail(nullptr, PTMC_ERR_ARG, "SphericalBC cannot be used in an NPT ensemble");   // src/Ensembles.jl:189
     if (npt && c->n_volume_moves < 1) return fail(nullptr, PTMC_ERR_ARG, "NPT needs n_volume_moves >= 1");
+    if (npt && c->separated_volume && c->bc_kind != PTMC_BC_RHOMBIC && c->bc_kind != PTMC_BC_RECTANGULAR)
+        return fail(nullptr, PTMC_ERR_ARG, "separated volume moves need RhombicBC or RectangularBC (scale_xy / scale_z, src/MCMoves.jl:189-222)");
     switch (c->pot_kind) {
         case PTMC_POT_ELJ: case PTMC_POT_ELJ_EVEN:
             if (c->n_coeff < 1 || c->n_coeff > PTMC_MAX_COEFF) return fail(nullptr, PTMC_ERR_ARG, "n_coeff must be in 1..%d", PTMC_MAX_COEFF);
@@ -322,6 +324,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     P.ensemble = c->ensemble; P.bc_kind = c->bc_kind; P.pot_kind = c->pot_kind; P.n_coeff = c->n_coeff;
     P.n_adjust = c->n_adjust; P.mc_sample = c->mc_sample; P.n_bin = c->n_bin;
     P.replay = c->rng_mode == PTMC_RNG_REPLAY;
+    P.separated = npt && c->separated_volume ? 1 : 0;
     P.min_acc = c->min_acc; P.max_acc = c->max_acc; P.pressure = c->pressure;
     for (int i = 0; i < PTMC_MAX_COEFF; ++i) P.coeff[i] = i < c->n_coeff ? c->coeff[i] : 0.0;
     if (c->pot_kind == PTMC_POT_ELJ_B)
@@ -345,7 +348,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) ||
         (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) || (rc = dev_alloc(h, &P.perm_g, R)) ||
         (rc = dev_alloc(h, &P.moved_g, R * ((N + 31) / 32 + 1))) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
-        (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
+        (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.max_boxheight, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
         (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4 * PTMC_RNG_LANES)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||
         (rc = dev_alloc(h, &P.slot_cursor, R)) || (rc = dev_alloc(h, &P.ladder_cursor, L)) ||
         (rc = dev_alloc(h, &en_min, L)) || (rc = dev_alloc(h, &en_max, L)) || (rc = dev_alloc(h, &v_min, L)) || (rc = dev_alloc(h, &v_max, L)) ||
@@ -425,11 +428,13 @@ extern "C" PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, co
     const DevParams& P = h->P;
     CU(h, cudaMemcpyAsync(P.pos, pos, sizeof(double) * R * N * 3, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(P.box, box, sizeof(double) * R * 2, cudaMemcpyHostToDevice, h->stream));
-    std::vector<double> md(R * 4), mb(R);
+    std::vector<double> md(R * 4), mb(R), mh(R);
     for (size_t r = 0; r < R; ++r) {
         for (int k = 0; k < 4; ++k) md[4 * r + k] = max_displ ? max_displ[4 * r + k] : 0.1;             // src/MCStates.jl:104
         mb[r] = h->cfg.bc_kind == PTMC_BC_SPHERICAL ? 30.0 : box[2 * r] * 1.8;                          // src/MCStates.jl:63-75
+        mh[r] = h->cfg.bc_kind == PTMC_BC_SPHERICAL ? 30.0 : (h->cfg.bc_kind == PTMC_BC_CUBIC ? box[2 * r] : box[2 * r + 1]) * 1.8;   // :76-87
     }
+    CU(h, cudaMemcpyAsync(P.max_boxheight, mh.data(), sizeof(double) * R, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(P.max_displ, md.data(), sizeof(double) * R * 4, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(P.max_boxlength, mb.data(), sizeof(double) * R, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(P.counters, 0, sizeof(i64) * R * PTMC_NCOUNT, h->stream));

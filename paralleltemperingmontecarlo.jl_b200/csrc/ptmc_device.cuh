@@ -63,6 +63,8 @@ struct DevParams {
     // slot-side state
     double* max_displ;  // [L][T][4]
     double* max_boxlength; // [L][T]
+    double* max_boxheight; // [L][T]  (separated volume moves)
+    int separated;         // NPT.separated_volume
     i64* counters;      // [L][T][PTMC_NCOUNT]
     double* ham;        // [L][T][2]
     const double* betas;// [T]

@@ -30,6 +30,7 @@ struct SmemLayout {
     int off_ham;        // ham [T][2] (slot side)
     int off_lrng;       // ladder stream, one private copy per warp: 4 x u64 state + cursor + pad
     int off_moved;      // periodic: int moved[T][words + 1]
+    int off_sep;        // periodic: per slot {max_displ[2], max_displ[3], max_boxheight, int n_acc_xy, n_adj_xy, n_acc_z, n_adj_z} (6 doubles)
     int off_tab;        // EAM: the mantissa table of eam_invrexp (PTMC_EAM_KTAB_DOUBLES, 16-byte aligned)
     size_t bytes;
 };
@@ -50,10 +51,42 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     s.off_lrng = off; off += 6 * n_warps;
     s.off_perm = off; off += (n_traj + 1) / 2 + 1;
     s.off_moved = off; off += pbc ? (n_traj * ((n_pad + 31) / 32 + 1) + 1) / 2 + 1 : 0;
+    s.off_sep = off; off += pbc ? 6 * n_traj : 0;
     off += off & 1;
     s.off_tab = off; off += pot_kind == PTMC_POT_EAM ? PTMC_EAM_KTAB_DOUBLES : 0;
     s.bytes = (size_t)off * sizeof(double);
     return s;
+}
+
+// Separated volume moves (src/MCMoves.jl:300-343), separate loops so that the uniform-move loops stay as they are.
+// Pair energy of the trial configuration (positions scaled by scale_xy / scale_z, box tL x tH) below the new cut-off:
+// get_distance2_mat!(new_dist2_mat, trial_config) + dimer_energy_config; exact distance2 arithmetic while the configuration
+// still holds never-moved lattice atoms, the reciprocal-multiply minimum image afterwards.  Returns this lane's partial sum.
+template <int G, int POT, int NC, bool RHOMBIC>
+__device__ __forceinline__ double sep_trial_energy(const DevParams& P, const double* X, const double* Y, const double* Z, int N, int g,
+                                               double scale_xy, double scale_z, double tL, double tH, double new_rcut, bool thawed) {
+    const Box tbx = make_box(P.bc_kind, tL, tH);
+    double acce = 0.0;
+    for (int a = 0; a < N - 1; ++a) {
+        const double pax = xmul(X[a], scale_xy), pay = xmul(Y[a], scale_xy), paz = xmul(Z[a], scale_z);
+        for (int j = a + 1 + g; j < N; j += G) {
+            const double pbx = xmul(X[j], scale_xy), pby = xmul(Y[j], scale_xy), pbz = xmul(Z[j], scale_z);
+            const double d2 = thawed ? dist2_pbc<RHOMBIC>(tbx, pax, pay, paz, pbx, pby, pbz)
+                                     : dist2_exact(P.bc_kind, pax, pay, paz, pbx, pby, pbz, tL, tH);
+            if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
+        }
+    }
+    return acce;
+}
+// dist2_mat .= new_dist2_mat after an accepted separated move (positions already scaled)
+template <int G>
+__device__ __forceinline__ void sep_rewrite_matrix(const DevParams& P, const double* X, const double* Y, const double* Z, int N, int g,
+                                               double tL, double tH, double* D) {
+    for (int a = 0; a < N - 1; ++a)
+        for (int j = a + 1 + g; j < N; j += G) {
+            const double v = dist2_exact(P.bc_kind, X[a], Y[a], Z[a], X[j], Y[j], Z[j], tL, tH);
+            __stcg(D + (size_t)a * N + j, v); __stcg(D + (size_t)j * N + a, v);
+        }
 }
 
 // DBG   : sequential slot stream (Julia-compatible XOSHIRO mode, or REPLAY) + optional trace.  !DBG: BATCH8.
@@ -128,6 +161,12 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
             vmax = P.max_displ[rep * 4 + 1];
             max_boxl = P.max_boxlength[rep];
             n_adj_vol = (int)P.counters[rep * PTMC_NCOUNT + PTMC_C_VOL_ADJ];
+            if (g == 0) {   // separated volume moves: rarely touched slot-side state lives in shared memory
+                double* sd = sm + lay.off_sep + 6 * slot; int* si = reinterpret_cast<int*>(sd + 3);
+                sd[0] = P.max_displ[rep * 4 + 2]; sd[1] = P.max_displ[rep * 4 + 3]; sd[2] = P.max_boxheight[rep];
+                si[0] = 0; si[1] = (int)P.counters[rep * PTMC_NCOUNT + PTMC_C_VOLXY_ADJ];
+                si[2] = 0; si[3] = (int)P.counters[rep * PTMC_NCOUNT + PTMC_C_VOLZ_ADJ];
+            }
         }
         S.draws = nullptr; S.pos = 0; S.len = 0; S.exhausted = 0;
         if (BATCH) {
@@ -424,27 +463,64 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     __syncwarp(gmask);
                 } else {
                     // ------------------------------- volume_change_uniform src/MCMoves.jl:277-287, :169-177
-                    const double uv = BATCH ? B.template rand<1>(gmask) : S.rand();
-                    double scale = pow(exp(xmul(xsub(uv, 0.5), vmax)), 1.0 / 3.0);
-                    if (boxL >= max_boxl && scale > 1.0) scale = 1.0;
-                    const double tL = xmul(scale, boxL), tH = xmul(scale, boxH);
+                    // ------------------------------- volume_change_separated :300-343 (NPT.separated_volume)
+                    const bool sepv = P.separated != 0;
+                    double* sepd = sm + lay.off_sep + 6 * slot; int* sepi = reinterpret_cast<int*>(sepd + 3);
+                    double scale_xy, scale_z;
+                    int xyz = 0;                                  // NPTVariables.xy_or_z: 0 all directions, 1 xy, 2 z
+                    if (sepv) {
+                        int ra; double uv;
+                        if (BATCH) { ra = (int)__umul64hi(B.template raw<2>(gmask), 6ull) + 1; uv = B.template rand<1>(gmask); }
+                        else { ra = S.range(6ull); uv = S.rand(); }
+                        const double lh = xdiv(boxL, boxH), lhr = xdiv(max_boxl, sepd[2]);     // lh_ratio src/MCStates.jl:107
+                        if (ra == 1) {                            // volume_change_z :256-271
+                            xyz = 2;
+                            double sc = exp(xmul(xsub(uv, 0.5), sepd[1]));
+                            if (lh <= xmul(lhr, 1.1) && sc > 1.0) sc = xdiv(1.0, sc);
+                            else if (lh >= xmul(lhr, 0.909) && sc < 1.0) sc = xdiv(1.0, sc);
+                            if (boxH >= sepd[2] && sc > 1.0) sc = xdiv(1.0, sc);
+                            scale_xy = 1.0; scale_z = sc;
+                        } else if (ra <= 3) {                     // volume_change_xy :232-247
+                            xyz = 1;
+                            double sc = pow(exp(xmul(xsub(uv, 0.5), sepd[0])), 1.0 / 2.0);
+                            if (lh >= xmul(lhr, 1.1) && sc > 1.0) sc = xdiv(1.0, sc);
+                            else if (lh <= xmul(lhr, 0.909) && sc < 1.0) sc = xdiv(1.0, sc);
+                            if (boxL >= max_boxl && sc > 1.0) sc = xdiv(1.0, sc);
+                            scale_xy = sc; scale_z = 1.0;
+                        } else {                                  // volume_change_xyz :169-177
+                            double sc = pow(exp(xmul(xsub(uv, 0.5), vmax)), 1.0 / 3.0);
+                            if (boxL >= max_boxl && sc > 1.0) sc = 1.0;
+                            scale_xy = sc; scale_z = sc;
+                        }
+                    } else {
+                        const double uv = BATCH ? B.template rand<1>(gmask) : S.rand();
+                        double scale = pow(exp(xmul(xsub(uv, 0.5), vmax)), 1.0 / 3.0);
+                        if (boxL >= max_boxl && scale > 1.0) scale = 1.0;
+                        scale_xy = scale; scale_z = scale;
+                    }
+                    const double tL = xmul(scale_xy, boxL), tH = xmul(scale_z, boxH);
                     const double new_rcut = get_r_cut(P.bc_kind, tL, tH);
-                    const double sc2 = xmul(scale, scale);
-                    // dimer_energy_config on new_dist2_mat = dist2_mat * scale^2 (src/MCRun.jl:76-85,
-                    // src/EnergyEvaluation.jl:397-474); rows are dealt to the lanes of the group.
+                    const double sc2 = xmul(scale_xy, scale_xy);
+                    // dimer_energy_config (src/MCRun.jl:76-85, src/EnergyEvaluation.jl:397-474) on new_dist2_mat: dist2_mat * scale^2
+                    // for the uniform move; recomputed from the trial configuration (get_distance2_mat!) for the separated moves.
+                    // Rows are dealt to the lanes of the group.
                     double acce = 0.0;
                     double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
                     const bool thawed = moved[c * MW + MW - 1] >= N;
-                    for (int a = 0; a < N - 1; ++a) {
-                        const double* Da = D + (size_t)a * N;
-                        const double xa = X[a], ya = Y[a], za = Z[a];
-                        for (int j = a + 1 + g; j < N; j += G) {
-                            double d2o;
-                            if (thawed) d2o = rhombic ? dist2_pbc<true>(bx, xa, ya, za, X[j], Y[j], Z[j]) : dist2_pbc<false>(bx, xa, ya, za, X[j], Y[j], Z[j]);
-                            else d2o = __ldcg(Da + j);
-                            const double d2 = xmul(d2o, sc2);                 // new_dist2_mat[a, j]
-                            if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
+                    if (!sepv) {
+                        for (int a = 0; a < N - 1; ++a) {
+                            const double* Da = D + (size_t)a * N;
+                            const double xa = X[a], ya = Y[a], za = Z[a];
+                            for (int j = a + 1 + g; j < N; j += G) {
+                                double d2o;
+                                if (thawed) d2o = rhombic ? dist2_pbc<true>(bx, xa, ya, za, X[j], Y[j], Z[j]) : dist2_pbc<false>(bx, xa, ya, za, X[j], Y[j], Z[j]);
+                                else d2o = __ldcg(Da + j);
+                                const double d2 = xmul(d2o, sc2);                 // new_dist2_mat[a, j]
+                                if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
+                            }
                         }
+                    } else {
+                        acce = sep_trial_energy<G, POT, NC, rhombic>(P, X, Y, Z, N, g, scale_xy, scale_z, tL, tH, new_rcut, thawed);
                     }
                     double e_new = group_sum<G>(acce, gmask);
                     const double l = lrc_even(P, new_rcut);
@@ -462,11 +538,19 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     if (acc) {
                         // swap_config_v! src/swap_config.jl:113-140
                         __syncwarp(gmask);
-                        for (int j = g; j < N; j += G) { X[j] = xmul(scale, X[j]); Y[j] = xmul(scale, Y[j]); Z[j] = xmul(scale, Z[j]); }
-                        if (!thawed) for (int k = g; k < N * N; k += G) __stcg(D + k, xmul(__ldcg(D + k), sc2));   // dist2_mat .= new_dist2_mat
+                        for (int j = g; j < N; j += G) { X[j] = xmul(scale_xy, X[j]); Y[j] = xmul(scale_xy, Y[j]); Z[j] = xmul(scale_z, Z[j]); }
+                        if (!thawed) {
+                            if (!sepv) {
+                                for (int k = g; k < N * N; k += G) __stcg(D + k, xmul(__ldcg(D + k), sc2));   // dist2_mat .= new_dist2_mat
+                            } else {
+                                __syncwarp(gmask);
+                                sep_rewrite_matrix<G>(P, X, Y, Z, N, g, tL, tH, D);
+                            }
+                        }
                         boxL = tL; boxH = tH; rcut = new_rcut; en = e_new;
                         bx = make_box(P.bc_kind, boxL, boxH);
-                        n_acc_vol += 1; n_adj_vol += 1;
+                        if (xyz == 0) { n_acc_vol += 1; n_adj_vol += 1; }
+                        else if (g == 0) { sepi[2 * (xyz - 1)] += 1; sepi[2 * (xyz - 1) + 1] += 1; }
                     }
                     __syncwarp(gmask);
                 }
@@ -545,11 +629,31 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                 else if (rate > P.max_acc) dmax = xmul(dmax, 1.1);
                 n_adj_atom = 0;
                 if (PBC) {
-                    if (npt) {
+                    if (npt && !P.separated) {
                         rate = xdiv((double)n_adj_vol, (double)((i64)P.n_adjust * P.n_volume_moves));
                         if (rate < P.min_acc) vmax = xmul(vmax, 0.9);
                         else if (rate > P.max_acc) vmax = xmul(vmax, 1.1);
                         n_adj_vol = 0;
+                    } else if (npt) {
+                        // src/Exchange.jl:221-245: half of the volume moves are uniform, a third xy, a sixth z
+                        const double nv = (double)((i64)P.n_adjust * P.n_volume_moves);
+                        double* sepd = sm + lay.off_sep + 6 * slot; int* sepi = reinterpret_cast<int*>(sepd + 3);
+                        rate = xdiv((double)n_adj_vol, xdiv(nv, 2.0));
+                        if (rate < P.min_acc) vmax = xmul(vmax, 0.9);
+                        else if (rate > P.max_acc) vmax = xmul(vmax, 1.1);
+                        n_adj_vol = 0;
+                        __syncwarp(gmask);
+                        if (g == 0) {
+                            rate = xdiv((double)sepi[1], xdiv(nv, 3.0));
+                            if (rate < P.min_acc) sepd[0] = xmul(sepd[0], 0.9);
+                            else if (rate > P.max_acc) sepd[0] = xmul(sepd[0], 1.1);
+                            sepi[1] = 0;
+                            rate = xdiv((double)sepi[3], xdiv(nv, 6.0));
+                            if (rate < P.min_acc) sepd[1] = xmul(sepd[1], 0.9);
+                            else if (rate > P.max_acc) sepd[1] = xmul(sepd[1], 1.1);
+                            sepi[3] = 0;
+                        }
+                        __syncwarp(gmask);
                     }
                 }
             }
@@ -615,6 +719,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                 P.box[rep * 2] = scal[4 * c + 1]; P.box[rep * 2 + 1] = scal[4 * c + 2];
                 P.max_displ[rep * 4 + 1] = vmax;
                 cn[PTMC_C_VOL_TOT] += n_acc_vol; cn[PTMC_C_VOL_ADJ] = n_adj_vol;
+                const double* sd = sm + lay.off_sep + 6 * slot; const int* si = reinterpret_cast<const int*>(sd + 3);
+                P.max_displ[rep * 4 + 2] = sd[0]; P.max_displ[rep * 4 + 3] = sd[1];
+                cn[PTMC_C_VOLXY_TOT] += si[0]; cn[PTMC_C_VOLXY_ADJ] = si[1];
+                cn[PTMC_C_VOLZ_TOT] += si[2]; cn[PTMC_C_VOLZ_ADJ] = si[3];
             }
             cn[PTMC_C_EXC_ATT] += exc_cnt[2 * slot]; cn[PTMC_C_EXC_ACC] += exc_cnt[2 * slot + 1];
             if (!BATCH) {

@@ -54,6 +54,7 @@ class SweepConfig:
     n_atom_moves: int | None = None
     n_volume_moves: int = 0
     pressure: float = 0.0
+    separated_volume: bool = False
     n_adjust: int = 100
     mc_sample: int = 1
     n_bin: int = 100
@@ -132,6 +133,7 @@ class SweepConfig:
         c.max_acc = self.max_acc
         c.seed = self.seed
         c.lanes_per_replica = self.lanes_per_replica
+        c.separated_volume = int(bool(self.separated_volume)) if self.ensemble == abi.ENS_NPT else 0
         return c
 
 

@@ -244,15 +244,15 @@ def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, e
     if isinstance(ensemble, NPT):
         if isinstance(bc, SphericalBC):
             raise ValueError("SphericalBC cannot be used in an NPT ensemble.")  # src/Ensembles.jl:189
-        if ensemble.separated_volume:
-            raise NotImplementedError("separated_volume moves are outside the B200 hot path (SURVEY §8f)")
+        if ensemble.separated_volume and not isinstance(bc, (RhombicBC, RectangularBC)):
+            raise ValueError("separated volume moves need a RhombicBC or RectangularBC (scale_xy / scale_z, src/MCMoves.jl:189-222)")
     kw = dict(n_ladders=n_ladders, n_traj=mc_params.n_traj, n_atoms=mc_params.n_atoms, betas=temp.beta_grid,
               pot_kind=potential.kind, bc_kind=bc.kind, ensemble=ensemble.kind,
               n_atom_moves=ensemble.atom_moves(), n_adjust=mc_params.n_adjust, mc_sample=mc_params.mc_sample,
               n_bin=mc_params.n_bin, min_acc=mc_params.min_acc, max_acc=mc_params.max_acc, seed=seed,
               device=device, rng_mode=rng_mode, lanes_per_replica=lanes_per_replica)
     if isinstance(ensemble, NPT):
-        kw.update(n_volume_moves=ensemble.n_volume_moves, pressure=ensemble.pressure)
+        kw.update(n_volume_moves=ensemble.n_volume_moves, pressure=ensemble.pressure, separated_volume=ensemble.separated_volume)
     if potential.kind in (abi.POT_ELJ, abi.POT_ELJ_EVEN):
         kw["coeff"] = tuple(potential.coeff)
     elif potential.kind == abi.POT_ELJ_B:

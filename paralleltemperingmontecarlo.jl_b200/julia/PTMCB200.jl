@@ -60,7 +60,7 @@ struct PtmcConfig
     max_acc::Float64
     seed::UInt64
     lanes_per_replica::Int32
-    reserved::Int32
+    separated_volume::Int32
     eljb_a::Ptr{Float64}       # ABI 2: ELJPotentialB coeff_a / coeff_b (coeff_c travels in coeff)
     eljb_b::Ptr{Float64}
 end
@@ -106,7 +106,7 @@ function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCPara
     cfg = Ref(PtmcConfig(PTMC_ABI_VERSION, b.device, L, T, N, npt ? 1 : 0, ensemble.n_atom_moves,
         npt ? ensemble.n_volume_moves : 0, bc_kind(bc), npt ? ensemble.pressure : 0.0, pk, nc, pad16(coeff),
         eam..., C_NULL, pointer(betas), mc_params.n_adjust, mc_params.mc_sample, mc_params.n_bin, b.rng_mode,
-        mc_params.min_acc, mc_params.max_acc, b.seed, b.lanes_per_replica, 0,
+        mc_params.min_acc, mc_params.max_acc, b.seed, b.lanes_per_replica, (npt && ensemble.separated_volume) ? 1 : 0,
         isempty(ea) ? Ptr{Float64}(C_NULL) : pointer(ea), isempty(eb) ? Ptr{Float64}(C_NULL) : pointer(eb)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve betas ea eb begin

@@ -570,3 +570,32 @@ def test_split_cycle_phases_equal_whole_cycles(case):
     for k in ("pos", "counters", "max_displ", "en_tot", "ham"):
         assert np.array_equal(st[k], ref[k]), k
     assert np.array_equal(hist, ref_hist)
+
+
+@pytest.mark.parametrize("bc_cls", [P.RectangularBC, P.RhombicBC])
+def test_separated_volume_moves_replay(bc_cls):
+    # NPT(separated_volume = true): volume_change_separated (src/MCMoves.jl:300-343) draws rand(1:6) -> z (1/6), xy (2/6) or
+    # uniform (3/6) scaling with its own step size, counter and adaptation rule (src/Exchange.jl:221-245); the trial distance
+    # matrix is recomputed (get_distance2_mat!).  Replayed streams: same decisions, dE to 1e-10, same counters / step sizes.
+    # (started from a slightly perturbed lattice: on a perfect rhombic lattice the image chosen for pairs that sit exactly half
+    #  a cell apart in y is decided by the last bit of the scale factor, i.e. by the libm's exp / pow - DESIGN.md waivers)
+    lattice = _small_pbc(bc_cls)
+    start = P.Config(lattice.positions + np.random.default_rng(8).uniform(-1e-3, 1e-3, lattice.positions.shape), lattice.boundary_condition)
+    mcp = P.MCParams(40, 6, 32, n_adjust=10)
+    temp = P.TempGrid(20.0, 40.0, 6)
+    pot = P.ELJPotentialEven(P.host.ELJ_NE_COEFF)
+    ens = P.NPT(32, 101325 * 3.398928944382626e-14, True, n_volume_moves=4)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=40, seed=33)
+    compare_traces(gpu, cpu, positions_exact=False)
+    cnt = gpu["states"]["counters"]
+    assert cnt[:, :, abi.C_VOLXY_TOT].sum() > 0 and cnt[:, :, abi.C_VOLZ_TOT].sum() > 0 and cnt[:, :, abi.C_VOL_TOT].sum() > 0
+    box = gpu["states"]["box"]
+    assert not np.allclose(box[:, :, 0] / box[:, :, 1], box[0, 0, 0] / box[0, 0, 1] * 0 + start.boundary_condition.box_length / start.boundary_condition.box_height)
+    # production streams: whole trajectory against the oracle
+    res = _free_run_pair((mcp, temp, start, pot, ens), 2, 5, abi.RNG_BATCH8, 40, bounds=(-1.0, 1.0, 0.5 * P.get_volume(start.boundary_condition), 3.0 * P.get_volume(start.boundary_condition)))
+    (sg, hg, rg), (sc, hc, rc) = res
+    assert np.array_equal(sg["counters"], sc["counters"]) and np.array_equal(hg, hc) and np.array_equal(rg[0], rc[0])
+    np.testing.assert_allclose(sg["pos"], sc["pos"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(sg["max_displ"], sc["max_displ"], rtol=1e-15)
+    with pytest.raises((PtmcError, ValueError)):      # scale_xy / scale_z do not exist for CubicBC
+        Engine(sweep_config(mcp, temp, _small_pbc(P.CubicBC), pot, ens))
