@@ -8,7 +8,7 @@ from ptmc_b200.host import initial_arrays, sweep_config
 
 from parity import make_replay
 
-CASES = ("ne13_elj_nvt", "cu55_eam_nvt", "ne32_cubic_npt", "ne216_rhombic_npt")
+CASES = ("ne13_elj_nvt", "cu55_eam_nvt", "ne32_cubic_npt", "ne216_rhombic_npt", "ne13_eljb_nvt", "ne32_rect_npt_separated")
 
 
 def _ne32_cubic():
@@ -36,12 +36,23 @@ def build_case(name, oracle):
         deck = P.host.deck_pbc216(n_traj=4, cycles=2)
         v0 = P.get_volume(deck[2][0].boundary_condition)
         L, cycles, seed, eq, bounds = 1, 2, 8, 0, (0.30, 0.40, 0.8 * v0, 2.0 * v0)
+    elif name == "ne13_eljb_nvt":       # scripts/ne13_B.jl: ELJPotentialB (magnetic field), Angstrom units
+        deck, L, cycles, seed, eq, bounds = P.host.deck_ne13_B(n_traj=6, cycles=24), 2, 24, 77, 6, (-0.02, 0.0, None, None)
+        deck[0].n_adjust = 10
+    elif name == "ne32_rect_npt_separated":   # NPT(separated_volume = true): xy / z / uniform volume moves, rectangular cell
+        start = _ne32_cubic()
+        start = P.Config(start.positions * [1, 1, 1.25], P.RectangularBC(start.boundary_condition.box_length, start.boundary_condition.box_length * 1.25))
+        deck = (P.MCParams(16, 4, 32, n_adjust=8), P.TempGrid(20.0, 40.0, 4), start, P.ELJPotentialEven(P.host.ELJ_NE_COEFF),
+                P.NPT(32, 101325 * 3.398928944382626e-14, True, n_volume_moves=3))
+        v0 = P.get_volume(start.boundary_condition)
+        L, cycles, seed, eq, bounds = 1, 16, 55, 4, (-0.05, 0.0, 0.8 * v0, 2.0 * v0)
     else:
         raise KeyError(name)
     mcp, temp, start, pot, ens = deck
     # start with step sizes that give ~50 % acceptance instead of the constructor's 0.1 (src/MCStates.jl:104)
     md = np.full((L, mcp.n_traj, 4), 0.1)
-    md[:, :, 0] = {"ne13_elj_nvt": 0.9, "cu55_eam_nvt": 0.5, "ne32_cubic_npt": 0.7, "ne216_rhombic_npt": 0.6}[name]
+    md[:, :, 0] = {"ne13_elj_nvt": 0.9, "cu55_eam_nvt": 0.5, "ne32_cubic_npt": 0.7, "ne216_rhombic_npt": 0.6,
+                   "ne13_eljb_nvt": 0.4, "ne32_rect_npt_separated": 0.7}[name]
     cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=seed, rng_mode=abi.RNG_REPLAY)
     pos, box = initial_arrays(mcp, start, L)
     slot, lad = make_replay(oracle, L, mcp.n_traj, cfg.n_steps, eq + cycles, seed)
