@@ -30,10 +30,11 @@ static sweep_fn generic_kernel(int pot, int geom, int dbg) {
 
 // Specialised production kernels of the headline family (ELJPotentialEven with 6 coefficients, SphericalBC,
 // BATCH8 streams): pair loop fully unrolled for ceil(n_atoms / G) = 1..8 (1..16 for G = 4).
-static sweep_fn special_kernel(int niter) {
+static sweep_fn special_kernel(int niter, int fullw) {
     constexpr int G = PTMC_G;
     switch (niter) {
-#define PTMC_SP(K) case K: return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_SPHERE, false, K, 6>;
+#define PTMC_SP(K) case K: return fullw ? (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_SPHERE, false, K, 6, true> \
+                                        : (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_SPHERE, false, K, 6, false>;
         PTMC_SP(1) PTMC_SP(2) PTMC_SP(3) PTMC_SP(4) PTMC_SP(5) PTMC_SP(6) PTMC_SP(7) PTMC_SP(8)
 #if PTMC_G == 4
         PTMC_SP(9) PTMC_SP(10) PTMC_SP(11) PTMC_SP(12) PTMC_SP(13) PTMC_SP(14) PTMC_SP(15) PTMC_SP(16)
@@ -44,11 +45,11 @@ static sweep_fn special_kernel(int niter) {
 }
 
 // pot: ptmc_pot_kind (ELJ, ELJ_EVEN, EAM); geom: Geom; dbg: sequential-stream / replay / trace build;
-// niter = n_pad / G; n_coeff: number of ELJ coefficients
-sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff) {
+// niter = n_pad / G; n_coeff: number of ELJ coefficients; fullw: n_traj * G is a multiple of 32 (no partly active warp)
+sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff, int fullw) {
     constexpr int G = PTMC_G;
     if (!dbg && pot == PTMC_POT_ELJ_EVEN && geom == GEOM_SPHERE && n_coeff == 6) {
-        sweep_fn f = special_kernel(niter);
+        sweep_fn f = special_kernel(niter, fullw);
         if (f) return f;
     }
     // EmbeddedAtomPotential: pair loop unrolled, trial components in registers

@@ -92,7 +92,7 @@ __device__ __forceinline__ void sep_rewrite_matrix(const DevParams& P, const dou
 // DBG   : sequential slot stream (Julia-compatible XOSHIRO mode, or REPLAY) + optional trace.  !DBG: BATCH8.
 // NITER : compile-time ceil(n_atoms / G) of the pair loop (n_pad = NITER * G), 0 = runtime trip count.
 // NC    : compile-time number of ELJ coefficients (6), 0 = runtime.
-template <int G, int POT, int GEOM, bool DBG, int NITER, int NC>
+template <int G, int POT, int GEOM, bool DBG, int NITER, int NC, bool FULLW = false>
 __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_idx, const i64 n_cycles, const int sample) {
     extern __shared__ double sm[];
     constexpr bool EAM = (POT == PTMC_POT_EAM);
@@ -107,6 +107,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     const int slot = tid / G, g = tid & (G - 1);
     const bool active = slot < T;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
+    // hot-path mask: when every group of the warp is active all 32 lanes run the move loop in lock step, and a compile-time
+    // full mask spares the MATCH / VOTE convergence sequences the compiler emits around a register mask (FULLW kernels)
+    const unsigned hmask = FULLW ? 0xffffffffu : gmask;
     constexpr bool EAM_REG = EAM && NITER > 0 && PTMC_EAM_UNROLL;     // trial (phi, rho) components in registers instead of shared memory
     const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG);
     double* scal = sm + lay.off_scal;
@@ -209,7 +212,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
 
             for (int step = 0; step < P.n_steps; ++step) {
                 int index;                                          // rand(1:N) src/MCRun.jl:145
-                if (BATCH) { B.begin(); index = (int)__umul64hi(B.template raw<0>(gmask), (u64)P.n_steps) + 1; }
+                if (BATCH) { B.begin(); index = (int)__umul64hi(B.template raw<0>(hmask), (u64)P.n_steps) + 1; }
                 else index = S.range((u64)P.n_steps);
                 double de = 0.0;
                 bool acc = false;
@@ -219,9 +222,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     double xi = X[i], yi = Y[i], zi = Z[i];
                     double tx, ty, tz;
                     if (BATCH) {
-                        tx = xadd(xi, xmul(xsub(B.template rand<1>(gmask), 0.5), dmax));
-                        ty = xadd(yi, xmul(xsub(B.template rand<2>(gmask), 0.5), dmax));
-                        tz = xadd(zi, xmul(xsub(B.template rand<3>(gmask), 0.5), dmax));
+                        tx = xadd(xi, xmul(xsub(B.template rand<1>(hmask), 0.5), dmax));
+                        ty = xadd(yi, xmul(xsub(B.template rand<2>(hmask), 0.5), dmax));
+                        tz = xadd(zi, xmul(xsub(B.template rand<3>(hmask), 0.5), dmax));
                     } else {
                         tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
                         ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
@@ -287,9 +290,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     double nph[EAM_NK], nrh[EAM_NK], nphi_i = 0.0, nrho_i = 0.0;   // EAM: trial components of this lane's atoms / of atom i
                     if (PARK) {
                         // park the moved atom: its own pair term (d2_old = 0) must not enter the row sums
-                        __syncwarp(gmask);
+                        __syncwarp(hmask);
                         if (g == 0) { X[i] = PTMC_FAR; Y[i] = PTMC_FAR; Z[i] = PTMC_FAR; }
-                        __syncwarp(gmask);
+                        __syncwarp(hmask);
                     }
                     if (!EAM) {
                         // dimer_energy_update! :804-821: sum_j e(new_ij) - sum_j e(old_ij) (the reference forms the same
@@ -379,7 +382,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             }
                         }
                         const double accd = accn - acco;
-                        const double delta_en = group_sum<G>(accd, gmask);
+                        const double delta_en = group_sum<G>(accd, hmask);
                         new_en = xadd(delta_en, en);
                     } else {
                         // calc_components :1111-1127 + calc_energies_from_components :1156-1162
@@ -418,7 +421,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     }
                     // ------------------------------------------------------------ acc_test! src/MCRun.jl:122-132
                     de = xsub(new_en, en);
-                    const double u = BATCH ? B.template rand<4>(gmask) : S.rand();
+                    const double u = BATCH ? B.template rand<4>(hmask) : S.rand();
                     acc = metropolis_accept(-xmul(de, beta), u);
                     if (PARK) {
                         if (!acc && g == 0) { X[i] = xi; Y[i] = yi; Z[i] = zi; }        // un-park
@@ -460,7 +463,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             }
                         }
                     }
-                    __syncwarp(gmask);
+                    __syncwarp(hmask);
                 } else {
                     // ------------------------------- volume_change_uniform src/MCMoves.jl:277-287, :169-177
                     // ------------------------------- volume_change_separated :300-343 (NPT.separated_volume)
@@ -619,7 +622,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
             }
             __syncthreads();
         } else {
-            __syncwarp(gmask);                                      // scal[] of this slot is visible to its group
+            __syncwarp(hmask);                                      // scal[] of this slot is visible to its group
         }
         if (active && phase != 1) {
             // ------------------------------------------- update_max_stepsize! src/Exchange.jl:198-263
@@ -741,10 +744,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     if (err) atomicMin(P.error, err);
 }
 
-template <int G, int POT, int GEOM, bool DBG, int NITER, int NC>
+template <int G, int POT, int GEOM, bool DBG, int NITER, int NC, bool FULLW = false>
 __global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
 sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
-    sweep_body<G, POT, GEOM, DBG, NITER, NC>(P, first_idx, n_cycles, sample);
+    sweep_body<G, POT, GEOM, DBG, NITER, NC, FULLW>(P, first_idx, n_cycles, sample);
 }
 // EmbeddedAtomPotential: the unrolled loop wants ~170 registers; capped so that two 224-thread ladders (scripts/cu55.jl:
 // 28 temperatures x 8 lanes) stay resident per SM (a 96-register cap for three ladders spills and measured slower)
