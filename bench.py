@@ -331,7 +331,7 @@ def run_b200(args):
                              "frac": (achieved / peak) if peak else None,
                              # dram__bytes_read + dram__bytes_write of one sweep launch from the ncu --set full capture
                              # profiles/r01_sweep_ne55_g8.md (state load / store; independent of the cycle count)
-                             "traffic": 305509120,
+                             "traffic": 301594368,
                              "note": "FP64 FMA pipe bound (not hbm/tensor): W = %d algorithmic flops per move; peak = DFMA-chain "
                                      "peak measured live (MEASURED_PEAKS.json has no FP64 figure); HBM traffic is ~0 B/move" % W_FLOPS_PER_MOVE},
                 "cpu_baseline": cpu}
