@@ -112,3 +112,29 @@ def test_ptmc_run_save_restart_and_rdf(tmp_path, oracle):
     assert res2[0].en_histogram.sum() == 4 * 3000 and (res2[0].en_histogram >= r.en_histogram).all()
     assert (st2["counters"][0, :, abi.C_ATOM_TOT] > st["counters"][0, :, abi.C_ATOM_TOT]).all()
     assert readsave.rebuild_states(4, d)[-1] == 3000
+
+
+def test_ptmc_run_save_restart_npt_separated(tmp_path, oracle):
+    # NPT with separated volume moves on a rectangular cell: volume_hist.data, box_dims in the xyz comment line, restart
+    from oracle import oracle as orc
+    a = 8.4
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
+    pos = np.array([(b + [i, j, k]) * a for i in range(2) for j in range(2) for k in range(2) for b in base]) * [1, 1, 1.25]
+    start = P.Config(pos, P.RectangularBC(2 * a, 2.5 * a))
+    mcp = P.MCParams(60, 3, 32, eq_percentage=0.1, n_adjust=10)
+    temp = P.TempGrid(20.0, 40.0, 3)
+    pot = P.ELJPotentialEven(P.host.ELJ_NE_COEFF)
+    ens = P.NPT(32, 101325 * 3.398928944382626e-14, True, n_volume_moves=2)
+    st, res = P.host.ptmc_run(mcp, temp, start, pot, ens, n_ladders=1, seed=3, engine_cls=orc.OracleEngine, save=30, save_dir=tmp_path)
+    assert (tmp_path / "volume_hist.data").exists() and res[0].ev_histogram.sum() == 3 * 60
+    line = (tmp_path / "configT2.xyz").read_text().splitlines()[1]
+    assert line.startswith("RectangularBC{Float64} box_dims: ") and line.split()[2].endswith(",")
+    cfgs, md, ca, cv, back, rdf, index = readsave.rebuild_states(3, tmp_path, npt=True)
+    assert index == 60 and np.array_equal(back.ev_histogram, res[0].ev_histogram)
+    assert np.array_equal(np.array([c.boundary_condition.box() for c in cfgs]), st["box"][0])
+    assert np.array_equal(cv, st["counters"][0, :, abi.C_VOL_TOT]) and back.v_min == res[0].v_min and back.delta_v_hist == res[0].delta_v_hist
+    mcp2, temp2, ens2, pot2 = readsave.read_init(tmp_path)
+    assert ens2.separated_volume is True and ens2.n_volume_moves == 2 and ens2.pressure == ens.pressure
+    mcp2.mc_cycles = 90
+    st2, res2 = P.host.ptmc_run(mcp2, temp2, cfgs, pot2, ens2, n_ladders=1, seed=3, engine_cls=orc.OracleEngine, save=30, save_dir=tmp_path, restart=True)
+    assert res2[0].ev_histogram.sum() == 3 * 90 and readsave.rebuild_states(3, tmp_path, npt=True)[-1] == 90
