@@ -263,13 +263,15 @@ __device__ __forceinline__ void elj_even_pair_acc(const DevParams& P, double d2n
 // dimer_energy(::ELJPotentialB) src/EnergyEvaluation.jl:943-958: sum_i c_i r^-k_i (1 + a_i t2 + b_i t4), k = 6, 8, 9, 10, ...;
 // t2 = cos 2theta = 2 / (tan^2 + 1) - 1 = 2 dz^2 / r^2 - 1 (no tangent matrix is stored: the angle comes from the positions
 // like the distance), t4 = 2 t2^2 - 1; below r2 = 5.30 the reference returns 0.1.
+template <int NC = 0>
 __device__ __forceinline__ double eljb_energy(const DevParams& P, double r2, double dz2) {
     const double y = rsqrt_pos(r2);
     const double x = y * y;
     const double t2 = fma(2.0 * dz2, x, -1.0);
     const double t4 = fma(2.0 * t2, t2, -1.0);
-    const int n = P.n_coeff;
+    const int n = NC ? NC : P.n_coeff;
     double p = 0.0;
+#pragma unroll
     for (int k = n - 1; k >= 1; --k) p = fma(p, y, fma(P.eljb_cb[k], t4, fma(P.eljb_ca[k], t2, P.coeff[k])));
     const double w1 = fma(P.eljb_cb[0], t4, fma(P.eljb_ca[0], t2, P.coeff[0]));
     const double s = (x * x * x) * fma(x, p, w1);

@@ -52,6 +52,16 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, 
         sweep_fn f = special_kernel(niter, fullw);
         if (f) return f;
     }
+    // ELJPotentialB with six coefficients (scripts/ne13_B.jl, ne38_B.jl, ne51_B.jl, ne55.jl): unrolled pair loop and Horner chain
+    if (!dbg && pot == PTMC_POT_ELJ_B && geom == GEOM_SPHERE && n_coeff == 6) {
+        switch (niter) {
+#define PTMC_SPB6(K) case K: return fullw ? (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_B, GEOM_SPHERE, false, K, 6, true> \
+                                          : (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_B, GEOM_SPHERE, false, K, 6, false>;
+            PTMC_SPB6(1) PTMC_SPB6(2) PTMC_SPB6(3) PTMC_SPB6(4) PTMC_SPB6(5) PTMC_SPB6(6) PTMC_SPB6(7) PTMC_SPB6(8)
+#undef PTMC_SPB6
+            default: break;
+        }
+    }
     // EmbeddedAtomPotential: pair loop unrolled, trial components in registers
     if (pot == PTMC_POT_EAM && geom == GEOM_SPHERE && eam_unrolled(niter, dbg != 0)) {
         switch (niter) {

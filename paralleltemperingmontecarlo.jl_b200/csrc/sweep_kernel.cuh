@@ -367,8 +367,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);     // parked atoms contribute exactly 0
                                 } else {
                                     // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
-                                    const double en_j = POT == PTMC_POT_ELJ_B ? eljb_energy(P, d2n, az * az) : pair_energy<POT, NC>(P, d2n);
-                                    const double eo_j = POT == PTMC_POT_ELJ_B ? eljb_energy(P, d2o, bz_ * bz_) : pair_energy<POT, NC>(P, d2o);
+                                    const double en_j = POT == PTMC_POT_ELJ_B ? eljb_energy<NC>(P, d2n, az * az) : pair_energy<POT, NC>(P, d2n);
+                                    const double eo_j = POT == PTMC_POT_ELJ_B ? eljb_energy<NC>(P, d2o, bz_ * bz_) : pair_energy<POT, NC>(P, d2o);
                                     accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                 }
                             };
