@@ -26,7 +26,7 @@ CASES = {
     "c1b_ne13_eljb_nvt_16T": (lambda: P.host.deck_ne13_B(n_traj=16, cycles=100), 8192, 200, 100, 5, (-0.02, 0.0, None, None)),
     "c2_ne55_elj_nvt_24T": (lambda: P.host.deck_ne55(n_traj=24, cycles=100), 4096, 200, 50, 5, (-0.1, 0.0, None, None)),
     "c3_cu55_eam_nvt_28T": (lambda: P.host.deck_cu55_eam(n_traj=28, cycles=100), 2048, 100, 20, 5, (-8.0, -5.0, None, None)),
-    "c4_pbc216_elj_npt_16T": (lambda: P.host.deck_pbc216(n_traj=16, cycles=100), 592, 20, 10, 3, None),
+    "c4_pbc216_elj_npt_16T": (lambda: P.host.deck_pbc216(n_traj=16, cycles=100), 592, 20, 40, 3, None),
     "c5_cu55_runner_nvt_28T": (lambda: P.host.deck_cu55_runner(n_traj=28, cycles=100), 37, 4, 4, 3, (-13.0, -11.0, None, None)),
 }
 
