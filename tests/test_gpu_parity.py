@@ -599,3 +599,31 @@ def test_separated_volume_moves_replay(bc_cls):
     np.testing.assert_allclose(sg["max_displ"], sc["max_displ"], rtol=1e-15)
     with pytest.raises((PtmcError, ValueError)):      # scale_xy / scale_z do not exist for CubicBC
         Engine(sweep_config(mcp, temp, _small_pbc(P.CubicBC), pot, ens))
+
+
+def test_ptmc_run_save_restart_other_potentials(tmp_path):
+    # the host driver's checkpoint / restart / rdf paths on the device for NPT (volume_hist.data), RuNNer and EAM
+    from ptmc_b200 import readsave
+    d = tmp_path / "npt"
+    mcp, temp, start, pot, ens = P.host.deck_pbc216(n_traj=4, cycles=40)
+    st, res = P.ptmc_run(mcp, temp, start, pot, ens, n_ladders=2, seed=1, save=20, save_dir=d)
+    cf, md, ca, cv, back, rdf, idx = readsave.rebuild_states(4, d / "ladder1", npt=True)
+    assert idx == 40 and np.array_equal(back.ev_histogram, res[1].ev_histogram) and back.ev_histogram.sum() == 4 * 40
+    mcp2, temp2, ens2, pot2 = readsave.read_init(d / "ladder0")
+    mcp2.mc_cycles = 60
+    _, res2 = P.ptmc_run(mcp2, temp2, start, pot2, ens2, n_ladders=2, seed=1, save=20, save_dir=d, restart=True)
+    assert res2[0].ev_histogram.sum() == 4 * 60
+    d = tmp_path / "runner"
+    mcp, temp, start, pot, ens = P.host.deck_cu55_runner(n_traj=3, cycles=1000)
+    mcp.eq_percentage = 0.0
+    _, res = P.ptmc_run(mcp, temp, start, pot, ens, n_ladders=1, seed=1, save=500, save_dir=d, rdfsave=True)
+    assert res[0].rdf.sum() == 3 * 55 * 54 // 2 and (d / "rdf.data").exists()       # one sample at cycle 1000, every pair inside the range
+    assert (d / "params.data").read_text().splitlines()[4].strip() == "runnerpotential"
+    d = tmp_path / "eam"
+    mcp, temp, start, pot, ens = P.host.deck_cu55_eam(n_traj=4, cycles=300)
+    P.ptmc_run(mcp, temp, start, pot, ens, n_ladders=2, seed=1, save=100, save_dir=d)
+    mcp2, temp2, ens2, pot2 = readsave.read_init(d / "ladder0")
+    assert (pot2.n, pot2.m, pot2.ean, pot2.eCam) == (pot.n, pot.m, pot.ean, pot.eCam)
+    mcp2.mc_cycles = 400
+    _, res2 = P.ptmc_run(mcp2, temp2, start, pot2, ens2, n_ladders=2, seed=1, save=100, save_dir=d, restart=True)
+    assert res2[0].en_histogram.sum() == 4 * 400
