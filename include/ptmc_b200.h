@@ -39,7 +39,7 @@ extern "C" {
 #define PTMC_API
 #endif
 
-#define PTMC_ABI_VERSION 2
+#define PTMC_ABI_VERSION 3
 #define PTMC_MAX_COEFF 16
 #define PTMC_NCOUNT 10
 
@@ -55,7 +55,8 @@ typedef enum ptmc_status {
 /* src/EnergyEvaluation.jl:891 (ELJPotential), :138 (ELJPotentialEven), :1059 (EmbeddedAtomPotential),
  * :1182 (RuNNerPotential) */
 /* :909-921 (ELJPotentialB: extended Lennard-Jones in a magnetic field, pair energy depends on the angle to the z axis) */
-typedef enum ptmc_pot_kind { PTMC_POT_ELJ = 0, PTMC_POT_ELJ_EVEN = 1, PTMC_POT_EAM = 2, PTMC_POT_RUNNER = 3, PTMC_POT_ELJ_B = 4 } ptmc_pot_kind;
+typedef enum ptmc_pot_kind { PTMC_POT_ELJ = 0, PTMC_POT_ELJ_EVEN = 1, PTMC_POT_EAM = 2, PTMC_POT_RUNNER = 3, PTMC_POT_ELJ_B = 4,
+                             PTMC_POT_LUT = 5 /* :214-295 LookupTablePotential: energy tabulated over (angle to z, distance) */ } ptmc_pot_kind;
 /* src/BoundaryConditions.jl:44,72,89,110 */
 typedef enum ptmc_bc_kind { PTMC_BC_SPHERICAL = 0, PTMC_BC_CUBIC = 1, PTMC_BC_RHOMBIC = 2, PTMC_BC_RECTANGULAR = 3 } ptmc_bc_kind;
 /* src/Ensembles.jl:42 (NVT), :75 (NPT; separated_volume in ptmc_config) */
@@ -133,6 +134,11 @@ typedef struct ptmc_config {
     /* ABI 2: PTMC_POT_ELJ_B only - coeff_a, coeff_b [n_coeff] (coeff_c travels in coeff[])                */
     const double* eljb_a;
     const double* eljb_b;
+    /* ABI 3: PTMC_POT_LUT only - LookupTablePotential fields (src/EnergyEvaluation.jl:214-223); table[l_dist][l_angle]
+     * in the file's order of the ANGLE index slowest is table[(i_angle - 1) * l_dist + (j_dist - 1)]                     */
+    const double* lut_table;
+    int32_t lut_l_dist, lut_l_angle;
+    double lut_start_dist, lut_d_dist, lut_start_angle, lut_d_angle, lut_c6coeff;
 } ptmc_config;
 
 typedef struct ptmc_handle ptmc_handle;

@@ -79,6 +79,7 @@ def load():
         "orc_get_tan": (C.c_double, [C.c_int, _dp, _dp, C.c_double, C.c_double]),
         "orc_dimer_energy_eljb": (C.c_double, [_dp, _dp, _dp, C.c_int, C.c_double, C.c_double]),
         "orc_lrc_eljb": (C.c_double, [C.c_int, C.c_double]),
+        "orc_dimer_energy_lut": (C.c_double, [_dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
         "orc_get_volume": (C.c_double, [C.c_int, C.c_double, C.c_double]),
         "orc_get_r_cut": (C.c_double, [C.c_int, C.c_double, C.c_double]),
         "orc_tempgrid": (None, [C.c_double, C.c_double, C.c_int, _dp, _dp]),
@@ -149,6 +150,13 @@ def get_tan(bc_kind, a, b, L=0.0, h=0.0):
 def dimer_energy_eljb(ca, cb, cc, r2, tan):
     (a, pa), (b, pb), (c, pc) = _arr(ca), _arr(cb), _arr(cc)
     return load().orc_dimer_energy_eljb(pa, pb, pc, len(c), float(r2), float(tan))
+
+
+def dimer_energy_lut(pot, r2, tan):
+    """dimer_energy(::LookupTablePotential); pot: ptmc_b200.host.LookupTablePotential"""
+    tab, pt = _arr(pot.table)
+    return load().orc_dimer_energy_lut(pt, int(pot.l_dist), int(pot.l_angle), float(pot.start_dist), float(pot.d_dist), float(pot.d_angle),
+                                       float(pot.c6coeff), float(r2), float(tan))
 
 
 def lrc_eljb(n_atoms, r_cut):

@@ -272,6 +272,27 @@ double orc_dimer_energy_eljb(const double* ca, const double* cb, const double* c
     }
     return sum1;
 }
+/* dimer_energy(::LookupTablePotential) src/EnergyEvaluation.jl:274-295; table[(i_angle - 1) * l_dist + (j_dist - 1)] */
+double orc_dimer_energy_lut(const double* table, int l_dist, int l_angle, double start_dist, double d_dist, double d_angle,
+                            double c6coeff, double r2, double tan_) {
+    (void)l_angle;
+    int angle_index = 1;
+    if (fabs(tan_) > 0.00872687153 && fabs(tan_) <= 114.592845357)
+        angle_index = (int)rint(atan(fabs(tan_)) / d_angle * 180.0 / M_PI + 1.0);      /* round(Int32, .): ties to even */
+    else if (fabs(tan_) > 114.592845357)
+        angle_index = 91;
+    double e;
+    const double lo = start_dist + 0.5 * d_dist, hi = start_dist + l_dist * d_dist;
+    if (r2 <= lo * lo) {
+        e = table[(size_t)(angle_index - 1) * l_dist];
+    } else if (r2 <= hi * hi) {
+        int dist_index = (int)rint((pow(r2, 0.5) - start_dist) / d_dist);
+        e = table[(size_t)(angle_index - 1) * l_dist + (dist_index - 1)];
+    } else {
+        e = c6coeff / (r2 * r2 * r2);
+    }
+    return e;
+}
 /* lrc(::ELJPotentialB) src/EnergyEvaluation.jl:983-998 */
 double orc_lrc_eljb(int n_atoms, double r_cut) {
     static const double coeff[4] = {-0.1279111890228638, -1.328138539967966, 12.260941135261255, 41.12212408251662};
@@ -361,6 +382,7 @@ typedef struct orc_handle {
     int n_threads;
     orc_runner* runner;
     double *eljb_a, *eljb_b;   /* copies of cfg.eljb_a / eljb_b */
+    double* lut;               /* copy of cfg.lut_table */
 } orc_handle;
 
 static int n_steps_of(const ptmc_config* c) { return c->n_atom_moves + (c->ensemble == PTMC_ENS_NPT ? c->n_volume_moves : 0); }
@@ -412,11 +434,17 @@ static void d2_matrix(const ptmc_config* c, const double* pos, const double* box
     for (int i = 0; i < n; ++i) d2[(size_t)i * n + i] = 0;
 }
 
+/* dimer_energy of the potentials that depend on the angle to the z axis (AbstractDimerPotentialB: ELJPotentialB, LookupTablePotential) */
+static double pair_energy_b(const ptmc_config* c, double r2, double tan_) {
+    if (c->pot_kind == PTMC_POT_LUT)
+        return orc_dimer_energy_lut(c->lut_table, c->lut_l_dist, c->lut_l_angle, c->lut_start_dist, c->lut_d_dist, c->lut_d_angle, c->lut_c6coeff, r2, tan_);
+    return orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, r2, tan_);
+}
 /* dimer_energy_atom with tangents src/EnergyEvaluation.jl:337-346 */
 static double eljb_energy_atom(const ptmc_config* c, int i, const double* d2vec, const double* tanvec, int n) {
     double sum1 = 0.0;
-    for (int j = 0; j < i; ++j) sum1 += orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, d2vec[j], tanvec[j]);
-    for (int j = i + 1; j < n; ++j) sum1 += orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, d2vec[j], tanvec[j]);
+    for (int j = 0; j < i; ++j) sum1 += pair_energy_b(c, d2vec[j], tanvec[j]);
+    for (int j = i + 1; j < n; ++j) sum1 += pair_energy_b(c, d2vec[j], tanvec[j]);
     return sum1;
 }
 
@@ -454,8 +482,8 @@ static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
         s->en_tot = eam_energy(c, s->comp, n); /* initialise_energy :1722-1734 */
     } else if (c->pot_kind == PTMC_POT_RUNNER) {
         /* done by the caller (needs the handle's orc_runner) */
-    } else if (c->pot_kind == PTMC_POT_ELJ_B) {
-        /* set_variables(::ELJPotentialB): get_tantheta_mat! src/Configurations.jl:229-244; dimer_energy_config :476-492 */
+    } else if (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT) {
+        /* set_variables(::ELJPotentialB / ::LookupTablePotential): get_tantheta_mat! src/Configurations.jl:229-244; dimer_energy_config :476-492 */
         for (int i = 0; i < n; ++i)
             for (int j = i + 1; j < n; ++j)
                 s->tan[(size_t)i * n + j] = s->tan[(size_t)j * n + i] = orc_get_tan(c->bc_kind, s->pos + 3 * i, s->pos + 3 * j, s->box[0], s->box[1]);
@@ -463,7 +491,7 @@ static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
         double energy_tot = 0.0;
         for (int i = 0; i < n; ++i)
             for (int j = i + 1; j < n; ++j)
-                energy_tot += orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, s->d2[(size_t)i * n + j], s->tan[(size_t)i * n + j]);
+                energy_tot += pair_energy_b(c, s->d2[(size_t)i * n + j], s->tan[(size_t)i * n + j]);
         s->en_tot = energy_tot;
     } else {
         s->en_tot = dimer_energy_config(c, s->d2, n, npt, s->r_cut, s->box); /* :1662-1693 */
@@ -603,8 +631,8 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
                 s->new_comp[2 * i] += t0; s->new_comp[2 * i + 1] += t1;
             }
             st->new_en = eam_energy(c, s->new_comp, n);
-        } else if (c->pot_kind == PTMC_POT_ELJ_B) {
-            /* energy_update!(::AbstractDimerPotentialB) src/EnergyEvaluation.jl:1508-1533, dimer_energy_update! :822-836 */
+        } else if (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT) {
+            /* energy_update!(::AbstractDimerPotentialB / ::LookupTablePotential) src/EnergyEvaluation.jl:1508-1533, dimer_energy_update! :822-836 */
             for (int j = 0; j < n; ++j) st->new_tan[j] = orc_get_tan(c->bc_kind, trial, s->pos + 3 * j, s->box[0], s->box[1]);
             st->new_tan[i] = 0;
             double delta_en = eljb_energy_atom(c, i, st->new_d2, st->new_tan, n) -
@@ -629,7 +657,7 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             double tmp = s->en_tot; s->en_tot = st->new_en; st->new_en = tmp;
             st->count[PTMC_C_ATOM_TOT] += 1; st->count[PTMC_C_ATOM_ADJ] += 1;
             if (c->pot_kind == PTMC_POT_EAM) { double* t = s->comp; s->comp = s->new_comp; s->new_comp = t; } /* swap_vars! :208-211 */
-            if (c->pot_kind == PTMC_POT_ELJ_B)   /* swap_vars!(::ELJPotentialBVariables) src/swap_config.jl:197-201 */
+            if (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT)   /* swap_vars!(::ELJPotentialBVariables / ::LookupTableVariables) src/swap_config.jl:197-206 */
                 for (int j = 0; j < n; ++j) { s->tan[(size_t)i * n + j] = st->new_tan[j]; s->tan[(size_t)j * n + i] = st->new_tan[j]; }
             if (c->pot_kind == PTMC_POT_RUNNER) {   /* swap_vars!(::NNPVariables) src/swap_config.jl:213-221 */
                 double* t = s->en_atom; s->en_atom = s->new_en_atom; s->new_en_atom = t;
@@ -868,8 +896,15 @@ orc_handle* orc_create(const ptmc_config* cfg) {
     /* ELJPotentialB: the free-space NVT path (scripts/ne13_B.jl); the periodic methods are outside the hot path */
     if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->ensemble != PTMC_ENS_NVT)) return NULL;
     if (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume && cfg->bc_kind != PTMC_BC_RHOMBIC && cfg->bc_kind != PTMC_BC_RECTANGULAR) return NULL;
+    if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91 || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->ensemble != PTMC_ENS_NVT)) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
     H->cfg = *cfg;
+    if (cfg->pot_kind == PTMC_POT_LUT) {
+        const size_t nt_ = (size_t)cfg->lut_l_dist * cfg->lut_l_angle;
+        H->lut = (double*)xcalloc(nt_, sizeof(double));
+        memcpy(H->lut, cfg->lut_table, sizeof(double) * nt_);
+        H->cfg.lut_table = H->lut;
+    } else H->cfg.lut_table = NULL;
     if (cfg->pot_kind == PTMC_POT_ELJ_B) {
         H->eljb_a = (double*)xcalloc(cfg->n_coeff, sizeof(double)); H->eljb_b = (double*)xcalloc(cfg->n_coeff, sizeof(double));
         memcpy(H->eljb_a, cfg->eljb_a, sizeof(double) * cfg->n_coeff); memcpy(H->eljb_b, cfg->eljb_b, sizeof(double) * cfg->n_coeff);
@@ -892,7 +927,7 @@ orc_handle* orc_create(const ptmc_config* cfg) {
         s->d2 = (double*)xcalloc((size_t)n * n, sizeof(double));
         if (npt) { s->trial_pos = (double*)xcalloc(3 * n, sizeof(double)); s->new_d2mat = (double*)xcalloc((size_t)n * n, sizeof(double)); }
         if (cfg->pot_kind == PTMC_POT_EAM) { s->comp = (double*)xcalloc(2 * n, sizeof(double)); s->new_comp = (double*)xcalloc(2 * n, sizeof(double)); }
-        if (cfg->pot_kind == PTMC_POT_ELJ_B) s->tan = (double*)xcalloc((size_t)n * n, sizeof(double));
+        if (cfg->pot_kind == PTMC_POT_ELJ_B || cfg->pot_kind == PTMC_POT_LUT) s->tan = (double*)xcalloc((size_t)n * n, sizeof(double));
         if (cfg->pot_kind == PTMC_POT_RUNNER) {
             const size_t ns = (size_t)orc_runner_nsym(H->runner);
             s->fmat = (double*)xcalloc((size_t)n * n, 8); s->new_f = (double*)xcalloc(n, 8);
@@ -929,7 +964,7 @@ void orc_destroy(orc_handle* H) {
     free(H->en_min); free(H->en_max); free(H->v_min); free(H->v_max); free(H->en_hist); free(H->ev_hist);
     free(H->tr_index); free(H->tr_de); free(H->tr_acc); free(H->tr_exc);
     orc_runner_free(H->runner);
-    free(H->eljb_a); free(H->eljb_b);
+    free(H->eljb_a); free(H->eljb_b); free(H->lut);
     free(H);
 }
 
@@ -1132,7 +1167,7 @@ int orc_import_config(orc_handle* H, int64_t ladder, int32_t slot, const double*
     s->box[0] = buf[3 * n]; s->box[1] = buf[3 * n + 1];
     /* derived matrices are functions of the positions alone in free space (distance2 and get_tan are symmetric bit for bit) */
     d2_matrix(c, s->pos, s->box, s->d2, n);
-    if (c->pot_kind == PTMC_POT_ELJ_B) {
+    if (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT) {
         for (int i = 0; i < n; ++i)
             for (int j = i + 1; j < n; ++j)
                 s->tan[(size_t)i * n + j] = s->tan[(size_t)j * n + i] = orc_get_tan(c->bc_kind, s->pos + 3 * i, s->pos + 3 * j, s->box[0], s->box[1]);

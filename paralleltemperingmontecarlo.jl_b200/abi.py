@@ -10,11 +10,11 @@ import pathlib
 PKG_DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libptmc_b200.so"
 
-PTMC_ABI_VERSION = 2
+PTMC_ABI_VERSION = 3
 PTMC_MAX_COEFF = 16
 PTMC_NCOUNT = 10
 
-POT_ELJ, POT_ELJ_EVEN, POT_EAM, POT_RUNNER, POT_ELJ_B = 0, 1, 2, 3, 4
+POT_ELJ, POT_ELJ_EVEN, POT_EAM, POT_RUNNER, POT_ELJ_B, POT_LUT = 0, 1, 2, 3, 4, 5
 BC_SPHERICAL, BC_CUBIC, BC_RHOMBIC, BC_RECTANGULAR = 0, 1, 2, 3
 ENS_NVT, ENS_NPT = 0, 1
 RNG_XOSHIRO, RNG_REPLAY, RNG_BATCH8 = 0, 1, 2
@@ -57,6 +57,9 @@ class Config(C.Structure):
         ("seed", C.c_uint64),
         ("lanes_per_replica", C.c_int32), ("separated_volume", C.c_int32),
         ("eljb_a", _dp), ("eljb_b", _dp),
+        ("lut_table", _dp), ("lut_l_dist", C.c_int32), ("lut_l_angle", C.c_int32),
+        ("lut_start_dist", C.c_double), ("lut_d_dist", C.c_double), ("lut_start_angle", C.c_double), ("lut_d_angle", C.c_double),
+        ("lut_c6coeff", C.c_double),
     ]
 
 

@@ -278,6 +278,11 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             if (!c->eljb_a || !c->eljb_b) return fail(nullptr, PTMC_ERR_ARG, "pot_kind ELJ_B needs ptmc_config.eljb_a / eljb_b");
             if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "ELJPotentialB is built for SphericalBC/NVT (scripts/ne13_B.jl); its periodic methods are outside the hot path");
             break;
+        case PTMC_POT_LUT:
+            if (!c->lut_table || c->lut_l_dist < 1 || c->lut_l_angle < 91 || !(c->lut_d_dist > 0) || !(c->lut_d_angle > 0))
+                return fail(nullptr, PTMC_ERR_ARG, "pot_kind LUT needs lut_table [l_angle >= 91][l_dist >= 1] and positive grid steps");
+            if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "LookupTablePotential is built for SphericalBC/NVT (scripts/ne13-lookup.jl); its periodic methods are outside the hot path");
+            break;
         case PTMC_POT_EAM:
             if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
             if (!(c->eam_n > 0 && c->eam_n <= 24 && c->eam_m > 0 && c->eam_m <= 24)) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential exponents n, m must be in (0, 24] (series of eam_invrexp)");
@@ -302,6 +307,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->cfg.betas = h->betas.data();
     h->cfg.runner = nullptr;
     h->cfg.eljb_a = nullptr; h->cfg.eljb_b = nullptr;      // copied into DevParams below
+    h->cfg.lut_table = nullptr;                              // copied to the device below
     h->runner = c->pot_kind == PTMC_POT_RUNNER;
     h->device = c->device;
     h->geom = sphere ? GEOM_SPHERE : (c->bc_kind == PTMC_BC_RHOMBIC ? GEOM_RHOMB : GEOM_PBC);
@@ -390,6 +396,15 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         if (cudaMemcpy(d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(h, PTMC_ERR_CUDA, "copying the EAM power tables failed"));
         P.eam_ktab = d_tab; P.eam_etab = d_tab + PTMC_EAM_KTAB_DOUBLES;
+    }
+    if (c->pot_kind == PTMC_POT_LUT) {
+        double* d_lut = nullptr;
+        const size_t nt = (size_t)c->lut_l_dist * c->lut_l_angle;
+        if ((rc = dev_alloc(h, &d_lut, nt))) return bail(rc);
+        if (cudaMemcpy(d_lut, c->lut_table, sizeof(double) * nt, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(h, PTMC_ERR_CUDA, "copying the lookup table failed"));
+        P.lut_table = d_lut; P.lut_l_dist = c->lut_l_dist;
+        P.lut_start = c->lut_start_dist; P.lut_d = c->lut_d_dist; P.lut_dang = c->lut_d_angle; P.lut_c6 = c->lut_c6coeff;
     }
     P.betas = d_betas; P.en_min = en_min; P.en_max = en_max; P.v_min = v_min; P.v_max = v_max;
     P.error = h->d_error;

@@ -40,6 +40,10 @@ struct DevParams {
     double min_acc, max_acc, pressure;
     double coeff[PTMC_MAX_COEFF];
     double eljb_ca[PTMC_MAX_COEFF], eljb_cb[PTMC_MAX_COEFF];   // ELJPotentialB: c_i a_i, c_i b_i (c_i in coeff[])
+    // LookupTablePotential (src/EnergyEvaluation.jl:214-223): table [l_angle][l_dist] in HBM (L2 resident, ~1 MB)
+    const double* lut_table;
+    int lut_l_dist;
+    double lut_start, lut_d, lut_dang, lut_c6;
     double eam_hn, eam_hm;               // n/2, m/2  (r^-n = (r2)^-(n/2))
     double eam_ean, eam_ecam;
     // table-driven (r2)^-p, p = n/2 and m/2 (eam_invrexp): binomial coefficients binom(-p, 1..6) and the tables
@@ -276,6 +280,24 @@ __device__ __forceinline__ double eljb_energy(const DevParams& P, double r2, dou
     const double w1 = fma(P.eljb_cb[0], t4, fma(P.eljb_ca[0], t2, P.coeff[0]));
     const double s = (x * x * x) * fma(x, p, w1);
     return r2 >= 5.30 ? s : 0.1;
+}
+
+// dimer_energy(::LookupTablePotential) src/EnergyEvaluation.jl:274-295 with get_tan (src/Configurations.jl:177-180) of the
+// separation (dx, dy, dz): the table indices are decisions, so the index arithmetic keeps the reference's operation order.
+__device__ __forceinline__ double lut_energy(const DevParams& P, double r2, double dx, double dy, double dz) {
+    const double t = fabs(xdiv(sqrt(xadd(xmul(dx, dx), xmul(dy, dy))), dz));
+    int ai = 1;
+    if (t > 0.00872687153 && t <= 114.592845357) ai = (int)rint(xadd(xdiv(xmul(xdiv(atan(t), P.lut_dang), 180.0), 3.14159265358979323846), 1.0));
+    else if (t > 114.592845357) ai = 91;
+    const double lo = xadd(P.lut_start, xmul(0.5, P.lut_d)), hi = xadd(P.lut_start, xmul((double)P.lut_l_dist, P.lut_d));
+    const double* row = P.lut_table + (size_t)(ai - 1) * P.lut_l_dist;
+    if (r2 <= xmul(lo, lo)) return __ldg(row);
+    if (r2 <= xmul(hi, hi)) {
+        int di = (int)rint(xdiv(xsub(sqrt(r2), P.lut_start), P.lut_d));
+        di = di < 1 ? 1 : di;              // (the reference indexes table[.., 0] -> BoundsError if the quotient rounds to 0)
+        return __ldg(row + di - 1);
+    }
+    return xdiv(P.lut_c6, xmul(xmul(r2, r2), r2));
 }
 
 // NC = 6: the six-coefficient form of every BASELINE script, fully unrolled; NC = 0: runtime n_coeff

@@ -12,6 +12,7 @@ void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st) {
     if (P.pot_kind == PTMC_POT_EAM) init_kernel<PTMC_POT_EAM><<<blocks, threads, 0, st>>>(P, n_rep);
     else if (P.pot_kind == PTMC_POT_ELJ) init_kernel<PTMC_POT_ELJ><<<blocks, threads, 0, st>>>(P, n_rep);
     else if (P.pot_kind == PTMC_POT_ELJ_B) init_kernel<PTMC_POT_ELJ_B><<<blocks, threads, 0, st>>>(P, n_rep);
+    else if (P.pot_kind == PTMC_POT_LUT) init_kernel<PTMC_POT_LUT><<<blocks, threads, 0, st>>>(P, n_rep);
     else init_kernel<PTMC_POT_ELJ_EVEN><<<blocks, threads, 0, st>>>(P, n_rep);
 }
 

@@ -367,8 +367,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);     // parked atoms contribute exactly 0
                                 } else {
                                     // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
-                                    const double en_j = POT == PTMC_POT_ELJ_B ? eljb_energy<NC>(P, d2n, az * az) : pair_energy<POT, NC>(P, d2n);
-                                    const double eo_j = POT == PTMC_POT_ELJ_B ? eljb_energy<NC>(P, d2o, bz_ * bz_) : pair_energy<POT, NC>(P, d2o);
+                                    const double en_j = POT == PTMC_POT_ELJ_B ? eljb_energy<NC>(P, d2n, az * az)
+                                                      : POT == PTMC_POT_LUT ? lut_energy(P, d2n, ax, ay, az) : pair_energy<POT, NC>(P, d2n);
+                                    const double eo_j = POT == PTMC_POT_ELJ_B ? eljb_energy<NC>(P, d2o, bz_ * bz_)
+                                                      : POT == PTMC_POT_LUT ? lut_energy(P, d2o, bx_, by_, bz_) : pair_energy<POT, NC>(P, d2o);
                                     accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                 }
                             };
@@ -806,6 +808,7 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                     double dx = xa - gp[3 * j], dy = ya - gp[3 * j + 1], dz = za - gp[3 * j + 2];
                     d2 = fma(dz, dz, fma(dy, dy, dx * dx));
                     if (POT == PTMC_POT_ELJ_B) { acc += eljb_energy(P, d2, dz * dz); continue; }
+                    if (POT == PTMC_POT_LUT) { acc += lut_energy(P, d2, dx, dy, dz); continue; }
                 }
                 if (!npt || d2 <= rcut) acc += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT>(P, d2);
             }

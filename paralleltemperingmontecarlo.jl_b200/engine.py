@@ -48,6 +48,7 @@ class SweepConfig:
     coeff: tuple = ()
     eam: tuple = (0.0, 0.0, 0.0, 0.0)  # n, m, ean, eCam
     eljb_ab: tuple | None = None       # ELJPotentialB: (coeff_a, coeff_b); coeff_c in `coeff`
+    lut: object | None = None           # LookupTablePotential (host.LookupTablePotential)
     runner: RunnerParams | None = None
     bc_kind: int = abi.BC_SPHERICAL
     ensemble: int = abi.ENS_NVT
@@ -105,6 +106,16 @@ class SweepConfig:
             self._keep += [ea, eb]
             c.eljb_a = ea.ctypes.data_as(C.POINTER(C.c_double))
             c.eljb_b = eb.ctypes.data_as(C.POINTER(C.c_double))
+        if self.lut is not None:
+            tab = np.ascontiguousarray(self.lut.table, dtype=np.float64)          # [l_angle][l_dist]
+            if tab.shape != (self.lut.l_angle, self.lut.l_dist):
+                raise ValueError("lookup table must be [l_angle][l_dist]")
+            self._keep.append(tab)
+            c.lut_table = tab.ctypes.data_as(C.POINTER(C.c_double))
+            c.lut_l_dist, c.lut_l_angle = int(self.lut.l_dist), int(self.lut.l_angle)
+            c.lut_start_dist, c.lut_d_dist = float(self.lut.start_dist), float(self.lut.d_dist)
+            c.lut_start_angle, c.lut_d_angle = float(self.lut.start_angle), float(self.lut.d_angle)
+            c.lut_c6coeff = float(self.lut.c6coeff)
         if self.runner is not None:
             r = self.runner
             d = abi.RunnerDesc()

@@ -205,6 +205,33 @@ class ELJPotentialB:
     kind = abi.POT_ELJ_B
 
 
+class LookupTablePotential:
+    """src/EnergyEvaluation.jl:214-262: pair energy tabulated over (angle between the pair and the z axis, distance);
+    `LookupTablePotential(file)` reads the reference's table format (read_lookuptable :231-260): line 1 `l_dist, start_dist,
+    d_dist`, line 2 `l_angle, start_angle, d_angle`, then l_angle x l_dist values with the angle index slowest; `!` starts a
+    comment.  c6coeff = mean_i table[i, 1000] * (start_dist + 1000 d_dist)^6 carries the tail beyond the table."""
+    kind = abi.POT_LUT
+
+    def __init__(self, source, start_dist=None, start_angle=None, d_dist=None, d_angle=None, c6coeff=None):
+        if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__"):
+            with open(source) as f:
+                first = f.readline().split("!")[0].split(", ")
+                l_dist, self.start_dist, self.d_dist = int(first[0]), float(first[1]), float(first[2])
+                second = f.readline().split("!")[0].split(", ")
+                l_angle, self.start_angle, self.d_angle = int(second[0]), float(second[1]), float(second[2])
+                vals = [float(f.readline().split("!")[0]) for _ in range(l_angle * l_dist)]
+            self.table = np.array(vals, dtype=np.float64).reshape(l_angle, l_dist)
+            avg_lr = 0.0
+            for i in range(l_angle):                       # sequential sum, then the division (:253-257)
+                avg_lr += self.table[i, 999]
+            avg_lr /= l_angle
+            self.c6coeff = avg_lr * (self.start_dist + 1000 * self.d_dist) ** 6
+        else:
+            self.table = np.ascontiguousarray(source, dtype=np.float64)
+            self.start_dist, self.start_angle, self.d_dist, self.d_angle, self.c6coeff = start_dist, start_angle, d_dist, d_angle, c6coeff
+        self.l_angle, self.l_dist = self.table.shape
+
+
 class EmbeddedAtomPotential:
     """src/EnergyEvaluation.jl:1059-1073: EmbeddedAtomPotential(n, m, eps, C, a)"""
     kind = abi.POT_EAM
@@ -258,6 +285,8 @@ def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, e
     elif potential.kind == abi.POT_ELJ_B:
         kw["coeff"] = tuple(potential.coeff_c)
         kw["eljb_ab"] = (tuple(potential.coeff_a), tuple(potential.coeff_b))
+    elif potential.kind == abi.POT_LUT:
+        kw["lut"] = potential
     elif potential.kind == abi.POT_EAM:
         kw["eam"] = (potential.n, potential.m, potential.ean, potential.eCam)
     else:
@@ -489,6 +518,14 @@ def deck_ne13_B(n_traj=16, cycles=1000):
     mcp, _, _, _, ens = deck_ne13(n_traj, cycles)
     start = Config(_geom("ne13"), SphericalBC(radius=5.32))
     return mcp, TempGrid(9.0, 16.0, n_traj), start, ELJPotentialB(ELJB_NE_A, ELJB_NE_B, ELJB_NE_C), ens
+
+
+def deck_ne13_lookup(table, n_traj=25, cycles=1000):
+    """scripts/ne13-lookup.jl: Ne13 with a LookupTablePotential (`table`: a file in the reference's format, e.g.
+    scripts/lookup-tables/LookupTable_Neon_B0.0_MP2.txt, or a LookupTablePotential), NVT, 25 temperatures 4-16 K, Angstrom."""
+    mcp, _, _, _, ens = deck_ne13(n_traj, cycles)
+    pot = table if isinstance(table, LookupTablePotential) else LookupTablePotential(table)
+    return mcp, TempGrid(4.0, 16.0, n_traj), Config(_geom("ne13"), SphericalBC(radius=5.32)), pot, ens
 
 
 def deck_ne55(n_traj=24, cycles=1000):

@@ -17,7 +17,7 @@ using ParallelTemperingMonteCarlo: MCParams, TempGrid, Config, MCState, Output, 
 
 export B200Backend, ptmc_run!
 
-const PTMC_ABI_VERSION = Int32(2)
+const PTMC_ABI_VERSION = Int32(3)
 const PTMC_MAX_COEFF = 16
 const PTMC_NCOUNT = 10
 
@@ -63,6 +63,14 @@ struct PtmcConfig
     separated_volume::Int32
     eljb_a::Ptr{Float64}       # ABI 2: ELJPotentialB coeff_a / coeff_b (coeff_c travels in coeff)
     eljb_b::Ptr{Float64}
+    lut_table::Ptr{Float64}    # ABI 3: LookupTablePotential (table transposed to [l_angle][l_dist] row-major = Julia's table' column-major)
+    lut_l_dist::Int32
+    lut_l_angle::Int32
+    lut_start_dist::Float64
+    lut_d_dist::Float64
+    lut_start_angle::Float64
+    lut_d_angle::Float64
+    lut_c6coeff::Float64
 end
 
 bc_kind(::SphericalBC) = Int32(0); bc_kind(::CubicBC) = Int32(1); bc_kind(::RhombicBC) = Int32(2); bc_kind(::RectangularBC) = Int32(3)
@@ -73,6 +81,7 @@ box_of(bc::Union{RhombicBC,RectangularBC}) = (bc.box_length, bc.box_height)
 pot_fields(p::ELJPotential{N}) where {N} = (Int32(0), Int32(N), Tuple(p.coeff), (0.0, 0.0, 0.0, 0.0))
 pot_fields(p::ELJPotentialEven{N}) where {N} = (Int32(1), Int32(N), Tuple(p.coeff), (0.0, 0.0, 0.0, 0.0))
 pot_fields(p::EmbeddedAtomPotential) = (Int32(2), Int32(0), (), (p.n, p.m, p.ean, p.eCam))
+pot_fields(p::LookupTablePotential) = (Int32(5), Int32(0), (), (0.0, 0.0, 0.0, 0.0))                       # SphericalBC / NVT only
 pot_fields(p::ELJPotentialB{N}) where {N} = (Int32(4), Int32(N), Tuple(p.coeff_c), (0.0, 0.0, 0.0, 0.0))   # SphericalBC / NVT only
 
 pad16(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, PTMC_MAX_COEFF)
@@ -103,13 +112,18 @@ function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCPara
     betas = collect(Float64, temp.beta_grid)
     ea = potential isa ELJPotentialB ? collect(Float64, potential.coeff_a) : Float64[]
     eb = potential isa ELJPotentialB ? collect(Float64, potential.coeff_b) : Float64[]
+    islut = potential isa LookupTablePotential
+    lut = islut ? collect(Float64, permutedims(potential.table)) : Float64[]        # memory order: distance index fastest
     cfg = Ref(PtmcConfig(PTMC_ABI_VERSION, b.device, L, T, N, npt ? 1 : 0, ensemble.n_atom_moves,
         npt ? ensemble.n_volume_moves : 0, bc_kind(bc), npt ? ensemble.pressure : 0.0, pk, nc, pad16(coeff),
         eam..., C_NULL, pointer(betas), mc_params.n_adjust, mc_params.mc_sample, mc_params.n_bin, b.rng_mode,
         mc_params.min_acc, mc_params.max_acc, b.seed, b.lanes_per_replica, (npt && ensemble.separated_volume) ? 1 : 0,
-        isempty(ea) ? Ptr{Float64}(C_NULL) : pointer(ea), isempty(eb) ? Ptr{Float64}(C_NULL) : pointer(eb)))
+        isempty(ea) ? Ptr{Float64}(C_NULL) : pointer(ea), isempty(eb) ? Ptr{Float64}(C_NULL) : pointer(eb),
+        islut ? pointer(lut) : Ptr{Float64}(C_NULL), islut ? potential.l_dist : Int32(0), islut ? potential.l_angle : Int32(0),
+        islut ? potential.start_dist : 0.0, islut ? potential.d_dist : 0.0, islut ? potential.start_angle : 0.0,
+        islut ? potential.d_angle : 0.0, islut ? potential.c6coeff : 0.0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve betas ea eb begin
+    GC.@preserve betas ea eb lut begin
         rc = ccall((:ptmc_create, lib), Cint, (Ref{PtmcConfig}, Ref{Ptr{Cvoid}}), cfg, h)
     end
     rc == 0 || error("libptmc_b200: " * unsafe_string(ccall((:ptmc_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))

@@ -627,3 +627,38 @@ def test_ptmc_run_save_restart_other_potentials(tmp_path):
     mcp2.mc_cycles = 400
     _, res2 = P.ptmc_run(mcp2, temp2, start, pot2, ens2, n_ladders=2, seed=1, save=100, save_dir=d, restart=True)
     assert res2[0].en_histogram.sum() == 4 * 400
+
+
+def _synthetic_lookup_table():
+    # a table in the reference's layout filled from a smooth anisotropic pair energy (Angstrom units like scripts/ne13-lookup.jl)
+    l_dist, start, dd = 1100, 2.0, 0.005
+    r = start + dd * np.arange(1, l_dist + 1)
+    ang = np.deg2rad(np.arange(91.0))
+    e0 = 1.2e-4 * ((3.1 / r) ** 12 - 2 * (3.1 / r) ** 6)
+    table = e0[None, :] * (1 + 0.2 * np.cos(2 * ang)[:, None])
+    c6 = table[:, 999].mean() * (start + 1000 * dd) ** 6
+    return P.LookupTablePotential(table, start_dist=start, start_angle=0.0, d_dist=dd, d_angle=1.0, c6coeff=c6)
+
+
+def test_lookup_table_potential(tmp_path, oracle):
+    # LookupTablePotential (src/EnergyEvaluation.jl:214-295), SphericalBC / NVT as scripts/ne13-lookup.jl (part of the reference's
+    # runtests): table indices from the angle to z and the distance; replayed decisions identical, production trajectory identical
+    pot = _synthetic_lookup_table()
+    # through the file format of read_lookuptable as well
+    f = tmp_path / "lut.txt"
+    with open(f, "w") as fh:
+        fh.write("%d, %r, %r ! distances\n%d, 0.0, 1.0\n" % (pot.l_dist, pot.start_dist, pot.d_dist, pot.l_angle))
+        fh.writelines("%r\n" % float(v) for v in pot.table.reshape(-1))
+    pot_f = P.LookupTablePotential(f)
+    assert np.array_equal(pot_f.table, pot.table) and pot_f.c6coeff == pytest.approx(pot.c6coeff, rel=1e-15) and pot_f.start_dist == pot.start_dist
+    mcp, temp, start, _, ens = P.host.deck_ne13_lookup(pot_f, n_traj=8, cycles=40)
+    gpu, cpu = run_pair(mcp, temp, start, pot_f, ens, n_ladders=2, n_cycles=40, seed=29)
+    compare_traces(gpu, cpu)
+    assert 0.05 < gpu["trace"]["accepted"].mean() < 0.999
+    res = _free_run_pair((mcp, temp, start, pot_f, ens), 3, 31, abi.RNG_BATCH8, 60, bounds=(-0.02, 0.0))
+    _assert_same_trajectory(res, e_rtol=1e-10)
+    (sg, _, _), _ = res
+    eng = Engine(sweep_config(mcp, temp, start, pot_f, ens, n_ladders=3, seed=1))
+    eng.upload_states(sg["pos"], sg["box"])
+    np.testing.assert_allclose(eng.download_states(("en_tot",))["en_tot"], sg["en_tot"], rtol=1e-11)
+    eng.close()

@@ -147,3 +147,27 @@ def test_eljb_rhombic_three_atom_energy(oracle):
                 e += oracle.dimer_energy_eljb(ELJB_NE_A, ELJB_NE_B, ELJB_NE_C, d2, oracle.get_tan(abi.BC_RHOMBIC, v[i], v[j], L, h))
     e = e + oracle.lrc_eljb(3, r_cut) * 3 / 4 * L / h
     assert e == -0.00016263185592172208
+
+
+REF_LUT = "/root/reference/scripts/lookup-tables"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_LUT), reason="the reference tree (its lookup tables) is not on this machine")
+def test_lookup_table_reader_and_energy(oracle):
+    # test/test_potentials.jl:58-65: LookupTablePotential(look-up_table-2.txt): table[1][1], start_dist, start_angle, size
+    pot = P.LookupTablePotential(REF_LUT + "/look-up_table-2.txt")
+    assert pot.table[0, 0] == 282.19449125205114 and pot.start_dist == 0.1 and pot.start_angle == 0
+    assert pot.table.size == pot.l_angle * pot.l_dist == 91 * 1491
+    # c6coeff (src/EnergyEvaluation.jl:252-258) and the three branches of dimer_energy (:274-295) against a direct evaluation
+    avg = 0.0
+    for i in range(pot.l_angle):
+        avg += pot.table[i, 999]
+    assert pot.c6coeff == avg / pot.l_angle * (pot.start_dist + 1000 * pot.d_dist) ** 6
+    r2, tan = 3.21 ** 2, 0.75
+    ai = int(round(math.atan(tan) / pot.d_angle * 180.0 / math.pi + 1.0))
+    di = int(round((r2 ** 0.5 - pot.start_dist) / pot.d_dist))
+    assert oracle.dimer_energy_lut(pot, r2, tan) == pot.table[ai - 1, di - 1]
+    assert oracle.dimer_energy_lut(pot, 0.01 ** 2, 0.001) == pot.table[0, 0]                       # inside the first distance bin, angle bin 1
+    assert oracle.dimer_energy_lut(pot, 4.0, 1e3) == pot.table[90, int(round((2.0 - pot.start_dist) / pot.d_dist)) - 1]   # |tan| > 114.59 -> angle bin 91
+    far = (pot.start_dist + pot.l_dist * pot.d_dist + 1.0) ** 2
+    assert oracle.dimer_energy_lut(pot, far, 0.3) == pot.c6coeff / far ** 3

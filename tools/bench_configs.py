@@ -20,10 +20,17 @@ import ptmc_b200 as P  # noqa: E402
 from ptmc_b200.engine import Engine  # noqa: E402
 from ptmc_b200.host import initial_arrays, sweep_config  # noqa: E402
 
+import os  # noqa: E402
+
+LUT_FILE = os.environ.get("PTMC_LUT_FILE", str(ROOT / "paralleltemperingmontecarlo.jl_b200" / "data" / "_lut" / "LookupTable_Neon_B0.0_MP2.txt"))
+
 CASES = {
     # name: (deck factory, ladders, warm-up cycles, timed cycles per step, steps, histogram window)
     "c1_ne13_elj_nvt_32T": (lambda: P.host.deck_ne13(n_traj=32, cycles=100), 8192, 200, 100, 5, (-0.01, 0.0, None, None)),
     "c1b_ne13_eljb_nvt_16T": (lambda: P.host.deck_ne13_B(n_traj=16, cycles=100), 8192, 200, 100, 5, (-0.02, 0.0, None, None)),
+    # scripts/ne13-lookup.jl; needs the reference's scripts/lookup-tables/LookupTable_Neon_B0.0_MP2.txt (not redistributed here):
+    # PTMC_LUT_FILE or paralleltemperingmontecarlo.jl_b200/data/_lut/ (git-ignored); the case is skipped without it
+    "c1c_ne13_lookup_nvt_25T": (lambda: P.host.deck_ne13_lookup(LUT_FILE, n_traj=25, cycles=100), 8192, 200, 100, 5, (-0.02, 0.0, None, None)),
     "c2_ne55_elj_nvt_24T": (lambda: P.host.deck_ne55(n_traj=24, cycles=100), 4096, 200, 50, 5, (-0.1, 0.0, None, None)),
     "c3_cu55_eam_nvt_28T": (lambda: P.host.deck_cu55_eam(n_traj=28, cycles=100), 2048, 100, 20, 5, (-8.0, -5.0, None, None)),
     "c4_pbc216_elj_npt_16T": (lambda: P.host.deck_pbc216(n_traj=16, cycles=100), 592, 20, 40, 3, None),
@@ -67,7 +74,7 @@ def run(name):
 
 
 CPU_SAMPLE = {   # ladders, cycles for the CPU-oracle sample of each config (a few seconds on 16 cores)
-    "c1_ne13_elj_nvt_32T": (64, 400), "c1b_ne13_eljb_nvt_16T": (64, 200), "c2_ne55_elj_nvt_24T": (64, 100), "c3_cu55_eam_nvt_28T": (32, 40),
+    "c1_ne13_elj_nvt_32T": (64, 400), "c1b_ne13_eljb_nvt_16T": (64, 200), "c1c_ne13_lookup_nvt_25T": (64, 200), "c2_ne55_elj_nvt_24T": (64, 100), "c3_cu55_eam_nvt_28T": (32, 40),
     "c4_pbc216_elj_npt_16T": (16, 20), "c5_cu55_runner_nvt_28T": (1, 1),
 }
 
@@ -103,6 +110,9 @@ def main():
     a = ap.parse_args()
     names = [n for n in CASES if not a.only or any(n.startswith(p) for p in a.only.split(","))]
     for n in names:
+        if "lookup" in n and not os.path.exists(LUT_FILE):
+            print(json.dumps({"config": n, "skipped": "lookup table file not present (PTMC_LUT_FILE)"}), flush=True)
+            continue
         t0 = time.time()
         r = run(n)
         if a.cpu:
