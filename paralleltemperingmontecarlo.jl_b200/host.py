@@ -364,7 +364,7 @@ def _ladder_dir(save_dir, ladder: int, n_ladders: int):
 def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensemble, *, n_ladders: int = 1,
              seed: int = 1234, device: int = 0, engine_cls=Engine, engine_kwargs=None, chunk: int = 100000,
              shared_bounds: bool = False, lanes_per_replica: int = 0, rdfsave: bool = False, save=False,
-             save_dir="./checkpoint", restart: bool = False):
+             save_dir="./checkpoint", restart: bool = False, saveconfigs=False, configsname: str = "configuration"):
     """ptmc_run! (src/MCRun.jl:363-432, restart method :434-488) for `n_ladders` independent ladders batched on one device.
 
     Returns (states, results): `states` is the dict of `Engine.download_states()` (per ladder, per slot),
@@ -374,6 +374,8 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
     rdfsave: radial distribution histograms every 1000 cycles (src/Sampling.jl:282-316), `results[l].rdf`.
     save: False or a cycle count: every `save` cycles (and at the end) the reference's checkpoint files are written to
     `save_dir` (one sub-directory `ladder<l>` per ladder when n_ladders > 1), readsave.py / src/ReadSave.jl.
+    saveconfigs: False or a cycle count: every `saveconfigs` cycles the configurations are written as
+    `<save_dir>/<configsname><i>T<k>.xyz` (save_configs(mc_states, string(configsname, i)), src/MCRun.jl:413-415).
     restart: continue from the checkpoint in `save_dir` (configurations, step sizes, total counters, histograms, cycle
     index); equilibration is skipped (src/MCRun.jl:337-339)."""
     from . import readsave
@@ -468,6 +470,8 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
             stop = min(i + chunk - 1, mc_params.mc_cycles)
             if save:
                 stop = min(stop, (i + save - 1) // save * save)
+            if saveconfigs:
+                stop = min(stop, (i + saveconfigs - 1) // saveconfigs * saveconfigs)
             if rdfsave:
                 stop = min(stop, (i + 999) // 1000 * 1000)
             eng.run_cycles(i, stop - i + 1, True)
@@ -476,6 +480,12 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
             if save and stop % save == 0:
                 write_checkpoint(stop)
                 last_saved = stop
+            if saveconfigs and stop % saveconfigs == 0:
+                snap = eng.download_states()
+                for l in range(n_ladders):
+                    d = _ladder_dir(save_dir, l, n_ladders)
+                    d.mkdir(parents=True, exist_ok=True)
+                    readsave.save_configs(snap, l, bc0.kind, d, filename="%s%d" % (configsname, stop))
             i = stop + 1
         if save and last_saved != mc_params.mc_cycles:
             write_checkpoint(mc_params.mc_cycles)                                 # :424-427

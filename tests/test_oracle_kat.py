@@ -171,3 +171,13 @@ def test_lookup_table_reader_and_energy(oracle):
     assert oracle.dimer_energy_lut(pot, 4.0, 1e3) == pot.table[90, int(round((2.0 - pot.start_dist) / pot.d_dist)) - 1]   # |tan| > 114.59 -> angle bin 91
     far = (pot.start_dist + pot.l_dist * pot.d_dist + 1.0) ** 2
     assert oracle.dimer_energy_lut(pot, far, 0.3) == pot.c6coeff / far ** 3
+
+
+def test_tangent_known_answers(oracle):
+    # test/runtests.jl:168-197 "Tangent" (get_tan returns absolute values, so the reference marks the signed ones broken)
+    v1, v2, v3 = [5.0, 0.0, 0.0], [-3.0, 0.0, 4.0], [-2.0, 0.0, -3.0]
+    assert oracle.get_tan(abi.BC_SPHERICAL, v1, v2) == 2.0 and oracle.get_tan(abi.BC_SPHERICAL, v1, v3) == 7 / 3 and oracle.get_tan(abi.BC_SPHERICAL, v2, v3) == 1 / 7
+    assert oracle.get_tan(abi.BC_CUBIC, v1, v2, 10.0, 10.0) == 1 / 2 and oracle.get_tan(abi.BC_CUBIC, v1, v3, 10.0, 10.0) == 1.0
+    assert oracle.get_tan(abi.BC_CUBIC, v2, v3, 10.0, 10.0) == 1 / 3
+    assert oracle.get_tan(abi.BC_RHOMBIC, v1, v2, 5.0, 5.0) == 2.0 and oracle.get_tan(abi.BC_RHOMBIC, v2, v3, 5.0, 5.0) == 0.5
+    assert oracle.get_tan(abi.BC_RHOMBIC, v1, v3, 5.0, 5.0) == 1.0

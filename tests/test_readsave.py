@@ -138,3 +138,19 @@ def test_ptmc_run_save_restart_npt_separated(tmp_path, oracle):
     mcp2.mc_cycles = 90
     st2, res2 = P.host.ptmc_run(mcp2, temp2, cfgs, pot2, ens2, n_ladders=1, seed=3, engine_cls=orc.OracleEngine, save=30, save_dir=tmp_path, restart=True)
     assert res2[0].ev_histogram.sum() == 3 * 90 and readsave.rebuild_states(3, tmp_path, npt=True)[-1] == 90
+
+
+def test_saveconfigs_files_like_the_reference_test(tmp_path, oracle):
+    # test/ne13_test.jl ("Saveconfigs"): ptmc_run!(...; save = 1000, saveconfigs = k, configsname = "Configurations") writes
+    # ./checkpoint/Configurations<i>T<t>.xyz whose atom lines are "1  " * join(position, " ") * " "
+    from oracle import oracle as orc
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=5, cycles=300)
+    st, res = P.host.ptmc_run(mcp, temp, start, pot, ens, n_ladders=1, seed=9, engine_cls=orc.OracleEngine, save=100, save_dir=tmp_path,
+                              saveconfigs=150, configsname="Configurations")
+    assert (tmp_path / "Configurations150T1.xyz").exists() and not (tmp_path / "Configurations100T1.xyz").exists()
+    for t in range(1, 6):
+        lines = (tmp_path / f"Configurations300T{t}.xyz").read_text().splitlines()
+        assert lines[0] == "13" and lines[1].startswith("SphericalBC{Float64} r2: ")
+        for a, line in enumerate(lines[2:]):
+            assert line[:3] == "1  " and line[3:] == " ".join(readsave.jl_float(v) for v in st["pos"][0, t - 1, a]) + " "
+            assert [float(x) for x in line.split()[1:]] == list(st["pos"][0, t - 1, a])
