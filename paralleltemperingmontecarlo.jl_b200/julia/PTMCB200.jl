@@ -101,7 +101,7 @@ back to the host only where the reference's driver touches them (histogram bound
 end of run).
 """
 function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCParams, temp::TempGrid, start_config,
-                                               potential, ensemble; rdfsave=false, save=false, saveconfigs=false, kwargs...)
+                                               potential, ensemble; rdfsave=false, save=false, saveconfigs=false, configsname="configuration", kwargs...)
     lib = b.lib
     # the package's own initialisation builds MCStates (host copies), MoveStrategy and the empty Output
     mc_states, move_strategy, results, n_steps, _ = initialisation(mc_params, temp, start_config, potential, ensemble)
@@ -165,7 +165,7 @@ function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCPara
                 download!(lib, h[], mc_states, results, N, T, L, npt)
                 rdfsave && download_rdf!(lib, h[], results, T, L)
                 save !== false && rem(i - 1, save) == 0 && ParallelTemperingMonteCarlo.checkpoint(i - 1, mc_states, results, ensemble, rdfsave)
-                saveconfigs !== false && rem(i - 1, saveconfigs) == 0 && ParallelTemperingMonteCarlo.save_configs(mc_states, string("configuration", i - 1))
+                saveconfigs !== false && rem(i - 1, saveconfigs) == 0 && ParallelTemperingMonteCarlo.save_configs(mc_states, string(configsname, i - 1))
             end
         end
         download!(lib, h[], mc_states, results, N, T, L, npt)
