@@ -79,3 +79,97 @@ def multihistogram_NPT(t_grid, beta_grid, ev_histogram, en_min, en_max, v_min, v
         h1, h2 = (w * enthalpy).sum(), (w * enthalpy ** 2).sum()
         cp[i] = (h2 - h1 ** 2) / (K_MULTIHIST * tt ** 2)
     return res.t_grid, cp
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# src/multihist.jl: the direct (linear-solve) multiple-histogram analysis behind `multihistogram(output, Tvec)` and
+# `postprocess()` (:236-485).  Unlike multihist_NVT.jl it bins with dE = (Emax - Emin) / (n_bin - 1) and
+# kB = 3.16681196e-6, like the sampler (readfile :52-73).
+K_B = 3.16681196e-6
+
+
+def _initialise(en_histogram, en_min, en_max, n_bin):
+    """readfile(output, Tvals) :52-73 + processhist! :83-107: drop the overflow bins, divide the counts by n_bin, remove
+    energy bins without counts."""
+    hist = np.asarray(en_histogram, dtype=np.float64)
+    if hist.shape[1] != n_bin:
+        hist = hist[:, 1:-1]
+    de = (en_max - en_min) / (n_bin - 1)
+    energy = np.array([(j - 1) * de + en_min for j in range(1, n_bin + 1)])
+    hist = hist / n_bin
+    nsum = hist.sum(axis=0)
+    keep = nsum != 0
+    return hist[:, keep], energy[keep], nsum[keep]
+
+
+def _systemsolver(hist, energy, beta, nsum):
+    """bvector :159-199, amatrix :204-219, systemsolver :224-252, Entropycalc :257-264."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        logmat = np.log(hist) + beta[:, None] * energy[None, :]
+        bmat = np.where(hist == 0.0, 0.0, hist * logmat)
+    rhvec = bmat.sum(axis=0)
+    b = (bmat - hist * rhvec[None, :] / nsum[None, :]).sum(axis=1)
+    a = -(hist[:, None, :] * hist[None, :, :] / nsum[None, None, :]).sum(axis=2)
+    a[np.diag_indices_from(a)] += hist.sum(axis=1)
+    if np.isnan(a).any() or np.isnan(b).any():
+        raise FloatingPointError("NaN in the multihistogram system")
+    alpha = np.linalg.solve(a, b)
+    entropy = (bmat - hist * alpha[:, None]).sum(axis=0) / nsum
+    return alpha, entropy
+
+
+def _analysis(energy, entropy, beta, k_b, n_points):
+    """analysis :272-340 (self-scaling Boltzmann factors: the running offset nexp keeps 1 <= Z <= 100)."""
+    tvec = 1.0 / (k_b * beta)
+    d_t = (tvec[-1] - tvec[0]) / n_points
+    t = np.array([(i - 1) * d_t + tvec[0] for i in range(1, n_points + 1)])
+    z, u, cv, dcv, s_t = (np.zeros(n_points) for _ in range(5))
+    nexp = 0.0
+    for i in range(n_points):
+        y = entropy - energy / (t[i] * k_b)
+        while True:
+            xp = np.exp(y - nexp)
+            z[i] = xp.sum()
+            if z[i] < 1.0:
+                nexp -= 1.0
+            elif z[i] > 100.0:
+                nexp += 0.7
+            else:
+                break
+        u[i] = (xp * energy).sum() / z[i]
+        u2 = (xp * energy * energy).sum() / z[i]
+        r2 = (xp * (energy - u[i]) ** 2).sum() / z[i]
+        r3 = (xp * (energy - u[i]) ** 3).sum() / z[i]
+        cv[i] = (u2 - u[i] * u[i]) / k_b / t[i] ** 2
+        s_t[i] = u[i] / t[i] + k_b * np.log(z[i])
+        dcv[i] = r3 / k_b ** 2 / t[i] ** 4 - 2 * r2 / k_b / t[i] ** 3
+    return z, u, cv, dcv, s_t, t
+
+
+def multihistogram(en_histogram, beta_grid, en_min, en_max, n_bin, outdir=None, n_points=1000):
+    """multihistogram(output::Output, Tvec::TempGrid; outdir, NPoints) src/multihist.jl:456-461 -> dict with T, Z, Cv, dCv, U, S_T,
+    alpha, energy, entropy.  With `outdir` the four files of run_multihistogram (:353-375) are written: histograms.data, Sol.X,
+    S.data, analysis.NVT (columns T Z Cv dCv U(T))."""
+    beta = np.asarray(beta_grid, dtype=np.float64)
+    hist, energy, nsum = _initialise(en_histogram, en_min, en_max, n_bin)
+    alpha, entropy = _systemsolver(hist, energy, beta, nsum)
+    z, u, cv, dcv, s_t, t = _analysis(energy, entropy, beta, K_B, n_points)
+    if outdir is not None:
+        import pathlib
+        from .readsave import _row
+        d = pathlib.Path(outdir)
+        d.mkdir(parents=True, exist_ok=True)
+        with open(d / "histograms.data", "w") as f:
+            f.write(_row([float(v) for v in energy], "\t"))
+            for row in hist:
+                f.write(_row([float(v) for v in row], "\t"))
+        (d / "Sol.X").write_text("alpha\n" + _row([float(v) for v in alpha], "\t"))
+        with open(d / "S.data", "w") as f:
+            f.write("E\tEntropy\n")
+            for e, s in zip(energy, entropy):
+                f.write(_row([float(e), float(s)], "\t"))
+        with open(d / "analysis.NVT", "w") as f:
+            f.write("T\tZ\tCv\tdCv\tU(T)\n")
+            for row in zip(t, z, cv, dcv, u):
+                f.write(_row([float(v) for v in row], "\t"))
+    return {"T": t, "Z": z, "Cv": cv, "dCv": dcv, "U": u, "S_T": s_t, "alpha": alpha, "energy": energy, "entropy": entropy}

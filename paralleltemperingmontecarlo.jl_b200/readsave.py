@@ -309,3 +309,17 @@ def rebuild_states(n_traj: int, directory="./checkpoint", npt=False):
         cfgs.append(c); md.append(m); ca.append(a); cv.append(v)
     index = int(float((d / "index.txt").read_text().split()[0])) if (d / "index.txt").exists() else 0
     return cfgs, np.array(md), np.array(ca), np.array(cv), results, rdf, index
+
+
+def postprocess(directory="./checkpoint", n_points=1000):
+    """postprocess() src/multihist.jl:463-485 on a checkpoint directory: rebuild the results from the checkpoint files, run the
+    multihistogram analysis (its four output files go to `directory`) and return (energies, histogramdata, T, Z, Cv, dCv, S)
+    as the reference does (S is the fifth column of analysis.NVT, U(T))."""
+    from . import multihist
+    params, temp, ens, pot = read_init(directory)
+    results, _ = setresults(directory, npt=ens.kind == abi.ENS_NPT)
+    out = multihist.multihistogram(results.en_histogram, temp.beta_grid, results.en_min, results.en_max, results.n_bin,
+                                   outdir=directory, n_points=n_points)
+    hists = [[float(v) for v in ln.split()] for ln in pathlib.Path(directory, "histograms.data").read_text().splitlines()]
+    energies, histogramdata = np.array(hists[0]), [np.array(h) for h in hists[1:1 + params.n_traj]]
+    return energies, histogramdata, out["T"], out["Z"], out["Cv"], out["dCv"], out["U"]

@@ -73,3 +73,47 @@ def test_heat_capacity_curves_agree(oracle):
     assert np.abs(cv_gpu - cv_cpu).max() < 0.08 * peak                      # statistical error of the smaller sample
     assert abs(t[np.argmax(cv_gpu)] - t[np.argmax(cv_cpu)]) < 0.8           # melting peak near 10 K
     assert np.abs(hc_gpu - hc_cpu).max() < 0.1 * hc_cpu.max()               # fluctuation estimate (E, E^2 sums), pooled over ladders
+
+
+def test_direct_multihistogram_and_postprocess(tmp_path, oracle):
+    # src/multihist.jl (the analysis behind postprocess(), which the reference's "Saveconfigs" test runs on a checkpoint): no
+    # known-answer vector exists for it, so it is checked for self-consistency on an oracle run with a histogram window that
+    # holds every sample: U(T) at the ladder temperatures equals the sampled <E>, the Cv curve agrees with the fluctuation
+    # formula and with the iterative multihistogram_NVT
+    from oracle import oracle as orc
+    from ptmc_b200 import abi, multihist, readsave
+    from ptmc_b200.host import initial_arrays, sweep_config, finalise_results
+    import ptmc_b200 as P
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=8, cycles=6000)
+    L, bounds = 4, (-0.0058, -0.0022)
+    eng = orc.OracleEngine(sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=11), threads=4)
+    pos, box = initial_arrays(mcp, start, L)
+    eng.upload_states(pos, box); eng.seed(11)
+    eng.run_cycles(1, 1500, False); eng.reset_counters(); eng.set_hist_bounds(*bounds)
+    eng.run_cycles(1, mcp.mc_cycles, True)
+    st, hl = eng.download_states(), eng.download_hist()
+    eng.close()
+    assert hl[:, :, 0].sum() + hl[:, :, -1].sum() <= 2e-4 * hl.sum()   # (practically) nothing outside the window
+    hist = hl.sum(axis=0)
+    res = P.Output(mcp.n_bin, en_min=bounds[0], en_max=bounds[1])
+    res.delta_en_hist = (res.en_max - res.en_min) / (res.n_bin - 1)
+    res.en_histogram = hist
+    en_avg = st["ham"][:, :, 0].mean(axis=0) / mcp.mc_cycles
+    cv_fluct = ((st["ham"][:, :, 1] / mcp.mc_cycles - (st["ham"][:, :, 0] / mcp.mc_cycles) ** 2) * temp.beta_grid ** 2).mean(axis=0) * multihist.K_B
+    out = multihist.multihistogram(hist, temp.beta_grid, res.en_min, res.en_max, mcp.n_bin)
+    u_at = np.interp(temp.t_grid[1:-1], out["T"], out["U"])
+    # (multihist.jl takes the LEFT edge of a bin as its energy, readfile :58, so U(T) sits about half a bin below the sampled mean)
+    assert np.abs(u_at - en_avg[1:-1]).max() < 2 * res.delta_en_hist
+    cv_at = np.interp(temp.t_grid[1:-1], out["T"], out["Cv"])
+    assert np.abs(cv_at - cv_fluct[1:-1]).max() < 0.15 * cv_fluct.max()
+    t2, cv2 = multihist.multihistogram_NVT(temp.t_grid, temp.beta_grid, hist, res.en_min, res.en_max, mcp.n_bin)
+    assert np.abs(np.interp(t2[5:-5], out["T"], out["Cv"]) - cv2[5:-5]).max() < 0.1 * cv2.max()
+    # postprocess() on a checkpoint directory of that run: files and return values
+    readsave.save_init(pot, ens, mcp, temp, tmp_path)
+    readsave.save_histparams(res, tmp_path)
+    readsave.checkpoint(mcp.mc_cycles, st, res, ens, abi.BC_SPHERICAL, directory=tmp_path)
+    energies, histdata, T, Z, Cv, dCv, S = readsave.postprocess(tmp_path)
+    assert len(histdata) == 8 and len(T) == 1000 and (Z >= 1.0).all() and (Z <= 100.0).all()
+    assert np.allclose(Cv, out["Cv"]) and np.allclose(S, out["U"])
+    assert (tmp_path / "analysis.NVT").read_text().splitlines()[0].split() == ["T", "Z", "Cv", "dCv", "U(T)"]
+    assert (tmp_path / "Sol.X").exists() and (tmp_path / "S.data").exists()
