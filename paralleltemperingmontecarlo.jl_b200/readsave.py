@@ -14,7 +14,6 @@ Host-side only: nothing here touches the device."""
 from __future__ import annotations
 
 import math
-import os
 import pathlib
 
 import numpy as np
