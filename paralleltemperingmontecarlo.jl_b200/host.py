@@ -558,6 +558,24 @@ def deck_cu55_eam(n_traj=28, cycles=1000):
     return MCParams(cycles, n_traj, 55), TempGrid(400.0, 1200.0, n_traj), start, pot, NVT(55)
 
 
+def deck_cu38_eam(n_traj=36, cycles=1000):
+    """scripts/cu38.jl:14-46,155-208 (one of the reference's script tests): Cu38, EmbeddedAtomPotential, NVT, 36 temperatures
+    150-1200 K; positions :161-200 are used as given, SphericalBC(radius = 6.0 Angstrom in bohr) :205."""
+    ev2h, nm2b = 0.0367493, 18.8973
+    pot = EmbeddedAtomPotential(8.482, 4.692, ev2h * 0.0370, 27.561, 0.25 * nm2b)
+    start = Config(_geom("cu38"), SphericalBC(radius=6.0 * 1.8897259886))
+    return MCParams(cycles, n_traj, 38), TempGrid(150.0, 1200.0, n_traj), start, pot, NVT(38)
+
+
+def deck_pbc32(n_traj=24, cycles=1000):
+    """scripts/pbc32-short.jl:9-25,46-47,89-91 (one of the reference's script tests): 32-atom fcc block, CubicBC, NPT,
+    ELJPotentialEven, 24 temperatures 10-25 K; the script's pressure conversion divides by AtoBohr^2."""
+    a2b = 1.8897261259077824
+    start = Config(_geom("ne32") * a2b, CubicBC(8.7674 * a2b))
+    ens = NPT(32, 101325 * 2.2937122783969076e-13 / a2b ** 2, False)
+    return MCParams(cycles, n_traj, 32), TempGrid(10.0, 25.0, n_traj), start, ELJPotentialEven(ELJ_NE_COEFF), ens
+
+
 def deck_pbc216(n_traj=16, cycles=100):
     """scripts/pbc216.jl:14-70,517-529 (BASELINE C4; the LookupTable lines 62-63 are dropped)"""
     a2b = 1.8897261259077824

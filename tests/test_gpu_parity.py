@@ -662,3 +662,18 @@ def test_lookup_table_potential(tmp_path, oracle):
     eng.upload_states(sg["pos"], sg["box"])
     np.testing.assert_allclose(eng.download_states(("en_tot",))["en_tot"], sg["en_tot"], rtol=1e-11)
     eng.close()
+
+
+def test_reference_script_decks_cu38_and_pbc32():
+    # the remaining decks of the reference's "scripts run without errors" tests (test/runtests.jl:296-316): scripts/cu38.jl (Cu38 EAM,
+    # 36 temperatures: five unrolled pair iterations) and scripts/pbc32-short.jl (32-atom fcc block, CubicBC, NPT, 24 temperatures)
+    res = _free_run_pair(P.host.deck_cu38_eam(cycles=12), 2, 41, abi.RNG_BATCH8, 12, bounds=(-5.0, -3.0))
+    _assert_same_trajectory(res, e_rtol=1e-10)
+    assert res[0][0]["counters"][:, :, abi.C_ATOM_TOT].sum() > 0
+    mcp, temp, start, pot, ens = P.host.deck_pbc32(cycles=20)
+    v0 = P.get_volume(start.boundary_condition)
+    (sg, hg, rg), (sc, hc, rc) = _free_run_pair((mcp, temp, start, pot, ens), 2, 43, abi.RNG_BATCH8, 20, bounds=(-1.0, 1.0, 0.8 * v0, 2.0 * v0))
+    assert np.array_equal(sg["counters"], sc["counters"]) and np.array_equal(hg, hc) and np.array_equal(rg[0], rc[0])
+    np.testing.assert_allclose(sg["pos"], sc["pos"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(sg["en_tot"], sc["en_tot"], rtol=1e-10)
+    assert sg["counters"][:, :, abi.C_VOL_TOT].sum() > 0

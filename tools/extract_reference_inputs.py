@@ -10,6 +10,7 @@ Sources (all under /root/reference):
   scripts/ne55.jl:65-121      Ne55 (used as given)
   scripts/cu55.jl:164-220     ico_55 unit icosahedron
   scripts/pbc216.jl:79-515    fcc / hcp 216-atom lattices (Angstrom)
+  scripts/cu38.jl:161-200     Cu38 (bohr), scripts/pbc32-short.jl:54-87  32-atom fcc block (Angstrom)
   scripts/data/weights.029.data, scripts/data/scaling.data  (RuNNer Cu network)
 """
 import json, re, shutil, sys
@@ -42,8 +43,10 @@ def main():
         "ico55": grab("scripts/cu55.jl", "ico_55"),
         "ne216_fcc": grab("scripts/pbc216.jl", "pos_ne216_fcc"),
         "ne216_hcp": grab("scripts/pbc216.jl", "pos_ne216_hcp"),
+        "cu38": grab("scripts/cu38.jl", "pos_cu38"),
+        "ne32": grab("scripts/pbc32-short.jl", "pos_ne32"),
     }
-    want = {"ne13": 13, "ne55": 55, "ico55": 55, "ne216_fcc": 216, "ne216_hcp": 216}
+    want = {"ne13": 13, "ne55": 55, "ico55": 55, "ne216_fcc": 216, "ne216_hcp": 216, "cu38": 38, "ne32": 32}
     for k, rows in geo.items():
         assert len(rows) == want[k], (k, len(rows))
         # keep the decimal literals as strings -> float() parses them exactly as Julia does
