@@ -26,6 +26,7 @@ DECKS = {
     "ne13_eljeven": (lambda: P.host.deck_ne13(n_traj=16, cycles=1), 512, 32, 2000, 8000),
     "ne13_eljb": (lambda: P.host.deck_ne13_B(n_traj=16, cycles=1), 512, 32, 2000, 8000),
     "cu55_eam": (lambda: P.host.deck_cu55_eam(n_traj=28, cycles=1), 128, 16, 1000, 3000),
+    "pbc216_npt": (lambda: P.host.deck_pbc216(n_traj=16, cycles=1), 148, 16, 400, 1200),       # Cp from H = E + pV (src/Sampling.jl:35-46)
     "ne13_lookup": (lambda: P.host.deck_ne13_lookup(str(LUT), n_traj=16, cycles=1), 256, 32, 2000, 8000),
 }
 
@@ -38,7 +39,7 @@ def heat_capacity(engine_cls, deck, L, eq, cycles, seed, **kw):
     eng.seed(seed)
     eng.run_cycles(1, eq, False)
     eng.reset_counters()
-    eng.set_hist_bounds(-1.0, 1.0)
+    eng.set_hist_bounds(-1.0, 1.0, 1.0, 2.0)
     eng.run_cycles(1, cycles, True)
     eng.sync()
     ham = eng.download_states(("ham",))["ham"]
