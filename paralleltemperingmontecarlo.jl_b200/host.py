@@ -599,9 +599,20 @@ RUNNER_R_CUT = 11.338
 
 
 def load_scaling(path=None):
-    """scaling.data rows (element, index, G_min, G_max, G_avg) -> [n][2] {G_max, G_min} as scripts/cu55.jl:104-112"""
-    rows = np.loadtxt(path or DATA_DIR / "scaling.data", usecols=(0, 1, 2, 3, 4), max_rows=176)   # a 2-number footer follows
+    """scaling.data rows (element, index, G_min, G_max, G_avg) -> [n][2] {G_max, G_min} as scripts/cu55.jl:104-112.
+    `path`: a RuNNer scaling.data file; default: the Cu / Zn table of the reference's scripts (data/cu_nnp_inputs.npz)."""
+    if path is None:
+        rows = np.load(DATA_DIR / "cu_nnp_inputs.npz")["scaling_rows"]
+    else:
+        rows = np.loadtxt(path, usecols=(0, 1, 2, 3, 4), max_rows=176)   # a 2-number footer follows
     return np.stack([rows[:, 3], rows[:, 2]], axis=1)
+
+
+def load_weights(path=None):
+    """RuNNer weights.XXX.data (one parameter per line, SURVEY A.2 order); default: the Cu network of scripts/cu55.jl."""
+    if path is None:
+        return np.load(DATA_DIR / "cu_nnp_inputs.npz")["weights_cu"]
+    return np.loadtxt(path).ravel()
 
 
 def cu_runner_potential(boundary: float = 0.0, weights=None, scaling=None):
@@ -616,7 +627,7 @@ def cu_runner_potential(boundary: float = 0.0, weights=None, scaling=None):
         for t in CU_ANGULAR_TYPES:
             angular.append((eta, lam, zeta, RUNNER_R_CUT, t, g[n_index, 0], g[n_index, 1]))
             n_index += 1
-    w = np.loadtxt(weights or DATA_DIR / "weights.029.data").ravel()
+    w = load_weights(weights)
     return RuNNerPotential([88, 20, 20, 1], [1, 2, 2, 1], w, radial, angular, boundary)
 
 

@@ -27,7 +27,7 @@ def test_forward_against_reference_binary(oracle):
     from oracle import ref_forward
     if not ref_forward.available():
         pytest.skip("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
-    w = np.loadtxt(P.host.DATA_DIR / "weights.029.data").ravel()
+    w = P.host.load_weights()
     rng = np.random.default_rng(1)
     x = rng.uniform(0.0, 1.0, (55, 88))
     ref = ref_forward.ref_forward(x, NODES, ACT, w)
@@ -46,8 +46,8 @@ def test_brass_six_atom_energy(oracle):
     g = P.host.load_scaling()
     rad_eta = [0.001, 0.020, 0.035, 0.100, 0.400]
     ang = np.array(P.host.CU_ANGULAR)
-    w_cu = np.loadtxt(P.host.DATA_DIR / "weights.029.data").ravel()
-    w_zn = np.loadtxt(ROOT / "tests" / "golden" / "weights.030.data").ravel()
+    w_cu = P.host.load_weights()
+    w_zn = np.load(ROOT / "tests" / "golden" / "brass_nnp_inputs.npz")["weights_zn"]
     e, f12 = oracle.runner2_energy(pos, 4, 2, rad_eta, ang[:, 0], ang[:, 1], ang[:, 2], 11.338, g[:88], g[88:176], NODES, ACT, w_cu, w_zn)
     d12 = np.sqrt(((pos[0] - pos[1]) ** 2).sum())
     assert f12 == oracle.cutoff(d12, 11.338)                  # test_potentials.jl:82

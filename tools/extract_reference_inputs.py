@@ -13,7 +13,7 @@ Sources (all under /root/reference):
   scripts/cu38.jl:161-200     Cu38 (bohr), scripts/pbc32-short.jl:54-87  32-atom fcc block (Angstrom)
   scripts/data/weights.029.data, scripts/data/scaling.data  (RuNNer Cu network)
 """
-import json, re, shutil, sys
+import json, re, sys
 from pathlib import Path
 
 REF = Path("/root/reference")
@@ -51,8 +51,13 @@ def main():
         assert len(rows) == want[k], (k, len(rows))
         # keep the decimal literals as strings -> float() parses them exactly as Julia does
         (OUT / f"{k}.json").write_text(json.dumps(rows))
-    for f in ("weights.029.data", "scaling.data"):
-        shutil.copy(REF / "scripts" / "data" / f, OUT / f)
+    # RuNNer inputs as numbers: the Cu network (2221 parameters, scripts/data/weights.029.data), the scaling table
+    # (scripts/data/scaling.data rows 1..176: element, index, G_min, G_max, G_avg), the Zn network of the brass KAT
+    import numpy as np
+    np.savez_compressed(OUT / "cu_nnp_inputs.npz", weights_cu=np.loadtxt(REF / "scripts" / "data" / "weights.029.data").ravel(),
+                        scaling_rows=np.loadtxt(REF / "scripts" / "data" / "scaling.data", usecols=(0, 1, 2, 3, 4), max_rows=176))
+    np.savez_compressed(OUT.parent.parent / "tests" / "golden" / "brass_nnp_inputs.npz",
+                        weights_zn=np.loadtxt(REF / "test" / "testing_data" / "weights.030.data").ravel())
     print("wrote", sorted(p.name for p in OUT.iterdir()))
 
 
