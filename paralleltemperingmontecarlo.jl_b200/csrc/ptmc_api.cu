@@ -14,10 +14,10 @@
 #include "sweep_kernel.cuh"
 
 namespace ptmc {
-sweep_fn sweep_table_g4(int pot, int geom, int dbg, int niter, int n_coeff, int fullw);
-sweep_fn sweep_table_g8(int pot, int geom, int dbg, int niter, int n_coeff, int fullw);
-sweep_fn sweep_table_g16(int pot, int geom, int dbg, int niter, int n_coeff, int fullw);
-sweep_fn sweep_table_g32(int pot, int geom, int dbg, int niter, int n_coeff, int fullw);
+sweep_fn sweep_table_g4(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
+sweep_fn sweep_table_g8(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
+sweep_fn sweep_table_g16(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
+sweep_fn sweep_table_g32(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
 int sweep_max_threads(int G);
 void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
@@ -139,11 +139,12 @@ static void julia_seed(uint64_t seed, uint64_t s[4]) {
 static sweep_fn pick_kernel(const ptmc_handle* h, int dbg) {
     const int niter = h->P.n_pad / h->G, nc = h->cfg.n_coeff;
     const int fullw = (h->cfg.n_traj * h->G) % 32 == 0 ? 1 : 0;      // every warp of the ladder fully active
+    const int rot = (h->cfg.n_atoms - 1) % h->G == 0 ? 1 : 0;          // the other N - 1 atoms fill the lanes exactly
     switch (h->G) {
-        case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw);
-        case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw);
-        case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw);
-        default: return sweep_table_g32(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw);
+        case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
+        case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
+        case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
+        default: return sweep_table_g32(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
     }
 }
 // words of generator state per slot

@@ -31,6 +31,18 @@ static sweep_fn generic_kernel(int pot, int geom, int dbg) {
 
 // Specialised production kernels of the headline family (ELJPotentialEven with 6 coefficients, SphericalBC,
 // BATCH8 streams): pair loop fully unrolled for ceil(n_atoms / G) = 1..8 (1..16 for G = 4).
+// (N - 1) % G == 0 and a fully active warp layout: rotated neighbour order, niter - 1 pair iterations (sweep_kernel.cuh, ROT)
+template <int POT>
+static sweep_fn rotated_kernel(int niter_rot) {
+    constexpr int G = PTMC_G;
+    switch (niter_rot) {
+#define PTMC_SPR(K) case K: return (sweep_fn)sweep_kernel<G, POT, GEOM_SPHERE, false, K, 6, true, true>;
+        PTMC_SPR(1) PTMC_SPR(2) PTMC_SPR(3) PTMC_SPR(4) PTMC_SPR(5) PTMC_SPR(6) PTMC_SPR(7) PTMC_SPR(8)
+#undef PTMC_SPR
+        default: return nullptr;
+    }
+}
+
 static sweep_fn special_kernel(int niter, int fullw) {
     constexpr int G = PTMC_G;
     switch (niter) {
@@ -47,8 +59,12 @@ static sweep_fn special_kernel(int niter, int fullw) {
 
 // pot: ptmc_pot_kind (ELJ, ELJ_EVEN, EAM); geom: Geom; dbg: sequential-stream / replay / trace build;
 // niter = n_pad / G; n_coeff: number of ELJ coefficients; fullw: n_traj * G is a multiple of 32 (no partly active warp)
-sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff, int fullw) {
+sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot) {
     constexpr int G = PTMC_G;
+    if (rot && fullw && !dbg && geom == GEOM_SPHERE && n_coeff == 6 && niter >= 2) {
+        sweep_fn f = pot == PTMC_POT_ELJ_EVEN ? rotated_kernel<PTMC_POT_ELJ_EVEN>(niter - 1) : pot == PTMC_POT_ELJ_B ? rotated_kernel<PTMC_POT_ELJ_B>(niter - 1) : nullptr;
+        if (f) return f;
+    }
     if (!dbg && pot == PTMC_POT_ELJ_EVEN && geom == GEOM_SPHERE && n_coeff == 6) {
         sweep_fn f = special_kernel(niter, fullw);
         if (f) return f;

@@ -92,16 +92,18 @@ __device__ __forceinline__ void sep_rewrite_matrix(const DevParams& P, const dou
 // DBG   : sequential slot stream (Julia-compatible XOSHIRO mode, or REPLAY) + optional trace.  !DBG: BATCH8.
 // NITER : compile-time ceil(n_atoms / G) of the pair loop (n_pad = NITER * G), 0 = runtime trip count.
 // NC    : compile-time number of ELJ coefficients (6), 0 = runtime.
-template <int G, int POT, int GEOM, bool DBG, int NITER, int NC, bool FULLW = false>
+template <int G, int POT, int GEOM, bool DBG, int NITER, int NC, bool FULLW = false, bool ROT = false>
 __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_idx, const i64 n_cycles, const int sample) {
     extern __shared__ double sm[];
     constexpr bool EAM = (POT == PTMC_POT_EAM);
     constexpr bool PBC = (GEOM != GEOM_SPHERE);
     constexpr bool rhombic = (GEOM == GEOM_RHOMB);
     constexpr bool BATCH = !DBG;
-    constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN;   // mask by parking atoms far away instead of per-pair selects
+    // ROT (free space, (N - 1) a multiple of G): lane g visits the OTHER atoms i+1+g, i+1+g+G, ... (mod N), so the row takes
+    // (N - 1) / G iterations instead of ceil(N / G) (Ne13 on 4 lanes: 3 instead of 4) and needs neither parking nor selects
+    constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN && !ROT;   // mask by parking atoms far away instead of per-pair selects
     const int T = P.n_traj, N = P.n_atoms;
-    const int NP = NITER ? NITER * G : P.n_pad;
+    const int NP = (NITER && !ROT) ? NITER * G : P.n_pad;
     const int lad = blockIdx.x;
     const int tid = threadIdx.x;
     const int slot = tid / G, g = tid & (G - 1);
@@ -356,9 +358,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             // free space: the old row is recomputed from the positions (no dist2_mat is stored)
                             const double* Xg = X + g;
                             auto pair_term = [&](int k) {
-                                const int j = g + k * G;
-                                const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
-                                const bool valid = (j != i) && (j < N);   // not the moved atom, not padding
+                                int j = g + k * G;
+                                if (ROT) { j += i + 1; j -= (j >= N) ? N : 0; }
+                                const double xj = ROT ? X[j] : Xg[k * G], yj = ROT ? X[NP + j] : Xg[NP + k * G], zj = ROT ? X[2 * NP + j] : Xg[2 * NP + k * G];
+                                const bool valid = ROT || ((j != i) && (j < N));   // not the moved atom, not padding
                                 double ax = tx - xj, ay = ty - yj, az = tz - zj;
                                 double d2n = fma(az, az, fma(ay, ay, ax * ax));
                                 double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
@@ -746,10 +749,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     if (err) atomicMin(P.error, err);
 }
 
-template <int G, int POT, int GEOM, bool DBG, int NITER, int NC, bool FULLW = false>
+template <int G, int POT, int GEOM, bool DBG, int NITER, int NC, bool FULLW = false, bool ROT = false>
 __global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
 sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
-    sweep_body<G, POT, GEOM, DBG, NITER, NC, FULLW>(P, first_idx, n_cycles, sample);
+    sweep_body<G, POT, GEOM, DBG, NITER, NC, FULLW, ROT>(P, first_idx, n_cycles, sample);
 }
 // EmbeddedAtomPotential: the unrolled loop wants ~170 registers; capped so that two 224-thread ladders (scripts/cu55.jl:
 // 28 temperatures x 8 lanes) stay resident per SM (a 96-register cap for three ladders spills and measured slower)

@@ -677,3 +677,17 @@ def test_reference_script_decks_cu38_and_pbc32():
     np.testing.assert_allclose(sg["pos"], sc["pos"], rtol=1e-11, atol=1e-11)
     np.testing.assert_allclose(sg["en_tot"], sc["en_tot"], rtol=1e-10)
     assert sg["counters"][:, :, abi.C_VOL_TOT].sum() > 0
+
+
+@pytest.mark.parametrize("n_traj", [8, 16, 32])
+def test_rotated_neighbour_order_kernels(n_traj):
+    # (N - 1) % G == 0 and no partly active warp (Ne13 on 4 lanes, n_traj * 4 a multiple of 32): the ROT kernels walk the other
+    # 12 atoms in three iterations in rotated order; production streams -> the trajectory of the oracle, bit for bit
+    res = _free_run_pair(P.host.deck_ne13(n_traj=n_traj, cycles=60), 3, 61 + n_traj, abi.RNG_BATCH8, 60, lanes=4)
+    _assert_same_trajectory(res)
+    assert res[0][0]["counters"][:, :, abi.C_ATOM_TOT].sum() > 0
+    # tight sphere: redraws and the recentre path inside the rotated kernels
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=8, cycles=20)
+    rmax = np.sqrt((start.positions ** 2).sum(axis=1).max())
+    tight = P.Config(start.positions, P.SphericalBC(radius=rmax * 1.05))
+    _assert_same_trajectory(_free_run_pair((mcp, temp, tight, pot, ens), 2, 3, abi.RNG_BATCH8, 20, lanes=4))
