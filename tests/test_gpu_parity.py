@@ -691,3 +691,36 @@ def test_rotated_neighbour_order_kernels(n_traj):
     rmax = np.sqrt((start.positions ** 2).sum(axis=1).max())
     tight = P.Config(start.positions, P.SphericalBC(radius=rmax * 1.05))
     _assert_same_trajectory(_free_run_pair((mcp, temp, tight, pot, ens), 2, 3, abi.RNG_BATCH8, 20, lanes=4))
+
+
+def _fcc_cluster(n, a):
+    # the n lattice points of an fcc crystal closest to the origin
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
+    r = range(-3, 4)
+    pts = np.array([(b + [i, j, k]) * a for i in r for j in r for k in r for b in base])
+    pts = pts[np.argsort((pts ** 2).sum(axis=1), kind="stable")][:n]
+    return pts - pts.mean(axis=0)
+
+
+@pytest.mark.parametrize("case", ["eam101", "elj150", "eam20"])
+def test_other_cluster_sizes_generic_kernels(case):
+    # sizes outside the unrolled instantiations: Cu101 EAM as scripts/cu101.jl (13 pair iterations on 8 lanes -> the generic EAM
+    # kernel with the trial components in shared memory), a 150-atom ELJ cluster on 32 lanes, a 20-atom EAM cluster on 4 lanes
+    if case == "eam101":
+        mcp, temp, start, pot, ens = P.host.deck_cu55_eam(n_traj=32, cycles=4)
+        mcp.n_atoms, ens = 101, P.NVT(101)
+        start = P.Config(_fcc_cluster(101, 0.36258 * 18.8973), P.SphericalBC(radius=14 * 1.8897259886))
+        bounds, cyc = (-20.0, 0.0), 4
+    elif case == "elj150":
+        mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=8, cycles=6)
+        mcp.n_atoms, ens = 150, P.NVT(150)
+        start = P.Config(_fcc_cluster(150, 8.4), P.SphericalBC(radius=40.0))
+        bounds, cyc = (-1.0, 0.0), 6
+    else:
+        mcp, temp, start, pot, ens = P.host.deck_cu55_eam(n_traj=6, cycles=20)
+        mcp.n_atoms, ens = 20, P.NVT(20)
+        start = P.Config(_fcc_cluster(20, 0.36258 * 18.8973), P.SphericalBC(radius=10 * 1.8897259886))
+        bounds, cyc = (-5.0, 0.0), 20
+    res = _free_run_pair((mcp, temp, start, pot, ens), 2, 71, abi.RNG_BATCH8, cyc, bounds=bounds)
+    _assert_same_trajectory(res, e_rtol=1e-10)
+    assert res[0][0]["counters"][:, :, abi.C_ATOM_TOT].sum() > 0
