@@ -724,3 +724,19 @@ def test_other_cluster_sizes_generic_kernels(case):
     res = _free_run_pair((mcp, temp, start, pot, ens), 2, 71, abi.RNG_BATCH8, cyc, bounds=bounds)
     _assert_same_trajectory(res, e_rtol=1e-10)
     assert res[0][0]["counters"][:, :, abi.C_ATOM_TOT].sum() > 0
+
+
+def test_edge_case_sizes_replay():
+    # smallest legal job (2 atoms, 2 temperatures, one atom move per cycle), sampling every third cycle, step-size adaptation
+    # every cycle; and a ladder of 48 temperatures on 8 lanes (384 threads, the largest ladder of the small-lane kernels)
+    start = P.Config(np.array([[0.0, 0.0, 2.9], [0.0, 0.0, -2.9]]), P.SphericalBC(radius=8.0))
+    mcp = P.MCParams(60, 2, 2, mc_sample=3, n_adjust=1)
+    gpu, cpu = run_pair(mcp, P.TempGrid(5.0, 9.0, 2), start, P.ELJPotentialEven(P.host.ELJ_NE_COEFF), P.NVT(2, n_atom_moves=1),
+                        n_ladders=3, n_cycles=60, seed=5)
+    compare_traces(gpu, cpu)
+    assert gpu["hist"].sum() == 3 * 2 * 20                      # cycles 3, 6, ..., 60
+    mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=48, cycles=6)
+    res = _free_run_pair((mcp, temp, start, pot, ens), 2, 9, abi.RNG_BATCH8, 6, bounds=(-0.1, 0.0))
+    _assert_same_trajectory(res)
+    with pytest.raises(PtmcError):                              # 49 temperatures x 8 lanes do not fit one ladder CTA
+        Engine(sweep_config(*P.host.deck_ne55(n_traj=49, cycles=1), lanes_per_replica=8))
