@@ -15,7 +15,7 @@ constexpr int RN_MAX_HID = 32;     // nodes per hidden layer
 #endif
 constexpr int RN_THREADS = PTMC_RN_THREADS;   // one CTA = one replica: 7 warps on the centre-j terms, 5 on the centre-i terms (N = 55)
 constexpr int RN_SUB = 4;          // threads sharing one atom j in the angular update
-constexpr int RN_MAX_ATOMS = (RN_THREADS / 32 - 2) * 32 / RN_SUB;   // at least two warps stay with the centre-i terms
+constexpr int RN_MAX_ATOMS = RN_THREADS >= 384 ? (RN_THREADS / 32 - 2) * 32 / RN_SUB : RN_THREADS / RN_SUB;   // split mode: at least two warps stay with the centre-i terms
 
 // Only symmetry functions of type 11 / 111 are ever evaluated (DeltaMatrix.jl:803,840, SymmFunc.jl:261,281); the rows
 // of all others stay exactly 0 for ever and contribute exactly 0 to the first network layer, so the device keeps a

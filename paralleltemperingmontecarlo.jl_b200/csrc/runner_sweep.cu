@@ -113,7 +113,10 @@ __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
     s.net = o; o += R.h1 * R.n_act + R.h1 + R.h2 * R.h1 + R.h2 + R.h2 + 1;
     s.h1 = o; o += N * R.h1; s.h2 = o; o += N * R.h2;
     s.misc = o; o += 16;
-    s.pair = o; o += (3 + R.n_eta) * (N * (N - 1) / 2);      // d2 | 1/d | f | ef[n_eta], upper triangle
+    s.pair = o;
+#ifndef PTMC_RN_GLOBAL_TABLES
+    o += (3 + R.n_eta) * (N * (N - 1) / 2);      // d2 | 1/d | f | ef[n_eta], upper triangle
+#endif
     s.ptab = o; o += (N * (N - 1) / 2 + 1) / 2;              // int (j << 16 | k) per pair
     s.total = o;
     return s;
@@ -196,7 +199,12 @@ __global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams
     const RnSmem L = rn_smem(N, R);
     double* pos = sm + L.pos; double* g = sm + L.g0; double* net = sm + L.net;
     const int NT = N * (N - 1) / 2;
-    double* D2 = sm + L.pair; double* INV = D2 + NT; double* F = INV + NT; double* EF = F + NT;
+#ifdef PTMC_RN_GLOBAL_TABLES
+    double* D2 = R.pair_c + rep * (size_t)(3 + R.n_eta) * NT;
+#else
+    double* D2 = sm + L.pair;
+#endif
+    double* INV = D2 + NT; double* F = INV + NT; double* EF = F + NT;
     for (int k = tid; k < 3 * N; k += RN_THREADS) { pos[k] = P.pos[rep * 3 * N + k]; R.pos_c[rep * 3 * N + k] = pos[k]; }
     for (int k = tid; k < L.h1 - L.net; k += RN_THREADS) net[k] = R.net[k];
     __syncthreads();
@@ -242,7 +250,9 @@ __global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams
         }
         for (int q = 0; q < R.n_act_ang; ++q) if (R.ang_init[q]) ga[R.n_act_rad + q] += R.ang_off[q];
     }
+#ifndef PTMC_RN_GLOBAL_TABLES
     for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) R.pair_c[rep * (size_t)(3 + R.n_eta) * NT + k] = D2[k];
+#endif
     __syncthreads();
     double* ea = sm + L.ea0;
     const double e = rn_forward(R, N, g, net, sm + L.h1, sm + L.h2, ea, sm + L.red);
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams
 // mc_step! for one replica slot: n_steps x mc_move! (src/MCRun.jl:142-182).  NA = number of evaluated angular
 // symmetry functions (unused; the accumulators are dense over (eta, lambda-zeta)).
 template <bool DBG, unsigned long long PRESENT, unsigned NSQ>
-__global__ void __launch_bounds__(RN_THREADS, 1)
+__global__ void __launch_bounds__(RN_THREADS, RN_THREADS <= 256 ? 2 : 1)
 runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launch) {
     extern __shared__ double sm[];
     constexpr bool BATCH = !DBG;
@@ -274,10 +284,16 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
     double* red = sm + L.red; double* net = sm + L.net;
     double* misc = sm + L.misc;        // 0 index, 1-3 trial, 4 u_acc, 5 accept, 6 error
     const int NT = N * (N - 1) / 2;
-    double* D2 = sm + L.pair; double* INV = D2 + NT; double* F = INV + NT; double* EF = F + NT;   // pair tables, shared memory
     double* pair_g = R.pair_c + cfg * (size_t)(3 + R.n_eta) * NT;
+#ifdef PTMC_RN_GLOBAL_TABLES      // experiment: pair tables read from HBM / L1 instead of shared memory
+    double* D2 = pair_g; double* INV = D2 + NT; double* F = INV + NT; double* EF = F + NT;
+#else
+    double* D2 = sm + L.pair; double* INV = D2 + NT; double* F = INV + NT; double* EF = F + NT;   // pair tables, shared memory
+#endif
     int cur = 0;
+#ifndef PTMC_RN_GLOBAL_TABLES
     for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) D2[k] = pair_g[k];
+#endif
     int* ptab = reinterpret_cast<int*>(sm + L.ptab);
     for (int p = tid; p < N * N; p += RN_THREADS) {
         const int a = p / N, b = p - a * N;
@@ -433,7 +449,8 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
             // The two passes are independent and run side by side: the first nwa warps take the centre-j terms (pass A), the
             // remaining warps the centre-i terms (pass B); N = 55: 7 warps x 13 k-iterations next to 5 warps x 10 pair iterations.
             const int nwa = (N * RN_SUB + 31) >> 5;
-            if (warp < nwa) {
+            constexpr bool SPLIT = RN_THREADS >= 384;       // enough warps to run the two passes side by side
+            if (!SPLIT || warp < nwa) {
             // ---- pass A: centre j, thread (j, s) takes k = s, s + RN_SUB, ...
             const int j = tid / RN_SUB, s = tid % RN_SUB;
             const bool jok = j < N && j != i;
@@ -468,10 +485,12 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
                         for (int m = 1; m < RN_SUB; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
                         const int q = R.qmap[e * RN_MAX_LZ + z];
                         if (s == 0 && jok) ng[j * R.n_act + R.n_act_rad + q] = g[j * R.n_act + R.n_act_rad + q] + v * R.ang_tpz[q];
+                        acc[e][z] = 0.0;
                     }
-            } else {
+            }
+            if (!SPLIT || warp >= nwa) {
             // ---- pass B: centre i, the pairs (j < k) dealt round-robin to the threads of the remaining warps
-            for (int p = tid - 32 * nwa; p < NT; p += RN_THREADS - 32 * nwa) {
+            for (int p = SPLIT ? tid - 32 * nwa : tid; p < NT; p += SPLIT ? RN_THREADS - 32 * nwa : RN_THREADS) {
                 const int jk = ptab[p], pj = jk >> 16, pk = jk & 0xffff;
                 if (pj == i || pk == i) continue;
                 const double c = D2[p];
@@ -501,7 +520,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
             __syncthreads();
             if (tid < R.n_act_ang) {
                 double v = 0.0;
-                for (int w = nwa; w < RN_THREADS / 32; ++w) v += red[w * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + tid];
+                for (int w = SPLIT ? nwa : 0; w < RN_THREADS / 32; ++w) v += red[w * (RN_MAX_ANG + RN_MAX_RAD) + RN_MAX_RAD + tid];
                 ng[i * R.n_act + R.n_act_rad + tid] = g[i * R.n_act + R.n_act_rad + tid] + v * R.ang_tpz[tid];
             }
             __syncthreads();
@@ -538,7 +557,9 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
     for (int k = tid; k < 3 * N; k += RN_THREADS) R.pos_c[cfg * 3 * N + k] = pos[k];
     for (int k = tid; k < N * R.n_act; k += RN_THREADS) R.g_c[cfg * N * R.n_act + k] = gbuf[cur][k];
     for (int k = tid; k < N; k += RN_THREADS) R.en_atom_c[cfg * N + k] = eabuf[cur][k];
+#ifndef PTMC_RN_GLOBAL_TABLES
     if (n_acc) for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) pair_g[k] = D2[k];
+#endif
     if (tid == 0) {
         R.en_c[cfg] = en;
         P.counters[rep * PTMC_NCOUNT + PTMC_C_ATOM_TOT] += n_acc;
