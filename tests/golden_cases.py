@@ -1,5 +1,5 @@
 """Definitions of the golden replay cases (inputs only; outputs live in tests/golden/<name>.npz, written by
-tools/make_golden.py with the CPU oracle)."""
+tests/tools/make_golden.py with the CPU oracle)."""
 import numpy as np
 
 import ptmc_b200 as P

@@ -1,4 +1,4 @@
-"""Committed golden trajectories (tests/golden/*.npz, written by tools/make_golden.py with the CPU oracle).
+"""Committed golden trajectories (tests/golden/*.npz, written by tests/tools/make_golden.py with the CPU oracle).
 
 CPU (`-m "not gpu"`): the oracle still reproduces them (guards the checker itself against drift).
 GPU (`-m gpu`): the CUDA library reproduces them through the C ABI without the oracle in the loop."""

@@ -2,7 +2,7 @@
 """Throughput of every BASELINE config (C1..C5) on one GPU, device-resident, CUDA-event timed.
 Not the driver's bench (that is bench.py, C2 only); this feeds profiles/ and DESIGN.md.
 
-    python tools/bench_configs.py [--only c1,c3] > gpurun_out/configs.json"""
+    python tests/tools/bench_configs.py [--only c1,c3] > gpurun_out/configs.json"""
 import argparse
 import json
 import pathlib
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 
 import torch  # noqa: E402

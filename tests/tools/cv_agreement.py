@@ -5,7 +5,7 @@ sweep (many ladders) and of the CPU oracle (fewer ladders, other seeds) agree wi
 Cv(T)/kB at the ladder temperatures from the fluctuation formula (finalise_results, src/Sampling.jl:377-399), pooled over
 ladders; the error bar is the ladder-to-ladder standard error of each estimate.  One JSON line per deck.
 
-    python tools/cv_agreement.py > gpurun_out/cv_agreement.json"""
+    python tests/tools/cv_agreement.py > gpurun_out/cv_agreement.json"""
 import json
 import os
 import pathlib
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 
 import ptmc_b200 as P  # noqa: E402

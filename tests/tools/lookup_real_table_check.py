@@ -1,12 +1,14 @@
 import sys, json, numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import pathlib
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / 'tests'))
 import ptmc_b200 as P
 from ptmc_b200 import abi
 from ptmc_b200.engine import Engine
 from ptmc_b200.host import initial_arrays, sweep_config
 from oracle import oracle
 from parity import compare_traces, run_pair
-f = '/root/repo/paralleltemperingmontecarlo.jl_b200/data/_lut/LookupTable_Neon_B0.0_MP2.txt'
+f = str(ROOT / 'paralleltemperingmontecarlo.jl_b200' / 'data' / '_lut' / 'LookupTable_Neon_B0.0_MP2.txt')
 deck = P.host.deck_ne13_lookup(f, n_traj=25, cycles=200)
 mcp, temp, start, pot, ens = deck
 gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=2, n_cycles=100, seed=5)

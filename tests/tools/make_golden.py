@@ -6,14 +6,14 @@ Each fixture is one replayed trajectory: the deck and the stream seed define the
 regenerated from the seed by tests/parity.py::make_replay), the file holds the outputs: per-move index / delta
 energy / accept bit, per-cycle exchange record, final positions, energies, counters, step sizes, histogram.
 
-    python tools/make_golden.py          # rewrites tests/golden/*.npz
+    python tests/tools/make_golden.py          # rewrites tests/golden/*.npz
 """
 import pathlib
 import sys
 
 import numpy as np
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 

@@ -2,14 +2,14 @@
 """One short run of a BASELINE config for ncu: warm-up launch(es), then ONE profiled launch of `--cycles` cycles.
 
     ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 2 -c 1 -o gpurun_out/prof_x \\
-        python tools/prof_case.py c3_cu55_eam_nvt_28T --cycles 10"""
+        python tests/tools/prof_case.py c3_cu55_eam_nvt_28T --cycles 10"""
 import argparse
 import pathlib
 import sys
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tools"))
+sys.path.insert(0, str(ROOT / "tests" / "tools"))
 
 import ptmc_b200 as P  # noqa: E402
 from bench_configs import CASES  # noqa: E402
