@@ -67,8 +67,8 @@ typedef enum ptmc_rng_mode {
     PTMC_RNG_REPLAY = 1,  /* consume pre-drawn raw UInt64 draws from ptmc_set_replay (same derivations)   */
     PTMC_RNG_BATCH8 = 2   /* production mode: every slot owns PTMC_RNG_LANES Xoshiro256++ substreams that
                              step together once per move ("batch"); position k of the batch comes from
-                             substream k: 0 index (1 + mulhi(u, n_steps)), 1-3 displacement x,y,z (1: volume
-                             move), 4 acceptance, 5-7 first out-of-sphere redraw; every further redraw steps a
+                             substream k: 0 index (1 + mulhi(u, n_steps)), 1-3 displacement x,y,z (volume move: 1 scale
+                             factor, 2 the rand(1:6) of volume_change_separated as 1 + mulhi(u, 6)), 4 acceptance, 5-7 first out-of-sphere redraw; every further redraw steps a
                              new batch and uses positions 0-2 (the acceptance uniform is position 4 of the
                              latest batch).  Same generator and same uniform construction as mode 0.          */
 } ptmc_rng_mode;
