@@ -79,6 +79,7 @@ def load():
         "orc_get_tan": (C.c_double, [C.c_int, _dp, _dp, C.c_double, C.c_double]),
         "orc_dimer_energy_eljb": (C.c_double, [_dp, _dp, _dp, C.c_int, C.c_double, C.c_double]),
         "orc_lrc_eljb": (C.c_double, [C.c_int, C.c_double]),
+        "orc_lrc_lut": (C.c_double, [C.c_double, C.c_int, C.c_double]),
         "orc_dimer_energy_lut": (C.c_double, [_dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
         "orc_get_volume": (C.c_double, [C.c_int, C.c_double, C.c_double]),
         "orc_get_r_cut": (C.c_double, [C.c_int, C.c_double, C.c_double]),

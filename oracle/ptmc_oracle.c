@@ -305,6 +305,16 @@ double orc_lrc_eljb(int n_atoms, double r_cut) {
     return e_lrc;
 }
 
+/* lrc(::LookupTablePotential) src/EnergyEvaluation.jl:999-1009 (1.0, not 0.0, below r_cut = 10: verbatim) */
+double orc_lrc_lut(double c6coeff, int n_atoms, double r_cut) {
+    if (r_cut <= 10) return 1.0;
+    double r_cut_sqrt = pow(r_cut, 0.5);
+    double rc3 = r_cut * r_cut_sqrt;
+    double e_lrc = c6coeff / rc3 / 3;
+    e_lrc *= M_PI * ((double)n_atoms * n_atoms) / 4 / (r_cut_sqrt * r_cut_sqrt * r_cut_sqrt);
+    return e_lrc;
+}
+
 double orc_get_volume(int bc_kind, double L, double h) {
     switch (bc_kind) {
         case PTMC_BC_CUBIC: return L * L * L;
@@ -440,12 +450,30 @@ static double pair_energy_b(const ptmc_config* c, double r2, double tan_) {
         return orc_dimer_energy_lut(c->lut_table, c->lut_l_dist, c->lut_l_angle, c->lut_start_dist, c->lut_d_dist, c->lut_d_angle, c->lut_c6coeff, r2, tan_);
     return orc_dimer_energy_eljb(c->eljb_a, c->eljb_b, c->coeff, c->n_coeff, r2, tan_);
 }
-/* dimer_energy_atom with tangents src/EnergyEvaluation.jl:337-346 */
-static double eljb_energy_atom(const ptmc_config* c, int i, const double* d2vec, const double* tanvec, int n) {
+/* dimer_energy_atom with tangents src/EnergyEvaluation.jl:337-346 (no cut), :347-362 (d2 <= r_cut) */
+static double eljb_energy_atom(const ptmc_config* c, int i, const double* d2vec, const double* tanvec, int n, int use_cut, double r_cut) {
     double sum1 = 0.0;
-    for (int j = 0; j < i; ++j) sum1 += pair_energy_b(c, d2vec[j], tanvec[j]);
-    for (int j = i + 1; j < n; ++j) sum1 += pair_energy_b(c, d2vec[j], tanvec[j]);
+    for (int j = 0; j < i; ++j) if (!use_cut || d2vec[j] <= r_cut) sum1 += pair_energy_b(c, d2vec[j], tanvec[j]);
+    for (int j = i + 1; j < n; ++j) if (!use_cut || d2vec[j] <= r_cut) sum1 += pair_energy_b(c, d2vec[j], tanvec[j]);
     return sum1;
+}
+/* dimer_energy_config for the tangent-dependent potentials: :476-492 (no cut), Cubic :494-516 / :673-696, Rhombic :519-543 /
+ * :697-746, Rectangular :590-636 / :747-789.  tan_mat and new_tan_mat are one array in the reference (set_variables :1790,1798),
+ * so the "new_tan_mat != tan_mat" branches never differ; uniform volume moves leave the tangents unchanged. */
+static double config_energy_b(const ptmc_config* c, const double* d2, const double* tanm, int n, int use_cut, double r_cut, const double* box) {
+    double energy_tot = 0.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (!use_cut || d2[(size_t)i * n + j] <= r_cut) energy_tot += pair_energy_b(c, d2[(size_t)i * n + j], tanm[(size_t)i * n + j]);
+    if (!use_cut) return energy_tot;
+    double l = c->pot_kind == PTMC_POT_LUT ? orc_lrc_lut(c->lut_c6coeff, n, r_cut) : orc_lrc_eljb(n, r_cut);
+    switch (c->bc_kind) {
+        case PTMC_BC_CUBIC: return energy_tot + l;
+        case PTMC_BC_RHOMBIC: return energy_tot + l * 3 / 4 * box[0] / box[1];
+        default:
+            if (box[0] < box[1]) return energy_tot + l * box[0] / box[1];
+            return energy_tot + l * (box[1] * box[1]) / (box[0] * box[0]);
+    }
 }
 
 /* MCState(temp,beta,config,ensemble,pot) src/MCStates.jl:137-162 */
@@ -488,11 +516,7 @@ static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
             for (int j = i + 1; j < n; ++j)
                 s->tan[(size_t)i * n + j] = s->tan[(size_t)j * n + i] = orc_get_tan(c->bc_kind, s->pos + 3 * i, s->pos + 3 * j, s->box[0], s->box[1]);
         for (int i = 0; i < n; ++i) s->tan[(size_t)i * n + i] = 0;
-        double energy_tot = 0.0;
-        for (int i = 0; i < n; ++i)
-            for (int j = i + 1; j < n; ++j)
-                energy_tot += pair_energy_b(c, s->d2[(size_t)i * n + j], s->tan[(size_t)i * n + j]);
-        s->en_tot = energy_tot;
+        s->en_tot = config_energy_b(c, s->d2, s->tan, n, npt, s->r_cut, s->box);
     } else {
         s->en_tot = dimer_energy_config(c, s->d2, n, npt, s->r_cut, s->box); /* :1662-1693 */
     }
@@ -635,8 +659,8 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             /* energy_update!(::AbstractDimerPotentialB / ::LookupTablePotential) src/EnergyEvaluation.jl:1508-1533, dimer_energy_update! :822-836 */
             for (int j = 0; j < n; ++j) st->new_tan[j] = orc_get_tan(c->bc_kind, trial, s->pos + 3 * j, s->box[0], s->box[1]);
             st->new_tan[i] = 0;
-            double delta_en = eljb_energy_atom(c, i, st->new_d2, st->new_tan, n) -
-                              eljb_energy_atom(c, i, s->d2 + (size_t)i * n, s->tan + (size_t)i * n, n);
+            double delta_en = eljb_energy_atom(c, i, st->new_d2, st->new_tan, n, npt, s->r_cut) -
+                              eljb_energy_atom(c, i, s->d2 + (size_t)i * n, s->tan + (size_t)i * n, n, npt, s->r_cut);
             st->new_en = delta_en + s->en_tot;
         } else {
             /* dimer_energy_update! src/EnergyEvaluation.jl:804-821 */
@@ -718,7 +742,9 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
         for (size_t k = 0; k < (size_t)n * n; ++k) s->new_d2mat[k] = s->d2[k] * sc2;
         }
         /* get_energy! NPT else-branch src/MCRun.jl:76-85 */
-        st->new_en = dimer_energy_config(c, s->new_d2mat, n, 1, s->new_r_cut, s->trial_box);
+        st->new_en = (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT)
+                         ? config_energy_b(c, s->new_d2mat, s->tan, n, 1, s->new_r_cut, s->trial_box)
+                         : dimer_energy_config(c, s->new_d2mat, n, 1, s->new_r_cut, s->trial_box);
         /* metropolis_condition NPT src/Exchange.jl:58-71,77-85 */
         double de = st->new_en - s->en_tot;
         double vc = orc_get_volume(c->bc_kind, s->trial_box[0], s->trial_box[1]);
@@ -893,10 +919,10 @@ static void* xcalloc(size_t n, size_t sz) { void* p = calloc(n ? n : 1, sz); if 
 int orc_seed(orc_handle* H, uint64_t seed);
 orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER && (!cfg->runner || cfg->bc_kind != PTMC_BC_SPHERICAL)) return NULL;
-    /* ELJPotentialB: the free-space NVT path (scripts/ne13_B.jl); the periodic methods are outside the hot path */
-    if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->ensemble != PTMC_ENS_NVT)) return NULL;
+    /* tangent-dependent potentials: everything except the separated volume moves (they write trial tangents into the state) */
+    if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b || (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume))) return NULL;
     if (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume && cfg->bc_kind != PTMC_BC_RHOMBIC && cfg->bc_kind != PTMC_BC_RECTANGULAR) return NULL;
-    if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91 || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->ensemble != PTMC_ENS_NVT)) return NULL;
+    if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91 || (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume))) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
     H->cfg = *cfg;
     if (cfg->pot_kind == PTMC_POT_LUT) {

@@ -272,17 +272,17 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     switch (c->pot_kind) {
         case PTMC_POT_ELJ: case PTMC_POT_ELJ_EVEN:
             if (c->n_coeff < 1 || c->n_coeff > PTMC_MAX_COEFF) return fail(nullptr, PTMC_ERR_ARG, "n_coeff must be in 1..%d", PTMC_MAX_COEFF);
-            if (npt && c->pot_kind != PTMC_POT_ELJ_EVEN) return fail(nullptr, PTMC_ERR_ARG, "NPT long-range correction exists for ELJPotentialEven only (src/EnergyEvaluation.jl:968)");
+            if (npt && c->pot_kind != PTMC_POT_ELJ_EVEN) return fail(nullptr, PTMC_ERR_ARG, "NPT long-range correction exists for ELJPotentialEven, ELJPotentialB and LookupTablePotential only (src/EnergyEvaluation.jl:968-1009)");
             break;
         case PTMC_POT_ELJ_B:
             if (c->n_coeff < 1 || c->n_coeff > PTMC_MAX_COEFF) return fail(nullptr, PTMC_ERR_ARG, "n_coeff must be in 1..%d", PTMC_MAX_COEFF);
             if (!c->eljb_a || !c->eljb_b) return fail(nullptr, PTMC_ERR_ARG, "pot_kind ELJ_B needs ptmc_config.eljb_a / eljb_b");
-            if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "ELJPotentialB is built for SphericalBC/NVT (scripts/ne13_B.jl); its periodic methods are outside the hot path");
+            if (npt && c->separated_volume) return fail(nullptr, PTMC_ERR_ARG, "ELJPotentialB with separated volume moves is not built: the reference writes the trial tangents into the state (tan_mat and new_tan_mat are one array)");
             break;
         case PTMC_POT_LUT:
             if (!c->lut_table || c->lut_l_dist < 1 || c->lut_l_angle < 91 || !(c->lut_d_dist > 0) || !(c->lut_d_angle > 0))
                 return fail(nullptr, PTMC_ERR_ARG, "pot_kind LUT needs lut_table [l_angle >= 91][l_dist >= 1] and positive grid steps");
-            if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "LookupTablePotential is built for SphericalBC/NVT (scripts/ne13-lookup.jl); its periodic methods are outside the hot path");
+            if (npt && c->separated_volume) return fail(nullptr, PTMC_ERR_ARG, "LookupTablePotential with separated volume moves is not built: the reference writes the trial tangents into the state (tan_mat and new_tan_mat are one array)");
             break;
         case PTMC_POT_EAM:
             if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");

@@ -360,6 +360,36 @@ __device__ __forceinline__ double lrc_even(const DevParams& P, double r_cut) {
     return e * 3.14159265358979323846 * nn / 4.0 / (rs * rs * rs);
 }
 
+// lrc(::ELJPotentialB) src/EnergyEvaluation.jl:983-998 (fixed coefficients), lrc(::LookupTablePotential) :999-1009 (1.0 below r_cut = 10)
+__device__ __forceinline__ double lrc_eljb(const DevParams& P, double r_cut) {
+    if (r_cut <= 16.0) return 0.0;
+    const double coeff[4] = {-0.1279111890228638, -1.328138539967966, 12.260941135261255, 41.12212408251662};
+    double rs = sqrt(r_cut);
+    double rc3 = r_cut * rs;
+    double e = 0.0;
+    for (int i = 1; i <= 4; ++i) { e += coeff[i - 1] / rc3 / (double)(2 * i + 1); rc3 *= r_cut; }
+    double nn = (double)((i64)P.n_atoms * P.n_atoms);
+    return e * 3.14159265358979323846 * nn / 4.0 / (rs * rs * rs);
+}
+__device__ __forceinline__ double lrc_lut(const DevParams& P, double r_cut) {
+    if (r_cut <= 10.0) return 1.0;
+    double rs = sqrt(r_cut);
+    double e = P.lut_c6 / (r_cut * rs) / 3.0;
+    double nn = (double)((i64)P.n_atoms * P.n_atoms);
+    return e * 3.14159265358979323846 * nn / 4.0 / (rs * rs * rs);
+}
+template <int POT>
+__device__ __forceinline__ double lrc_pot(const DevParams& P, double r_cut) {
+    return POT == PTMC_POT_ELJ_B ? lrc_eljb(P, r_cut) : (POT == PTMC_POT_LUT ? lrc_lut(P, r_cut) : lrc_even(P, r_cut));
+}
+// pair energy of the tangent-dependent potentials from r2 and the (minimum-image) separation; s2 scales the separation's
+// squared z component to the scale of r2 (uniform volume trial: r2 = d2 * scale^2, the direction is unchanged)
+template <int POT, int NC>
+__device__ __forceinline__ double pair_energy_dir(const DevParams& P, double r2, double dx, double dy, double dz, double s2 = 1.0) {
+    if (POT == PTMC_POT_ELJ_B) return eljb_energy<NC>(P, r2, dz * dz * s2);
+    return lut_energy(P, r2, dx, dy, dz);
+}
+
 // ----------------------------------------------------------------------------------------- geometry --
 // Periodic box of one configuration with the constants the minimum-image formulas need.
 struct Box {
@@ -397,6 +427,23 @@ __device__ __forceinline__ double dist2_pbc(const Box& b, double ax, double ay, 
         dy = fma(-b.L, rint(ey * b.iL), ey);
     }
     const double dz = fma(-b.h, rint(ez * b.ih), ez);
+    return fma(dz, dz, fma(dy, dy, dx * dx));
+}
+// The same with the minimum-image separation itself (the tangent-dependent potentials need the direction of the pair)
+template <bool RHOMBIC>
+__device__ __forceinline__ double dist2_pbc_vec(const Box& b, double ax, double ay, double az, double bx, double by, double bz,
+                                                double& dx, double& dy, double& dz) {
+    const double ex = ax - bx, ey = ay - by, ez = az - bz;
+    if (RHOMBIC) {
+        const double nv = rint(ey * b.ihy);
+        const double nu = rint(fma(-b.is3, ey, ex) * b.iL);
+        dx = fma(-b.hL, nv, fma(-b.L, nu, ex));
+        dy = fma(-b.hy, nv, ey);
+    } else {
+        dx = fma(-b.L, rint(ex * b.iL), ex);
+        dy = fma(-b.L, rint(ey * b.iL), ey);
+    }
+    dz = fma(-b.h, rint(ez * b.ih), ez);
     return fma(dz, dz, fma(dy, dy, dx * dx));
 }
 // distance2 exactly as the reference writes it (src/Configurations.jl:101-126: true divisions, no FMA, image of

@@ -23,7 +23,11 @@ static sweep_fn generic_kernel(int pot, int geom, int dbg) {
     PTMC_PICK(PTMC_POT_ELJ, GEOM_PBC)
     PTMC_PICK(PTMC_POT_ELJ, GEOM_RHOMB)
     PTMC_PICK(PTMC_POT_ELJ_B, GEOM_SPHERE)
+    PTMC_PICK(PTMC_POT_ELJ_B, GEOM_PBC)
+    PTMC_PICK(PTMC_POT_ELJ_B, GEOM_RHOMB)
     PTMC_PICK(PTMC_POT_LUT, GEOM_SPHERE)
+    PTMC_PICK(PTMC_POT_LUT, GEOM_PBC)
+    PTMC_PICK(PTMC_POT_LUT, GEOM_RHOMB)
     if (pot == PTMC_POT_EAM && geom == GEOM_SPHERE) return dbg ? (sweep_fn)sweep_kernel_eam<G, true, 0> : (sweep_fn)sweep_kernel_eam<G, false, 0>;
 #undef PTMC_PICK
     return nullptr;

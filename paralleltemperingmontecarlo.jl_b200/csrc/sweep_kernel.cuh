@@ -99,6 +99,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     constexpr bool PBC = (GEOM != GEOM_SPHERE);
     constexpr bool rhombic = (GEOM == GEOM_RHOMB);
     constexpr bool BATCH = !DBG;
+    constexpr bool DIRP = POT == PTMC_POT_ELJ_B || POT == PTMC_POT_LUT;   // pair energy depends on the direction of the pair
     // ROT (free space, (N - 1) a multiple of G): lane g visits the OTHER atoms i+1+g, i+1+g+G, ... (mod N), so the row takes
     // (N - 1) / G iterations instead of ceil(N / G) (Ne13 on 4 lanes: 3 instead of 4) and needs neither parking nor selects
     constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN && !ROT;   // mask by parking atoms far away instead of per-pair selects
@@ -314,8 +315,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 auto pbc_term = [&](int k) {
                                     const int j = g + k * G;
                                     const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
-                                    const double d2n = rhombic ? dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj) : dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj);
-                                    const double d2o = rhombic ? dist2_pbc<true>(bx, xi, yi, zi, xj, yj, zj) : dist2_pbc<false>(bx, xi, yi, zi, xj, yj, zj);
+                                    double vn0 = 0, vn1 = 0, vn2 = 0, vo0 = 0, vo1 = 0, vo2 = 0;
+                                    const double d2n = DIRP ? dist2_pbc_vec<rhombic>(bx, tx, ty, tz, xj, yj, zj, vn0, vn1, vn2)
+                                                            : dist2_pbc<rhombic>(bx, tx, ty, tz, xj, yj, zj);
+                                    const double d2o = DIRP ? dist2_pbc_vec<rhombic>(bx, xi, yi, zi, xj, yj, zj, vo0, vo1, vo2)
+                                                            : dist2_pbc<rhombic>(bx, xi, yi, zi, xj, yj, zj);
                                     const bool valid = (j != i) && (j < N);
                                     if (POT == PTMC_POT_ELJ_EVEN) {
                                         const double a = (valid && (!npt || d2n <= rcut)) ? d2n : PTMC_PAIR_OFF;
@@ -323,7 +327,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                         elj_even_pair_acc<NC>(P, a, b, accn, acco);
                                     } else {
                                         const double dn = valid ? d2n : 1.0, dold = valid ? d2o : 1.0;
-                                        double en_j = pair_energy<POT, NC>(P, dn), eo_j = pair_energy<POT, NC>(P, dold);
+                                        double en_j = DIRP ? pair_energy_dir<POT, NC>(P, dn, vn0, vn1, vn2) : pair_energy<POT, NC>(P, dn);
+                                        double eo_j = DIRP ? pair_energy_dir<POT, NC>(P, dold, vo0, vo1, vo2) : pair_energy<POT, NC>(P, dold);
                                         if (npt) { en_j = (dn <= rcut) ? en_j : 0.0; eo_j = (dold <= rcut) ? eo_j : 0.0; }
                                         accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                     }
@@ -338,8 +343,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             } else
                             for (int j = g; j < N; j += G) {
                                 const double xj = X[j], yj = Y[j], zj = Z[j];
-                                double d2n = rhombic ? dist2_pbc<true>(bx, tx, ty, tz, xj, yj, zj) : dist2_pbc<false>(bx, tx, ty, tz, xj, yj, zj);
+                                double vn0 = 0, vn1 = 0, vn2 = 0, vo0 = 0, vo1 = 0, vo2 = 0;
+                                double d2n = DIRP ? dist2_pbc_vec<rhombic>(bx, tx, ty, tz, xj, yj, zj, vn0, vn1, vn2) : dist2_pbc<rhombic>(bx, tx, ty, tz, xj, yj, zj);
                                 double d2o = __ldcg(Drow + j);
+                                if (DIRP) (void)dist2_pbc_vec<rhombic>(bx, xi, yi, zi, xj, yj, zj, vo0, vo1, vo2);   // direction of the old pair
                                 const bool valid = (j != i);
                                 NEW[j] = valid ? d2n : 0.0;                       // new_dist2_vec[index] = 0, MCMoves.jl:111
                                 if (POT == PTMC_POT_ELJ_EVEN) {
@@ -349,7 +356,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     elj_even_pair_acc<NC>(P, a, b, accn, acco);
                                 } else {
                                     d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
-                                    double en_j = pair_energy<POT, NC>(P, d2n), eo_j = pair_energy<POT, NC>(P, d2o);
+                                    double en_j = DIRP ? pair_energy_dir<POT, NC>(P, d2n, vn0, vn1, vn2) : pair_energy<POT, NC>(P, d2n);
+                                    double eo_j = DIRP ? pair_energy_dir<POT, NC>(P, d2o, vo0, vo1, vo2) : pair_energy<POT, NC>(P, d2o);
                                     if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }   // :323-336
                                     accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                 }
@@ -520,18 +528,20 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             const double* Da = D + (size_t)a * N;
                             const double xa = X[a], ya = Y[a], za = Z[a];
                             for (int j = a + 1 + g; j < N; j += G) {
-                                double d2o;
-                                if (thawed) d2o = rhombic ? dist2_pbc<true>(bx, xa, ya, za, X[j], Y[j], Z[j]) : dist2_pbc<false>(bx, xa, ya, za, X[j], Y[j], Z[j]);
-                                else d2o = __ldcg(Da + j);
+                                double d2o, v0 = 0, v1 = 0, v2 = 0;
+                                if (DIRP) d2o = dist2_pbc_vec<rhombic>(bx, xa, ya, za, X[j], Y[j], Z[j], v0, v1, v2);
+                                if (!thawed) d2o = __ldcg(Da + j);
+                                else if (!DIRP) d2o = dist2_pbc<rhombic>(bx, xa, ya, za, X[j], Y[j], Z[j]);
                                 const double d2 = xmul(d2o, sc2);                 // new_dist2_mat[a, j]
-                                if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
+                                if (d2 <= new_rcut) acce += DIRP ? pair_energy_dir<POT, NC>(P, d2, v0, v1, v2, sc2)      // tangents unchanged by a uniform scaling
+                                                                 : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
                             }
                         }
                     } else {
                         acce = sep_trial_energy<G, POT, NC, rhombic>(P, X, Y, Z, N, g, scale_xy, scale_z, tL, tH, new_rcut, thawed);
                     }
                     double e_new = group_sum<G>(acce, gmask);
-                    const double l = lrc_even(P, new_rcut);
+                    const double l = lrc_pot<POT>(P, new_rcut);
                     if (P.bc_kind == PTMC_BC_CUBIC) e_new = e_new + l;
                     else if (P.bc_kind == PTMC_BC_RHOMBIC) e_new = e_new + l * 3 / 4 * tL / tH;
                     else e_new = (tL < tH) ? e_new + l * tL / tH : e_new + l * (tH * tH) / (tL * tL);
@@ -807,6 +817,14 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                     // get_distance2_mat! src/Configurations.jl:146-162: dest[i,j] = dest[j,i] = distance2(c[i], c[j], bc)
                     d2 = dist2_exact(P.bc_kind, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], L, h);
                     D[(size_t)a * N + j] = d2; D[(size_t)j * N + a] = d2;
+                    if (POT == PTMC_POT_ELJ_B || POT == PTMC_POT_LUT) {
+                        const Box b = make_box(P.bc_kind, L, h);
+                        double v0, v1, v2;
+                        if (P.bc_kind == PTMC_BC_RHOMBIC) (void)dist2_pbc_vec<true>(b, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], v0, v1, v2);
+                        else (void)dist2_pbc_vec<false>(b, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], v0, v1, v2);
+                        if (!npt || d2 <= rcut) acc += pair_energy_dir<POT, 0>(P, d2, v0, v1, v2);
+                        continue;
+                    }
                 } else {
                     double dx = xa - gp[3 * j], dy = ya - gp[3 * j + 1], dz = za - gp[3 * j + 2];
                     d2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -819,7 +837,7 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
         if (pbc) for (int a = g; a < N; a += 32) D[(size_t)a * N + a] = 0.0;
         double e = group_sum<32>(acc, 0xffffffffu);
         if (npt) {
-            const double l = lrc_even(P, rcut);
+            const double l = lrc_pot<POT>(P, rcut);
             if (P.bc_kind == PTMC_BC_CUBIC) e = e + l;
             else if (P.bc_kind == PTMC_BC_RHOMBIC) e = e + l * 3 / 4 * L / h;
             else e = (L < h) ? e + l * L / h : e + l * (h * h) / (L * L);

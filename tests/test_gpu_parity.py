@@ -538,8 +538,6 @@ def test_eljb_magnetic_field_potential(oracle):
     eng.upload_states(sg["pos"], sg["box"])
     np.testing.assert_allclose(eng.download_states(("en_tot",))["en_tot"], sg["en_tot"], rtol=1e-11)
     eng.close()
-    with pytest.raises(PtmcError):          # periodic / NPT ELJB is outside the hot path: refused, not approximated
-        Engine(sweep_config(P.MCParams(10, 4, 32), P.TempGrid(20.0, 40.0, 4), _small_pbc(P.CubicBC), pot, P.NVT(32)))
 
 
 @pytest.mark.parametrize("case", ["ne13", "eam", "eljb"])
@@ -740,3 +738,30 @@ def test_edge_case_sizes_replay():
     _assert_same_trajectory(res)
     with pytest.raises(PtmcError):                              # 49 temperatures x 8 lanes do not fit one ladder CTA
         Engine(sweep_config(*P.host.deck_ne55(n_traj=49, cycles=1), lanes_per_replica=8))
+
+
+def _scaled(cfg, f):
+    bc = cfg.boundary_condition
+    nbc = P.CubicBC(bc.box_length * f) if isinstance(bc, P.CubicBC) else type(bc)(bc.box_length * f, bc.box_height * f)
+    return P.Config(cfg.positions * f, nbc)
+
+
+@pytest.mark.parametrize("pot_name", ["eljb", "lookup"])
+@pytest.mark.parametrize("bc_cls", [P.CubicBC, P.RectangularBC, P.RhombicBC])
+def test_periodic_direction_dependent_potentials(pot_name, bc_cls, oracle):
+    # ELJPotentialB / LookupTablePotential in a periodic cell, NVT and NPT with uniform volume moves (scripts/pbc150.jl, pbc96.jl run
+    # the lookup table this way): tangent from the minimum-image separation, d2 <= r_cut and the potentials' own long-range
+    # corrections (src/EnergyEvaluation.jl:494-543,673-789,983-1009).  Replayed streams: decisions identical, dE to 1e-10.
+    start = _scaled(_small_pbc(bc_cls), 1 / 1.8897259886)            # both potentials work in Angstrom
+    pot = P.ELJPotentialB(P.host.ELJB_NE_A, P.host.ELJB_NE_B, P.host.ELJB_NE_C) if pot_name == "eljb" else _synthetic_lookup_table()
+    temp = P.TempGrid(20.0, 40.0, 4)
+    # NVT
+    gpu, cpu = run_pair(P.MCParams(20, 4, 32, n_adjust=10), temp, start, pot, P.NVT(32), n_ladders=2, n_cycles=20, seed=3)
+    compare_traces(gpu, cpu)
+    # NPT, uniform volume moves
+    ens = P.NPT(32, 101325 * 3.398928944382626e-14 * 1.8897259886 ** 3, False, n_volume_moves=2)
+    gpu, cpu = run_pair(P.MCParams(30, 4, 32, n_adjust=10), temp, start, pot, ens, n_ladders=2, n_cycles=30, seed=4)
+    compare_traces(gpu, cpu, positions_exact=False)
+    assert gpu["trace"]["move_index"].max() == 34 and gpu["states"]["counters"][:, :, abi.C_VOL_TOT].sum() > 0
+    with pytest.raises(PtmcError):      # separated volume moves would write trial tangents into the state (reference: one aliased array)
+        Engine(sweep_config(P.MCParams(30, 4, 32), temp, _scaled(_small_pbc(P.RhombicBC), 1 / 1.8897259886), pot, P.NPT(32, 1e-9, True)))

@@ -181,3 +181,16 @@ def test_tangent_known_answers(oracle):
     assert oracle.get_tan(abi.BC_CUBIC, v2, v3, 10.0, 10.0) == 1 / 3
     assert oracle.get_tan(abi.BC_RHOMBIC, v1, v2, 5.0, 5.0) == 2.0 and oracle.get_tan(abi.BC_RHOMBIC, v2, v3, 5.0, 5.0) == 0.5
     assert oracle.get_tan(abi.BC_RHOMBIC, v1, v3, 5.0, 5.0) == 1.0
+
+
+def test_eljb_rhombic_state_energy_through_the_engine(oracle):
+    # the same known answer (test/separated_v_test.jl:90-111) through the oracle's MCState construction for a periodic NPT state
+    from ptmc_b200.host import ELJB_NE_A, ELJB_NE_B, ELJB_NE_C
+    start = P.Config(np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [0.0, 1.0, 0.0]]), P.RhombicBC(10.0, 10.0))
+    mcp, temp = P.MCParams(10, 2, 3), P.TempGrid(10.0, 15.0, 2)
+    ens = P.NPT(3, 101325 * 3.398928944382626e-14, False)
+    eng = oracle.OracleEngine(sweep_config(mcp, temp, start, P.ELJPotentialB(ELJB_NE_A, ELJB_NE_B, ELJB_NE_C), ens))
+    pos, box = initial_arrays(mcp, start, 1)
+    eng.upload_states(pos, box)
+    assert (eng.download_states(("en_tot",))["en_tot"] == -0.00016263185592172208).all()
+    eng.close()
