@@ -26,7 +26,7 @@ LUT_FILE = os.environ.get("PTMC_LUT_FILE", str(ROOT / "paralleltemperingmontecar
 
 CASES = {
     # name: (deck factory, ladders, warm-up cycles, timed cycles per step, steps, histogram window)
-    "c1_ne13_elj_nvt_32T": (lambda: P.host.deck_ne13(n_traj=32, cycles=100), 8192, 200, 100, 5, (-0.01, 0.0, None, None)),
+    "c1_ne13_elj_nvt_32T": (lambda: P.host.deck_ne13(n_traj=32, cycles=100), 8880, 200, 100, 5, (-0.01, 0.0, None, None)),
     "c1b_ne13_eljb_nvt_16T": (lambda: P.host.deck_ne13_B(n_traj=16, cycles=100), 8192, 200, 100, 5, (-0.02, 0.0, None, None)),
     # scripts/ne13-lookup.jl; needs the reference's scripts/lookup-tables/LookupTable_Neon_B0.0_MP2.txt (not redistributed here):
     # PTMC_LUT_FILE or paralleltemperingmontecarlo.jl_b200/data/_lut/ (git-ignored); the case is skipped without it
