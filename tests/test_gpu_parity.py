@@ -406,17 +406,20 @@ def test_eam_power_accuracy():
     eng.close()
 
 
-@pytest.mark.parametrize("case", ["eam", "pbc216", "runner"])
+@pytest.mark.parametrize("case", ["eam", "pbc216", "runner", "eam_full", "pbc216_full", "runner_full"])
 def test_energy_bookkeeping_other_potentials(case):
     # size-independent property for the other potentials: the running en_tot (updated move by move, through exchanges,
     # volume moves, the frozen -> thawed switch of the periodic kernel, incremental G-matrix updates of RuNNer) equals the
     # energy a fresh handle computes from the final positions and boxes
+    # "_full": the ladder counts of the benchmark configurations (C3 2048 x 28, C4 592 x 16, C5 37 x 28 replicas)
+    full = case.endswith("_full")
+    case = case.replace("_full", "")
     if case == "eam":
-        deck, L, cycles, tol = P.host.deck_cu55_eam(n_traj=28, cycles=40), 64, 40, 1e-11
+        deck, L, cycles, tol = P.host.deck_cu55_eam(n_traj=28, cycles=40), (2048 if full else 64), (10 if full else 40), 1e-11
     elif case == "pbc216":
-        deck, L, cycles, tol = P.host.deck_pbc216(n_traj=16, cycles=40), 8, 40, 1e-10
+        deck, L, cycles, tol = P.host.deck_pbc216(n_traj=16, cycles=40), (592 if full else 8), (12 if full else 40), 1e-10
     else:
-        deck, L, cycles, tol = P.host.deck_cu55_runner(n_traj=8, cycles=6), 2, 6, 1e-11
+        deck, L, cycles, tol = P.host.deck_cu55_runner(n_traj=28 if full else 8, cycles=6), (37 if full else 2), (3 if full else 6), 1e-11
     mcp, temp, start, pot, ens = deck
     cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=3)
     pos, box = initial_arrays(mcp, start, L)
@@ -436,7 +439,7 @@ def test_energy_bookkeeping_other_potentials(case):
         # rows 80/83/86 of the G matrix differ between the incremental path and an initialisation from scratch (quirk 3),
         # so compare per-configuration energies through the G matrices' common rows instead: re-derive with the oracle-free
         # property that the sum of per-atom energies equals en_tot
-        for l in range(L):
+        for l in range(0, L, 9 if full else 1):
             for t in range(mcp.n_traj):
                 g, ea = eng.runner_state(l, t)
                 assert ea.sum() == pytest.approx(st["en_tot"][l, t], rel=1e-13)
