@@ -729,6 +729,15 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             }
             s->new_r_cut = orc_get_r_cut(c->bc_kind, s->trial_box[0], s->trial_box[1]);
             d2_matrix(c, s->trial_pos, s->trial_box, s->new_d2mat, n);
+            if (xy_or_z >= 1 && (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT)) {
+                /* src/MCMoves.jl:333-341: get_tantheta_mat!(new_tan_mat, trial_config) - and new_tan_mat IS tan_mat (one array,
+                 * set_variables src/EnergyEvaluation.jl:1790,1798): the trial's tangents stay in the state even if the move is rejected */
+                for (int i = 0; i < n; ++i)
+                    for (int j = i + 1; j < n; ++j)
+                        s->tan[(size_t)i * n + j] = s->tan[(size_t)j * n + i] =
+                            orc_get_tan(c->bc_kind, s->trial_pos + 3 * i, s->trial_pos + 3 * j, s->trial_box[0], s->trial_box[1]);
+                for (int i = 0; i < n; ++i) s->tan[(size_t)i * n + i] = 0;
+            }
         } else {
         /* volume_change_uniform src/MCMoves.jl:277-287, volume_change_xyz :169-177 */
         double uv = bm ? rng_batch_rand(&st->rng, 1) : rng_rand(&st->rng);
@@ -919,10 +928,9 @@ static void* xcalloc(size_t n, size_t sz) { void* p = calloc(n ? n : 1, sz); if 
 int orc_seed(orc_handle* H, uint64_t seed);
 orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER && (!cfg->runner || cfg->bc_kind != PTMC_BC_SPHERICAL)) return NULL;
-    /* tangent-dependent potentials: everything except the separated volume moves (they write trial tangents into the state) */
-    if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b || (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume))) return NULL;
+    if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b)) return NULL;
     if (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume && cfg->bc_kind != PTMC_BC_RHOMBIC && cfg->bc_kind != PTMC_BC_RECTANGULAR) return NULL;
-    if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91 || (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume))) return NULL;
+    if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91)) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
     H->cfg = *cfg;
     if (cfg->pot_kind == PTMC_POT_LUT) {

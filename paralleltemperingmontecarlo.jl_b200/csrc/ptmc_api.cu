@@ -277,12 +277,10 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         case PTMC_POT_ELJ_B:
             if (c->n_coeff < 1 || c->n_coeff > PTMC_MAX_COEFF) return fail(nullptr, PTMC_ERR_ARG, "n_coeff must be in 1..%d", PTMC_MAX_COEFF);
             if (!c->eljb_a || !c->eljb_b) return fail(nullptr, PTMC_ERR_ARG, "pot_kind ELJ_B needs ptmc_config.eljb_a / eljb_b");
-            if (npt && c->separated_volume) return fail(nullptr, PTMC_ERR_ARG, "ELJPotentialB with separated volume moves is not built: the reference writes the trial tangents into the state (tan_mat and new_tan_mat are one array)");
             break;
         case PTMC_POT_LUT:
             if (!c->lut_table || c->lut_l_dist < 1 || c->lut_l_angle < 91 || !(c->lut_d_dist > 0) || !(c->lut_d_angle > 0))
                 return fail(nullptr, PTMC_ERR_ARG, "pot_kind LUT needs lut_table [l_angle >= 91][l_dist >= 1] and positive grid steps");
-            if (npt && c->separated_volume) return fail(nullptr, PTMC_ERR_ARG, "LookupTablePotential with separated volume moves is not built: the reference writes the trial tangents into the state (tan_mat and new_tan_mat are one array)");
             break;
         case PTMC_POT_EAM:
             if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
@@ -354,7 +352,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     int rc = 0;
     if ((rc = dev_alloc(h, &P.pos, R * N * 3)) || (rc = dev_alloc(h, &P.box, R * 2)) || (rc = dev_alloc(h, &P.en_tot, R)) ||
         (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) ||
-        (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) || (rc = dev_alloc(h, &P.perm_g, R)) ||
+        (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) ||
+        (rc = dev_alloc(h, &P.tanmat, (!sphere && npt && c->separated_volume && (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT)) ? R * N * N : 1)) || (rc = dev_alloc(h, &P.perm_g, R)) ||
         (rc = dev_alloc(h, &P.moved_g, R * ((N + 31) / 32 + 1))) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
         (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.max_boxheight, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
         (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4 * PTMC_RNG_LANES)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||

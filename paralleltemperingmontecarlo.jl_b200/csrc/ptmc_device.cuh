@@ -58,6 +58,7 @@ struct DevParams {
     // periodic boundaries: the reference's dist2_mat, kept in HBM per CONFIGURATION (not per slot) so that an
     // exchange never moves it; perm_g is the slot -> configuration map, persisted between launches
     double* d2mat;      // [L][T][N][N]
+    double* tanmat;     // [L][T][N][N]  tan_mat of the tangent-dependent potentials, kept only with separated volume moves
     int* perm_g;        // [L][T]
     // per configuration: bit mask of the atoms moved (accepted) since the upload + their count.  Frozen dist2_mat
     // entries can only differ in a DECISION from recomputed distances for pairs of never-moved lattice atoms (exact
@@ -268,10 +269,20 @@ __device__ __forceinline__ void elj_even_pair_acc(const DevParams& P, double d2n
 // t2 = cos 2theta = 2 / (tan^2 + 1) - 1 = 2 dz^2 / r^2 - 1 (no tangent matrix is stored: the angle comes from the positions
 // like the distance), t4 = 2 t2^2 - 1; below r2 = 5.30 the reference returns 0.1.
 template <int NC = 0>
+__device__ __forceinline__ double eljb_energy_t2(const DevParams& P, double r2, double y, double t2);
+template <int NC = 0>
 __device__ __forceinline__ double eljb_energy(const DevParams& P, double r2, double dz2) {
     const double y = rsqrt_pos(r2);
+    return eljb_energy_t2<NC>(P, r2, y, fma(2.0 * dz2, y * y, -1.0));
+}
+// the same from a stored tangent: t2 = 2 / (tan^2 + 1) - 1 as the reference writes it (:946); tan = Inf -> -1
+template <int NC = 0>
+__device__ __forceinline__ double eljb_energy_tan(const DevParams& P, double r2, double tan_) {
+    return eljb_energy_t2<NC>(P, r2, rsqrt_pos(r2), xsub(xdiv(2.0, xadd(xmul(tan_, tan_), 1.0)), 1.0));
+}
+template <int NC>
+__device__ __forceinline__ double eljb_energy_t2(const DevParams& P, double r2, double y, double t2) {
     const double x = y * y;
-    const double t2 = fma(2.0 * dz2, x, -1.0);
     const double t4 = fma(2.0 * t2, t2, -1.0);
     const int n = NC ? NC : P.n_coeff;
     double p = 0.0;
@@ -284,8 +295,13 @@ __device__ __forceinline__ double eljb_energy(const DevParams& P, double r2, dou
 
 // dimer_energy(::LookupTablePotential) src/EnergyEvaluation.jl:274-295 with get_tan (src/Configurations.jl:177-180) of the
 // separation (dx, dy, dz): the table indices are decisions, so the index arithmetic keeps the reference's operation order.
+// get_tan src/Configurations.jl:177-180 of a separation
+__device__ __forceinline__ double tan_of(double dx, double dy, double dz) { return fabs(xdiv(sqrt(xadd(xmul(dx, dx), xmul(dy, dy))), dz)); }
+__device__ __forceinline__ double lut_energy_tan(const DevParams& P, double r2, double t);
 __device__ __forceinline__ double lut_energy(const DevParams& P, double r2, double dx, double dy, double dz) {
-    const double t = fabs(xdiv(sqrt(xadd(xmul(dx, dx), xmul(dy, dy))), dz));
+    return lut_energy_tan(P, r2, tan_of(dx, dy, dz));
+}
+__device__ __forceinline__ double lut_energy_tan(const DevParams& P, double r2, double t) {
     int ai = 1;
     if (t > 0.00872687153 && t <= 114.592845357) ai = (int)rint(xadd(xdiv(xmul(xdiv(atan(t), P.lut_dang), 180.0), 3.14159265358979323846), 1.0));
     else if (t > 114.592845357) ai = 91;
@@ -388,6 +404,12 @@ template <int POT, int NC>
 __device__ __forceinline__ double pair_energy_dir(const DevParams& P, double r2, double dx, double dy, double dz, double s2 = 1.0) {
     if (POT == PTMC_POT_ELJ_B) return eljb_energy<NC>(P, r2, dz * dz * s2);
     return lut_energy(P, r2, dx, dy, dz);
+}
+// ... and from a stored tangent (separated volume moves keep the reference's tan_mat, stale entries included)
+template <int POT, int NC>
+__device__ __forceinline__ double pair_energy_tan(const DevParams& P, double r2, double tan_) {
+    if (POT == PTMC_POT_ELJ_B) return eljb_energy_tan<NC>(P, r2, tan_);
+    return lut_energy_tan(P, r2, tan_);
 }
 
 // ----------------------------------------------------------------------------------------- geometry --

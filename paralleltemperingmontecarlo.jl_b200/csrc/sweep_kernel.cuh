@@ -42,7 +42,8 @@ struct SmemLayout {
 __host__ __device__ constexpr bool eam_unrolled(int niter, bool dbg) { return PTMC_EAM_UNROLL && !dbg && niter >= 1 && niter <= PTMC_EAM_MAX_NITER; }
 __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch) {
     SmemLayout s;
-    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + (pbc ? 1 : 0);   // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec)
+    const bool dirp = pot_kind == PTMC_POT_ELJ_B || pot_kind == PTMC_POT_LUT;
+    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + (pbc ? 1 : 0) + (pbc && dirp ? 1 : 0);   // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec [+ new_tan_vec])
     s.cfg_stride = arrays * n_pad;
     s.off_scal = n_traj * s.cfg_stride;
     int off = s.off_scal + 4 * n_traj;
@@ -64,16 +65,28 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
 // still holds never-moved lattice atoms, the reciprocal-multiply minimum image afterwards.  Returns this lane's partial sum.
 template <int G, int POT, int NC, bool RHOMBIC>
 __device__ __forceinline__ double sep_trial_energy(const DevParams& P, const double* X, const double* Y, const double* Z, int N, int g,
-                                               double scale_xy, double scale_z, double tL, double tH, double new_rcut, bool thawed) {
+                                                  double scale_xy, double scale_z, double tL, double tH, double new_rcut, bool thawed,
+                                                  double* T = nullptr, bool write_tan = false) {
+    constexpr bool DIRP = POT == PTMC_POT_ELJ_B || POT == PTMC_POT_LUT;
     const Box tbx = make_box(P.bc_kind, tL, tH);
     double acce = 0.0;
     for (int a = 0; a < N - 1; ++a) {
         const double pax = xmul(X[a], scale_xy), pay = xmul(Y[a], scale_xy), paz = xmul(Z[a], scale_z);
         for (int j = a + 1 + g; j < N; j += G) {
             const double pbx = xmul(X[j], scale_xy), pby = xmul(Y[j], scale_xy), pbz = xmul(Z[j], scale_z);
-            const double d2 = thawed ? dist2_pbc<RHOMBIC>(tbx, pax, pay, paz, pbx, pby, pbz)
-                                     : dist2_exact(P.bc_kind, pax, pay, paz, pbx, pby, pbz, tL, tH);
-            if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
+            double v0 = 0, v1 = 0, v2 = 0;
+            double d2 = (DIRP || thawed) ? dist2_pbc_vec<RHOMBIC>(tbx, pax, pay, paz, pbx, pby, pbz, v0, v1, v2) : 0.0;
+            if (!thawed) d2 = dist2_exact(P.bc_kind, pax, pay, paz, pbx, pby, pbz, tL, tH);
+            if (DIRP) {
+                // tangent-dependent potentials: xy / z trials write the trial configuration's tangents into tan_mat (kept even if
+                // the move is rejected: the reference's new_tan_mat is the same array, src/MCMoves.jl:333-341); the uniform trial reads it
+                double tn;
+                if (write_tan) { tn = tan_of(v0, v1, v2); __stcg(T + (size_t)a * N + j, tn); __stcg(T + (size_t)j * N + a, tn); }
+                else tn = __ldcg(T + (size_t)a * N + j);
+                if (d2 <= new_rcut) acce += pair_energy_tan<POT, NC>(P, d2, tn);
+            } else {
+                if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
+            }
         }
     }
     return acce;
@@ -309,6 +322,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             const bool thawed = moved[c * MW + MW - 1] >= N;
                             const double* Drow = P.d2mat + (((size_t)lad * T + c) * N + i) * N;
                             double* NEW = Z + NP;
+                            // tangent-dependent potentials with separated volume moves: tan_mat is state (stale entries included)
+                            const bool tanst = DIRP && P.separated != 0;
+                            const double* Trow = tanst ? P.tanmat + (((size_t)lad * T + c) * N + i) * N : nullptr;
+                            double* NEWT = Z + 2 * NP;
                             if (thawed) {
                                 // thawed: both rows from the positions in shared memory, pair loop unrolled like the free-space one
                                 const double* Xg = X + g;
@@ -327,8 +344,16 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                         elj_even_pair_acc<NC>(P, a, b, accn, acco);
                                     } else {
                                         const double dn = valid ? d2n : 1.0, dold = valid ? d2o : 1.0;
-                                        double en_j = DIRP ? pair_energy_dir<POT, NC>(P, dn, vn0, vn1, vn2) : pair_energy<POT, NC>(P, dn);
-                                        double eo_j = DIRP ? pair_energy_dir<POT, NC>(P, dold, vo0, vo1, vo2) : pair_energy<POT, NC>(P, dold);
+                                        double en_j, eo_j;
+                                        if (DIRP && tanst) {
+                                            const double tn = tan_of(vn0, vn1, vn2);
+                                            if (j < N) NEWT[j] = valid ? tn : 0.0;                      // new_tan_vec, [index] = 0
+                                            en_j = pair_energy_tan<POT, NC>(P, dn, tn);
+                                            eo_j = pair_energy_tan<POT, NC>(P, dold, (j < N) ? __ldcg(Trow + j) : 0.0);
+                                        } else {
+                                            en_j = DIRP ? pair_energy_dir<POT, NC>(P, dn, vn0, vn1, vn2) : pair_energy<POT, NC>(P, dn);
+                                            eo_j = DIRP ? pair_energy_dir<POT, NC>(P, dold, vo0, vo1, vo2) : pair_energy<POT, NC>(P, dold);
+                                        }
                                         if (npt) { en_j = (dn <= rcut) ? en_j : 0.0; eo_j = (dold <= rcut) ? eo_j : 0.0; }
                                         accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                     }
@@ -356,8 +381,16 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     elj_even_pair_acc<NC>(P, a, b, accn, acco);
                                 } else {
                                     d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
-                                    double en_j = DIRP ? pair_energy_dir<POT, NC>(P, d2n, vn0, vn1, vn2) : pair_energy<POT, NC>(P, d2n);
-                                    double eo_j = DIRP ? pair_energy_dir<POT, NC>(P, d2o, vo0, vo1, vo2) : pair_energy<POT, NC>(P, d2o);
+                                    double en_j, eo_j;
+                                    if (DIRP && tanst) {
+                                        const double tn = tan_of(vn0, vn1, vn2);
+                                        NEWT[j] = valid ? tn : 0.0;
+                                        en_j = pair_energy_tan<POT, NC>(P, d2n, tn);
+                                        eo_j = pair_energy_tan<POT, NC>(P, d2o, __ldcg(Trow + j));
+                                    } else {
+                                        en_j = DIRP ? pair_energy_dir<POT, NC>(P, d2n, vn0, vn1, vn2) : pair_energy<POT, NC>(P, d2n);
+                                        eo_j = DIRP ? pair_energy_dir<POT, NC>(P, d2o, vo0, vo1, vo2) : pair_energy<POT, NC>(P, d2o);
+                                    }
                                     if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }   // :323-336
                                     accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                 }
@@ -445,6 +478,17 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                         en = new_en;
                         n_acc_atom += 1; n_adj_atom += 1;
                         if (PBC) {
+                            if (DIRP && P.separated != 0) {
+                                // tan_mat[index, :] = tan_mat[:, index] = new_tan_vec  (swap_vars! src/swap_config.jl:197-206)
+                                double* Tm = P.tanmat + ((size_t)lad * T + c) * N * N;
+                                const double* NEWT = Z + 2 * NP;
+                                __syncwarp(gmask);
+                                for (int j = g; j < N; j += G) {
+                                    const double v = NEWT[j];
+                                    __stcg(Tm + (size_t)i * N + j, v);
+                                    __stcg(Tm + (size_t)j * N + i, v);
+                                }
+                            }
                             if (moved[c * MW + MW - 1] < N) {
                                 // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
                                 double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
@@ -538,7 +582,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             }
                         }
                     } else {
-                        acce = sep_trial_energy<G, POT, NC, rhombic>(P, X, Y, Z, N, g, scale_xy, scale_z, tL, tH, new_rcut, thawed);
+                        acce = sep_trial_energy<G, POT, NC, rhombic>(P, X, Y, Z, N, g, scale_xy, scale_z, tL, tH, new_rcut, thawed,
+                                                                     DIRP ? P.tanmat + ((size_t)lad * T + c) * N * N : nullptr, xyz >= 1);
                     }
                     double e_new = group_sum<G>(acce, gmask);
                     const double l = lrc_pot<POT>(P, new_rcut);
@@ -822,7 +867,12 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                         double v0, v1, v2;
                         if (P.bc_kind == PTMC_BC_RHOMBIC) (void)dist2_pbc_vec<true>(b, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], v0, v1, v2);
                         else (void)dist2_pbc_vec<false>(b, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], v0, v1, v2);
-                        if (!npt || d2 <= rcut) acc += pair_energy_dir<POT, 0>(P, d2, v0, v1, v2);
+                        if (P.separated) {      // set_variables: tan_mat = get_tantheta_mat(config)
+                            const double tn = tan_of(v0, v1, v2);
+                            double* Tm = P.tanmat + (size_t)rep * N * N;
+                            Tm[(size_t)a * N + j] = tn; Tm[(size_t)j * N + a] = tn;
+                            if (!npt || d2 <= rcut) acc += pair_energy_tan<POT, 0>(P, d2, tn);
+                        } else if (!npt || d2 <= rcut) acc += pair_energy_dir<POT, 0>(P, d2, v0, v1, v2);
                         continue;
                     }
                 } else {

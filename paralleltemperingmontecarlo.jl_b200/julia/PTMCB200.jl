@@ -81,8 +81,8 @@ box_of(bc::Union{RhombicBC,RectangularBC}) = (bc.box_length, bc.box_height)
 pot_fields(p::ELJPotential{N}) where {N} = (Int32(0), Int32(N), Tuple(p.coeff), (0.0, 0.0, 0.0, 0.0))
 pot_fields(p::ELJPotentialEven{N}) where {N} = (Int32(1), Int32(N), Tuple(p.coeff), (0.0, 0.0, 0.0, 0.0))
 pot_fields(p::EmbeddedAtomPotential) = (Int32(2), Int32(0), (), (p.n, p.m, p.ean, p.eCam))
-pot_fields(p::LookupTablePotential) = (Int32(5), Int32(0), (), (0.0, 0.0, 0.0, 0.0))                       # not with separated volume moves
-pot_fields(p::ELJPotentialB{N}) where {N} = (Int32(4), Int32(N), Tuple(p.coeff_c), (0.0, 0.0, 0.0, 0.0))   # not with separated volume moves
+pot_fields(p::LookupTablePotential) = (Int32(5), Int32(0), (), (0.0, 0.0, 0.0, 0.0))
+pot_fields(p::ELJPotentialB{N}) where {N} = (Int32(4), Int32(N), Tuple(p.coeff_c), (0.0, 0.0, 0.0, 0.0))
 
 pad16(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, PTMC_MAX_COEFF)
 
