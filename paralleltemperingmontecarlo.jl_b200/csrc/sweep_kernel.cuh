@@ -2,7 +2,7 @@
 // ladder per CTA.  Instantiated per (lanes-per-replica G, potential, geometry, debug, unrolling) in sweep_inst.cu.
 //
 //   mc_step!  (src/MCRun.jl:169-182)  -> every group runs n_steps x mc_move! on its slot, no CTA sync
-//   exchange  (src/MCRun.jl:203-205, src/Exchange.jl:132-186) -> thread 0 between two __syncthreads()
+//   exchange  (src/MCRun.jl:203-205, src/Exchange.jl:132-186) -> lane 0 of the lower slot between two barriers of the two warps involved
 //   update_max_stepsize! (src/Exchange.jl:198-263), sampling_step! (src/Sampling.jl:330-371) -> per group
 #pragma once
 #include "ptmc_device.cuh"
@@ -57,6 +57,10 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     s.off_tab = off; off += pot_kind == PTMC_POT_EAM ? PTMC_EAM_KTAB_DOUBLES : 0;
     s.bytes = (size_t)off * sizeof(double);
     return s;
+}
+
+__device__ __forceinline__ void named_barrier(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
 // Separated volume moves (src/MCMoves.jl:300-343), separate loops so that the uniform-move loops stay as they are.
@@ -654,10 +658,22 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
         }
         ex_gate = __shfl_sync(0xffffffffu, ex_gate, 0);
         if (ex_gate) {
-            __syncthreads();                                        // every slot has finished this cycle's moves
-            if (tid == 0) {
+            ex_n = __shfl_sync(0xffffffffu, ex_n, 0);
+            ex_u = __shfl_sync(0xffffffffu, ex_u, 0);
+            // Only the two slots of the attempt have to meet: every warp steps its own copy of the ladder stream, so the other
+            // warps run on (replicas differ a lot in work per cycle: volume moves, out-of-sphere redraws).  The two warps meet on
+            // named barrier 1 + (lower warp) - ids 1..15, hence CTAs of up to 16 warps; larger ones use the CTA barrier.
+            const int a = ex_n - 1, b = ex_n;
+            const int wa = (a * G) >> 5, wb = (b * G) >> 5, wme = tid >> 5;
+            // (not for 4 lanes per replica: a data-dependent barrier id makes the CTA reserve all 16 hardware barriers, which
+            //  caps the number of resident CTAs of the small Ne13-class kernels - measured -16 % there, profiles/r01_experiments.md)
+            const bool pairwise = G >= 8 && blockDim.x <= 512;
+            const bool mine = !pairwise || wme == wa || wme == wb;
+            if (!pairwise) __syncthreads();                         // every slot has finished this cycle's moves
+            else if (mine && wa != wb) named_barrier(1 + wa, 64);
+            else __syncwarp();
+            if (tid == a * G) {
                 int ex_acc = 0;
-                const int a = ex_n - 1, b = ex_n;
                 exc_cnt[2 * a] += 1; exc_cnt[2 * b] += 1;
                 const int ca = perm[a], cb = perm[b];
                 double ea = scal[4 * ca], eb = scal[4 * cb];
@@ -680,7 +696,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     }
                 }
             }
-            __syncthreads();
+            if (!pairwise) __syncthreads();
+            else if (mine && wa != wb) named_barrier(1 + wa, 64);
+            else __syncwarp();
         } else {
             __syncwarp(hmask);                                      // scal[] of this slot is visible to its group
         }
