@@ -2,7 +2,7 @@
 // ladder per CTA.  Instantiated per (lanes-per-replica G, potential, geometry, debug, unrolling) in sweep_inst.cu.
 //
 //   mc_step!  (src/MCRun.jl:169-182)  -> every group runs n_steps x mc_move! on its slot, no CTA sync
-//   exchange  (src/MCRun.jl:203-205, src/Exchange.jl:132-186) -> lane 0 of the lower slot between two barriers of the two warps involved
+//   exchange  (src/MCRun.jl:203-205, src/Exchange.jl:132-186) -> lane 0 of the lower slot between two mbarrier phases of the two warps involved
 //   update_max_stepsize! (src/Exchange.jl:198-263), sampling_step! (src/Sampling.jl:330-371) -> per group
 #pragma once
 #include "ptmc_device.cuh"
@@ -59,8 +59,19 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     return s;
 }
 
-__device__ __forceinline__ void named_barrier(int id, int n_threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+// Barrier of the two warps that hold the slots of one exchange attempt: an mbarrier in shared memory (64 arrivals), so no
+// hardware named barrier is reserved (a data-dependent `bar.sync id` makes every CTA claim all 16 and caps residency at 4 CTAs / SM).
+__device__ __forceinline__ void pair_barrier_init(u64* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 64;" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void pair_barrier(u64* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
 }
 
 // Separated volume moves (src/MCMoves.jl:300-343), separate loops so that the uniform-move loops stay as they are.
@@ -207,6 +218,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
         wl[0] = P.ladder_rng[lad * 4]; wl[1] = P.ladder_rng[lad * 4 + 1];
         wl[2] = P.ladder_rng[lad * 4 + 2]; wl[3] = P.ladder_rng[lad * 4 + 3];
         wl[4] = (DBG && P.replay) ? (u64)P.ladder_cursor[lad] : 0;
+        pair_barrier_init(wl + 5);        // exchange meeting point of this warp and the next one
     }
     // cycle phases instead of 64-bit modulo in the loop
     int adj_phase = (int)(first_idx % P.n_adjust);
@@ -215,6 +227,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
 
     const bool tracing = DBG && P.trace_cap > 0;
     int err = 0;
+    unsigned xpar = 0;      // phase parities of the two exchange mbarriers this warp takes part in (bit 0: with the next warp, bit 1: with the previous one)
 
     // P.phase splits mc_cycle! at the exchange (a ladder that spans GPUs exchanges on the host, ptmc_run_phase)
     const int phase = P.phase;
@@ -661,16 +674,14 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
             ex_n = __shfl_sync(0xffffffffu, ex_n, 0);
             ex_u = __shfl_sync(0xffffffffu, ex_u, 0);
             // Only the two slots of the attempt have to meet: every warp steps its own copy of the ladder stream, so the other
-            // warps run on (replicas differ a lot in work per cycle: volume moves, out-of-sphere redraws).  The two warps meet on
-            // named barrier 1 + (lower warp) - ids 1..15, hence CTAs of up to 16 warps; larger ones use the CTA barrier.
+            // warps run on (replicas differ a lot in work per cycle: volume moves, out-of-sphere redraws).  Slots in two warps
+            // meet on the mbarrier of the lower warp; its phase parity is tracked per side in xpar.
             const int a = ex_n - 1, b = ex_n;
             const int wa = (a * G) >> 5, wb = (b * G) >> 5, wme = tid >> 5;
-            // (not for 4 lanes per replica: a data-dependent barrier id makes the CTA reserve all 16 hardware barriers, which
-            //  caps the number of resident CTAs of the small Ne13-class kernels - measured -16 % there, profiles/r01_experiments.md)
-            const bool pairwise = G >= 8 && blockDim.x <= 512;
-            const bool mine = !pairwise || wme == wa || wme == wb;
-            if (!pairwise) __syncthreads();                         // every slot has finished this cycle's moves
-            else if (mine && wa != wb) named_barrier(1 + wa, 64);
+            const bool meet = wa != wb && (wme == wa || wme == wb);
+            u64* xbar = lrng + 6 * wa + 5;
+            const int side = wme == wa ? 0 : 1;
+            if (meet) { pair_barrier(xbar, (xpar >> side) & 1u); xpar ^= 1u << side; }   // both slots have finished this cycle's moves
             else __syncwarp();
             if (tid == a * G) {
                 int ex_acc = 0;
@@ -696,8 +707,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     }
                 }
             }
-            if (!pairwise) __syncthreads();
-            else if (mine && wa != wb) named_barrier(1 + wa, 64);
+            if (meet) { pair_barrier(xbar, (xpar >> side) & 1u); xpar ^= 1u << side; }
             else __syncwarp();
         } else {
             __syncwarp(hmask);                                      // scal[] of this slot is visible to its group

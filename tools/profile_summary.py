@@ -17,6 +17,8 @@ KEYS = [
     ("launch__grid_size", "grid size"),
     ("launch__occupancy_limit_registers", "occupancy limit: registers (CTAs/SM)"),
     ("launch__occupancy_limit_shared_mem", "occupancy limit: shared memory (CTAs/SM)"),
+    ("launch__occupancy_limit_barriers", "occupancy limit: hardware barriers (CTAs/SM)"),
+    ("launch__occupancy_limit_warps", "occupancy limit: warps (CTAs/SM)"),
     ("launch__waves_per_multiprocessor", "waves per SM"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy (% of 64 warps)"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy"),
