@@ -266,8 +266,9 @@ __device__ __forceinline__ void elj_even_pair_acc(const DevParams& P, double d2n
 }
 
 // dimer_energy(::ELJPotentialB) src/EnergyEvaluation.jl:943-958: sum_i c_i r^-k_i (1 + a_i t2 + b_i t4), k = 6, 8, 9, 10, ...;
-// t2 = cos 2theta = 2 / (tan^2 + 1) - 1 = 2 dz^2 / r^2 - 1 (no tangent matrix is stored: the angle comes from the positions
-// like the distance), t4 = 2 t2^2 - 1; below r2 = 5.30 the reference returns 0.1.
+// t2 = cos 2theta = 2 / (tan^2 + 1) - 1 = 2 dz^2 / r^2 - 1 (the angle comes from the positions like the distance; a tangent
+// matrix is stored only where the reference's becomes state of its own: periodic cells with separated volume moves,
+// eljb_energy_tan), t4 = 2 t2^2 - 1; below r2 = 5.30 the reference returns 0.1.
 template <int NC = 0>
 __device__ __forceinline__ double eljb_energy_t2(const DevParams& P, double r2, double y, double t2);
 template <int NC = 0>
