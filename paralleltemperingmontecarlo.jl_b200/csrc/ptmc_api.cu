@@ -22,6 +22,7 @@ int sweep_max_threads(int G);
 void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
 void launch_rdf(const DevParams& P, u64* rdf, double delta_r2, int n_rdf_bins, i64 n_rep, cudaStream_t st);
+void launch_lut_thresholds(const DevParams& P, double* thr, cudaStream_t st);
 double measure_fp64_peak(cudaStream_t st, int iters);
 int run_issue_probe(double sm_mhz, double out_cycles[4]);
 int run_pair_probe(const DevParams& P, int n, const double* h_d2n, const double* h_d2o, double* h_en, double* h_eo);
@@ -405,6 +406,11 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             return bail(fail(h, PTMC_ERR_CUDA, "copying the lookup table failed"));
         P.lut_table = d_lut; P.lut_l_dist = c->lut_l_dist;
         P.lut_start = c->lut_start_dist; P.lut_d = c->lut_d_dist; P.lut_dang = c->lut_d_angle; P.lut_c6 = c->lut_c6coeff;
+        double* d_thr = nullptr;
+        if ((rc = dev_alloc(h, &d_thr, PTMC_LUT_THR + 1))) return bail(rc);
+        launch_lut_thresholds(P, d_thr, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, PTMC_ERR_CUDA, "building the angle-index steps of the lookup table failed"));
+        P.lut_thr = d_thr; P.lut_kf = (float)(180.0 / 3.14159265358979323846 / c->lut_d_angle);
     }
     P.betas = d_betas; P.en_min = en_min; P.en_max = en_max; P.v_min = v_min; P.v_max = v_max;
     P.error = h->d_error;

@@ -44,6 +44,8 @@ struct DevParams {
     const double* lut_table;
     int lut_l_dist;
     double lut_start, lut_d, lut_dang, lut_c6;
+    float lut_kf;             // (float)(180 / pi / d_angle)
+    const double* lut_thr;    // [PTMC_LUT_THR] ascending tangents at which the angle index steps up (NaN padded), lut_thresholds_kernel
     double eam_hn, eam_hm;               // n/2, m/2  (r^-n = (r2)^-(n/2))
     double eam_ean, eam_ecam;
     // table-driven (r2)^-p, p = n/2 and m/2 (eam_invrexp): binomial coefficients binom(-p, 1..6) and the tables
@@ -302,14 +304,39 @@ __device__ __forceinline__ double lut_energy_tan(const DevParams& P, double r2, 
 __device__ __forceinline__ double lut_energy(const DevParams& P, double r2, double dx, double dy, double dz) {
     return lut_energy_tan(P, r2, tan_of(dx, dy, dz));
 }
-__device__ __forceinline__ double lut_energy_tan(const DevParams& P, double r2, double t) {
+// angle index as the reference writes it (src/EnergyEvaluation.jl:273-283): round(atan(|tan|) / d_angle * 180 / pi + 1) inside
+// (0.00872687153, 114.592845357], 1 below, 91 above
+__device__ __forceinline__ int lut_angle_index_direct(const DevParams& P, double t) {
     int ai = 1;
     if (t > 0.00872687153 && t <= 114.592845357) ai = (int)rint(xadd(xdiv(xmul(xdiv(atan(t), P.lut_dang), 180.0), 3.14159265358979323846), 1.0));
     else if (t > 114.592845357) ai = 91;
+    return ai;
+}
+// The index is a non-decreasing step function of the tangent, so the sweep kernels count the steps at or below t instead of
+// evaluating an FP64 atan and two divisions per pair: thr[k] = smallest double with index >= k + 2, found by bisection over the
+// bit patterns with lut_angle_index_direct itself (lut_thresholds_kernel) -> the same index for every t.  A single-precision
+// atan gives the count to +-1; four independent loads around it fix and verify it (a window that does not bracket t - only
+// possible for d_angle != 1, where the index jumps to 91 - falls back to the direct formula).
+#define PTMC_LUT_THR 127
+__device__ __forceinline__ int lut_angle_index(const DevParams& P, double t) {
+    const float xf = atanf((float)t) * P.lut_kf;                              // ~ atan(t) / d_angle * 180 / pi
+    int lo = (int)rintf(xf) - 1;
+    lo = lo < 1 ? 1 : (lo > 90 ? 90 : lo);                                    // window thr[lo-1 .. lo+2]
+    const double* w = P.lut_thr + lo - 1;
+    const double t0 = __ldg(w), t1 = __ldg(w + 1), t2 = __ldg(w + 2), t3 = __ldg(w + 3);
+    int n = lo + (t >= t1 ? 1 : 0) + (t >= t2 ? 1 : 0);
+    if (!(t >= t0)) n = (lo == 1) ? 0 : -1;                                   // below the window: fine only if the window starts at 0
+    if (t >= t3) n = -1;                                                      // above the window
+    if (n < 0) return lut_angle_index_direct(P, t);
+    return 1 + n;
+}
+__device__ __forceinline__ double lut_energy_tan(const DevParams& P, double r2, double t) {
+    const int ai = lut_angle_index(P, t);
     const double lo = xadd(P.lut_start, xmul(0.5, P.lut_d)), hi = xadd(P.lut_start, xmul((double)P.lut_l_dist, P.lut_d));
     const double* row = P.lut_table + (size_t)(ai - 1) * P.lut_l_dist;
     if (r2 <= xmul(lo, lo)) return __ldg(row);
     if (r2 <= xmul(hi, hi)) {
+        // (the same step-counting for this index was slower: its loads sit in front of the dependent table gather, -17 %)
         int di = (int)rint(xdiv(xsub(sqrt(r2), P.lut_start), P.lut_d));
         di = di < 1 ? 1 : di;              // (the reference indexes table[.., 0] -> BoundsError if the quotient rounds to 0)
         return __ldg(row + di - 1);

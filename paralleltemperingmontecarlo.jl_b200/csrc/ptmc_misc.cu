@@ -53,6 +53,25 @@ void launch_rdf(const DevParams& P, u64* rdf, double delta_r2, int n_rdf_bins, i
     rdf_kernel<<<(unsigned)n_rep, 256, (size_t)n_rdf_bins * sizeof(unsigned int), st>>>(P, rdf, delta_r2, n_rdf_bins);
 }
 
+// Steps of the lookup table's angle index (ptmc_device.cuh: lut_angle_index): thread k bisects for the smallest tangent
+// whose index is >= k + 2 (positive doubles order like their bit patterns; index(0) = 1, index(inf) = 91).
+__global__ void lut_thresholds_kernel(const DevParams P, double* thr) {
+    const int k = threadIdx.x;
+    if (k >= PTMC_LUT_THR) return;
+    const int target = k + 2;
+    double out = __longlong_as_double(0x7ff8000000000000ll);          // NaN: never reached
+    if (target <= 91) {
+        unsigned long long lo = 0ull, hi = 0x7ff0000000000000ull;      // index(lo) < target <= index(hi)
+        while (hi - lo > 1) {
+            const unsigned long long mid = lo + (hi - lo) / 2;
+            if (lut_angle_index_direct(P, __longlong_as_double((long long)mid)) >= target) hi = mid; else lo = mid;
+        }
+        out = __longlong_as_double((long long)hi);
+    }
+    thr[k] = out;
+}
+void launch_lut_thresholds(const DevParams& P, double* thr, cudaStream_t st) { lut_thresholds_kernel<<<1, 128, 0, st>>>(P, thr); }
+
 // Accuracy probe of the production pair arithmetic: e_new[k], e_old[k] exactly as the sweep kernel accumulates
 // them for the pair (d2_new[k], d2_old[k]).
 __global__ void pair_probe_kernel(const DevParams P, int n, const double* d2n, const double* d2o, double* en, double* eo) {
