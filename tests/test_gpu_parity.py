@@ -123,6 +123,24 @@ def test_pbc216_npt_replay_through_thaw():
     assert min(moved_atoms) > 200, moved_atoms          # (exchanges permute configurations; every slot saw nearly all atoms move)
 
 
+def test_pbc216_separated_moves_tangent_potential_replay():
+    # (f-3) at C4's size: pbc216 in Angstrom with ELJPotentialB and NPT(separated_volume = true) - the 216 x 216 tangent matrix of
+    # every configuration is state in HBM, rewritten by every xy / z trial; replayed streams against the oracle.
+    # (lattice perturbed by 1e-3: half-cell ties under a separated scaling are a documented waiver)
+    a2b = 1.8897261259077824
+    mcp, temp, start, _, ens = P.host.deck_pbc216(n_traj=4, cycles=12)
+    bc = start[0].boundary_condition
+    rng = np.random.default_rng(5)
+    start = [P.Config(c.positions / a2b + rng.uniform(-1e-3, 1e-3, c.positions.shape), P.RhombicBC(bc.box_length / a2b, bc.box_height / a2b))
+             for c in start]
+    pot = P.ELJPotentialB(P.host.ELJB_NE_A, P.host.ELJB_NE_B, P.host.ELJB_NE_C)
+    ens = P.NPT(216, ens.pressure * a2b ** 3, True, n_volume_moves=6)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=12, seed=14)
+    compare_traces(gpu, cpu, positions_exact=False)
+    cnt = gpu["states"]["counters"]
+    assert cnt[:, :, abi.C_VOLXY_TOT].sum() > 0 and cnt[:, :, abi.C_VOLZ_TOT].sum() > 0 and cnt[:, :, abi.C_VOL_TOT].sum() > 0
+
+
 def test_periodic_nvt_replay():
     start = _small_pbc(P.CubicBC)
     mcp = P.MCParams(20, 4, 32)

@@ -24,6 +24,20 @@ import os  # noqa: E402
 
 LUT_FILE = os.environ.get("PTMC_LUT_FILE", str(ROOT / "paralleltemperingmontecarlo.jl_b200" / "data" / "_lut" / "LookupTable_Neon_B0.0_MP2.txt"))
 
+def _pbc216_variant(pot_name):
+    """pbc216 the way most scripts/pbc*.jl run it: NPT with separated xy / z volume moves (scripts/pbc216.jl:62-70 names the
+    lookup table; the table file is the Neon one of scripts/lookup-tables).  The tangent-dependent potentials work in Angstrom."""
+    mcp, temp, start, pot, ens = P.host.deck_pbc216(n_traj=16, cycles=100)
+    if pot_name == "elj":
+        return mcp, temp, start, pot, P.NPT(216, ens.pressure, True)
+    a2b = 1.8897261259077824
+    bc = start[0].boundary_condition
+    start = [P.Config(c.positions / a2b, P.RhombicBC(bc.box_length / a2b, bc.box_height / a2b)) for c in start]
+    pot = (P.ELJPotentialB(P.host.ELJB_NE_A, P.host.ELJB_NE_B, P.host.ELJB_NE_C) if pot_name == "eljb"
+           else P.LookupTablePotential(LUT_FILE))
+    return mcp, temp, start, pot, P.NPT(216, ens.pressure * a2b ** 3, True)
+
+
 CASES = {
     # name: (deck factory, ladders, warm-up cycles, timed cycles per step, steps, histogram window)
     "c1_ne13_elj_nvt_32T": (lambda: P.host.deck_ne13(n_traj=32, cycles=100), 8880, 200, 100, 5, (-0.01, 0.0, None, None)),
@@ -35,6 +49,10 @@ CASES = {
     "c3_cu55_eam_nvt_28T": (lambda: P.host.deck_cu55_eam(n_traj=28, cycles=100), 2048, 100, 20, 5, (-8.0, -5.0, None, None)),
     "c4_pbc216_elj_npt_16T": (lambda: P.host.deck_pbc216(n_traj=16, cycles=100), 592, 20, 40, 3, None),
     "c5_cu55_runner_nvt_28T": (lambda: P.host.deck_cu55_runner(n_traj=28, cycles=100), 37, 4, 4, 3, (-13.0, -11.0, None, None)),
+    # (f-3) rows at C4's size: separated volume moves, tangent matrix as state (not BASELINE configs; run with --only c4)
+    "c4b_pbc216_elj_npt_separated_16T": (lambda: _pbc216_variant("elj"), 592, 20, 40, 3, None),
+    "c4c_pbc216_eljb_npt_separated_16T": (lambda: _pbc216_variant("eljb"), 592, 20, 40, 3, None),
+    "c4d_pbc216_lookup_npt_separated_16T": (lambda: _pbc216_variant("lookup"), 592, 20, 40, 3, None),
 }
 
 
@@ -76,6 +94,7 @@ def run(name):
 CPU_SAMPLE = {   # ladders, cycles for the CPU-oracle sample of each config (a few seconds on 16 cores)
     "c1_ne13_elj_nvt_32T": (64, 400), "c1b_ne13_eljb_nvt_16T": (64, 200), "c1c_ne13_lookup_nvt_25T": (64, 200), "c2_ne55_elj_nvt_24T": (64, 100), "c3_cu55_eam_nvt_28T": (32, 40),
     "c4_pbc216_elj_npt_16T": (16, 20), "c5_cu55_runner_nvt_28T": (1, 1),
+    "c4b_pbc216_elj_npt_separated_16T": (16, 20), "c4c_pbc216_eljb_npt_separated_16T": (16, 10), "c4d_pbc216_lookup_npt_separated_16T": (16, 10),
 }
 
 
@@ -108,7 +127,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a bounded sample")
     a = ap.parse_args()
-    names = [n for n in CASES if not a.only or any(n.startswith(p) for p in a.only.split(","))]
+    names = [n for n in CASES if (any(n.startswith(p) for p in a.only.split(",")) if a.only else n[:3] not in ("c4b", "c4c", "c4d"))]
     for n in names:
         if "lookup" in n and not os.path.exists(LUT_FILE):
             print(json.dumps({"config": n, "skipped": "lookup table file not present (PTMC_LUT_FILE)"}), flush=True)
