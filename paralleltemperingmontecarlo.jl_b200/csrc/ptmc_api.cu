@@ -354,7 +354,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     if ((rc = dev_alloc(h, &P.pos, R * N * 3)) || (rc = dev_alloc(h, &P.box, R * 2)) || (rc = dev_alloc(h, &P.en_tot, R)) ||
         (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) ||
         (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) ||
-        (rc = dev_alloc(h, &P.tanmat, (!sphere && npt && c->separated_volume && (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT)) ? R * N * N : 1)) || (rc = dev_alloc(h, &P.perm_g, R)) ||
+        (rc = dev_alloc(h, &P.tan_rho, R)) || (rc = dev_alloc(h, &P.fresh_g, R * ((N + 31) / 32))) || (rc = dev_alloc(h, &P.perm_g, R)) ||
         (rc = dev_alloc(h, &P.moved_g, R * ((N + 31) / 32 + 1))) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
         (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.max_boxheight, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
         (rc = dev_alloc(h, &d_betas, (size_t)c->n_traj)) || (rc = dev_alloc(h, &P.slot_rng, R * 4 * PTMC_RNG_LANES)) || (rc = dev_alloc(h, &P.ladder_rng, L * 4)) ||

@@ -60,7 +60,8 @@ struct DevParams {
     // periodic boundaries: the reference's dist2_mat, kept in HBM per CONFIGURATION (not per slot) so that an
     // exchange never moves it; perm_g is the slot -> configuration map, persisted between launches
     double* d2mat;      // [L][T][N][N]
-    double* tanmat;     // [L][T][N][N]  tan_mat of the tangent-dependent potentials, kept only with separated volume moves
+    double* tan_rho;    // [L][T]  tangent-dependent potentials with separated volume moves: factor of the stale tangents (sweep_kernel.cuh)
+    int* fresh_g;       // [L][T][moved_words]  atoms moved since the last xy / z volume trial
     int* perm_g;        // [L][T]
     // per configuration: bit mask of the atoms moved (accepted) since the upload + their count.  Frozen dist2_mat
     // entries can only differ in a DECISION from recomputed distances for pairs of never-moved lattice atoms (exact
@@ -268,20 +269,15 @@ __device__ __forceinline__ void elj_even_pair_acc(const DevParams& P, double d2n
 }
 
 // dimer_energy(::ELJPotentialB) src/EnergyEvaluation.jl:943-958: sum_i c_i r^-k_i (1 + a_i t2 + b_i t4), k = 6, 8, 9, 10, ...;
-// t2 = cos 2theta = 2 / (tan^2 + 1) - 1 = 2 dz^2 / r^2 - 1 (the angle comes from the positions like the distance; a tangent
-// matrix is stored only where the reference's becomes state of its own: periodic cells with separated volume moves,
-// eljb_energy_tan), t4 = 2 t2^2 - 1; below r2 = 5.30 the reference returns 0.1.
+// t2 = cos 2theta = 2 / (tan^2 + 1) - 1 = 2 dz^2 / r^2 - 1 (the angle comes from the positions like the distance; no tangent
+// matrix is stored - where the reference's becomes state of its own, periodic cells with separated volume moves, it is carried
+// as one factor per configuration: pair_energy_stale), t4 = 2 t2^2 - 1; below r2 = 5.30 the reference returns 0.1.
 template <int NC = 0>
 __device__ __forceinline__ double eljb_energy_t2(const DevParams& P, double r2, double y, double t2);
 template <int NC = 0>
 __device__ __forceinline__ double eljb_energy(const DevParams& P, double r2, double dz2) {
     const double y = rsqrt_pos(r2);
     return eljb_energy_t2<NC>(P, r2, y, fma(2.0 * dz2, y * y, -1.0));
-}
-// the same from a stored tangent: t2 = 2 / (tan^2 + 1) - 1 as the reference writes it (:946); tan = Inf -> -1
-template <int NC = 0>
-__device__ __forceinline__ double eljb_energy_tan(const DevParams& P, double r2, double tan_) {
-    return eljb_energy_t2<NC>(P, r2, rsqrt_pos(r2), xsub(xdiv(2.0, xadd(xmul(tan_, tan_), 1.0)), 1.0));
 }
 template <int NC>
 __device__ __forceinline__ double eljb_energy_t2(const DevParams& P, double r2, double y, double t2) {
@@ -433,11 +429,17 @@ __device__ __forceinline__ double pair_energy_dir(const DevParams& P, double r2,
     if (POT == PTMC_POT_ELJ_B) return eljb_energy<NC>(P, r2, dz * dz * s2);
     return lut_energy(P, r2, dx, dy, dz);
 }
-// ... and from a stored tangent (separated volume moves keep the reference's tan_mat, stale entries included)
+// ... and with the tangent of the state instead of the pair's own: tan_mat[i, j] = rho * tan(i, j) for a stale pair (separated volume
+// moves, sweep_kernel.cuh: sep_trial_energy).  ELJPotentialB needs no tangent: t2 = 2 / (tan^2 + 1) - 1 = 2 dz^2 / (rho^2 (dx^2 + dy^2) + dz^2) - 1.
 template <int POT, int NC>
-__device__ __forceinline__ double pair_energy_tan(const DevParams& P, double r2, double tan_) {
-    if (POT == PTMC_POT_ELJ_B) return eljb_energy_tan<NC>(P, r2, tan_);
-    return lut_energy_tan(P, r2, tan_);
+__device__ __forceinline__ double pair_energy_stale(const DevParams& P, double r2, double dx, double dy, double dz, double rho, bool stale) {
+    if (POT == PTMC_POT_ELJ_B) {
+        const double q = dz * dz, s = fma(dx, dx, dy * dy);
+        const double den = fma(stale ? rho * rho : 1.0, s, q);
+        return eljb_energy_t2<NC>(P, r2, rsqrt_pos(r2), fma(2.0 * q, rcp_pos3(den), -1.0));
+    }
+    const double t = tan_of(dx, dy, dz);
+    return lut_energy_tan(P, r2, stale ? xmul(t, rho) : t);
 }
 
 // ----------------------------------------------------------------------------------------- geometry --

@@ -105,6 +105,18 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, 
         }
     }
 #endif
+    // periodic ELJPotentialB, six coefficients (the scripts/pbc*.jl family at one warp per replica): the same unrolling
+#if PTMC_G == 32
+    if (!dbg && pot == PTMC_POT_ELJ_B && n_coeff == 6 && (geom == GEOM_PBC || geom == GEOM_RHOMB)) {
+        switch (niter) {
+#define PTMC_SPBB(K) case K: return geom == GEOM_PBC ? (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_B, GEOM_PBC, false, K, 6> \
+                                                     : (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_B, GEOM_RHOMB, false, K, 6>;
+            PTMC_SPBB(1) PTMC_SPBB(2) PTMC_SPBB(3) PTMC_SPBB(4) PTMC_SPBB(5) PTMC_SPBB(6) PTMC_SPBB(7) PTMC_SPBB(8)
+#undef PTMC_SPBB
+            default: break;
+        }
+    }
+#endif
     if (!dbg && pot == PTMC_POT_ELJ_EVEN && n_coeff == 6) {
         if (geom == GEOM_PBC) return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_PBC, false, 0, 6>;
         if (geom == GEOM_RHOMB) return (sweep_fn)sweep_kernel<G, PTMC_POT_ELJ_EVEN, GEOM_RHOMB, false, 0, 6>;

@@ -31,6 +31,7 @@ struct SmemLayout {
     int off_lrng;       // ladder stream, one private copy per warp: 4 x u64 state + cursor + pad
     int off_moved;      // periodic: int moved[T][words + 1]
     int off_sep;        // periodic: per slot {max_displ[2], max_displ[3], max_boxheight, int n_acc_xy, n_adj_xy, n_acc_z, n_adj_z} (6 doubles)
+    int off_tan;        // periodic tangent-dependent potentials: double tan_rho[T], int fresh[T][words] (stale-tangent state, see sep_trial_energy)
     int off_tab;        // EAM: the mantissa table of eam_invrexp (PTMC_EAM_KTAB_DOUBLES, 16-byte aligned)
     size_t bytes;
 };
@@ -43,7 +44,7 @@ __host__ __device__ constexpr bool eam_unrolled(int niter, bool dbg) { return PT
 __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch) {
     SmemLayout s;
     const bool dirp = pot_kind == PTMC_POT_ELJ_B || pot_kind == PTMC_POT_LUT;
-    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + (pbc ? 1 : 0) + (pbc && dirp ? 1 : 0);   // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec [+ new_tan_vec])
+    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + (pbc ? 1 : 0);   // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec)
     s.cfg_stride = arrays * n_pad;
     s.off_scal = n_traj * s.cfg_stride;
     int off = s.off_scal + 4 * n_traj;
@@ -53,6 +54,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     s.off_perm = off; off += (n_traj + 1) / 2 + 1;
     s.off_moved = off; off += pbc ? (n_traj * ((n_pad + 31) / 32 + 1) + 1) / 2 + 1 : 0;
     s.off_sep = off; off += pbc ? 6 * n_traj : 0;
+    s.off_tan = off; off += (pbc && dirp) ? n_traj + (n_traj * ((n_pad + 31) / 32) + 1) / 2 : 0;
     off += off & 1;
     s.off_tab = off; off += pot_kind == PTMC_POT_EAM ? PTMC_EAM_KTAB_DOUBLES : 0;
     s.bytes = (size_t)off * sizeof(double);
@@ -78,27 +80,33 @@ __device__ __forceinline__ void pair_barrier(u64* bar, unsigned parity) {
 // Pair energy of the trial configuration (positions scaled by scale_xy / scale_z, box tL x tH) below the new cut-off:
 // get_distance2_mat!(new_dist2_mat, trial_config) + dimer_energy_config; exact distance2 arithmetic while the configuration
 // still holds never-moved lattice atoms, the reciprocal-multiply minimum image afterwards.  Returns this lane's partial sum.
+//
+// Tangent-dependent potentials: the reference keeps tan_mat, and its new_tan_mat is the SAME array (set_variables
+// src/EnergyEvaluation.jl:1790,1798), so an xy / z trial leaves the TRIAL configuration's tangents in the state whether or not it is
+// accepted (src/MCMoves.jl:333-341); later atom moves refresh row and column of the moved atom, the uniform trial reads the matrix.
+// A trial tangent is rho = scale_xy / scale_z times the true one, so the whole matrix is carried as one factor per configuration
+// plus one bit per atom ("moved since the last xy / z trial"): tan_mat[i, j] = tan(i, j) * (fresh_i | fresh_j ? 1 : rho), equal to
+// the stored value up to rounding.  No N x N matrix in HBM, no scattered column writes (profiles/r01_experiments.md).
+__device__ __forceinline__ bool tan_fresh(const int* fr, int j) { return (fr[j >> 5] >> (j & 31)) & 1; }
 template <int G, int POT, int NC, bool RHOMBIC>
 __device__ __forceinline__ double sep_trial_energy(const DevParams& P, const double* X, const double* Y, const double* Z, int N, int g,
                                                   double scale_xy, double scale_z, double tL, double tH, double new_rcut, bool thawed,
-                                                  double* T = nullptr, bool write_tan = false) {
+                                                  const int* fr = nullptr, double rho = 1.0, bool trial_tan = false) {
     constexpr bool DIRP = POT == PTMC_POT_ELJ_B || POT == PTMC_POT_LUT;
     const Box tbx = make_box(P.bc_kind, tL, tH);
     double acce = 0.0;
     for (int a = 0; a < N - 1; ++a) {
         const double pax = xmul(X[a], scale_xy), pay = xmul(Y[a], scale_xy), paz = xmul(Z[a], scale_z);
+        const bool fa = DIRP && !trial_tan && tan_fresh(fr, a);
         for (int j = a + 1 + g; j < N; j += G) {
             const double pbx = xmul(X[j], scale_xy), pby = xmul(Y[j], scale_xy), pbz = xmul(Z[j], scale_z);
             double v0 = 0, v1 = 0, v2 = 0;
             double d2 = (DIRP || thawed) ? dist2_pbc_vec<RHOMBIC>(tbx, pax, pay, paz, pbx, pby, pbz, v0, v1, v2) : 0.0;
             if (!thawed) d2 = dist2_exact(P.bc_kind, pax, pay, paz, pbx, pby, pbz, tL, tH);
             if (DIRP) {
-                // tangent-dependent potentials: xy / z trials write the trial configuration's tangents into tan_mat (kept even if
-                // the move is rejected: the reference's new_tan_mat is the same array, src/MCMoves.jl:333-341); the uniform trial reads it
-                double tn;
-                if (write_tan) { tn = tan_of(v0, v1, v2); __stcg(T + (size_t)a * N + j, tn); __stcg(T + (size_t)j * N + a, tn); }
-                else tn = __ldcg(T + (size_t)a * N + j);
-                if (d2 <= new_rcut) acce += pair_energy_tan<POT, NC>(P, d2, tn);
+                // xy / z trial: get_tantheta_mat!(new_tan_mat, trial_config); uniform trial: the state's tangents
+                const bool stale = !trial_tan && !(fa || tan_fresh(fr, j));
+                if (d2 <= new_rcut) acce += pair_energy_stale<POT, NC>(P, d2, v0, v1, v2, rho, stale);
             } else {
                 if (d2 <= new_rcut) acce += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
             }
@@ -149,6 +157,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     u64* lrng = reinterpret_cast<u64*>(sm + lay.off_lrng);
     int* perm = reinterpret_cast<int*>(sm + lay.off_perm);
     int* moved = reinterpret_cast<int*>(sm + lay.off_moved);
+    double* trho = sm + lay.off_tan;                       // stale-tangent factor per configuration
+    int* fresh = reinterpret_cast<int*>(trho + T);          // atoms moved since the last xy / z trial, [T][FW]
+    const int FW = (NP + 31) / 32;
     const int MW = P.moved_words + 1;            // ints per configuration in moved[]
     const bool npt = PBC && P.ensemble == PTMC_ENS_NPT;
     const i64 rep = (i64)lad * T + slot;      // replica (slot) index in the global arrays
@@ -178,6 +189,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
             scal[4 * c0 + 3] = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
             perm[slot] = c0;
             if (PBC) for (int w = 0; w < MW; ++w) moved[c0 * MW + w] = P.moved_g[((i64)lad * T + c0) * MW + w];
+            if (PBC && DIRP) {
+                const bool st = P.separated != 0;
+                trho[c0] = st ? P.tan_rho[(i64)lad * T + c0] : 1.0;
+                for (int w = 0; w < FW; ++w) fresh[c0 * FW + w] = (st && w < P.moved_words) ? P.fresh_g[((i64)lad * T + c0) * P.moved_words + w] : 0;
+            }
             exc_cnt[2 * slot] = 0; exc_cnt[2 * slot + 1] = 0;
             hams[2 * slot] = P.ham[rep * 2]; hams[2 * slot + 1] = P.ham[rep * 2 + 1];
         }
@@ -339,10 +355,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             const bool thawed = moved[c * MW + MW - 1] >= N;
                             const double* Drow = P.d2mat + (((size_t)lad * T + c) * N + i) * N;
                             double* NEW = Z + NP;
-                            // tangent-dependent potentials with separated volume moves: tan_mat is state (stale entries included)
+                            // tangent-dependent potentials with separated volume moves: stale tangents of the old row (sep_trial_energy)
                             const bool tanst = DIRP && P.separated != 0;
-                            const double* Trow = tanst ? P.tanmat + (((size_t)lad * T + c) * N + i) * N : nullptr;
-                            double* NEWT = Z + 2 * NP;
+                            const double rho_c = tanst ? trho[c] : 1.0;
+                            const int* fr = fresh + c * FW;
+                            const bool fresh_i = tanst && tan_fresh(fr, i);
                             if (thawed) {
                                 // thawed: both rows from the positions in shared memory, pair loop unrolled like the free-space one
                                 const double* Xg = X + g;
@@ -363,10 +380,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                         const double dn = valid ? d2n : 1.0, dold = valid ? d2o : 1.0;
                                         double en_j, eo_j;
                                         if (DIRP && tanst) {
-                                            const double tn = tan_of(vn0, vn1, vn2);
-                                            if (j < N) NEWT[j] = valid ? tn : 0.0;                      // new_tan_vec, [index] = 0
-                                            en_j = pair_energy_tan<POT, NC>(P, dn, tn);
-                                            eo_j = pair_energy_tan<POT, NC>(P, dold, (j < N) ? __ldcg(Trow + j) : 0.0);
+                                            en_j = pair_energy_dir<POT, NC>(P, dn, vn0, vn1, vn2);
+                                            eo_j = pair_energy_stale<POT, NC>(P, dold, vo0, vo1, vo2, rho_c, !(fresh_i || (j < N && tan_fresh(fr, j))));
                                         } else {
                                             en_j = DIRP ? pair_energy_dir<POT, NC>(P, dn, vn0, vn1, vn2) : pair_energy<POT, NC>(P, dn);
                                             eo_j = DIRP ? pair_energy_dir<POT, NC>(P, dold, vo0, vo1, vo2) : pair_energy<POT, NC>(P, dold);
@@ -400,10 +415,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     d2n = valid ? d2n : 1.0; d2o = valid ? d2o : 1.0;
                                     double en_j, eo_j;
                                     if (DIRP && tanst) {
-                                        const double tn = tan_of(vn0, vn1, vn2);
-                                        NEWT[j] = valid ? tn : 0.0;
-                                        en_j = pair_energy_tan<POT, NC>(P, d2n, tn);
-                                        eo_j = pair_energy_tan<POT, NC>(P, d2o, __ldcg(Trow + j));
+                                        en_j = pair_energy_dir<POT, NC>(P, d2n, vn0, vn1, vn2);
+                                        eo_j = pair_energy_stale<POT, NC>(P, d2o, vo0, vo1, vo2, rho_c, !(fresh_i || tan_fresh(fr, j)));
                                     } else {
                                         en_j = DIRP ? pair_energy_dir<POT, NC>(P, d2n, vn0, vn1, vn2) : pair_energy<POT, NC>(P, d2n);
                                         eo_j = DIRP ? pair_energy_dir<POT, NC>(P, d2o, vo0, vo1, vo2) : pair_energy<POT, NC>(P, d2o);
@@ -496,15 +509,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                         n_acc_atom += 1; n_adj_atom += 1;
                         if (PBC) {
                             if (DIRP && P.separated != 0) {
-                                // tan_mat[index, :] = tan_mat[:, index] = new_tan_vec  (swap_vars! src/swap_config.jl:197-206)
-                                double* Tm = P.tanmat + ((size_t)lad * T + c) * N * N;
-                                const double* NEWT = Z + 2 * NP;
+                                // tan_mat[index, :] = tan_mat[:, index] = new_tan_vec  (swap_vars! src/swap_config.jl:197-206): row and column are fresh
                                 __syncwarp(gmask);
-                                for (int j = g; j < N; j += G) {
-                                    const double v = NEWT[j];
-                                    __stcg(Tm + (size_t)i * N + j, v);
-                                    __stcg(Tm + (size_t)j * N + i, v);
-                                }
+                                if (g == 0) fresh[c * FW + (i >> 5)] |= 1 << (i & 31);
                             }
                             if (moved[c * MW + MW - 1] < N) {
                                 // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
@@ -600,7 +607,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                         }
                     } else {
                         acce = sep_trial_energy<G, POT, NC, rhombic>(P, X, Y, Z, N, g, scale_xy, scale_z, tL, tH, new_rcut, thawed,
-                                                                     DIRP ? P.tanmat + ((size_t)lad * T + c) * N * N : nullptr, xyz >= 1);
+                                                                     fresh + c * FW, DIRP ? trho[c] : 1.0, xyz >= 1);
                     }
                     double e_new = group_sum<G>(acce, gmask);
                     const double l = lrc_pot<POT>(P, new_rcut);
@@ -615,6 +622,15 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     p = p > 1.0 ? 1.0 : p;
                     const double u = BATCH ? B.template rand<4>(gmask) : S.rand();
                     acc = p >= u;
+                    if (DIRP && sepv && xyz >= 1) {
+                        // the trial's tangents are the state now, for every pair: rejected -> rho times the true ones, accepted -> the true ones
+                        __syncwarp(gmask);
+                        if (g == 0) {
+                            trho[c] = acc ? 1.0 : xdiv(scale_xy, scale_z);
+                            for (int w = 0; w < FW; ++w) fresh[c * FW + w] = 0;
+                        }
+                        __syncwarp(gmask);
+                    }
                     if (acc) {
                         // swap_config_v! src/swap_config.jl:113-140
                         __syncwarp(gmask);
@@ -807,6 +823,10 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
             if (PBC) {
                 P.perm_g[rep] = c;
                 for (int w = 0; w < MW; ++w) P.moved_g[((i64)lad * T + c) * MW + w] = moved[c * MW + w];
+                if (DIRP && P.separated) {
+                    P.tan_rho[(i64)lad * T + c] = trho[c];
+                    for (int w = 0; w < P.moved_words; ++w) P.fresh_g[((i64)lad * T + c) * P.moved_words + w] = fresh[c * FW + w];
+                }
                 P.box[rep * 2] = scal[4 * c + 1]; P.box[rep * 2 + 1] = scal[4 * c + 2];
                 P.max_displ[rep * 4 + 1] = vmax;
                 cn[PTMC_C_VOL_TOT] += n_acc_vol; cn[PTMC_C_VOL_ADJ] = n_adj_vol;
@@ -895,12 +915,7 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                         double v0, v1, v2;
                         if (P.bc_kind == PTMC_BC_RHOMBIC) (void)dist2_pbc_vec<true>(b, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], v0, v1, v2);
                         else (void)dist2_pbc_vec<false>(b, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], v0, v1, v2);
-                        if (P.separated) {      // set_variables: tan_mat = get_tantheta_mat(config)
-                            const double tn = tan_of(v0, v1, v2);
-                            double* Tm = P.tanmat + (size_t)rep * N * N;
-                            Tm[(size_t)a * N + j] = tn; Tm[(size_t)j * N + a] = tn;
-                            if (!npt || d2 <= rcut) acc += pair_energy_tan<POT, 0>(P, d2, tn);
-                        } else if (!npt || d2 <= rcut) acc += pair_energy_dir<POT, 0>(P, d2, v0, v1, v2);
+                        if (!npt || d2 <= rcut) acc += pair_energy_dir<POT, 0>(P, d2, v0, v1, v2);
                         continue;
                     }
                 } else {
@@ -921,6 +936,10 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
             else e = (L < h) ? e + l * L / h : e + l * (h * h) / (L * L);
         }
         if (g == 0) P.en_tot[rep] = e;
+        if (g == 0 && pbc && (POT == PTMC_POT_ELJ_B || POT == PTMC_POT_LUT) && P.separated) {
+            P.tan_rho[rep] = 1.0;                     // tan_mat = get_tantheta_mat(config): nothing stale
+            for (int w = 0; w < P.moved_words; ++w) P.fresh_g[rep * P.moved_words + w] = 0;
+        }
     }
 }
 

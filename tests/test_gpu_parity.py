@@ -124,8 +124,9 @@ def test_pbc216_npt_replay_through_thaw():
 
 
 def test_pbc216_separated_moves_tangent_potential_replay():
-    # (f-3) at C4's size: pbc216 in Angstrom with ELJPotentialB and NPT(separated_volume = true) - the 216 x 216 tangent matrix of
-    # every configuration is state in HBM, rewritten by every xy / z trial; replayed streams against the oracle.
+    # (f-3) at C4's size: pbc216 in Angstrom with ELJPotentialB and NPT(separated_volume = true) - the reference's tangent matrix is
+    # state (stale after rejected xy / z trials); the kernels carry it as one factor per configuration + one bit per atom,
+    # the oracle literally as the 216 x 216 matrix; replayed streams.
     # (lattice perturbed by 1e-3: half-cell ties under a separated scaling are a documented waiver)
     a2b = 1.8897261259077824
     mcp, temp, start, _, ens = P.host.deck_pbc216(n_traj=4, cycles=12)
