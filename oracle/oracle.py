@@ -67,6 +67,8 @@ def load():
         "orc_runner_forward_raw": (None, [_dp, C.c_int, _ip, _ip, _dp, C.c_int, _dp]),
         "orc_runner2_energy": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
                                             C.c_int, _ip, _ip, _dp, _dp, _dp]),
+        "orc_runner2_move_delta": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
+                                            C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp]),
         "orc_julia_seed": (None, [C.c_uint64, _u64p]),
         "orc_xoshiro_next": (C.c_uint64, [_u64p]),
         "orc_rand_from_state": (C.c_double, [_u64p]),
@@ -211,6 +213,24 @@ def runner2_energy(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cut, g
     e = load().orc_runner2_energy(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
                                   nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, C.cast(C.byref(f12), _dp))
     return e, f12.value
+
+
+def runner2_move_delta(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, nodes, act, params1, params2, atom, trial):
+    """2-species energy change of one atom move through calc_delta_matrix (KAT checker, test/test_states.jl:148-159); atom 0-based"""
+    p, pp = _arr(pos)
+    re_, pre = _arr(rad_eta)
+    ae, pae = _arr(ang_eta)
+    al, pal = _arr(ang_lambda)
+    az, paz = _arr(ang_zeta)
+    ga, pga = _arr(gmaxmin_a)
+    gb, pgb = _arr(gmaxmin_b)
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    ac = np.ascontiguousarray(act, dtype=np.int32)
+    p1, pp1 = _arr(params1)
+    p2, pp2 = _arr(params2)
+    tr, ptr = _arr(trial)
+    return load().orc_runner2_move_delta(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
+                                         nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, int(atom), ptr)
 
 
 class OracleEngine(Engine):

@@ -233,20 +233,16 @@ void orc_runner_delta(const orc_runner* r, const double* pos, const double* newp
  * n1 atoms of type 1 then n2 of type 2; n_rad radial functions -> 2 rows each, n_ang angular -> 3 rows each
  * (SymmFunc.jl:320-470, 511-545); scaling rows: type-1 network rows then type-2 (scaling.data 1..88, 89..176).
  * gmaxmin_a/b: [n_rows][2] {G_max, G_min} for the two element networks. */
-double orc_runner2_energy(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
-                          const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
-                          int n_layers, const int* nodes, const int* act, const double* params1, const double* params2, double* f12_out) {
+static void runner2_gmatrix(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
+                            const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
+                            double* d2, double* f, double* g /* [atom][row], zeroed */) {
     const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang;
-    double* d2 = (double*)xc((size_t)n * n, 8);
-    double* f = (double*)xc((size_t)n * n, 8);
-    double* g = (double*)xc((size_t)n * ns, 8);     /* [atom][row] */
     for (int a = 0; a < n; ++a)
         for (int b = 0; b < n; ++b) {
             double x = pos[3 * a] - pos[3 * b], y = pos[3 * a + 1] - pos[3 * b + 1], z = pos[3 * a + 2] - pos[3 * b + 2];
             d2[(size_t)a * n + b] = x * x + y * y + z * z;
             f[(size_t)a * n + b] = orc_cutoff(sqrt(d2[(size_t)a * n + b]), r_cut);
         }
-    if (f12_out) *f12_out = f[1];
 #define GM(tab, row) (1 / ((tab)[2 * (row)] - (tab)[2 * (row) + 1]))
 #define GO(tab, row) (-(tab)[2 * (row) + 1] * GM(tab, row))
 #define TYPE(a) ((a) < n1 ? 0 : 1)
@@ -289,11 +285,100 @@ double orc_runner2_energy(const double* pos, int n1, int n2, int n_rad, const do
                 *gv = *gv * tpz + GO(tab, base + s);
             }
     }
+}
+static double runner2_total(const double* g, int n1, int n2, int ns, int n_layers, const int* nodes, const int* act,
+                            const double* params1, const double* params2) {
+    const int n = n1 + n2;
     double* e = (double*)xc(n, 8);
     orc_runner_forward_raw(g, n_layers, nodes, act, params1, n1, e);
     if (n2) orc_runner_forward_raw(g + (size_t)n1 * ns, n_layers, nodes, act, params2, n2, e + n1);
     double tot = 0.0;
     for (int a = 0; a < n; ++a) tot += e[a];
-    free(d2); free(f); free(g); free(e);
+    free(e);
     return tot;
+}
+double orc_runner2_energy(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
+                          const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
+                          int n_layers, const int* nodes, const int* act, const double* params1, const double* params2, double* f12_out) {
+    const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang;
+    double* d2 = (double*)xc((size_t)n * n, 8);
+    double* f = (double*)xc((size_t)n * n, 8);
+    double* g = (double*)xc((size_t)n * ns, 8);
+    runner2_gmatrix(pos, n1, n2, n_rad, rad_eta, n_ang, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, d2, f, g);
+    if (f12_out) *f12_out = f[1];
+    const double tot = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
+    free(d2); free(f); free(g);
+    return tot;
+}
+
+/* ---- 2-species atom move (KAT checker only; test/test_states.jl:148-159): energy change of moving atom `atom` to `trial`,
+ * through calc_delta_matrix (MachineLearningPotential/DeltaMatrix.jl:69-316) as get_new_state_vars! /
+ * calc_new_runner_energy! use it (src/EnergyEvaluation.jl:1347-1418): new_g_matrix = g_matrix + delta, two forward passes. */
+double orc_runner2_move_delta(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
+                              const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
+                              int n_layers, const int* nodes, const int* act, const double* params1, const double* params2,
+                              int atom, const double* trial) {
+    const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang, i = atom;
+    double* d2 = (double*)xc((size_t)n * n, 8);
+    double* f = (double*)xc((size_t)n * n, 8);
+    double* g = (double*)xc((size_t)n * ns, 8);
+    double* dg = (double*)xc((size_t)n * ns, 8);
+    double* nd2 = (double*)xc(n, 8);
+    double* nf = (double*)xc(n, 8);
+    runner2_gmatrix(pos, n1, n2, n_rad, rad_eta, n_ang, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, d2, f, g);
+    const double e_old = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
+    for (int b = 0; b < n; ++b) {
+        double x = trial[0] - pos[3 * b], y = trial[1] - pos[3 * b + 1], z = trial[2] - pos[3 * b + 2];
+        nd2[b] = x * x + y * y + z * z;
+        nf[b] = orc_cutoff(sqrt(nd2[b]), r_cut);            /* new_f_vec = cutoff_function.(sqrt.(new_dist2_vec), r_cut) :1357-1359 */
+    }
+    nd2[i] = 0.0; nf[i] = 1.0;
+    const int ti = TYPE(i);
+    /* radial rows, calc_delta_symm_val! :69-122: the centre gains in the row of the neighbour's species, the neighbour in the row of
+     * the centre's species; new_radial_symm_val! :23-25 = exponential_part(new) - exponential_part(old) */
+    for (int k = 0; k < n_rad; ++k) {
+        const int base = 2 * k;
+        for (int b = 0; b < n; ++b) {                       /* Cu neighbours first, then Zn (loop order of the reference) */
+            if (b == i) continue;
+            const double gn = exp(-rad_eta[k] * nd2[b]) * nf[b] - exp(-rad_eta[k] * d2[(size_t)i * n + b]) * f[(size_t)i * n + b];
+            dg[(size_t)i * ns + base + TYPE(b)] += gn;
+            dg[(size_t)b * ns + base + ti] += gn;
+        }
+        for (int a = 0; a < n; ++a)
+            for (int s_ = 0; s_ < 2; ++s_) dg[(size_t)a * ns + base + s_] *= GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
+    }
+    /* angular rows, calc_delta_symm_val! :124-250: pairs (j, k) of the other atoms in the order CuCu, ZnZn, CuZn; centre i gains
+     * in row (#Zn among j, k), j in row (#Zn among i, k), k in row (#Zn among i, j); new_angular_symm_vals :31-62 */
+    for (int k = 0; k < n_ang; ++k) {
+        const int base = 2 * n_rad + 3 * k;
+        for (int cls = 0; cls < 3; ++cls) {
+            const int j0 = cls == 1 ? n1 : 0, j1 = cls == 1 ? n : n1;
+            for (int j = j0; j < j1; ++j) {
+                if (j == i) continue;
+                const int k0 = cls == 2 ? n1 : j + 1, k1 = cls == 0 ? n1 : n;
+                for (int c = k0; c < k1; ++c) {
+                    if (c == i) continue;
+                    double thn[3], tho[3];
+                    const double r2jk = d2[(size_t)j * n + c];
+                    all_angular_measure(trial, pos + 3 * j, pos + 3 * c, nd2[j], nd2[c], r2jk, thn);
+                    all_angular_measure(pos + 3 * i, pos + 3 * j, pos + 3 * c, d2[(size_t)i * n + j], d2[(size_t)i * n + c], r2jk, tho);
+                    const double en = exp_part6(ang_eta[k], nd2[j], nd2[c], r2jk, nf[j], nf[c], f[(size_t)j * n + c]);
+                    const double eo = exp_part6(ang_eta[k], d2[(size_t)i * n + j], d2[(size_t)i * n + c], r2jk, f[(size_t)i * n + j], f[(size_t)i * n + c], f[(size_t)j * n + c]);
+                    double gv[3];
+                    for (int m = 0; m < 3; ++m)
+                        gv[m] = theta_part(thn[m], ang_lambda[k], ang_zeta[k]) * en - theta_part(tho[m], ang_lambda[k], ang_zeta[k]) * eo;
+                    dg[(size_t)i * ns + base + TYPE(j) + TYPE(c)] += gv[0];
+                    dg[(size_t)j * ns + base + ti + TYPE(c)] += gv[1];
+                    dg[(size_t)c * ns + base + ti + TYPE(j)] += gv[2];
+                }
+            }
+        }
+        for (int a = 0; a < n; ++a)
+            for (int s_ = 0; s_ < 3; ++s_)
+                dg[(size_t)a * ns + base + s_] *= pow(2.0, 1 - ang_zeta[k]) * GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
+    }
+    for (size_t q = 0; q < (size_t)n * ns; ++q) g[q] += dg[q];          /* new_g_matrix = g_matrix .+ delta :1379-1380 */
+    const double e_new = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
+    free(d2); free(f); free(g); free(dg); free(nd2); free(nf);
+    return e_new - e_old;
 }

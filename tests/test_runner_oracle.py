@@ -56,6 +56,27 @@ def test_brass_six_atom_energy(oracle):
     assert e == pytest.approx(-0.26165289933547947, rel=1e-12)   # SURVEY A.3 (independent restatement + native forward)
 
 
+def test_brass_atom_move_delta_energy(oracle):
+    # test/test_states.jl:148-159 ("States NNVT"): Random.seed!(123); atom_displacement(config[1], max_displ[1] = 0.1, SphericalBC);
+    # get_energy!(state, runnerpotential, "atommove") through calc_delta_matrix (2 species) -> new_en - en_tot ≈ -7.5971516e-5
+    from ptmc_b200 import multi
+    pos = np.array([[2.36, 2.36, 0.0], [6.99, 2.33, 0.0], [2.33, 6.99, 0.0], [-2.36, 2.36, 0.0], [-6.99, 2.33, 0.0], [-2.33, 6.99, 0.0]])
+    g = P.host.load_scaling()
+    rad_eta = [0.001, 0.020, 0.035, 0.100, 0.400]
+    ang = np.array(P.host.CU_ANGULAR)
+    w_cu = P.host.load_weights()
+    w_zn = np.load(ROOT / "tests" / "golden" / "brass_nnp_inputs.npz")["weights_zn"]
+    st = [int(x) for x in multi.julia_seed_state(123)]
+    trial = pos[0] + (np.array([multi._jl_rand(st) for _ in range(3)]) - 0.5) * 0.1
+    de = oracle.runner2_move_delta(pos, 4, 2, rad_eta, ang[:, 0], ang[:, 1], ang[:, 2], 11.338, g[:88], g[88:176], NODES, ACT, w_cu, w_zn, 0, trial)
+    assert de == pytest.approx(-7.5971516e-5, rel=2e-8)        # Julia's ≈: rtol = sqrt(eps)
+    # the delta path against a fresh evaluation of the moved configuration
+    moved = pos.copy(); moved[0] = trial
+    e0, _ = oracle.runner2_energy(pos, 4, 2, rad_eta, ang[:, 0], ang[:, 1], ang[:, 2], 11.338, g[:88], g[88:176], NODES, ACT, w_cu, w_zn)
+    e1, _ = oracle.runner2_energy(moved, 4, 2, rad_eta, ang[:, 0], ang[:, 1], ang[:, 2], 11.338, g[:88], g[88:176], NODES, ACT, w_cu, w_zn)
+    assert de == pytest.approx(e1 - e0, rel=1e-9, abs=1e-15)
+
+
 def _cu55_engine(oracle, n_traj=3, seed=5, boundary=0.0):
     mcp, temp, start, pot, ens = P.host.deck_cu55_runner(n_traj=n_traj, cycles=2, boundary=boundary)
     cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=1, seed=seed, rng_mode=abi.RNG_XOSHIRO)
