@@ -77,6 +77,26 @@ def test_brass_atom_move_delta_energy(oracle):
     assert de == pytest.approx(e1 - e0, rel=1e-9, abs=1e-15)
 
 
+def test_brass_atom_swap_energy(oracle):
+    # test/test_states.jl:166-183: Random.seed!(123); swap_atoms -> rand(1:N1), rand(N1+1:N) = (3, 6) (the test's own dist2_mat / config
+    # assertions say so); get_energy!(state, runnerpotential, "atomswap") ≈ -0.0017084901948.  The swap exchanges the positions of one
+    # atom of each species; here through a fresh evaluation of the swapped configuration (calc_swap_matrix itself, DeltaMatrix.jl:319-632,
+    # is restated with the 2-species sweep, DESIGN.md §8 "Next")
+    from ptmc_b200 import multi
+    pos = np.array([[2.36, 2.36, 0.0], [6.99, 2.33, 0.0], [2.33, 6.99, 0.0], [-2.36, 2.36, 0.0], [-6.99, 2.33, 0.0], [-2.33, 6.99, 0.0]])
+    g = P.host.load_scaling()
+    ang = np.array(P.host.CU_ANGULAR)
+    w_zn = np.load(ROOT / "tests" / "golden" / "brass_nnp_inputs.npz")["weights_zn"]
+    args = (4, 2, [0.001, 0.020, 0.035, 0.100, 0.400], ang[:, 0], ang[:, 1], ang[:, 2], 11.338, g[:88], g[88:176], NODES, ACT, P.host.load_weights(), w_zn)
+    st = [int(x) for x in multi.julia_seed_state(123)]
+    i1, i2 = multi._jl_rand_range(st, 4), 4 + multi._jl_rand_range(st, 2)
+    assert (i1, i2) == (3, 6)
+    swapped = pos.copy()
+    swapped[[i1 - 1, i2 - 1]] = pos[[i2 - 1, i1 - 1]]
+    de = oracle.runner2_energy(swapped, *args)[0] - oracle.runner2_energy(pos, *args)[0]
+    assert de == pytest.approx(-0.0017084901948, rel=2e-8)
+
+
 def _cu55_engine(oracle, n_traj=3, seed=5, boundary=0.0):
     mcp, temp, start, pot, ens = P.host.deck_cu55_runner(n_traj=n_traj, cycles=2, boundary=boundary)
     cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=1, seed=seed, rng_mode=abi.RNG_XOSHIRO)
