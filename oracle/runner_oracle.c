@@ -14,7 +14,9 @@
  * Pinning (tests/test_runner_oracle.py): forward == 21 for the all-ones network (test/test_runner_forward.jl:44-75);
  * forward against the reference's own librunnerjulia.so (oracle/_ref) on real weights; the 6-atom Cu4Zn2 energy
  * -0.261652899 of test/test_potentials.jl:67-87 through orc_runner2_energy, which shares every per-pair and
- * per-triple function with the single-species path (the 2-species bookkeeping itself is not part of the product).
+ * per-triple function with the single-species path; the 2-species atom-move energy change -7.5971516e-5 of
+ * test/test_states.jl:148-159 through orc_runner2_move_delta (calc_delta_matrix for two species) and the swap energy change
+ * -0.0017084901948 of :166-175 by fresh evaluation (the 2-species sweep itself is not part of the product yet).
  */
 #include "../include/ptmc_b200.h"
 
