@@ -69,6 +69,8 @@ def load():
                                             C.c_int, _ip, _ip, _dp, _dp, _dp]),
         "orc_runner2_move_delta": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
                                             C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp]),
+        "orc_runner2_swap_delta": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
+                                            C.c_int, _ip, _ip, _dp, _dp, C.c_int, C.c_int]),
         "orc_julia_seed": (None, [C.c_uint64, _u64p]),
         "orc_xoshiro_next": (C.c_uint64, [_u64p]),
         "orc_rand_from_state": (C.c_double, [_u64p]),
@@ -231,6 +233,23 @@ def runner2_move_delta(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cu
     tr, ptr = _arr(trial)
     return load().orc_runner2_move_delta(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
                                          nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, int(atom), ptr)
+
+
+def runner2_swap_delta(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, nodes, act, params1, params2, a1, a2):
+    """2-species energy change of swapping atoms a1 (species 1) and a2 (species 2) through calc_swap_matrix; 0-based indices"""
+    p, pp = _arr(pos)
+    re_, pre = _arr(rad_eta)
+    ae, pae = _arr(ang_eta)
+    al, pal = _arr(ang_lambda)
+    az, paz = _arr(ang_zeta)
+    ga, pga = _arr(gmaxmin_a)
+    gb, pgb = _arr(gmaxmin_b)
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    ac = np.ascontiguousarray(act, dtype=np.int32)
+    p1, pp1 = _arr(params1)
+    p2, pp2 = _arr(params2)
+    return load().orc_runner2_swap_delta(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
+                                         nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, int(a1), int(a2))
 
 
 class OracleEngine(Engine):

@@ -16,7 +16,8 @@
  * -0.261652899 of test/test_potentials.jl:67-87 through orc_runner2_energy, which shares every per-pair and
  * per-triple function with the single-species path; the 2-species atom-move energy change -7.5971516e-5 of
  * test/test_states.jl:148-159 through orc_runner2_move_delta (calc_delta_matrix for two species) and the swap energy change
- * -0.0017084901948 of :166-175 by fresh evaluation (the 2-species sweep itself is not part of the product yet).
+ * -0.0017084901948 of :166-175 through orc_runner2_swap_delta (calc_swap_matrix) (the 2-species sweep itself is not part of the
+ * product yet).
  */
 #include "../include/ptmc_b200.h"
 
@@ -311,6 +312,111 @@ double orc_runner2_energy(const double* pos, int n1, int n2, int n_rad, const do
     const double tot = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
     free(d2); free(f); free(g);
     return tot;
+}
+
+/* calc_one_symm_val SymmFunc.jl:229-241 (radial: 0 when the cut-off function is 0 or 1; angular: symmfunc_calc :196-202) */
+static double one_radial(double r2, double fc, double eta) { return (fc != 0.0 && fc != 1.0) ? fc * exp(-eta * r2) : 0.0; }
+static void one_angular(const double* pos, const double* d2, const double* f, int n, int a, int b, int c, double eta, double lambda, double zeta, double gv[3]) {
+    double th[3];
+    const double r2ab = d2[(size_t)a * n + b], r2ac = d2[(size_t)a * n + c], r2bc = d2[(size_t)b * n + c];
+    all_angular_measure(pos + 3 * a, pos + 3 * b, pos + 3 * c, r2ab, r2ac, r2bc, th);
+    const double ep = exp_part6(eta, r2ab, r2ac, r2bc, f[(size_t)a * n + b], f[(size_t)a * n + c], f[(size_t)b * n + c]);
+    for (int m = 0; m < 3; ++m) gv[m] = ep * theta_part(th[m], lambda, zeta);
+}
+/* ---- 2-species atom swap (KAT checker only; test/test_states.jl:166-175): energy change of exchanging the positions of atom a1
+ * (species 1) and a2 (species 2) through calc_swap_matrix (MachineLearningPotential/DeltaMatrix.jl:319-632) as swap_energy_update uses
+ * it (src/EnergyEvaluation.jl:1381-1448).  Rows are 0-based here: radial row = species of the neighbour, angular row = number of
+ * species-2 atoms among the two neighbours; the statements keep the reference's order. */
+double orc_runner2_swap_delta(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
+                              const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
+                              int n_layers, const int* nodes, const int* act, const double* params1, const double* params2, int a1, int a2) {
+    const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang;
+    double* d2 = (double*)xc((size_t)n * n, 8);
+    double* f = (double*)xc((size_t)n * n, 8);
+    double* g = (double*)xc((size_t)n * ns, 8);
+    double* dg = (double*)xc((size_t)n * ns, 8);
+    runner2_gmatrix(pos, n1, n2, n_rad, rad_eta, n_ang, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, d2, f, g);
+    const double e_old = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
+#define DG(row, atom) dg[(size_t)(atom) * ns + base + (row)]
+    for (int k = 0; k < n_rad; ++k) {                                           /* :322-371 */
+        const int base = 2 * k;
+        const double eta = rad_eta[k];
+        for (int x = 0; x < n1; ++x) {
+            if (x == a1) continue;
+            const double g1 = one_radial(d2[(size_t)a1 * n + x], f[(size_t)a1 * n + x], eta);
+            const double g2 = one_radial(d2[(size_t)a2 * n + x], f[(size_t)a2 * n + x], eta);
+            DG(0, x) += g2 - g1; DG(1, x) += g1 - g2;
+            DG(0, a1) += g2 - g1;
+            DG(0, a2) += g1 - g2;
+        }
+        for (int x = n1; x < n; ++x) {
+            if (x == a2) continue;
+            const double g1 = one_radial(d2[(size_t)a1 * n + x], f[(size_t)a1 * n + x], eta);
+            const double g2 = one_radial(d2[(size_t)a2 * n + x], f[(size_t)a2 * n + x], eta);
+            DG(0, x) += g2 - g1; DG(1, x) += g1 - g2;
+            DG(1, a1) += g2 - g1;
+            DG(1, a2) += g1 - g2;
+        }
+        for (int a = 0; a < n; ++a)
+            for (int s_ = 0; s_ < 2; ++s_) DG(s_, a) *= GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
+    }
+    for (int k = 0; k < n_ang; ++k) {                                           /* :373-580 */
+        const int base = 2 * n_rad + 3 * k;
+        const double eta = ang_eta[k], la = ang_lambda[k], ze = ang_zeta[k];
+        double v1[3], v2[3];
+        for (int j = 0; j < n1; ++j) {                                          /* both neighbours of species 1 */
+            if (j == a1) continue;
+            for (int c = j + 1; c < n1; ++c) {
+                if (c == a1) continue;
+                one_angular(pos, d2, f, n, a1, j, c, eta, la, ze, v1);
+                one_angular(pos, d2, f, n, a2, j, c, eta, la, ze, v2);
+                DG(0, a1) += v2[0] - v1[0]; DG(0, a2) += v1[0] - v2[0];
+                DG(0, j) += v2[1] - v1[1]; DG(0, c) += v2[2] - v1[2];
+                DG(1, j) += v1[1] - v2[1]; DG(1, c) += v1[2] - v2[2];
+            }
+        }
+        for (int j = n1; j < n; ++j) {                                          /* both neighbours of species 2 */
+            if (j == a2) continue;
+            for (int c = j + 1; c < n; ++c) {
+                if (c == a2) continue;
+                one_angular(pos, d2, f, n, a1, j, c, eta, la, ze, v1);
+                one_angular(pos, d2, f, n, a2, j, c, eta, la, ze, v2);
+                DG(2, a1) += v2[0] - v1[0]; DG(2, a2) += v1[0] - v2[0];
+                DG(1, j) += v2[1] - v1[1]; DG(1, c) += v2[2] - v1[2];
+                DG(2, j) += v1[1] - v2[1]; DG(2, c) += v1[2] - v2[2];
+            }
+        }
+        for (int j = 0; j < n1; ++j) {                                          /* one neighbour of each species */
+            if (j == a1) continue;
+            for (int c = n1; c < n; ++c) {
+                if (c == a2) continue;
+                one_angular(pos, d2, f, n, a1, j, c, eta, la, ze, v1);
+                one_angular(pos, d2, f, n, a2, j, c, eta, la, ze, v2);
+                DG(1, a1) += v2[0] - v1[0]; DG(1, a2) += v1[0] - v2[0];
+                DG(1, j) += v2[1] - v1[1]; DG(0, c) += v2[2] - v1[2];
+                DG(2, j) += v1[1] - v2[1]; DG(1, c) += v1[2] - v2[2];
+            }
+        }
+        for (int c = 0; c < n1; ++c) {                                          /* triples that hold both swapped atoms */
+            if (c == a1) continue;
+            one_angular(pos, d2, f, n, a1, a2, c, eta, la, ze, v1);
+            DG(1, a1) -= v1[0]; DG(0, a2) += v1[0];
+            DG(0, a2) -= v1[1]; DG(1, a1) += v1[1];
+        }
+        for (int c = n1; c < n; ++c) {
+            if (c == a2) continue;
+            one_angular(pos, d2, f, n, a1, a2, c, eta, la, ze, v1);
+            DG(2, a1) -= v1[0]; DG(1, a2) += v1[0];
+            DG(1, a2) -= v1[1]; DG(2, a1) += v1[1];
+        }
+        for (int a = 0; a < n; ++a)
+            for (int s_ = 0; s_ < 3; ++s_) DG(s_, a) *= pow(2.0, 1 - ze) * GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
+    }
+#undef DG
+    for (size_t q = 0; q < (size_t)n * ns; ++q) g[q] += dg[q];
+    const double e_new = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
+    free(d2); free(f); free(g); free(dg);
+    return e_new - e_old;
 }
 
 /* ---- 2-species atom move (KAT checker only; test/test_states.jl:148-159): energy change of moving atom `atom` to `trial`,

@@ -80,8 +80,7 @@ def test_brass_atom_move_delta_energy(oracle):
 def test_brass_atom_swap_energy(oracle):
     # test/test_states.jl:166-183: Random.seed!(123); swap_atoms -> rand(1:N1), rand(N1+1:N) = (3, 6) (the test's own dist2_mat / config
     # assertions say so); get_energy!(state, runnerpotential, "atomswap") ≈ -0.0017084901948.  The swap exchanges the positions of one
-    # atom of each species; here through a fresh evaluation of the swapped configuration (calc_swap_matrix itself, DeltaMatrix.jl:319-632,
-    # is restated with the 2-species sweep, DESIGN.md §8 "Next")
+    # atom of each species: checked through a fresh evaluation of the swapped configuration and through calc_swap_matrix
     from ptmc_b200 import multi
     pos = np.array([[2.36, 2.36, 0.0], [6.99, 2.33, 0.0], [2.33, 6.99, 0.0], [-2.36, 2.36, 0.0], [-6.99, 2.33, 0.0], [-2.33, 6.99, 0.0]])
     g = P.host.load_scaling()
@@ -95,6 +94,17 @@ def test_brass_atom_swap_energy(oracle):
     swapped[[i1 - 1, i2 - 1]] = pos[[i2 - 1, i1 - 1]]
     de = oracle.runner2_energy(swapped, *args)[0] - oracle.runner2_energy(pos, *args)[0]
     assert de == pytest.approx(-0.0017084901948, rel=2e-8)
+    # ... and through the restatement of calc_swap_matrix (DeltaMatrix.jl:319-632)
+    assert oracle.runner2_swap_delta(pos, *args, i1 - 1, i2 - 1) == pytest.approx(-0.0017084901948, rel=2e-8)
+    rng = np.random.default_rng(3)
+    p2 = pos + rng.uniform(-0.3, 0.3, pos.shape)
+    p2[:, 2] = rng.uniform(-1, 1, 6)
+    for a1 in range(4):
+        for a2 in (4, 5):
+            sw = p2.copy()
+            sw[[a1, a2]] = p2[[a2, a1]]
+            fresh = oracle.runner2_energy(sw, *args)[0] - oracle.runner2_energy(p2, *args)[0]
+            assert oracle.runner2_swap_delta(p2, *args, a1, a2) == pytest.approx(fresh, rel=1e-9, abs=1e-14)
 
 
 def _cu55_engine(oracle, n_traj=3, seed=5, boundary=0.0):
