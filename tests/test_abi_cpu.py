@@ -40,6 +40,29 @@ def test_config_struct_matches_header():
     assert int(out[1]) == C.sizeof(abi.RunnerDesc)
 
 
+def _header_fields(struct_name):
+    header = (abi.PKG_DIR.parent / "include" / "ptmc_b200.h").read_text()
+    i = header.index("typedef struct %s" % struct_name)
+    body = re.sub(r"/\*.*?\*/", "", header[i:header.index("} %s;" % struct_name, i)], flags=re.S)
+    names = []
+    for stmt in body.replace("typedef struct %s {" % struct_name, "").split(";"):
+        m = re.match(r"\s*(?:const\s+)?\w+\s*\*?\s+(.*)", stmt, re.S)
+        if m:
+            names += [re.sub(r"\[.*\]", "", d.strip().lstrip("*").strip()) for d in m.group(1).split(",") if d.strip()]
+    return names
+
+
+def test_bindings_list_the_header_fields_in_order():
+    # the ctypes mirror (what the tests drive) and the Julia struct a maintainer adds against include/ptmc_b200.h
+    for struct_name, ctype, jl_name in (("ptmc_config", abi.Config, "PtmcConfig"), ("ptmc_runner_desc", abi.RunnerDesc, "PtmcRunnerDesc")):
+        fields = _header_fields(struct_name)
+        assert fields == [f[0] for f in ctype._fields_], struct_name
+        jl = (abi.PKG_DIR / "julia" / "PTMCB200.jl").read_text()
+        if "struct %s" % jl_name in jl:
+            i = jl.index("struct %s" % jl_name)
+            assert fields == re.findall(r"^\s*(\w+)::", jl[i:jl.index("\nend", i)], flags=re.M), jl_name
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
