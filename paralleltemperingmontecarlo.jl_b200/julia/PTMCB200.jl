@@ -84,6 +84,53 @@ pot_fields(p::EmbeddedAtomPotential) = (Int32(2), Int32(0), (), (p.n, p.m, p.ean
 pot_fields(p::LookupTablePotential) = (Int32(5), Int32(0), (), (0.0, 0.0, 0.0, 0.0))
 pot_fields(p::ELJPotentialB{N}) where {N} = (Int32(4), Int32(N), Tuple(p.coeff_c), (0.0, 0.0, 0.0, 0.0))
 
+pot_fields(p::RuNNerPotential) = (Int32(3), Int32(0), (), (0.0, 0.0, 0.0, 0.0))
+
+# mirror of `ptmc_runner_desc` (include/ptmc_b200.h); field order and types must match the header
+struct PtmcRunnerDesc
+    n_rad::Int32
+    n_ang::Int32
+    rad_eta::Ptr{Float64}
+    rad_type::Ptr{Int32}
+    rad_gmax_gmin::Ptr{Float64}
+    ang_eta::Ptr{Float64}
+    ang_lambda::Ptr{Float64}
+    ang_zeta::Ptr{Float64}
+    ang_type::Ptr{Int32}
+    ang_gmax_gmin::Ptr{Float64}
+    r_cut::Float64
+    boundary2::Float64
+    n_layers::Int32
+    num_nodes::Ptr{Int32}
+    activation::Ptr{Int32}
+    n_params::Int32
+    params::Ptr{Float64}
+end
+
+# RuNNerPotential -> descriptor + the arrays it points into (keep them alive across ptmc_create).  The package's symmetry-function
+# structs hold G_norm = 1 / (G_max - G_min) and G_offset = -G_min * G_norm (SymmFunc.jl:40-44,107-112), the descriptor wants the
+# scaling.data pair itself: a script that still has its `G_value_vec` should pass that instead (`scaling = G_value_vec`), because
+# the pair recovered here, G_min = -G_offset / G_norm and G_max = G_min + 1 / G_norm, can differ from the file's by an ulp.
+function runner_desc(p::RuNNerPotential{Nrad,Nang}; scaling=nothing) where {Nrad,Nang}
+    rs, as = p.radsymfunctions, p.angsymfunctions
+    gpair(norm, off) = (gmin = -off / norm; (gmin + 1 / norm, gmin))
+    rg = Float64[]; ag = Float64[]
+    for k in 1:Nrad
+        append!(rg, scaling === nothing ? gpair(rs.G_norm[k], rs.G_offset[k]) : (scaling[k][1], scaling[k][2]))
+    end
+    for k in 1:Nang
+        norm = as.tpz[k] / 2.0^(1 - as.zeta[k])
+        append!(ag, scaling === nothing ? gpair(norm, as.G_offset[k]) : (scaling[Nrad + k][1], scaling[Nrad + k][2]))
+    end
+    arrays = (collect(Float64, rs.eta), collect(Int32, rs.type_vec), rg, collect(Float64, as.eta), collect(Float64, as.lambda),
+              collect(Float64, as.zeta), collect(Int32, as.type_vec), ag, collect(Int32, p.nnp.num_nodes),
+              collect(Int32, p.nnp.activation_functions), collect(Float64, p.nnp.parameters))
+    desc = PtmcRunnerDesc(Nrad, Nang, pointer(arrays[1]), pointer(arrays[2]), pointer(arrays[3]), pointer(arrays[4]), pointer(arrays[5]),
+                          pointer(arrays[6]), pointer(arrays[7]), pointer(arrays[8]), p.r_cut, p.boundary, p.nnp.n_layers,
+                          pointer(arrays[9]), pointer(arrays[10]), p.nnp.n_params, pointer(arrays[11]))
+    return Ref(desc), arrays
+end
+
 pad16(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, PTMC_MAX_COEFF)
 
 function check(lib, h, rc)
@@ -114,16 +161,17 @@ function ParallelTemperingMonteCarlo.ptmc_run!(b::B200Backend, mc_params::MCPara
     eb = potential isa ELJPotentialB ? collect(Float64, potential.coeff_b) : Float64[]
     islut = potential isa LookupTablePotential
     lut = islut ? collect(Float64, permutedims(potential.table)) : Float64[]        # memory order: distance index fastest
+    rdesc, rkeep = potential isa RuNNerPotential ? runner_desc(potential; scaling=get(kwargs, :scaling, nothing)) : (nothing, ())
     cfg = Ref(PtmcConfig(PTMC_ABI_VERSION, b.device, L, T, N, npt ? 1 : 0, ensemble.n_atom_moves,
         npt ? ensemble.n_volume_moves : 0, bc_kind(bc), npt ? ensemble.pressure : 0.0, pk, nc, pad16(coeff),
-        eam..., C_NULL, pointer(betas), mc_params.n_adjust, mc_params.mc_sample, mc_params.n_bin, b.rng_mode,
+        eam..., rdesc === nothing ? Ptr{Cvoid}(C_NULL) : Ptr{Cvoid}(Base.unsafe_convert(Ptr{PtmcRunnerDesc}, rdesc)), pointer(betas), mc_params.n_adjust, mc_params.mc_sample, mc_params.n_bin, b.rng_mode,
         mc_params.min_acc, mc_params.max_acc, b.seed, b.lanes_per_replica, (npt && ensemble.separated_volume) ? 1 : 0,
         isempty(ea) ? Ptr{Float64}(C_NULL) : pointer(ea), isempty(eb) ? Ptr{Float64}(C_NULL) : pointer(eb),
         islut ? pointer(lut) : Ptr{Float64}(C_NULL), islut ? potential.l_dist : Int32(0), islut ? potential.l_angle : Int32(0),
         islut ? potential.start_dist : 0.0, islut ? potential.d_dist : 0.0, islut ? potential.start_angle : 0.0,
         islut ? potential.d_angle : 0.0, islut ? potential.c6coeff : 0.0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve betas ea eb lut begin
+    GC.@preserve betas ea eb lut rdesc rkeep begin
         rc = ccall((:ptmc_create, lib), Cint, (Ref{PtmcConfig}, Ref{Ptr{Cvoid}}), cfg, h)
     end
     rc == 0 || error("libptmc_b200: " * unsafe_string(ccall((:ptmc_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
