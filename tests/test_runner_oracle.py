@@ -70,6 +70,7 @@ def test_brass_atom_move_delta_energy(oracle):
     trial = pos[0] + (np.array([multi._jl_rand(st) for _ in range(3)]) - 0.5) * 0.1
     de = oracle.runner2_move_delta(pos, 4, 2, rad_eta, ang[:, 0], ang[:, 1], ang[:, 2], 11.338, g[:88], g[88:176], NODES, ACT, w_cu, w_zn, 0, trial)
     assert de == pytest.approx(-7.5971516e-5, rel=2e-8)        # Julia's ≈: rtol = sqrt(eps)
+    assert de == pytest.approx(-7.597151644539446e-05, abs=1e-13)   # SURVEY §8c anchor (independent full-energy recompute)
     # the delta path against a fresh evaluation of the moved configuration
     moved = pos.copy(); moved[0] = trial
     e0, _ = oracle.runner2_energy(pos, 4, 2, rad_eta, ang[:, 0], ang[:, 1], ang[:, 2], 11.338, g[:88], g[88:176], NODES, ACT, w_cu, w_zn)
@@ -96,6 +97,7 @@ def test_brass_atom_swap_energy(oracle):
     assert de == pytest.approx(-0.0017084901948, rel=2e-8)
     # ... and through the restatement of calc_swap_matrix (DeltaMatrix.jl:319-632)
     assert oracle.runner2_swap_delta(pos, *args, i1 - 1, i2 - 1) == pytest.approx(-0.0017084901948, rel=2e-8)
+    assert oracle.runner2_swap_delta(pos, *args, i1 - 1, i2 - 1) == pytest.approx(-0.0017084901948977715, abs=1e-13)   # SURVEY §8c anchor
     rng = np.random.default_rng(3)
     p2 = pos + rng.uniform(-0.3, 0.3, pos.shape)
     p2[:, 2] = rng.uniform(-1, 1, 6)
