@@ -8,7 +8,8 @@ from ptmc_b200.host import initial_arrays, sweep_config
 
 from parity import make_replay
 
-CASES = ("ne13_elj_nvt", "cu55_eam_nvt", "ne32_cubic_npt", "ne216_rhombic_npt", "ne13_eljb_nvt", "ne32_rect_npt_separated")
+CASES = ("ne13_elj_nvt", "cu55_eam_nvt", "ne32_cubic_npt", "ne216_rhombic_npt", "ne13_eljb_nvt", "ne32_rect_npt_separated",
+         "ne32_rhombic_eljb_npt_separated")
 
 
 def _ne32_cubic():
@@ -46,13 +47,28 @@ def build_case(name, oracle):
                 P.NPT(32, 101325 * 3.398928944382626e-14, True, n_volume_moves=3))
         v0 = P.get_volume(start.boundary_condition)
         L, cycles, seed, eq, bounds = 1, 16, 55, 4, (-0.05, 0.0, 0.8 * v0, 2.0 * v0)
+    elif name == "ne32_rhombic_eljb_npt_separated":
+        # ELJPotentialB in a rhombic cell (Angstrom) with separated volume moves: the reference's aliased tan_mat / new_tan_mat leaves
+        # the tangents of rejected xy / z trials in the state; lattice perturbed by 1e-3 (no half-cell ties)
+        a2b = 1.8897259886
+        lat = _ne32_cubic()
+        pos = (lat.positions @ np.array([[1, 0, 0], [0.5, 3 ** 0.5 / 2, 0], [0, 0, 1]])) / a2b
+        pos = pos + np.random.default_rng(8).uniform(-1e-3, 1e-3, pos.shape)
+        Lb = lat.boundary_condition.box_length / a2b
+        start = P.Config(pos, P.RhombicBC(Lb, Lb))
+        deck = (P.MCParams(16, 4, 32, n_adjust=8), P.TempGrid(20.0, 40.0, 4), start,
+                P.ELJPotentialB(P.host.ELJB_NE_A, P.host.ELJB_NE_B, P.host.ELJB_NE_C),
+                P.NPT(32, 101325 * 3.398928944382626e-14 * a2b ** 3, True, n_volume_moves=4))
+        v0 = P.get_volume(start.boundary_condition)
+        L, cycles, seed, eq, bounds = 1, 16, 91, 4, (0.2, 1.0, 0.8 * v0, 2.0 * v0)
     else:
         raise KeyError(name)
     mcp, temp, start, pot, ens = deck
     # start with step sizes that give ~50 % acceptance instead of the constructor's 0.1 (src/MCStates.jl:104)
     md = np.full((L, mcp.n_traj, 4), 0.1)
     md[:, :, 0] = {"ne13_elj_nvt": 0.9, "cu55_eam_nvt": 0.5, "ne32_cubic_npt": 0.7, "ne216_rhombic_npt": 0.6,
-                   "ne13_eljb_nvt": 0.4, "ne32_rect_npt_separated": 0.7}[name]
+                   "ne13_eljb_nvt": 0.4, "ne32_rect_npt_separated": 0.7,
+                   "ne32_rhombic_eljb_npt_separated": 0.35}[name]
     cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=seed, rng_mode=abi.RNG_REPLAY)
     pos, box = initial_arrays(mcp, start, L)
     slot, lad = make_replay(oracle, L, mcp.n_traj, cfg.n_steps, eq + cycles, seed)

@@ -6,7 +6,7 @@ Each fixture is one replayed trajectory: the deck and the stream seed define the
 regenerated from the seed by tests/parity.py::make_replay), the file holds the outputs: per-move index / delta
 energy / accept bit, per-cycle exchange record, final positions, energies, counters, step sizes, histogram.
 
-    python tests/tools/make_golden.py          # rewrites tests/golden/*.npz
+    python tests/tools/make_golden.py [case ...]     # rewrites tests/golden/<case>.npz (all cases without arguments)
 """
 import pathlib
 import sys
@@ -26,7 +26,7 @@ def main():
     from oracle import oracle
     out = ROOT / "tests" / "golden"
     out.mkdir(exist_ok=True)
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         cfg, pos, box, slot, lad, n_cycles, bounds, kw = build_case(name, oracle)
         res = run_engine(oracle.OracleEngine, cfg, pos, box, slot, lad, n_cycles, bounds, **kw)
         tr, st = res["trace"], res["states"]
