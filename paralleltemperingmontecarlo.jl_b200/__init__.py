@@ -7,6 +7,6 @@ julia/PTMCB200.jl (the ccall binding for the reference package), data/ (input de
 from . import abi  # noqa: F401
 from .engine import Engine, PtmcError, RunnerParams, SweepConfig  # noqa: F401
 from .host import (  # noqa: F401
-    Config, CubicBC, ELJPotential, ELJPotentialB, ELJPotentialEven, EmbeddedAtomPotential, LookupTablePotential, MCParams, NPT, NVT, Output,
-    RectangularBC, RhombicBC, RuNNerPotential, SphericalBC, TempGrid, get_volume, kB, ptmc_run,
+    Config, CubicBC, ELJPotential, ELJPotentialB, ELJPotentialEven, EmbeddedAtomPotential, LookupTablePotential, MCParams, NNVT, NPT, NVT, Output,
+    RectangularBC, RhombicBC, RuNNerPotential, RuNNerPotential2Atom, SphericalBC, TempGrid, get_volume, kB, ptmc_run,
 )

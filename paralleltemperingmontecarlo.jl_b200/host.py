@@ -263,9 +263,36 @@ class RuNNerPotential:
             params=np.asarray(params, dtype=np.float64))
 
 
+class RuNNerPotential2Atom:
+    """src/EnergyEvaluation.jl:1287-1314: two-species network potential (nnp1, nnp2, RadialType2a / AngularType3a tables, n1, n2).
+    The constructor mirrors the reference's so that a brass deck can be written down; the sweep for it is not built yet
+    (the oracle restates its initial energy, calc_delta_matrix and calc_swap_matrix and pins them to the
+    reference's known answers) and `sweep_config` says so instead of running something else."""
+    kind = None
+
+    def __init__(self, nnp1, nnp2, radsymvec, angsymvec, n1, n2, boundary: float = 0.0):
+        self.nnp1, self.nnp2, self.radsymvec, self.angsymvec = nnp1, nnp2, radsymvec, angsymvec
+        self.n1, self.n2, self.boundary2 = int(n1), int(n2), float(boundary) * float(boundary)
+
+
+@dataclass
+class NNVT:
+    """src/Ensembles.jl:138-151 — NNVT(natoms; natomswaps = 1, natommoves = sum(natoms)): two species, atom moves + atom swaps"""
+    natoms: tuple
+    n_atom_swaps: int = 1
+    n_atom_moves: int | None = None
+    kind = None
+
+    def atom_moves(self):
+        return sum(self.natoms) if self.n_atom_moves is None else self.n_atom_moves
+
+
 # ------------------------------------------------------------------------------- config building --
 def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, ensemble, *, n_ladders=1,
                  seed=1234, device=0, rng_mode=abi.RNG_BATCH8, lanes_per_replica=0) -> SweepConfig:
+    if isinstance(ensemble, NNVT) or isinstance(potential, RuNNerPotential2Atom):
+        raise NotImplementedError("the two-species sweep (RuNNerPotential2Atom + NNVT atom swaps, scripts/brass55.jl) is not built in "
+                                  "libptmc_b200 yet: single-species RuNNerPotential with NVT is (DESIGN.md section 8)")
     cfgs = start_config if isinstance(start_config, (list, tuple)) else (start_config,)
     bc = cfgs[0].boundary_condition
     if isinstance(ensemble, NPT):

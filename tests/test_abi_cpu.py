@@ -87,3 +87,11 @@ def test_argument_validation_precedes_device(lib):
     c.n_volume_moves = 1
     assert lib.ptmc_create(C.byref(c), C.byref(h)) == abi.ERR_ARG
     assert b"SphericalBC cannot be used in an NPT ensemble" in lib.ptmc_last_error(None)
+
+
+def test_two_species_sweep_is_refused_loudly():
+    # RuNNerPotential2Atom / NNVT (scripts/brass55.jl) exist in the host mirror, and say that the sweep for them is not built
+    cfg = P.Config(np.zeros((6, 3)) + np.arange(6)[:, None], P.SphericalBC(radius=8.0))
+    with pytest.raises(NotImplementedError, match="two-species"):
+        sweep_config(P.MCParams(10, 2, 6), P.TempGrid(500.0, 650.0, 2), cfg, P.RuNNerPotential2Atom(None, None, [], [], 4, 2), P.NNVT((4, 2)))
+    assert P.NNVT((4, 2)).atom_moves() == 6 and P.NNVT((4, 2)).n_atom_swaps == 1          # src/Ensembles.jl:144
