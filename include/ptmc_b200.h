@@ -39,7 +39,7 @@ extern "C" {
 #define PTMC_API
 #endif
 
-#define PTMC_ABI_VERSION 3
+#define PTMC_ABI_VERSION 4
 #define PTMC_MAX_COEFF 16
 #define PTMC_NCOUNT 10
 
@@ -56,11 +56,12 @@ typedef enum ptmc_status {
  * :1182 (RuNNerPotential) */
 /* :909-921 (ELJPotentialB: extended Lennard-Jones in a magnetic field, pair energy depends on the angle to the z axis) */
 typedef enum ptmc_pot_kind { PTMC_POT_ELJ = 0, PTMC_POT_ELJ_EVEN = 1, PTMC_POT_EAM = 2, PTMC_POT_RUNNER = 3, PTMC_POT_ELJ_B = 4,
-                             PTMC_POT_LUT = 5 /* :214-295 LookupTablePotential: energy tabulated over (angle to z, distance) */ } ptmc_pot_kind;
+                             PTMC_POT_LUT = 5 /* :214-295 LookupTablePotential: energy tabulated over (angle to z, distance) */,
+                             PTMC_POT_RUNNER2 = 6 /* :1287-1314 RuNNerPotential2Atom: two species, one network per species */ } ptmc_pot_kind;
 /* src/BoundaryConditions.jl:44,72,89,110 */
 typedef enum ptmc_bc_kind { PTMC_BC_SPHERICAL = 0, PTMC_BC_CUBIC = 1, PTMC_BC_RHOMBIC = 2, PTMC_BC_RECTANGULAR = 3 } ptmc_bc_kind;
-/* src/Ensembles.jl:42 (NVT), :75 (NPT; separated_volume in ptmc_config) */
-typedef enum ptmc_ens_kind { PTMC_ENS_NVT = 0, PTMC_ENS_NPT = 1 } ptmc_ens_kind;
+/* src/Ensembles.jl:42 (NVT), :75 (NPT; separated_volume in ptmc_config), :138 (NNVT: two species, atom moves + atom swaps) */
+typedef enum ptmc_ens_kind { PTMC_ENS_NVT = 0, PTMC_ENS_NPT = 1, PTMC_ENS_NNVT = 2 } ptmc_ens_kind;
 typedef enum ptmc_rng_mode {
     PTMC_RNG_XOSHIRO = 0, /* Julia's default RNG as ONE sequential stream per slot: Xoshiro256++,
                              rand()=(u>>11)*2^-53, rand(1:n)=Lemire.  Compatibility mode (slower kernel).  */
@@ -104,6 +105,30 @@ typedef struct ptmc_runner_desc {
     const double* params;          /* weights.XXX.data order                         */
 } ptmc_runner_desc;
 
+/* RuNNer two-species potential (RuNNerPotential2Atom src/EnergyEvaluation.jl:1287-1314; RadialType2a / AngularType3a
+ * MachineLearningPotential/SymmFunc.jl:53-84,113-171): atoms 0 .. n1-1 are species 1, n1 .. n1+n2-1 species 2.  Every radial
+ * function owns two rows of the g matrix (neighbour of species 1 / 2), every angular function three (0 / 1 / 2 neighbours of
+ * species 2): n_sym = 2 n_rad + 3 n_ang rows, radial function k at rows 2k, 2k+1, angular function k at 2 n_rad + 3k + {0,1,2}
+ * (total_symm_calc SymmFunc.jl:511-545).  All functions are evaluated (no type filter, DeltaMatrix.jl:256-316). */
+typedef struct ptmc_runner2_desc {
+    int32_t n_rad, n_ang;          /* Nrad, Nang (5, 26 for scripts/brass55.jl)                       */
+    int32_t n1, n2;                /* N1, N2 (50, 5)                                                  */
+    const double* rad_eta;         /* [n_rad]                                                         */
+    const double* ang_eta;         /* [n_ang]                                                         */
+    const double* ang_lambda;      /* [n_ang]                                                         */
+    const double* ang_zeta;        /* [n_ang]                                                         */
+    const double* gmax_gmin_1;     /* [n_sym][2] {G_max, G_min} of species 1 in g-matrix row order (scaling.data rows 1-88)  */
+    const double* gmax_gmin_2;     /* [n_sym][2] the same for species 2 (rows 89-176)                 */
+    double r_cut;                  /* pot.r_cut                                                       */
+    double boundary2;              /* pot.boundary (squared, :1305-1314; energy_update! :1623-1643 does not use it) */
+    int32_t n_layers;              /* both networks share the topology (scripts/brass55.jl:151-164)   */
+    const int32_t* num_nodes;      /* [n_layers]                                                      */
+    const int32_t* activation;     /* [n_layers]                                                      */
+    int32_t n_params;
+    const double* params_1;        /* nnp1 (weights.029.data order)                       */
+    const double* params_2;        /* nnp2                                                            */
+} ptmc_runner2_desc;
+
 /* Everything that is fixed for the lifetime of a handle.  Mirrors what ptmc_run! receives:
  * MCParams (src/InputParams.jl:35), TempGrid (:77), the potential, the ensemble and the BC kind. */
 typedef struct ptmc_config {
@@ -139,6 +164,10 @@ typedef struct ptmc_config {
     const double* lut_table;
     int32_t lut_l_dist, lut_l_angle;
     double lut_start_dist, lut_d_dist, lut_start_angle, lut_d_angle, lut_c6coeff;
+    /* ABI 4: PTMC_ENS_NNVT - NNVT.n_atom_swaps (src/Ensembles.jl:138-151): move indices n_atom_moves + 1 .. n_atom_moves +
+     * n_atom_swaps of MoveStrategy(::NNVT) (:270-282) are "atomswap"; PTMC_POT_RUNNER2 - the two-species potential       */
+    int32_t n_atom_swaps;
+    const ptmc_runner2_desc* runner2;
 } ptmc_config;
 
 typedef struct ptmc_handle ptmc_handle;
@@ -218,7 +247,8 @@ PTMC_API int ptmc_sync(ptmc_handle* h);
 /* Record per-move (index, new_en - en_tot, accepted) and per-cycle exchange (gate, n_exc, accepted) for
  * the next run_cycles calls; capacity in cycles.  capacity 0 disables tracing. */
 PTMC_API int ptmc_trace_enable(ptmc_handle* h, int64_t capacity_cycles);
-/* move_index [n_ladders][cycles][n_traj][n_steps] (1-based, > n_atoms = volume move),
+/* move_index [n_ladders][cycles][n_traj][n_steps] (1-based, > n_atoms = volume move; an NNVT atom swap records
+ * index + (i1 << 10) + (i2 << 20) with the 1-based swap_indices of swap_atoms, src/MCMoves.jl:363-370),
  * delta_en same shape, accepted same shape (0/1); exchange [n_ladders][cycles][3] = {gate, n_exc, acc}.
  * Any pointer may be NULL.  *n_cycles_out = cycles recorded. */
 PTMC_API int ptmc_trace_download(ptmc_handle* h, int32_t* move_index, double* delta_en, uint8_t* accepted,

@@ -65,12 +65,7 @@ def load():
         "orc_get_runner_state": (C.c_int, [_vp, C.c_int64, _dp, _dp]),
         "orc_cutoff": (C.c_double, [C.c_double, C.c_double]),
         "orc_runner_forward_raw": (None, [_dp, C.c_int, _ip, _ip, _dp, C.c_int, _dp]),
-        "orc_runner2_energy": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
-                                            C.c_int, _ip, _ip, _dp, _dp, _dp]),
-        "orc_runner2_move_delta": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
-                                            C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp]),
-        "orc_runner2_swap_delta": (C.c_double, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp,
-                                            C.c_int, _ip, _ip, _dp, _dp, C.c_int, C.c_int]),
+        "orc_runner2_check": (C.c_double, [C.POINTER(abi.Runner2Desc), _dp, C.c_int, C.c_int, C.c_int, _dp, _dp]),
         "orc_julia_seed": (None, [C.c_uint64, _u64p]),
         "orc_xoshiro_next": (C.c_uint64, [_u64p]),
         "orc_rand_from_state": (C.c_double, [_u64p]),
@@ -198,58 +193,30 @@ def runner_forward(inp, nodes, act, params):
     return e
 
 
-def runner2_energy(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, nodes, act, params1, params2):
-    """2-species initial energy (KAT checker, test/test_potentials.jl:67-87) -> (E, f_matrix[1,2])"""
+def _runner2_check(r2, pos, what, a=0, b=0, trial=None):
+    """orc_runner2_check: the oracle engine's two-species functions on one configuration; r2: engine.Runner2Params"""
+    keep = []
+    d = r2.to_c(keep)
     p, pp = _arr(pos)
-    re_, pre = _arr(rad_eta)
-    ae, pae = _arr(ang_eta)
-    al, pal = _arr(ang_lambda)
-    az, paz = _arr(ang_zeta)
-    ga, pga = _arr(gmaxmin_a)
-    gb, pgb = _arr(gmaxmin_b)
-    nd = np.ascontiguousarray(nodes, dtype=np.int32)
-    ac = np.ascontiguousarray(act, dtype=np.int32)
-    p1, pp1 = _arr(params1)
-    p2, pp2 = _arr(params2)
+    t, pt = _arr(np.zeros(3) if trial is None else trial)
     f12 = C.c_double()
-    e = load().orc_runner2_energy(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
-                                  nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, C.cast(C.byref(f12), _dp))
-    return e, f12.value
+    v = load().orc_runner2_check(C.byref(d), pp, what, int(a), int(b), pt, C.cast(C.byref(f12), _dp))
+    return v, f12.value
 
 
-def runner2_move_delta(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, nodes, act, params1, params2, atom, trial):
-    """2-species energy change of one atom move through calc_delta_matrix (KAT checker, test/test_states.jl:148-159); atom 0-based"""
-    p, pp = _arr(pos)
-    re_, pre = _arr(rad_eta)
-    ae, pae = _arr(ang_eta)
-    al, pal = _arr(ang_lambda)
-    az, paz = _arr(ang_zeta)
-    ga, pga = _arr(gmaxmin_a)
-    gb, pgb = _arr(gmaxmin_b)
-    nd = np.ascontiguousarray(nodes, dtype=np.int32)
-    ac = np.ascontiguousarray(act, dtype=np.int32)
-    p1, pp1 = _arr(params1)
-    p2, pp2 = _arr(params2)
-    tr, ptr = _arr(trial)
-    return load().orc_runner2_move_delta(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
-                                         nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, int(atom), ptr)
+def runner2_energy(r2, pos):
+    """initial energy through total_symm_calc + two forward passes (test/test_potentials.jl:67-87) -> (E, f_matrix[1,2])"""
+    return _runner2_check(r2, pos, 0)
 
 
-def runner2_swap_delta(pos, n1, n2, rad_eta, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, nodes, act, params1, params2, a1, a2):
-    """2-species energy change of swapping atoms a1 (species 1) and a2 (species 2) through calc_swap_matrix; 0-based indices"""
-    p, pp = _arr(pos)
-    re_, pre = _arr(rad_eta)
-    ae, pae = _arr(ang_eta)
-    al, pal = _arr(ang_lambda)
-    az, paz = _arr(ang_zeta)
-    ga, pga = _arr(gmaxmin_a)
-    gb, pgb = _arr(gmaxmin_b)
-    nd = np.ascontiguousarray(nodes, dtype=np.int32)
-    ac = np.ascontiguousarray(act, dtype=np.int32)
-    p1, pp1 = _arr(params1)
-    p2, pp2 = _arr(params2)
-    return load().orc_runner2_swap_delta(pp, n1, n2, len(re_), pre, len(ae), pae, pal, paz, r_cut, pga, pgb, len(nd),
-                                         nd.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), pp1, pp2, int(a1), int(a2))
+def runner2_move_delta(r2, pos, atom, trial):
+    """energy change of one atom move through calc_delta_matrix (test/test_states.jl:148-159); atom 0-based"""
+    return _runner2_check(r2, pos, 1, atom, 0, trial)[0]
+
+
+def runner2_swap_delta(r2, pos, a1, a2):
+    """energy change of swapping atoms a1 (species 1) and a2 (species 2) through calc_swap_matrix; 0-based indices"""
+    return _runner2_check(r2, pos, 2, a1, a2)[0]
 
 
 class OracleEngine(Engine):
@@ -305,7 +272,7 @@ class OracleEngine(Engine):
     def runner_state(self, ladder: int, slot: int):
         """(g_matrix [atom][n_sym], en_atom [atom]) of one replica (RuNNer)"""
         n = self.cfg.n_atoms
-        ns = len(self.cfg.runner.rad_eta) + len(self.cfg.runner.ang_eta)
+        ns = self.cfg.runner2.n_sym if self.cfg.runner2 is not None else len(self.cfg.runner.rad_eta) + len(self.cfg.runner.ang_eta)
         g, e = np.zeros((n, ns)), np.zeros(n)
         rc = self.lib.orc_get_runner_state(self._h, ladder * self.cfg.n_traj + slot, g.ctypes.data_as(_dp), e.ctypes.data_as(_dp))
         if rc:

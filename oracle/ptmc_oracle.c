@@ -38,6 +38,18 @@ double orc_cutoff(double r_ij, double r_cut);
 void orc_runner_fmatrix(const orc_runner* r, const double* d2, int n, double* f);
 void orc_runner_init_g(const orc_runner* r, const double* pos, const double* d2, const double* f, int n, double* g);
 void orc_runner_forward(const orc_runner* r, const double* g, int n, double* eatom);
+/* two species (RuNNerPotential2Atom), oracle/runner_oracle.c */
+typedef struct orc_runner2 orc_runner2;
+orc_runner2* orc_runner2_new(const ptmc_runner2_desc* d);
+void orc_runner2_free(orc_runner2* r);
+int orc_runner2_nsym(const orc_runner2* r);
+int orc_runner2_n1(const orc_runner2* r);
+double orc_runner2_rcut(const orc_runner2* r);
+void orc_runner2_init_g(const orc_runner2* r, const double* pos, const double* d2, const double* f, int n, double* g);
+void orc_runner2_forward(const orc_runner2* r, const double* g, int n, double* eatom);
+void orc_runner2_delta(const orc_runner2* r, const double* pos, const double* trial, const double* d2, const double* nd2,
+                       const double* f, const double* nf, int i, int n, double* g);
+void orc_runner2_swap(const orc_runner2* r, const double* pos, const double* d2, const double* f, int a1, int a2, int n, double* g);
 void orc_runner_delta(const orc_runner* r, const double* pos, const double* newpos, const double* d2, const double* new_d2,
                       const double* f, const double* new_f, int i, int n, double* g);
 
@@ -391,11 +403,15 @@ typedef struct orc_handle {
     int error;
     int n_threads;
     orc_runner* runner;
+    orc_runner2* runner2;
     double *eljb_a, *eljb_b;   /* copies of cfg.eljb_a / eljb_b */
     double* lut;               /* copy of cfg.lut_table */
 } orc_handle;
 
-static int n_steps_of(const ptmc_config* c) { return c->n_atom_moves + (c->ensemble == PTMC_ENS_NPT ? c->n_volume_moves : 0); }
+/* length(MoveStrategy) src/Ensembles.jl:236-282 */
+static int n_steps_of(const ptmc_config* c) {
+    return c->n_atom_moves + (c->ensemble == PTMC_ENS_NPT ? c->n_volume_moves : 0) + (c->ensemble == PTMC_ENS_NNVT ? c->n_atom_swaps : 0);
+}
 
 /* ------------------------------------------------------------------------------ pair energies -- */
 static double pair_energy(const ptmc_config* c, double r2) {
@@ -490,6 +506,20 @@ static void init_cfgside_runner(const orc_runner* R, orc_cfgside* s, int n) {
     memset(s->new_f, 0, sizeof(double) * n);
 }
 
+/* set_variables(::RuNNerPotential2Atom) src/EnergyEvaluation.jl:1823-1857 + initialise_energy :1748-1768 */
+static void init_cfgside_runner2(const orc_runner2* R, orc_cfgside* s, int n) {
+    const size_t ns = (size_t)orc_runner2_nsym(R);
+    for (size_t k = 0; k < (size_t)n * n; ++k) s->fmat[k] = orc_cutoff(sqrt(s->d2[k]), orc_runner2_rcut(R));
+    orc_runner2_init_g(R, s->pos, s->d2, s->fmat, n, s->g);
+    memset(s->new_g, 0, sizeof(double) * (size_t)n * ns);
+    orc_runner2_forward(R, s->g, n, s->en_atom);
+    double e = 0.0;
+    for (int i = 0; i < n; ++i) e += s->en_atom[i];
+    s->en_tot = e;
+    memset(s->new_en_atom, 0, sizeof(double) * n);
+    memset(s->new_f, 0, sizeof(double) * n);
+}
+
 static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
     int n = c->n_atoms;
     d2_matrix(c, s->pos, s->box, s->d2, n);
@@ -508,8 +538,8 @@ static void init_cfgside(const ptmc_config* c, orc_cfgside* s) {
             s->new_comp[2 * i] = 0; s->new_comp[2 * i + 1] = 0;
         }
         s->en_tot = eam_energy(c, s->comp, n); /* initialise_energy :1722-1734 */
-    } else if (c->pot_kind == PTMC_POT_RUNNER) {
-        /* done by the caller (needs the handle's orc_runner) */
+    } else if (c->pot_kind == PTMC_POT_RUNNER || c->pot_kind == PTMC_POT_RUNNER2) {
+        /* done by the caller (needs the handle's orc_runner / orc_runner2) */
     } else if (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT) {
         /* set_variables(::ELJPotentialB / ::LookupTablePotential): get_tantheta_mat! src/Configurations.jl:229-244; dimer_energy_config :476-492 */
         for (int i = 0; i < n; ++i)
@@ -643,6 +673,19 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
                 for (int j = 0; j < n; ++j) e += s->new_en_atom[j];
                 st->new_en = e;
             }
+        } else if (c->pot_kind == PTMC_POT_RUNNER2) {
+            /* energy_update!(::RuNNerPotential2Atom) src/EnergyEvaluation.jl:1623-1643 (no boundary guard): get_new_state_vars!
+             * :1347-1383 (new_g_matrix = g_matrix .+ calc_delta_matrix(zeros)), calc_new_runner_energy! :1418-1433 */
+            const orc_runner2* R = H->runner2;
+            const size_t ng = (size_t)n * orc_runner2_nsym(R);
+            for (int j = 0; j < n; ++j) s->new_f[j] = orc_cutoff(sqrt(st->new_d2[j]), orc_runner2_rcut(R));
+            memset(s->new_g, 0, sizeof(double) * ng);
+            orc_runner2_delta(R, s->pos, trial, s->d2, st->new_d2, s->fmat, s->new_f, i, n, s->new_g);
+            for (size_t q = 0; q < ng; ++q) s->new_g[q] = s->g[q] + s->new_g[q];
+            orc_runner2_forward(R, s->new_g, n, s->new_en_atom);
+            double e = 0.0;
+            for (int j = 0; j < n; ++j) e += s->new_en_atom[j];
+            st->new_en = e;
         } else if (c->pot_kind == PTMC_POT_EAM) {
             /* src/EnergyEvaluation.jl:1567-1591 + calc_components :1111-1127 */
             memcpy(s->new_comp, s->comp, sizeof(double) * 2 * n);
@@ -683,11 +726,54 @@ static int mc_move(orc_handle* H, orc_state* st, int32_t* tr_i, double* tr_de, u
             if (c->pot_kind == PTMC_POT_EAM) { double* t = s->comp; s->comp = s->new_comp; s->new_comp = t; } /* swap_vars! :208-211 */
             if (c->pot_kind == PTMC_POT_ELJ_B || c->pot_kind == PTMC_POT_LUT)   /* swap_vars!(::ELJPotentialBVariables / ::LookupTableVariables) src/swap_config.jl:197-206 */
                 for (int j = 0; j < n; ++j) { s->tan[(size_t)i * n + j] = st->new_tan[j]; s->tan[(size_t)j * n + i] = st->new_tan[j]; }
-            if (c->pot_kind == PTMC_POT_RUNNER) {   /* swap_vars!(::NNPVariables) src/swap_config.jl:213-221 */
+            if (c->pot_kind == PTMC_POT_RUNNER || c->pot_kind == PTMC_POT_RUNNER2) {   /* swap_vars!(::NNPVariables / ::NNPVariables2a) src/swap_config.jl:213-235 */
                 double* t = s->en_atom; s->en_atom = s->new_en_atom; s->new_en_atom = t;
                 t = s->g; s->g = s->new_g; s->new_g = t;
                 for (int j = 0; j < n; ++j) { s->fmat[(size_t)i * n + j] = s->new_f[j]; s->fmat[(size_t)j * n + i] = s->new_f[j]; }
             }
+        }
+    } else if (c->ensemble == PTMC_ENS_NNVT) {
+        /* "atomswap": swap_atoms src/MCMoves.jl:363-370 - i1 = rand(1:N1), i2 = rand((N1+1):N); BATCH8: positions 1 and 2 */
+        const orc_runner2* R = H->runner2;
+        const int n1 = orc_runner2_n1(R), n2 = n - n1;
+        int i1, i2;
+        if (bm) {
+            i1 = (int)(((__uint128_t)st->rng.buf[1] * (uint64_t)n1) >> 64) + 1;
+            i2 = n1 + (int)(((__uint128_t)st->rng.buf[2] * (uint64_t)n2) >> 64) + 1;
+        } else {
+            i1 = (int)rng_range(&st->rng, (uint64_t)n1);
+            i2 = n1 + (int)rng_range(&st->rng, (uint64_t)n2);
+        }
+        const int a1 = i1 - 1, a2 = i2 - 1;
+        /* get_energy! src/MCRun.jl:88-110 -> swap_energy_update src/EnergyEvaluation.jl:1437-1448: get_new_state_vars! :1385-1410 */
+        const size_t ng = (size_t)n * orc_runner2_nsym(R);
+        memset(s->new_g, 0, sizeof(double) * ng);
+        orc_runner2_swap(R, s->pos, s->d2, s->fmat, a1, a2, n, s->new_g);
+        for (size_t q = 0; q < ng; ++q) s->new_g[q] = s->g[q] + s->new_g[q];
+        orc_runner2_forward(R, s->new_g, n, s->new_en_atom);
+        double e = 0.0;
+        for (int j = 0; j < n; ++j) e += s->new_en_atom[j];
+        st->new_en = e;
+        /* acc_test! src/MCRun.jl:122-132, metropolis_condition("atomswap") src/Exchange.jl:86-87 */
+        double de = st->new_en - s->en_tot;
+        double p = metropolis(de, st->beta);
+        double u = bm ? rng_batch_rand(&st->rng, 4) : rng_rand(&st->rng);
+        if (tr_i) { *tr_i = index + (i1 << 10) + (i2 << 20); *tr_de = de; }
+        if (p >= u) {
+            /* swap_move_config! src/swap_config.jl:241-276: energies, positions, rows then columns of dist2_mat and f_matrix
+             * (diagonals reset), en_atom_vec <-> new_en_atom, g_matrix <-> new_g_matrix; no counter is touched */
+            accepted = 1;
+            double tmp = s->en_tot; s->en_tot = st->new_en; st->new_en = tmp;
+            for (int k = 0; k < 3; ++k) { tmp = s->pos[3 * a1 + k]; s->pos[3 * a1 + k] = s->pos[3 * a2 + k]; s->pos[3 * a2 + k] = tmp; }
+            double* mats[2] = {s->d2, s->fmat};
+            for (int m = 0; m < 2; ++m) {
+                double* M = mats[m];
+                for (int k = 0; k < n; ++k) { tmp = M[(size_t)a1 * n + k]; M[(size_t)a1 * n + k] = M[(size_t)a2 * n + k]; M[(size_t)a2 * n + k] = tmp; }
+                for (int k = 0; k < n; ++k) { tmp = M[(size_t)k * n + a1]; M[(size_t)k * n + a1] = M[(size_t)k * n + a2]; M[(size_t)k * n + a2] = tmp; }
+                M[(size_t)a1 * n + a1] = M[(size_t)a2 * n + a2] = m == 0 ? 0.0 : 1.0;
+            }
+            double* t = s->en_atom; s->en_atom = s->new_en_atom; s->new_en_atom = t;
+            t = s->g; s->g = s->new_g; s->new_g = t;
         }
     } else {
         int xy_or_z = 0;
@@ -929,6 +1015,9 @@ int orc_seed(orc_handle* H, uint64_t seed);
 orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER && (!cfg->runner || cfg->bc_kind != PTMC_BC_SPHERICAL)) return NULL;
     if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b)) return NULL;
+    if ((cfg->pot_kind == PTMC_POT_RUNNER2) != (cfg->ensemble == PTMC_ENS_NNVT)) return NULL;
+    if (cfg->pot_kind == PTMC_POT_RUNNER2 && (!cfg->runner2 || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->runner2->n1 < 1 || cfg->runner2->n2 < 1 ||
+                                              cfg->runner2->n1 + cfg->runner2->n2 != cfg->n_atoms || cfg->n_atom_swaps < 0)) return NULL;
     if (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume && cfg->bc_kind != PTMC_BC_RHOMBIC && cfg->bc_kind != PTMC_BC_RECTANGULAR) return NULL;
     if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91)) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
@@ -945,7 +1034,8 @@ orc_handle* orc_create(const ptmc_config* cfg) {
         H->cfg.eljb_a = H->eljb_a; H->cfg.eljb_b = H->eljb_b;
     } else { H->cfg.eljb_a = NULL; H->cfg.eljb_b = NULL; }
     if (cfg->pot_kind == PTMC_POT_RUNNER) H->runner = orc_runner_new(cfg->runner);
-    H->cfg.runner = NULL;
+    if (cfg->pot_kind == PTMC_POT_RUNNER2) H->runner2 = orc_runner2_new(cfg->runner2);
+    H->cfg.runner = NULL; H->cfg.runner2 = NULL;
     const int n = cfg->n_atoms, nt = cfg->n_traj;
     H->betas = (double*)xcalloc(nt, sizeof(double));
     memcpy(H->betas, cfg->betas, sizeof(double) * nt);
@@ -962,8 +1052,8 @@ orc_handle* orc_create(const ptmc_config* cfg) {
         if (npt) { s->trial_pos = (double*)xcalloc(3 * n, sizeof(double)); s->new_d2mat = (double*)xcalloc((size_t)n * n, sizeof(double)); }
         if (cfg->pot_kind == PTMC_POT_EAM) { s->comp = (double*)xcalloc(2 * n, sizeof(double)); s->new_comp = (double*)xcalloc(2 * n, sizeof(double)); }
         if (cfg->pot_kind == PTMC_POT_ELJ_B || cfg->pot_kind == PTMC_POT_LUT) s->tan = (double*)xcalloc((size_t)n * n, sizeof(double));
-        if (cfg->pot_kind == PTMC_POT_RUNNER) {
-            const size_t ns = (size_t)orc_runner_nsym(H->runner);
+        if (cfg->pot_kind == PTMC_POT_RUNNER || cfg->pot_kind == PTMC_POT_RUNNER2) {
+            const size_t ns = cfg->pot_kind == PTMC_POT_RUNNER ? (size_t)orc_runner_nsym(H->runner) : (size_t)orc_runner2_nsym(H->runner2);
             s->fmat = (double*)xcalloc((size_t)n * n, 8); s->new_f = (double*)xcalloc(n, 8);
             s->g = (double*)xcalloc(n * ns, 8); s->new_g = (double*)xcalloc(n * ns, 8);
             s->en_atom = (double*)xcalloc(n, 8); s->new_en_atom = (double*)xcalloc(n, 8);
@@ -998,6 +1088,7 @@ void orc_destroy(orc_handle* H) {
     free(H->en_min); free(H->en_max); free(H->v_min); free(H->v_max); free(H->en_hist); free(H->ev_hist);
     free(H->tr_index); free(H->tr_de); free(H->tr_acc); free(H->tr_exc);
     orc_runner_free(H->runner);
+    orc_runner2_free(H->runner2);
     free(H->eljb_a); free(H->eljb_b); free(H->lut);
     free(H);
 }
@@ -1026,6 +1117,7 @@ int orc_upload_states(orc_handle* H, const double* pos, const double* box, const
     for (int64_t r = 0; r < H->n_rep; ++r) {
         init_cfgside(c, &H->cs[r]);
         if (c->pot_kind == PTMC_POT_RUNNER) init_cfgside_runner(H->runner, &H->cs[r], n);
+        if (c->pot_kind == PTMC_POT_RUNNER2) init_cfgside_runner2(H->runner2, &H->cs[r], n);
     }
     return 0;
 }
@@ -1184,7 +1276,7 @@ int64_t orc_config_doubles(const orc_handle* H) {
     return 3 * n + 3 + (H->cfg.pot_kind == PTMC_POT_EAM ? 2 * n : 0);
 }
 int orc_export_config(orc_handle* H, int64_t ladder, int32_t slot, double* buf) {
-    if (H->cfg.bc_kind != PTMC_BC_SPHERICAL || H->cfg.pot_kind == PTMC_POT_RUNNER) return PTMC_ERR_ARG;
+    if (H->cfg.bc_kind != PTMC_BC_SPHERICAL || H->cfg.pot_kind == PTMC_POT_RUNNER || H->cfg.pot_kind == PTMC_POT_RUNNER2) return PTMC_ERR_ARG;
     const int n = H->cfg.n_atoms;
     const orc_cfgside* s = H->st[ladder * H->cfg.n_traj + slot].c;
     memcpy(buf, s->pos, sizeof(double) * 3 * n);
@@ -1193,7 +1285,7 @@ int orc_export_config(orc_handle* H, int64_t ladder, int32_t slot, double* buf) 
     return 0;
 }
 int orc_import_config(orc_handle* H, int64_t ladder, int32_t slot, const double* buf) {
-    if (H->cfg.bc_kind != PTMC_BC_SPHERICAL || H->cfg.pot_kind == PTMC_POT_RUNNER) return PTMC_ERR_ARG;
+    if (H->cfg.bc_kind != PTMC_BC_SPHERICAL || H->cfg.pot_kind == PTMC_POT_RUNNER || H->cfg.pot_kind == PTMC_POT_RUNNER2) return PTMC_ERR_ARG;
     const ptmc_config* c = &H->cfg;
     const int n = c->n_atoms;
     orc_cfgside* s = H->st[ladder * c->n_traj + slot].c;
@@ -1253,8 +1345,8 @@ int orc_probe_atom_move(orc_handle* H, int64_t replica, int index1, double* tria
 
 /* RuNNer: g_matrix [atom][n_sym] and per-atom energies of one replica (tests) */
 int orc_get_runner_state(orc_handle* H, int64_t replica, double* g, double* en_atom) {
-    if (!H->runner) return PTMC_ERR_ARG;
-    const size_t ns = (size_t)orc_runner_nsym(H->runner), n = (size_t)H->cfg.n_atoms;
+    if (!H->runner && !H->runner2) return PTMC_ERR_ARG;
+    const size_t ns = H->runner ? (size_t)orc_runner_nsym(H->runner) : (size_t)orc_runner2_nsym(H->runner2), n = (size_t)H->cfg.n_atoms;
     if (g) memcpy(g, H->st[replica].c->g, sizeof(double) * n * ns);
     if (en_atom) memcpy(en_atom, H->st[replica].c->en_atom, sizeof(double) * n);
     return 0;

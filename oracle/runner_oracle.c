@@ -232,90 +232,74 @@ void orc_runner_delta(const orc_runner* r, const double* pos, const double* newp
     }
 }
 
-/* ---- 2-species initial energy (KAT checker only; test/test_potentials.jl:67-87, potentialfile.jl) -------------
- * n1 atoms of type 1 then n2 of type 2; n_rad radial functions -> 2 rows each, n_ang angular -> 3 rows each
- * (SymmFunc.jl:320-470, 511-545); scaling rows: type-1 network rows then type-2 (scaling.data 1..88, 89..176).
- * gmaxmin_a/b: [n_rows][2] {G_max, G_min} for the two element networks. */
-static void runner2_gmatrix(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
-                            const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
-                            double* d2, double* f, double* g /* [atom][row], zeroed */) {
-    const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang;
-    for (int a = 0; a < n; ++a)
-        for (int b = 0; b < n; ++b) {
-            double x = pos[3 * a] - pos[3 * b], y = pos[3 * a + 1] - pos[3 * b + 1], z = pos[3 * a + 2] - pos[3 * b + 2];
-            d2[(size_t)a * n + b] = x * x + y * y + z * z;
-            f[(size_t)a * n + b] = orc_cutoff(sqrt(d2[(size_t)a * n + b]), r_cut);
-        }
-#define GM(tab, row) (1 / ((tab)[2 * (row)] - (tab)[2 * (row) + 1]))
-#define GO(tab, row) (-(tab)[2 * (row) + 1] * GM(tab, row))
-#define TYPE(a) ((a) < n1 ? 0 : 1)
-    for (int k = 0; k < n_rad; ++k) {
-        const int base = 2 * k;
-        for (int a = 0; a < n; ++a)
-            for (int b = a + 1; b < n; ++b) {
-                double fc = f[(size_t)a * n + b];
-                double v = (fc != 0.0 && fc != 1.0) ? fc * exp(-rad_eta[k] * d2[(size_t)a * n + b]) : 0.0;
-                /* row of the NEIGHBOUR's species: Cu-neighbour -> row 1, Zn-neighbour -> row 2 */
-                g[(size_t)a * ns + base + TYPE(b)] += v;
-                g[(size_t)b * ns + base + TYPE(a)] += v;
-            }
-        for (int a = 0; a < n; ++a)
-            for (int s = 0; s < 2; ++s) {
-                const double* tab = a < n1 ? gmaxmin_a : gmaxmin_b;
-                double* gv = &g[(size_t)a * ns + base + s];
-                *gv = *gv * GM(tab, base + s) + GO(tab, base + s);
-            }
-    }
-    for (int k = 0; k < n_ang; ++k) {
-        const int base = 2 * n_rad + 3 * k;
-        for (int a = 0; a < n; ++a)
-            for (int b = a + 1; b < n; ++b)
-                for (int c = b + 1; c < n; ++c) {
-                    double th[3];
-                    double r2ab = d2[(size_t)a * n + b], r2ac = d2[(size_t)a * n + c], r2bc = d2[(size_t)b * n + c];
-                    all_angular_measure(pos + 3 * a, pos + 3 * b, pos + 3 * c, r2ab, r2ac, r2bc, th);
-                    double ep = exp_part6(ang_eta[k], r2ab, r2ac, r2bc, f[(size_t)a * n + b], f[(size_t)a * n + c], f[(size_t)b * n + c]);
-                    /* row = number of Zn atoms among the two neighbours (CuCu 1, CuZn 2, ZnZn 3) */
-                    g[(size_t)a * ns + base + TYPE(b) + TYPE(c)] += ep * theta_part(th[0], ang_lambda[k], ang_zeta[k]);
-                    g[(size_t)b * ns + base + TYPE(a) + TYPE(c)] += ep * theta_part(th[1], ang_lambda[k], ang_zeta[k]);
-                    g[(size_t)c * ns + base + TYPE(a) + TYPE(b)] += ep * theta_part(th[2], ang_lambda[k], ang_zeta[k]);
-                }
-        for (int a = 0; a < n; ++a)
-            for (int s = 0; s < 3; ++s) {
-                const double* tab = a < n1 ? gmaxmin_a : gmaxmin_b;
-                double tpz = pow(2.0, 1 - ang_zeta[k]) * GM(tab, base + s);
-                double* gv = &g[(size_t)a * ns + base + s];
-                *gv = *gv * tpz + GO(tab, base + s);
-            }
-    }
-}
-static double runner2_total(const double* g, int n1, int n2, int ns, int n_layers, const int* nodes, const int* act,
-                            const double* params1, const double* params2) {
-    const int n = n1 + n2;
-    double* e = (double*)xc(n, 8);
-    orc_runner_forward_raw(g, n_layers, nodes, act, params1, n1, e);
-    if (n2) orc_runner_forward_raw(g + (size_t)n1 * ns, n_layers, nodes, act, params2, n2, e + n1);
-    double tot = 0.0;
-    for (int a = 0; a < n; ++a) tot += e[a];
-    free(e);
-    return tot;
-}
-double orc_runner2_energy(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
-                          const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
-                          int n_layers, const int* nodes, const int* act, const double* params1, const double* params2, double* f12_out) {
-    const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang;
-    double* d2 = (double*)xc((size_t)n * n, 8);
-    double* f = (double*)xc((size_t)n * n, 8);
-    double* g = (double*)xc((size_t)n * ns, 8);
-    runner2_gmatrix(pos, n1, n2, n_rad, rad_eta, n_ang, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, d2, f, g);
-    if (f12_out) *f12_out = f[1];
-    const double tot = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
-    free(d2); free(f); free(g);
-    return tot;
-}
+/* ================================================================== two species (RuNNerPotential2Atom) ==
+ * src/EnergyEvaluation.jl:1287-1448,1623-1643,1748-1768,1823-1857; MachineLearningPotential/SymmFunc.jl:53-84,113-171
+ * (RadialType2a / AngularType3a), :320-470 (calc_symm_vals! for two species), :511-545 (total_symm_calc);
+ * DeltaMatrix.jl:23-316 (calc_delta_matrix), :319-632 (calc_swap_matrix).
+ * Atoms 0 .. n1-1 are species 1 ("Cu"), n1 .. n-1 species 2 ("Zn").  g is [atom][n_sym] (= Julia's column-major
+ * (n_sym x N) matrix): radial function k owns rows 2k (species-1 neighbour) and 2k+1 (species-2 neighbour), angular
+ * function k rows 2 n_rad + 3k + {0, 1, 2} = number of species-2 atoms among the two neighbours. */
+typedef struct orc_runner2 {
+    int n_rad, n_ang, n_sym, n1, n2;
+    double* rad_eta;
+    double* rad_norm;   /* [n_rad][4] G_norm: species-1 rows 1,2 then species-2 rows 1,2 (SymmFunc.jl:64-83) */
+    double* rad_off;    /* [n_rad][4] G_offset */
+    double *ang_eta, *ang_lambda, *ang_zeta;
+    double* ang_tpz;    /* [n_ang][6] 2^(1-zeta) * G_norm (:136-158) */
+    double* ang_off;    /* [n_ang][6] */
+    double r_cut, boundary2;
+    int n_layers, n_params;
+    int *nodes, *act;
+    double *params1, *params2;
+} orc_runner2;
 
-/* calc_one_symm_val SymmFunc.jl:229-241 (radial: 0 when the cut-off function is 0 or 1; angular: symmfunc_calc :196-202) */
+orc_runner2* orc_runner2_new(const ptmc_runner2_desc* d) {
+    orc_runner2* r = (orc_runner2*)xc(1, sizeof *r);
+    r->n_rad = d->n_rad; r->n_ang = d->n_ang; r->n_sym = 2 * d->n_rad + 3 * d->n_ang; r->n1 = d->n1; r->n2 = d->n2;
+    r->rad_eta = (double*)xc(d->n_rad, 8); r->rad_norm = (double*)xc(4 * d->n_rad, 8); r->rad_off = (double*)xc(4 * d->n_rad, 8);
+    for (int k = 0; k < d->n_rad; ++k) {
+        r->rad_eta[k] = d->rad_eta[k];
+        for (int q = 0; q < 4; ++q) {                       /* RadialType2a{T}(eta, r_cut, type, G_vals_a, G_vals_b) :64-83 */
+            const double* tab = q < 2 ? d->gmax_gmin_1 : d->gmax_gmin_2;
+            const int row = 2 * k + (q & 1);
+            const double g_norm = 1 / (tab[2 * row] - tab[2 * row + 1]);
+            r->rad_norm[4 * k + q] = g_norm;
+            r->rad_off[4 * k + q] = -tab[2 * row + 1] * g_norm;
+        }
+    }
+    r->ang_eta = (double*)xc(d->n_ang, 8); r->ang_lambda = (double*)xc(d->n_ang, 8); r->ang_zeta = (double*)xc(d->n_ang, 8);
+    r->ang_tpz = (double*)xc(6 * d->n_ang, 8); r->ang_off = (double*)xc(6 * d->n_ang, 8);
+    for (int k = 0; k < d->n_ang; ++k) {
+        r->ang_eta[k] = d->ang_eta[k]; r->ang_lambda[k] = d->ang_lambda[k]; r->ang_zeta[k] = d->ang_zeta[k];
+        for (int q = 0; q < 6; ++q) {                       /* AngularType3a{T}(..., G_valsa, G_valsb) :133-171 */
+            const double* tab = q < 3 ? d->gmax_gmin_1 : d->gmax_gmin_2;
+            const int row = 2 * d->n_rad + 3 * k + q % 3;
+            const double g_norm = 1 / (tab[2 * row] - tab[2 * row + 1]);
+            r->ang_off[6 * k + q] = -tab[2 * row + 1] * g_norm;
+            r->ang_tpz[6 * k + q] = pow(2.0, 1 - d->ang_zeta[k]) * g_norm;
+        }
+    }
+    r->r_cut = d->r_cut; r->boundary2 = d->boundary2;
+    r->n_layers = d->n_layers; r->n_params = d->n_params;
+    r->nodes = (int*)xc(d->n_layers, sizeof(int)); r->act = (int*)xc(d->n_layers, sizeof(int));
+    for (int l = 0; l < d->n_layers; ++l) { r->nodes[l] = d->num_nodes[l]; r->act[l] = d->activation[l]; }
+    r->params1 = (double*)xc(d->n_params, 8); r->params2 = (double*)xc(d->n_params, 8);
+    memcpy(r->params1, d->params_1, 8 * (size_t)d->n_params);
+    memcpy(r->params2, d->params_2, 8 * (size_t)d->n_params);
+    return r;
+}
+void orc_runner2_free(orc_runner2* r) {
+    if (!r) return;
+    free(r->rad_eta); free(r->rad_norm); free(r->rad_off); free(r->ang_eta); free(r->ang_lambda); free(r->ang_zeta);
+    free(r->ang_tpz); free(r->ang_off); free(r->nodes); free(r->act); free(r->params1); free(r->params2); free(r);
+}
+int orc_runner2_nsym(const orc_runner2* r) { return r->n_sym; }
+int orc_runner2_n1(const orc_runner2* r) { return r->n1; }
+double orc_runner2_rcut(const orc_runner2* r) { return r->r_cut; }
+
+/* calc_one_symm_val(r2_ij, fc_ij, eta) SymmFunc.jl:229-231: 0 when the cut-off function is 0 or 1 */
 static double one_radial(double r2, double fc, double eta) { return (fc != 0.0 && fc != 1.0) ? fc * exp(-eta * r2) : 0.0; }
+/* calc_one_symm_val(positions..., eta, lambda, zeta) :233-241 -> symmfunc_calc :196-202: exp_part * theta_part(theta) */
 static void one_angular(const double* pos, const double* d2, const double* f, int n, int a, int b, int c, double eta, double lambda, double zeta, double gv[3]) {
     double th[3];
     const double r2ab = d2[(size_t)a * n + b], r2ac = d2[(size_t)a * n + c], r2bc = d2[(size_t)b * n + c];
@@ -323,56 +307,163 @@ static void one_angular(const double* pos, const double* d2, const double* f, in
     const double ep = exp_part6(eta, r2ab, r2ac, r2bc, f[(size_t)a * n + b], f[(size_t)a * n + c], f[(size_t)b * n + c]);
     for (int m = 0; m < 3; ++m) gv[m] = ep * theta_part(th[m], lambda, zeta);
 }
-/* ---- 2-species atom swap (KAT checker only; test/test_states.jl:166-175): energy change of exchanging the positions of atom a1
- * (species 1) and a2 (species 2) through calc_swap_matrix (MachineLearningPotential/DeltaMatrix.jl:319-632) as swap_energy_update uses
- * it (src/EnergyEvaluation.jl:1381-1448).  Rows are 0-based here: radial row = species of the neighbour, angular row = number of
- * species-2 atoms among the two neighbours; the statements keep the reference's order. */
-double orc_runner2_swap_delta(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
-                              const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
-                              int n_layers, const int* nodes, const int* act, const double* params1, const double* params2, int a1, int a2) {
-    const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang;
-    double* d2 = (double*)xc((size_t)n * n, 8);
-    double* f = (double*)xc((size_t)n * n, 8);
-    double* g = (double*)xc((size_t)n * ns, 8);
-    double* dg = (double*)xc((size_t)n * ns, 8);
-    runner2_gmatrix(pos, n1, n2, n_rad, rad_eta, n_ang, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, d2, f, g);
-    const double e_old = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
-#define DG(row, atom) dg[(size_t)(atom) * ns + base + (row)]
-    for (int k = 0; k < n_rad; ++k) {                                           /* :322-371 */
+#define G2(atom, row) g[(size_t)(atom) * ns + (row)]
+/* rows 1:n1 / (n1+1):N of a function's block are scaled by the species' factors: row q of species s uses entry s * nrow + q */
+static void scale_block(double* g, int ns, int n1, int n, int base, int nrow, const double* mul, const double* add) {
+    for (int q = 0; q < nrow; ++q) for (int a = 0; a < n1; ++a) G2(a, base + q) = G2(a, base + q) * mul[q] + (add ? add[q] : 0.0);
+    for (int q = 0; q < nrow; ++q) for (int a = n1; a < n; ++a) G2(a, base + q) = G2(a, base + q) * mul[nrow + q] + (add ? add[nrow + q] : 0.0);
+}
+static void scale_block_mul(double* g, int ns, int n1, int n, int base, int nrow, const double* mul) {
+    for (int q = 0; q < nrow; ++q) for (int a = 0; a < n1; ++a) G2(a, base + q) = G2(a, base + q) * mul[q];
+    for (int q = 0; q < nrow; ++q) for (int a = n1; a < n; ++a) G2(a, base + q) = G2(a, base + q) * mul[nrow + q];
+}
+
+/* total_symm_calc (two species) SymmFunc.jl:511-545 with calc_symm_vals! :320-367 (radial: CuCu, ZnZn, CuZn) and :369-470
+ * (angular: CuCuCu, ZnZnZn, CuCuZn, CuZnZn); g [atom][n_sym] is overwritten. */
+void orc_runner2_init_g(const orc_runner2* r, const double* pos, const double* d2, const double* f, int n, double* g) {
+    const int ns = r->n_sym, n1 = r->n1;
+    memset(g, 0, 8 * (size_t)n * ns);
+    for (int k = 0; k < r->n_rad; ++k) {
         const int base = 2 * k;
-        const double eta = rad_eta[k];
+        const double eta = r->rad_eta[k];
+        for (int a = 0; a < n1; ++a)
+            for (int b = a + 1; b < n1; ++b) { const double v = one_radial(d2[(size_t)a * n + b], f[(size_t)a * n + b], eta); G2(a, base) += v; G2(b, base) += v; }
+        for (int a = n1; a < n; ++a)
+            for (int b = a + 1; b < n; ++b) { const double v = one_radial(d2[(size_t)a * n + b], f[(size_t)a * n + b], eta); G2(a, base + 1) += v; G2(b, base + 1) += v; }
+        for (int a = 0; a < n1; ++a)
+            for (int b = n1; b < n; ++b) { const double v = one_radial(d2[(size_t)a * n + b], f[(size_t)a * n + b], eta); G2(a, base + 1) += v; G2(b, base) += v; }
+        scale_block(g, ns, n1, n, base, 2, r->rad_norm + 4 * k, r->rad_off + 4 * k);
+    }
+    for (int k = 0; k < r->n_ang; ++k) {
+        const int base = 2 * r->n_rad + 3 * k;
+        const double eta = r->ang_eta[k], la = r->ang_lambda[k], ze = r->ang_zeta[k];
+        double gv[3];
+        for (int a = 0; a < n1; ++a) for (int b = a + 1; b < n1; ++b) for (int c = b + 1; c < n1; ++c) {
+            one_angular(pos, d2, f, n, a, b, c, eta, la, ze, gv); G2(a, base) += gv[0]; G2(b, base) += gv[1]; G2(c, base) += gv[2]; }
+        for (int a = n1; a < n; ++a) for (int b = a + 1; b < n; ++b) for (int c = b + 1; c < n; ++c) {
+            one_angular(pos, d2, f, n, a, b, c, eta, la, ze, gv); G2(a, base + 2) += gv[0]; G2(b, base + 2) += gv[1]; G2(c, base + 2) += gv[2]; }
+        for (int a = 0; a < n1; ++a) for (int b = a + 1; b < n1; ++b) for (int c = n1; c < n; ++c) {
+            one_angular(pos, d2, f, n, a, b, c, eta, la, ze, gv); G2(a, base + 1) += gv[0]; G2(b, base + 1) += gv[1]; G2(c, base) += gv[2]; }
+        for (int a = 0; a < n1; ++a) for (int b = n1; b < n; ++b) for (int c = b + 1; c < n; ++c) {
+            one_angular(pos, d2, f, n, a, b, c, eta, la, ze, gv); G2(a, base + 2) += gv[0]; G2(b, base + 1) += gv[1]; G2(c, base + 1) += gv[2]; }
+        scale_block(g, ns, n1, n, base, 3, r->ang_tpz + 6 * k, r->ang_off + 6 * k);
+    }
+}
+
+/* forward_pass on the two species' columns, initialise_energy :1748-1768 / calc_new_runner_energy! :1418-1433 */
+void orc_runner2_forward(const orc_runner2* r, const double* g, int n, double* eatom) {
+    orc_runner_forward_raw(g, r->n_layers, r->nodes, r->act, r->params1, r->n1, eatom);
+    if (r->n2 != 0) orc_runner_forward_raw(g + (size_t)r->n1 * r->n_sym, r->n_layers, r->nodes, r->act, r->params2, n - r->n1, eatom + r->n1);
+}
+
+/* new_angular_symm_vals DeltaMatrix.jl:31-62: theta_part(new) * exp_new - theta_part(old) * exp_old for the centres i, j, k */
+static void new_angular(const double* trial, const double* pos, const double* d2, const double* nd2, const double* f, const double* nf,
+                        int n, int i, int j, int c, double eta, double la, double ze, double gv[3]) {
+    double thn[3], tho[3];
+    const double r2jk = d2[(size_t)j * n + c];
+    all_angular_measure(trial, pos + 3 * j, pos + 3 * c, nd2[j], nd2[c], r2jk, thn);
+    all_angular_measure(pos + 3 * i, pos + 3 * j, pos + 3 * c, d2[(size_t)i * n + j], d2[(size_t)i * n + c], r2jk, tho);
+    const double en = exp_part6(eta, nd2[j], nd2[c], r2jk, nf[j], nf[c], f[(size_t)j * n + c]);
+    const double eo = exp_part6(eta, d2[(size_t)i * n + j], d2[(size_t)i * n + c], r2jk, f[(size_t)i * n + j], f[(size_t)i * n + c], f[(size_t)j * n + c]);
+    for (int m = 0; m < 3; ++m) gv[m] = theta_part(thn[m], la, ze) * en - theta_part(tho[m], la, ze) * eo;
+}
+
+/* calc_delta_matrix DeltaMatrix.jl:256-316: g (zero-filled by the caller, EnergyEvaluation.jl:1361) receives the change of
+ * every symmetry value when atom i moves to `trial`. */
+void orc_runner2_delta(const orc_runner2* r, const double* pos, const double* trial, const double* d2, const double* nd2,
+                       const double* f, const double* nf, int i, int n, double* g) {
+    const int ns = r->n_sym, n1 = r->n1;
+    const int ind = i < n1 ? 0 : 1;
+    for (int k = 0; k < r->n_rad; ++k) {                     /* calc_delta_symm_val! (radial) :69-122 */
+        const int base = 2 * k;
+        const double eta = r->rad_eta[k];
+        for (int b = 0; b < n1; ++b) {
+            if (b == i) continue;
+            /* new_radial_symm_val! :23-25 = exponential_part(eta, new) - exponential_part(eta, old) */
+            const double gn = exp(-eta * nd2[b]) * nf[b] - exp(-eta * d2[(size_t)i * n + b]) * f[(size_t)i * n + b];
+            G2(i, base) += gn;
+            G2(b, base + ind) = gn;                          /* sic: assignment (:97); the entry is zero before */
+        }
+        for (int b = n1; b < n; ++b) {
+            if (b == i) continue;
+            const double gn = exp(-eta * nd2[b]) * nf[b] - exp(-eta * d2[(size_t)i * n + b]) * f[(size_t)i * n + b];
+            G2(i, base + 1) += gn;
+            G2(b, base + ind) += gn;
+        }
+        scale_block_mul(g, ns, n1, n, base, 2, r->rad_norm + 4 * k);
+    }
+    for (int k = 0; k < r->n_ang; ++k) {                     /* calc_delta_symm_val! (angular) :124-250 */
+        const int base = 2 * r->n_rad + 3 * k;
+        const double eta = r->ang_eta[k], la = r->ang_lambda[k], ze = r->ang_zeta[k];
+        const int iv0 = ind, iv1 = 1 + ind, iv2 = 1 + ind, iv3 = ind;      /* i_val = (1, 2, 2, 1) (+1 for a species-2 mover) */
+        double gv[3];
+        for (int j = 0; j < n1; ++j) {
+            if (j == i) continue;
+            for (int c = j + 1; c < n1; ++c) {
+                if (c == i) continue;
+                new_angular(trial, pos, d2, nd2, f, nf, n, i, j, c, eta, la, ze, gv);
+                G2(i, base) += gv[0]; G2(j, base + iv0) += gv[1]; G2(c, base + iv0) += gv[2];
+            }
+        }
+        for (int j = n1; j < n; ++j) {
+            if (j == i) continue;
+            for (int c = j + 1; c < n; ++c) {
+                if (c == i) continue;
+                new_angular(trial, pos, d2, nd2, f, nf, n, i, j, c, eta, la, ze, gv);
+                G2(i, base + 2) += gv[0]; G2(j, base + iv1) += gv[1]; G2(c, base + iv1) += gv[2];
+            }
+        }
+        for (int j = 0; j < n1; ++j) {
+            if (j == i) continue;
+            for (int c = n1; c < n; ++c) {
+                if (c == i) continue;
+                new_angular(trial, pos, d2, nd2, f, nf, n, i, j, c, eta, la, ze, gv);
+                G2(i, base + 1) += gv[0]; G2(j, base + iv2) += gv[1]; G2(c, base + iv3) += gv[2];
+            }
+        }
+        scale_block_mul(g, ns, n1, n, base, 3, r->ang_tpz + 6 * k);
+    }
+}
+
+/* calc_swap_matrix DeltaMatrix.jl:583-632 with calc_swap_symm_val :319-371 (radial) and :373-580 (angular): g (zero-filled by the
+ * caller, EnergyEvaluation.jl:1392) receives the change of every symmetry value when atom a1 (species 1) and atom a2 (species 2)
+ * exchange their positions. */
+void orc_runner2_swap(const orc_runner2* r, const double* pos, const double* d2, const double* f, int a1, int a2, int n, double* g) {
+    const int ns = r->n_sym, n1 = r->n1;
+    for (int k = 0; k < r->n_rad; ++k) {
+        const int base = 2 * k;
+        const double eta = r->rad_eta[k];
         for (int x = 0; x < n1; ++x) {
             if (x == a1) continue;
             const double g1 = one_radial(d2[(size_t)a1 * n + x], f[(size_t)a1 * n + x], eta);
             const double g2 = one_radial(d2[(size_t)a2 * n + x], f[(size_t)a2 * n + x], eta);
-            DG(0, x) += g2 - g1; DG(1, x) += g1 - g2;
-            DG(0, a1) += g2 - g1;
-            DG(0, a2) += g1 - g2;
+            G2(x, base) += g2 - g1; G2(x, base + 1) += g1 - g2;
+            G2(a1, base) += g2 - g1;
+            G2(a2, base) += g1 - g2;
         }
         for (int x = n1; x < n; ++x) {
             if (x == a2) continue;
             const double g1 = one_radial(d2[(size_t)a1 * n + x], f[(size_t)a1 * n + x], eta);
             const double g2 = one_radial(d2[(size_t)a2 * n + x], f[(size_t)a2 * n + x], eta);
-            DG(0, x) += g2 - g1; DG(1, x) += g1 - g2;
-            DG(1, a1) += g2 - g1;
-            DG(1, a2) += g1 - g2;
+            G2(x, base) += g2 - g1; G2(x, base + 1) += g1 - g2;
+            G2(a1, base + 1) += g2 - g1;
+            G2(a2, base + 1) += g1 - g2;
         }
-        for (int a = 0; a < n; ++a)
-            for (int s_ = 0; s_ < 2; ++s_) DG(s_, a) *= GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
+        scale_block_mul(g, ns, n1, n, base, 2, r->rad_norm + 4 * k);
     }
-    for (int k = 0; k < n_ang; ++k) {                                           /* :373-580 */
-        const int base = 2 * n_rad + 3 * k;
-        const double eta = ang_eta[k], la = ang_lambda[k], ze = ang_zeta[k];
+    for (int k = 0; k < r->n_ang; ++k) {
+        const int base = 2 * r->n_rad + 3 * k;
+        const double eta = r->ang_eta[k], la = r->ang_lambda[k], ze = r->ang_zeta[k];
         double v1[3], v2[3];
-        for (int j = 0; j < n1; ++j) {                                          /* both neighbours of species 1 */
+        for (int j = 0; j < n1; ++j) {                                          /* both neighbours of species 1 :377-424 */
             if (j == a1) continue;
             for (int c = j + 1; c < n1; ++c) {
                 if (c == a1) continue;
                 one_angular(pos, d2, f, n, a1, j, c, eta, la, ze, v1);
                 one_angular(pos, d2, f, n, a2, j, c, eta, la, ze, v2);
-                DG(0, a1) += v2[0] - v1[0]; DG(0, a2) += v1[0] - v2[0];
-                DG(0, j) += v2[1] - v1[1]; DG(0, c) += v2[2] - v1[2];
-                DG(1, j) += v1[1] - v2[1]; DG(1, c) += v1[2] - v2[2];
+                G2(a1, base) += v2[0] - v1[0]; G2(a2, base) += v1[0] - v2[0];
+                G2(j, base) += v2[1] - v1[1]; G2(c, base) += v2[2] - v1[2];
+                G2(j, base + 1) += v1[1] - v2[1]; G2(c, base + 1) += v1[2] - v2[2];
             }
         }
         for (int j = n1; j < n; ++j) {                                          /* both neighbours of species 2 */
@@ -381,9 +472,9 @@ double orc_runner2_swap_delta(const double* pos, int n1, int n2, int n_rad, cons
                 if (c == a2) continue;
                 one_angular(pos, d2, f, n, a1, j, c, eta, la, ze, v1);
                 one_angular(pos, d2, f, n, a2, j, c, eta, la, ze, v2);
-                DG(2, a1) += v2[0] - v1[0]; DG(2, a2) += v1[0] - v2[0];
-                DG(1, j) += v2[1] - v1[1]; DG(1, c) += v2[2] - v1[2];
-                DG(2, j) += v1[1] - v2[1]; DG(2, c) += v1[2] - v2[2];
+                G2(a1, base + 2) += v2[0] - v1[0]; G2(a2, base + 2) += v1[0] - v2[0];
+                G2(j, base + 1) += v2[1] - v1[1]; G2(c, base + 1) += v2[2] - v1[2];
+                G2(j, base + 2) += v1[1] - v2[1]; G2(c, base + 2) += v1[2] - v2[2];
             }
         }
         for (int j = 0; j < n1; ++j) {                                          /* one neighbour of each species */
@@ -392,101 +483,74 @@ double orc_runner2_swap_delta(const double* pos, int n1, int n2, int n_rad, cons
                 if (c == a2) continue;
                 one_angular(pos, d2, f, n, a1, j, c, eta, la, ze, v1);
                 one_angular(pos, d2, f, n, a2, j, c, eta, la, ze, v2);
-                DG(1, a1) += v2[0] - v1[0]; DG(1, a2) += v1[0] - v2[0];
-                DG(1, j) += v2[1] - v1[1]; DG(0, c) += v2[2] - v1[2];
-                DG(2, j) += v1[1] - v2[1]; DG(1, c) += v1[2] - v2[2];
+                G2(a1, base + 1) += v2[0] - v1[0]; G2(a2, base + 1) += v1[0] - v2[0];
+                G2(j, base + 1) += v2[1] - v1[1]; G2(c, base) += v2[2] - v1[2];
+                G2(j, base + 2) += v1[1] - v2[1]; G2(c, base + 1) += v1[2] - v2[2];
             }
         }
         for (int c = 0; c < n1; ++c) {                                          /* triples that hold both swapped atoms */
             if (c == a1) continue;
             one_angular(pos, d2, f, n, a1, a2, c, eta, la, ze, v1);
-            DG(1, a1) -= v1[0]; DG(0, a2) += v1[0];
-            DG(0, a2) -= v1[1]; DG(1, a1) += v1[1];
+            G2(a1, base + 1) -= v1[0]; G2(a2, base) += v1[0];
+            G2(a2, base) -= v1[1]; G2(a1, base + 1) += v1[1];
         }
         for (int c = n1; c < n; ++c) {
             if (c == a2) continue;
             one_angular(pos, d2, f, n, a1, a2, c, eta, la, ze, v1);
-            DG(2, a1) -= v1[0]; DG(1, a2) += v1[0];
-            DG(1, a2) -= v1[1]; DG(2, a1) += v1[1];
+            G2(a1, base + 2) -= v1[0]; G2(a2, base + 1) += v1[0];
+            G2(a2, base + 1) -= v1[1]; G2(a1, base + 2) += v1[1];
         }
-        for (int a = 0; a < n; ++a)
-            for (int s_ = 0; s_ < 3; ++s_) DG(s_, a) *= pow(2.0, 1 - ze) * GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
+        scale_block_mul(g, ns, n1, n, base, 3, r->ang_tpz + 6 * k);
     }
-#undef DG
-    for (size_t q = 0; q < (size_t)n * ns; ++q) g[q] += dg[q];
-    const double e_new = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
-    free(d2); free(f); free(g); free(dg);
-    return e_new - e_old;
 }
+#undef G2
 
-/* ---- 2-species atom move (KAT checker only; test/test_states.jl:148-159): energy change of moving atom `atom` to `trial`,
- * through calc_delta_matrix (MachineLearningPotential/DeltaMatrix.jl:69-316) as get_new_state_vars! /
- * calc_new_runner_energy! use it (src/EnergyEvaluation.jl:1347-1418): new_g_matrix = g_matrix + delta, two forward passes. */
-double orc_runner2_move_delta(const double* pos, int n1, int n2, int n_rad, const double* rad_eta, int n_ang, const double* ang_eta,
-                              const double* ang_lambda, const double* ang_zeta, double r_cut, const double* gmaxmin_a, const double* gmaxmin_b,
-                              int n_layers, const int* nodes, const int* act, const double* params1, const double* params2,
-                              int atom, const double* trial) {
-    const int n = n1 + n2, ns = 2 * n_rad + 3 * n_ang, i = atom;
+/* ---- known-answer checkers (tests/test_runner_oracle.py): the engine functions above on one configuration -----------------
+ * what = 0: initial energy (test/test_potentials.jl:67-87); 1: energy change of moving atom `a` to `trial`
+ * (test/test_states.jl:148-159, get_new_state_vars! + calc_new_runner_energy! EnergyEvaluation.jl:1347-1433);
+ * 2: energy change of swapping atoms a and b (test/test_states.jl:166-175, swap_energy_update :1437-1448). */
+double orc_runner2_check(const ptmc_runner2_desc* d, const double* pos, int what, int a, int b, const double* trial, double* f12_out) {
+    orc_runner2* r = orc_runner2_new(d);
+    const int n = r->n1 + r->n2, ns = r->n_sym;
     double* d2 = (double*)xc((size_t)n * n, 8);
     double* f = (double*)xc((size_t)n * n, 8);
     double* g = (double*)xc((size_t)n * ns, 8);
     double* dg = (double*)xc((size_t)n * ns, 8);
-    double* nd2 = (double*)xc(n, 8);
-    double* nf = (double*)xc(n, 8);
-    runner2_gmatrix(pos, n1, n2, n_rad, rad_eta, n_ang, ang_eta, ang_lambda, ang_zeta, r_cut, gmaxmin_a, gmaxmin_b, d2, f, g);
-    const double e_old = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
-    for (int b = 0; b < n; ++b) {
-        double x = trial[0] - pos[3 * b], y = trial[1] - pos[3 * b + 1], z = trial[2] - pos[3 * b + 2];
-        nd2[b] = x * x + y * y + z * z;
-        nf[b] = orc_cutoff(sqrt(nd2[b]), r_cut);            /* new_f_vec = cutoff_function.(sqrt.(new_dist2_vec), r_cut) :1357-1359 */
-    }
-    nd2[i] = 0.0; nf[i] = 1.0;
-    const int ti = TYPE(i);
-    /* radial rows, calc_delta_symm_val! :69-122: the centre gains in the row of the neighbour's species, the neighbour in the row of
-     * the centre's species; new_radial_symm_val! :23-25 = exponential_part(new) - exponential_part(old) */
-    for (int k = 0; k < n_rad; ++k) {
-        const int base = 2 * k;
-        for (int b = 0; b < n; ++b) {                       /* Cu neighbours first, then Zn (loop order of the reference) */
-            if (b == i) continue;
-            const double gn = exp(-rad_eta[k] * nd2[b]) * nf[b] - exp(-rad_eta[k] * d2[(size_t)i * n + b]) * f[(size_t)i * n + b];
-            dg[(size_t)i * ns + base + TYPE(b)] += gn;
-            dg[(size_t)b * ns + base + ti] += gn;
+    double* e = (double*)xc(n, 8);
+    for (int p = 0; p < n; ++p)
+        for (int q = 0; q < n; ++q) {
+            const double x = pos[3 * p] - pos[3 * q], y = pos[3 * p + 1] - pos[3 * q + 1], z = pos[3 * p + 2] - pos[3 * q + 2];
+            d2[(size_t)p * n + q] = x * x + y * y + z * z;
         }
-        for (int a = 0; a < n; ++a)
-            for (int s_ = 0; s_ < 2; ++s_) dg[(size_t)a * ns + base + s_] *= GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
-    }
-    /* angular rows, calc_delta_symm_val! :124-250: pairs (j, k) of the other atoms in the order CuCu, ZnZn, CuZn; centre i gains
-     * in row (#Zn among j, k), j in row (#Zn among i, k), k in row (#Zn among i, j); new_angular_symm_vals :31-62 */
-    for (int k = 0; k < n_ang; ++k) {
-        const int base = 2 * n_rad + 3 * k;
-        for (int cls = 0; cls < 3; ++cls) {
-            const int j0 = cls == 1 ? n1 : 0, j1 = cls == 1 ? n : n1;
-            for (int j = j0; j < j1; ++j) {
-                if (j == i) continue;
-                const int k0 = cls == 2 ? n1 : j + 1, k1 = cls == 0 ? n1 : n;
-                for (int c = k0; c < k1; ++c) {
-                    if (c == i) continue;
-                    double thn[3], tho[3];
-                    const double r2jk = d2[(size_t)j * n + c];
-                    all_angular_measure(trial, pos + 3 * j, pos + 3 * c, nd2[j], nd2[c], r2jk, thn);
-                    all_angular_measure(pos + 3 * i, pos + 3 * j, pos + 3 * c, d2[(size_t)i * n + j], d2[(size_t)i * n + c], r2jk, tho);
-                    const double en = exp_part6(ang_eta[k], nd2[j], nd2[c], r2jk, nf[j], nf[c], f[(size_t)j * n + c]);
-                    const double eo = exp_part6(ang_eta[k], d2[(size_t)i * n + j], d2[(size_t)i * n + c], r2jk, f[(size_t)i * n + j], f[(size_t)i * n + c], f[(size_t)j * n + c]);
-                    double gv[3];
-                    for (int m = 0; m < 3; ++m)
-                        gv[m] = theta_part(thn[m], ang_lambda[k], ang_zeta[k]) * en - theta_part(tho[m], ang_lambda[k], ang_zeta[k]) * eo;
-                    dg[(size_t)i * ns + base + TYPE(j) + TYPE(c)] += gv[0];
-                    dg[(size_t)j * ns + base + ti + TYPE(c)] += gv[1];
-                    dg[(size_t)c * ns + base + ti + TYPE(j)] += gv[2];
-                }
+    for (size_t k = 0; k < (size_t)n * n; ++k) f[k] = orc_cutoff(sqrt(d2[k]), r->r_cut);   /* set_variables :1838-1839 */
+    if (f12_out) *f12_out = f[1];
+    orc_runner2_init_g(r, pos, d2, f, n, g);
+    orc_runner2_forward(r, g, n, e);
+    double e_old = 0.0;
+    for (int p = 0; p < n; ++p) e_old += e[p];
+    double out = e_old;
+    if (what != 0) {
+        if (what == 1) {
+            double* nd2 = (double*)xc(n, 8);
+            double* nf = (double*)xc(n, 8);
+            for (int q = 0; q < n; ++q) {
+                const double x = trial[0] - pos[3 * q], y = trial[1] - pos[3 * q + 1], z = trial[2] - pos[3 * q + 2];
+                nd2[q] = x * x + y * y + z * z;
             }
+            nd2[a] = 0.0;
+            for (int q = 0; q < n; ++q) nf[q] = orc_cutoff(sqrt(nd2[q]), r->r_cut);
+            orc_runner2_delta(r, pos, trial, d2, nd2, f, nf, a, n, dg);
+            free(nd2); free(nf);
+        } else {
+            orc_runner2_swap(r, pos, d2, f, a, b, n, dg);
         }
-        for (int a = 0; a < n; ++a)
-            for (int s_ = 0; s_ < 3; ++s_)
-                dg[(size_t)a * ns + base + s_] *= pow(2.0, 1 - ang_zeta[k]) * GM(a < n1 ? gmaxmin_a : gmaxmin_b, base + s_);
+        for (size_t q = 0; q < (size_t)n * ns; ++q) g[q] = g[q] + dg[q];        /* new_g_matrix = g_matrix .+ new_g_matrix */
+        orc_runner2_forward(r, g, n, e);
+        double e_new = 0.0;
+        for (int p = 0; p < n; ++p) e_new += e[p];
+        out = e_new - e_old;
     }
-    for (size_t q = 0; q < (size_t)n * ns; ++q) g[q] += dg[q];          /* new_g_matrix = g_matrix .+ delta :1379-1380 */
-    const double e_new = runner2_total(g, n1, n2, ns, n_layers, nodes, act, params1, params2);
-    free(d2); free(f); free(g); free(dg); free(nd2); free(nf);
-    return e_new - e_old;
+    free(d2); free(f); free(g); free(dg); free(e);
+    orc_runner2_free(r);
+    return out;
 }

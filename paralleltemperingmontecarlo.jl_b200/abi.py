@@ -10,13 +10,13 @@ import pathlib
 PKG_DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libptmc_b200.so"
 
-PTMC_ABI_VERSION = 3
+PTMC_ABI_VERSION = 4
 PTMC_MAX_COEFF = 16
 PTMC_NCOUNT = 10
 
-POT_ELJ, POT_ELJ_EVEN, POT_EAM, POT_RUNNER, POT_ELJ_B, POT_LUT = 0, 1, 2, 3, 4, 5
+POT_ELJ, POT_ELJ_EVEN, POT_EAM, POT_RUNNER, POT_ELJ_B, POT_LUT, POT_RUNNER2 = 0, 1, 2, 3, 4, 5, 6
 BC_SPHERICAL, BC_CUBIC, BC_RHOMBIC, BC_RECTANGULAR = 0, 1, 2, 3
-ENS_NVT, ENS_NPT = 0, 1
+ENS_NVT, ENS_NPT, ENS_NNVT = 0, 1, 2
 RNG_XOSHIRO, RNG_REPLAY, RNG_BATCH8 = 0, 1, 2
 RNG_LANES = 8
 
@@ -40,6 +40,17 @@ class RunnerDesc(C.Structure):
     ]
 
 
+class Runner2Desc(C.Structure):
+    _fields_ = [
+        ("n_rad", C.c_int32), ("n_ang", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32),
+        ("rad_eta", _dp), ("ang_eta", _dp), ("ang_lambda", _dp), ("ang_zeta", _dp),
+        ("gmax_gmin_1", _dp), ("gmax_gmin_2", _dp),
+        ("r_cut", C.c_double), ("boundary2", C.c_double),
+        ("n_layers", C.c_int32), ("num_nodes", _ip), ("activation", _ip),
+        ("n_params", C.c_int32), ("params_1", _dp), ("params_2", _dp),
+    ]
+
+
 class Config(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("device", C.c_int32),
@@ -60,6 +71,7 @@ class Config(C.Structure):
         ("lut_table", _dp), ("lut_l_dist", C.c_int32), ("lut_l_angle", C.c_int32),
         ("lut_start_dist", C.c_double), ("lut_d_dist", C.c_double), ("lut_start_angle", C.c_double), ("lut_d_angle", C.c_double),
         ("lut_c6coeff", C.c_double),
+        ("n_atom_swaps", C.c_int32), ("runner2", C.POINTER(Runner2Desc)),
     ]
 
 

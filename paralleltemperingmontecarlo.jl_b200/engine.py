@@ -39,6 +39,49 @@ class RunnerParams:
 
 
 @dataclass
+class Runner2Params:
+    """RuNNerPotential2Atom payload (src/EnergyEvaluation.jl:1287-1314): gmax_gmin_1 / _2 are [2 n_rad + 3 n_ang][2] {G_max, G_min}
+    in g-matrix row order for species 1 / 2."""
+    n1: int
+    n2: int
+    rad_eta: np.ndarray
+    ang_eta: np.ndarray
+    ang_lambda: np.ndarray
+    ang_zeta: np.ndarray
+    gmax_gmin_1: np.ndarray
+    gmax_gmin_2: np.ndarray
+    r_cut: float
+    boundary2: float
+    num_nodes: np.ndarray
+    activation: np.ndarray
+    params_1: np.ndarray
+    params_2: np.ndarray
+
+    @property
+    def n_sym(self) -> int:
+        return 2 * len(self.rad_eta) + 3 * len(self.ang_eta)
+
+    def to_c(self, keep: list) -> "abi.Runner2Desc":
+        d = abi.Runner2Desc()
+        arrs = {}
+        for name, dt in (("rad_eta", np.float64), ("ang_eta", np.float64), ("ang_lambda", np.float64), ("ang_zeta", np.float64),
+                         ("gmax_gmin_1", np.float64), ("gmax_gmin_2", np.float64), ("num_nodes", np.int32), ("activation", np.int32),
+                         ("params_1", np.float64), ("params_2", np.float64)):
+            a = np.ascontiguousarray(getattr(self, name), dtype=dt)
+            arrs[name] = a
+            setattr(d, name, a.ctypes.data_as(C.POINTER(C.c_double) if dt == np.float64 else C.POINTER(C.c_int32)))
+        d.n_rad, d.n_ang, d.n1, d.n2 = len(arrs["rad_eta"]), len(arrs["ang_eta"]), int(self.n1), int(self.n2)
+        if arrs["gmax_gmin_1"].shape != (self.n_sym, 2) or arrs["gmax_gmin_2"].shape != (self.n_sym, 2):
+            raise ValueError("gmax_gmin_1 / gmax_gmin_2 must be [2 n_rad + 3 n_ang][2]")
+        if arrs["params_1"].shape != arrs["params_2"].shape:
+            raise ValueError("the two networks must share one topology")
+        d.r_cut, d.boundary2 = float(self.r_cut), float(self.boundary2)
+        d.n_layers, d.n_params = len(arrs["num_nodes"]), len(arrs["params_1"])
+        keep += [arrs, d]
+        return d
+
+
+@dataclass
 class SweepConfig:
     n_ladders: int
     n_traj: int
@@ -50,6 +93,8 @@ class SweepConfig:
     eljb_ab: tuple | None = None       # ELJPotentialB: (coeff_a, coeff_b); coeff_c in `coeff`
     lut: object | None = None           # LookupTablePotential (host.LookupTablePotential)
     runner: RunnerParams | None = None
+    runner2: Runner2Params | None = None
+    n_atom_swaps: int = 0               # NNVT.n_atom_swaps
     bc_kind: int = abi.BC_SPHERICAL
     ensemble: int = abi.ENS_NVT
     n_atom_moves: int | None = None
@@ -69,7 +114,8 @@ class SweepConfig:
 
     @property
     def n_steps(self) -> int:
-        return self.atom_moves + (self.n_volume_moves if self.ensemble == abi.ENS_NPT else 0)
+        return (self.atom_moves + (self.n_volume_moves if self.ensemble == abi.ENS_NPT else 0)
+                + (self.n_atom_swaps if self.ensemble == abi.ENS_NNVT else 0))
 
     @property
     def atom_moves(self) -> int:
@@ -136,6 +182,9 @@ class SweepConfig:
             d.n_params = len(arrs["params"])
             self._keep += [arrs, d]
             c.runner = C.pointer(d)
+        if self.runner2 is not None:
+            c.runner2 = C.pointer(self.runner2.to_c(self._keep))
+        c.n_atom_swaps = self.n_atom_swaps if self.ensemble == abi.ENS_NNVT else 0
         c.n_adjust = self.n_adjust
         c.mc_sample = self.mc_sample
         c.n_bin = self.n_bin
@@ -365,7 +414,7 @@ class Engine:
     def runner_state(self, ladder: int, slot: int):
         """(g_matrix [atom][n_sym], en_atom [atom]) of the configuration held by one slot (RuNNer)"""
         n = self.cfg.n_atoms
-        ns = len(self.cfg.runner.rad_eta) + len(self.cfg.runner.ang_eta)
+        ns = self.cfg.runner2.n_sym if self.cfg.runner2 is not None else len(self.cfg.runner.rad_eta) + len(self.cfg.runner.ang_eta)
         g, e = np.zeros((n, ns)), np.zeros(n)
         self._check(self._fn("debug_runner_state")(self._h, ladder, slot, _p(g), _p(e)))
         return g, e

@@ -263,16 +263,62 @@ class RuNNerPotential:
             params=np.asarray(params, dtype=np.float64))
 
 
+@dataclass(frozen=True)
+class NeuralNetworkPotential:
+    """MachineLearningPotential/ForwardPass.jl:23-45 — NeuralNetworkPotential(num_nodes, activation_functions, parameters)"""
+    num_nodes: tuple
+    activation_functions: tuple
+    parameters: np.ndarray
+
+
+@dataclass(frozen=True)
+class RadialType2a:
+    """MachineLearningPotential/SymmFunc.jl:53-84 — RadialType2a{T}(eta, r_cut, type_vector, G_vals_a, G_vals_b): G_vals_x are the
+    two {G_max, G_min} pairs (species-1 neighbour row, species-2 neighbour row) of the network of species x."""
+    eta: float
+    r_cut: float
+    type_vec: int
+    G_vals_a: tuple
+    G_vals_b: tuple
+
+
+@dataclass(frozen=True)
+class AngularType3a:
+    """MachineLearningPotential/SymmFunc.jl:113-171 — AngularType3a{T}(eta, lambda, zeta, r_cut, type_vector, G_valsa, G_valsb):
+    three {G_max, G_min} pairs per species (0 / 1 / 2 neighbours of species 2)."""
+    eta: float
+    lambda_: float
+    zeta: float
+    r_cut: float
+    type_vec: int
+    G_valsa: tuple
+    G_valsb: tuple
+
+
 class RuNNerPotential2Atom:
-    """src/EnergyEvaluation.jl:1287-1314: two-species network potential (nnp1, nnp2, RadialType2a / AngularType3a tables, n1, n2).
-    The constructor mirrors the reference's so that a brass deck can be written down; the sweep for it is not built yet
-    (the oracle restates its initial energy, calc_delta_matrix and calc_swap_matrix and pins them to the
-    reference's known answers) and `sweep_config` says so instead of running something else."""
-    kind = None
+    """src/EnergyEvaluation.jl:1287-1314 — RuNNerPotential2Atom(nnp1, nnp2, radsymvec, angsymvec, n1, n2[, boundary]): two-species
+    network potential; atoms 1..n1 are species 1, n1+1..n1+n2 species 2."""
+    kind = abi.POT_RUNNER2
 
     def __init__(self, nnp1, nnp2, radsymvec, angsymvec, n1, n2, boundary: float = 0.0):
-        self.nnp1, self.nnp2, self.radsymvec, self.angsymvec = nnp1, nnp2, radsymvec, angsymvec
-        self.n1, self.n2, self.boundary2 = int(n1), int(n2), float(boundary) * float(boundary)
+        from .engine import Runner2Params
+        if tuple(nnp1.num_nodes) != tuple(nnp2.num_nodes) or tuple(nnp1.activation_functions) != tuple(nnp2.activation_functions):
+            raise ValueError("the two networks must share one topology")
+        self.nnp1, self.nnp2, self.radsymvec, self.angsymvec = nnp1, nnp2, list(radsymvec), list(angsymvec)
+        self.n1, self.n2 = int(n1), int(n2)
+        self.r_cut = float(self.radsymvec[0].r_cut)                      # :1297
+        self.boundary2 = float(boundary) * float(boundary)               # :1312-1314
+        g1 = [row for r in self.radsymvec for row in r.G_vals_a] + [row for a in self.angsymvec for row in a.G_valsa]
+        g2 = [row for r in self.radsymvec for row in r.G_vals_b] + [row for a in self.angsymvec for row in a.G_valsb]
+        self.params = Runner2Params(
+            n1=self.n1, n2=self.n2, rad_eta=np.array([r.eta for r in self.radsymvec], dtype=np.float64),
+            ang_eta=np.array([a.eta for a in self.angsymvec], dtype=np.float64),
+            ang_lambda=np.array([a.lambda_ for a in self.angsymvec], dtype=np.float64),
+            ang_zeta=np.array([a.zeta for a in self.angsymvec], dtype=np.float64),
+            gmax_gmin_1=np.array(g1, dtype=np.float64).reshape(-1, 2), gmax_gmin_2=np.array(g2, dtype=np.float64).reshape(-1, 2),
+            r_cut=self.r_cut, boundary2=self.boundary2, num_nodes=np.asarray(nnp1.num_nodes, dtype=np.int32),
+            activation=np.asarray(nnp1.activation_functions, dtype=np.int32),
+            params_1=np.asarray(nnp1.parameters, dtype=np.float64), params_2=np.asarray(nnp2.parameters, dtype=np.float64))
 
 
 @dataclass
@@ -281,7 +327,7 @@ class NNVT:
     natoms: tuple
     n_atom_swaps: int = 1
     n_atom_moves: int | None = None
-    kind = None
+    kind = abi.ENS_NNVT
 
     def atom_moves(self):
         return sum(self.natoms) if self.n_atom_moves is None else self.n_atom_moves
@@ -290,9 +336,11 @@ class NNVT:
 # ------------------------------------------------------------------------------- config building --
 def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, ensemble, *, n_ladders=1,
                  seed=1234, device=0, rng_mode=abi.RNG_BATCH8, lanes_per_replica=0) -> SweepConfig:
-    if isinstance(ensemble, NNVT) or isinstance(potential, RuNNerPotential2Atom):
-        raise NotImplementedError("the two-species sweep (RuNNerPotential2Atom + NNVT atom swaps, scripts/brass55.jl) is not built in "
-                                  "libptmc_b200 yet: single-species RuNNerPotential with NVT is (DESIGN.md section 8)")
+    if isinstance(ensemble, NNVT) != isinstance(potential, RuNNerPotential2Atom):
+        raise ValueError("NNVT (atom swaps between two species) goes with RuNNerPotential2Atom and vice versa "
+                         "(swap_energy_update is defined for that potential only, src/EnergyEvaluation.jl:1437-1448)")
+    if isinstance(ensemble, NNVT) and (tuple(ensemble.natoms) != (potential.n1, potential.n2) or sum(ensemble.natoms) != mc_params.n_atoms):
+        raise ValueError("NNVT.natoms must equal the potential's (n1, n2) and add up to n_atoms")
     cfgs = start_config if isinstance(start_config, (list, tuple)) else (start_config,)
     bc = cfgs[0].boundary_condition
     if isinstance(ensemble, NPT):
@@ -316,6 +364,9 @@ def sweep_config(mc_params: MCParams, temp: TempGrid, start_config, potential, e
         kw["lut"] = potential
     elif potential.kind == abi.POT_EAM:
         kw["eam"] = (potential.n, potential.m, potential.ean, potential.eCam)
+    elif potential.kind == abi.POT_RUNNER2:
+        kw["runner2"] = potential.params
+        kw["n_atom_swaps"] = ensemble.n_atom_swaps
     else:
         kw["runner"] = potential.params
     return SweepConfig(**kw)
@@ -663,3 +714,35 @@ def deck_cu55_runner(n_traj=28, cycles=100, boundary: float = 0.0):
     a2b = 1.8897259886
     start = Config(cu55_geometry(), SphericalBC(radius=14 * a2b))
     return (MCParams(cycles, n_traj, 55), TempGrid(400.0, 1200.0, n_traj), start, cu_runner_potential(boundary), NVT(55))
+
+
+def load_weights_zn():
+    """weights.030.data: the Zn network of scripts/brass55.jl:160-164 (data/cu_nnp_inputs.npz)"""
+    return np.load(DATA_DIR / "cu_nnp_inputs.npz")["weights_zn"]
+
+
+def brass_runner_potential(n1: int, n2: int, boundary: float = 0.0):
+    """scripts/brass55.jl:37-167 (= test/potentialfile.jl): 5 radial + 26 angular two-species symmetry functions, scaling rows 1-88
+    (Cu network) / 89-176 (Zn network), networks 88-20-20-1 from weights.029.data / weights.030.data."""
+    g = load_scaling()
+    ga, gb = g[:88], g[88:176]
+    rad = [RadialType2a(eta, RUNNER_R_CUT, 2, (tuple(ga[2 * k]), tuple(ga[2 * k + 1])), (tuple(gb[2 * k]), tuple(gb[2 * k + 1])))
+           for k, eta in enumerate((0.001, 0.020, 0.035, 0.100, 0.400))]
+    ang = [AngularType3a(eta, lam, zeta, RUNNER_R_CUT, 2, tuple(tuple(ga[10 + 3 * k + q]) for q in range(3)),
+                         tuple(tuple(gb[10 + 3 * k + q]) for q in range(3))) for k, (eta, lam, zeta) in enumerate(CU_ANGULAR)]
+    nodes, acts = (88, 20, 20, 1), (1, 2, 2, 1)
+    return RuNNerPotential2Atom(NeuralNetworkPotential(nodes, acts, load_weights()), NeuralNetworkPotential(nodes, acts, load_weights_zn()),
+                                rad, ang, n1, n2, boundary)
+
+
+def deck_brass55(n_traj=10, cycles=100, n_zn=5, n_swaps=2):
+    """scripts/brass55.jl: Cu50Zn5 icosahedron, RuNNerPotential2Atom, NNVT([50, 5]; natomswaps = 2), 10 temperatures 250-900 K,
+    SphericalBC(14 Angstrom); its ico_55 (:172-228) is used as given.  The script shuffles the 55 sites with Julia's `shuffle!`
+    (Random.seed!(1234), :229-230) before the first 50 become Cu; without Julia that permutation is not reproducible here, so the
+    deck takes the sites in a fixed pseudo-random order of its own (numpy default_rng(1234)) — which sites start as Zn is an input,
+    not part of the path."""
+    a2b = 1.8897259886
+    pos = _geom("brass55")[np.random.default_rng(1234).permutation(55)]
+    start = Config(pos, SphericalBC(radius=14 * a2b))
+    ens = NNVT((55 - n_zn, n_zn), n_atom_swaps=n_swaps)
+    return MCParams(cycles, n_traj, 55), TempGrid(250.0, 900.0, n_traj), start, brass_runner_potential(55 - n_zn, n_zn), ens

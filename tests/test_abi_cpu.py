@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
 def test_config_struct_matches_header():
     # sizes the C compiler sees (computed by compiling a probe would need gcc + the header: do exactly that)
     import subprocess, tempfile, pathlib
-    src = '#include "ptmc_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu\\n", sizeof(ptmc_config), sizeof(ptmc_runner_desc));return 0;}\n'
+    src = '#include "ptmc_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(ptmc_config), sizeof(ptmc_runner_desc), sizeof(ptmc_runner2_desc));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         p = pathlib.Path(d)
         (p / "probe.c").write_text(src)
@@ -38,6 +38,7 @@ def test_config_struct_matches_header():
         out = subprocess.run([str(p / "probe")], capture_output=True, text=True, check=True).stdout.split()
     assert int(out[0]) == C.sizeof(abi.Config)
     assert int(out[1]) == C.sizeof(abi.RunnerDesc)
+    assert int(out[2]) == C.sizeof(abi.Runner2Desc)
 
 
 def _header_fields(struct_name):
@@ -54,12 +55,13 @@ def _header_fields(struct_name):
 
 def test_bindings_list_the_header_fields_in_order():
     # the ctypes mirror (what the tests drive) and the Julia struct a maintainer adds against include/ptmc_b200.h
-    for struct_name, ctype, jl_name in (("ptmc_config", abi.Config, "PtmcConfig"), ("ptmc_runner_desc", abi.RunnerDesc, "PtmcRunnerDesc")):
+    for struct_name, ctype, jl_name in (("ptmc_config", abi.Config, "PtmcConfig"), ("ptmc_runner_desc", abi.RunnerDesc, "PtmcRunnerDesc"),
+                                         ("ptmc_runner2_desc", abi.Runner2Desc, "PtmcRunner2Desc")):
         fields = _header_fields(struct_name)
         assert fields == [f[0] for f in ctype._fields_], struct_name
         jl = (abi.PKG_DIR / "julia" / "PTMCB200.jl").read_text()
-        if "struct %s" % jl_name in jl:
-            i = jl.index("struct %s" % jl_name)
+        i = jl.index("struct %s" % jl_name)
+        if True:
             assert fields == re.findall(r"^\s*(\w+)::", jl[i:jl.index("\nend", i)], flags=re.M), jl_name
 
 
@@ -89,9 +91,18 @@ def test_argument_validation_precedes_device(lib):
     assert b"SphericalBC cannot be used in an NPT ensemble" in lib.ptmc_last_error(None)
 
 
-def test_two_species_sweep_is_refused_loudly():
-    # RuNNerPotential2Atom / NNVT (scripts/brass55.jl) exist in the host mirror, and say that the sweep for them is not built
-    cfg = P.Config(np.zeros((6, 3)) + np.arange(6)[:, None], P.SphericalBC(radius=8.0))
-    with pytest.raises(NotImplementedError, match="two-species"):
-        sweep_config(P.MCParams(10, 2, 6), P.TempGrid(500.0, 650.0, 2), cfg, P.RuNNerPotential2Atom(None, None, [], [], 4, 2), P.NNVT((4, 2)))
+def test_two_species_host_mirror():
+    # RuNNerPotential2Atom / NNVT (scripts/brass55.jl): the host mirror builds the descriptor in g-matrix row order and refuses
+    # inconsistent combinations
+    pot = P.host.brass_runner_potential(4, 2)
+    assert pot.params.n_sym == 88 and pot.params.gmax_gmin_1.shape == (88, 2) and pot.kind == abi.POT_RUNNER2
+    g = P.host.load_scaling()
+    assert np.array_equal(pot.params.gmax_gmin_1, g[:88]) and np.array_equal(pot.params.gmax_gmin_2, g[88:176])
     assert P.NNVT((4, 2)).atom_moves() == 6 and P.NNVT((4, 2)).n_atom_swaps == 1          # src/Ensembles.jl:144
+    cfg = P.Config(np.zeros((6, 3)) + np.arange(6)[:, None], P.SphericalBC(radius=8.0))
+    sc = sweep_config(P.MCParams(10, 2, 6), P.TempGrid(500.0, 650.0, 2), cfg, pot, P.NNVT((4, 2), n_atom_swaps=2))
+    assert sc.n_steps == 8 and sc.to_c().n_atom_swaps == 2
+    with pytest.raises(ValueError, match="NNVT"):
+        sweep_config(P.MCParams(10, 2, 6), P.TempGrid(500.0, 650.0, 2), cfg, pot, P.NVT(6))
+    with pytest.raises(ValueError, match="natoms"):
+        sweep_config(P.MCParams(10, 2, 6), P.TempGrid(500.0, 650.0, 2), cfg, pot, P.NNVT((3, 3)))

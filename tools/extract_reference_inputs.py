@@ -11,7 +11,8 @@ Sources (all under /root/reference):
   scripts/cu55.jl:164-220     ico_55 unit icosahedron
   scripts/pbc216.jl:79-515    fcc / hcp 216-atom lattices (Angstrom)
   scripts/cu38.jl:161-200     Cu38 (bohr), scripts/pbc32-short.jl:54-87  32-atom fcc block (Angstrom)
-  scripts/data/weights.029.data, scripts/data/scaling.data  (RuNNer Cu network)
+  scripts/brass55.jl:172-228  ico_55 of the brass script (bohr, used as given :230-233)
+  scripts/data/weights.029.data, weights.030.data, scripts/data/scaling.data  (RuNNer Cu / Zn networks)
 """
 import json, re, sys
 from pathlib import Path
@@ -45,8 +46,9 @@ def main():
         "ne216_hcp": grab("scripts/pbc216.jl", "pos_ne216_hcp"),
         "cu38": grab("scripts/cu38.jl", "pos_cu38"),
         "ne32": grab("scripts/pbc32-short.jl", "pos_ne32"),
+        "brass55": grab("scripts/brass55.jl", "ico_55"),
     }
-    want = {"ne13": 13, "ne55": 55, "ico55": 55, "ne216_fcc": 216, "ne216_hcp": 216, "cu38": 38, "ne32": 32}
+    want = {"ne13": 13, "ne55": 55, "ico55": 55, "ne216_fcc": 216, "ne216_hcp": 216, "cu38": 38, "ne32": 32, "brass55": 55}
     for k, rows in geo.items():
         assert len(rows) == want[k], (k, len(rows))
         # keep the decimal literals as strings -> float() parses them exactly as Julia does
@@ -55,6 +57,7 @@ def main():
     # (scripts/data/scaling.data rows 1..176: element, index, G_min, G_max, G_avg), the Zn network of the brass KAT
     import numpy as np
     np.savez_compressed(OUT / "cu_nnp_inputs.npz", weights_cu=np.loadtxt(REF / "scripts" / "data" / "weights.029.data").ravel(),
+                        weights_zn=np.loadtxt(REF / "scripts" / "data" / "weights.030.data").ravel(),
                         scaling_rows=np.loadtxt(REF / "scripts" / "data" / "scaling.data", usecols=(0, 1, 2, 3, 4), max_rows=176))
     np.savez_compressed(OUT.parent.parent / "tests" / "golden" / "brass_nnp_inputs.npz",
                         weights_zn=np.loadtxt(REF / "test" / "testing_data" / "weights.030.data").ravel())
