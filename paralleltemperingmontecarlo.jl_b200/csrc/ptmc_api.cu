@@ -32,6 +32,11 @@ void runner_launch_init(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaS
 int runner_launch_cycle(const DevParams& P, const RunnerDev& R, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st);
 void runner_launch_gather(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaStream_t st);
 void runner_launch_export(const DevParams& P, const RunnerDev& R, i64 rep, double* g_out, double* e_out, cudaStream_t st);
+size_t runner2_smem_bytes(int N, const Runner2Dev& R);
+cudaError_t runner2_prepare(int N, const Runner2Dev& R);
+void runner2_launch_init(const DevParams& P, const Runner2Dev& R, i64 n_rep, cudaStream_t st);
+int runner2_launch_cycle(const DevParams& P, const Runner2Dev& R, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st);
+void runner2_launch_export(const DevParams& P, const Runner2Dev& R, i64 rep, double* g_out, double* e_out, cudaStream_t st);
 }  // namespace ptmc
 
 using namespace ptmc;
@@ -43,7 +48,9 @@ struct ptmc_handle {
     std::vector<double> betas;
     DevParams P;
     RunnerDev R;
-    bool runner = false;
+    Runner2Dev R2;
+    bool runner = false;             // one of the RuNNer kernels (one CTA per replica, two launches per cycle)
+    bool runner2 = false;            // ... the two-species one
     int device = 0;
     int G = 0;
     int threads = 0;
@@ -229,6 +236,75 @@ static int build_runner(ptmc_handle* h, const ptmc_runner_desc* d, std::vector<d
     return 0;
 }
 
+// RuNNerPotential2Atom -> Runner2Dev: distinct eta and (lambda, zeta) values of the angular functions, scaling factors per species
+// and row (RadialType2a / AngularType3a, SymmFunc.jl:64-83,133-171), the two networks back to back.
+static int build_runner2(ptmc_handle* h, const ptmc_runner2_desc* d, std::vector<double>& net_host) {
+    Runner2Dev& R = h->R2;
+    memset(&R, 0, sizeof R);
+    if (!d->rad_eta || !d->ang_eta || !d->ang_lambda || !d->ang_zeta || !d->gmax_gmin_1 || !d->gmax_gmin_2 || !d->num_nodes ||
+        !d->activation || !d->params_1 || !d->params_2)
+        return fail(h, PTMC_ERR_ARG, "ptmc_runner2_desc has null tables");
+    if (d->n_rad < 1 || d->n_rad > RN_MAX_RAD || d->n_ang < 1 || d->n_ang > RN_MAX_ANG)
+        return fail(h, PTMC_ERR_ARG, "the two-species sweep handles 1..%d radial and 1..%d angular symmetry functions", RN_MAX_RAD, RN_MAX_ANG);
+    if (d->n1 < 1 || d->n2 < 1 || d->n1 + d->n2 != h->cfg.n_atoms) return fail(h, PTMC_ERR_ARG, "n1, n2 >= 1 and n1 + n2 == n_atoms required");
+    R.n_rad = d->n_rad; R.n_ang = d->n_ang; R.n_sym = 2 * d->n_rad + 3 * d->n_ang; R.n1 = d->n1;
+    R.r_cut = d->r_cut;
+    for (int k = 0; k < d->n_rad; ++k) {
+        R.rad_eta[k] = d->rad_eta[k];
+        for (int q = 0; q < 4; ++q) {
+            const double* tab = q < 2 ? d->gmax_gmin_1 : d->gmax_gmin_2;
+            const int row = 2 * k + (q & 1);
+            const double g_norm = 1 / (tab[2 * row] - tab[2 * row + 1]);
+            R.rad_norm[k][q] = g_norm; R.rad_off[k][q] = -tab[2 * row + 1] * g_norm;
+        }
+    }
+    for (int k = 0; k < RN_MAX_ETA * RN_MAX_LZ; ++k) R.qmap[k] = -1;
+    for (int a = 0; a < d->n_ang; ++a) {
+        int e = -1, z = -1;
+        for (int k = 0; k < R.n_eta; ++k) if (R.eta[k] == d->ang_eta[a]) e = k;
+        if (e < 0) {
+            if (R.n_eta == RN_MAX_ETA) return fail(h, PTMC_ERR_ARG, "more than %d distinct eta among the angular symmetry functions", RN_MAX_ETA);
+            e = R.n_eta++; R.eta[e] = d->ang_eta[a];
+        }
+        for (int k = 0; k < R.n_lz; ++k) if (R.lz_lambda[k] == d->ang_lambda[a] && R.lz_zeta[k] == d->ang_zeta[a]) z = k;
+        if (z < 0) {
+            if (R.n_lz == RN_MAX_LZ) return fail(h, PTMC_ERR_ARG, "more than %d distinct (lambda, zeta) among the angular symmetry functions", RN_MAX_LZ);
+            z = R.n_lz++; R.lz_lambda[z] = d->ang_lambda[a]; R.lz_zeta[z] = d->ang_zeta[a];
+            const double ze = d->ang_zeta[a];
+            int zi = (ze >= 1 && ze <= 1024 && ze == std::floor(ze)) ? (int)ze : 0;
+            if (zi && (zi & (zi - 1))) zi = 0;
+            R.lz_zint[z] = zi;
+            int nsq = 15;
+            if (zi) { nsq = 0; while ((1 << nsq) < zi) ++nsq; }
+            if (nsq > 5) nsq = 15;
+            R.lz_nsq[z] = nsq;
+        }
+        R.ang_eta_idx[a] = e; R.ang_lz_idx[a] = z;
+        for (int q = 0; q < 6; ++q) {
+            const double* tab = q < 3 ? d->gmax_gmin_1 : d->gmax_gmin_2;
+            const int row = 2 * d->n_rad + 3 * a + q % 3;
+            const double g_norm = 1 / (tab[2 * row] - tab[2 * row + 1]);
+            R.ang_off[a][q] = -tab[2 * row + 1] * g_norm;
+            R.ang_tpz[a][q] = std::pow(2.0, 1 - d->ang_zeta[a]) * g_norm;
+        }
+        const int bit = e * RN_MAX_LZ + z;
+        if (R.present >> bit & 1ull) return fail(h, PTMC_ERR_ARG, "two angular symmetry functions share (eta, lambda, zeta)");
+        R.present |= 1ull << bit;
+        R.qmap[bit] = (signed char)a;
+    }
+    if (d->n_layers != 4 || d->num_nodes[0] != R.n_sym || d->num_nodes[3] != 1 || d->num_nodes[1] < 1 || d->num_nodes[2] < 1 ||
+        d->num_nodes[1] > RN_MAX_HID || d->num_nodes[2] > RN_MAX_HID)
+        return fail(h, PTMC_ERR_ARG, "the sweep kernel supports networks n_sym-h1-h2-1 with h <= %d (forward() handles any topology)", RN_MAX_HID);
+    R.h1 = d->num_nodes[1]; R.h2 = d->num_nodes[2];
+    R.act1 = d->activation[1]; R.act2 = d->activation[2]; R.act3 = d->activation[3];
+    const size_t need = (size_t)R.h1 * R.n_sym + R.h1 + (size_t)R.h2 * R.h1 + R.h2 + R.h2 + 1;
+    if ((size_t)d->n_params < need) return fail(h, PTMC_ERR_ARG, "n_params %d < %zu", d->n_params, need);
+    R.net_len = (int)need;
+    net_host.assign(d->params_1, d->params_1 + need);
+    net_host.insert(net_host.end(), d->params_2, d->params_2 + need);
+    return 0;
+}
+
 // lanes per replica: enough lanes to keep the per-move serial chain short, few enough that the redundant
 // per-group scalar work (RNG, Metropolis) stays small and many replicas are resident.
 static int auto_lanes(int n_atoms, int n_traj) {
@@ -259,12 +335,16 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     if (c->abi_version != PTMC_ABI_VERSION) return fail(nullptr, PTMC_ERR_ARG, "abi_version %d != %d", c->abi_version, PTMC_ABI_VERSION);
     if (c->n_ladders < 1 || c->n_traj < 2 || c->n_atoms < 2) return fail(nullptr, PTMC_ERR_ARG, "need n_ladders >= 1, n_traj >= 2, n_atoms >= 2");
     if (!c->betas) return fail(nullptr, PTMC_ERR_ARG, "betas is null");
+    const bool nnvt = c->ensemble == PTMC_ENS_NNVT;
+    if ((c->pot_kind == PTMC_POT_RUNNER2) != nnvt)
+        return fail(nullptr, PTMC_ERR_ARG, "NNVT (atom swaps between two species) goes with RuNNerPotential2Atom and vice versa (src/EnergyEvaluation.jl:1437-1448)");
+    if (nnvt && c->n_atom_swaps < 0) return fail(nullptr, PTMC_ERR_ARG, "n_atom_swaps must be >= 0");
     if (c->n_atom_moves < 1 || c->n_atom_moves > c->n_atoms) return fail(nullptr, PTMC_ERR_ARG, "n_atom_moves must be in 1..n_atoms");
     if (c->n_adjust < 1 || c->mc_sample < 1 || c->n_bin < 2) return fail(nullptr, PTMC_ERR_ARG, "n_adjust, mc_sample >= 1 and n_bin >= 2 required");
     if (c->rng_mode < PTMC_RNG_XOSHIRO || c->rng_mode > PTMC_RNG_BATCH8) return fail(nullptr, PTMC_ERR_ARG, "unknown rng_mode %d", c->rng_mode);
     const bool npt = c->ensemble == PTMC_ENS_NPT;
     const bool sphere = c->bc_kind == PTMC_BC_SPHERICAL;
-    if (c->ensemble != PTMC_ENS_NVT && !npt) return fail(nullptr, PTMC_ERR_ARG, "unknown ensemble %d", c->ensemble);
+    if (c->ensemble != PTMC_ENS_NVT && !npt && !nnvt) return fail(nullptr, PTMC_ERR_ARG, "unknown ensemble %d", c->ensemble);
     if (c->bc_kind < PTMC_BC_SPHERICAL || c->bc_kind > PTMC_BC_RECTANGULAR) return fail(nullptr, PTMC_ERR_ARG, "unknown boundary condition %d", c->bc_kind);
     if (npt && sphere) return fail(nullptr, PTMC_ERR_ARG, "SphericalBC cannot be used in an NPT ensemble");   // src/Ensembles.jl:189
     if (npt && c->n_volume_moves < 1) return fail(nullptr, PTMC_ERR_ARG, "NPT needs n_volume_moves >= 1");
@@ -292,6 +372,11 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
             if (!sphere || npt) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
             if (c->n_atoms > RN_MAX_ATOMS) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential sweep handles up to %d atoms", RN_MAX_ATOMS);
             break;
+        case PTMC_POT_RUNNER2:
+            if (!c->runner2) return fail(nullptr, PTMC_ERR_ARG, "pot_kind RUNNER2 needs ptmc_config.runner2");
+            if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential2Atom is built for SphericalBC/NNVT (scripts/brass55.jl)");
+            if (c->n_atoms > RN_MAX_ATOMS) return fail(nullptr, PTMC_ERR_ARG, "RuNNerPotential2Atom sweep handles up to %d atoms", RN_MAX_ATOMS);
+            break;
         default: return fail(nullptr, PTMC_ERR_ARG, "unknown potential %d", c->pot_kind);
     }
     int ndev = 0;
@@ -305,14 +390,15 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->cfg = *c;
     h->betas.assign(c->betas, c->betas + c->n_traj);
     h->cfg.betas = h->betas.data();
-    h->cfg.runner = nullptr;
+    h->cfg.runner = nullptr; h->cfg.runner2 = nullptr;
     h->cfg.eljb_a = nullptr; h->cfg.eljb_b = nullptr;      // copied into DevParams below
     h->cfg.lut_table = nullptr;                              // copied to the device below
-    h->runner = c->pot_kind == PTMC_POT_RUNNER;
+    h->runner2 = c->pot_kind == PTMC_POT_RUNNER2;
+    h->runner = c->pot_kind == PTMC_POT_RUNNER || h->runner2;
     h->device = c->device;
     h->geom = sphere ? GEOM_SPHERE : (c->bc_kind == PTMC_BC_RHOMBIC ? GEOM_RHOMB : GEOM_PBC);
     h->n_rep = c->n_ladders * c->n_traj;
-    h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0);
+    h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0) + (nnvt ? c->n_atom_swaps : 0);     // length(MoveStrategy) src/Ensembles.jl:236-282
     int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj);
     if (h->runner) G = 32;          // the RuNNer kernels use one 256-thread CTA per replica; G is not used
     if (G != 4 && G != 8 && G != 16 && G != 32) { delete h; return fail(nullptr, PTMC_ERR_ARG, "lanes_per_replica must be 0, 4, 8, 16 or 32"); }
@@ -339,10 +425,10 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     P.eam_hn = c->eam_n / 2; P.eam_hm = c->eam_m / 2; P.eam_ean = c->eam_ean; P.eam_ecam = c->eam_ecam;
 
     std::vector<double> net_host;
-    if (h->runner) { int rr = build_runner(h, c->runner, net_host); if (rr) return bail(rr); }
+    if (h->runner) { int rr = h->runner2 ? build_runner2(h, c->runner2, net_host) : build_runner(h, c->runner, net_host); if (rr) return bail(rr); }
     for (int dbg = 0; dbg < 2; ++dbg)
         h->smem_k[dbg] = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere, !eam_unrolled(P.n_pad / G, dbg != 0)).bytes;
-    h->smem = h->runner ? runner_smem_bytes(c->n_atoms, h->R) : std::max(h->smem_k[0], h->smem_k[1]);
+    h->smem = h->runner2 ? runner2_smem_bytes(c->n_atoms, h->R2) : h->runner ? runner_smem_bytes(c->n_atoms, h->R) : std::max(h->smem_k[0], h->smem_k[1]);
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
 
     const size_t R = (size_t)h->n_rep, N = (size_t)c->n_atoms, L = (size_t)c->n_ladders;
@@ -363,7 +449,17 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         (rc = dev_alloc(h, &P.hist, L * h->hist_per_ladder)) || (rc = dev_alloc(h, &h->d_reduced, h->hist_per_ladder)) ||
         (rc = dev_alloc(h, &h->d_error, 1)))
         return bail(rc);
-    if (h->runner) {
+    if (h->runner2) {
+        Runner2Dev& Rr = h->R2;
+        double* d_net = nullptr;
+        if ((rc = dev_alloc(h, &Rr.pos_c, R * N * 3)) || (rc = dev_alloc(h, &Rr.en_c, R)) || (rc = dev_alloc(h, &Rr.en_atom_c, R * N)) ||
+            (rc = dev_alloc(h, &Rr.g_c, R * N * Rr.n_sym)) || (rc = dev_alloc(h, &Rr.pair_c, R * (N * (N - 1) / 2) * (3 + Rr.n_eta))) ||
+            (rc = dev_alloc(h, &d_net, net_host.size())))
+            return bail(rc);
+        if (cudaMemcpy(d_net, net_host.data(), sizeof(double) * net_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(h, PTMC_ERR_CUDA, "copying the networks failed"));
+        Rr.net = d_net;
+    } else if (h->runner) {
         RunnerDev& Rr = h->R;
         double* d_net = nullptr;
         if ((rc = dev_alloc(h, &Rr.pos_c, R * N * 3)) || (rc = dev_alloc(h, &Rr.en_c, R)) || (rc = dev_alloc(h, &Rr.en_atom_c, R * N)) ||
@@ -417,7 +513,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     if (cudaMemcpy(d_betas, h->betas.data(), sizeof(double) * c->n_traj, cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(fail(h, PTMC_ERR_CUDA, "copying betas failed"));
     if (h->runner) {
-        if (runner_prepare(c->n_atoms, h->R) != cudaSuccess)
+        if ((h->runner2 ? runner2_prepare(c->n_atoms, h->R2) : runner_prepare(c->n_atoms, h->R)) != cudaSuccess)
             return bail(fail(h, PTMC_ERR_CUDA, "RuNNer kernels need %zu B of shared memory: %s", h->smem, cudaGetErrorString(cudaGetLastError())));
     }
     // opt in to large dynamic shared memory for both builds of the kernel
@@ -468,7 +564,8 @@ extern "C" PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, co
         CU(h, cudaMemcpy(P.perm_g, perm.data(), sizeof(int) * R, cudaMemcpyHostToDevice));
         CU(h, cudaMemset(P.moved_g, 0, sizeof(int) * R * (P.moved_words + 1)));
     }
-    if (h->runner) runner_launch_init(P, h->R, h->n_rep, h->stream);
+    if (h->runner2) runner2_launch_init(P, h->R2, h->n_rep, h->stream);
+    else if (h->runner) runner_launch_init(P, h->R, h->n_rep, h->stream);
     else launch_init(P, h->n_rep, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());
@@ -592,8 +689,10 @@ extern "C" PTMC_API int ptmc_run_phase(ptmc_handle* h, int64_t first_idx, int64_
         P.tr_index = static_cast<int32_t*>(h->d_trace[0]); P.tr_de = static_cast<double*>(h->d_trace[1]);
         P.tr_acc = static_cast<uint8_t*>(h->d_trace[2]); P.tr_exc = static_cast<int32_t*>(h->d_trace[3]);
         for (i64 k = 0; k < n_cycles; ++k)
-            h->launches += runner_launch_cycle(P, h->R, h->cfg.n_ladders, first_idx + k, k, sample, dbg != 0, h->stream);
-        runner_launch_gather(P, h->R, h->n_rep, h->stream);
+            h->launches += h->runner2 ? runner2_launch_cycle(P, h->R2, h->cfg.n_ladders, first_idx + k, k, sample, dbg != 0, h->stream)
+                                      : runner_launch_cycle(P, h->R, h->cfg.n_ladders, first_idx + k, k, sample, dbg != 0, h->stream);
+        if (h->runner2) runner_launch_gather_ptr(P, h->R2.pos_c, h->R2.en_c, h->n_rep, h->stream);
+        else runner_launch_gather(P, h->R, h->n_rep, h->stream);
         h->launches += 1;
         CU(h, cudaGetLastError());
         if (tracing) h->trace_n += n_cycles;
@@ -801,10 +900,11 @@ extern "C" PTMC_API int ptmc_debug_runner_state(ptmc_handle* h, int64_t ladder, 
     if (!h || !h->runner || !g_matrix || !en_atom || ladder < 0 || ladder >= h->cfg.n_ladders || slot < 0 || slot >= h->cfg.n_traj)
         return h ? fail(h, PTMC_ERR_ARG, "ptmc_debug_runner_state: not a RuNNer handle or bad index") : PTMC_ERR_ARG;
     TRY(ptmc_sync(h));
-    const size_t N = (size_t)h->cfg.n_atoms, ng = N * h->R.n_sym;
+    const size_t N = (size_t)h->cfg.n_atoms, ng = N * (h->runner2 ? h->R2.n_sym : h->R.n_sym);
     double* d = nullptr;
     CU(h, cudaMalloc(&d, sizeof(double) * (ng + N)));
-    runner_launch_export(h->P, h->R, ladder * h->cfg.n_traj + slot, d, d + ng, h->stream);
+    if (h->runner2) runner2_launch_export(h->P, h->R2, ladder * h->cfg.n_traj + slot, d, d + ng, h->stream);
+    else runner_launch_export(h->P, h->R, ladder * h->cfg.n_traj + slot, d, d + ng, h->stream);
     h->launches += 1;
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaMemcpy(g_matrix, d, sizeof(double) * ng, cudaMemcpyDeviceToHost);

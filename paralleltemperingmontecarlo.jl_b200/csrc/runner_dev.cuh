@@ -48,6 +48,38 @@ struct RunnerDev {
     double* pair_c;     // [3 + n_eta][NT]: dist2_mat, 1/sqrt(dist2_mat), f_matrix, exp(-eta d2) * f
 };
 
+// Two species (RuNNerPotential2Atom, src/EnergyEvaluation.jl:1287-1314): atoms 0 .. n1-1 are species 1, the rest species 2; every
+// symmetry function is evaluated (DeltaMatrix.jl:256-316 has no type filter).  The g matrix keeps the reference's rows:
+// radial function k at rows 2k + {species of the neighbour}, angular function q at 2 n_rad + 3q + {number of species-2 atoms among
+// the two neighbours} (SymmFunc.jl:511-545).  One network per species.
+struct Runner2Dev {
+    int n_sym, n_rad, n_ang, n1;
+    int n_eta, n_lz;
+    double rad_eta[RN_MAX_RAD];
+    double rad_norm[RN_MAX_RAD][4], rad_off[RN_MAX_RAD][4];      // [2 * species of the centre + row]  (RadialType2a, SymmFunc.jl:64-83)
+    int ang_eta_idx[RN_MAX_ANG], ang_lz_idx[RN_MAX_ANG];
+    double ang_tpz[RN_MAX_ANG][6], ang_off[RN_MAX_ANG][6];       // [3 * species of the centre + row]  (AngularType3a, :133-171)
+    unsigned long long present;                 // as RunnerDev
+    signed char qmap[RN_MAX_ETA * RN_MAX_LZ];
+    double eta[RN_MAX_ETA];
+    double lz_lambda[RN_MAX_LZ], lz_zeta[RN_MAX_LZ];
+    int lz_zint[RN_MAX_LZ], lz_nsq[RN_MAX_LZ];
+    double r_cut;
+    int h1, h2, act1, act2, act3;
+    int net_len;                                // doubles per network: W1 [h1 x n_sym] col-major, b1, W2 [h2 x h1] col-major, b2, W3 [h2], b3
+    const double* net;                          // network of species 1, then of species 2
+    // per-configuration state, indexed [ladder][config]
+    double* pos_c;      // [N][3]
+    double* en_c;
+    double* en_atom_c;  // [N]
+    double* g_c;        // [N][n_sym]
+    double* pair_c;     // [3 + n_eta][NT] as RunnerDev; read from HBM / L1 by the kernel (the two g matrices fill shared memory)
+};
+
+// end-of-cycle step (exchange / step-size adaptation / sampling) and slot-ordered gather, shared by the one- and two-species sweeps
+void runner_launch_cycle_end(const DevParams& P, const double* en_c, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st);
+void runner_launch_gather_ptr(const DevParams& P, const double* pos_c, const double* en_c, i64 n_rep, cudaStream_t st);
+
 // The angular symmetry-function set of every RuNNer script of the reference (scripts/cu55.jl:70-97, cu38.jl, brass55.jl,
 // test/potentialfile.jl: the 26-row table "V"), as structure only: which (eta index, (lambda, zeta) index) pairs exist
 // and how many squarings each (lambda, zeta) needs, with indices in order of first appearance.  The kernels are
@@ -75,4 +107,94 @@ __host__ __device__ __forceinline__ int rn_tri(int a, int b, int N) {
     return lo * N - (lo * (lo + 1)) / 2 + (hi - lo - 1);
 }
 
+// ------------------------------------------------------------------------------------------ helpers --
+__device__ __forceinline__ double rn_cutoff(double r, double rc) {       // Cutoff.jl:79-86
+    return r < rc ? 0.5 * (cos(3.14159265358979323846 * (r / rc)) + 1.0) : 0.0;
+}
+// (1 + lambda c)^zeta: repeated squaring for zeta = 2^m (1, 2, 4, 8, 16, ...), pow() otherwise  (SymmFunc.jl:192)
+__device__ __forceinline__ double rn_theta(double c, double lambda, double zeta, int zint) {
+    double b = fma(lambda, c, 1.0);
+    if (zint > 0) {
+        for (int m = zint; m > 1; m >>= 1) b *= b;
+        return b;
+    }
+    return pow(b, zeta);
+}
+// the same with the number of squarings nsq (zeta = 2^nsq, at most 2^5); nsq == 15 -> pow().  In the specialised
+// kernels nsq is a compile-time constant after unrolling and the predicates fold away.
+__device__ __forceinline__ double rn_theta_n(double c, double lambda, double zeta, int nsq) {
+    double b = fma(lambda, c, 1.0);
+    if (nsq == 15) return pow(b, zeta);
+#pragma unroll
+    for (int m = 0; m < 5; ++m) if (m < nsq) b *= b;
+    return b;
+}
+// exp(x) for x in [-700, 0], branch-free: x = k ln2 + r, |r| <= ln2 / 2, Taylor series to degree 13 (remainder 4e-18),
+// exponent patched into the high word
+__device__ __forceinline__ double rn_exp_neg(double x) {
+    x = fmax(x, -700.0);
+    const double kf = rint(x * 1.4426950408889634);
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 1.60590438368216145994e-10;                  // 1/13!
+    p = fma(p, r, 2.08767569878680989792e-09);
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)kf << 20), __double2loint(p));
+}
+// tanh(z) = sign(z) (1 - t) / (1 + t), t = exp(-2 |z|): branch-free, absolute error ~1e-16 (the library routine
+// diverges between its two argument ranges inside a warp: 9 % of the kernel's instructions before)
+__device__ __forceinline__ double rn_tanh(double z) {
+    const double t = rn_exp_neg(-2.0 * fabs(z));
+    const double r = (1.0 - t) * rcp_pos(1.0 + t);
+    return copysign(r, z);
+}
+__device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? rn_tanh(z) : z; }
+
+// acc[e][z] += ep_new[e] (1 + lambda_z cos_new)^zeta_z - ep_old[e] (1 + lambda_z cos_old)^zeta_z for every evaluated (e, z).
+// SPEC (the reference's standard set): the slots are walked along the two squaring chains of RN_ZSEQ_V.
+template <bool SPEC, unsigned long long PRESENT, unsigned NSQ, class RD>
+__device__ __forceinline__ void rn_angular_acc(const RD& R, unsigned long long present, double cn, double co,
+                                               const double (&epn)[RN_MAX_ETA], const double (&epo)[RN_MAX_ETA], double (&acc)[RN_MAX_ETA][RN_MAX_LZ]) {
+    if (SPEC) {
+        double bn = 0.0, bo = 0.0;
+#pragma unroll
+        for (int q = 0; q < RN_MAX_LZ; ++q) {
+            const int z = (int)((RN_ZSEQ_V >> (4 * q)) & 15u), sq = (int)((RN_ZSQ_V >> (4 * q)) & 15u);
+            if ((RN_ZROOT_V >> q) & 1u) { bn = fma(R.lz_lambda[z], cn, 1.0); bo = fma(R.lz_lambda[z], co, 1.0); }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) if (m < sq) { bn *= bn; bo *= bo; }
+#pragma unroll
+            for (int e = 0; e < RN_MAX_ETA; ++e)
+                if (PRESENT >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * bn - epo[e] * bo;
+        }
+    } else {
+#pragma unroll
+        for (int z = 0; z < RN_MAX_LZ; ++z) {
+            if (z < R.n_lz) {
+                const double tn = rn_theta_n(cn, R.lz_lambda[z], R.lz_zeta[z], R.lz_nsq[z]);
+                const double to = rn_theta_n(co, R.lz_lambda[z], R.lz_zeta[z], R.lz_nsq[z]);
+#pragma unroll
+                for (int e = 0; e < RN_MAX_ETA; ++e)
+                    if (present >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * tn - epo[e] * to;
+            }
+        }
+    }
+}
+
+// D (8 x 8, FP64) += A (8 x 4, row) * B (4 x 8, col) on the tensor cores (DMMA; tcgen05 has no f64 kind).  Lane l holds
+// A[l / 4][l % 4], B[l % 4][l / 4] and D[l / 4][2 (l % 4) + {0, 1}].
+__device__ __forceinline__ void rn_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 }  // namespace ptmc

@@ -14,91 +14,6 @@
 
 namespace ptmc {
 
-// ------------------------------------------------------------------------------------------ helpers --
-__device__ __forceinline__ double rn_cutoff(double r, double rc) {       // Cutoff.jl:79-86
-    return r < rc ? 0.5 * (cos(3.14159265358979323846 * (r / rc)) + 1.0) : 0.0;
-}
-// (1 + lambda c)^zeta: repeated squaring for zeta = 2^m (1, 2, 4, 8, 16, ...), pow() otherwise  (SymmFunc.jl:192)
-__device__ __forceinline__ double rn_theta(double c, double lambda, double zeta, int zint) {
-    double b = fma(lambda, c, 1.0);
-    if (zint > 0) {
-        for (int m = zint; m > 1; m >>= 1) b *= b;
-        return b;
-    }
-    return pow(b, zeta);
-}
-// the same with the number of squarings nsq (zeta = 2^nsq, at most 2^5); nsq == 15 -> pow().  In the specialised
-// kernels nsq is a compile-time constant after unrolling and the predicates fold away.
-__device__ __forceinline__ double rn_theta_n(double c, double lambda, double zeta, int nsq) {
-    double b = fma(lambda, c, 1.0);
-    if (nsq == 15) return pow(b, zeta);
-#pragma unroll
-    for (int m = 0; m < 5; ++m) if (m < nsq) b *= b;
-    return b;
-}
-// exp(x) for x in [-700, 0], branch-free: x = k ln2 + r, |r| <= ln2 / 2, Taylor series to degree 13 (remainder 4e-18),
-// exponent patched into the high word
-__device__ __forceinline__ double rn_exp_neg(double x) {
-    x = fmax(x, -700.0);
-    const double kf = rint(x * 1.4426950408889634);
-    double r = fma(kf, -6.93147180369123816490e-01, x);
-    r = fma(kf, -1.90821492927058770002e-10, r);
-    double p = 1.60590438368216145994e-10;                  // 1/13!
-    p = fma(p, r, 2.08767569878680989792e-09);
-    p = fma(p, r, 2.50521083854417187751e-08);
-    p = fma(p, r, 2.75573192239858906526e-07);
-    p = fma(p, r, 2.75573192239858906526e-06);
-    p = fma(p, r, 2.48015873015873015873e-05);
-    p = fma(p, r, 1.98412698412698412698e-04);
-    p = fma(p, r, 1.38888888888888888889e-03);
-    p = fma(p, r, 8.33333333333333333333e-03);
-    p = fma(p, r, 4.16666666666666666667e-02);
-    p = fma(p, r, 1.66666666666666666667e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + ((int)kf << 20), __double2loint(p));
-}
-// tanh(z) = sign(z) (1 - t) / (1 + t), t = exp(-2 |z|): branch-free, absolute error ~1e-16 (the library routine
-// diverges between its two argument ranges inside a warp: 9 % of the kernel's instructions before)
-__device__ __forceinline__ double rn_tanh(double z) {
-    const double t = rn_exp_neg(-2.0 * fabs(z));
-    const double r = (1.0 - t) * rcp_pos(1.0 + t);
-    return copysign(r, z);
-}
-__device__ __forceinline__ double rn_act(double z, int code) { return code == 2 ? rn_tanh(z) : z; }
-
-// acc[e][z] += ep_new[e] (1 + lambda_z cos_new)^zeta_z - ep_old[e] (1 + lambda_z cos_old)^zeta_z for every evaluated (e, z).
-// SPEC (the reference's standard set): the slots are walked along the two squaring chains of RN_ZSEQ_V.
-template <bool SPEC, unsigned long long PRESENT, unsigned NSQ>
-__device__ __forceinline__ void rn_angular_acc(const RunnerDev& R, unsigned long long present, double cn, double co,
-                                               const double (&epn)[RN_MAX_ETA], const double (&epo)[RN_MAX_ETA], double (&acc)[RN_MAX_ETA][RN_MAX_LZ]) {
-    if (SPEC) {
-        double bn = 0.0, bo = 0.0;
-#pragma unroll
-        for (int q = 0; q < RN_MAX_LZ; ++q) {
-            const int z = (int)((RN_ZSEQ_V >> (4 * q)) & 15u), sq = (int)((RN_ZSQ_V >> (4 * q)) & 15u);
-            if ((RN_ZROOT_V >> q) & 1u) { bn = fma(R.lz_lambda[z], cn, 1.0); bo = fma(R.lz_lambda[z], co, 1.0); }
-#pragma unroll
-            for (int m = 0; m < 4; ++m) if (m < sq) { bn *= bn; bo *= bo; }
-#pragma unroll
-            for (int e = 0; e < RN_MAX_ETA; ++e)
-                if (PRESENT >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * bn - epo[e] * bo;
-        }
-    } else {
-#pragma unroll
-        for (int z = 0; z < RN_MAX_LZ; ++z) {
-            if (z < R.n_lz) {
-                const double tn = rn_theta_n(cn, R.lz_lambda[z], R.lz_zeta[z], R.lz_nsq[z]);
-                const double to = rn_theta_n(co, R.lz_lambda[z], R.lz_zeta[z], R.lz_nsq[z]);
-#pragma unroll
-                for (int e = 0; e < RN_MAX_ETA; ++e)
-                    if (present >> (e * RN_MAX_LZ + z) & 1ull) acc[e][z] += epn[e] * tn - epo[e] * to;
-            }
-        }
-    }
-}
-
 struct RnSmem {          // offsets in doubles into the dynamic shared memory of the move kernel
     int pos, g0, g1, ea0, ea1, rn, ro, red, net, h1, h2, misc, pair, ptab, total;
 };
@@ -122,11 +37,6 @@ __host__ __device__ inline RnSmem rn_smem(int N, const RunnerDev& R) {
     return s;
 }
 
-// D (8 x 8, FP64) += A (8 x 4, row) * B (4 x 8, col) on the tensor cores (DMMA; tcgen05 has no f64 kind).  Lane l holds
-// A[l / 4][l % 4], B[l % 4][l / 4] and D[l / 4][2 (l % 4) + {0, 1}].
-__device__ __forceinline__ void rn_dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 // One dense layer for all atoms: out[a][o] = act(b[o] + sum_r W[o][r] in[a][r]) as (n_out x n_in) * (n_in x N) tiles of
 // 8 output nodes x 8 atoms, one tile per warp and round, k in steps of 4.  W is column-major [r * n_out + o].
 __device__ __forceinline__ void rn_layer_dmma(const double* W, const double* b, int n_out, int n_in, int act, const double* in, int in_stride,
@@ -577,7 +487,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
 // Second half of mc_cycle! (src/MCRun.jl:203-212, 248-250) for one ladder per warp: exchange attempt
 // (src/Exchange.jl:132-155), update_max_stepsize! (:250-263), sampling_step! (src/Sampling.jl:330-349).
 template <bool DBG>
-__global__ void runner_cycle_end_kernel(const DevParams P, const RunnerDev R, const i64 idx, const i64 cyc_in_launch, const int sample) {
+__global__ void runner_cycle_end_kernel(const DevParams P, const double* __restrict__ en_c, const i64 idx, const i64 cyc_in_launch, const int sample) {
     const int lad = blockIdx.x, T = P.n_traj, lane = threadIdx.x;
     int* perm = P.perm_g + (i64)lad * T;
     if (lane == 0) {
@@ -591,7 +501,7 @@ __global__ void runner_cycle_end_kernel(const DevParams P, const RunnerDev R, co
             const int a = n_exc - 1, b = n_exc;
             i64* ca = P.counters + ((i64)lad * T + a) * PTMC_NCOUNT; i64* cb = P.counters + ((i64)lad * T + b) * PTMC_NCOUNT;
             ca[PTMC_C_EXC_ATT] += 1; cb[PTMC_C_EXC_ATT] += 1;
-            const double ea = R.en_c[(i64)lad * T + perm[a]], eb = R.en_c[(i64)lad * T + perm[b]];
+            const double ea = en_c[(i64)lad * T + perm[a]], eb = en_c[(i64)lad * T + perm[b]];
             double pe = exp(xmul(xsub(P.betas[a], P.betas[b]), xsub(ea, eb)));
             pe = (pe != pe) ? pe : (pe < 1.0 ? pe : 1.0);
             int ex_acc = 0;
@@ -626,7 +536,7 @@ __global__ void runner_cycle_end_kernel(const DevParams P, const RunnerDev R, co
             cn[PTMC_C_ATOM_ADJ] = 0;
         }
         if (sample && idx % P.mc_sample == 0) {
-            const double e = R.en_c[(i64)lad * T + perm[slot]];
+            const double e = en_c[(i64)lad * T + perm[slot]];
             const int nb = P.n_bin;
             const double en_min = P.en_min[lad];
             const double delta_en = xdiv(xsub(P.en_max[lad], en_min), (double)(nb - 1));
@@ -641,12 +551,12 @@ __global__ void runner_cycle_end_kernel(const DevParams P, const RunnerDev R, co
 }
 
 // slot-ordered copies of the configuration-side state for ptmc_download_states
-__global__ void runner_gather_kernel(const DevParams P, const RunnerDev R) {
+__global__ void runner_gather_kernel(const DevParams P, const double* __restrict__ pos_c, const double* __restrict__ en_c) {
     const i64 rep = blockIdx.x;
     const int T = P.n_traj, N = P.n_atoms;
     const i64 cfg = (rep / T) * T + P.perm_g[rep];
-    for (int k = threadIdx.x; k < 3 * N; k += blockDim.x) P.pos[rep * 3 * N + k] = R.pos_c[cfg * 3 * N + k];
-    if (threadIdx.x == 0) P.en_tot[rep] = R.en_c[cfg];
+    for (int k = threadIdx.x; k < 3 * N; k += blockDim.x) P.pos[rep * 3 * N + k] = pos_c[cfg * 3 * N + k];
+    if (threadIdx.x == 0) P.en_tot[rep] = en_c[cfg];
 }
 // compact g matrix / per-atom energies of the configuration in one slot (tests): g_out [N][n_sym], e_out [N]
 __global__ void runner_export_kernel(const DevParams P, const RunnerDev R, i64 rep, double* g_out, double* e_out) {
@@ -701,12 +611,18 @@ void runner_launch_init(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaS
 int runner_launch_cycle(const DevParams& P, const RunnerDev& R, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st) {
     rn_moves_fn f = pick_moves(R, dbg);
     f<<<(unsigned)(n_ladders * P.n_traj), RN_THREADS, runner_smem_bytes(P.n_atoms, R), st>>>(P, R, cyc_in_launch);
-    if (dbg) runner_cycle_end_kernel<true><<<(unsigned)n_ladders, 32, 0, st>>>(P, R, idx, cyc_in_launch, sample);
-    else runner_cycle_end_kernel<false><<<(unsigned)n_ladders, 32, 0, st>>>(P, R, idx, cyc_in_launch, sample);
+    runner_launch_cycle_end(P, R.en_c, n_ladders, idx, cyc_in_launch, sample, dbg, st);
     return 2;
 }
+void runner_launch_cycle_end(const DevParams& P, const double* en_c, i64 n_ladders, i64 idx, i64 cyc_in_launch, int sample, bool dbg, cudaStream_t st) {
+    if (dbg) runner_cycle_end_kernel<true><<<(unsigned)n_ladders, 32, 0, st>>>(P, en_c, idx, cyc_in_launch, sample);
+    else runner_cycle_end_kernel<false><<<(unsigned)n_ladders, 32, 0, st>>>(P, en_c, idx, cyc_in_launch, sample);
+}
 void runner_launch_gather(const DevParams& P, const RunnerDev& R, i64 n_rep, cudaStream_t st) {
-    runner_gather_kernel<<<(unsigned)n_rep, 64, 0, st>>>(P, R);
+    runner_launch_gather_ptr(P, R.pos_c, R.en_c, n_rep, st);
+}
+void runner_launch_gather_ptr(const DevParams& P, const double* pos_c, const double* en_c, i64 n_rep, cudaStream_t st) {
+    runner_gather_kernel<<<(unsigned)n_rep, 64, 0, st>>>(P, pos_c, en_c);
 }
 void runner_launch_export(const DevParams& P, const RunnerDev& R, i64 rep, double* g_out, double* e_out, cudaStream_t st) {
     runner_export_kernel<<<1, 256, 0, st>>>(P, R, rep, g_out, e_out);

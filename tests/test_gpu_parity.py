@@ -803,3 +803,127 @@ def test_periodic_direction_dependent_potentials(pot_name, bc_cls, oracle):
     (sg, hg, rg), (sc, hc, rc) = res
     assert np.array_equal(sg["counters"], sc["counters"]) and np.array_equal(hg, hc) and np.array_equal(rg[0], rc[0])
     np.testing.assert_allclose(sg["pos"], sc["pos"], rtol=1e-11, atol=1e-11)
+
+
+# ---- two species: RuNNerPotential2Atom + NNVT atom swaps (scripts/brass55.jl) ------------------------------------------------
+BRASS6 = np.array([[2.36, 2.36, 0.0], [6.99, 2.33, 0.0], [2.33, 6.99, 0.0], [-2.36, 2.36, 0.0], [-6.99, 2.33, 0.0], [-2.33, 6.99, 0.0]])
+
+
+def _brass6_deck(n_traj=2, n_swaps=1, cycles=10, t=(500.0, 650.0)):
+    """test/test_states.jl:110-125 ("States NNVT"): Cu4Zn2, SphericalBC(radius = 8), NNVT([4, 2]), TempGrid{2}(500, 650)"""
+    return (P.MCParams(cycles, n_traj, 6), P.TempGrid(t[0], t[1], n_traj), P.Config(BRASS6, P.SphericalBC(radius=8.0)),
+            P.host.brass_runner_potential(4, 2), P.host.NNVT((4, 2), n_atom_swaps=n_swaps))
+
+
+def test_brass_known_answers_on_the_device(oracle):
+    """The reference's own two-species known answers (test/test_potentials.jl:86, test/test_states.jl:159,175) through the CUDA
+    kernels: the replay stream is the index draw that selects the move type followed by Julia's Random.seed!(123) stream."""
+    from ptmc_b200 import multi
+    from parity import xoshiro_streams
+    from test_runner_oracle import _raw_for_index
+    seed123 = xoshiro_streams(np.array([multi.julia_seed_state(123)], dtype=np.uint64), 8)[0]
+    mcp, temp, start, pot, ens = _brass6_deck()
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=1, seed=5, rng_mode=abi.RNG_REPLAY)
+    pos, box = initial_arrays(mcp, start, 1)
+    half = np.uint64(1) << np.uint64(63)
+    for kind in ("move", "swap"):
+        slot = np.zeros((1, 2, 64), dtype=np.uint64)
+        if kind == "move":
+            slot[0, :, 0] = _raw_for_index(1, 7); slot[0, :, 1:4] = seed123[:3]; base = 5
+        else:
+            slot[0, :, 0] = _raw_for_index(7, 7); slot[0, :, 1:3] = seed123[:2]; base = 4
+        for m in range(6):
+            slot[0, :, base + 5 * m] = _raw_for_index(2, 7)
+            slot[0, :, base + 5 * m + 1:base + 5 * m + 4] = half                  # rand() = 0.5: zero displacement
+        lad = np.full((1, 8), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+        out = []
+        for cls in (Engine, oracle.OracleEngine):
+            eng = cls(cfg)
+            eng.upload_states(pos, box)
+            e0 = eng.download_states(("en_tot",))["en_tot"].copy()
+            eng.set_replay(slot, lad)
+            eng.trace_enable(1)
+            eng.set_hist_bounds(-1.0, 0.0)
+            eng.run_cycles(1, 1, False)
+            out.append((e0, eng.trace_download(), eng.download_states(), eng.runner_state(0, 0)))
+            eng.close()
+        (e0g, tg, sg, (gg, eg)), (e0c, tc, sc, (gc, ec)) = out
+        assert e0g[0, 0] == pytest.approx(-0.261652899, rel=1e-8)                 # test/test_potentials.jl:86
+        np.testing.assert_allclose(e0g, e0c, rtol=1e-13)
+        assert np.array_equal(tg["move_index"], tc["move_index"]) and np.array_equal(tg["accepted"], tc["accepted"])
+        want = -7.5971516e-5 if kind == "move" else -0.0017084901948                # test/test_states.jl:159 / :175
+        assert tg["delta_en"][0, 0, 0, 0] == pytest.approx(want, rel=2e-8)
+        np.testing.assert_allclose(tg["delta_en"], tc["delta_en"], rtol=1e-10, atol=1e-16)
+        assert tg["move_index"][0, 0, 0, 0] == (1 if kind == "move" else 7 + (3 << 10) + (6 << 20))
+        assert np.array_equal(sg["pos"], sc["pos"]) and np.array_equal(sg["counters"], sc["counters"])
+        if kind == "swap":
+            assert np.array_equal(sg["pos"][0, 0, 2], BRASS6[5]) and np.array_equal(sg["pos"][0, 0, 5], BRASS6[2])   # :185-186
+        np.testing.assert_allclose(sg["en_tot"], sc["en_tot"], rtol=1e-12)
+        np.testing.assert_allclose(gg, gc, rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose(eg, ec, rtol=1e-11, atol=1e-15)
+
+
+def test_brass6_nnvt_replay_and_production(oracle):
+    # many cycles of atom moves + swaps + exchanges on the small cluster: per-move trace against the oracle, then the production
+    # stream (BATCH8) trajectory
+    mcp, temp, start, pot, ens = _brass6_deck(n_traj=4, n_swaps=3, t=(500.0, 2500.0))
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=3, n_cycles=40, seed=29, n_adjust=5, max_displ=np.full((3, 4, 4), 0.6),
+                        bounds=(-0.5, 0.0, None, None))
+    compare_traces(gpu, cpu)
+    swaps = gpu["trace"]["move_index"] > 1024
+    assert swaps.sum() > 100 and gpu["trace"]["accepted"][swaps].sum() > 10 and gpu["trace"]["accepted"][~swaps].mean() > 0.2
+    assert gpu["trace"]["exchange"][..., 0].sum() > 3
+    res = _free_run_pair(_brass6_deck(n_traj=4, n_swaps=3, t=(500.0, 2500.0)), 3, 41, abi.RNG_BATCH8, 40, bounds=(-0.5, 0.0))
+    _assert_same_trajectory(res, e_rtol=1e-11)
+    res = _free_run_pair(_brass6_deck(n_traj=4, n_swaps=3, t=(500.0, 2500.0)), 2, 43, abi.RNG_XOSHIRO, 20, bounds=(-0.5, 0.0))
+    _assert_same_trajectory(res, e_rtol=1e-11)
+
+
+def test_brass55_nnvt_replay(oracle):
+    # scripts/brass55.jl sizes: Cu50Zn5, 5 radial + 26 angular two-species symmetry functions, two 88-20-20-1 networks; atom moves
+    # AND swaps (6 swap slots per cycle so that a short run holds many), temperatures high enough that swaps are accepted
+    mcp, temp, start, pot, ens = P.host.deck_brass55(n_traj=3, cycles=2, n_swaps=6)
+    temp = P.TempGrid(600.0, 3000.0, 3)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=2, seed=19, n_adjust=1, max_displ=np.full((1, 3, 4), 0.35))
+    worst = compare_traces(gpu, cpu)
+    swaps = gpu["trace"]["move_index"] > 1024
+    assert swaps.sum() >= 10 and gpu["trace"]["accepted"][swaps].sum() >= 1
+    assert 0.1 < gpu["trace"]["accepted"][~swaps].mean() < 0.9
+    print("brass55 max |dE err|", worst, "swaps", int(swaps.sum()), "accepted", int(gpu["trace"]["accepted"][swaps].sum()))
+
+
+def test_brass55_state_matrices_and_production(oracle):
+    from oracle import oracle as orc
+    mcp, temp, start, pot, ens = P.host.deck_brass55(n_traj=2, cycles=1, n_swaps=4)
+    temp = P.TempGrid(800.0, 3000.0, 2)
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=1, seed=6, rng_mode=abi.RNG_BATCH8)
+    pos, box = initial_arrays(mcp, start, 1)
+    md = np.full((1, 2, 4), 0.3)
+    engs = [Engine(cfg), orc.OracleEngine(cfg)]
+    for e in engs:
+        e.upload_states(pos, box, md)
+    g0, e0 = engs[0].runner_state(0, 1)
+    g1, e1 = engs[1].runner_state(0, 1)
+    assert g0.shape == (55, 88)
+    np.testing.assert_allclose(g0, g1, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(e0, e1, rtol=1e-12)
+    for e in engs:
+        e.seed(6)
+        e.run_cycles(1, 1, False)
+        e.sync()
+    sg, sc = engs[0].download_states(), engs[1].download_states()
+    assert np.array_equal(sg["counters"], sc["counters"]) and np.array_equal(sg["pos"], sc["pos"])
+    np.testing.assert_allclose(sg["en_tot"], sc["en_tot"], rtol=1e-11)
+    moved = (sg["pos"] != pos).any(axis=-1)
+    assert moved.sum() > 20
+    for slot in range(2):
+        gg, eg = engs[0].runner_state(0, slot)
+        gc, ec = engs[1].runner_state(0, slot)
+        np.testing.assert_allclose(gg, gc, rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(eg, ec, rtol=1e-10, atol=1e-14)
+    # the running state is a state: a fresh upload of the final configuration gives the same energies
+    eng2 = Engine(cfg)
+    eng2.upload_states(sg["pos"], sg["box"])
+    np.testing.assert_allclose(sg["en_tot"], eng2.download_states(("en_tot",))["en_tot"], rtol=1e-11)
+    for e in engs + [eng2]:
+        e.close()
