@@ -680,12 +680,16 @@ extern "C" PTMC_API int ptmc_run_phase(ptmc_handle* h, int64_t first_idx, int64_
     const bool tracing = h->trace_cap > 0;
     if (tracing && h->trace_n + n_cycles > h->trace_cap) return fail(h, PTMC_ERR_ARG, "trace capacity %lld exceeded", (long long)h->trace_cap);
     CU(h, cudaSetDevice(h->device));
-    if (tracing && h->cfg.rng_mode == PTMC_RNG_BATCH8) return fail(h, PTMC_ERR_STATE, "tracing needs rng_mode XOSHIRO or REPLAY (sequential-stream kernels)");
+#ifndef PTMC_PROD_TRACE
+    if (tracing && h->cfg.rng_mode == PTMC_RNG_BATCH8 && !h->runner)
+        return fail(h, PTMC_ERR_STATE, "tracing the production (BATCH8) kernels needs the test build lib/libptmc_b200_trace.so (-DPTMC_PROD_TRACE); "
+                                       "this library traces rng_mode XOSHIRO / REPLAY");
+#endif
     const int dbg = h->cfg.rng_mode != PTMC_RNG_BATCH8 ? 1 : 0;
     if (h->runner) {
         // one launch pair per cycle: the exchange between replicas happens at the kernel boundary
         DevParams P = h->P;
-        P.trace_cap = h->trace_cap; P.trace_base = h->trace_n;
+        P.trace_cap = h->trace_cap; P.trace_base = h->trace_n; P.trace_on = h->trace_cap > 0 ? 1 : 0;
         P.tr_index = static_cast<int32_t*>(h->d_trace[0]); P.tr_de = static_cast<double*>(h->d_trace[1]);
         P.tr_acc = static_cast<uint8_t*>(h->d_trace[2]); P.tr_exc = static_cast<int32_t*>(h->d_trace[3]);
         for (i64 k = 0; k < n_cycles; ++k)
@@ -706,7 +710,7 @@ extern "C" PTMC_API int ptmc_run_phase(ptmc_handle* h, int64_t first_idx, int64_
         const i64 k = std::min(max_chunk, n_cycles - done);
         DevParams P = h->P;
         P.phase = phase;
-        P.trace_cap = h->trace_cap; P.trace_base = h->trace_n;
+        P.trace_cap = h->trace_cap; P.trace_base = h->trace_n; P.trace_on = h->trace_cap > 0 ? 1 : 0;
         P.tr_index = static_cast<int32_t*>(h->d_trace[0]); P.tr_de = static_cast<double*>(h->d_trace[1]);
         P.tr_acc = static_cast<uint8_t*>(h->d_trace[2]); P.tr_exc = static_cast<int32_t*>(h->d_trace[3]);
         f<<<(unsigned)h->cfg.n_ladders, h->threads, h->smem_k[dbg ? 1 : 0], h->stream>>>(P, first_idx + done, k, sample);

@@ -87,6 +87,7 @@ struct DevParams {
     // trace (parity mode)
     int32_t* tr_index; double* tr_de; uint8_t* tr_acc; int32_t* tr_exc;
     i64 trace_cap, trace_base;
+    int trace_on;       // trace_cap > 0 as a 32-bit flag: one uniform predicate in the move loop of every instantiation
     int* error;         // device error word (most negative ptmc_status wins)
 };
 

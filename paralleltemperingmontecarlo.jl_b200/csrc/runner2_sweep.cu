@@ -392,7 +392,7 @@ runner2_moves_kernel(const DevParams P, const Runner2Dev R, const i64 cyc_in_lau
             if (P.replay) { S.draws = P.slot_draws + rep * P.slot_len; S.len = P.slot_len; S.pos = P.slot_cursor[rep]; }
         }
     }
-    const bool tracing = DBG && P.trace_cap > 0;
+    const bool tracing = P.trace_cap > 0;
     int err = 0;
     __syncthreads();
 
@@ -506,7 +506,7 @@ runner2_moves_kernel(const DevParams P, const Runner2Dev R, const i64 cyc_in_lau
         // ============================================================ phase 4: acc_test! src/MCRun.jl:122-132 ==
         const double de = xsub(new_en, en);
         const bool acc = metropolis_accept(-xmul(de, beta), misc[4]);
-        if (DBG) {
+        {
             if (tracing && tid == 0) {
                 size_t o = ((((size_t)lad * P.trace_cap + P.trace_base + cyc_in_launch) * T + slot) * P.n_steps) + step;
                 P.tr_index[o] = (int)misc[9]; P.tr_de[o] = de; P.tr_acc[o] = acc ? 1 : 0;

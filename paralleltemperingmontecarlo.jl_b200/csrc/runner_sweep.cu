@@ -229,7 +229,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
             if (P.replay) { S.draws = P.slot_draws + rep * P.slot_len; S.len = P.slot_len; S.pos = P.slot_cursor[rep]; }
         }
     }
-    const bool tracing = DBG && P.trace_cap > 0;
+    const bool tracing = P.trace_cap > 0;
     int err = 0;
     __syncthreads();
 
@@ -440,7 +440,7 @@ runner_moves_kernel(const DevParams P, const RunnerDev R, const i64 cyc_in_launc
         // ============================================================ phase 4: acc_test! src/MCRun.jl:122-132 ==
         const double de = xsub(new_en, en);
         const bool acc = metropolis_accept(-xmul(de, beta), misc[4]);
-        if (DBG) {
+        {
             if (tracing && tid == 0) {
                 size_t o = ((((size_t)lad * P.trace_cap + P.trace_base + cyc_in_launch) * T + slot) * P.n_steps) + step;
                 P.tr_index[o] = i + 1; P.tr_de[o] = de; P.tr_acc[o] = acc ? 1 : 0;
@@ -510,7 +510,7 @@ __global__ void runner_cycle_end_kernel(const DevParams P, const double* __restr
                 ca[PTMC_C_EXC_ACC] += 1; cb[PTMC_C_EXC_ACC] += 1;
                 const int t = perm[a]; perm[a] = perm[b]; perm[b] = t;
             }
-            if (DBG) {
+            {
                 if (P.trace_cap > 0) {
                     int32_t* e = P.tr_exc + ((size_t)lad * P.trace_cap + P.trace_base + cyc_in_launch) * 3;
                     e[0] = 1; e[1] = n_exc; e[2] = ex_acc;

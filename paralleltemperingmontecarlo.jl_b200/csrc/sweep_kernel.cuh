@@ -241,7 +241,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     int smp_phase = (int)(first_idx % P.mc_sample);
     __syncthreads();
 
-    const bool tracing = DBG && P.trace_cap > 0;
+#ifdef PTMC_PROD_TRACE         // test-only build (lib/libptmc_b200_trace.so): the production instantiations write the per-move trace
+    const bool tracing = P.trace_on != 0;      // under a runtime flag; 3 instructions per move (0.8 % on C2), so the shipped library leaves it out
+#else
+    const bool tracing = DBG && P.trace_on != 0;
+#endif
     int err = 0;
     unsigned xpar = 0;      // phase parities of the two exchange mbarriers this warp takes part in (bit 0: with the next warp, bit 1: with the previous one)
 
@@ -650,13 +654,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     }
                     __syncwarp(gmask);
                 }
-                if (DBG) {
-                    if (tracing && g == 0) {
-                        size_t o = ((((size_t)lad * P.trace_cap + P.trace_base + cyc) * T + slot) * P.n_steps) + step;
-                        P.tr_index[o] = index; P.tr_de[o] = de; P.tr_acc[o] = acc ? 1 : 0;
-                    }
-                    if (S.exhausted) err = PTMC_ERR_REPLAY;
+                if (tracing) {      // uniform branch; the lanes of a group store identical values to one address
+                    size_t o = ((((size_t)lad * P.trace_cap + P.trace_base + cyc) * T + slot) * P.n_steps) + step;
+                    P.tr_index[o] = index; P.tr_de[o] = de; P.tr_acc[o] = acc ? 1 : 0;
                 }
+                if (DBG) { if (S.exhausted) err = PTMC_ERR_REPLAY; }
             }
             if (g == 0) {
                 scal[4 * c] = en;
@@ -716,11 +718,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     exc_cnt[2 * a + 1] += 1; exc_cnt[2 * b + 1] += 1;
                     perm[a] = cb; perm[b] = ca;       // exc_trajectories! :115-124
                 }
-                if (DBG) {
-                    if (tracing) {
-                        int32_t* e = P.tr_exc + ((size_t)lad * P.trace_cap + P.trace_base + cyc) * 3;
-                        e[0] = 1; e[1] = ex_n; e[2] = ex_acc;
-                    }
+                if (tracing) {
+                    int32_t* e = P.tr_exc + ((size_t)lad * P.trace_cap + P.trace_base + cyc) * 3;
+                    e[0] = 1; e[1] = ex_n; e[2] = ex_acc;
                 }
             }
             if (meet) { pair_barrier(xbar, (xpar >> side) & 1u); xpar ^= 1u << side; }

@@ -217,6 +217,90 @@ def test_batch8_production_mode_eam_and_redraws():
     _assert_same_trajectory(res)
 
 
+def _production_trace_pair(deck, n_ladders, seed, cycles, bounds, *, eq_cycles=0, max_displ=None, lanes=0, positions_exact=True, rel=1e-10):
+    """Per-move trace of the PRODUCTION kernels (rng_mode BATCH8: the instantiations bench.py times) against the oracle stepping
+    the same eight substreams per slot: move index, accept bit and exchange record bit-identical, per-move delta energy to
+    north_star's 1e-10 (src/MCRun.jl:122-162).  Runs on the test-only build lib/libptmc_b200_trace.so (same sources,
+    -DPTMC_PROD_TRACE: those instantiations write the trace under a runtime flag; the shipped library leaves the three
+    instructions per move out), and checks that the shipped library follows the same trajectory."""
+    from oracle import oracle
+    trace_lib = abi.load_library(abi.LIB_PATH.parent / "libptmc_b200_trace.so")
+    mcp, temp, start, pot, ens = deck
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=n_ladders, seed=seed, rng_mode=abi.RNG_BATCH8, lanes_per_replica=lanes)
+    pos, box = initial_arrays(mcp, start, n_ladders)
+    out = []
+    for make, traced in ((lambda: Engine(cfg, lib=trace_lib), True), (lambda: oracle.OracleEngine(cfg), True), (lambda: Engine(cfg), False)):
+        eng = make()
+        eng.upload_states(pos, box, max_displ)
+        init = eng.download_states(("en_tot",))["en_tot"].copy()
+        eng.seed(seed)
+        if eq_cycles:
+            eng.run_cycles(1, eq_cycles, False)
+            eng.reset_counters()
+        if traced:
+            eng.trace_enable(cycles)
+        eng.set_hist_bounds(*bounds)
+        eng.run_cycles(1, cycles, True)
+        eng.sync()
+        out.append({"init_en": init, "states": eng.download_states(), "hist": eng.download_hist(),
+                    "hist_reduced": eng.download_hist(reduce_ladders=True), "trace": eng.trace_download() if traced else None,
+                    "rng": eng.get_rng_states()})
+        eng.close()
+    gpu, cpu, shipped = out
+    worst = compare_traces(gpu, cpu, positions_exact=positions_exact, rel=rel)
+    assert np.array_equal(gpu["rng"][0], cpu["rng"][0]) and np.array_equal(gpu["rng"][1], cpu["rng"][1])
+    # the shipped library (no trace code in these kernels) walks the same trajectory bit for bit
+    for k in ("pos", "box", "en_tot", "max_displ", "counters", "ham"):
+        assert np.array_equal(shipped["states"][k], gpu["states"][k]), k
+    assert np.array_equal(shipped["hist"], gpu["hist"]) and np.array_equal(shipped["rng"][0], gpu["rng"][0])
+    return gpu, cpu, worst
+
+
+def test_shipped_library_refuses_production_trace():
+    mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=8, cycles=5)
+    eng = Engine(sweep_config(mcp, temp, start, pot, ens, n_ladders=1, seed=1, rng_mode=abi.RNG_BATCH8))
+    pos, box = initial_arrays(mcp, start, 1)
+    eng.upload_states(pos, box)
+    eng.trace_enable(2)
+    with pytest.raises(PtmcError, match="libptmc_b200_trace"):
+        eng.run_cycles(1, 2, False)
+    eng.close()
+
+
+def test_production_kernel_trace_c2_ne55():
+    # BASELINE C2 at its own ladder shape: 24 temperatures x 8 lanes = sweep_kernel<8, ELJ_EVEN, SPHERE, false, 7, 6, FULLW>, the
+    # kernel of the headline number; step sizes adapted during 100 equilibration cycles as bench.py's pilot does
+    mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=24, cycles=40)
+    mcp.n_adjust = 10
+    gpu, _, worst = _production_trace_pair((mcp, temp, start, pot, ens), 3, 77, 40, (-0.035, -0.02, None, None), eq_cycles=100)
+    acc = gpu["trace"]["accepted"].mean()
+    assert 0.3 < acc < 0.75 and gpu["trace"]["exchange"][..., 0].sum() > 3
+    print("C2 production trace: %d moves, acceptance %.3f, max |dE err| %.2e" % (gpu["trace"]["accepted"].size, acc, worst))
+
+
+def test_production_kernel_trace_c1_c3_c4():
+    # C1 Ne13 at 32 temperatures (ROT kernel, 4 lanes), C3 Cu55 EAM at 28 temperatures (unrolled EAM kernel, trial components in
+    # registers), C4 pbc216 at 16 temperatures through the frozen -> thawed switch with volume moves
+    deck = P.host.deck_ne13(n_traj=32, cycles=60)
+    deck[0].n_adjust = 10
+    gpu, _, w1 = _production_trace_pair(deck, 4, 5, 60, (-0.006, -0.003, None, None), eq_cycles=100)
+    assert 0.3 < gpu["trace"]["accepted"].mean() < 0.8
+    deck = P.host.deck_cu55_eam(n_traj=28, cycles=15)
+    deck[0].n_adjust = 5
+    gpu, _, w3 = _production_trace_pair(deck, 2, 9, 15, (-6.3, -5.6, None, None), eq_cycles=30)
+    assert 0.2 < gpu["trace"]["accepted"].mean() < 0.95
+    mcp, temp, start, pot, ens = P.host.deck_pbc216(n_traj=16, cycles=30)
+    md = np.full((1, 16, 4), 0.1)
+    md[:, :, 0] = 0.5
+    v0 = P.get_volume(start[0].boundary_condition)
+    gpu, _, w4 = _production_trace_pair((mcp, temp, start, pot, ens), 1, 3, 30, (-0.5, 1.5, 0.8 * v0, 2.0 * v0), max_displ=md, positions_exact=False)
+    idx, acc = gpu["trace"]["move_index"], gpu["trace"]["accepted"]
+    assert (idx == 217).sum() > 100 and acc[idx == 217].sum() > 5                     # volume moves, some accepted
+    moved = [len(np.unique(idx[0, :, s][(acc[0, :, s] == 1) & (idx[0, :, s] <= 216)])) for s in range(16)]
+    assert min(moved) > 150, moved
+    print("production traces: max |dE err| C1 %.2e, C3 %.2e, C4 %.2e" % (w1, w3, w4))
+
+
 def test_energy_bookkeeping_at_full_size():
     # size-independent property at BASELINE C2's full batch (4096 ladders x 24 temperatures): after a sweep
     # the running en_tot of every replica equals the energy recomputed from its positions (the init kernel).
@@ -541,6 +625,46 @@ def test_forward_all_ones_kat():
     ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
     lib.forward(dp(x), i32(88), i32(4), ip(nodes), i32(2), i32(npar), dp(params), ip(act), dp(e))
     assert np.allclose(e, 21.0, rtol=1e-14)
+
+
+def _device_forward(x, nodes, act, params):
+    """the exported `forward` of libptmc_b200.so with the Fortran symbol's calling convention (every argument by reference)"""
+    import ctypes as C
+    lib = abi.load_library()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    nodes = np.ascontiguousarray(nodes, dtype=np.int32); act = np.ascontiguousarray(act, dtype=np.int32)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    e = np.zeros(x.shape[0])
+    i32 = lambda v: C.byref(C.c_int32(v))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    ret = lib.forward(dp(x), i32(int(nodes[0])), i32(len(nodes)), ip(nodes), i32(x.shape[0]), i32(len(params)), dp(params), ip(act), dp(e))
+    return e, ret
+
+
+def test_forward_export_against_reference_binary(oracle):
+    """The drop-in `forward` on REAL weights and on random networks: column-major W, bias offsets, the activation index shift and
+    the [batch][n_in] input layout are all visible here (the all-ones KAT sees none of them).  Reference = the reference's own
+    binary (oracle/_ref/librunnerjulia.so) where it was built, and always the oracle restatement (itself pinned to that binary)."""
+    from oracle import ref_forward
+    rng = np.random.default_rng(12)
+    cases = []
+    nodes, act = [88, 20, 20, 1], [1, 2, 2, 1]
+    for w in (P.host.load_weights(), P.host.load_weights_zn()):               # weights.029.data / weights.030.data
+        cases.append((rng.uniform(0.0, 1.0, (55, 88)), nodes, act, w))        # batch 55 = one Cu55 configuration
+    cases.append((rng.normal(size=(7, 5)), [5, 4, 3, 1], [1, 2, 2, 1], rng.normal(size=5 * 4 + 4 + 4 * 3 + 3 + 3 + 1)))
+    cases.append((rng.normal(size=(130, 5)), [5, 4, 3, 1], [1, 1, 2, 2], rng.normal(size=5 * 4 + 4 + 4 * 3 + 3 + 3 + 1)))   # mixed activations, tanh output
+    cases.append((rng.normal(size=(3, 6)), [6, 9, 2, 5, 1], [1, 2, 1, 2, 1], rng.normal(scale=0.5, size=6 * 9 + 9 + 9 * 2 + 2 + 2 * 5 + 5 + 5 + 1)))
+    cases.append((rng.normal(size=(1, 4)), [4, 1], [1, 2], rng.normal(size=5)))                                            # a single layer, batch 1
+    for x, nd, ac, w in cases:
+        got, ret = _device_forward(x, nd, ac, w)
+        want = oracle.runner_forward(x, nd, ac, w)
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-15)
+        assert ret == got[-1]                                                  # the Fortran function's return register
+        if ref_forward.available():
+            np.testing.assert_allclose(got, ref_forward.ref_forward(x, nd, ac, w), rtol=1e-13, atol=1e-15)
+    # error behaviour: inconsistent sizes give NaN instead of reading out of bounds
+    assert np.isnan(_device_forward(np.ones((2, 4)), [4, 3, 1], [1, 2, 1], np.ones(5))[1])  # too few parameters
 
 
 def test_eljb_magnetic_field_potential(oracle):
