@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — MC moves/s of the parallel-tempering sweep hot path (BASELINE.json metric).
 
-Workload (config.workload): BASELINE C2 — Ne55 extended-Lennard-Jones NVT, 24-temperature ladder
+Headline workload (config.workload): BASELINE C2 — Ne55 extended-Lennard-Jones NVT, 24-temperature ladder
 (scripts/ne55.jl), 4096 independent ladders batched per GPU, ladders sharded across GPUs (weak scaling,
 no data-path collective; one NCCL all-reduce of the ladder-summed energy histogram at the end).
 One "step" = `--cycles` calls of mc_cycle! (src/MCRun.jl:215) for every ladder of the rank =
@@ -9,13 +9,18 @@ n_ladders * 24 * 55 * cycles MC moves, including exchange, step-size adaptation 
 
   value    device-resident throughput: states already in HBM, K steps timed with CUDA events on the
            launching stream, max over ranks.
-  e2e      the same metric through the reference-facing call with HOST buffers: every step uploads the
+  e2e      the same metric through the reference-facing calls with HOST buffers: every step uploads the
            start configurations from pinned host memory (MCState construction), runs the cycles and
-           downloads positions / energies / step sizes / counters / ham and the histogram.
-  roofline FP64-pipe bound (BASELINE.json: "% FP64 roofline"): achieved = moves/s * W, W = 36*(N-1) = 1944
-           algorithmic flops per move, peak = DFMA-chain peak measured live by ptmc_fp64_peak.
+           downloads positions / energies / step sizes / counters / ham and the histogram into pinned host
+           memory.  The rank's ladders run as two half-batches (two handles, two streams, two host threads),
+           so the copies of one half overlap the sweep of the other; nothing is skipped.
+  roofline FP64-pipe bound (BASELINE.json: "% FP64 roofline"): achieved = moves/s * W, W = algorithmic flops
+           per move, peak = DFMA-chain peak measured live by ptmc_fp64_peak.
   cpu_baseline / --impl reference: the oracle's C restatement of the reference's CPU path, OpenMP over
            all host cores, on a bounded sample of the same workload (Julia itself is not in the image).
+  configs  the other BASELINE configs (C1 Ne13, C3 Cu55 EAM, C4 pbc216 NPT, C5 Cu55 RuNNer) measured in the same
+           run with the same method (pilot-adapted step sizes, >= 3 warm-up and >= 3 timed steps, CUDA events,
+           e2e, roofline, CPU sample); under --gpus N they shard over the ranks like C2.
 """
 from __future__ import annotations
 
@@ -34,10 +39,9 @@ import numpy as np
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-N_TRAJ, N_ATOMS = 24, 55
-W_FLOPS_PER_MOVE = 36 * (N_ATOMS - 1)          # (8 + 14 + 14) flops per pair, N-1 pairs
 METRIC = "MC moves/sec (all replicas)"
 UNIT = "moves/s"
+SEED = 1234
 
 
 def parse():
@@ -46,36 +50,67 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ladders", type=int, default=4096, help="independent PT ladders per GPU")
-    ap.add_argument("--cycles", type=int, default=200, help="mc_cycle! calls per step")
+    ap.add_argument("--ladders", type=int, default=4096, help="independent PT ladders per GPU (C2)")
+    ap.add_argument("--cycles", type=int, default=200, help="mc_cycle! calls per step (C2)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per replica (0 = auto)")
-    ap.add_argument("--cpu-ladders", type=int, default=0, help="ladders in the CPU sample (0 = 8 per core)")
+    ap.add_argument("--cpu-ladders", type=int, default=0, help="ladders in the CPU sample of C2 (0 = 8 per core)")
     ap.add_argument("--cpu-cycles", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="c1,c3,c4,c5", help="other BASELINE configs measured next to the headline ('' = none)")
     return ap.parse_args()
 
 
-def workload_config(ladders, cycles):
-    return {"workload": "Ne55 ELJ NVT (scripts/ne55.jl), 24-temperature ladder, %d independent PT ladders per GPU" % ladders,
-            "n_atoms": N_ATOMS, "n_traj": N_TRAJ, "ladders_per_gpu": ladders, "cycles_per_step": cycles,
-            "moves_per_step_per_gpu": ladders * N_TRAJ * N_ATOMS * cycles,
-            "rng": "PTMC_RNG_BATCH8: 8 Xoshiro256++ substreams per slot (Julia's generator), seeded Random.seed!(seed + k)",
-            "l2": "flushed between timed steps (256 MiB write); resident state 130 MB > 126 MB L2"}
+# ------------------------------------------------------------------------------------------- workloads --
+def specs(args):
+    """Every BASELINE config: deck, ladders per GPU (whole waves of CTAs on 148 SMs), cycles per step, pilot that adapts the step
+    sizes (src/Exchange.jl:250-263), W = algorithmic flops per move (SURVEY §8d / BASELINE.md §3), CPU sample (ladders, cycles)."""
+    import ptmc_b200 as P
+    H = P.host
+    return {
+        "c2": dict(workload="Ne55 ELJ NVT (scripts/ne55.jl), 24-temperature ladder, %d independent PT ladders per GPU" % args.ladders,
+                   deck=lambda c: H.deck_ne55(n_traj=24, cycles=c), ladders=args.ladders, cycles=args.cycles, eq=200,
+                   pilot=dict(ladders=64, cycles=3000, n_adjust=100), W=36 * 54, W_note="36 (N-1): 8 distance + 14 + 14 energy flops per pair",
+                   cpu=(args.cpu_ladders or 0, args.cpu_cycles), lanes=args.lanes),
+        "c1": dict(workload="Ne13 ELJ NVT (examples/ne13.jl), 32-temperature ladder, 8880 independent PT ladders per GPU",
+                   deck=lambda c: H.deck_ne13(n_traj=32, cycles=c), ladders=8880, cycles=400, eq=200,
+                   pilot=dict(ladders=148, cycles=3000, n_adjust=100), W=36 * 12, W_note="36 (N-1)", cpu=(64, 400), lanes=0),
+        "c3": dict(workload="Cu55 embedded-atom NVT (scripts/cu55.jl), 28-temperature ladder, 2048 independent PT ladders per GPU",
+                   deck=lambda c: H.deck_cu55_eam(n_traj=28, cycles=c), ladders=2048, cycles=40, eq=100,
+                   pilot=dict(ladders=148, cycles=1500, n_adjust=50), W=20 * 54 + 5 * 55,
+                   W_note="20 flops x 54 pairs + 5 x 55 atoms (+ 324 specials: rsqrt / pow), SURVEY §8d", cpu=(32, 40), lanes=0,
+                   pair_evals_per_move=2 * 54),
+        "c4": dict(workload="pbc216 ELJ NPT, RhombicBC, volume moves (scripts/pbc216.jl), 16-temperature ladder, 592 independent PT ladders per GPU",
+                   deck=lambda c: H.deck_pbc216(n_traj=16, cycles=c), ladders=592, cycles=100, eq=60,
+                   pilot=dict(ladders=148, cycles=600, n_adjust=20), W=14125,
+                   W_note="(216 x 12470 + 371520) / 217: minimum-image atom moves + one full-energy volume move per cycle", cpu=(16, 20), lanes=0),
+        "c5": dict(workload="Cu55 RuNNer neural-network potential NVT (scripts/cu55.jl, boundary 0), 28-temperature ladder, 37 independent PT ladders per GPU",
+                   deck=lambda c: H.deck_cu55_runner(n_traj=28, cycles=c), ladders=37, cycles=4, eq=4,
+                   pilot=dict(ladders=37, cycles=24, n_adjust=2, start_from="c3"), W=3.6e6,
+                   W_note="symmetry functions 3.35 Mflop + forward pass 0.24 Mflop as the reference evaluates them", cpu=(1, 1), lanes=0),
+    }
+
+
+def workload_config(spec):
+    mcp = spec["deck"](spec["cycles"])[0]
+    return {"workload": spec["workload"], "n_atoms": mcp.n_atoms, "n_traj": mcp.n_traj, "ladders_per_gpu": spec["ladders"],
+            "cycles_per_step": spec["cycles"],
+            "rng": "PTMC_RNG_BATCH8: 8 Xoshiro256++ substreams per slot (Julia's generator)",
+            "l2": "flushed between timed steps (256 MiB write)"}
 
 
 # --------------------------------------------------------------------------------------- CPU baseline --
-def cpu_sample(ladders, cycles, threads, repeats=1, warm=True):
+def cpu_sample(spec, ladders, cycles, threads, repeats=1, warm=True):
     """The oracle (C restatement of the reference's CPU path, reference operation order) on `threads` cores."""
     import ptmc_b200 as P
     from ptmc_b200.host import initial_arrays, sweep_config
     from oracle import oracle
-    mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=N_TRAJ, cycles=cycles)
-    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=ladders, seed=1234)
+    mcp, temp, start, pot, ens = spec["deck"](cycles)
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=ladders, seed=SEED)
     eng = oracle.OracleEngine(cfg, threads=threads)
     pos, box = initial_arrays(mcp, start, ladders)
     eng.upload_states(pos, box)
-    eng.seed(1234)
-    eng.set_hist_bounds(-0.1, 0.0)
+    eng.seed(SEED)
+    eng.set_hist_bounds(*hist_window(P, start, None))
     if warm:
         eng.run_cycles(1, max(1, cycles // 8), True)
     times = []
@@ -84,8 +119,29 @@ def cpu_sample(ladders, cycles, threads, repeats=1, warm=True):
         eng.run_cycles(1 + r * cycles, cycles, True)
         times.append(time.perf_counter() - t0)
     eng.close()
-    moves = ladders * N_TRAJ * N_ATOMS * cycles
-    return moves, times
+    return ladders * mcp.n_traj * cfg.n_steps * cycles, times
+
+
+def hist_window(P, start, en):
+    """energy window from the equilibrated energies (as the host does, src/MCRun.jl:293-310); NPT: 0.8 V0 .. 2 V0 (src/Sampling.jl:203-211)"""
+    s0 = start[0] if isinstance(start, (list, tuple)) else start
+    lo, hi = (-1.0, 1.0) if en is None else (float(en.min()), float(en.max()))
+    pad = 0.05 * (abs(lo) + abs(hi)) + 1e-6
+    if isinstance(s0.boundary_condition, P.SphericalBC):
+        return (lo - pad, hi + pad, None, None)
+    v0 = P.get_volume(s0.boundary_condition)
+    return (lo - pad, hi + pad, 0.8 * v0, 2.0 * v0)
+
+
+def cpu_record(spec, cores, repeats=3):
+    ladders, cycles = spec["cpu"]
+    ladders = ladders or 8 * cores
+    mv, times = cpu_sample(spec, ladders, cycles, cores, repeats=repeats, warm=repeats > 1)
+    best = min(times)
+    n_traj = spec["deck"](1)[0].n_traj
+    return {"value": mv / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d ladders x %d temperatures x %d cycles (%d moves), best of %d, OpenMP over ladders; oracle/ptmc_oracle.c restates "
+                      "the reference's Julia CPU path (Julia is not in the image)" % (ladders, n_traj, cycles, mv, repeats)}
 
 
 def run_reference(args):
@@ -95,18 +151,23 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    S = specs(args)
+    spec = S["c2"]
     ladders = args.cpu_ladders or 8 * cores
-    moves, times = cpu_sample(ladders, args.cpu_cycles, cores, repeats=args.warmup + args.steps, warm=False)
+    moves, times = cpu_sample(spec, ladders, args.cpu_cycles, cores, repeats=args.warmup + args.steps, warm=False)
     timed = times[args.warmup:]
     total = sum(timed)
     value = moves * len(timed) / total
-    sample = "%d ladders x %d temperatures x %d cycles per step (%d moves/step), OpenMP over ladders" % (ladders, N_TRAJ, args.cpu_cycles, moves)
+    sample = "%d ladders x 24 temperatures x %d cycles per step (%d moves/step), OpenMP over ladders" % (ladders, args.cpu_cycles, moves)
+    others = {}
+    for name in [c for c in args.configs.split(",") if c]:
+        rec = cpu_record(S[name], cores, repeats=1)
+        others[name] = {"config": workload_config(S[name]), "value": rec["value"], "unit": UNIT, "cpu_baseline": rec}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.ladders, args.cycles), cpu_sample=sample),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(spec),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "configs": others}
     print(json.dumps(line), flush=True)
 
 
@@ -157,66 +218,64 @@ class DevArray:
 
 
 # ------------------------------------------------------------------------------------------- B200 arm --
-def run_b200(args):
-    import torch
-    import ptmc_b200 as P
-    from ptmc_b200 import abi
+class Ctx:
+    pass
+
+
+def pilot_step_sizes(ctx, spec, start_md=None):
+    """Step sizes the timed region works at: a small pilot batch runs enough adaptation periods (update_max_stepsize!,
+    src/Exchange.jl:250-263) that every temperature sits in the 40-60 % acceptance window the reference steers to, instead of
+    the constructor's max_displ = 0.1 (src/MCStates.jl:104).  The median over the pilot's ladders is used for every ladder."""
     from ptmc_b200.engine import Engine
     from ptmc_b200.host import initial_arrays, sweep_config
+    p = spec["pilot"]
+    mcp, temp, start, pot, ens = spec["deck"](p["cycles"])
+    mcp.n_adjust = p["n_adjust"]
+    L = p["ladders"]
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=SEED + 7_000_003, device=ctx.local, lanes_per_replica=spec["lanes"])
+    eng = Engine(cfg)
+    pos, box = initial_arrays(mcp, start, L)
+    md = None if start_md is None else np.ascontiguousarray(np.broadcast_to(start_md, (L, mcp.n_traj, 4)))
+    eng.upload_states(pos, box, md)
+    eng.run_cycles(1, p["cycles"], False)
+    md_slot = np.median(eng.download_states(("max_displ",))["max_displ"], axis=0)      # [n_traj][4]
+    eng.close()
+    return md_slot
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the sweep has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
 
-    L, cycles = args.ladders, args.cycles
-    mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=N_TRAJ, cycles=cycles)
-    # ladder l of rank r is global ladder r*L + l of a job of world*L ladders: streams are indexed globally
-    # (ptmc_b200.multi), so per-ladder results do not depend on the number of GPUs
-    from ptmc_b200 import multi
-    seed = 1234
-    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=seed, device=local, lanes_per_replica=args.lanes)
+def measure(ctx, name, spec, steps, warmup, md_slot, with_cpu):
+    """One BASELINE config on this rank's GPU: device-resident value (CUDA events), e2e with host buffers, roofline, CPU sample."""
+    import torch
+    import ptmc_b200 as P
+    from ptmc_b200 import abi, multi
+    from ptmc_b200.engine import Engine
+    from ptmc_b200.host import initial_arrays, sweep_config
+    dist, dev, rank, world, local = ctx.dist, ctx.dev, ctx.rank, ctx.world, ctx.local
+    L, cycles = spec["ladders"], spec["cycles"]
+    mcp, temp, start, pot, ens = spec["deck"](cycles)
+    T, N = mcp.n_traj, mcp.n_atoms
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=SEED, device=local, lanes_per_replica=spec["lanes"])
+    n_steps = cfg.n_steps
     eng = Engine(cfg)
     stream = torch.cuda.Stream(device=dev)
     eng.set_stream(stream.cuda_stream)
     pos, box = initial_arrays(mcp, start, L)
-    pin_pos = torch.from_numpy(pos).pin_memory()
-    pin_box = torch.from_numpy(box).pin_memory()
-    # step sizes: a pilot of 64 ladders runs 3000 cycles (30 adaptations, src/Exchange.jl:250-263) so that the timed
-    # region works at the adapted 40-60 % acceptance instead of the constructor's max_displ = 0.1 (~87 %)
-    pcfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=64, seed=seed + 7, device=local, lanes_per_replica=args.lanes)
-    pilot = Engine(pcfg)
-    ppos, pbox = initial_arrays(mcp, start, 64)
-    pilot.upload_states(ppos, pbox)
-    pilot.run_cycles(1, 3000, False)
-    md_slot = np.median(pilot.download_states(("max_displ",))["max_displ"], axis=0)      # [n_traj][4]
-    pilot.close()
-    max_displ = np.ascontiguousarray(np.broadcast_to(md_slot, (L, N_TRAJ, 4)))
-    pin_md = torch.from_numpy(max_displ).pin_memory()
+    max_displ = np.ascontiguousarray(np.broadcast_to(md_slot, (L, T, 4)))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    pin_pos, pin_box, pin_md = pin(pos), pin(box), pin(max_displ)
     eng.upload_states(pin_pos.numpy(), pin_box.numpy(), pin_md.numpy())
+    # ladder l of rank r is global ladder r*L + l of a job of world*L ladders: streams are indexed globally
+    # (ptmc_b200.multi), so per-ladder results do not depend on the number of GPUs
     if world > 1:
-        multi.seed_global(eng, seed, rank * L, world * L)
+        multi.seed_global(eng, SEED, rank * L, world * L)
     else:
-        eng.seed(seed)
-    # equilibrate so that the histogram window is meaningful
-    eng.run_cycles(1, 200, False)
+        eng.seed(SEED)
+    eng.run_cycles(1, spec["eq"], False)                       # equilibrate so that the histogram window is meaningful
     en = eng.download_states(("en_tot",))["en_tot"]
+    bounds = hist_window(P, start, en)
     eng.reset_counters()
-    eng.set_hist_bounds(float(en.min()) - 1e-3, float(en.max()) + 2e-3)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    moves_per_step = L * N_TRAJ * N_ATOMS * cycles
-
-    def step(idx):
-        with torch.cuda.stream(stream):
-            flush.fill_(idx & 0xFF)
-        eng.run_cycles(idx, cycles, True)
+    eng.set_hist_bounds(*bounds)
+    moves_per_step = L * T * n_steps * cycles
 
     def barrier():
         if dist is not None:
@@ -225,24 +284,25 @@ def run_b200(args):
 
     # ---------------------------------------------------------------- device-resident timing (value)
     idx = 1
-    for _ in range(args.warmup):
-        step(idx); idx += cycles
+    for _ in range(warmup):
+        with torch.cuda.stream(stream):
+            ctx.flush.fill_(idx & 0xFF)
+        eng.run_cycles(idx, cycles, True); idx += cycles
     barrier()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
+    kernel_ev = []
     with ClockSampler(local) as clk:
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             with torch.cuda.stream(stream):
-                flush.fill_(idx & 0xFF)
+                ctx.flush.fill_(idx & 0xFF)                      # L2 flush between timed steps
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             k0.record(stream)
             eng.run_cycles(idx, cycles, True)
             k1.record(stream)
             idx += cycles
-            kernel_ms.append((k0, k1))
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kernel_ev.append((k0, k1))
         # the one collective of the path: ladder-summed histogram, all-reduced across GPUs
         ptr, n = eng.reduced_hist_dev()
         hist_t = torch.as_tensor(DevArray(ptr, n), device=dev)
@@ -253,92 +313,153 @@ def run_b200(args):
         barrier()
     launches = eng.launch_count() - launches0
     eng.sync()
-    acc_timed = float(eng.download_states(("counters",))["counters"][:, :, abi.C_ATOM_TOT].sum()) / (L * N_TRAJ * N_ATOMS * cycles * (args.steps + args.warmup))
+    st_end = eng.download_states(("counters",))["counters"]
+    acc_timed = float(st_end[:, :, abi.C_ATOM_TOT].sum()) / (L * T * cfg.atom_moves * cycles * (steps + warmup))
     ms = e0.elapsed_time(e1)
-    kms = [a.elapsed_time(b) for a, b in kernel_ms]
+    kms = [a.elapsed_time(b) for a, b in kernel_ev]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * moves_per_step * args.steps / (ms_max * 1e-3)
+    value = world * moves_per_step * steps / (ms_max * 1e-3)
     hist_total = int(hist_t.sum().item())
-    expect = world * L * N_TRAJ * cycles * (args.steps + args.warmup) // mcp.mc_sample
+    expect = world * L * T * cycles * (steps + warmup) // mcp.mc_sample
     kernel_ms_avg = sum(kms) / len(kms)
+    lanes = eng.lanes_per_replica()
+    eng.close()
 
     # ------------------------------------------------------------------- end-to-end timing (e2e)
-    # results land in pinned host buffers owned by the caller (what a Julia Array passed to ccall would be after
-    # cudaHostRegister): positions, box, energies, step sizes, counters, ham
-    pinned = {k: torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory().numpy()
-              for k, (shp, dt) in eng.state_shapes().items()}
-    h2d = pin_pos.numel() * 8 + pin_box.numel() * 8 + pin_md.numel() * 8
-    d2h = 0
-    e2e_steps = max(3, min(args.steps, 5))
+    # The reference-facing sequence (upload = MCState construction, set_hist_bounds, run_cycles, download everything the driver
+    # reads: positions, box, energies, step sizes, counters, ham, histogram) on HOST buffers, every step.  Two half-batches with
+    # their own handle, stream and host thread: the copies of one half overlap the sweep of the other.
+    e2e_steps = max(3, min(steps, 5))
+    halves = [L - L // 2, L // 2] if L >= 2 else [L]
+    jobs = []
+    off = 0
+    for Lh in halves:
+        hcfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=Lh, seed=SEED, device=local, lanes_per_replica=spec["lanes"])
+        he = Engine(hcfg)
+        hs = torch.cuda.Stream(device=dev)
+        he.set_stream(hs.cuda_stream)
+        if world > 1:
+            multi.seed_global(he, SEED, rank * L + off, world * L)
+        else:
+            multi.seed_global(he, SEED, off, L)
+        inp = (pin(pos[off:off + Lh]), pin(box[off:off + Lh]), pin(max_displ[off:off + Lh]))
+        outp = {k: torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory().numpy()
+                for k, (shp, dt) in he.state_shapes().items()}
+        jobs.append((he, inp, outp))
+        off += Lh
+    h2d = sum(sum(x.numel() * 8 for x in inp) for _, inp, _ in jobs)
+    d2h_box = [0] * len(jobs)
 
-    def e2e_step(i):
-        eng.upload_states(pin_pos.numpy(), pin_box.numpy(), pin_md.numpy())
-        eng.set_hist_bounds(float(en.min()) - 1e-3, float(en.max()) + 2e-3)
-        eng.run_cycles(i, cycles, True)
-        st = eng.download_states(out=pinned)
-        hs = eng.download_hist(reduce_ladders=True)
-        return sum(v.nbytes for v in st.values()) + hs.nbytes
+    def e2e_loop(k, n):
+        he, inp, outp = jobs[k]
+        for s in range(n):
+            he.upload_states(inp[0].numpy(), inp[1].numpy(), inp[2].numpy())
+            he.set_hist_bounds(*bounds)
+            he.run_cycles(1 + s * cycles, cycles, True)
+            st = he.download_states(out=outp)
+            hs_ = he.download_hist(reduce_ladders=True)
+            d2h_box[k] = sum(v.nbytes for v in st.values()) + hs_.nbytes
 
-    d2h = e2e_step(1)
+    def run_threads(n):
+        th = [threading.Thread(target=e2e_loop, args=(k, n)) for k in range(len(jobs))]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        torch.cuda.synchronize(dev)
+
+    run_threads(1)                                               # warm-up (pins, first launches)
     barrier()
     t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        e2e_step(1 + s * cycles)
-    torch.cuda.synchronize(dev)
+    run_threads(e2e_steps)
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * moves_per_step * e2e_steps / float(t.item())
+    for he, _, _ in jobs:
+        he.close()
 
-    # ------------------------------------------------------------------------------- roofline
-    peak = eng_peak = None
+    achieved = (moves_per_step / (kernel_ms_avg * 1e-3)) * spec["W"] / 1e12     # this rank's sweep kernel
+    rec = None
     if rank == 0:
-        import ctypes as C
-        v = C.c_double()
-        if abi.load_library().ptmc_fp64_peak(local, 5, C.byref(v)) == 0:
-            eng_peak = v.value
-    achieved = (moves_per_step / (kernel_ms_avg * 1e-3)) * W_FLOPS_PER_MOVE / 1e12   # this rank's sweep kernel
-    peak = eng_peak
-    lanes = eng.lanes_per_replica()
-    eng.close()
+        cpu = None
+        if with_cpu and world == 1:
+            cpu = cpu_record(spec, os.cpu_count() or 1, repeats=3 if name == "c2" else 1)
+        roof = {"bound": "fp64", "achieved": achieved, "peak": ctx.peak, "unit": "TFLOP/s", "frac": (achieved / ctx.peak) if ctx.peak else None,
+                "traffic": None,
+                "note": "FP64 FMA pipe bound (not hbm/tensor): W = %g algorithmic flops per move (%s); peak = DFMA-chain peak measured live "
+                        "(MEASURED_PEAKS.json has no FP64 figure); traffic: not read in this run - state load / store per launch, ncu "
+                        "dram bytes in profiles/r01_sweep_ne55_g8.md (C2), r02_*.md" % (spec["W"], spec["W_note"])}
+        if "pair_evals_per_move" in spec:
+            roof["pair_evals_per_s"] = moves_per_step / (kernel_ms_avg * 1e-3) * spec["pair_evals_per_move"]
+        rec = {"value": value, "unit": UNIT, "ms_per_step": ms_max / steps, "steps": steps, "warmup": warmup,
+               "config": workload_config(spec), "clocks": clk.summary(),
+               "details": {"lanes_per_replica": lanes, "moves_per_step_per_gpu": moves_per_step, "hist_samples_total": hist_total,
+                           "hist_samples_expected": expect, "sweep_kernel_ms_avg": kernel_ms_avg, "e2e_steps": e2e_steps,
+                           "e2e_mode": "two half-batches (two handles / streams / host threads): copies of one overlap the sweep of the other",
+                           "atom_move_acceptance": acc_timed,
+                           "max_displ_range": [float(md_slot[:, 0].min()), float(md_slot[:, 0].max())],
+                           "pilot": {k: v for k, v in spec["pilot"].items()},
+                           "algorithmic_hbm_bytes_per_move": 0, "state_bytes_per_launch_per_gpu": int(pos.nbytes * 2)},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(sum(d2h_box))},
+               "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+    return rec
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        cl = args.cpu_ladders or 8 * cores
-        mv, times = cpu_sample(cl, args.cpu_cycles, cores, repeats=3)
-        best = min(times)
-        cpu = {"value": mv / best, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d ladders x %d temperatures x %d cycles (%d moves), best of 3, OpenMP over ladders; "
-                         "oracle/ptmc_oracle.c restates the reference's Julia CPU path (Julia is not in the image)" % (cl, N_TRAJ, args.cpu_cycles, mv)}
 
-    if rank == 0:
-        conf = workload_config(L, cycles)
-        conf.update({"lanes_per_replica": lanes, "hist_samples_total": hist_total, "hist_samples_expected": expect,
-                     "sweep_kernel_ms_avg": kernel_ms_avg, "e2e_steps": e2e_steps, "atom_move_acceptance": acc_timed,
-                     "max_displ_range": [float(md_slot[:, 0].min()), float(md_slot[:, 0].max())],
-                     "algorithmic_hbm_bytes_per_move": 0, "state_bytes_per_launch_per_gpu": int(pos.nbytes * 2)})
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": conf, "clocks": clk.summary(),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": (achieved / peak) if peak else None,
-                             # dram__bytes_read + dram__bytes_write of one sweep launch from the ncu --set full capture
-                             # profiles/r01_sweep_ne55_g8.md (state load / store; independent of the cycle count)
-                             "traffic": 301594368,
-                             "note": "FP64 FMA pipe bound (not hbm/tensor): W = %d algorithmic flops per move; peak = DFMA-chain "
-                                     "peak measured live (MEASURED_PEAKS.json has no FP64 figure); HBM traffic is ~0 B/move" % W_FLOPS_PER_MOVE},
-                "cpu_baseline": cpu}
+def run_b200(args):
+    import torch
+    from ptmc_b200 import abi
+
+    ctx = Ctx()
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the sweep has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(ctx.local)
+    ctx.dist = None
+    if ctx.world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local))
+        ctx.dist = dist
+    ctx.dev = torch.device("cuda", ctx.local)
+    ctx.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=ctx.dev)
+    import ctypes as C
+    v = C.c_double()
+    ctx.peak = v.value if abi.load_library().ptmc_fp64_peak(ctx.local, 5, C.byref(v)) == 0 else None
+
+    S = specs(args)
+    with_cpu = not args.no_cpu_baseline
+    md = {"c2": pilot_step_sizes(ctx, S["c2"])}
+    head = measure(ctx, "c2", S["c2"], args.steps, args.warmup, md["c2"], with_cpu)
+    others = {}
+    names = [c for c in args.configs.split(",") if c]
+    for name in names:
+        spec = S[name]
+        start_md = None
+        if spec["pilot"].get("start_from"):
+            src = spec["pilot"]["start_from"]
+            if src not in md:
+                md[src] = pilot_step_sizes(ctx, S[src])
+            start_md = md[src]
+        md[name] = pilot_step_sizes(ctx, spec, start_md)
+        rec = measure(ctx, name, spec, max(3, min(args.steps, 4)), max(3, args.warmup), md[name], with_cpu)
+        if rec is not None:
+            others[name] = rec
+    if ctx.rank == 0:
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": head["config"], "clocks": head["clocks"], "details": head["details"],
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+                "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"], "configs": others}
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main():

@@ -49,7 +49,8 @@ typedef enum ptmc_status {
     PTMC_ERR_CUDA = -2,        /* CUDA runtime error (text in ptmc_last_error)                   */
     PTMC_ERR_STATE = -3,       /* call order (e.g. run before upload)                            */
     PTMC_ERR_SPHERE = -4,      /* "too many moves out of binding sphere" (src/MCMoves.jl:132)    */
-    PTMC_ERR_REPLAY = -5       /* replay stream exhausted                                        */
+    PTMC_ERR_REPLAY = -5,      /* replay stream exhausted                                        */
+    PTMC_ERR_TIES = -6         /* periodic NPT: more than 32 neighbours of one atom sit on the cut-off sphere at upload */
 } ptmc_status;
 
 /* src/EnergyEvaluation.jl:891 (ELJPotential), :138 (ELJPotentialEven), :1059 (EmbeddedAtomPotential),

@@ -1019,7 +1019,8 @@ orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER2 && (!cfg->runner2 || cfg->bc_kind != PTMC_BC_SPHERICAL || cfg->runner2->n1 < 1 || cfg->runner2->n2 < 1 ||
                                               cfg->runner2->n1 + cfg->runner2->n2 != cfg->n_atoms || cfg->n_atom_swaps < 0)) return NULL;
     if (cfg->ensemble == PTMC_ENS_NPT && cfg->separated_volume && cfg->bc_kind != PTMC_BC_RHOMBIC && cfg->bc_kind != PTMC_BC_RECTANGULAR) return NULL;
-    if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91)) return NULL;
+    if (cfg->pot_kind == PTMC_POT_LUT && (!cfg->lut_table || cfg->lut_l_dist < 1 || cfg->lut_l_angle < 91 || !(cfg->lut_d_angle > 0) ||
+                                          cfg->lut_l_angle < (int)rint(90.0 / cfg->lut_d_angle + 1.0))) return NULL;
     orc_handle* H = (orc_handle*)xcalloc(1, sizeof *H);
     H->cfg = *cfg;
     if (cfg->pot_kind == PTMC_POT_LUT) {

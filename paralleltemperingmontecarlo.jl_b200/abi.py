@@ -23,7 +23,7 @@ RNG_LANES = 8
 (C_ATOM_TOT, C_ATOM_ADJ, C_VOL_TOT, C_VOL_ADJ, C_VOLXY_TOT, C_VOLXY_ADJ, C_VOLZ_TOT, C_VOLZ_ADJ,
  C_EXC_ATT, C_EXC_ACC) = range(10)
 
-ERR_ARG, ERR_CUDA, ERR_STATE, ERR_SPHERE, ERR_REPLAY = -1, -2, -3, -4, -5
+ERR_ARG, ERR_CUDA, ERR_STATE, ERR_SPHERE, ERR_REPLAY, ERR_TIES = -1, -2, -3, -4, -5, -6
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -14,10 +14,10 @@
 #include "sweep_kernel.cuh"
 
 namespace ptmc {
-sweep_fn sweep_table_g4(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
-sweep_fn sweep_table_g8(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
-sweep_fn sweep_table_g16(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
-sweep_fn sweep_table_g32(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot);
+sweep_fn sweep_table_g4(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
+sweep_fn sweep_table_g8(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
+sweep_fn sweep_table_g16(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
+sweep_fn sweep_table_g32(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
 int sweep_max_threads(int G);
 void launch_init(const DevParams& P, i64 n_rep, cudaStream_t st);
 void launch_reduce_hist(const u64* hist, u64* out, i64 n_ladders, i64 per, cudaStream_t st);
@@ -149,10 +149,10 @@ static sweep_fn pick_kernel(const ptmc_handle* h, int dbg) {
     const int fullw = (h->cfg.n_traj * h->G) % 32 == 0 ? 1 : 0;      // every warp of the ladder fully active
     const int rot = (h->cfg.n_atoms - 1) % h->G == 0 ? 1 : 0;          // the other N - 1 atoms fill the lanes exactly
     switch (h->G) {
-        case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
-        case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
-        case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
-        default: return sweep_table_g32(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot);
+        case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
+        case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
+        case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
+        default: return sweep_table_g32(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
     }
 }
 // words of generator state per slot
@@ -362,6 +362,9 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         case PTMC_POT_LUT:
             if (!c->lut_table || c->lut_l_dist < 1 || c->lut_l_angle < 91 || !(c->lut_d_dist > 0) || !(c->lut_d_angle > 0))
                 return fail(nullptr, PTMC_ERR_ARG, "pot_kind LUT needs lut_table [l_angle >= 91][l_dist >= 1] and positive grid steps");
+            // the angle index reaches round(90 / d_angle + 1) (src/EnergyEvaluation.jl:273-283); the reference throws a BoundsError beyond the table
+            if (c->lut_l_angle < (int)std::rint(90.0 / c->lut_d_angle + 1.0))
+                return fail(nullptr, PTMC_ERR_ARG, "lookup table has %d angle rows, d_angle = %g needs %d", c->lut_l_angle, c->lut_d_angle, (int)std::rint(90.0 / c->lut_d_angle + 1.0));
             break;
         case PTMC_POT_EAM:
             if (!sphere) return fail(nullptr, PTMC_ERR_ARG, "EmbeddedAtomPotential is built for SphericalBC/NVT (scripts/cu55.jl)");
@@ -426,8 +429,10 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
 
     std::vector<double> net_host;
     if (h->runner) { int rr = h->runner2 ? build_runner2(h, c->runner2, net_host) : build_runner(h, c->runner, net_host); if (rr) return bail(rr); }
+    // periodic NPT with uniform volume moves: tie table instead of the N x N matrix (n_atoms <= 256: partner indices are bytes)
+    P.use_ties = (!sphere && npt && !P.separated && c->n_atoms <= 256) ? 1 : 0;
     for (int dbg = 0; dbg < 2; ++dbg)
-        h->smem_k[dbg] = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere, !eam_unrolled(P.n_pad / G, dbg != 0)).bytes;
+        h->smem_k[dbg] = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere, !eam_unrolled(P.n_pad / G, dbg != 0), !P.use_ties).bytes;
     h->smem = h->runner2 ? runner2_smem_bytes(c->n_atoms, h->R2) : h->runner ? runner_smem_bytes(c->n_atoms, h->R) : std::max(h->smem_k[0], h->smem_k[1]);
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
 
@@ -439,7 +444,9 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     int rc = 0;
     if ((rc = dev_alloc(h, &P.pos, R * N * 3)) || (rc = dev_alloc(h, &P.box, R * 2)) || (rc = dev_alloc(h, &P.en_tot, R)) ||
         (rc = dev_alloc(h, &P.comp, c->pot_kind == PTMC_POT_EAM ? R * N * 2 : 1)) ||
-        (rc = dev_alloc(h, &P.d2mat, sphere ? 1 : R * N * N)) ||
+        (rc = dev_alloc(h, &P.d2mat, (sphere || P.use_ties) ? 1 : R * N * N)) ||
+        (rc = dev_alloc(h, &P.tie_cnt, P.use_ties ? R * N : 1)) || (rc = dev_alloc(h, &P.tie_idx, P.use_ties ? R * N * PTMC_TIE_K : 1)) ||
+        (rc = dev_alloc(h, &P.tie_val, P.use_ties ? R * N * PTMC_TIE_K : 1)) ||
         (rc = dev_alloc(h, &P.tan_rho, R)) || (rc = dev_alloc(h, &P.fresh_g, R * ((N + 31) / 32))) || (rc = dev_alloc(h, &P.perm_g, R)) ||
         (rc = dev_alloc(h, &P.moved_g, R * ((N + 31) / 32 + 1))) || (rc = dev_alloc(h, &P.max_displ, R * 4)) ||
         (rc = dev_alloc(h, &P.max_boxlength, R)) || (rc = dev_alloc(h, &P.max_boxheight, R)) || (rc = dev_alloc(h, &P.counters, R * PTMC_NCOUNT)) || (rc = dev_alloc(h, &P.ham, R * 2)) ||
@@ -561,8 +568,9 @@ extern "C" PTMC_API int ptmc_upload_states(ptmc_handle* h, const double* pos, co
     {   // slot -> configuration map starts as the identity
         std::vector<int> perm(R);
         for (size_t r = 0; r < R; ++r) perm[r] = (int)(r % (size_t)h->cfg.n_traj);
-        CU(h, cudaMemcpy(P.perm_g, perm.data(), sizeof(int) * R, cudaMemcpyHostToDevice));
-        CU(h, cudaMemset(P.moved_g, 0, sizeof(int) * R * (P.moved_words + 1)));
+        CU(h, cudaMemcpyAsync(P.perm_g, perm.data(), sizeof(int) * R, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemsetAsync(P.moved_g, 0, sizeof(int) * R * (P.moved_words + 1), h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));   // perm is stack-owned
     }
     if (h->runner2) runner2_launch_init(P, h->R2, h->n_rep, h->stream);
     else if (h->runner) runner_launch_init(P, h->R, h->n_rep, h->stream);
@@ -727,9 +735,11 @@ extern "C" PTMC_API int ptmc_sync(ptmc_handle* h) {
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
     int e = 0;
-    CU(h, cudaMemcpy(&e, h->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpyAsync(&e, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     if (e == PTMC_ERR_SPHERE) return fail(h, e, "Error: too many moves out of binding sphere");   // src/MCMoves.jl:132
     if (e == PTMC_ERR_REPLAY) return fail(h, e, "replay stream exhausted");
+    if (e == PTMC_ERR_TIES) return fail(h, e, "more than %d neighbours of one atom sit on the cut-off sphere of the uploaded configuration", PTMC_TIE_K);
     if (e) return fail(h, e, "device error %d", e);
     return PTMC_OK;
 }
@@ -777,12 +787,14 @@ extern "C" PTMC_API int ptmc_download_states(ptmc_handle* h, double* pos, double
     TRY(ptmc_sync(h));
     const size_t R = (size_t)h->n_rep, N = (size_t)h->cfg.n_atoms;
     const DevParams& P = h->P;
-    if (pos) CU(h, cudaMemcpy(pos, P.pos, sizeof(double) * R * N * 3, cudaMemcpyDeviceToHost));
-    if (box) CU(h, cudaMemcpy(box, P.box, sizeof(double) * R * 2, cudaMemcpyDeviceToHost));
-    if (en_tot) CU(h, cudaMemcpy(en_tot, P.en_tot, sizeof(double) * R, cudaMemcpyDeviceToHost));
-    if (max_displ) CU(h, cudaMemcpy(max_displ, P.max_displ, sizeof(double) * R * 4, cudaMemcpyDeviceToHost));
-    if (counters) CU(h, cudaMemcpy(counters, P.counters, sizeof(i64) * R * PTMC_NCOUNT, cudaMemcpyDeviceToHost));
-    if (ham) CU(h, cudaMemcpy(ham, P.ham, sizeof(double) * R * 2, cudaMemcpyDeviceToHost));
+    // all copies on the handle's stream (never the legacy default stream: handles on other streams keep running), one wait at the end
+    if (pos) CU(h, cudaMemcpyAsync(pos, P.pos, sizeof(double) * R * N * 3, cudaMemcpyDeviceToHost, h->stream));
+    if (box) CU(h, cudaMemcpyAsync(box, P.box, sizeof(double) * R * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (en_tot) CU(h, cudaMemcpyAsync(en_tot, P.en_tot, sizeof(double) * R, cudaMemcpyDeviceToHost, h->stream));
+    if (max_displ) CU(h, cudaMemcpyAsync(max_displ, P.max_displ, sizeof(double) * R * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (counters) CU(h, cudaMemcpyAsync(counters, P.counters, sizeof(i64) * R * PTMC_NCOUNT, cudaMemcpyDeviceToHost, h->stream));
+    if (ham) CU(h, cudaMemcpyAsync(ham, P.ham, sizeof(double) * R * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     return PTMC_OK;
 }
 
@@ -811,7 +823,8 @@ extern "C" PTMC_API int ptmc_download_hist(ptmc_handle* h, double* en_hist, doub
         src = static_cast<const u64*>(p); n = (size_t)m;
     }
     std::vector<u64> tmp(n);
-    CU(h, cudaMemcpy(tmp.data(), src, n * sizeof(u64), cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpyAsync(tmp.data(), src, n * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < n; ++i) dst[i] = (double)tmp[i];   // Output.en_histogram holds Float64 counts
     return PTMC_OK;
 }

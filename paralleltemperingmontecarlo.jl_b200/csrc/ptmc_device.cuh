@@ -17,6 +17,8 @@ namespace ptmc {
 typedef unsigned long long u64;
 typedef long long i64;
 
+#define PTMC_TIE_K 32           // tie-table row capacity (fcc / hcp shells on a cut-off sphere: <= 24)
+#define PTMC_TIE_REL 1e-7       // relative distance to the cut-off below which a pair keeps its frozen dist2_mat entry
 #define PTMC_EAM_DEG 6          // degree of the binomial series of (1 + t)^-p, |t| <= 2^-9
 #define PTMC_EAM_K 256          // mantissa intervals
 #ifndef PTMC_EAM_KSTRIDE
@@ -67,6 +69,14 @@ struct DevParams {
     // entries can only differ in a DECISION from recomputed distances for pairs of never-moved lattice atoms (exact
     // cut-off ties); once every atom of a configuration has moved, its matrix is no longer read or maintained.
     int* moved_g;       // [L][T][moved_words + 1]  (last int: count)
+    // Periodic NPT with uniform volume moves (use_ties): instead of the N x N matrix, the pairs that sit on the cut-off at upload
+    // (|d2 / r_cut - 1| < PTMC_TIE_REL, exact distance2 arithmetic) are kept per configuration and per atom with their frozen
+    // values; every other pair is recomputed from the positions (its decision cannot differ: it is >= 1e-7 away from the cut-off,
+    // rounding moves it by 1e-16 per volume move).  A configuration without such pairs starts thawed.
+    int use_ties;
+    int* tie_cnt;             // [L][T][N]
+    unsigned char* tie_idx;   // [L][T][N][PTMC_TIE_K]
+    double* tie_val;          // [L][T][N][PTMC_TIE_K]  dist2_mat entries, scaled like the reference's at accepted volume moves
     int moved_words;    // ceil(n_atoms / 32)
     // slot-side state
     double* max_displ;  // [L][T][4]

@@ -63,8 +63,9 @@ static sweep_fn special_kernel(int niter, int fullw) {
 
 // pot: ptmc_pot_kind (ELJ, ELJ_EVEN, EAM); geom: Geom; dbg: sequential-stream / replay / trace build;
 // niter = n_pad / G; n_coeff: number of ELJ coefficients; fullw: n_traj * G is a multiple of 32 (no partly active warp)
-sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot) {
+sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads) {
     constexpr int G = PTMC_G;
+    (void)threads;
     if (rot && fullw && !dbg && geom == GEOM_SPHERE && n_coeff == 6 && niter >= 2) {
         sweep_fn f = pot == PTMC_POT_ELJ_EVEN ? rotated_kernel<PTMC_POT_ELJ_EVEN>(niter - 1) : pot == PTMC_POT_ELJ_B ? rotated_kernel<PTMC_POT_ELJ_B>(niter - 1) : nullptr;
         if (f) return f;

@@ -41,10 +41,11 @@ struct SmemLayout {
 #define PTMC_EAM_UNROLL 1
 #endif
 __host__ __device__ constexpr bool eam_unrolled(int niter, bool dbg) { return PTMC_EAM_UNROLL && !dbg && niter >= 1 && niter <= PTMC_EAM_MAX_NITER; }
-__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch) {
+__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch, bool newvec) {
     SmemLayout s;
     const bool dirp = pot_kind == PTMC_POT_ELJ_B || pot_kind == PTMC_POT_LUT;
-    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + (pbc ? 1 : 0);   // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec)
+    // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec where the N x N matrix is kept: periodic without the tie table)
+    int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + ((pbc && newvec) ? 1 : 0);
     s.cfg_stride = arrays * n_pad;
     s.off_scal = n_traj * s.cfg_stride;
     int off = s.off_scal + 4 * n_traj;
@@ -150,7 +151,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     // full mask spares the MATCH / VOTE convergence sequences the compiler emits around a register mask (FULLW kernels)
     const unsigned hmask = FULLW ? 0xffffffffu : gmask;
     constexpr bool EAM_REG = EAM && NITER > 0 && PTMC_EAM_UNROLL;     // trial (phi, rho) components in registers instead of shared memory
-    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG);
+    const bool ties = PBC && P.use_ties != 0;      // periodic NPT, uniform volume moves: tie table instead of dist2_mat
+    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG, !ties);
     double* scal = sm + lay.off_scal;
     i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
     double* hams = sm + lay.off_ham;
@@ -364,7 +366,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             const double rho_c = tanst ? trho[c] : 1.0;
                             const int* fr = fresh + c * FW;
                             const bool fresh_i = tanst && tan_fresh(fr, i);
-                            if (thawed) {
+                            if (thawed || ties) {
                                 // thawed: both rows from the positions in shared memory, pair loop unrolled like the free-space one
                                 const double* Xg = X + g;
                                 auto pbc_term = [&](int k) {
@@ -427,6 +429,25 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     }
                                     if (npt) { en_j = (d2n <= rcut) ? en_j : 0.0; eo_j = (d2o <= rcut) ? eo_j : 0.0; }   // :323-336
                                     accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
+                                }
+                            }
+                            if (ties && !thawed && !((moved[c * MW + (i >> 5)] >> (i & 31)) & 1)) {
+                                // never-moved atom of a configuration that still holds cut-off ties: its tie partners that never moved either
+                                // take the frozen dist2_mat entry in the old row (the d2 <= r_cut decision of the reference) instead of the
+                                // recomputed distance the loop above used
+                                const size_t row = ((size_t)lad * T + c) * N + i;
+                                const int cnt = __ldg(P.tie_cnt + row);
+                                for (int t = g; t < cnt; t += G) {
+                                    const int j = __ldg(P.tie_idx + row * PTMC_TIE_K + t);
+                                    if ((moved[c * MW + (j >> 5)] >> (j & 31)) & 1) continue;
+                                    const double d2f = __ldcg(P.tie_val + row * PTMC_TIE_K + t);
+                                    double v0, v1, v2;
+                                    const double d2r = dist2_pbc_vec<rhombic>(bx, xi, yi, zi, X[j], Y[j], Z[j], v0, v1, v2);
+                                    auto old_term = [&](double d) {
+                                        if (npt && !(d <= rcut)) return 0.0;
+                                        return DIRP ? pair_energy_dir<POT, NC>(P, d, v0, v1, v2) : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d);
+                                    };
+                                    acco += old_term(d2f) - old_term(d2r);
                                 }
                             }
                         } else {
@@ -518,13 +539,15 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 if (g == 0) fresh[c * FW + (i >> 5)] |= 1 << (i & 31);
                             }
                             if (moved[c * MW + MW - 1] < N) {
-                                // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
-                                double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
-                                const double* NEW = Z + NP;
-                                for (int j = g; j < N; j += G) {
-                                    const double v = NEW[j];
-                                    __stcg(D + (size_t)i * N + j, v);
-                                    __stcg(D + (size_t)j * N + i, v);
+                                if (!ties) {
+                                    // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
+                                    double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
+                                    const double* NEW = Z + NP;
+                                    for (int j = g; j < N; j += G) {
+                                        const double v = NEW[j];
+                                        __stcg(D + (size_t)i * N + j, v);
+                                        __stcg(D + (size_t)j * N + i, v);
+                                    }
                                 }
                                 __syncwarp(gmask);
                                 if (g == 0) {
@@ -595,6 +618,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     double acce = 0.0;
                     double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
                     const bool thawed = moved[c * MW + MW - 1] >= N;
+                    const bool recompute = thawed || ties;
                     if (!sepv) {
                         for (int a = 0; a < N - 1; ++a) {
                             const double* Da = D + (size_t)a * N;
@@ -602,11 +626,30 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             for (int j = a + 1 + g; j < N; j += G) {
                                 double d2o, v0 = 0, v1 = 0, v2 = 0;
                                 if (DIRP) d2o = dist2_pbc_vec<rhombic>(bx, xa, ya, za, X[j], Y[j], Z[j], v0, v1, v2);
-                                if (!thawed) d2o = __ldcg(Da + j);
+                                if (!recompute) d2o = __ldcg(Da + j);
                                 else if (!DIRP) d2o = dist2_pbc<rhombic>(bx, xa, ya, za, X[j], Y[j], Z[j]);
                                 const double d2 = xmul(d2o, sc2);                 // new_dist2_mat[a, j]
                                 if (d2 <= new_rcut) acce += DIRP ? pair_energy_dir<POT, NC>(P, d2, v0, v1, v2, sc2)      // tangents unchanged by a uniform scaling
                                                                  : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
+                            }
+                        }
+                        if (ties && !thawed) {
+                            // pairs of never-moved atoms on the cut-off: new_dist2_mat entry = frozen dist2_mat entry * scale^2
+                            for (int a = g; a < N; a += G) {
+                                if ((moved[c * MW + (a >> 5)] >> (a & 31)) & 1) continue;
+                                const size_t row = ((size_t)lad * T + c) * N + a;
+                                const int cnt = __ldg(P.tie_cnt + row);
+                                for (int t = 0; t < cnt; ++t) {
+                                    const int j = __ldg(P.tie_idx + row * PTMC_TIE_K + t);
+                                    if (j < a || ((moved[c * MW + (j >> 5)] >> (j & 31)) & 1)) continue;
+                                    double v0, v1, v2;
+                                    const double d2r = dist2_pbc_vec<rhombic>(bx, X[a], Y[a], Z[a], X[j], Y[j], Z[j], v0, v1, v2);
+                                    auto new_term = [&](double d) {
+                                        if (!(d <= new_rcut)) return 0.0;
+                                        return DIRP ? pair_energy_dir<POT, NC>(P, d, v0, v1, v2, sc2) : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d);
+                                    };
+                                    acce += new_term(xmul(__ldcg(P.tie_val + row * PTMC_TIE_K + t), sc2)) - new_term(xmul(d2r, sc2));
+                                }
                             }
                         }
                     } else {
@@ -640,7 +683,13 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                         __syncwarp(gmask);
                         for (int j = g; j < N; j += G) { X[j] = xmul(scale_xy, X[j]); Y[j] = xmul(scale_xy, Y[j]); Z[j] = xmul(scale_z, Z[j]); }
                         if (!thawed) {
-                            if (!sepv) {
+                            if (ties) {
+                                for (int a = g; a < N; a += G) {                  // dist2_mat .= new_dist2_mat, the entries that are kept
+                                    const size_t row = ((size_t)lad * T + c) * N + a;
+                                    const int cnt = __ldg(P.tie_cnt + row);
+                                    for (int t = 0; t < cnt; ++t) __stcg(P.tie_val + row * PTMC_TIE_K + t, xmul(__ldcg(P.tie_val + row * PTMC_TIE_K + t), sc2));
+                                }
+                            } else if (!sepv) {
                                 for (int k = g; k < N * N; k += G) __stcg(D + k, xmul(__ldcg(D + k), sc2));   // dist2_mat .= new_dist2_mat
                             } else {
                                 __syncwarp(gmask);
@@ -901,7 +950,8 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
         if (g == 0) P.en_tot[rep] = se;
     } else {
         double acc = 0.0;
-        double* D = pbc ? P.d2mat + (size_t)rep * N * N : nullptr;   // perm is the identity right after an upload
+        const bool ties = pbc && P.use_ties != 0;
+        double* D = (pbc && !ties) ? P.d2mat + (size_t)rep * N * N : nullptr;   // perm is the identity right after an upload
         for (int a = 0; a < N - 1; ++a) {
             const double xa = gp[3 * a], ya = gp[3 * a + 1], za = gp[3 * a + 2];
             for (int j = a + 1 + g; j < N; j += 32) {
@@ -909,7 +959,7 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                 if (pbc) {
                     // get_distance2_mat! src/Configurations.jl:146-162: dest[i,j] = dest[j,i] = distance2(c[i], c[j], bc)
                     d2 = dist2_exact(P.bc_kind, xa, ya, za, gp[3 * j], gp[3 * j + 1], gp[3 * j + 2], L, h);
-                    D[(size_t)a * N + j] = d2; D[(size_t)j * N + a] = d2;
+                    if (!ties) { D[(size_t)a * N + j] = d2; D[(size_t)j * N + a] = d2; }
                     if (POT == PTMC_POT_ELJ_B || POT == PTMC_POT_LUT) {
                         const Box b = make_box(P.bc_kind, L, h);
                         double v0, v1, v2;
@@ -927,7 +977,38 @@ __global__ void init_kernel(const DevParams P, const i64 n_rep) {
                 if (!npt || d2 <= rcut) acc += pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT>(P, d2);
             }
         }
-        if (pbc) for (int a = g; a < N; a += 32) D[(size_t)a * N + a] = 0.0;
+        if (pbc && !ties) for (int a = g; a < N; a += 32) D[(size_t)a * N + a] = 0.0;
+        if (ties) {
+            // tie table: per atom, the partners whose dist2_mat entry (dest[i,j] = dest[j,i] = distance2(c[i], c[j]), i < j) sits on the cut-off
+            int total = 0;
+            for (int a = g; a < N; a += 32) {
+                const size_t row = (size_t)rep * N + a;
+                int cnt = 0;
+                for (int j = 0; j < N; ++j) {
+                    if (j == a) continue;
+                    const int lo = a < j ? a : j, hi = a < j ? j : a;
+                    const double d2 = dist2_exact(P.bc_kind, gp[3 * lo], gp[3 * lo + 1], gp[3 * lo + 2], gp[3 * hi], gp[3 * hi + 1], gp[3 * hi + 2], L, h);
+                    if (fabs(d2 - rcut) <= PTMC_TIE_REL * rcut) {
+                        if (cnt < PTMC_TIE_K) { P.tie_idx[row * PTMC_TIE_K + cnt] = (unsigned char)j; P.tie_val[row * PTMC_TIE_K + cnt] = d2; }
+                        ++cnt;
+                    }
+                }
+                if (cnt > PTMC_TIE_K) { atomicMin(P.error, (int)PTMC_ERR_TIES); cnt = PTMC_TIE_K; }
+                P.tie_cnt[row] = cnt;
+                total += cnt;
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+            if (total == 0 && g == 0) {
+                // nothing on the cut-off: the configuration starts thawed
+                int* mv = P.moved_g + rep * (P.moved_words + 1);
+                for (int w = 0; w < P.moved_words; ++w) {
+                    const int nb = N - 32 * w;
+                    mv[w] = nb >= 32 ? -1 : (int)((1u << nb) - 1u);
+                }
+                mv[P.moved_words] = N;
+            }
+        }
         double e = group_sum<32>(acc, 0xffffffffu);
         if (npt) {
             const double l = lrc_pot<POT>(P, rcut);

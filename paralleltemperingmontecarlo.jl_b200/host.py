@@ -387,6 +387,13 @@ def initial_arrays(mc_params: MCParams, start_config, n_ladders: int):
     return pos, box
 
 
+def recentre(positions):
+    """recentre! src/Configurations.jl:79-85: subtract the centre (sum / n, coordinate by coordinate)"""
+    p = np.asarray(positions, dtype=np.float64)
+    c = np.array([sum(p[:, k].tolist()) / len(p) for k in range(3)])
+    return p - c
+
+
 def check_e_bounds(energy, ebounds):
     """src/MCRun.jl:258-265 (note the elseif)"""
     if energy < ebounds[0]:
@@ -472,20 +479,21 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
             T, N = mc_params.n_traj, mc_params.n_atoms
             pos = np.empty((n_ladders, T, N, 3)); box = np.empty((n_ladders, T, 2)); md = np.full((n_ladders, T, 4), 0.1)
             counters = np.zeros((n_ladders, T, abi.PTMC_NCOUNT), dtype=np.int64)
-            bounds = np.zeros((n_ladders, 4)); deltas = np.zeros((n_ladders, 3))
+            bounds = np.zeros((n_ladders, 4)); ck_delta_r2 = None
             old_hist = np.zeros((n_ladders, T, nb2, nb2) if npt else (n_ladders, T, nb2))
             old_rdf = np.zeros((n_ladders, T, 5 * mc_params.n_bin))
             for l in range(n_ladders):
                 cf, m, ca, cv, res, rdf, index = readsave.rebuild_states(T, _ladder_dir(save_dir, l, n_ladders), npt)
                 for t in range(T):
-                    pos[l, t] = cf[t].positions; box[l, t] = cf[t].boundary_condition.box(); md[l, t, :3] = m[t]
+                    # recentre!(state.config) of every rebuilt state (src/Initialization.jl:115-117, src/Configurations.jl:79-85)
+                    pos[l, t] = recentre(cf[t].positions); box[l, t] = cf[t].boundary_condition.box(); md[l, t, :3] = m[t]
                 counters[l, :, abi.C_ATOM_TOT] = ca; counters[l, :, abi.C_VOL_TOT] = cv
                 bounds[l] = (res.en_min, res.en_max, res.v_min, res.v_max)
-                deltas[l] = (res.delta_en_hist, res.delta_v_hist, res.delta_r2)
+                ck_delta_r2 = res.delta_r2                 # the checkpointed bin width of the rdf (hist_info.data)
                 old_hist[l] = res.ev_histogram if npt else res.en_histogram
                 if rdf is not None:
                     old_rdf[l] = rdf
-                start_counter = index + 1
+                start_counter = index                      # start_counter = Int(readdlm("./checkpoint/index.txt")[1]): cycle `index` runs again (:108)
             eng.upload_states(pos, box, md)
             eng.upload_counters(counters, None)
             eng.seed(seed + start_counter)          # the reference restarts with whatever its task-local generator holds
@@ -504,7 +512,7 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
                 bounds[:, 1] = bounds[:, 1].max()
             eng.reset_counters()
         eng.set_hist_bounds(bounds[:, 0].copy(), bounds[:, 1].copy(), bounds[:, 2].copy(), bounds[:, 3].copy())
-        delta_r2 = rdf_delta_r2(bc0, mc_params.n_bin)
+        delta_r2 = ck_delta_r2 if (restart and ck_delta_r2) else rdf_delta_r2(bc0, mc_params.n_bin)
         if rdfsave:
             eng.rdf_enable(delta_r2)
 
@@ -533,6 +541,10 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
                 readsave.checkpoint(i, states, res[l], ensemble, bc0.kind, ladder=l, rdf=res[l].rdf if rdfsave else None,
                                     directory=_ladder_dir(save_dir, l, n_ladders))
 
+        if save and restart:
+            res0 = make_results({"max_displ": np.zeros((n_ladders, mc_params.n_traj, 4))}, np.zeros_like(old_hist), None)
+            for l in range(n_ladders):
+                readsave.save_histparams(res0[l], _ladder_dir(save_dir, l, n_ladders))   # the restart method rewrites hist_info.data (src/MCRun.jl:452-454)
         if save and not restart:
             res0 = make_results({"max_displ": np.zeros((n_ladders, mc_params.n_traj, 4))},
                                 np.zeros((n_ladders,) + ((mc_params.n_traj, nb2, nb2) if npt else (mc_params.n_traj, nb2))), None)
@@ -566,7 +578,7 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
                     readsave.save_configs(snap, l, bc0.kind, d, filename="%s%d" % (configsname, stop))
             i = stop + 1
         if save and last_saved != mc_params.mc_cycles:
-            write_checkpoint(mc_params.mc_cycles)                                 # :424-427
+            write_checkpoint(mc_params.mc_cycles)                                 # :424-427 (also after a restart, where the reference leaves it out, :434-481)
         eng.sync()
         states = eng.download_states()
         results = make_results(states, eng.download_hist(), eng.download_rdf() if rdfsave else None)

@@ -104,6 +104,9 @@ def params_text(potential, ensemble, params: H.MCParams, temp: H.TempGrid) -> st
         out += "ensemble n_atom_moves n_volume_moves n_atom_swaps pressure separated_volume\n"
         out += _row(["NPT", ensemble.n_atoms, ensemble.atom_moves(), ensemble.n_volume_moves, 0, float(ensemble.pressure),
                      bool(ensemble.separated_volume)])
+    elif ensemble.kind == abi.ENS_NNVT:                   # writeensemble(::NNVT) :51-56
+        out += "ensemble n_1 n_2 n_atom_moves n_atom_swaps\n"
+        out += _row(["NNVT", ensemble.natoms[0], ensemble.natoms[1], ensemble.atom_moves(), ensemble.n_atom_swaps])
     else:
         out += "ensemble n_atom_moves n_atom_swaps\n"
         out += _row(["NVT", ensemble.n_atoms, ensemble.atom_moves(), ensemble.n_atom_swaps])
@@ -111,8 +114,15 @@ def params_text(potential, ensemble, params: H.MCParams, temp: H.TempGrid) -> st
         out += _type_name(potential) + " " + _row([float(c) for c in potential.coeff])
     elif isinstance(potential, H.EmbeddedAtomPotential):
         out += "EAM: %s %s %s %s \n" % (jl_float(potential.n), jl_float(potential.m), jl_float(potential.ean), jl_float(potential.eCam))
-    elif isinstance(potential, H.RuNNerPotential):
-        out += "runnerpotential \n"
+    elif isinstance(potential, (H.RuNNerPotential, H.RuNNerPotential2Atom)):
+        out += "runnerpotential \n"                       # writepotential(::AbstractMachineLearningPotential) :82-84
+    elif isinstance(potential, H.ELJPotentialB):
+        # writepotential(::AbstractDimerPotentialB) :70-76: header line, then writedlm([a', b', c']) with its default tab delimiter
+        out += "ELJB %d \n" % len(potential.coeff_a)
+        for row in (potential.coeff_a, potential.coeff_b, potential.coeff_c):
+            out += _row([float(v) for v in row], "\t")
+    elif isinstance(potential, H.LookupTablePotential):
+        out += "LookupTablePotential \n"                  # :85-87 (the table itself is not saved; readpotential has no branch for it)
     else:
         raise TypeError(type(potential))
     return out
@@ -240,6 +250,8 @@ def read_init(directory="./checkpoint", restart=True, eq_cycles=0.2):
         ens = H.NVT(int(e[1]), int(e[2]), int(e[3]))
     elif "NPT" in str(e[0]):
         ens = H.NPT(int(e[1]), float(e[5]), str(e[6]) == "true", n_atom_moves=int(e[2]), n_volume_moves=int(e[3]))
+    elif "NNVT" in str(e[0]):                             # readensemble :238-242
+        ens = H.NNVT((int(e[1]), int(e[2])), n_atom_swaps=int(e[4]), n_atom_moves=int(e[3]))
     else:
         raise ValueError("ensemble %r is outside the sweep path" % (e[0],))
     q = lines[4].split()
@@ -254,6 +266,13 @@ def read_init(directory="./checkpoint", restart=True, eq_cycles=0.2):
         pot.n, pot.m, pot.ean, pot.eCam = (float(v) for v in q[1:5])
     elif q[0] == "runnerpotential":
         pot = "runnerpotential"
+    elif q[0] == "ELJB":                                  # readpotential :266-272: rows 2-4 of the potential block are a, b, c
+        n = int(float(q[1]))
+        a, b, c = (tuple(float(v) for v in lines[5 + k].split()[:n]) for k in range(3))
+        pot = H.ELJPotentialB(a, b, c)
+    elif q[0] == "LookupTablePotential":
+        raise ValueError("params.data names a LookupTablePotential: the reference saves only this marker (src/ReadSave.jl:85-87) and its "
+                         "readpotential has no branch for it - pass the potential (with its table file) to ptmc_run(restart=True) yourself")
     else:
         raise ValueError("potential %r is outside the sweep path" % (q[0],))
     return params, temp, ens, pot
@@ -310,15 +329,21 @@ def rebuild_states(n_traj: int, directory="./checkpoint", npt=False):
     return cfgs, np.array(md), np.array(ca), np.array(cv), results, rdf, index
 
 
-def postprocess(directory="./checkpoint", n_points=1000):
+def postprocess(directory="./checkpoint", n_points=1000, outdir=None):
     """postprocess() src/multihist.jl:463-485 on a checkpoint directory: rebuild the results from the checkpoint files, run the
-    multihistogram analysis (its four output files go to `directory`) and return (energies, histogramdata, T, Z, Cv, dCv, S)
-    as the reference does (S is the fifth column of analysis.NVT, U(T))."""
+    multihistogram analysis and return (energies, histogramdata, T, Z, Cv, dCv, S) as the reference does (S is the fifth column
+    of analysis.NVT, U(T)).  The analysis writes its four files (histograms.data with the bin energies in the first row, Sol.X,
+    S.data, analysis.NVT) to `outdir`, by default the PARENT of the checkpoint directory: the reference works in pwd() with the
+    checkpoint in ./checkpoint, so the checkpoint's own histograms.data (the raw counts a restart reads) is left alone."""
     from . import multihist
+    directory = pathlib.Path(directory)
+    outdir = directory.resolve().parent if outdir is None else pathlib.Path(outdir)
+    if outdir.resolve() == directory.resolve():
+        raise ValueError("postprocess: outdir must differ from the checkpoint directory (the analysis writes its own histograms.data)")
     params, temp, ens, pot = read_init(directory)
     results, _ = setresults(directory, npt=ens.kind == abi.ENS_NPT)
     out = multihist.multihistogram(results.en_histogram, temp.beta_grid, results.en_min, results.en_max, results.n_bin,
-                                   outdir=directory, n_points=n_points)
-    hists = [[float(v) for v in ln.split()] for ln in pathlib.Path(directory, "histograms.data").read_text().splitlines()]
+                                   outdir=outdir, n_points=n_points)
+    hists = [[float(v) for v in ln.split()] for ln in pathlib.Path(outdir, "histograms.data").read_text().splitlines()]
     energies, histogramdata = np.array(hists[0]), [np.array(h) for h in hists[1:1 + params.n_traj]]
     return energies, histogramdata, out["T"], out["Z"], out["Cv"], out["dCv"], out["U"]

@@ -91,6 +91,17 @@ def test_argument_validation_precedes_device(lib):
     assert b"SphericalBC cannot be used in an NPT ensemble" in lib.ptmc_last_error(None)
 
 
+def test_lookup_table_needs_every_angle_row(lib):
+    # d_angle = 0.5 -> the angle index reaches round(90 / 0.5 + 1) = 181: a 91-row table would be read out of bounds (the reference
+    # throws a BoundsError); refused at create, before any device is touched
+    mcp, temp, start, _, ens = P.host.deck_ne13(n_traj=4, cycles=5)
+    lut = P.LookupTablePotential(np.ones((91, 8)), start_dist=2.0, start_angle=0.0, d_dist=0.5, d_angle=0.5, c6coeff=-1.0)
+    c = sweep_config(mcp, temp, start, lut, ens).to_c()
+    h = C.c_void_p()
+    assert lib.ptmc_create(C.byref(c), C.byref(h)) == abi.ERR_ARG
+    assert b"needs 181" in lib.ptmc_last_error(None)
+
+
 def test_two_species_host_mirror():
     # RuNNerPotential2Atom / NNVT (scripts/brass55.jl): the host mirror builds the descriptor in g-matrix row order and refuses
     # inconsistent combinations

@@ -467,7 +467,7 @@ def test_ptmc_run_checkpoint_files_gpu(tmp_path):
     mcp2, temp2, ens2, pot2 = readsave.read_init(tmp_path / "ladder0")
     mcp2.mc_cycles = 2500
     st2, res2 = P.host.ptmc_run(mcp2, temp2, start, pot2, ens2, n_ladders=3, seed=5, save=1000, save_dir=tmp_path, restart=True)
-    assert all(r.en_histogram.sum() == 8 * 2500 for r in res2)
+    assert all(r.en_histogram.sum() == 8 * 2501 for r in res2)      # cycle 2000 runs again: start_counter = index (src/Initialization.jl:108)
     assert readsave.rebuild_states(8, tmp_path / "ladder2")[-1] == 2500
 
 
@@ -756,7 +756,7 @@ def test_ptmc_run_save_restart_other_potentials(tmp_path):
     mcp2, temp2, ens2, pot2 = readsave.read_init(d / "ladder0")
     mcp2.mc_cycles = 60
     _, res2 = P.ptmc_run(mcp2, temp2, start, pot2, ens2, n_ladders=2, seed=1, save=20, save_dir=d, restart=True)
-    assert res2[0].ev_histogram.sum() == 4 * 60
+    assert res2[0].ev_histogram.sum() == 4 * 61
     d = tmp_path / "runner"
     mcp, temp, start, pot, ens = P.host.deck_cu55_runner(n_traj=3, cycles=1000)
     mcp.eq_percentage = 0.0
@@ -770,7 +770,7 @@ def test_ptmc_run_save_restart_other_potentials(tmp_path):
     assert (pot2.n, pot2.m, pot2.ean, pot2.eCam) == (pot.n, pot.m, pot.ean, pot.eCam)
     mcp2.mc_cycles = 400
     _, res2 = P.ptmc_run(mcp2, temp2, start, pot2, ens2, n_ladders=2, seed=1, save=100, save_dir=d, restart=True)
-    assert res2[0].en_histogram.sum() == 4 * 400
+    assert res2[0].en_histogram.sum() == 4 * 401
 
 
 def _synthetic_lookup_table():

@@ -109,11 +109,19 @@ def test_direct_multihistogram_and_postprocess(tmp_path, oracle):
     t2, cv2 = multihist.multihistogram_NVT(temp.t_grid, temp.beta_grid, hist, res.en_min, res.en_max, mcp.n_bin)
     assert np.abs(np.interp(t2[5:-5], out["T"], out["Cv"]) - cv2[5:-5]).max() < 0.1 * cv2.max()
     # postprocess() on a checkpoint directory of that run: files and return values
-    readsave.save_init(pot, ens, mcp, temp, tmp_path)
-    readsave.save_histparams(res, tmp_path)
-    readsave.checkpoint(mcp.mc_cycles, st, res, ens, abi.BC_SPHERICAL, directory=tmp_path)
-    energies, histdata, T, Z, Cv, dCv, S = readsave.postprocess(tmp_path)
-    assert len(histdata) == 8 and len(T) == 1000 and (Z >= 1.0).all() and (Z <= 100.0).all()
-    assert np.allclose(Cv, out["Cv"]) and np.allclose(S, out["U"])
+    ckpt = tmp_path / "checkpoint"                       # the reference: pwd()/checkpoint, analysis files in pwd()
+    readsave.save_init(pot, ens, mcp, temp, ckpt)
+    readsave.save_histparams(res, ckpt)
+    readsave.checkpoint(mcp.mc_cycles, st, res, ens, abi.BC_SPHERICAL, directory=ckpt)
+    raw = (ckpt / "histograms.data").read_text()
+    for _ in range(2):                                   # twice: the analysis must not touch the checkpoint it reads
+        energies, histdata, T, Z, Cv, dCv, S = readsave.postprocess(ckpt)
+        assert len(histdata) == 8 and len(T) == 1000 and (Z >= 1.0).all() and (Z <= 100.0).all()
+        assert np.allclose(Cv, out["Cv"]) and np.allclose(S, out["U"])
     assert (tmp_path / "analysis.NVT").read_text().splitlines()[0].split() == ["T", "Z", "Cv", "dCv", "U(T)"]
-    assert (tmp_path / "Sol.X").exists() and (tmp_path / "S.data").exists()
+    assert (tmp_path / "Sol.X").exists() and (tmp_path / "S.data").exists() and (tmp_path / "histograms.data").exists()
+    assert (ckpt / "histograms.data").read_text() == raw and not (ckpt / "analysis.NVT").exists()
+    cfgs, md, ca, cv, res2, rdf, index = readsave.rebuild_states(8, ckpt)          # ... and a restart still reads the raw counts
+    assert res2.n_bin == mcp.n_bin and np.array_equal(res2.en_histogram, hist) and index == mcp.mc_cycles
+    with pytest.raises(ValueError, match="outdir"):
+        readsave.postprocess(ckpt, outdir=ckpt)

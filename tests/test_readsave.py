@@ -109,7 +109,9 @@ def test_ptmc_run_save_restart_and_rdf(tmp_path, oracle):
     mcp2.mc_cycles = 3000
     st2, res2 = P.host.ptmc_run(mcp2, temp2, cfgs, pot2, ens2, n_ladders=1, seed=5, engine_cls=orc.OracleEngine, rdfsave=True,
                                 save=1000, save_dir=d, restart=True)
-    assert res2[0].en_histogram.sum() == 4 * 3000 and (res2[0].en_histogram >= r.en_histogram).all()
+    # (start_counter = index: the reference's restart runs cycle 2000 again, src/Initialization.jl:108 -> 1001 sampled cycles)
+    assert res2[0].en_histogram.sum() == 4 * 3001 and (res2[0].en_histogram >= r.en_histogram).all()
+    assert (d / "hist_info.data").read_text().split()[7:] == [readsave.jl_float(v) for v in (r.en_min, r.en_max, 0.0, 0.0, r.delta_en_hist, 0.0, r.delta_r2)]
     assert (st2["counters"][0, :, abi.C_ATOM_TOT] > st["counters"][0, :, abi.C_ATOM_TOT]).all()
     assert readsave.rebuild_states(4, d)[-1] == 3000
 
@@ -137,7 +139,7 @@ def test_ptmc_run_save_restart_npt_separated(tmp_path, oracle):
     assert ens2.separated_volume is True and ens2.n_volume_moves == 2 and ens2.pressure == ens.pressure
     mcp2.mc_cycles = 90
     st2, res2 = P.host.ptmc_run(mcp2, temp2, cfgs, pot2, ens2, n_ladders=1, seed=3, engine_cls=orc.OracleEngine, save=30, save_dir=tmp_path, restart=True)
-    assert res2[0].ev_histogram.sum() == 3 * 90 and readsave.rebuild_states(3, tmp_path, npt=True)[-1] == 90
+    assert res2[0].ev_histogram.sum() == 3 * 91 and readsave.rebuild_states(3, tmp_path, npt=True)[-1] == 90   # cycle 60 runs again (start_counter = index)
 
 
 def test_saveconfigs_files_like_the_reference_test(tmp_path, oracle):
@@ -154,3 +156,36 @@ def test_saveconfigs_files_like_the_reference_test(tmp_path, oracle):
         for a, line in enumerate(lines[2:]):
             assert line[:3] == "1  " and line[3:] == " ".join(readsave.jl_float(v) for v in st["pos"][0, t - 1, a]) + " "
             assert [float(x) for x in line.split()[1:]] == list(st["pos"][0, t - 1, a])
+
+
+def test_params_file_eljb_lookup_and_nnvt(tmp_path, oracle):
+    # writepotential(::AbstractDimerPotentialB) / (::LookupTablePotential) src/ReadSave.jl:70-76,85-87, writeensemble(::NNVT) :51-56,
+    # readpotential's ELJB branch :266-272, readensemble's NNVT branch :238-242
+    mcp, temp, start, pot, ens = P.host.deck_ne13_B(n_traj=4, cycles=60)
+    text = readsave.params_text(pot, ens, mcp, temp)
+    lines = text.splitlines()
+    assert lines[4] == "ELJB 6 " and lines[5].split("\t") == [readsave.jl_float(v) for v in pot.coeff_a] and len(lines) == 8
+    assert lines[7].split("\t")[2] == "35.6955"
+    readsave.save_init(pot, ens, mcp, temp, tmp_path / "b")
+    _, _, ens2, pot2 = readsave.read_init(tmp_path / "b")
+    assert isinstance(pot2, P.ELJPotentialB) and pot2 == pot and ens2.atom_moves() == ens.atom_moves() == 13
+    lut = P.LookupTablePotential(np.ones((91, 4)), start_dist=2.0, start_angle=0.0, d_dist=0.5, d_angle=1.0, c6coeff=-1.0)
+    assert readsave.params_text(lut, ens, mcp, temp).splitlines()[4] == "LookupTablePotential "
+    readsave.save_init(lut, ens, mcp, temp, tmp_path / "l")
+    with pytest.raises(ValueError, match="LookupTablePotential"):
+        readsave.read_init(tmp_path / "l")
+    nn = P.host.NNVT((50, 5), n_atom_swaps=2)
+    t2 = readsave.params_text(P.host.brass_runner_potential(50, 5), nn, P.MCParams(100, 10, 55), P.TempGrid(250.0, 900.0, 10)).splitlines()
+    assert t2[2] == "ensemble n_1 n_2 n_atom_moves n_atom_swaps" and t2[3] == "NNVT 50 5 55 2" and t2[4] == "runnerpotential "
+    readsave.save_init(P.host.brass_runner_potential(50, 5), nn, P.MCParams(100, 10, 55), P.TempGrid(250.0, 900.0, 10), tmp_path / "n")
+    _, _, ens3, pot3 = readsave.read_init(tmp_path / "n")
+    assert tuple(ens3.natoms) == (50, 5) and ens3.n_atom_swaps == 2 and ens3.atom_moves() == 55 and pot3 == "runnerpotential"
+    # save -> restart of an ELJPotentialB run on the oracle engine
+    from oracle import oracle as orc
+    d = tmp_path / "run"
+    st, res = P.host.ptmc_run(mcp, temp, start, pot, ens, n_ladders=1, seed=8, engine_cls=orc.OracleEngine, save=30, save_dir=d)
+    mcp2, temp2, ens2, pot2 = readsave.read_init(d)
+    cfgs = readsave.rebuild_states(4, d)[0]
+    mcp2.mc_cycles = 90
+    st2, res2 = P.host.ptmc_run(mcp2, temp2, cfgs, pot2, ens2, n_ladders=1, seed=8, engine_cls=orc.OracleEngine, save=30, save_dir=d, restart=True)
+    assert res2[0].en_histogram.sum() == 4 * 91 and readsave.rebuild_states(4, d)[-1] == 90

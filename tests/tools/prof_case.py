@@ -21,13 +21,20 @@ ap.add_argument("case")
 ap.add_argument("--cycles", type=int, default=10)
 ap.add_argument("--warm", type=int, default=100)
 ap.add_argument("--ladders", type=int, default=0)
+ap.add_argument("--lanes", type=int, default=0)
+ap.add_argument("--max-displ", type=float, default=0.0, help="atom step size (0 = the constructor's 0.1)")
 a = ap.parse_args()
 deck, L, _, _, _, bounds = CASES[a.case]
 L = a.ladders or L
 mcp, temp, start, pot, ens = deck()
-eng = Engine(sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=99))
+eng = Engine(sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=99, lanes_per_replica=a.lanes))
 pos, box = initial_arrays(mcp, start, L)
-eng.upload_states(pos, box)
+md = None
+if a.max_displ:
+    import numpy as np
+    md = np.full((L, mcp.n_traj, 4), 0.1)
+    md[:, :, 0] = a.max_displ
+eng.upload_states(pos, box, md)
 if bounds is None:
     v0 = P.get_volume(start[0].boundary_condition)
     bounds = (0.0, 1.0, 0.8 * v0, 2.0 * v0)
