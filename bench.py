@@ -84,7 +84,7 @@ def specs(args):
                    pilot=dict(ladders=148, cycles=600, n_adjust=20), W=14125,
                    W_note="(216 x 12470 + 371520) / 217: minimum-image atom moves + one full-energy volume move per cycle", cpu=(16, 20), lanes=0),
         "c5": dict(workload="Cu55 RuNNer neural-network potential NVT (scripts/cu55.jl, boundary 0), 28-temperature ladder, 37 independent PT ladders per GPU",
-                   deck=lambda c: H.deck_cu55_runner(n_traj=28, cycles=c), ladders=37, cycles=4, eq=4,
+                   deck=lambda c: H.deck_cu55_runner(n_traj=28, cycles=c), ladders=37, cycles=8, eq=4,
                    pilot=dict(ladders=37, cycles=24, n_adjust=2, start_from="c3"), W=3.6e6,
                    W_note="symmetry functions 3.35 Mflop + forward pass 0.24 Mflop as the reference evaluates them", cpu=(1, 1), lanes=0),
     }
@@ -94,7 +94,7 @@ def workload_config(spec):
     mcp = spec["deck"](spec["cycles"])[0]
     return {"workload": spec["workload"], "n_atoms": mcp.n_atoms, "n_traj": mcp.n_traj, "ladders_per_gpu": spec["ladders"],
             "cycles_per_step": spec["cycles"],
-            "rng": "PTMC_RNG_BATCH8: 8 Xoshiro256++ substreams per slot (Julia's generator)",
+            "rng": "PTMC_RNG_BATCH8: 8 Xoshiro256++ substreams per slot (Julia's generator), each seeded from SHA-256(seed, stream id)",
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -109,7 +109,7 @@ def cpu_sample(spec, ladders, cycles, threads, repeats=1, warm=True):
     eng = oracle.OracleEngine(cfg, threads=threads)
     pos, box = initial_arrays(mcp, start, ladders)
     eng.upload_states(pos, box)
-    eng.seed(SEED)
+    eng.seed_job(SEED)
     eng.set_hist_bounds(*hist_window(P, start, None))
     if warm:
         eng.run_cycles(1, max(1, cycles // 8), True)
@@ -232,7 +232,7 @@ def pilot_step_sizes(ctx, spec, start_md=None):
     mcp, temp, start, pot, ens = spec["deck"](p["cycles"])
     mcp.n_adjust = p["n_adjust"]
     L = p["ladders"]
-    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=SEED + 7_000_003, device=ctx.local, lanes_per_replica=spec["lanes"])
+    cfg = sweep_config(mcp, temp, start, pot, ens, n_ladders=L, seed=SEED + 1, device=ctx.local, lanes_per_replica=spec["lanes"])   # its own job seed: no stream shared with the run
     eng = Engine(cfg)
     pos, box = initial_arrays(mcp, start, L)
     md = None if start_md is None else np.ascontiguousarray(np.broadcast_to(start_md, (L, mcp.n_traj, 4)))
@@ -264,12 +264,9 @@ def measure(ctx, name, spec, steps, warmup, md_slot, with_cpu):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     pin_pos, pin_box, pin_md = pin(pos), pin(box), pin(max_displ)
     eng.upload_states(pin_pos.numpy(), pin_box.numpy(), pin_md.numpy())
-    # ladder l of rank r is global ladder r*L + l of a job of world*L ladders: streams are indexed globally
-    # (ptmc_b200.multi), so per-ladder results do not depend on the number of GPUs
-    if world > 1:
-        multi.seed_global(eng, SEED, rank * L, world * L)
-    else:
-        eng.seed(SEED)
+    # ladder l of rank r is global ladder r*L + l of the job: streams are hashed from (seed, global stream id) (ptmc_seed_job),
+    # so per-ladder results do not depend on the number of GPUs and jobs with different seeds share no stream
+    eng.seed_job(SEED, rank * L)
     eng.run_cycles(1, spec["eq"], False)                       # equilibrate so that the histogram window is meaningful
     en = eng.download_states(("en_tot",))["en_tot"]
     bounds = hist_window(P, start, en)
@@ -341,10 +338,7 @@ def measure(ctx, name, spec, steps, warmup, md_slot, with_cpu):
         he = Engine(hcfg)
         hs = torch.cuda.Stream(device=dev)
         he.set_stream(hs.cuda_stream)
-        if world > 1:
-            multi.seed_global(he, SEED, rank * L + off, world * L)
-        else:
-            multi.seed_global(he, SEED, off, L)
+        he.seed_job(SEED, rank * L + off)
         inp = (pin(pos[off:off + Lh]), pin(box[off:off + Lh]), pin(max_displ[off:off + Lh]))
         outp = {k: torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory().numpy()
                 for k, (shp, dt) in he.state_shapes().items()}

@@ -154,7 +154,7 @@ typedef struct ptmc_config {
     int32_t n_bin;            /* MCParams.n_bin                                                      */
     int32_t rng_mode;         /* ptmc_rng_mode                                                       */
     double min_acc, max_acc;  /* MCParams.min_acc / max_acc                                          */
-    uint64_t seed;            /* base seed: slot stream s gets Random.seed!(seed + s), see ptmc_seed  */
+    uint64_t seed;            /* job seed: ptmc_create seeds with ptmc_seed_job(h, seed, 0)           */
     int32_t lanes_per_replica;/* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one replica       */
     int32_t separated_volume; /* NPT.separated_volume (src/Ensembles.jl:81): volume_change_separated, RhombicBC / RectangularBC */
     /* ABI 2: PTMC_POT_ELJ_B only - coeff_a, coeff_b [n_coeff] (coeff_c travels in coeff[])                */
@@ -198,11 +198,18 @@ PTMC_API int ptmc_upload_counters(ptmc_handle* h, const int64_t* counters, const
 PTMC_API int ptmc_reset_counters(ptmc_handle* h);
 
 /* ---- random streams ------------------------------------------------------------------------------ */
-/* Julia-compatible seeding (Random.seed!(n): SHA-256 of the seed words).  With W = ptmc_rng_words()/4
+/* Consecutive Julia seeds (compatibility / parity rule; jobs that must not share streams use ptmc_seed_job): Random.seed!(n) is the
+ * SHA-256 of the seed words.  With W = ptmc_rng_words()/4
  * substreams per slot (1, or PTMC_RNG_LANES in BATCH8 mode): substream k of (ladder l, slot i) =
  * Random.seed!(seed + (l*n_traj + i)*W + k), ladder ("driver task") stream of ladder l =
  * Random.seed!(seed + n_ladders*n_traj*W + l). */
 PTMC_API int ptmc_seed(ptmc_handle* h, uint64_t seed);
+/* Job seeding (what ptmc_create does with cfg.seed, first_ladder = 0): every stream is the SHA-256 of the PAIR (seed, stream id), so
+ * two jobs with different seeds share no stream (with ptmc_seed's consecutive rule, seeds 1234 and 1235 share all but one), and a
+ * ladder's streams depend on its GLOBAL number only: local ladder l is ladder first_ladder + l of the job, whatever the number of GPUs.
+ *   substream k of (global ladder gl, slot i): id = (gl * n_traj + i) * W + k + 1;   driver-task stream of ladder gl: id = 2^63 + gl
+ *   state = Random.seed!(seed + id * 2^64)  (Julia hashes the little-endian UInt32 words of the integer, trailing zero words dropped) */
+PTMC_API int ptmc_seed_job(ptmc_handle* h, uint64_t seed, int64_t first_ladder);
 /* Number of UInt64 words of generator state per slot: 4 (XOSHIRO, REPLAY) or 4*PTMC_RNG_LANES (BATCH8). */
 PTMC_API int ptmc_rng_words(const ptmc_handle* h);
 /* Raw Xoshiro256++ states: slot_states [n_ladders][n_traj][ptmc_rng_words()], ladder_states [n_ladders][4]. */

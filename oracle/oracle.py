@@ -46,6 +46,7 @@ def load():
         "orc_upload_counters": (C.c_int, [_vp, _i64p, _dp]),
         "orc_reset_counters": (C.c_int, [_vp]),
         "orc_seed": (C.c_int, [_vp, C.c_uint64]),
+        "orc_seed_job": (C.c_int, [_vp, C.c_uint64, C.c_int64]),
         "orc_rng_words": (C.c_int, [_vp]),
         "orc_set_rng_states": (C.c_int, [_vp, _u64p, _u64p]),
         "orc_get_rng_states": (C.c_int, [_vp, _u64p, _u64p]),

@@ -118,6 +118,21 @@ void orc_julia_seed(uint64_t seed, uint64_t s[4]) {
     }
 }
 
+/* Random.seed!(lo + hi * 2^64): little-endian UInt32 words, trailing zero words dropped (make_seed of Julia's Random) */
+void orc_julia_seed128(uint64_t lo, uint64_t hi, uint64_t s[4]) {
+    uint8_t msg[16];
+    for (int i = 0; i < 8; ++i) { msg[i] = (uint8_t)(lo >> (8 * i)); msg[8 + i] = (uint8_t)(hi >> (8 * i)); }
+    size_t len = 16;
+    while (len > 4 && msg[len - 1] == 0 && msg[len - 2] == 0 && msg[len - 3] == 0 && msg[len - 4] == 0) len -= 4;
+    uint8_t dig[32];
+    sha256_short(msg, len, dig);
+    for (int k = 0; k < 4; ++k) {
+        uint64_t v = 0;
+        for (int i = 7; i >= 0; --i) v = (v << 8) | dig[8 * k + i];
+        s[k] = v;
+    }
+}
+
 typedef struct orc_rng {
     uint64_t s[4];
     const uint64_t* replay; /* non-NULL: consume pre-drawn raw draws instead of stepping s */
@@ -1012,6 +1027,7 @@ static int mc_cycle(orc_handle* H, int64_t lad, int64_t idx, int sample, int64_t
 static void* xcalloc(size_t n, size_t sz) { void* p = calloc(n ? n : 1, sz); if (!p) { perror("oracle calloc"); abort(); } return p; }
 
 int orc_seed(orc_handle* H, uint64_t seed);
+int orc_seed_job(orc_handle* H, uint64_t seed, int64_t first_ladder);
 orc_handle* orc_create(const ptmc_config* cfg) {
     if (cfg->pot_kind == PTMC_POT_RUNNER && (!cfg->runner || cfg->bc_kind != PTMC_BC_SPHERICAL)) return NULL;
     if (cfg->pot_kind == PTMC_POT_ELJ_B && (!cfg->eljb_a || !cfg->eljb_b)) return NULL;
@@ -1073,7 +1089,7 @@ orc_handle* orc_create(const ptmc_config* cfg) {
     if (npt) H->ev_hist = (double*)xcalloc((size_t)H->n_rep * nb2 * nb2, sizeof(double));
     else H->en_hist = (double*)xcalloc((size_t)H->n_rep * nb2, sizeof(double));
     H->n_threads = 1;
-    if (cfg->rng_mode != PTMC_RNG_REPLAY) orc_seed(H, cfg->seed);   /* like ptmc_create */
+    if (cfg->rng_mode != PTMC_RNG_REPLAY) orc_seed_job(H, cfg->seed, 0);   /* like ptmc_create */
     return H;
 }
 
@@ -1168,6 +1184,21 @@ int orc_seed(orc_handle* H, uint64_t seed) {
     uint64_t* l = (uint64_t*)xcalloc((size_t)H->cfg.n_ladders * 4, 8);
     for (int64_t r = 0; r < H->n_rep * w; ++r) orc_julia_seed(seed + (uint64_t)r, s + 4 * r);
     for (int64_t k = 0; k < H->cfg.n_ladders; ++k) orc_julia_seed(seed + (uint64_t)(H->n_rep * w) + (uint64_t)k, l + 4 * k);
+    int rc = orc_set_rng_states(H, s, l);
+    free(s); free(l);
+    return rc;
+}
+/* seeding rule of ptmc_seed_job (include/ptmc_b200.h) */
+int orc_seed_job(orc_handle* H, uint64_t seed, int64_t first_ladder) {
+    const uint64_t W = (uint64_t)orc_rng_words(H) / 4, T = (uint64_t)H->cfg.n_traj, L = (uint64_t)H->cfg.n_ladders;
+    uint64_t* s = (uint64_t*)xcalloc((size_t)(L * T * W * 4), 8);
+    uint64_t* l = (uint64_t*)xcalloc((size_t)(L * 4), 8);
+    for (uint64_t a = 0; a < L; ++a) {
+        const uint64_t gl = (uint64_t)first_ladder + a;
+        for (uint64_t t = 0; t < T; ++t)
+            for (uint64_t k = 0; k < W; ++k) orc_julia_seed128(seed, (gl * T + t) * W + k + 1, s + ((a * T + t) * W + k) * 4);
+        orc_julia_seed128(seed, (1ull << 63) | gl, l + 4 * a);
+    }
     int rc = orc_set_rng_states(H, s, l);
     free(s); free(l);
     return rc;

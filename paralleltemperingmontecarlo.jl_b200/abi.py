@@ -90,6 +90,7 @@ SYMBOLS = {
     "ptmc_upload_counters": (C.c_int, [_vp, _i64p, _dp]),
     "ptmc_reset_counters": (C.c_int, [_vp]),
     "ptmc_seed": (C.c_int, [_vp, C.c_uint64]),
+    "ptmc_seed_job": (C.c_int, [_vp, C.c_uint64, C.c_int64]),
     "ptmc_rng_words": (C.c_int, [_vp]),
     "ptmc_set_rng_states": (C.c_int, [_vp, _u64p, _u64p]),
     "ptmc_get_rng_states": (C.c_int, [_vp, _u64p, _u64p]),

@@ -144,6 +144,20 @@ static void julia_seed(uint64_t seed, uint64_t s[4]) {
     }
 }
 
+// Random.seed!(lo + hi * 2^64): the little-endian UInt32 words of the integer, trailing zero words dropped (at least one)
+static void julia_seed128(uint64_t lo, uint64_t hi, uint64_t s[4]) {
+    uint8_t msg[16], dig[32];
+    for (int i = 0; i < 8; ++i) { msg[i] = (uint8_t)(lo >> (8 * i)); msg[8 + i] = (uint8_t)(hi >> (8 * i)); }
+    size_t len = 16;
+    while (len > 4 && msg[len - 1] == 0 && msg[len - 2] == 0 && msg[len - 3] == 0 && msg[len - 4] == 0) len -= 4;
+    sha256_block(msg, len, dig);
+    for (int k = 0; k < 4; ++k) {
+        uint64_t v = 0;
+        for (int i = 7; i >= 0; --i) v = (v << 8) | dig[8 * k + i];
+        s[k] = v;
+    }
+}
+
 static sweep_fn pick_kernel(const ptmc_handle* h, int dbg) {
     const int niter = h->P.n_pad / h->G, nc = h->cfg.n_coeff;
     const int fullw = (h->cfg.n_traj * h->G) % 32 == 0 ? 1 : 0;      // every warp of the ladder fully active
@@ -533,7 +547,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
         cudaFuncSetAttribute((const void*)f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     *out = h;
-    if (c->rng_mode != PTMC_RNG_REPLAY) { int r2 = ptmc_seed(h, c->seed); if (r2) { *out = nullptr; return bail(r2); } }
+    if (c->rng_mode != PTMC_RNG_REPLAY) { int r2 = ptmc_seed_job(h, c->seed, 0); if (r2) { *out = nullptr; return bail(r2); } }
     return PTMC_OK;
 }
 
@@ -623,6 +637,19 @@ extern "C" PTMC_API int ptmc_seed(ptmc_handle* h, uint64_t seed) {
     std::vector<uint64_t> s(R * 4), l(L * 4);
     for (size_t r = 0; r < R; ++r) julia_seed(seed + r, &s[4 * r]);
     for (size_t k = 0; k < L; ++k) julia_seed(seed + R + k, &l[4 * k]);
+    return ptmc_set_rng_states(h, s.data(), l.data());
+}
+extern "C" PTMC_API int ptmc_seed_job(ptmc_handle* h, uint64_t seed, int64_t first_ladder) {
+    if (!h) return PTMC_ERR_ARG;
+    if (first_ladder < 0) return fail(h, PTMC_ERR_ARG, "first_ladder must be >= 0");
+    const size_t W = (size_t)rng_words(h) / 4, T = (size_t)h->cfg.n_traj, L = (size_t)h->cfg.n_ladders;
+    std::vector<uint64_t> s(L * T * W * 4), l(L * 4);
+    for (size_t a = 0; a < L; ++a) {
+        const uint64_t gl = (uint64_t)first_ladder + a;
+        for (size_t t = 0; t < T; ++t)
+            for (size_t k = 0; k < W; ++k) julia_seed128(seed, (gl * T + t) * W + k + 1, &s[((a * T + t) * W + k) * 4]);
+        julia_seed128(seed, (1ull << 63) | gl, &l[4 * a]);
+    }
     return ptmc_set_rng_states(h, s.data(), l.data());
 }
 extern "C" PTMC_API int ptmc_rng_words(const ptmc_handle* h) { return h ? rng_words(h) : 0; }

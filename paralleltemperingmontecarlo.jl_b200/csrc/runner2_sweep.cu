@@ -129,36 +129,39 @@ __global__ void __launch_bounds__(RN_THREADS) runner2_init_kernel(const DevParam
         for (int e = 0; e < R.n_eta; ++e) EF[e * NT + t] = exp(-R.eta[e] * d2) * f;
     }
     __syncthreads();
-    // one thread per atom a: every contribution with centre a, summed per neighbour class, then scaled (calc_symm_vals! :320-470)
-    for (int a = tid; a < N; a += RN_THREADS) {
-        double* ga = g + a * gs;
-        const int sa = a >= n1 ? 1 : 0;
-        for (int q = 0; q < R.n_sym; ++q) ga[q] = 0.0;
-        for (int r = 0; r < R.n_rad; ++r)
-            for (int b = 0; b < N; ++b) {
-                if (b == a) continue;
-                const int t = rn_tri(a, b, N);
-                const double f = F[t];
-                if (f != 0.0 && f != 1.0) ga[2 * r + (b >= n1 ? 1 : 0)] += f * exp(-R.rad_eta[r] * D2[t]);   // calc_one_symm_val :229-231
-            }
+    // one thread per (atom a, symmetry function): every contribution with centre a, summed per neighbour class, then scaled
+    // (calc_symm_vals! SymmFunc.jl:320-470)
+    for (int w = tid; w < N * R.n_rad; w += RN_THREADS) {
+        const int a = w / R.n_rad, r = w - a * R.n_rad, sa = a >= n1 ? 1 : 0;
+        double s[2] = {0.0, 0.0};
         for (int b = 0; b < N; ++b) {
             if (b == a) continue;
+            const int t = rn_tri(a, b, N);
+            const double f = F[t];
+            if (f != 0.0 && f != 1.0) s[b >= n1 ? 1 : 0] += f * exp(-R.rad_eta[r] * D2[t]);   // calc_one_symm_val :229-231
+        }
+        for (int c = 0; c < 2; ++c) g[a * gs + 2 * r + c] = s[c] * R.rad_norm[r][2 * sa + c] + R.rad_off[r][2 * sa + c];
+    }
+    for (int w = tid; w < N * R.n_ang; w += RN_THREADS) {
+        const int a = w / R.n_ang, q = w - a * R.n_ang, sa = a >= n1 ? 1 : 0;
+        const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
+        const double* EFe = EF + e * NT;
+        const double la = R.lz_lambda[z], ze = R.lz_zeta[z];
+        const int zi = R.lz_zint[z];
+        double s[3] = {0.0, 0.0, 0.0};
+        for (int b = 0; b < N; ++b) {
+            if (b == a) continue;
+            const int tab = rn_tri(a, b, N);
+            const double dab = D2[tab], iab = INV[tab], eab = EFe[tab];
+            const int sb = b >= n1 ? 1 : 0;
             for (int c = b + 1; c < N; ++c) {
                 if (c == a) continue;
-                const int tab = rn_tri(a, b, N), tac = rn_tri(a, c, N), tbc = rn_tri(b, c, N);
-                const double ca = (D2[tab] + D2[tac] - D2[tbc]) * 0.5 * INV[tab] * INV[tac];
-                const int cls = (b >= n1 ? 1 : 0) + (c >= n1 ? 1 : 0);
-                for (int q = 0; q < R.n_ang; ++q) {
-                    const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
-                    const double ep = EF[e * NT + tab] * EF[e * NT + tac] * EF[e * NT + tbc];
-                    ga[nr2 + 3 * q + cls] += ep * rn_theta(ca, R.lz_lambda[z], R.lz_zeta[z], R.lz_zint[z]);
-                }
+                const int tac = rn_tri(a, c, N), tbc = rn_tri(b, c, N);
+                const double ca = (dab + D2[tac] - D2[tbc]) * 0.5 * iab * INV[tac];
+                s[sb + (c >= n1 ? 1 : 0)] += eab * EFe[tac] * EFe[tbc] * rn_theta(ca, la, ze, zi);
             }
         }
-        for (int r = 0; r < R.n_rad; ++r)
-            for (int c = 0; c < 2; ++c) ga[2 * r + c] = ga[2 * r + c] * R.rad_norm[r][2 * sa + c] + R.rad_off[r][2 * sa + c];
-        for (int q = 0; q < R.n_ang; ++q)
-            for (int c = 0; c < 3; ++c) ga[nr2 + 3 * q + c] = ga[nr2 + 3 * q + c] * R.ang_tpz[q][3 * sa + c] + R.ang_off[q][3 * sa + c];
+        for (int c = 0; c < 3; ++c) g[a * gs + nr2 + 3 * q + c] = s[c] * R.ang_tpz[q][3 * sa + c] + R.ang_off[q][3 * sa + c];
     }
     __syncthreads();
     double* ea = sm + L.ea0;

@@ -130,35 +130,42 @@ __global__ void __launch_bounds__(RN_THREADS) runner_init_kernel(const DevParams
         for (int e = 0; e < R.n_eta; ++e) EF[e * NT + t] = exp(-R.eta[e] * d2) * f;
     }
     __syncthreads();
-    // one thread per atom a: every contribution with centre a
-    for (int a = tid; a < N; a += RN_THREADS) {
-        double* ga = g + a * R.n_act;
-        for (int r = 0; r < R.n_act_rad; ++r) {
-            double s = 0.0;
-            for (int b = 0; b < N; ++b) {
-                if (b == a) continue;
-                const int t = rn_tri(a, b, N);
-                const double f = F[t];
-                if (f != 0.0 && f != 1.0) s += f * exp(-R.rad_eta[r] * D2[t]) * R.rad_norm[r];   // calc_one_symm_val :231
-            }
-            ga[r] = s + R.rad_off[r];
-        }
-        for (int q = 0; q < R.n_act_ang; ++q) ga[R.n_act_rad + q] = 0.0;
+    // one thread per (atom a, symmetry function): every contribution with centre a, in the (b, c) order of calc_symm_vals!
+    // (SymmFunc.jl:259-312) - 55 x 31 work items instead of 55 threads walking all functions (the upload was 4 cycles' worth of time)
+    for (int w = tid; w < N * R.n_act_rad; w += RN_THREADS) {
+        const int a = w / R.n_act_rad, r = w - a * R.n_act_rad;
+        double s = 0.0;
         for (int b = 0; b < N; ++b) {
             if (b == a) continue;
-            for (int c = b + 1; c < N; ++c) {
-                if (c == a) continue;
-                const int tab = rn_tri(a, b, N), tac = rn_tri(a, c, N), tbc = rn_tri(b, c, N);
-                const double ca = (D2[tab] + D2[tac] - D2[tbc]) * 0.5 * INV[tab] * INV[tac];
-                for (int q = 0; q < R.n_act_ang; ++q) {
-                    if (!R.ang_init[q]) continue;
-                    const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
-                    const double ep = EF[e * NT + tab] * EF[e * NT + tac] * EF[e * NT + tbc];
-                    ga[R.n_act_rad + q] += ep * rn_theta(ca, R.lz_lambda[z], R.lz_zeta[z], R.lz_zint[z]) * R.ang_tpz[q];
+            const int t = rn_tri(a, b, N);
+            const double f = F[t];
+            if (f != 0.0 && f != 1.0) s += f * exp(-R.rad_eta[r] * D2[t]) * R.rad_norm[r];   // calc_one_symm_val :231
+        }
+        g[a * R.n_act + r] = s + R.rad_off[r];
+    }
+    for (int w = tid; w < N * R.n_act_ang; w += RN_THREADS) {
+        const int a = w / R.n_act_ang, q = w - a * R.n_act_ang;
+        double s = 0.0;
+        if (R.ang_init[q]) {
+            const int e = R.ang_eta_idx[q], z = R.ang_lz_idx[q];
+            const double* EFe = EF + e * NT;
+            const double la = R.lz_lambda[z], ze = R.lz_zeta[z], tpz = R.ang_tpz[q];
+            const int zi = R.lz_zint[z];
+            for (int b = 0; b < N; ++b) {
+                if (b == a) continue;
+                const int tab = rn_tri(a, b, N);
+                const double dab = D2[tab], iab = INV[tab], eab = EFe[tab];
+                for (int c = b + 1; c < N; ++c) {
+                    if (c == a) continue;
+                    const int tac = rn_tri(a, c, N), tbc = rn_tri(b, c, N);
+                    const double ca = (dab + D2[tac] - D2[tbc]) * 0.5 * iab * INV[tac];
+                    const double ep = eab * EFe[tac] * EFe[tbc];
+                    s += ep * rn_theta(ca, la, ze, zi) * tpz;
                 }
             }
+            s += R.ang_off[q];
         }
-        for (int q = 0; q < R.n_act_ang; ++q) if (R.ang_init[q]) ga[R.n_act_rad + q] += R.ang_off[q];
+        g[a * R.n_act + R.n_act_rad + q] = s;
     }
 #ifndef PTMC_RN_GLOBAL_TABLES
     for (int k = tid; k < (3 + R.n_eta) * NT; k += RN_THREADS) R.pair_c[rep * (size_t)(3 + R.n_eta) * NT + k] = D2[k];

@@ -274,6 +274,11 @@ class Engine:
     def seed(self, seed: int):
         self._check(self._fn("seed")(self._h, C.c_uint64(seed)))
 
+    def seed_job(self, seed: int, first_ladder: int = 0):
+        """hashed (seed, stream id) rule with GLOBAL ladder numbers: disjoint streams for different seeds, same per-ladder streams for
+        any sharding (ptmc_seed_job)"""
+        self._check(self._fn("seed_job")(self._h, C.c_uint64(seed), C.c_int64(first_ladder)))
+
     def rng_words(self) -> int:
         return int(self._fn("rng_words")(self._h))
 

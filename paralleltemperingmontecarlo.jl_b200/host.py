@@ -496,11 +496,11 @@ def ptmc_run(mc_params: MCParams, temp: TempGrid, start_config, potential, ensem
                 start_counter = index                      # start_counter = Int(readdlm("./checkpoint/index.txt")[1]): cycle `index` runs again (:108)
             eng.upload_states(pos, box, md)
             eng.upload_counters(counters, None)
-            eng.seed(seed + start_counter)          # the reference restarts with whatever its task-local generator holds
+            eng.seed_job(seed + start_counter)      # the reference restarts with whatever its task-local generator holds; hashed: no stream is reused
         else:
             pos, box = initial_arrays(mc_params, start_config, n_ladders)
             eng.upload_states(pos, box)
-            eng.seed(seed)
+            eng.seed_job(seed)
             # equilibration (src/MCRun.jl:282-313): MC for eq_cycles ÷ 2 cycles only, cycle index from 1
             n_eq = mc_params.eq_cycles // 2
             if n_eq > 0:

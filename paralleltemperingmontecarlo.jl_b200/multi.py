@@ -30,6 +30,29 @@ def julia_seed_state(seed: int) -> np.ndarray:
     return np.frombuffer(hashlib.sha256(msg).digest(), dtype="<u8").copy()
 
 
+def julia_seed128_state(lo: int, hi: int) -> np.ndarray:
+    """Random.seed!(lo + hi * 2^64): SHA-256 of the little-endian UInt32 words of the integer, trailing zero words dropped."""
+    msg = (lo & (2 ** 64 - 1)).to_bytes(8, "little") + (hi & (2 ** 64 - 1)).to_bytes(8, "little")
+    n = 16
+    while n > 4 and msg[n - 4:n] == b"\0\0\0\0":
+        n -= 4
+    return np.frombuffer(hashlib.sha256(msg[:n]).digest(), dtype="<u8").copy()
+
+
+def job_stream_states(seed: int, first_ladder: int, n_ladders: int, n_traj: int, words: int):
+    """The rule of ptmc_seed_job (include/ptmc_b200.h): stream = hash of (seed, stream id), ids from the GLOBAL ladder number."""
+    w = words // 4
+    slot = np.empty((n_ladders, n_traj, w, 4), dtype=np.uint64)
+    lad = np.empty((n_ladders, 4), dtype=np.uint64)
+    for l in range(n_ladders):
+        gl = first_ladder + l
+        for t in range(n_traj):
+            for k in range(w):
+                slot[l, t, k] = julia_seed128_state(seed, (gl * n_traj + t) * w + k + 1)
+        lad[l] = julia_seed128_state(seed, (1 << 63) | gl)
+    return slot.reshape(n_ladders, n_traj, words), lad
+
+
 def global_stream_states(seed: int, first_ladder: int, n_ladders: int, total_ladders: int, n_traj: int, words: int):
     """Generator states of ladders [first_ladder, first_ladder + n_ladders) of a job of `total_ladders` ladders,
     following the rule of ptmc_seed (include/ptmc_b200.h) with GLOBAL ladder indices."""
@@ -82,7 +105,7 @@ def run_sharded(mc_params, temp, start_config, potential, ensemble, *, total_lad
     try:
         pos, box = initial_arrays(mc_params, start_config, count)
         eng.upload_states(pos, box)
-        seed_global(eng, seed, first, total_ladders)
+        eng.seed_job(seed, first)
         if eq_cycles:
             eng.run_cycles(1, eq_cycles, False)
             eng.reset_counters()
