@@ -87,6 +87,11 @@ def specs(args):
                    deck=lambda c: H.deck_cu55_runner(n_traj=28, cycles=c), ladders=37, cycles=8, eq=4,
                    pilot=dict(ladders=37, cycles=24, n_adjust=2, start_from="c3"), W=3.6e6,
                    W_note="symmetry functions 3.35 Mflop + forward pass 0.24 Mflop as the reference evaluates them", cpu=(1, 1), lanes=0),
+        # not a BASELINE config: --configs brass
+        "brass": dict(workload="Cu50Zn5 two-species RuNNer potential, NNVT with 2 atom swaps per cycle (scripts/brass55.jl), 10-temperature ladder, 74 independent PT ladders per GPU",
+                      deck=lambda c: H.deck_brass55(n_traj=10, cycles=c), ladders=74, cycles=8, eq=4,
+                      pilot=dict(ladders=74, cycles=24, n_adjust=2), W=(55 * 3.6e6 + 2 * 7.2e6) / 57,
+                      W_note="atom moves as C5, a swap as two atom moves", cpu=(2, 1), lanes=0),
     }
 
 
