@@ -352,7 +352,15 @@ def measure(ctx, name, spec, steps, warmup, md_slot, with_cpu):
     h2d = sum(sum(x.numel() * 8 for x in inp) for _, inp, _ in jobs)
     d2h_box = [0] * len(jobs)
 
+    errors = []
+
     def e2e_loop(k, n):
+        try:
+            _e2e_loop(k, n)
+        except BaseException as exc:       # a failed half must fail the run, not shorten its clock
+            errors.append(exc)
+
+    def _e2e_loop(k, n):
         he, inp, outp = jobs[k]
         for s in range(n):
             he.upload_states(inp[0].numpy(), inp[1].numpy(), inp[2].numpy())
@@ -369,6 +377,8 @@ def measure(ctx, name, spec, steps, warmup, md_slot, with_cpu):
         for x in th:
             x.join()
         torch.cuda.synchronize(dev)
+        if errors:
+            raise errors[0]
 
     run_threads(1)                                               # warm-up (pins, first launches)
     barrier()

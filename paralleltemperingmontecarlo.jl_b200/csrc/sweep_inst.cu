@@ -87,7 +87,7 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, 
     // EmbeddedAtomPotential: pair loop unrolled, trial components in registers
     if (pot == PTMC_POT_EAM && geom == GEOM_SPHERE && eam_unrolled(niter, dbg != 0)) {
         switch (niter) {
-#define PTMC_SPE(K) case K: return (sweep_fn)sweep_kernel_eam<G, false, K>;
+#define PTMC_SPE(K) case K: return fullw ? (sweep_fn)sweep_kernel_eam<G, false, K, true> : (sweep_fn)sweep_kernel_eam<G, false, K, false>;
             PTMC_SPE(1) PTMC_SPE(2) PTMC_SPE(3) PTMC_SPE(4) PTMC_SPE(5) PTMC_SPE(6) PTMC_SPE(7) PTMC_SPE(8)
 #undef PTMC_SPE
             default: break;

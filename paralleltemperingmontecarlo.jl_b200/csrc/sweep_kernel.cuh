@@ -516,7 +516,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 NPHI[j] = nphi; NRHO[j] = nrho;
                             }
                         }
-                        sphi = group_sum<G>(sphi, gmask); srho = group_sum<G>(srho, gmask); se = group_sum<G>(se, gmask);
+                        sphi = group_sum<G>(sphi, hmask); srho = group_sum<G>(srho, hmask); se = group_sum<G>(se, hmask);
                         nphi_i = PHI[i] + sphi; nrho_i = RHO[i] + srho;
                         new_en = se + fma(-P.eam_ecam, sqrt_pos(nrho_i), P.eam_ean * nphi_i);
                     }
@@ -558,7 +558,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                         }
                         if (EAM) {
                             double* PHI = Z + NP; double* RHO = PHI + NP;
-                            __syncwarp(gmask);
+                            __syncwarp(gmask);            // inside `if (acc)`: only the accepting groups are here
                             if (EAM_REG) {
 #pragma unroll
                                 for (int k = 0; k < EAM_NK; ++k) {
@@ -911,10 +911,10 @@ sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const i
 #ifndef PTMC_EAM_MAXREG
 #define PTMC_EAM_MAXREG 128
 #endif
-template <int G, bool DBG, int NITER>
+template <int G, bool DBG, int NITER, bool FULLW = false>
 __global__ void __maxnreg__(PTMC_EAM_MAXREG)
 sweep_kernel_eam(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
-    sweep_body<G, PTMC_POT_EAM, GEOM_SPHERE, DBG, NITER, 0>(P, first_idx, n_cycles, sample);
+    sweep_body<G, PTMC_POT_EAM, GEOM_SPHERE, DBG, NITER, 0, FULLW>(P, first_idx, n_cycles, sample);
 }
 
 // ------------------------------------------------------------------------------------------- init --
