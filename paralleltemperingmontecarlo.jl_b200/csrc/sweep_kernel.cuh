@@ -379,9 +379,14 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                                             : dist2_pbc<rhombic>(bx, xi, yi, zi, xj, yj, zj);
                                     const bool valid = (j != i) && (j < N);
                                     if (POT == PTMC_POT_ELJ_EVEN) {
-                                        const double a = (valid && (!npt || d2n <= rcut)) ? d2n : PTMC_PAIR_OFF;
-                                        const double b = (valid && (!npt || d2o <= rcut)) ? d2o : PTMC_PAIR_OFF;
-                                        elj_even_pair_acc<NC>(P, a, b, accn, acco);
+                                        // beyond the cut-off (:323-336), self or padding: the accumulation is predicated off instead of
+                                        // selecting a far distance (no FSEL; a NaN of the self pair, d2o = 0, never reaches the sums)
+                                        const bool okn = valid && (!npt || d2n <= rcut), oko = valid && (!npt || d2o <= rcut);
+                                        const double y = rcp_pos3(d2n * d2o);
+                                        const double xn = y * d2o, xo = y * d2n;
+                                        const double pn = elj_even_poly<NC>(P, xn), po = elj_even_poly<NC>(P, xo);
+                                        if (okn) accn = fma(pn, xn * xn * xn, accn);
+                                        if (oko) acco = fma(po, xo * xo * xo, acco);
                                     } else {
                                         const double dn = valid ? d2n : 1.0, dold = valid ? d2o : 1.0;
                                         double en_j, eo_j;
@@ -629,6 +634,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 if (!recompute) d2o = __ldcg(Da + j);
                                 else if (!DIRP) d2o = dist2_pbc<rhombic>(bx, xa, ya, za, X[j], Y[j], Z[j]);
                                 const double d2 = xmul(d2o, sc2);                 // new_dist2_mat[a, j]
+                                if (POT == PTMC_POT_ELJ_EVEN) {
+                                    // branch-free: some lane of the warp is inside the cut-off for practically every j, so a branch saves nothing
+                                    const double e_ = pair_energy<PTMC_POT_ELJ_EVEN, NC>(P, d2);
+                                    acce += (d2 <= new_rcut) ? e_ : 0.0;
+                                } else
                                 if (d2 <= new_rcut) acce += DIRP ? pair_energy_dir<POT, NC>(P, d2, v0, v1, v2, sc2)      // tangents unchanged by a uniform scaling
                                                                  : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d2);
                             }
