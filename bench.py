@@ -290,11 +290,11 @@ def measure(ctx, name, spec, steps, warmup, md_slot, with_cpu):
         with torch.cuda.stream(stream):
             ctx.flush.fill_(idx & 0xFF)
         eng.run_cycles(idx, cycles, True); idx += cycles
-    barrier()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ev = []
     with ClockSampler(local) as clk:
+        barrier()                                                # all ranks enter the timed region together (after the sampler thread started)
         e0.record(stream)
         for _ in range(steps):
             with torch.cuda.stream(stream):
