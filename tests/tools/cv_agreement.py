@@ -28,7 +28,15 @@ DECKS = {
     "cu55_eam": (lambda: P.host.deck_cu55_eam(n_traj=28, cycles=1), 128, 16, 1000, 3000),
     "pbc216_npt": (lambda: P.host.deck_pbc216(n_traj=16, cycles=1), 148, 16, 400, 1200),       # Cp from H = E + pV (src/Sampling.jl:35-46)
     "ne13_lookup": (lambda: P.host.deck_ne13_lookup(str(LUT), n_traj=16, cycles=1), 256, 32, 2000, 8000),
+    # two species with atom swaps (NNVT): the Cu4Zn2 cluster of the reference's "States NNVT" test, 8 temperatures
+    "brass6_nnvt": (lambda: brass6_deck(), 256, 32, 1000, 4000),
 }
+
+
+def brass6_deck():
+    pos = np.array([[2.36, 2.36, 0.0], [6.99, 2.33, 0.0], [2.33, 6.99, 0.0], [-2.36, 2.36, 0.0], [-6.99, 2.33, 0.0], [-2.33, 6.99, 0.0]])
+    return (P.MCParams(1, 8, 6), P.TempGrid(500.0, 2500.0, 8), P.Config(pos, P.SphericalBC(radius=8.0)),
+            P.host.brass_runner_potential(4, 2), P.host.NNVT((4, 2), n_atom_swaps=1))
 
 
 def heat_capacity(engine_cls, deck, L, eq, cycles, seed, **kw):
@@ -51,7 +59,10 @@ def heat_capacity(engine_cls, deck, L, eq, cycles, seed, **kw):
 
 def main():
     from oracle import oracle
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, (mk, lg, lc, eq, cyc) in DECKS.items():
+        if only and name not in only:
+            continue
         if name == "ne13_lookup" and not LUT.exists():
             continue
         deck = mk()
