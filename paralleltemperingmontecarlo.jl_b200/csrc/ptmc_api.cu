@@ -321,8 +321,10 @@ static int build_runner2(ptmc_handle* h, const ptmc_runner2_desc* d, std::vector
 
 // lanes per replica: enough lanes to keep the per-move serial chain short, few enough that the redundant
 // per-group scalar work (RNG, Metropolis) stays small and many replicas are resident.
-static int auto_lanes(int n_atoms, int n_traj) {
+static int auto_lanes(int n_atoms, int n_traj, bool elj_even_sphere) {
     int g = n_atoms <= 20 ? 4 : (n_atoms <= 72 ? 8 : (n_atoms <= 144 ? 16 : 32));
+    // free-space ELJEven ladders of at most 128 threads: 4 lanes per replica, 8 replicas per warp (sweep_kernel_g4s)
+    if (elj_even_sphere && n_atoms <= 64 && n_traj * 4 <= 128) g = 4;
     while (g > 4 && ((n_traj * g + 31) / 32) * 32 > sweep_max_threads(g)) g /= 2;
     return g;
 }
@@ -416,7 +418,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->geom = sphere ? GEOM_SPHERE : (c->bc_kind == PTMC_BC_RHOMBIC ? GEOM_RHOMB : GEOM_PBC);
     h->n_rep = c->n_ladders * c->n_traj;
     h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0) + (nnvt ? c->n_atom_swaps : 0);     // length(MoveStrategy) src/Ensembles.jl:236-282
-    int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj);
+    int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj, c->pot_kind == PTMC_POT_ELJ_EVEN && sphere && c->n_coeff == 6);
     if (h->runner) G = 32;          // the RuNNer kernels use one 256-thread CTA per replica; G is not used
     if (G != 4 && G != 8 && G != 16 && G != 32) { delete h; return fail(nullptr, PTMC_ERR_ARG, "lanes_per_replica must be 0, 4, 8, 16 or 32"); }
     h->G = G;
@@ -446,7 +448,7 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     // periodic NPT with uniform volume moves: tie table instead of the N x N matrix (n_atoms <= 256: partner indices are bytes)
     P.use_ties = (!sphere && npt && !P.separated && c->n_atoms <= 256) ? 1 : 0;
     for (int dbg = 0; dbg < 2; ++dbg)
-        h->smem_k[dbg] = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere, !eam_unrolled(P.n_pad / G, dbg != 0), !P.use_ties).bytes;
+        h->smem_k[dbg] = smem_layout(c->n_traj, P.n_pad, c->pot_kind, h->threads / 32, !sphere, !eam_unrolled(P.n_pad / G, dbg != 0), !P.use_ties, G).bytes;
     h->smem = h->runner2 ? runner2_smem_bytes(c->n_atoms, h->R2) : h->runner ? runner_smem_bytes(c->n_atoms, h->R) : std::max(h->smem_k[0], h->smem_k[1]);
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));
 

@@ -66,6 +66,27 @@ static sweep_fn special_kernel(int niter, int fullw) {
 sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads) {
     constexpr int G = PTMC_G;
     (void)threads;
+#if PTMC_G == 4
+    // ELJEven, six coefficients, sphere, production streams, ladders of at most 128 threads: the 96-register build (sweep_kernel_g4s)
+    if (!dbg && pot == PTMC_POT_ELJ_EVEN && geom == GEOM_SPHERE && n_coeff == 6 && threads <= 128) {
+        if (rot && fullw && niter >= 2) {
+            switch (niter - 1) {
+#define PTMC_G4R(K) case K: return (sweep_fn)sweep_kernel_g4s<PTMC_POT_ELJ_EVEN, false, K, 6, true, true>;
+                PTMC_G4R(1) PTMC_G4R(2) PTMC_G4R(3) PTMC_G4R(4) PTMC_G4R(5) PTMC_G4R(6) PTMC_G4R(7) PTMC_G4R(8)
+#undef PTMC_G4R
+                default: break;
+            }
+        }
+        switch (niter) {
+#define PTMC_G4N(K) case K: return fullw ? (sweep_fn)sweep_kernel_g4s<PTMC_POT_ELJ_EVEN, false, K, 6, true, false> \
+                                         : (sweep_fn)sweep_kernel_g4s<PTMC_POT_ELJ_EVEN, false, K, 6, false, false>;
+            PTMC_G4N(1) PTMC_G4N(2) PTMC_G4N(3) PTMC_G4N(4) PTMC_G4N(5) PTMC_G4N(6) PTMC_G4N(7) PTMC_G4N(8)
+            PTMC_G4N(9) PTMC_G4N(10) PTMC_G4N(11) PTMC_G4N(12) PTMC_G4N(13) PTMC_G4N(14) PTMC_G4N(15) PTMC_G4N(16)
+#undef PTMC_G4N
+            default: break;
+        }
+    }
+#endif
     if (rot && fullw && !dbg && geom == GEOM_SPHERE && n_coeff == 6 && niter >= 2) {
         sweep_fn f = pot == PTMC_POT_ELJ_EVEN ? rotated_kernel<PTMC_POT_ELJ_EVEN>(niter - 1) : pot == PTMC_POT_ELJ_B ? rotated_kernel<PTMC_POT_ELJ_B>(niter - 1) : nullptr;
         if (f) return f;

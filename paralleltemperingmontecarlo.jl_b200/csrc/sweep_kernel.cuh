@@ -41,12 +41,16 @@ struct SmemLayout {
 #define PTMC_EAM_UNROLL 1
 #endif
 __host__ __device__ constexpr bool eam_unrolled(int niter, bool dbg) { return PTMC_EAM_UNROLL && !dbg && niter >= 1 && niter <= PTMC_EAM_MAX_NITER; }
-__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch, bool newvec) {
+__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch, bool newvec, int lanes) {
     SmemLayout s;
     const bool dirp = pot_kind == PTMC_POT_ELJ_B || pot_kind == PTMC_POT_LUT;
     // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec where the N x N matrix is kept: periodic without the tie table)
     int arrays = 3 + (pot_kind == PTMC_POT_EAM ? (eam_scratch ? 4 : 2) : 0) + ((pbc && newvec) ? 1 : 0);
     s.cfg_stride = arrays * n_pad;
+    // The 32 / G replicas of a warp read the same atom slots of DIFFERENT configuration buffers: a buffer stride of G doubles (mod 16)
+    // lets their 8 G-byte runs tile the 32 banks instead of landing on one another (G = 4: 168 doubles = 8 (mod 16) is a 2-way conflict
+    // on top of the two wavefronts a 256-byte request needs anyway)
+    if (lanes <= 8) while ((s.cfg_stride & 15) != (lanes & 15)) s.cfg_stride += 1;
     s.off_scal = n_traj * s.cfg_stride;
     int off = s.off_scal + 4 * n_traj;
     s.off_exc = off; off += 2 * n_traj;
@@ -152,7 +156,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     const unsigned hmask = FULLW ? 0xffffffffu : gmask;
     constexpr bool EAM_REG = EAM && NITER > 0 && PTMC_EAM_UNROLL;     // trial (phi, rho) components in registers instead of shared memory
     const bool ties = PBC && P.use_ties != 0;      // periodic NPT, uniform volume moves: tie table instead of dist2_mat
-    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG, !ties);
+    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG, !ties, G);
     double* scal = sm + lay.off_scal;
     i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
     double* hams = sm + lay.off_ham;
@@ -915,6 +919,19 @@ template <int G, int POT, int GEOM, bool DBG, int NITER, int NC, bool FULLW = fa
 __global__ void __launch_bounds__(sweep_max_threads_c(G), sweep_min_blocks_c(G))
 sweep_kernel(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
     sweep_body<G, POT, GEOM, DBG, NITER, NC, FULLW, ROT>(P, first_idx, n_cycles, sample);
+}
+// Small ladders on 4 lanes per replica (at most 128 threads): 8 replicas share a warp, so the per-move work that every lane repeats
+// (RNG, trial position, Metropolis, commit) is paid once per 8 moves instead of once per 4 (-15.5 % warp instructions for Ne55).  Shared
+// memory, not registers, bounds the residency there (6 ladders of 24 x Ne55 per SM = 18 warps), so the kernel takes the registers that
+// are free anyway (96 instead of 80) to keep more of the 14 unrolled pair iterations in flight: C2 170.9 -> 155.5 ms per step
+// (profiles/r02_experiments.md; caps of 112 / 128 registers: 156.0 / 157.0 ms).
+#ifndef PTMC_G4S_MAXREG
+#define PTMC_G4S_MAXREG 96
+#endif
+template <int POT, bool DBG, int NITER, int NC, bool FULLW, bool ROT>
+__global__ void __maxnreg__(PTMC_G4S_MAXREG)
+sweep_kernel_g4s(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
+    sweep_body<4, POT, GEOM_SPHERE, DBG, NITER, NC, FULLW, ROT>(P, first_idx, n_cycles, sample);
 }
 // EmbeddedAtomPotential: the unrolled loop wants ~170 registers; capped so that two 224-thread ladders (scripts/cu55.jl:
 // 28 temperatures x 8 lanes) stay resident per SM (a 96-register cap for three ladders spills and measured slower)

@@ -31,12 +31,14 @@ def test_ne13_elj_nvt_replay(lanes):
     print("ne13 lanes", lanes, "max |dE err|", worst)
 
 
-def test_ne55_elj_nvt_replay():
-    # BASELINE C2 geometry and ladder (scripts/ne55.jl), 3 ladders
+@pytest.mark.parametrize("lanes", [0, 8])
+def test_ne55_elj_nvt_replay(lanes):
+    # BASELINE C2 geometry and ladder (scripts/ne55.jl), 3 ladders; lanes 0 = auto: 4 lanes per replica for free-space ELJEven
+    # ladders of at most 128 threads (8 replicas per warp), 8 otherwise
     mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=24, cycles=20)
-    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=3, n_cycles=20, seed=99, n_adjust=10)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=3, n_cycles=20, seed=99, n_adjust=10, lanes=lanes)
     compare_traces(gpu, cpu)
-    assert gpu["lanes"] == 8
+    assert gpu["lanes"] == (lanes or 4)
 
 
 def test_elj_odd_potential_replay():
@@ -268,11 +270,13 @@ def test_shipped_library_refuses_production_trace():
 
 
 def test_production_kernel_trace_c2_ne55():
-    # BASELINE C2 at its own ladder shape: 24 temperatures x 8 lanes = sweep_kernel<8, ELJ_EVEN, SPHERE, false, 7, 6, FULLW>, the
+    # BASELINE C2 at its own ladder shape: 24 temperatures x 4 lanes = sweep_kernel_g4s<ELJ_EVEN, false, 14, 6, FULLW, false>, the
     # kernel of the headline number; step sizes adapted during 100 equilibration cycles as bench.py's pilot does
     mcp, temp, start, pot, ens = P.host.deck_ne55(n_traj=24, cycles=40)
     mcp.n_adjust = 10
     gpu, _, worst = _production_trace_pair((mcp, temp, start, pot, ens), 3, 77, 40, (-0.035, -0.02, None, None), eq_cycles=100)
+    # ... and the 8-lane kernel (sweep_kernel<8, ELJ_EVEN, SPHERE, false, 7, 6, FULLW>: ladders of more than 32 temperatures, round 1's headline)
+    _production_trace_pair((mcp, temp, start, pot, ens), 2, 78, 20, (-0.035, -0.02, None, None), eq_cycles=50, lanes=8)
     acc = gpu["trace"]["accepted"].mean()
     assert 0.3 < acc < 0.75 and gpu["trace"]["exchange"][..., 0].sum() > 3
     print("C2 production trace: %d moves, acceptance %.3f, max |dE err| %.2e" % (gpu["trace"]["accepted"].size, acc, worst))
