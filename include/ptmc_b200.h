@@ -155,7 +155,7 @@ typedef struct ptmc_config {
     int32_t rng_mode;         /* ptmc_rng_mode                                                       */
     double min_acc, max_acc;  /* MCParams.min_acc / max_acc                                          */
     uint64_t seed;            /* job seed: ptmc_create seeds with ptmc_seed_job(h, seed, 0)           */
-    int32_t lanes_per_replica;/* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one replica       */
+    int32_t lanes_per_replica;/* 0 = auto; else 2 (free-space ELJEven only), 4, 8, 16, 32 lanes cooperating on one replica */
     int32_t separated_volume; /* NPT.separated_volume (src/Ensembles.jl:81): volume_change_separated, RhombicBC / RectangularBC */
     /* ABI 2: PTMC_POT_ELJ_B only - coeff_a, coeff_b [n_coeff] (coeff_c travels in coeff[])                */
     const double* eljb_a;

@@ -14,6 +14,7 @@
 #include "sweep_kernel.cuh"
 
 namespace ptmc {
+sweep_fn sweep_table_g2(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
 sweep_fn sweep_table_g4(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
 sweep_fn sweep_table_g8(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
 sweep_fn sweep_table_g16(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads);
@@ -163,6 +164,7 @@ static sweep_fn pick_kernel(const ptmc_handle* h, int dbg) {
     const int fullw = (h->cfg.n_traj * h->G) % 32 == 0 ? 1 : 0;      // every warp of the ladder fully active
     const int rot = (h->cfg.n_atoms - 1) % h->G == 0 ? 1 : 0;          // the other N - 1 atoms fill the lanes exactly
     switch (h->G) {
+        case 2: return sweep_table_g2(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
         case 4: return sweep_table_g4(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
         case 8: return sweep_table_g8(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
         case 16: return sweep_table_g16(h->cfg.pot_kind, h->geom, dbg, niter, nc, fullw, rot, h->threads);
@@ -325,6 +327,8 @@ static int auto_lanes(int n_atoms, int n_traj, bool elj_even_sphere) {
     int g = n_atoms <= 20 ? 4 : (n_atoms <= 72 ? 8 : (n_atoms <= 144 ? 16 : 32));
     // free-space ELJEven ladders of at most 128 threads: 4 lanes per replica, 8 replicas per warp (sweep_kernel_g4s)
     if (elj_even_sphere && n_atoms <= 64 && n_traj * 4 <= 128) g = 4;
+    // ... small clusters whose ladder fills whole warps on 2 lanes and whose other atoms split evenly (rotated order): 16 replicas per warp
+    if (elj_even_sphere && n_atoms <= 34 && (n_atoms - 1) % 2 == 0 && n_atoms >= 5 && (n_traj * 2) % 32 == 0 && n_traj * 2 <= 128) g = 2;
     while (g > 4 && ((n_traj * g + 31) / 32) * 32 > sweep_max_threads(g)) g /= 2;
     return g;
 }
@@ -420,7 +424,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0) + (nnvt ? c->n_atom_swaps : 0);     // length(MoveStrategy) src/Ensembles.jl:236-282
     int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj, c->pot_kind == PTMC_POT_ELJ_EVEN && sphere && c->n_coeff == 6);
     if (h->runner) G = 32;          // the RuNNer kernels use one 256-thread CTA per replica; G is not used
-    if (G != 4 && G != 8 && G != 16 && G != 32) { delete h; return fail(nullptr, PTMC_ERR_ARG, "lanes_per_replica must be 0, 4, 8, 16 or 32"); }
+    if (G != 2 && G != 4 && G != 8 && G != 16 && G != 32) { delete h; return fail(nullptr, PTMC_ERR_ARG, "lanes_per_replica must be 0, 2, 4, 8, 16 or 32"); }
+    if (G == 2 && !(c->pot_kind == PTMC_POT_ELJ_EVEN && sphere)) { delete h; return fail(nullptr, PTMC_ERR_ARG, "2 lanes per replica are built for free-space ELJPotentialEven ladders only"); }
     h->G = G;
     h->threads = ((c->n_traj * G + 31) / 32) * 32;
     if (!h->runner && h->threads > sweep_max_threads(G)) { int mt = sweep_max_threads(G); delete h; return fail(nullptr, PTMC_ERR_ARG, "n_traj * lanes_per_replica = %d exceeds %d threads per ladder", c->n_traj * G, mt); }

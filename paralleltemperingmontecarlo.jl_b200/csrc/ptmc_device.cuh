@@ -155,26 +155,35 @@ struct Stream {
 // draw costs two SHFL instead of a redundant ~25-instruction generator step in every lane.
 template <int G>
 struct BatchRng {
-    Xo a, b;          // b: second substream of the lane, G == 4 only
-    u64 bufa, bufb;
+    // lane g of the group steps the substreams g, g + G, ... (NS = 8 / G of them for G < 8, one for G >= 8): substream K lives in
+    // slot K / G of lane K % G
+    static constexpr int NS = G >= 8 ? 1 : 8 / G;
+    Xo st_[NS];
+    u64 buf[NS];
     __device__ __forceinline__ void load(const u64* st, int g) {
-        const u64* p = st + 4 * (g & 7);
-        a.s0 = p[0]; a.s1 = p[1]; a.s2 = p[2]; a.s3 = p[3];
-        if (G == 4) { p = st + 4 * (g + 4); b.s0 = p[0]; b.s1 = p[1]; b.s2 = p[2]; b.s3 = p[3]; }
-        bufa = 0; bufb = 0;
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+            const u64* p = st + 4 * ((G >= 8 ? (g & 7) : g) + m * G);
+            st_[m].s0 = p[0]; st_[m].s1 = p[1]; st_[m].s2 = p[2]; st_[m].s3 = p[3];
+            buf[m] = 0;
+        }
     }
     __device__ __forceinline__ void store(u64* st, int g) const {
-        if (g < 8) { u64* p = st + 4 * g; p[0] = a.s0; p[1] = a.s1; p[2] = a.s2; p[3] = a.s3; }
-        if (G == 4) { u64* p = st + 4 * (g + 4); p[0] = b.s0; p[1] = b.s1; p[2] = b.s2; p[3] = b.s3; }
+        if (G >= 8 && g >= 8) return;
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+            u64* p = st + 4 * (g + m * G);
+            p[0] = st_[m].s0; p[1] = st_[m].s1; p[2] = st_[m].s2; p[3] = st_[m].s3;
+        }
     }
     __device__ __forceinline__ void begin() {
-        bufa = xo_next(a);
-        if (G == 4) bufb = xo_next(b);
+#pragma unroll
+        for (int m = 0; m < NS; ++m) buf[m] = xo_next(st_[m]);
     }
     template <int K>
     __device__ __forceinline__ u64 raw(unsigned mask) const {
-        if (G == 4) return __shfl_sync(mask, K < 4 ? bufa : bufb, K & 3, 4);
-        return __shfl_sync(mask, bufa, K, G);
+        if (G >= 8) return __shfl_sync(mask, buf[0], K, G);
+        return __shfl_sync(mask, buf[(K / G) % NS], K % G, G);
     }
     template <int K>
     __device__ __forceinline__ double rand(unsigned mask) const { return (double)(raw<K>(mask) >> 11) * 0x1.0p-53; }

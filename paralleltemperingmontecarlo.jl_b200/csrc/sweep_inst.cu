@@ -3,12 +3,42 @@
 #include "sweep_kernel.cuh"
 
 #ifndef PTMC_G
-#error "compile with -DPTMC_G=<4|8|16|32>"
+#error "compile with -DPTMC_G=<2|4|8|16|32>"
 #endif
 #define PTMC_CAT2(a, b) a##b
 #define PTMC_CAT(a, b) PTMC_CAT2(a, b)
 
 namespace ptmc {
+
+#if PTMC_G == 2
+// Two lanes per replica, 16 replicas per warp: free-space ELJEven ladders whose n_traj x 2 threads fill whole warps (Ne13 at 32
+// temperatures: BASELINE C1) and whose other N - 1 atoms split evenly over the two lanes (ROT: no parking, no padding).  The per-move
+// work every lane repeats is paid once per 16 moves.  Only this family is instantiated for G = 2.  A 64-thread ladder leaves registers
+// to spare; measured on C1 (ms per step of 1.48e9 moves): caps of 80 / 96 / 112 / 128 / 152 registers -> 80.2 / 71.7 / 67.6 / 66.2 / 70.7
+// (the 4-lane kernel: 79.1).
+#ifndef PTMC_G2_MAXREG
+#define PTMC_G2_MAXREG 128
+#endif
+template <int POT, bool DBG, int NITER, int NC, bool FULLW, bool ROT>
+__global__ void __maxnreg__(PTMC_G2_MAXREG)
+sweep_kernel_g2(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
+    sweep_body<2, POT, GEOM_SPHERE, DBG, NITER, NC, FULLW, ROT>(P, first_idx, n_cycles, sample);
+}
+sweep_fn sweep_table_g2(int pot, int geom, int dbg, int niter, int n_coeff, int fullw, int rot, int threads) {
+    (void)threads;
+    if (pot != PTMC_POT_ELJ_EVEN || geom != GEOM_SPHERE) return nullptr;
+    if (dbg) return (sweep_fn)sweep_kernel_g2<PTMC_POT_ELJ_EVEN, true, 0, 0, false, false>;
+    if (n_coeff == 6 && rot && fullw && niter >= 2) {
+        switch (niter - 1) {
+#define PTMC_G2R(K) case K: return (sweep_fn)sweep_kernel_g2<PTMC_POT_ELJ_EVEN, false, K, 6, true, true>;
+            PTMC_G2R(2) PTMC_G2R(3) PTMC_G2R(4) PTMC_G2R(5) PTMC_G2R(6) PTMC_G2R(7) PTMC_G2R(8) PTMC_G2R(9) PTMC_G2R(10) PTMC_G2R(12) PTMC_G2R(14) PTMC_G2R(16)
+#undef PTMC_G2R
+            default: break;
+        }
+    }
+    return (sweep_fn)sweep_kernel_g2<PTMC_POT_ELJ_EVEN, false, 0, 0, false, false>;
+}
+#else
 
 // Generic kernels (runtime pair-loop trip count and coefficient count), one per potential / geometry / debug.
 static sweep_fn generic_kernel(int pot, int geom, int dbg) {
@@ -145,5 +175,7 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, 
     }
     return generic_kernel(pot, geom, dbg);
 }
+
+#endif   // PTMC_G != 2
 
 }  // namespace ptmc

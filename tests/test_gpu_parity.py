@@ -13,7 +13,7 @@ from parity import compare_traces, run_pair
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("lanes", [0, 4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [0, 2, 4, 8, 16, 32])
 def test_ne13_elj_nvt_replay(lanes):
     # BASELINE C1 at the script's own 25 temperatures (examples/ne13.jl:82): 2 ladders, 60 cycles incl. one
     # step-size adjustment (n_adjust=25) and two launches (chunks) so cursors/RNG/counters persist correctly.
@@ -191,7 +191,7 @@ def test_xoshiro_mode_matches_oracle_seeding():
     _assert_same_trajectory(res)
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
 def test_batch8_production_mode_ne13(lanes):
     # production RNG mode (8 substreams per slot, one batch per move) through the specialised kernels:
     # the whole trajectory (positions, counters, step sizes, histograms, generator states) is bit-identical
@@ -839,6 +839,12 @@ def test_rotated_neighbour_order_kernels(n_traj):
     rmax = np.sqrt((start.positions ** 2).sum(axis=1).max())
     tight = P.Config(start.positions, P.SphericalBC(radius=rmax * 1.05))
     _assert_same_trajectory(_free_run_pair((mcp, temp, tight, pot, ens), 2, 3, abi.RNG_BATCH8, 20, lanes=4))
+    # two lanes per replica (16 replicas per warp, six rotated iterations, four substreams per lane): n_traj * 2 a multiple of 32
+    if n_traj % 16 == 0:
+        _assert_same_trajectory(_free_run_pair(P.host.deck_ne13(n_traj=n_traj, cycles=60), 3, 91 + n_traj, abi.RNG_BATCH8, 60, lanes=2))
+        mcp, temp, start, pot, ens = P.host.deck_ne13(n_traj=16, cycles=20)
+        tight = P.Config(start.positions, P.SphericalBC(radius=rmax * 1.05))
+        _assert_same_trajectory(_free_run_pair((mcp, temp, tight, pot, ens), 2, 5, abi.RNG_BATCH8, 20, lanes=2))
 
 
 def _fcc_cluster(n, a):
