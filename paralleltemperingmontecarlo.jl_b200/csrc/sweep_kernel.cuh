@@ -467,13 +467,18 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 if (ROT) { j += i + 1; j -= (j >= N) ? N : 0; }
                                 const double xj = ROT ? X[j] : Xg[k * G], yj = ROT ? X[NP + j] : Xg[NP + k * G], zj = ROT ? X[2 * NP + j] : Xg[2 * NP + k * G];
                                 const bool valid = ROT || ((j != i) && (j < N));   // not the moved atom, not padding
-                                double ax = tx - xj, ay = ty - yj, az = tz - zj;
-                                double d2n = fma(az, az, fma(ay, ay, ax * ax));
                                 double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
                                 double d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
                                 if (POT == PTMC_POT_ELJ_EVEN) {
+                                    // (forming d2n from d2o, |b + s|^2 = |b|^2 + 2 s.b + |s|^2, saves 2 of the 34 FP64 instructions per pair and
+                                    // measured 1.4 % SLOWER: the longer dependency chain costs more `wait` stalls than the issue slots give back,
+                                    // profiles/r02_experiments.md)
+                                    const double ax = tx - xj, ay = ty - yj, az = tz - zj;
+                                    const double d2n = fma(az, az, fma(ay, ay, ax * ax));
                                     elj_even_pair_acc<NC>(P, d2n, d2o, accn, acco);     // parked atoms contribute exactly 0
                                 } else {
+                                    double ax = tx - xj, ay = ty - yj, az = tz - zj;
+                                    double d2n = fma(az, az, fma(ay, ay, ax * ax));
                                     // the moved atom itself (d2o = 0 -> NaN) and the padding atoms are discarded here
                                     const double en_j = POT == PTMC_POT_ELJ_B ? eljb_energy<NC>(P, d2n, az * az)
                                                       : POT == PTMC_POT_LUT ? lut_energy(P, d2n, ax, ay, az) : pair_energy<POT, NC>(P, d2n);
