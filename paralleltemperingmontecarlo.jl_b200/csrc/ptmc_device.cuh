@@ -482,6 +482,16 @@ __device__ __forceinline__ Box make_box(int bc_kind, double L, double h) {
 // distance2 with minimum image, src/Configurations.jl:104-109 (cubic), :110-120 (rhombic), :121-126 (rect).
 // Divisions are replaced by multiplications with reciprocals: the rounded quotient feeding rint() differs
 // only when a pair sits exactly on the half-box plane, where both images are equidistant.
+// round(a * b) for the minimum-image quotients (|a b| of order 1).  PTMC_RINT_MAGIC: fma(a, b, 1.5 * 2^52) - 1.5 * 2^52 on the FP64
+// pipe (exact ties-to-even for |a b| < 2^51, one rounding instead of two) instead of DMUL + FRND on the XU pipe - experiment,
+// profiles/r02_experiments.md
+__device__ __forceinline__ double rint_mul(double a, double b) {
+#ifdef PTMC_RINT_MAGIC
+    return __dadd_rn(__fma_rn(a, b, 6755399441055744.0), -6755399441055744.0);
+#else
+    return rint(a * b);
+#endif
+}
 template <bool RHOMBIC>
 __device__ __forceinline__ double dist2_pbc(const Box& b, double ax, double ay, double az, double bx, double by, double bz) {
     // The reference's rhombic image (:110-120) is b + nu a1 + nv a2 with a1 = (L, 0), a2 = (L/2, sqrt(3)/2 L) and
@@ -490,15 +500,15 @@ __device__ __forceinline__ double dist2_pbc(const Box& b, double ax, double ay, 
     const double ex = ax - bx, ey = ay - by, ez = az - bz;
     double dx, dy;
     if (RHOMBIC) {
-        const double nv = rint(ey * b.ihy);
-        const double nu = rint(fma(-b.is3, ey, ex) * b.iL);
+        const double nv = rint_mul(ey, b.ihy);
+        const double nu = rint_mul(fma(-b.is3, ey, ex), b.iL);
         dx = fma(-b.hL, nv, fma(-b.L, nu, ex));
         dy = fma(-b.hy, nv, ey);
     } else {
-        dx = fma(-b.L, rint(ex * b.iL), ex);
-        dy = fma(-b.L, rint(ey * b.iL), ey);
+        dx = fma(-b.L, rint_mul(ex, b.iL), ex);
+        dy = fma(-b.L, rint_mul(ey, b.iL), ey);
     }
-    const double dz = fma(-b.h, rint(ez * b.ih), ez);
+    const double dz = fma(-b.h, rint_mul(ez, b.ih), ez);
     return fma(dz, dz, fma(dy, dy, dx * dx));
 }
 // The same with the minimum-image separation itself (the tangent-dependent potentials need the direction of the pair)

@@ -5,6 +5,7 @@
 //   exchange  (src/MCRun.jl:203-205, src/Exchange.jl:132-186) -> lane 0 of the lower slot between two mbarrier phases of the two warps involved
 //   update_max_stepsize! (src/Exchange.jl:198-263), sampling_step! (src/Sampling.jl:330-371) -> per group
 #pragma once
+#include <type_traits>
 #include "ptmc_device.cuh"
 
 namespace ptmc {
@@ -32,9 +33,16 @@ struct SmemLayout {
     int off_moved;      // periodic: int moved[T][words + 1]
     int off_sep;        // periodic: per slot {max_displ[2], max_displ[3], max_boxheight, int n_acc_xy, n_adj_xy, n_acc_z, n_adj_z} (6 doubles)
     int off_tan;        // periodic tangent-dependent potentials: double tan_rho[T], int fresh[T][words] (stale-tangent state, see sep_trial_energy)
+    int off_psum;       // periodic NPT with the tie table, ELJPotentialEven: power sums per configuration, double [T][6][lanes] + int valid[T]
     int off_tab;        // EAM: the mantissa table of eam_invrexp (PTMC_EAM_KTAB_DOUBLES, 16-byte aligned)
     size_t bytes;
 };
+// Power sums (uniform volume moves of ELJPotentialEven with 6 coefficients, periodic NPT with the tie table):
+// E = sum_k c_k S_k, S_k = sum over the pairs inside the cut-off of (1 / d2)^(3 + k).  A uniform scaling by s multiplies every
+// distance and the cut-off alike, so the trial energy of volume_change_uniform (src/MCMoves.jl:277-287 + dimer_energy_config on
+// dist2_mat * s^2, src/MCRun.jl:76-85) is sum_k c_k s^-(6 + 2k) S_k: O(1) instead of N (N - 1) / 2 pair energies, once the S_k are
+// carried along by the atom moves.
+#define PTMC_PSUM_K 6
 // EAM kernels with an unrolled pair loop keep the trial components in registers (eam_scratch = false).
 #define PTMC_EAM_MAX_NITER 8
 #ifndef PTMC_EAM_UNROLL
@@ -60,6 +68,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     s.off_moved = off; off += pbc ? (n_traj * ((n_pad + 31) / 32 + 1) + 1) / 2 + 1 : 0;
     s.off_sep = off; off += pbc ? 6 * n_traj : 0;
     s.off_tan = off; off += (pbc && dirp) ? n_traj + (n_traj * ((n_pad + 31) / 32) + 1) / 2 : 0;
+    s.off_psum = off; off += (pbc && !newvec && pot_kind == PTMC_POT_ELJ_EVEN) ? n_traj * PTMC_PSUM_K * lanes + (n_traj + 1) / 2 : 0;
     off += off & 1;
     s.off_tab = off; off += pot_kind == PTMC_POT_EAM ? PTMC_EAM_KTAB_DOUBLES : 0;
     s.bytes = (size_t)off * sizeof(double);
@@ -130,6 +139,24 @@ __device__ __forceinline__ void sep_rewrite_matrix(const DevParams& P, const dou
         }
 }
 
+// power sums: s[k] +/-= x^(3 + k), k = 0..5, under a predicate (the cut-off / self / padding mask of the pair)
+template <bool ADD>
+__device__ __forceinline__ void psum_acc(double x, bool ok, double (&s)[PTMC_PSUM_K]) {
+    // x^3 .. x^8 as a tree (depth 3, 7 multiplications) rather than a chain of depth 7: the pair loop is latency sensitive
+    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+    const double pw[PTMC_PSUM_K] = {x3, x4, x2 * x3, x3 * x3, x3 * x4, x4 * x4};
+#pragma unroll
+    for (int k = 0; k < PTMC_PSUM_K; ++k)
+        if (ok) s[k] = ADD ? s[k] + pw[k] : s[k] - pw[k];
+}
+// sum_k c_k s_k
+__device__ __forceinline__ double psum_energy(const DevParams& P, const double (&s)[PTMC_PSUM_K]) {
+    double e = P.coeff[PTMC_PSUM_K - 1] * s[PTMC_PSUM_K - 1];
+#pragma unroll
+    for (int k = PTMC_PSUM_K - 2; k >= 0; --k) e = fma(P.coeff[k], s[k], e);
+    return e;
+}
+
 // DBG   : sequential slot stream (Julia-compatible XOSHIRO mode, or REPLAY) + optional trace.  !DBG: BATCH8.
 // NITER : compile-time ceil(n_atoms / G) of the pair loop (n_pad = NITER * G), 0 = runtime trip count.
 // NC    : compile-time number of ELJ coefficients (6), 0 = runtime.
@@ -156,6 +183,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     const unsigned hmask = FULLW ? 0xffffffffu : gmask;
     constexpr bool EAM_REG = EAM && NITER > 0 && PTMC_EAM_UNROLL;     // trial (phi, rho) components in registers instead of shared memory
     const bool ties = PBC && P.use_ties != 0;      // periodic NPT, uniform volume moves: tie table instead of dist2_mat
+    // ... and with it, for ELJPotentialEven{6}: power sums instead of the O(N^2) trial energy of a volume move
+    constexpr bool PSUM = PBC && POT == PTMC_POT_ELJ_EVEN && NC == PTMC_PSUM_K;
+    const bool psum = PSUM && ties;
     const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG, !ties, G);
     double* scal = sm + lay.off_scal;
     i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
@@ -165,6 +195,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     int* moved = reinterpret_cast<int*>(sm + lay.off_moved);
     double* trho = sm + lay.off_tan;                       // stale-tangent factor per configuration
     int* fresh = reinterpret_cast<int*>(trho + T);          // atoms moved since the last xy / z trial, [T][FW]
+    double* psp = sm + lay.off_psum;                                  // power sums per configuration and lane, [T][6][G]
+    int* psv = reinterpret_cast<int*>(psp + T * PTMC_PSUM_K * G);     // ... valid in this launch (built at the first volume move)
     const int FW = (NP + 31) / 32;
     const int MW = P.moved_words + 1;            // ints per configuration in moved[]
     const bool npt = PBC && P.ensemble == PTMC_ENS_NPT;
@@ -194,6 +226,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
             scal[4 * c0 + 1] = L; scal[4 * c0 + 2] = h;
             scal[4 * c0 + 3] = npt ? get_r_cut(P.bc_kind, L, h) : 0.0;
             perm[slot] = c0;
+            if (PSUM && psum) psv[c0] = 0;
             if (PBC) for (int w = 0; w < MW; ++w) moved[c0 * MW + w] = P.moved_g[((i64)lad * T + c0) * MW + w];
             if (PBC && DIRP) {
                 const bool st = P.separated != 0;
@@ -261,6 +294,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
         if (active && phase != 2) {
             // ================================================================== mc_step! for this slot ==
             const int c = perm[slot];
+            if (PSUM && psum && ((first_idx + cyc) & 255) == 0) {     // bound the rounding drift of the carried sums: rebuild now and then
+                __syncwarp(gmask);
+                if (g == 0) psv[c] = 0;
+                __syncwarp(gmask);
+            }
             double* X = sm + (size_t)c * lay.cfg_stride;
             double* Y = X + NP; double* Z = Y + NP;
             double en = scal[4 * c];
@@ -345,6 +383,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     }
                     // -------------------------------- energy_update! src/EnergyEvaluation.jl:1474-1506,1567-1591
                     double new_en;
+                    double dS[PTMC_PSUM_K];                 // power sums of the new row minus those of the old row (this lane's pairs)
+                    if (PSUM) {
+#pragma unroll
+                        for (int k = 0; k < PTMC_PSUM_K; ++k) dS[k] = 0.0;
+                    }
                     constexpr int EAM_NK = EAM_REG ? NITER : 1;
                     double nph[EAM_NK], nrh[EAM_NK], nphi_i = 0.0, nrho_i = 0.0;   // EAM: trial components of this lane's atoms / of atom i
                     if (PARK) {
@@ -373,7 +416,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             if (thawed || ties) {
                                 // thawed: both rows from the positions in shared memory, pair loop unrolled like the free-space one
                                 const double* Xg = X + g;
-                                auto pbc_term = [&](int k) {
+                                auto pbc_term = [&](int k, auto ps_tag) {
+                                    constexpr bool PS = decltype(ps_tag)::value;
                                     const int j = g + k * G;
                                     const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
                                     double vn0 = 0, vn1 = 0, vn2 = 0, vo0 = 0, vo1 = 0, vo2 = 0;
@@ -388,9 +432,15 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                         const bool okn = valid && (!npt || d2n <= rcut), oko = valid && (!npt || d2o <= rcut);
                                         const double y = rcp_pos3(d2n * d2o);
                                         const double xn = y * d2o, xo = y * d2n;
-                                        const double pn = elj_even_poly<NC>(P, xn), po = elj_even_poly<NC>(P, xo);
-                                        if (okn) accn = fma(pn, xn * xn * xn, accn);
-                                        if (oko) acco = fma(po, xo * xo * xo, acco);
+                                        if (PS) {
+                                            // the row difference of the six power sums instead of the two Horner forms: they give dE (below)
+                                            // and, on acceptance, carry the configuration's S_k along
+                                            if (PSUM) { psum_acc<true>(xn, okn, dS); psum_acc<false>(xo, oko, dS); }
+                                        } else {
+                                            const double pn = elj_even_poly<NC>(P, xn), po = elj_even_poly<NC>(P, xo);
+                                            if (okn) accn = fma(pn, xn * xn * xn, accn);
+                                            if (oko) acco = fma(po, xo * xo * xo, acco);
+                                        }
                                     } else {
                                         const double dn = valid ? d2n : 1.0, dold = valid ? d2o : 1.0;
                                         double en_j, eo_j;
@@ -405,13 +455,17 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                         accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                     }
                                 };
-                                if (NITER) {
+                                auto pbc_row = [&](auto ps_tag) {
+                                    if (NITER) {
 #pragma unroll
-                                    for (int k = 0; k < NITER; ++k) pbc_term(k);
-                                } else {
-                                    const int nk = NP / G;
-                                    for (int k = 0; k < nk; ++k) pbc_term(k);
-                                }
+                                        for (int k = 0; k < NITER; ++k) pbc_term(k, ps_tag);
+                                    } else {
+                                        const int nk = NP / G;
+                                        for (int k = 0; k < nk; ++k) pbc_term(k, ps_tag);
+                                    }
+                                };
+                                if (PSUM && psum) { pbc_row(std::true_type{}); accn = psum_energy(P, dS); }
+                                else pbc_row(std::false_type{});
                             } else
                             for (int j = g; j < N; j += G) {
                                 const double xj = X[j], yj = Y[j], zj = Z[j];
@@ -457,6 +511,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                         return DIRP ? pair_energy_dir<POT, NC>(P, d, v0, v1, v2) : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d);
                                     };
                                     acco += old_term(d2f) - old_term(d2r);
+                                    // the pair was an active tie until now, i.e. outside the power sums: take back what the row loop subtracted
+                                    if (PSUM && psum) psum_acc<true>(rcp_pos(d2r), d2r <= rcut, dS);
                                 }
                             }
                         } else {
@@ -552,6 +608,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 __syncwarp(gmask);
                                 if (g == 0) fresh[c * FW + (i >> 5)] |= 1 << (i & 31);
                             }
+                            if (PSUM && psum && psv[c]) {
+                                double* sp = psp + (size_t)c * PTMC_PSUM_K * G + g;
+#pragma unroll
+                                for (int k = 0; k < PTMC_PSUM_K; ++k) sp[k * G] += dS[k];
+                            }
                             if (moved[c * MW + MW - 1] < N) {
                                 if (!ties) {
                                     // dist2_mat[index, :] = dist2_mat[:, index] = new_dist2_vec  (swap_config.jl:45-46)
@@ -633,7 +694,61 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     double* D = P.d2mat + ((size_t)lad * T + c) * N * N;
                     const bool thawed = moved[c * MW + MW - 1] >= N;
                     const bool recompute = thawed || ties;
-                    if (!sepv) {
+                    if (PSUM && psum) {
+                        double* sp = psp + (size_t)c * PTMC_PSUM_K * G + g;
+                        if (!psv[c]) {
+                            // first volume move of this configuration in the launch: build the sums from the positions (one pass of the
+                            // size of the loop this replaces), active cut-off ties (pairs of never-moved atoms in the tie table) left out
+                            double sk[PTMC_PSUM_K];
+#pragma unroll
+                            for (int k = 0; k < PTMC_PSUM_K; ++k) sk[k] = 0.0;
+                            for (int a = 0; a < N - 1; ++a) {
+                                const double xa = X[a], ya = Y[a], za = Z[a];
+                                for (int j = a + 1 + g; j < N; j += G) {
+                                    const double d2 = dist2_pbc<rhombic>(bx, xa, ya, za, X[j], Y[j], Z[j]);
+                                    psum_acc<true>(rcp_pos(d2), d2 <= rcut, sk);
+                                }
+                            }
+                            if (!thawed) {
+                                for (int a = g; a < N; a += G) {
+                                    if ((moved[c * MW + (a >> 5)] >> (a & 31)) & 1) continue;
+                                    const size_t row = ((size_t)lad * T + c) * N + a;
+                                    const int cnt = __ldg(P.tie_cnt + row);
+                                    for (int t = 0; t < cnt; ++t) {
+                                        const int j = __ldg(P.tie_idx + row * PTMC_TIE_K + t);
+                                        if (j < a || ((moved[c * MW + (j >> 5)] >> (j & 31)) & 1)) continue;
+                                        const double d2r = dist2_pbc<rhombic>(bx, X[a], Y[a], Z[a], X[j], Y[j], Z[j]);
+                                        psum_acc<false>(rcp_pos(d2r), d2r <= rcut, sk);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < PTMC_PSUM_K; ++k) sp[k * G] = sk[k];
+                            __syncwarp(gmask);
+                            if (g == 0) psv[c] = 1;
+                            __syncwarp(gmask);
+                        }
+                        // dimer_energy_config on dist2_mat * scale^2 below the scaled cut-off: sum_k c_k (1 / scale^2)^(3 + k) S_k
+                        const double r = xdiv(1.0, sc2);
+                        double e_ = P.coeff[PTMC_PSUM_K - 1] * sp[(PTMC_PSUM_K - 1) * G];
+#pragma unroll
+                        for (int k = PTMC_PSUM_K - 2; k >= 0; --k) e_ = fma(e_, r, P.coeff[k] * sp[k * G]);
+                        acce = e_ * (r * r * r);
+                        if (!thawed) {
+                            // active ties: new_dist2_mat entry = frozen dist2_mat entry * scale^2, decided against the new cut-off
+                            for (int a = g; a < N; a += G) {
+                                if ((moved[c * MW + (a >> 5)] >> (a & 31)) & 1) continue;
+                                const size_t row = ((size_t)lad * T + c) * N + a;
+                                const int cnt = __ldg(P.tie_cnt + row);
+                                for (int t = 0; t < cnt; ++t) {
+                                    const int j = __ldg(P.tie_idx + row * PTMC_TIE_K + t);
+                                    if (j < a || ((moved[c * MW + (j >> 5)] >> (j & 31)) & 1)) continue;
+                                    const double d2 = xmul(__ldcg(P.tie_val + row * PTMC_TIE_K + t), sc2);
+                                    if (d2 <= new_rcut) acce += pair_energy<PTMC_POT_ELJ_EVEN, NC>(P, d2);
+                                }
+                            }
+                        }
+                    } else if (!sepv) {
                         for (int a = 0; a < N - 1; ++a) {
                             const double* Da = D + (size_t)a * N;
                             const double xa = X[a], ya = Y[a], za = Z[a];
@@ -701,6 +816,13 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                         // swap_config_v! src/swap_config.jl:113-140
                         __syncwarp(gmask);
                         for (int j = g; j < N; j += G) { X[j] = xmul(scale_xy, X[j]); Y[j] = xmul(scale_xy, Y[j]); Z[j] = xmul(scale_z, Z[j]); }
+                        if (PSUM && psum) {
+                            double* sp = psp + (size_t)c * PTMC_PSUM_K * G + g;
+                            const double r = xdiv(1.0, sc2);
+                            double rk = r * r * r;
+#pragma unroll
+                            for (int k = 0; k < PTMC_PSUM_K; ++k) { sp[k * G] *= rk; rk *= r; }
+                        }
                         if (!thawed) {
                             if (ties) {
                                 for (int a = g; a < N; a += G) {                  // dist2_mat .= new_dist2_mat, the entries that are kept
