@@ -482,14 +482,15 @@ __device__ __forceinline__ Box make_box(int bc_kind, double L, double h) {
 // distance2 with minimum image, src/Configurations.jl:104-109 (cubic), :110-120 (rhombic), :121-126 (rect).
 // Divisions are replaced by multiplications with reciprocals: the rounded quotient feeding rint() differs
 // only when a pair sits exactly on the half-box plane, where both images are equidistant.
-// round(a * b) for the minimum-image quotients (|a b| of order 1).  PTMC_RINT_MAGIC: fma(a, b, 1.5 * 2^52) - 1.5 * 2^52 on the FP64
-// pipe (exact ties-to-even for |a b| < 2^51, one rounding instead of two) instead of DMUL + FRND on the XU pipe - experiment,
-// profiles/r02_experiments.md
+// round(a * b) for the minimum-image quotients of dist2_pbc (|a b| of order 1): fma(a, b, 1.5 * 2^52) - 1.5 * 2^52 on the FP64 pipe
+// (ties-to-even like rint for |a b| < 2^51; one rounding instead of two) instead of DMUL + FRND on the XU pipe, whose latency sits
+// in the middle of the pair loop's dependency chain: C4 +4.5 % (profiles/r02_experiments.md).  Only where the image of a pair that
+// sits exactly on a half-cell plane cannot matter (see dist2_pbc); dist2_pbc_vec keeps rint.
 __device__ __forceinline__ double rint_mul(double a, double b) {
-#ifdef PTMC_RINT_MAGIC
-    return __dadd_rn(__fma_rn(a, b, 6755399441055744.0), -6755399441055744.0);
-#else
+#ifdef PTMC_RINT_FRND
     return rint(a * b);
+#else
+    return __dadd_rn(__fma_rn(a, b, 6755399441055744.0), -6755399441055744.0);
 #endif
 }
 template <bool RHOMBIC>
@@ -497,6 +498,9 @@ __device__ __forceinline__ double dist2_pbc(const Box& b, double ax, double ay, 
     // The reference's rhombic image (:110-120) is b + nu a1 + nv a2 with a1 = (L, 0), a2 = (L/2, sqrt(3)/2 L) and
     // nv = round(ey / (sqrt(3)/2 L)), nu = round((ex - ey / sqrt(3)) / L) of the ORIGINAL separation e = a - b, i.e. an independent
     // round per lattice coordinate: 17 FP64 instructions per distance (the literal form: 24).
+    // Callers: pairs with at least one atom at a random (moved / trial) position, and lattice pairs under the NPT cut-off - a pair on a
+    // half-cell plane is at least the inscribed radius = sqrt(r_cut) apart in either image, so it is outside the cut-off or an exact
+    // cut-off tie, whose recomputed term the tie table replaces by the frozen one (computed through this same function).
     const double ex = ax - bx, ey = ay - by, ez = az - bz;
     double dx, dy;
     if (RHOMBIC) {

@@ -504,8 +504,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     const int j = __ldg(P.tie_idx + row * PTMC_TIE_K + t);
                                     if ((moved[c * MW + (j >> 5)] >> (j & 31)) & 1) continue;
                                     const double d2f = __ldcg(P.tie_val + row * PTMC_TIE_K + t);
-                                    double v0, v1, v2;
-                                    const double d2r = dist2_pbc_vec<rhombic>(bx, xi, yi, zi, X[j], Y[j], Z[j], v0, v1, v2);
+                                    double v0 = 0, v1 = 0, v2 = 0;      // the same distance function as the row loop, so that the recomputed term cancels
+                                    const double d2r = DIRP ? dist2_pbc_vec<rhombic>(bx, xi, yi, zi, X[j], Y[j], Z[j], v0, v1, v2)
+                                                            : dist2_pbc<rhombic>(bx, xi, yi, zi, X[j], Y[j], Z[j]);
                                     auto old_term = [&](double d) {
                                         if (npt && !(d <= rcut)) return 0.0;
                                         return DIRP ? pair_energy_dir<POT, NC>(P, d, v0, v1, v2) : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d);
@@ -776,8 +777,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 for (int t = 0; t < cnt; ++t) {
                                     const int j = __ldg(P.tie_idx + row * PTMC_TIE_K + t);
                                     if (j < a || ((moved[c * MW + (j >> 5)] >> (j & 31)) & 1)) continue;
-                                    double v0, v1, v2;
-                                    const double d2r = dist2_pbc_vec<rhombic>(bx, X[a], Y[a], Z[a], X[j], Y[j], Z[j], v0, v1, v2);
+                                    double v0 = 0, v1 = 0, v2 = 0;
+                                    const double d2r = DIRP ? dist2_pbc_vec<rhombic>(bx, X[a], Y[a], Z[a], X[j], Y[j], Z[j], v0, v1, v2)
+                                                            : dist2_pbc<rhombic>(bx, X[a], Y[a], Z[a], X[j], Y[j], Z[j]);
                                     auto new_term = [&](double d) {
                                         if (!(d <= new_rcut)) return 0.0;
                                         return DIRP ? pair_energy_dir<POT, NC>(P, d, v0, v1, v2, sc2) : pair_energy<POT == PTMC_POT_EAM ? PTMC_POT_ELJ_EVEN : POT, NC>(P, d);
