@@ -423,6 +423,10 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     h->n_rep = c->n_ladders * c->n_traj;
     h->n_steps = c->n_atom_moves + (npt ? c->n_volume_moves : 0) + (nnvt ? c->n_atom_swaps : 0);     // length(MoveStrategy) src/Ensembles.jl:236-282
     int G = c->lanes_per_replica ? c->lanes_per_replica : auto_lanes(c->n_atoms, c->n_traj, c->pot_kind == PTMC_POT_ELJ_EVEN && sphere && c->n_coeff == 6);
+    // the pbc216 class (rhombic NPT, uniform volume moves from power sums, 14 atoms per lane on 16 lanes, 256-thread ladders): two replicas
+    // per warp, two ladders per SM (sweep_kernel_p16)
+    if (!c->lanes_per_replica && c->pot_kind == PTMC_POT_ELJ_EVEN && c->n_coeff == 6 && c->bc_kind == PTMC_BC_RHOMBIC && npt && !c->separated_volume &&
+        (c->n_atoms + 15) / 16 == 14 && c->n_traj * 16 <= 256) G = 16;
     if (h->runner) G = 32;          // the RuNNer kernels use one 256-thread CTA per replica; G is not used
     if (G != 2 && G != 4 && G != 8 && G != 16 && G != 32) { delete h; return fail(nullptr, PTMC_ERR_ARG, "lanes_per_replica must be 0, 2, 4, 8, 16 or 32"); }
     if (G == 2 && !(c->pot_kind == PTMC_POT_ELJ_EVEN && sphere)) { delete h; return fail(nullptr, PTMC_ERR_ARG, "2 lanes per replica are built for free-space ELJPotentialEven ladders only"); }

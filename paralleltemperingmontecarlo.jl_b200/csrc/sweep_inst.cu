@@ -146,6 +146,10 @@ sweep_fn PTMC_CAT(sweep_table_g, PTMC_G)(int pot, int geom, int dbg, int niter, 
     }
     // periodic ELJEven with the six-coefficient form: Horner chain unrolled, coefficients in uniform registers; for the wide
     // lane groups that periodic systems use, the thawed pair loop is unrolled as well
+#if PTMC_G == 16
+    if (!dbg && pot == PTMC_POT_ELJ_EVEN && n_coeff == 6 && geom == GEOM_RHOMB && niter == 14 && threads <= 256)
+        return (sweep_fn)sweep_kernel_p16<GEOM_RHOMB, 14>;
+#endif
 #if PTMC_G >= 16
     if (!dbg && pot == PTMC_POT_ELJ_EVEN && n_coeff == 6 && (geom == GEOM_PBC || geom == GEOM_RHOMB)) {
         switch (niter) {

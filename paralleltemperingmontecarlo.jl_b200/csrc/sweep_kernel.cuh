@@ -1062,6 +1062,14 @@ __global__ void __maxnreg__(PTMC_G4S_MAXREG)
 sweep_kernel_g4s(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
     sweep_body<4, POT, GEOM_SPHERE, DBG, NITER, NC, FULLW, ROT>(P, first_idx, n_cycles, sample);
 }
+// Periodic ELJEven{6} on 16 lanes per replica (two replicas per warp, 256-thread ladders of 16 temperatures, two ladders per SM at
+// 128 registers): worth it only since uniform volume moves are O(1) (power sums) - before, a volume move of one replica stalled
+// its warp mate for 80 atom moves (profiles/r02_experiments.md)
+template <int GEOM, int NITER>
+__global__ void __maxnreg__(128)
+sweep_kernel_p16(const DevParams P, const i64 first_idx, const i64 n_cycles, const int sample) {
+    sweep_body<16, PTMC_POT_ELJ_EVEN, GEOM, false, NITER, 6>(P, first_idx, n_cycles, sample);
+}
 // EmbeddedAtomPotential: the unrolled loop wants ~170 registers; capped so that two 224-thread ladders (scripts/cu55.jl:
 // 28 temperatures x 8 lanes) stay resident per SM (a 96-register cap for three ladders spills and measured slower)
 #ifndef PTMC_EAM_MAXREG

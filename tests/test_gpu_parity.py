@@ -104,20 +104,24 @@ def test_small_npt_replay(bc_cls):
     assert gpu["trace"]["move_index"].max() == 33          # volume moves happened
 
 
-def test_pbc216_npt_replay():
+@pytest.mark.parametrize("lanes", [0, 32])
+def test_pbc216_npt_replay(lanes):
     # BASELINE C4 (scripts/pbc216.jl): 216 atoms, rhombic cell, 16 temperatures, fcc/hcp alternating
+    # (lanes 0 -> 16 lanes per replica, two replicas per warp; 32: one warp per replica)
     mcp, temp, start, pot, ens = P.host.deck_pbc216(n_traj=16, cycles=3)
-    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=3, seed=8)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=3, seed=8, lanes=lanes)
     compare_traces(gpu, cpu, positions_exact=False)
 
 
-def test_pbc216_npt_replay_through_thaw():
-    # long enough for every atom of every configuration to have moved: the kernel stops reading the frozen dist2_mat and
-    # recomputes old rows from the positions ("thawed"); decisions and energies must stay on the oracle's trajectory
+@pytest.mark.parametrize("lanes", [0, 32])
+def test_pbc216_npt_replay_through_thaw(lanes):
+    # long enough for every atom of every configuration to have moved: the kernel stops correcting old rows from the tie table
+    # ("thawed"); uniform volume moves take their trial energy from the power sums the atom moves carry;
+    # decisions and energies must stay on the oracle's trajectory
     mcp, temp, start, pot, ens = P.host.deck_pbc216(n_traj=4, cycles=40)
     md = np.full((1, 4, 4), 0.1)
     md[:, :, 0] = 0.5
-    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=40, seed=12, max_displ=md, n_adjust=20)
+    gpu, cpu = run_pair(mcp, temp, start, pot, ens, n_ladders=1, n_cycles=40, seed=12, max_displ=md, n_adjust=20, lanes=lanes)
     compare_traces(gpu, cpu, positions_exact=False)
     acc = gpu["trace"]["accepted"]
     idx = gpu["trace"]["move_index"]
@@ -298,6 +302,8 @@ def test_production_kernel_trace_c1_c3_c4():
     md[:, :, 0] = 0.5
     v0 = P.get_volume(start[0].boundary_condition)
     gpu, _, w4 = _production_trace_pair((mcp, temp, start, pot, ens), 1, 3, 30, (-0.5, 1.5, 0.8 * v0, 2.0 * v0), max_displ=md, positions_exact=False)
+    # (that was sweep_kernel_p16, the 16-lane kernel the benchmark times; the one-warp-per-replica kernel of the other periodic sizes:)
+    _production_trace_pair((mcp, temp, start, pot, ens), 1, 4, 12, (-0.5, 1.5, 0.8 * v0, 2.0 * v0), max_displ=md, positions_exact=False, lanes=32)
     idx, acc = gpu["trace"]["move_index"], gpu["trace"]["accepted"]
     assert (idx == 217).sum() > 100 and acc[idx == 217].sum() > 5                     # volume moves, some accepted
     moved = [len(np.unique(idx[0, :, s][(acc[0, :, s] == 1) & (idx[0, :, s] <= 216)])) for s in range(16)]
@@ -825,6 +831,28 @@ def test_reference_script_decks_cu38_and_pbc32():
     np.testing.assert_allclose(sg["pos"], sc["pos"], rtol=1e-11, atol=1e-11)
     np.testing.assert_allclose(sg["en_tot"], sc["en_tot"], rtol=1e-10)
     assert sg["counters"][:, :, abi.C_VOL_TOT].sum() > 0
+
+
+@pytest.mark.parametrize("bc_cls,lanes", [(P.RhombicBC, 0), (P.CubicBC, 16), (P.RhombicBC, 32)])
+def test_uniform_volume_moves_from_power_sums(bc_cls, lanes):
+    # periodic NPT, ELJPotentialEven{6}, production streams: the kernels take the trial energy of volume_change_uniform
+    # (src/MCMoves.jl:277-287, dimer_energy_config on dist2_mat * scale^2: src/MCRun.jl:76-85) from six power sums that the atom moves
+    # carry along - five volume moves per cycle from the perfect lattice (cut-off ties live, then thawed), 256+ cycles so
+    # that the periodic rebuild of the sums is crossed: same decisions as the oracle's O(N^2) sums, energies to 1e-10
+    start = _small_pbc(bc_cls)
+    mcp = P.MCParams(300, 6, 32, n_adjust=20)
+    temp = P.TempGrid(20.0, 40.0, 6)
+    pot = P.ELJPotentialEven(P.host.ELJ_NE_COEFF)
+    ens = P.NPT(32, 101325 * 3.398928944382626e-14, False, n_volume_moves=5)
+    v0 = P.get_volume(start.boundary_condition)
+    (sg, hg, rg), (sc, hc, rc) = _free_run_pair((mcp, temp, start, pot, ens), 2, 17, abi.RNG_BATCH8, 300, lanes=lanes,
+                                                bounds=(-1.0, 1.0, 0.5 * v0, 3.0 * v0))
+    assert np.array_equal(sg["counters"], sc["counters"]) and np.array_equal(hg, hc) and np.array_equal(rg[0], rc[0])
+    assert sg["counters"][:, :, abi.C_VOL_TOT].sum() > 100
+    np.testing.assert_allclose(sg["pos"], sc["pos"], rtol=1e-10, atol=1e-10)     # exp / pow of two libms in every accepted scale factor
+    np.testing.assert_allclose(sg["box"], sc["box"], rtol=1e-11)
+    np.testing.assert_allclose(sg["en_tot"], sc["en_tot"], rtol=1e-10)
+    np.testing.assert_allclose(sg["ham"], sc["ham"], rtol=1e-10)
 
 
 @pytest.mark.parametrize("n_traj", [8, 16, 32])
