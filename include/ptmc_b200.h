@@ -301,7 +301,8 @@ PTMC_API int ptmc_issue_probe(int device, double sm_mhz, double* cycles_per_dfma
 
 /* Accuracy probe (tests): the pair arithmetic of the sweep kernel for n pairs of squared distances, exactly as
  * it is accumulated per move: e_new[k] = e(d2_new[k]), e_old[k] = e(d2_old[k]) for the handle's potential
- * (ELJ / ELJEven: dimer_energy src/EnergyEvaluation.jl:923-942; EAM: the r^-n term of invrexp :1088-1095). */
+ * (ELJ / ELJEven: dimer_energy src/EnergyEvaluation.jl:923-942; EAM: e_new = the r^-n term of invrexp :1088-1095 for d2_new,
+ * e_old = the kernel's square root, :1156-1162, of d2_old). */
 PTMC_API int ptmc_debug_pair_energy(ptmc_handle* h, int n, const double* d2_new, const double* d2_old, double* e_new, double* e_old);
 
 /* RuNNer (tests): the g_matrix [n_atoms][n_rad + n_ang] (= Julia's column-major (n_sym x N) NNPVariables.g_matrix) and

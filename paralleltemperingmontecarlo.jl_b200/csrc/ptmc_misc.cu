@@ -85,7 +85,8 @@ __global__ void pair_probe_kernel(const DevParams P, int n, const double* d2n, c
         a = elj_odd(P, d2n[k]); b = elj_odd(P, d2o[k]);
     } else {
         double p, r;
-        eam_invrexp(P, P.eam_ktab, P.eam_etab, d2n[k], p, r); a = p; eam_invrexp(P, P.eam_ktab, P.eam_etab, d2o[k], p, r); b = p;   // phi terms
+        eam_invrexp(P, P.eam_ktab, P.eam_etab, d2n[k], p, r); a = p;      // phi term
+        b = sqrt_pos(d2o[k]);                                             // the kernel's square root (of the rho sums)
     }
     en[k] = a; eo[k] = b;
 }

@@ -519,6 +519,21 @@ def test_eam_power_accuracy():
     eng.close()
 
 
+def test_eam_sqrt_accuracy():
+    # calc_energies_from_components (src/EnergyEvaluation.jl:1156-1162) takes sqrt(rho_i) for every atom and move: the kernel's branch-free
+    # square root (rsqrt seed, one coupled Newton step, one residual step) against the correctly rounded one: <= 1 ulp
+    mcp, temp, start, pot, ens = P.host.deck_cu55_eam(n_traj=4, cycles=1)
+    eng = Engine(sweep_config(mcp, temp, start, pot, ens))
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(1e-3, 1e3, 400000), 2.0 ** rng.uniform(-200, 200, 100000), np.array([1.0, 2.0, 4.0, 1.0 + 2.0 ** -52, 4.0 - 2.0 ** -50])])
+    _, got = eng.debug_pair_energy(np.ones_like(x), x)
+    ref = np.sqrt(x)
+    ulp = np.abs(got - ref) / np.spacing(ref)
+    assert ulp.max() <= 1.0, ulp.max()
+    assert (ulp == 0).mean() > 0.9
+    eng.close()
+
+
 @pytest.mark.parametrize("case", ["eam", "pbc216", "runner", "eam_full", "pbc216_full", "runner_full"])
 def test_energy_bookkeeping_other_potentials(case):
     # size-independent property for the other potentials: the running en_tot (updated move by move, through exchanges,
