@@ -171,8 +171,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     // ROT (free space, (N - 1) a multiple of G): lane g visits the OTHER atoms i+1+g, i+1+g+G, ... (mod N), so the row takes
     // (N - 1) / G iterations instead of ceil(N / G) (Ne13 on 4 lanes: 3 instead of 4) and needs neither parking nor selects
     constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN && !ROT;   // mask by parking atoms far away instead of per-pair selects
-    const int T = P.n_traj, N = P.n_atoms;
-    const int NP = (NITER && !ROT) ? NITER * G : P.n_pad;
+    // ROT kernels: N = NITER G + 1 is a compile-time constant, and every coordinate array is stored twice in a row (atoms 0 .. N-1,
+    // then 0 .. N-2 again), so that the rotated walk i+1+g, i+1+g+G, ... needs no wrap-around: all loads of a row are immediate
+    // offsets from one address (the index arithmetic was 6 integer instructions per pair iteration)
+    const int T = P.n_traj, N = ROT ? NITER * G + 1 : P.n_atoms;
+    const int NP = ROT ? 2 * (NITER * G + 1) : (NITER ? NITER * G : P.n_pad);
     const int lad = blockIdx.x;
     const int tid = threadIdx.x;
     const int slot = tid / G, g = tid & (G - 1);
@@ -210,10 +213,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
         double* X = sm + (size_t)c0 * lay.cfg_stride;
         double* Y = X + NP; double* Z = Y + NP;
         const double* gp = P.pos + rep * 3 * N;
-        for (int j = g; j < NP; j += G) {
+        for (int jj = g; jj < NP; jj += G) {
+            const int j = (ROT && jj >= N) ? jj - N : jj;       // ROT: second copy
             bool v = j < N;
             const double pad = PARK ? PTMC_FAR : 0.0;
-            X[j] = v ? gp[3 * j] : pad; Y[j] = v ? gp[3 * j + 1] : pad; Z[j] = v ? gp[3 * j + 2] : pad;
+            X[jj] = v ? gp[3 * j] : pad; Y[jj] = v ? gp[3 * j + 1] : pad; Z[jj] = v ? gp[3 * j + 2] : pad;
             if (EAM) {
                 Z[NP + j] = v ? P.comp[(rep * N + j) * 2] : 1.0;          // phi
                 Z[2 * NP + j] = v ? P.comp[(rep * N + j) * 2 + 1] : 1.0;  // rho
@@ -340,7 +344,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                 for (int j = 0; j < N; ++j) cz = xadd(cz, Z[j]);
                                 cx = xdiv(cx, (double)N); cy = xdiv(cy, (double)N); cz = xdiv(cz, (double)N);
                                 __syncwarp(gmask);
-                                for (int j = g; j < N; j += G) { X[j] = xsub(X[j], cx); Y[j] = xsub(Y[j], cy); Z[j] = xsub(Z[j], cz); }
+                                for (int j = g; j < N; j += G) {
+                                    const double nx = xsub(X[j], cx), ny = xsub(Y[j], cy), nz = xsub(Z[j], cz);
+                                    X[j] = nx; Y[j] = ny; Z[j] = nz;
+                                    if (ROT) { X[j + N] = nx; Y[j + N] = ny; Z[j + N] = nz; }
+                                }
                                 __syncwarp(gmask);
                                 xi = X[i]; yi = Y[i]; zi = Z[i];
                             } else {
@@ -518,11 +526,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             }
                         } else {
                             // free space: the old row is recomputed from the positions (no dist2_mat is stored)
-                            const double* Xg = X + g;
+                            const double* Xg = ROT ? X + (i + 1 + g) : X + g;
                             auto pair_term = [&](int k) {
-                                int j = g + k * G;
-                                if (ROT) { j += i + 1; j -= (j >= N) ? N : 0; }
-                                const double xj = ROT ? X[j] : Xg[k * G], yj = ROT ? X[NP + j] : Xg[NP + k * G], zj = ROT ? X[2 * NP + j] : Xg[2 * NP + k * G];
+                                const int j = g + k * G;
+                                // ROT: Xg points at atom i + 1 + g of the doubled arrays
+                                const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
                                 const bool valid = ROT || ((j != i) && (j < N));   // not the moved atom, not padding
                                 double bx_ = xi - xj, by_ = yi - yj, bz_ = zi - zj;
                                 double d2o = fma(bz_, bz_, fma(by_, by_, bx_ * bx_));
@@ -600,7 +608,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     }
                     if (acc) {
                         // swap_atom_config! src/swap_config.jl:40-51 (+ swap_vars! :208-211 for EAM)
-                        if (g == 0) { X[i] = tx; Y[i] = ty; Z[i] = tz; }
+                        if (ROT) { if (g < 2) { const int o = g ? i + N : i; X[o] = tx; Y[o] = ty; Z[o] = tz; } }     // both copies (G >= 2)
+                        else if (g == 0) { X[i] = tx; Y[i] = ty; Z[i] = tz; }
                         en = new_en;
                         n_acc_atom += 1; n_adj_atom += 1;
                         if (PBC) {
