@@ -457,8 +457,8 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     // periodic NPT with uniform volume moves: tie table instead of the N x N matrix (n_atoms <= 256: partner indices are bytes)
     P.use_ties = (!sphere && npt && !P.separated && c->n_atoms <= 256) ? 1 : 0;
     for (int dbg = 0; dbg < 2; ++dbg) {
-        // the production ROT kernels (free-space ELJEven, (N - 1) a multiple of G) keep every coordinate array twice: 2 N slots per array
-        const bool rot2 = !dbg && sphere && c->pot_kind == PTMC_POT_ELJ_EVEN && (c->n_atoms - 1) % G == 0;
+        // the production ROT kernels (free-space ELJEven / ELJPotentialB, (N - 1) a multiple of G) keep every coordinate array twice: 2 N slots per array
+        const bool rot2 = !dbg && sphere && (c->pot_kind == PTMC_POT_ELJ_EVEN || c->pot_kind == PTMC_POT_ELJ_B) && (c->n_atoms - 1) % G == 0;
         h->smem_k[dbg] = smem_layout(c->n_traj, rot2 ? std::max(P.n_pad, 2 * c->n_atoms) : P.n_pad, c->pot_kind, h->threads / 32, !sphere,
                                      !eam_unrolled(P.n_pad / G, dbg != 0), !P.use_ties, G).bytes;
     }

@@ -187,6 +187,17 @@ struct BatchRng {
     }
     template <int K>
     __device__ __forceinline__ double rand(unsigned mask) const { return (double)(raw<K>(mask) >> 11) * 0x1.0p-53; }
+    // (rand() - 0.5) * 2^53 = v - 2^52 for the 53-bit integer v = raw >> 11, exactly, without the 64-bit integer -> double conversion
+    // (I2F.F64.U64 runs on the XU pipe, and its latency heads the dependency chain of every move): the low 52 bits m go under the
+    // exponent of 2^52 (w = 2^52 + m), then w - (bit 52 ? 2^52 : 2^53).  With max_displ * 2^-53 (exact) the displacement
+    // (rand() - 0.5) * max_displ of atom_displacement (src/MCMoves.jl:35-37) comes out bit for bit.
+    template <int K>
+    __device__ __forceinline__ double centered(unsigned mask) const {
+        const u64 v = raw<K>(mask) >> 11;
+        const unsigned hi = (unsigned)(v >> 32);
+        const double w = __hiloint2double((int)(0x43300000u | (hi & 0xfffffu)), (int)(unsigned)v);
+        return w - ((hi >> 20) ? 4503599627370496.0 : 9007199254740992.0);
+    }
 };
 
 // ----------------------------------------------------------------------------------- group reduction --

@@ -245,10 +245,11 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     Stream<DBG> S;      // sequential stream (DBG kernels)
     BatchRng<G> B;      // BATCH8 substreams (production kernels)
     double beta = 0, dmax = 0, vmax = 0, max_boxl = 0;
+    double dmax53 = 0;      // max_displ[1] * 2^-53 (BatchRng::centered)
     int n_acc_atom = 0, n_adj_atom = 0, n_acc_vol = 0, n_adj_vol = 0;   // this launch / since last adjustment
     if (active) {
         beta = P.betas[slot];
-        dmax = P.max_displ[rep * 4];
+        dmax = P.max_displ[rep * 4]; dmax53 = dmax * 0x1.0p-53;
         n_adj_atom = (int)P.counters[rep * PTMC_NCOUNT + PTMC_C_ATOM_ADJ];
         if (PBC) {
             vmax = P.max_displ[rep * 4 + 1];
@@ -323,9 +324,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                     double xi = X[i], yi = Y[i], zi = Z[i];
                     double tx, ty, tz;
                     if (BATCH) {
-                        tx = xadd(xi, xmul(xsub(B.template rand<1>(hmask), 0.5), dmax));
-                        ty = xadd(yi, xmul(xsub(B.template rand<2>(hmask), 0.5), dmax));
-                        tz = xadd(zi, xmul(xsub(B.template rand<3>(hmask), 0.5), dmax));
+                        tx = xadd(xi, xmul(B.template centered<1>(hmask), dmax53));
+                        ty = xadd(yi, xmul(B.template centered<2>(hmask), dmax53));
+                        tz = xadd(zi, xmul(B.template centered<3>(hmask), dmax53));
                     } else {
                         tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
                         ty = xadd(yi, xmul(xsub(S.rand(), 0.5), dmax));
@@ -354,14 +355,14 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             } else {
                                 if (BATCH) {
                                     if (++redraws == 1) {
-                                        tx = xadd(xi, xmul(xsub(B.template rand<5>(gmask), 0.5), dmax));
-                                        ty = xadd(yi, xmul(xsub(B.template rand<6>(gmask), 0.5), dmax));
-                                        tz = xadd(zi, xmul(xsub(B.template rand<7>(gmask), 0.5), dmax));
+                                        tx = xadd(xi, xmul(B.template centered<5>(gmask), dmax53));
+                                        ty = xadd(yi, xmul(B.template centered<6>(gmask), dmax53));
+                                        tz = xadd(zi, xmul(B.template centered<7>(gmask), dmax53));
                                     } else {
                                         B.begin();
-                                        tx = xadd(xi, xmul(xsub(B.template rand<0>(gmask), 0.5), dmax));
-                                        ty = xadd(yi, xmul(xsub(B.template rand<1>(gmask), 0.5), dmax));
-                                        tz = xadd(zi, xmul(xsub(B.template rand<2>(gmask), 0.5), dmax));
+                                        tx = xadd(xi, xmul(B.template centered<0>(gmask), dmax53));
+                                        ty = xadd(yi, xmul(B.template centered<1>(gmask), dmax53));
+                                        tz = xadd(zi, xmul(B.template centered<2>(gmask), dmax53));
                                     }
                                 } else {
                                     tx = xadd(xi, xmul(xsub(S.rand(), 0.5), dmax));
@@ -935,6 +936,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                 double rate = xdiv((double)n_adj_atom, (double)((i64)P.n_adjust * P.n_atom_moves));
                 if (rate < P.min_acc) dmax = xmul(dmax, 0.9);
                 else if (rate > P.max_acc) dmax = xmul(dmax, 1.1);
+                dmax53 = dmax * 0x1.0p-53;
                 n_adj_atom = 0;
                 if (PBC) {
                     if (npt && !P.separated) {
