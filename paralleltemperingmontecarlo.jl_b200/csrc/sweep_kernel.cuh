@@ -142,12 +142,14 @@ __device__ __forceinline__ void sep_rewrite_matrix(const DevParams& P, const dou
 // power sums: s[k] +/-= x^(3 + k), k = 0..5, under a predicate (the cut-off / self / padding mask of the pair)
 template <bool ADD>
 __device__ __forceinline__ void psum_acc(double x, bool ok, double (&s)[PTMC_PSUM_K]) {
-    // x^3 .. x^8 as a tree (depth 3, 7 multiplications) rather than a chain of depth 7: the pair loop is latency sensitive
+    // x^3 .. x^8 as a tree (depth 3, 7 multiplications) rather than a chain of depth 7: the pair loop is latency sensitive.
+    // The predicate zeroes x (one select) instead of guarding the six additions: the compiler turned those into a divergent
+    // branch per distance (BSSY / BRA / BSYNC: 11 % of the kernel's instructions, ncu) - and a NaN of the self pair never enters.
+    x = ok ? x : 0.0;
     const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
     const double pw[PTMC_PSUM_K] = {x3, x4, x2 * x3, x3 * x3, x3 * x4, x4 * x4};
 #pragma unroll
-    for (int k = 0; k < PTMC_PSUM_K; ++k)
-        if (ok) s[k] = ADD ? s[k] + pw[k] : s[k] - pw[k];
+    for (int k = 0; k < PTMC_PSUM_K; ++k) s[k] = ADD ? s[k] + pw[k] : s[k] - pw[k];
 }
 // sum_k c_k s_k
 __device__ __forceinline__ double psum_energy(const DevParams& P, const double (&s)[PTMC_PSUM_K]) {
