@@ -142,14 +142,20 @@ __device__ __forceinline__ void sep_rewrite_matrix(const DevParams& P, const dou
 // power sums: s[k] +/-= x^(3 + k), k = 0..5, under a predicate (the cut-off / self / padding mask of the pair)
 template <bool ADD>
 __device__ __forceinline__ void psum_acc(double x, bool ok, double (&s)[PTMC_PSUM_K]) {
-    // x^3 .. x^8 as a tree (depth 3, 7 multiplications) rather than a chain of depth 7: the pair loop is latency sensitive.
+    // x^3 .. x^8 as a tree (depth 3) rather than a chain of depth 7: the pair loop is latency sensitive.
     // The predicate zeroes x (one select) instead of guarding the six additions: the compiler turned those into a divergent
     // branch per distance (BSSY / BRA / BSYNC: 11 % of the kernel's instructions, ncu) - and a NaN of the self pair never enters.
+    // x^5 .. x^8 are leaves of the tree, so their products fuse with the accumulation: 3 DMUL + 2 DADD + 4 DFMA per distance.
     x = ok ? x : 0.0;
     const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
-    const double pw[PTMC_PSUM_K] = {x3, x4, x2 * x3, x3 * x3, x3 * x4, x4 * x4};
-#pragma unroll
-    for (int k = 0; k < PTMC_PSUM_K; ++k) s[k] = ADD ? s[k] + pw[k] : s[k] - pw[k];
+    const double m2 = ADD ? x2 : -x2, m3 = ADD ? x3 : -x3, m4 = ADD ? x4 : -x4;
+    s[0] += m3;
+    s[1] += m4;
+    s[2] = fma(m2, x3, s[2]);
+    s[3] = fma(m3, x3, s[3]);
+    s[4] = fma(m3, x4, s[4]);
+    s[5] = fma(m4, x4, s[5]);
+    static_assert(PTMC_PSUM_K == 6, "psum_acc is written for six coefficients");
 }
 // sum_k c_k s_k
 __device__ __forceinline__ double psum_energy(const DevParams& P, const double (&s)[PTMC_PSUM_K]) {
