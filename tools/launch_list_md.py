@@ -18,7 +18,7 @@ t,tot=table(agg)
 sw=sum(v[1] for k,v in agg.items() if 'sweep_kernel' in k or 'runner_moves' in k)
 open('/root/repo/profiles/r02_launches_bench.md','w').write("\n".join(["# Launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (all five BASELINE configs)\n",
 "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (profiles/r02_launches_bench.csv; first 400 launches; kernels serialised and cold-cache under the profiler: shares, not absolute times).\n"]+t+
-["\nThe sweep kernels (`sweep_kernel*`, `runner_moves_kernel`) are %.1f %% of the GPU time of the command; every kernel in the list is this repository's except torch's `fill` (the L2 flush) and `reduce` (one histogram total).  C2 runs `sweep_kernel_g4s<1, 0, 14, 6, 1, 0>` (4 lanes per replica, 14 unrolled pair iterations), C1 `sweep_kernel_g2<1, 0, 6, 6, 1, 1>` (2 lanes, rotated order), C3 `sweep_kernel_eam<8, 0, 7, 1>`, C4 `sweep_kernel<32, 1, 2, 0, 7, 6, 0, 0>`, C5 `runner_moves_kernel`."%(100*sw/tot)])+"\n")
+["\nThe sweep kernels (`sweep_kernel*`, `runner_moves_kernel`) are %.1f %% of the GPU time of the command; every kernel in the list is this repository's except torch's `fill` (the L2 flush) and `reduce` (one histogram total).  C2 runs `sweep_kernel_g4s<1, 0, 14, 6, 1, 0>` (4 lanes per replica, 14 unrolled pair iterations), C1 `sweep_kernel_g2<1, 0, 6, 6, 1, 1>` (2 lanes, rotated order), C3 `sweep_kernel_eam<8, 0, 7, 1>`, C4 `sweep_kernel_p16<2, 14>` (16 lanes, power sums), C5 `runner_moves_kernel`."%(100*sw/tot)])+"\n")
 agg,seq=load('/root/repo/gpurun_out/r02_launches_bench_c2.csv')
 t,tot=table(agg)
 hk=[k for k in agg if 'sweep_kernel' in k]
