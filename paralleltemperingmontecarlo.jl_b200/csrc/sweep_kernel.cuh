@@ -591,7 +591,9 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             double tp = pn - po, tr = rn - ro;          // exactly 0 when !valid
                             nphi = PHI[j] + tp; nrho = RHO[j] + tr;
                             sphi += tp; srho += tr;
-                            se += valid ? fma(-P.eam_ecam, sqrt_pos(nrho), P.eam_ean * nphi) : 0.0;
+                            // masked by a 0 / 1 factor rather than a select of the term: the compiler guarded the square root with a divergent
+                            // branch per pair iteration (BSSY / BRA / BSYNC, reconvergence in 46 % of the iterations: ncu, profiles/r02_c3_eam.md)
+                            se = fma(valid ? 1.0 : 0.0, fma(-P.eam_ecam, sqrt_pos(nrho), P.eam_ean * nphi), se);
                         };
                         if (EAM_REG) {
 #pragma unroll
