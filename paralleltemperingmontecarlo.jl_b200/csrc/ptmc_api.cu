@@ -456,11 +456,18 @@ extern "C" PTMC_API int ptmc_create(const ptmc_config* c, ptmc_handle** out) {
     if (h->runner) { int rr = h->runner2 ? build_runner2(h, c->runner2, net_host) : build_runner(h, c->runner, net_host); if (rr) return bail(rr); }
     // periodic NPT with uniform volume moves: tie table instead of the N x N matrix (n_atoms <= 256: partner indices are bytes)
     P.use_ties = (!sphere && npt && !P.separated && c->n_atoms <= 256) ? 1 : 0;
+    {
+        // production free-space ELJEven{6} ladders on 4 lanes with an even number of atoms per lane: blocked atom ownership + LDS.128
+        // (BLK in sweep_body) wants the configuration buffers 8 doubles (mod 16) apart
+        const int niter = P.n_pad / G;
+        const bool rot_kernel = (c->n_atoms - 1) % G == 0 && (c->n_traj * G) % 32 == 0 && niter >= 2;
+        P.cfg_mod = (G == 4 && sphere && c->pot_kind == PTMC_POT_ELJ_EVEN && c->n_coeff == 6 && niter % 2 == 0 && !rot_kernel) ? 8 : -1;
+    }
     for (int dbg = 0; dbg < 2; ++dbg) {
         // the production ROT kernels (free-space ELJEven / ELJPotentialB, (N - 1) a multiple of G) keep every coordinate array twice: 2 N slots per array
         const bool rot2 = !dbg && sphere && (c->pot_kind == PTMC_POT_ELJ_EVEN || c->pot_kind == PTMC_POT_ELJ_B) && (c->n_atoms - 1) % G == 0;
         h->smem_k[dbg] = smem_layout(c->n_traj, rot2 ? std::max(P.n_pad, 2 * c->n_atoms) : P.n_pad, c->pot_kind, h->threads / 32, !sphere,
-                                     !eam_unrolled(P.n_pad / G, dbg != 0), !P.use_ties, G).bytes;
+                                     !eam_unrolled(P.n_pad / G, dbg != 0), !P.use_ties, G, P.cfg_mod).bytes;
     }
     h->smem = h->runner2 ? runner2_smem_bytes(c->n_atoms, h->R2) : h->runner ? runner_smem_bytes(c->n_atoms, h->R) : std::max(h->smem_k[0], h->smem_k[1]);
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return bail(fail(h, PTMC_ERR_ARG, "ladder needs %zu B of shared memory, device offers %zu", h->smem, (size_t)prop.sharedMemPerBlockOptin));

@@ -73,6 +73,7 @@ struct DevParams {
     // (|d2 / r_cut - 1| < PTMC_TIE_REL, exact distance2 arithmetic) are kept per configuration and per atom with their frozen
     // values; every other pair is recomputed from the positions (its decision cannot differ: it is >= 1e-7 away from the cut-off,
     // rounding moves it by 1e-16 per volume move).  A configuration without such pairs starts thawed.
+    int cfg_mod;        // residue (mod 16 doubles) of the stride between configuration buffers in shared memory, -1: the lane count (smem_layout)
     int use_ties;
     int* tie_cnt;             // [L][T][N]
     unsigned char* tie_idx;   // [L][T][N][PTMC_TIE_K]

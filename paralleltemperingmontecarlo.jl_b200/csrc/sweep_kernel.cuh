@@ -49,7 +49,8 @@ struct SmemLayout {
 #define PTMC_EAM_UNROLL 1
 #endif
 __host__ __device__ constexpr bool eam_unrolled(int niter, bool dbg) { return PTMC_EAM_UNROLL && !dbg && niter >= 1 && niter <= PTMC_EAM_MAX_NITER; }
-__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch, bool newvec, int lanes) {
+__host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot_kind, int n_warps, bool pbc, bool eam_scratch, bool newvec, int lanes,
+                                                  int cfg_mod = -1) {
     SmemLayout s;
     const bool dirp = pot_kind == PTMC_POT_ELJ_B || pot_kind == PTMC_POT_LUT;
     // x,y,z (+ phi,rho[,new_phi,new_rho] | + new_dist2_vec where the N x N matrix is kept: periodic without the tie table)
@@ -58,7 +59,10 @@ __host__ __device__ inline SmemLayout smem_layout(int n_traj, int n_pad, int pot
     // The 32 / G replicas of a warp read the same atom slots of DIFFERENT configuration buffers: a buffer stride of G doubles (mod 16)
     // lets their 8 G-byte runs tile the 32 banks instead of landing on one another (G = 4: 168 doubles = 8 (mod 16) is a 2-way conflict
     // on top of the two wavefronts a 256-byte request needs anyway)
-    if (lanes <= 8) while ((s.cfg_stride & 15) != (lanes & 15)) s.cfg_stride += 1;
+    // (cfg_mod: the residue the host asks for instead - 8 for the kernels whose lanes own a BLOCK of consecutive atoms and read them
+    // two at a time with LDS.128: lanes 112 bytes apart, the second replica of a quarter warp half the banks further)
+    const int mod = cfg_mod >= 0 ? cfg_mod : lanes;
+    if (lanes <= 8) while ((s.cfg_stride & 15) != (mod & 15)) s.cfg_stride += 1;
     s.off_scal = n_traj * s.cfg_stride;
     int off = s.off_scal + 4 * n_traj;
     s.off_exc = off; off += 2 * n_traj;
@@ -179,6 +183,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     // ROT (free space, (N - 1) a multiple of G): lane g visits the OTHER atoms i+1+g, i+1+g+G, ... (mod N), so the row takes
     // (N - 1) / G iterations instead of ceil(N / G) (Ne13 on 4 lanes: 3 instead of 4) and needs neither parking nor selects
     constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN && !ROT;   // mask by parking atoms far away instead of per-pair selects
+    constexpr bool BLK = PARK && G == 4 && !DBG && NITER > 0 && NITER % 2 == 0;   // blocked atom ownership, LDS.128 (see the pair loop)
     // ROT kernels: N = NITER G + 1 is a compile-time constant, and every coordinate array is stored twice in a row (atoms 0 .. N-1,
     // then 0 .. N-2 again), so that the rotated walk i+1+g, i+1+g+G, ... needs no wrap-around: all loads of a row are immediate
     // offsets from one address (the index arithmetic was 6 integer instructions per pair iteration)
@@ -197,7 +202,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     // ... and with it, for ELJPotentialEven{6}: power sums instead of the O(N^2) trial energy of a volume move
     constexpr bool PSUM = PBC && POT == PTMC_POT_ELJ_EVEN && NC == PTMC_PSUM_K;
     const bool psum = PSUM && ties;
-    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG, !ties, G);
+    const SmemLayout lay = smem_layout(T, NP, POT, (int)(blockDim.x >> 5), PBC, !EAM_REG, !ties, G, P.cfg_mod);
     double* scal = sm + lay.off_scal;
     i64* exc_cnt = reinterpret_cast<i64*>(sm + lay.off_exc);
     double* hams = sm + lay.off_ham;
@@ -561,7 +566,25 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                     accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                 }
                             };
-                            if (NITER) {
+                            if (BLK) {
+                                // lane g owns the block of atoms g NITER .. g NITER + NITER - 1 and reads them two at a time (LDS.128):
+                                // 1.5 instead of 3 shared-memory loads per pair (any split of the row over the lanes gives the same sum set)
+                                const double* Xb = X + g * NITER;
+#pragma unroll
+                                for (int k = 0; k < NITER; k += 2) {
+                                    const double2 xx = *reinterpret_cast<const double2*>(Xb + k);
+                                    const double2 yy = *reinterpret_cast<const double2*>(Xb + NP + k);
+                                    const double2 zz = *reinterpret_cast<const double2*>(Xb + 2 * NP + k);
+                                    {
+                                        const double ax = tx - xx.x, ay = ty - yy.x, az = tz - zz.x, bx_ = xi - xx.x, by_ = yi - yy.x, bz_ = zi - zz.x;
+                                        elj_even_pair_acc<NC>(P, fma(az, az, fma(ay, ay, ax * ax)), fma(bz_, bz_, fma(by_, by_, bx_ * bx_)), accn, acco);
+                                    }
+                                    {
+                                        const double ax = tx - xx.y, ay = ty - yy.y, az = tz - zz.y, bx_ = xi - xx.y, by_ = yi - yy.y, bz_ = zi - zz.y;
+                                        elj_even_pair_acc<NC>(P, fma(az, az, fma(ay, ay, ax * ax)), fma(bz_, bz_, fma(by_, by_, bx_ * bx_)), accn, acco);
+                                    }
+                                }
+                            } else if (NITER) {
 #pragma unroll
                                 for (int k = 0; k < NITER; ++k) pair_term(k);
                             } else {
