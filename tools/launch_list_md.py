@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""profiles/r02_launches_bench*.md from the ncu launch lists (gpurun_out/r02_launches_bench*.csv: `ncu --metrics gpu__time_duration.sum
+--clock-control none -c 400 --csv --log-file ... python bench.py ...`): time and share per kernel, share of the sweep kernel in a timed step."""
 import csv,collections,sys
 def load(path):
     rows=list(csv.reader(open(path)))
