@@ -848,7 +848,7 @@ def test_reference_script_decks_cu38_and_pbc32():
     assert sg["counters"][:, :, abi.C_VOL_TOT].sum() > 0
 
 
-@pytest.mark.parametrize("bc_cls,lanes", [(P.RhombicBC, 0), (P.CubicBC, 16), (P.RhombicBC, 32)])
+@pytest.mark.parametrize("bc_cls,lanes", [(P.RhombicBC, 0), (P.CubicBC, 16), (P.RhombicBC, 32), (P.RectangularBC, 0)])
 def test_uniform_volume_moves_from_power_sums(bc_cls, lanes):
     # periodic NPT, ELJPotentialEven{6}, production streams: the kernels take the trial energy of volume_change_uniform
     # (src/MCMoves.jl:277-287, dimer_energy_config on dist2_mat * scale^2: src/MCRun.jl:76-85) from six power sums that the atom moves
