@@ -184,6 +184,7 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
     // (N - 1) / G iterations instead of ceil(N / G) (Ne13 on 4 lanes: 3 instead of 4) and needs neither parking nor selects
     constexpr bool PARK = !PBC && POT == PTMC_POT_ELJ_EVEN && !ROT;   // mask by parking atoms far away instead of per-pair selects
     constexpr bool BLK = PARK && G == 4 && !DBG && NITER > 0 && NITER % 2 == 0;   // blocked atom ownership, LDS.128 (see the pair loop)
+    constexpr bool PBLK = PBC && POT == PTMC_POT_ELJ_EVEN && G == 16 && !DBG && NITER == 14;   // the same for the pbc216 class (sweep_kernel_p16)
     // ROT kernels: N = NITER G + 1 is a compile-time constant, and every coordinate array is stored twice in a row (atoms 0 .. N-1,
     // then 0 .. N-2 again), so that the rotated walk i+1+g, i+1+g+G, ... needs no wrap-around: all loads of a row are immediate
     // offsets from one address (the index arithmetic was 6 integer instructions per pair iteration)
@@ -438,10 +439,8 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                             if (thawed || ties) {
                                 // thawed: both rows from the positions in shared memory, pair loop unrolled like the free-space one
                                 const double* Xg = X + g;
-                                auto pbc_term = [&](int k, auto ps_tag) {
+                                auto pbc_pair = [&](int j, double xj, double yj, double zj, auto ps_tag) {
                                     constexpr bool PS = decltype(ps_tag)::value;
-                                    const int j = g + k * G;
-                                    const double xj = Xg[k * G], yj = Xg[NP + k * G], zj = Xg[2 * NP + k * G];
                                     double vn0 = 0, vn1 = 0, vn2 = 0, vo0 = 0, vo1 = 0, vo2 = 0;
                                     const double d2n = DIRP ? dist2_pbc_vec<rhombic>(bx, tx, ty, tz, xj, yj, zj, vn0, vn1, vn2)
                                                             : dist2_pbc<rhombic>(bx, tx, ty, tz, xj, yj, zj);
@@ -477,8 +476,21 @@ __device__ __forceinline__ void sweep_body(const DevParams& P, const i64 first_i
                                         accn += valid ? en_j : 0.0; acco += valid ? eo_j : 0.0;
                                     }
                                 };
+                                auto pbc_term = [&](int k, auto ps_tag) { pbc_pair(g + k * G, Xg[k * G], Xg[NP + k * G], Xg[2 * NP + k * G], ps_tag); };
                                 auto pbc_row = [&](auto ps_tag) {
-                                    if (NITER) {
+                                    if (PBLK) {
+                                        // 16 lanes, 14 atoms per lane: lane g owns the block of atoms 14 g .. 14 g + 13 and reads them two at a
+                                        // time (LDS.128; the 8 lanes of a quarter warp, 112 bytes apart, cover all banks)
+                                        const double* Xb = X + g * NITER;
+#pragma unroll
+                                        for (int k = 0; k < NITER; k += 2) {
+                                            const double2 xx = *reinterpret_cast<const double2*>(Xb + k);
+                                            const double2 yy = *reinterpret_cast<const double2*>(Xb + NP + k);
+                                            const double2 zz = *reinterpret_cast<const double2*>(Xb + 2 * NP + k);
+                                            pbc_pair(g * NITER + k, xx.x, yy.x, zz.x, ps_tag);
+                                            pbc_pair(g * NITER + k + 1, xx.y, yy.y, zz.y, ps_tag);
+                                        }
+                                    } else if (NITER) {
 #pragma unroll
                                         for (int k = 0; k < NITER; ++k) pbc_term(k, ps_tag);
                                     } else {
