@@ -24,8 +24,12 @@ typedef long long i64;
 #ifndef PTMC_EAM_KSTRIDE
 #define PTMC_EAM_KSTRIDE 6       // doubles per mantissa entry {1/m_k, (1/m_k)^(n/2), (1/m_k)^(m/2), pad}: 48 B spreads LDS.128 over all banks
 #endif
+// Horner (0) or Estrin (1) form of the two degree-6 series of eam_invrexp.  Estrin is three levels shallower and won in round 1; every one
+// of its inner FMAs has two coefficient operands, though, so half of the twelve coefficients must sit in registers (or be re-read: ncu
+// counted 6 LDC per pair iteration at the 128-register cap), whereas Horner takes them all as constant-bank operands.  Since the
+// divergent branch around the square root went, Horner is ahead: 54.9 -> 53.3 ms per C3 step (profiles/r02_experiments.md).
 #ifndef PTMC_EAM_ESTRIN
-#define PTMC_EAM_ESTRIN 1
+#define PTMC_EAM_ESTRIN 0
 #endif
 #define PTMC_EAM_KTAB_DOUBLES (PTMC_EAM_K * PTMC_EAM_KSTRIDE)
 #define PTMC_EAM_ETAB_DOUBLES (2048 * 2)  // every biased binary exponent of r2
@@ -395,7 +399,7 @@ __device__ __forceinline__ void eam_invrexp(const DevParams& P, const double* kt
     const double2 ee = __ldg(reinterpret_cast<const double2*>(etab) + eb);
     const double t = fma(m, a.x, -1.0);
 #if PTMC_EAM_ESTRIN
-    // Estrin: 1 + c1 t + t2 ((c2 + c3 t) + t2 ((c4 + c5 t) + t2 c6)): depth 4 instead of 7 (the kernel is latency bound)
+    // Estrin: 1 + c1 t + t2 ((c2 + c3 t) + t2 ((c4 + c5 t) + t2 c6)): depth 4 instead of 7
     const double t2 = t * t;
     double pn = fma(P.eam_cn[5], t2, fma(P.eam_cn[4], t, P.eam_cn[3])), pm = fma(P.eam_cm[5], t2, fma(P.eam_cm[4], t, P.eam_cm[3]));
     pn = fma(pn, t2, fma(P.eam_cn[2], t, P.eam_cn[1])); pm = fma(pm, t2, fma(P.eam_cm[2], t, P.eam_cm[1]));
